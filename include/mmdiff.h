@@ -1,0 +1,148 @@
+/* libmmdiff — C ABI of the B200-native MM-Diffusion denoising hot path.
+ *
+ * The reference (researchmm/MM-Diffusion) has no FFI of its own: its boundary is the Python
+ * API.  This header is the C-ABI the Python shim (mm_diffusion_b200/) binds
+ * with ctypes; every entry point names the reference interface it stands in for
+ * (paths relative to the reference repo).  Conventions: plain pointers and sizes only, every
+ * call returns 0 on success or a negative MMD_E* code (message via mmd_last_error()), the
+ * caller owns every buffer, device pointers are CUDA device memory of the current device,
+ * `stream` is a cudaStream_t passed as void*.  Handles are not thread-safe; distinct handles are.
+ * There is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef MMDIFF_H_
+#define MMDIFF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMD_OK 0
+#define MMD_EINVAL (-1)   /* bad argument / unsupported configuration */
+#define MMD_ECUDA (-2)    /* CUDA runtime or driver error */
+#define MMD_ESTATE (-3)   /* call order violated (e.g. forward before weights are complete) */
+#define MMD_ENOTFOUND (-4)
+
+#define MMD_MAX_LEVELS 8
+
+/* Mirror of the constructor arguments of MultimodalUNet
+ * (mm_diffusion/multimodal_unet.py:737-764) after create_model's string parsing
+ * (mm_diffusion/multimodal_script_util.py:156-201). */
+typedef struct MmdConfig {
+    int video_f, video_c, video_h, video_w; /* video_size [F,C,H,W] */
+    int audio_c, audio_l;                   /* audio_size [C,L] */
+    int model_channels;
+    int video_out_channels, audio_out_channels;
+    int num_res_blocks;
+    int n_levels;
+    int channel_mult[MMD_MAX_LEVELS];
+    int num_heads;          /* heads of the in-ResBlock self-attention (always used, :410-419) */
+    int num_head_channels;  /* cross-attention head width, or -1 -> num_heads (:591-598) */
+    int n_cross;
+    int cross_attention_resolutions[MMD_MAX_LEVELS];
+    int cross_attention_windows[MMD_MAX_LEVELS];
+    int cross_attention_shift; /* bool */
+    int n_video_attn;
+    int video_attention_resolutions[MMD_MAX_LEVELS];
+    int n_audio_attn;
+    int audio_attention_resolutions[MMD_MAX_LEVELS];
+    int max_batch;
+} MmdConfig;
+
+typedef struct MmdModel MmdModel;
+
+const char* mmd_last_error(void);
+const char* mmd_version(void);
+
+/* ---- model lifecycle: stands in for MultimodalUNet.__init__ / load_state_dict
+ *      (multimodal_unet.py:737-1012, :1033-1054; key schema SURVEY.md App. F) ---- */
+int mmd_model_create(const MmdConfig* cfg, MmdModel** out);
+int mmd_model_destroy(MmdModel* m);
+/* Parameter inventory in the reference's registration order. */
+int mmd_model_num_params(const MmdModel* m);
+int mmd_model_param_info(const MmdModel* m, int index, const char** name, int* ndim, int64_t shape[5]);
+/* Upload one parameter (fp32, contiguous, device pointer, reference layout [Cout,Cin,k...]).
+ * The library repacks into its own fp16 K-major layout; the caller keeps ownership of `data`. */
+int mmd_model_set_param(MmdModel* m, const char* name, const float* data, int64_t numel, void* stream);
+/* Number of cross-attention blocks that draw a random window shift per forward
+ * (CrossAttentionBlock.attention_index, multimodal_unet.py:619-622), in execution order,
+ * and the inclusive upper bound F - window of each draw. */
+int mmd_model_num_shifts(const MmdModel* m);
+int mmd_model_shift_bound(const MmdModel* m, int index);
+/* Device bytes the model needs for a batch of `batch` samples (activations + scratch). */
+size_t mmd_model_workspace_bytes(const MmdModel* m, int batch);
+int mmd_model_num_launches(const MmdModel* m, int batch);
+
+/* ---- MultimodalUNet.forward (multimodal_unet.py:1058-1101) ----
+ * video_in  [B,F,C,H,W] fp32, audio_in [B,C,L] fp32, timesteps [B] fp32 (all device);
+ * shifts: host array of mmd_model_num_shifts() ints (the values random.randint would have returned);
+ * video_out [B,F,Cout,H,W] fp32, audio_out [B,Cout,L] fp32 (device). */
+int mmd_model_forward(MmdModel* m, int batch, const float* video_in, const float* audio_in, const float* timesteps,
+                      const int32_t* shifts, float* video_out, float* audio_out, void* stream);
+
+/* ---- sampler tail: GaussianDiffusion.p_sample after the model call
+ *      (multimodal_gaussian_diffusion.py:292-350, :453-470): per element
+ *      x0 = clip(a*x - b*eps); mean = c1*x0 + c2*x; sample = mean + nz*sigma*z.
+ *      coef: device [B][6] fp32 = {a,b,c1,c2,sigma,nz}; pred_xstart may be NULL. ---- */
+int mmd_p_sample_tail(const float* x, const float* eps, const float* noise, const float* coef, int batch,
+                      int64_t per_sample, int clip_denoised, float* sample, float* pred_xstart, void* stream);
+/* GaussianDiffusion.q_sample (multimodal_gaussian_diffusion.py:187-205); coef device [B][2]. */
+int mmd_q_sample(const float* x_start, const float* noise, const float* coef, int batch, int64_t per_sample, float* out,
+                 void* stream);
+
+/* ---- operator-level entry points (used by the parity tests; same kernels the model plan launches) ---- */
+
+/* GroupNorm32 (+SiLU, +FiLM) on channels-last fp16: x [ns*rows, c1(+c2)] -> y.  nn.py:16-33. */
+int mmd_op_group_norm(const void* x1, int c1, const void* x2, int c2, int ns, int rows, const float* gamma,
+                      const float* beta, const float* film, int film_ld, int ns_per_batch, int silu, void* y,
+                      void* stream);
+int mmd_op_group_norm_temporal(const void* x, void* y, const float* gamma, const float* beta, int B, int F, int P, int C,
+                               void* stream);
+/* mode 0 video avg-pool(1,2,2), 1 audio avg-pool(4), 2 video nearest x2, 3 audio nearest x4. */
+int mmd_op_resample(const void* x, void* y, int mode, int n, int h, int w, int c, void* stream);
+
+/* Implicit-GEMM convolution (VideoConv / AudioConv, multimodal_unet.py:68-131) on channels-last fp16.
+ * geometry: rank-1 token coordinates (innermost first) with extents dims[] and box[] (product 128);
+ * taps: n_taps x 3 coordinate deltas; sources are concatenated along channels.
+ * weight: fp32 [n][c_total][n_taps] (reference layout, flattened kernel dims), bias fp32 [n].
+ * out: fp16 [tokens][n] (out_f32 == NULL) or fp32 scatter with strides (heads). */
+typedef struct MmdConvDesc {
+    int rank;          /* 2..5 including the channel coordinate */
+    int64_t dims[4];
+    int box[4];
+    int n_src;
+    const void* src[4];
+    int src_channels[4];
+    int n_taps;
+    int taps[27][3];
+    const float* weight;
+    const float* bias;
+    int n;
+    void* out;
+    float* out_f32;
+    int64_t ostride[4];
+    int64_t ostride_c;
+} MmdConvDesc;
+int mmd_op_conv(const MmdConvDesc* d, void* stream);
+
+/* Attention core.  q/k/v are column ranges of row-major fp16 matrices.
+ * Query block i of sample b attends key blocks (i+shift+j) mod n_blocks, j<win
+ * (QKVAttention.forward multimodal_unet.py:507-564; SingleModalQKVAttention :221-240 with win=1, shift=0). */
+typedef struct MmdAttnDesc {
+    const void* q; int q_ld; int q_col0; int64_t q_rows;
+    const void* k; int k_ld; int k_col0; int64_t k_rows;
+    const void* v; int v_ld; int v_col0;
+    void* out; int out_ld;
+    int batch, heads, head_dim;
+    int n_blocks, q_blk, k_blk, win, shift;
+} MmdAttnDesc;
+int mmd_op_attention(const MmdAttnDesc* d, void* stream);
+/* 16-token temporal attention: qkv [B,F,P,3C] -> out [B,F,P,C]. */
+int mmd_op_temporal_attention(const void* qkv, void* out, int B, int F, int P, int C, int heads, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMDIFF_H_ */

@@ -1,0 +1,323 @@
+// Flash-style attention core on tcgen05/TMEM for sm_100a.
+//
+// Covers (reference: mm_diffusion/multimodal_unet.py)
+//   * SingleModalQKVAttention.forward :221-240  (spatial video self-attention, audio self-attention)
+//   * QKVAttention.forward            :507-564  with CrossAttentionBlock.attention_index :614-647
+//     (Random-Shift cross-modal attention: query block i attends the key blocks
+//      (i + shift + j) mod n_blocks, j < win)
+// softmax(q k^T / sqrt(d)) v with fp32 logits/softmax, fp16 operands.
+//
+// One CTA = one 128-row query tile of one (sample, block, head).  Warp roles:
+//   warps 0-3  softmax + output accumulation (thread = query row)
+//   warp  4    TMA producer (Q once, K/V tiles double buffered)
+//   warp  5    tcgen05.mma issuer: S = Q K^T into TMEM (double buffered), O_t = P V into TMEM
+// The key window of the cross-modal case is a contiguous token range modulo the
+// per-sample key count, i.e. at most two contiguous segments, walked in 128-key tiles.
+#pragma once
+#include "common.cuh"
+
+namespace mmd {
+
+constexpr int ATT_THREADS = 192;
+constexpr int ATT_BQ = 128;
+constexpr int ATT_BKV = 128;
+
+struct alignas(64) AttnParams {
+    CUtensorMap q_map, k_map, v_map;  // 2-D views [rows][cols], box (64 cols, 128 rows), SWIZZLE_128B
+    act_t* out;                       // [q rows][out_ld]; head h writes columns [h*d, (h+1)*d)
+    int out_ld;
+    int B, heads;
+    int q_col0, k_col0, v_col0;       // column of head 0 inside each view
+    int n_blocks;                     // query blocks (frames / audio segments) per sample
+    int q_blk, q_per_batch;           // query rows per block / per sample
+    int k_blk, k_per_batch;           // key rows per block / per sample (wrap modulus)
+    int win;                          // window, in blocks
+    const int* shift_ptr;             // device scalar (random window shift), may be null
+    int q_tiles;                      // ceil(q_blk / 128)
+    float scale_log2;                 // d^-1/2 * log2(e)
+};
+
+struct AttnWork {
+    int q_row0, q_valid;
+    int seg_row[2], seg_len[2];  // absolute key row start and length of the <=2 contiguous key segments
+    int n_tiles;
+    int head;
+};
+
+MMD_DEVINL AttnWork attn_decode(const AttnParams& p, int idx) {
+    AttnWork w;
+    const int qt = idx % p.q_tiles; idx /= p.q_tiles;
+    w.head = idx % p.heads; idx /= p.heads;
+    const int blk = idx % p.n_blocks;
+    const int b = idx / p.n_blocks;
+    w.q_row0 = b * p.q_per_batch + blk * p.q_blk + qt * ATT_BQ;
+    w.q_valid = min(ATT_BQ, p.q_blk - qt * ATT_BQ);
+    const int shift = p.shift_ptr ? *p.shift_ptr : 0;
+    const int start = ((blk + shift) % p.n_blocks) * p.k_blk;
+    const int len = p.win * p.k_blk;
+    const int len0 = min(len, p.k_per_batch - start);
+    w.seg_row[0] = b * p.k_per_batch + start;
+    w.seg_len[0] = len0;
+    w.seg_row[1] = b * p.k_per_batch;
+    w.seg_len[1] = len - len0;
+    w.n_tiles = (len0 + ATT_BKV - 1) / ATT_BKV + (len - len0 + ATT_BKV - 1) / ATT_BKV;
+    return w;
+}
+// tile t -> (absolute key row, valid keys)
+MMD_DEVINL void attn_tile(const AttnWork& w, int t, int& row, int& valid) {
+    const int t0 = (w.seg_len[0] + ATT_BKV - 1) / ATT_BKV;
+    if (t < t0) {
+        row = w.seg_row[0] + t * ATT_BKV;
+        valid = min(ATT_BKV, w.seg_len[0] - t * ATT_BKV);
+    } else {
+        const int u = t - t0;
+        row = w.seg_row[1] + u * ATT_BKV;
+        valid = min(ATT_BKV, w.seg_len[1] - u * ATT_BKV);
+    }
+}
+
+template <int D>
+struct AttnSmem {
+    static constexpr int NCH = (D + 63) / 64;          // 64-column boxes per operand tile
+    static constexpr int TILE = NCH * ATT_BQ * 128;    // bytes of one Q/K/V tile
+    static constexpr int Q_OFF = 0;
+    static constexpr int K_OFF = TILE;
+    static constexpr int V_OFF = K_OFF + 2 * TILE;
+    static constexpr int P_OFF = V_OFF + 2 * TILE;
+    static constexpr int P_BYTES = 2 * ATT_BQ * 128;
+    static constexpr int BAR_OFF = P_OFF + P_BYTES;
+    static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+};
+
+template <int D>
+__global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_constant__ AttnParams p) {
+    using S = AttnSmem<D>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
+    uint64_t* q_full = bars;        // 1
+    uint64_t* k_full = bars + 1;    // 2
+    uint64_t* k_empty = bars + 3;   // 2
+    uint64_t* v_full = bars + 5;    // 2
+    uint64_t* v_empty = bars + 7;   // 2
+    uint64_t* s_full = bars + 9;    // 2
+    uint64_t* p_ready = bars + 11;  // 1 (128 arrivals)
+    uint64_t* o_full = bars + 12;   // 1
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const AttnWork w = attn_decode(p, blockIdx.x);
+    const int T = w.n_tiles;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&p.q_map);
+        tma_prefetch_desc(&p.k_map);
+        tma_prefetch_desc(&p.v_map);
+        mbar_init(q_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&k_full[i], 1);
+            mbar_init(&k_empty[i], 1);
+            mbar_init(&v_full[i], 1);
+            mbar_init(&v_empty[i], 1);
+            mbar_init(&s_full[i], 1);
+        }
+        mbar_init(p_ready, 128);
+        mbar_init(o_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 5) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_S = tmem_base;        // two 128-column buffers
+    const uint32_t tmem_O = tmem_base + 256;  // D columns
+
+    if (warp == 4) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            mbar_expect_tx(q_full, S::TILE);
+            for (int ch = 0; ch < S::NCH; ++ch)
+                tma_load_2d(smem + S::Q_OFF + ch * (ATT_BQ * 128), &p.q_map, q_full, p.q_col0 + w.head * D + ch * 64,
+                            w.q_row0);
+            for (int t = 0; t < T; ++t) {
+                const int st = t & 1;
+                const uint32_t ph = (t >> 1) & 1;
+                int krow, kvalid;
+                attn_tile(w, t, krow, kvalid);
+                mbar_wait(&k_empty[st], ph ^ 1);
+                mbar_expect_tx(&k_full[st], S::TILE);
+                for (int ch = 0; ch < S::NCH; ++ch)
+                    tma_load_2d(smem + S::K_OFF + st * S::TILE + ch * (ATT_BKV * 128), &p.k_map, &k_full[st],
+                                p.k_col0 + w.head * D + ch * 64, krow);
+                mbar_wait(&v_empty[st], ph ^ 1);
+                mbar_expect_tx(&v_full[st], S::TILE);
+                for (int ch = 0; ch < S::NCH; ++ch)
+                    tma_load_2d(smem + S::V_OFF + st * S::TILE + ch * (ATT_BKV * 128), &p.v_map, &v_full[st],
+                                p.v_col0 + w.head * D + ch * 64, krow);
+            }
+        }
+    } else if (warp == 5) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc_qk = umma_idesc_f16(ATT_BQ, ATT_BKV, 0, 0);
+            constexpr uint32_t idesc_pv = umma_idesc_f16(ATT_BQ, D, 0, 1);  // B (=V) is MN-major
+            const uint32_t q_addr = smem_u32(smem + S::Q_OFF);
+            const uint32_t p_addr = smem_u32(smem + S::P_OFF);
+            auto issue_qk = [&](int t) {
+                const int st = t & 1;
+                const uint32_t ph = (t >> 1) & 1;
+                mbar_wait(&k_full[st], ph);
+                tc_fence_after();
+                const uint32_t k_addr = smem_u32(smem + S::K_OFF + st * S::TILE);
+#pragma unroll
+                for (int ks = 0; ks < D / 16; ++ks) {
+                    const uint32_t off = (ks >> 2) * (ATT_BQ * 128) + (ks & 3) * 32;
+                    umma_f16_ss(tmem_S + st * 128, umma_desc_sw128(q_addr + off, 16, 1024),
+                                umma_desc_sw128(k_addr + off, 16, 1024), idesc_qk, ks != 0 ? 1u : 0u);
+                }
+                umma_commit(&k_empty[st]);
+                umma_commit(&s_full[st]);
+            };
+            mbar_wait(q_full, 0);
+            tc_fence_after();
+            issue_qk(0);
+            for (int t = 0; t < T; ++t) {
+                if (t + 1 < T) issue_qk(t + 1);
+                const int st = t & 1;
+                const uint32_t ph = (t >> 1) & 1;
+                int krow, kvalid;
+                attn_tile(w, t, krow, kvalid);
+                mbar_wait(p_ready, t & 1);
+                mbar_wait(&v_full[st], ph);
+                tc_fence_after();
+                const uint32_t v_addr = smem_u32(smem + S::V_OFF + st * S::TILE);
+                const int nks = (kvalid + 15) >> 4;
+                for (int ks = 0; ks < nks; ++ks) {
+                    const uint32_t poff = (ks >> 2) * (ATT_BQ * 128) + (ks & 3) * 32;
+                    umma_f16_ss(tmem_O, umma_desc_sw128(p_addr + poff, 16, 1024),
+                                umma_desc_sw128(v_addr + ks * 2048, ATT_BKV * 128, 1024), idesc_pv, ks != 0 ? 1u : 0u);
+                }
+                umma_commit(&v_empty[st]);
+                umma_commit(o_full);
+            }
+        }
+    } else {
+        // ===================== softmax / accumulate (thread = row) =====================
+        const int row = warp * 32 + lane;
+        const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+        float o_acc[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) o_acc[i] = 0.f;
+        float m_run = -INFINITY;  // running max of scaled logits (log2 domain)
+        float l_run = 0.f;
+        float alpha_prev = 1.f;
+        uint8_t* p_smem = smem + S::P_OFF;
+        for (int t = 0; t < T; ++t) {
+            const int st = t & 1;
+            int krow, kvalid;
+            attn_tile(w, t, krow, kvalid);
+            mbar_wait(&s_full[st], (t >> 1) & 1);
+            tc_fence_after();
+            const uint32_t s_addr = tmem_S + st * 128 + lane_base;
+            // pass 1: row max
+            float mx = -INFINITY;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                if (c * 32 >= kvalid) break;
+                uint32_t v[32];
+                tmem_ld32(s_addr + c * 32, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (c * 32 + i < kvalid) mx = fmaxf(mx, __uint_as_float(v[i]));
+            }
+            const float m_new = fmaxf(m_run, mx * p.scale_log2);
+            const float alpha = exp2f(m_run - m_new);  // first tile: exp2(-inf) = 0
+            // fold in the previous tile's PV result (also proves P / O buffers are free again)
+            if (t > 0) {
+                mbar_wait(o_full, (t - 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < D / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_O + lane_base + c * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = o_acc[c * 32 + i] * alpha_prev + __uint_as_float(v[i]);
+                }
+            }
+            // pass 2: probabilities -> smem (K-major SW128, two 64-key chunks), row sum
+            float psum = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t v[32];
+                if (c * 32 < kvalid) {
+                    tmem_ld32(s_addr + c * 32, v);
+                    tmem_ld_wait();
+                }
+                uint8_t* chunk = p_smem + (c >> 1) * (ATT_BQ * 128);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint4 pk;
+                    uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int col = c * 32 + j * 8 + 2 * k;
+                        float e0 = 0.f, e1 = 0.f;
+                        if (col < kvalid) e0 = exp2f(__uint_as_float(v[j * 8 + 2 * k]) * p.scale_log2 - m_new);
+                        if (col + 1 < kvalid) e1 = exp2f(__uint_as_float(v[j * 8 + 2 * k + 1]) * p.scale_log2 - m_new);
+                        const __half2 h = __floats2half2_rn(e0, e1);
+                        // accumulate the rounded values so the normaliser matches what the MMA sees
+                        const float2 hr = __half22float2(h);
+                        psum += hr.x + hr.y;
+                        pw[k] = *reinterpret_cast<const uint32_t*>(&h);
+                    }
+                    *reinterpret_cast<uint4*>(chunk + sw128_off(row, (c & 1) * 4 + j)) = pk;
+                }
+            }
+            l_run = l_run * alpha + psum;
+            m_run = m_new;
+            alpha_prev = alpha;
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(p_ready);
+        }
+        // last PV result
+        mbar_wait(o_full, (T - 1) & 1);
+        tc_fence_after();
+        const float inv_l = 1.f / l_run;
+        act_t* orow = p.out + static_cast<size_t>(w.q_row0 + row) * p.out_ld + w.head * D;
+#pragma unroll
+        for (int c = 0; c < D / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld32(tmem_O + lane_base + c * 32, v);
+            tmem_ld_wait();
+            if (row < w.q_valid) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint4 pk;
+                    __half2* ph2 = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int i = c * 32 + j * 8 + 2 * k;
+                        const float a0 = (o_acc[i] * alpha_prev + __uint_as_float(v[j * 8 + 2 * k])) * inv_l;
+                        const float a1 = (o_acc[i + 1] * alpha_prev + __uint_as_float(v[j * 8 + 2 * k + 1])) * inv_l;
+                        ph2[k] = __floats2half2_rn(a0, a1);
+                    }
+                    *reinterpret_cast<uint4*>(orow + c * 32 + j * 8) = pk;
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+}  // namespace mmd

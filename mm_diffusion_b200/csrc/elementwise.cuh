@@ -1,0 +1,502 @@
+// HBM-bound helper kernels of the denoising step (channels-last fp16 activations):
+// GroupNorm statistics / apply (+SiLU, +FiLM), pooling / nearest upsampling,
+// im2col of the 3- and 1-channel network inputs, timestep-embedding MLPs,
+// the 16-token temporal self-attention core and the fused p_sample tail.
+// Each kernel cites the reference lines whose arithmetic it restates.
+#pragma once
+#include "common.cuh"
+
+namespace mmd {
+
+// ---------------------------------------------------------------------------
+// GroupNorm statistics.  Reference: nn.py:16-33 (GroupNorm32: 32 groups, eps 1e-5,
+// statistics in fp32 over (C/32 channels x all positions of the domain)).
+// Input is the channel-concatenation of up to two row-major sources
+// (U-Net skip concat, multimodal_unet.py:1093-1094).  A "domain" is R consecutive
+// rows; sums go to double accumulators [NS][32][2].
+// ---------------------------------------------------------------------------
+struct GnSrc {
+    const act_t* x1; int c1; int ld1;
+    const act_t* x2; int c2; int ld2;
+};
+
+__global__ void gn_stats_kernel(GnSrc s, int R, int rows_per_block, double* __restrict__ sums) {
+    const int C = s.c1 + s.c2;
+    const int cpg = C / 32;
+    const int vpr = C / 8;  // 16-byte vectors per row
+    const int ns = blockIdx.y;
+    const int r0 = blockIdx.x * rows_per_block;
+    const int r1 = min(R, r0 + rows_per_block);
+    const int rows_per_pass = blockDim.x / vpr;
+    const int vec = threadIdx.x % vpr;
+    const int rsub = threadIdx.x / vpr;
+    __shared__ float sh[64];
+    if (threadIdx.x < 64) sh[threadIdx.x] = 0.f;
+    __syncthreads();
+    float sm[8], sq[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sm[i] = 0.f; sq[i] = 0.f; }
+    if (rsub < rows_per_pass) {
+        const int c0 = vec * 8;
+        const act_t* base;
+        int ld, cc;
+        if (c0 < s.c1) { base = s.x1; ld = s.ld1; cc = c0; } else { base = s.x2; ld = s.ld2; cc = c0 - s.c1; }
+        for (int r = r0 + rsub; r < r1; r += rows_per_pass) {
+            const uint4 raw = __ldg(reinterpret_cast<const uint4*>(base + (static_cast<size_t>(ns) * R + r) * ld + cc));
+            const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = __half22float2(h[i]);
+                sm[2 * i] += f.x; sq[2 * i] += f.x * f.x;
+                sm[2 * i + 1] += f.y; sq[2 * i + 1] += f.y * f.y;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int g = (c0 + i) / cpg;
+            atomicAdd(&sh[2 * g], sm[i]);
+            atomicAdd(&sh[2 * g + 1], sq[i]);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 64) atomicAdd(&sums[static_cast<size_t>(ns) * 64 + threadIdx.x], static_cast<double>(sh[threadIdx.x]));
+}
+
+// ---------------------------------------------------------------------------
+// GroupNorm apply: y = act( gn(x) * (1 + scale) + shift ), act = SiLU or identity.
+// Reference: nn.py:22-33; multimodal_unet.py:338-347 (in_layers: GN -> SiLU),
+// :459-470 (out_layers: GN * (1+scale) + shift -> SiLU), :284/:664 (attention norm, no SiLU).
+// film points at [B][film_ld] floats with scale at [0,C) and shift at [C,2C)
+// (th.chunk order, multimodal_unet.py:462,468).
+// ---------------------------------------------------------------------------
+__global__ void gn_apply_kernel(GnSrc s, int R, int rows_per_block, const double* __restrict__ sums,
+                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                const float* __restrict__ film, int film_ld, int ns_per_batch, int do_silu,
+                                act_t* __restrict__ y) {
+    extern __shared__ float coef[];  // [2][C]
+    const int C = s.c1 + s.c2;
+    const int cpg = C / 32;
+    const int vpr = C / 8;
+    const int ns = blockIdx.y;
+    const double inv_n = 1.0 / (static_cast<double>(R) * cpg);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / cpg;
+        const double su = sums[static_cast<size_t>(ns) * 64 + 2 * g];
+        const double ss = sums[static_cast<size_t>(ns) * 64 + 2 * g + 1];
+        const double mean = su * inv_n;
+        double var = ss * inv_n - mean * mean;
+        if (var < 0) var = 0;
+        const float rstd = static_cast<float>(1.0 / sqrt(var + 1e-5));
+        float a = rstd * gamma[c];
+        float b = beta[c] - static_cast<float>(mean) * a;
+        if (film != nullptr) {
+            const float* fb = film + static_cast<size_t>(ns / ns_per_batch) * film_ld;
+            const float sc = 1.f + fb[c];
+            a *= sc;
+            b = b * sc + fb[C + c];
+        }
+        coef[c] = a;
+        coef[C + c] = b;
+    }
+    __syncthreads();
+    const int r0 = blockIdx.x * rows_per_block;
+    const int r1 = min(R, r0 + rows_per_block);
+    const int total = (r1 - r0) * vpr;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int r = r0 + i / vpr;
+        const int c0 = (i % vpr) * 8;
+        const act_t* src = (c0 < s.c1) ? s.x1 + (static_cast<size_t>(ns) * R + r) * s.ld1 + c0
+                                       : s.x2 + (static_cast<size_t>(ns) * R + r) * s.ld2 + (c0 - s.c1);
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(src));
+        const __half2* h = reinterpret_cast<const __half2*>(&raw);
+        uint4 outv;
+        __half2* o = reinterpret_cast<__half2*>(&outv);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 f = __half22float2(h[k]);
+            float u0 = f.x * coef[c0 + 2 * k] + coef[C + c0 + 2 * k];
+            float u1 = f.y * coef[c0 + 2 * k + 1] + coef[C + c0 + 2 * k + 1];
+            if (do_silu) { u0 = silu_f(u0); u1 = silu_f(u1); }
+            o[k] = __floats2half2_rn(u0, u1);
+        }
+        *reinterpret_cast<uint4*>(y + (static_cast<size_t>(ns) * R + r) * C + c0) = outv;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// GroupNorm whose domain is one pixel across the F frames (temporal attention norm:
+// input rearranged "(b h w) c f", multimodal_unet.py:489-490 -> stats over C/32 x F).
+// x, y: [B][F][P][C].  One thread per (pixel, group).
+// ---------------------------------------------------------------------------
+__global__ void gn_temporal_kernel(const act_t* __restrict__ x, act_t* __restrict__ y, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, int B, int F, int P, int C) {
+    const int cpg = C / 32;
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long total = static_cast<long long>(B) * P * 32;
+    if (idx >= total) return;
+    const int g = static_cast<int>(idx % 32);
+    const long long bp = idx / 32;
+    const int p = static_cast<int>(bp % P);
+    const int b = static_cast<int>(bp / P);
+    const size_t fstride = static_cast<size_t>(P) * C;
+    const size_t base = (static_cast<size_t>(b) * F * P + p) * C + g * cpg;
+    float su = 0.f, ss = 0.f;
+    for (int f = 0; f < F; ++f) {
+        const __half2* row = reinterpret_cast<const __half2*>(x + base + f * fstride);
+        for (int k = 0; k < cpg / 2; ++k) {
+            const float2 v = __half22float2(row[k]);
+            su += v.x + v.y;
+            ss += v.x * v.x + v.y * v.y;
+        }
+    }
+    const float inv_n = 1.f / (F * cpg);
+    const float mean = su * inv_n;
+    const float var = fmaxf(ss * inv_n - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + 1e-5f);
+    for (int f = 0; f < F; ++f) {
+        const __half2* row = reinterpret_cast<const __half2*>(x + base + f * fstride);
+        __half2* orow = reinterpret_cast<__half2*>(y + base + f * fstride);
+        for (int k = 0; k < cpg / 2; ++k) {
+            const float2 v = __half22float2(row[k]);
+            const int c = g * cpg + 2 * k;
+            orow[k] = __floats2half2_rn((v.x - mean) * rstd * gamma[c] + beta[c],
+                                        (v.y - mean) * rstd * gamma[c + 1] + beta[c + 1]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Resampling (multimodal_unet.py:133-208): AvgPool3d (1,2,2) / AvgPool1d(4) and
+// nearest x(1,2,2) / x4, channels-last.  mode 0: video pool, 1: audio pool,
+// 2: video up, 3: audio up.  Thread = one 8-channel vector of one output token.
+// ---------------------------------------------------------------------------
+__global__ void resample_kernel(const act_t* __restrict__ x, act_t* __restrict__ y, int mode, int N, int H, int W,
+                                int C) {
+    // video: x [N][H][W][C]; audio: x [N][H(=L)][C] with W unused
+    const int vpr = C / 8;
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    long long total;
+    if (mode == 0) total = static_cast<long long>(N) * (H / 2) * (W / 2) * vpr;
+    else if (mode == 1) total = static_cast<long long>(N) * (H / 4) * vpr;
+    else if (mode == 2) total = static_cast<long long>(N) * (H * 2) * (W * 2) * vpr;
+    else total = static_cast<long long>(N) * (H * 4) * vpr;
+    if (idx >= total) return;
+    const int v = static_cast<int>(idx % vpr);
+    long long t = idx / vpr;
+    if (mode == 0 || mode == 1) {
+        const uint4* src[4];
+        if (mode == 0) {
+            const int ow = static_cast<int>(t % (W / 2)); t /= (W / 2);
+            const int oh = static_cast<int>(t % (H / 2));
+            const long long n = t / (H / 2);
+            const act_t* b0 = x + ((n * H + 2 * oh) * W + 2 * ow) * static_cast<long long>(C) + v * 8;
+            src[0] = reinterpret_cast<const uint4*>(b0);
+            src[1] = reinterpret_cast<const uint4*>(b0 + C);
+            src[2] = reinterpret_cast<const uint4*>(b0 + static_cast<long long>(W) * C);
+            src[3] = reinterpret_cast<const uint4*>(b0 + static_cast<long long>(W) * C + C);
+        } else {
+            const int ol = static_cast<int>(t % (H / 4));
+            const long long n = t / (H / 4);
+            const act_t* b0 = x + (n * H + 4 * ol) * static_cast<long long>(C) + v * 8;
+            for (int k = 0; k < 4; ++k) src[k] = reinterpret_cast<const uint4*>(b0 + static_cast<long long>(k) * C);
+        }
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint4 raw = __ldg(src[k]);
+            const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = __half22float2(h[i]);
+                acc[2 * i] += f.x;
+                acc[2 * i + 1] += f.y;
+            }
+        }
+        uint4 o;
+        __half2* oh2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) oh2[i] = __floats2half2_rn(acc[2 * i] * 0.25f, acc[2 * i + 1] * 0.25f);
+        reinterpret_cast<uint4*>(y)[idx] = o;
+    } else {
+        const act_t* b0;
+        if (mode == 2) {
+            const int ow = static_cast<int>(t % (W * 2)); t /= (W * 2);
+            const int oh = static_cast<int>(t % (H * 2));
+            const long long n = t / (H * 2);
+            b0 = x + ((n * H + oh / 2) * W + ow / 2) * static_cast<long long>(C) + v * 8;
+        } else {
+            const int ol = static_cast<int>(t % (H * 4));
+            const long long n = t / (H * 4);
+            b0 = x + (n * H + ol / 4) * static_cast<long long>(C) + v * 8;
+        }
+        reinterpret_cast<uint4*>(y)[idx] = __ldg(reinterpret_cast<const uint4*>(b0));
+    }
+}
+
+// ---------------------------------------------------------------------------
+// im2col of the raw network inputs (InitialBlock, multimodal_unet.py:680-694):
+// video fp32 [BF][3][H][W] -> A [BF*H*W][64] with k = (ky*3+kx)*3 + c, zero padded;
+// audio fp32 [B][1][L]     -> A [B*L][64]    with k = tap.
+// ---------------------------------------------------------------------------
+__global__ void im2col_video_kernel(const float* __restrict__ x, act_t* __restrict__ a, int BF, int Cin, int H, int W) {
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long total = static_cast<long long>(BF) * H * W * 8;  // 8 vectors of 8 per token
+    if (idx >= total) return;
+    const int v = static_cast<int>(idx & 7);
+    long long t = idx >> 3;
+    const int w = static_cast<int>(t % W); t /= W;
+    const int h = static_cast<int>(t % H);
+    const long long n = t / H;
+    uint4 o;
+    __half* oh = reinterpret_cast<__half*>(&o);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int k = v * 8 + i;
+        float val = 0.f;
+        if (k < 9 * Cin) {
+            const int tap = k / Cin, c = k % Cin;
+            const int yy = h + tap / 3 - 1, xx = w + tap % 3 - 1;
+            if (yy >= 0 && yy < H && xx >= 0 && xx < W) val = x[((n * Cin + c) * H + yy) * W + xx];
+        }
+        oh[i] = __float2half_rn(val);
+    }
+    reinterpret_cast<uint4*>(a)[idx] = o;
+}
+
+__global__ void im2col_audio_kernel(const float* __restrict__ x, act_t* __restrict__ a, int B, int Cin, int L) {
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long total = static_cast<long long>(B) * L * 8;
+    if (idx >= total) return;
+    const int v = static_cast<int>(idx & 7);
+    long long t = idx >> 3;
+    const int l = static_cast<int>(t % L);
+    const long long n = t / L;
+    uint4 o;
+    __half* oh = reinterpret_cast<__half*>(&o);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int k = v * 8 + i;
+        float val = 0.f;
+        if (k < 3 * Cin) {
+            const int tap = k / Cin, c = k % Cin;
+            const int ll = l + tap - 1;
+            if (ll >= 0 && ll < L) val = x[(n * Cin + c) * L + ll];
+        }
+        oh[i] = __float2half_rn(val);
+    }
+    reinterpret_cast<uint4*>(a)[idx] = o;
+}
+
+// ---------------------------------------------------------------------------
+// Timestep embedding + time_embed MLP (nn.py:192-210, multimodal_unet.py:791-795,1075)
+// emb[b] = W2 * silu(W1 * [cos(t f_i), sin(t f_i)] + b1) + b2, all fp32; then stores silu(emb)
+// because every consumer is emb_layers = Linear(SiLU(emb)) (multimodal_unet.py:366-372).
+// One block per sample, blockDim = dim (128).
+// ---------------------------------------------------------------------------
+__global__ void time_embed_kernel(const float* __restrict__ t, const float* __restrict__ w1, const float* __restrict__ b1,
+                                  const float* __restrict__ w2, const float* __restrict__ b2, int dim,
+                                  float* __restrict__ emb_out, float* __restrict__ silu_emb_out) {
+    extern __shared__ float sh[];  // [2][dim]
+    float* e0 = sh;
+    float* e1 = sh + dim;
+    const int b = blockIdx.x;
+    const int i = threadIdx.x;
+    const int half = dim / 2;
+    const float tv = t[b];
+    if (i < dim) {
+        const int j = (i < half) ? i : i - half;
+        const float freq = expf(-logf(10000.0f) * static_cast<float>(j) / static_cast<float>(half));
+        const float arg = tv * freq;
+        e0[i] = (i < half) ? cosf(arg) : sinf(arg);
+    }
+    __syncthreads();
+    if (i < dim) {
+        float acc = b1[i];
+        for (int k = 0; k < dim; ++k) acc += w1[i * dim + k] * e0[k];
+        e1[i] = silu_f(acc);
+    }
+    __syncthreads();
+    if (i < dim) {
+        float acc = b2[i];
+        for (int k = 0; k < dim; ++k) acc += w2[i * dim + k] * e1[k];
+        emb_out[b * dim + i] = acc;
+        silu_emb_out[b * dim + i] = silu_f(acc);
+    }
+}
+
+// All ResBlock emb_layers at once: out[b][j] = bias[j] + sum_k W[j][k] * silu_emb[b][k]
+// (rows of all 28 emb_layers.1 Linear layers stacked).  One warp per row j.
+__global__ void emb_layers_kernel(const float* __restrict__ silu_emb, const float* __restrict__ w,
+                                  const float* __restrict__ bias, int B, int dim, int rows, float* __restrict__ out) {
+    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (j >= rows) return;
+    for (int b = 0; b < B; ++b) {
+        float acc = 0.f;
+        for (int k = lane; k < dim; k += 32) acc += w[static_cast<size_t>(j) * dim + k] * silu_emb[b * dim + k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) out[static_cast<size_t>(b) * rows + j] = acc + bias[j];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Temporal self-attention core: sequences of F (<=16) tokens per (sample, pixel), heads
+// of width d = C/heads (SingleModalQKVAttention, multimodal_unet.py:221-240; fp32 softmax).
+// qkv: [B][F][P][3C] (q | k | v on channels, head h = channels [h*d,(h+1)*d)), out: [B][F][P][C].
+// One warp per (b, p, head); bandwidth-bound (8 FLOP/B).
+// ---------------------------------------------------------------------------
+template <int F_>
+__global__ void temporal_attn_kernel(const act_t* __restrict__ qkv, act_t* __restrict__ out, int B, int P, int C,
+                                     int heads) {
+    extern __shared__ __align__(16) uint8_t tsm[];
+    const int d = C / heads;
+    const int wpb = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long item = static_cast<long long>(blockIdx.x) * wpb + warp;
+    const long long total = static_cast<long long>(B) * P * heads;
+    // per-warp smem: q,k,v [F][d] half + P [F][F] float
+    const size_t per_warp = static_cast<size_t>(3) * F_ * d * sizeof(act_t) + F_ * F_ * sizeof(float);
+    uint8_t* mine = tsm + warp * per_warp;
+    act_t* sq = reinterpret_cast<act_t*>(mine);
+    act_t* sk = sq + F_ * d;
+    act_t* sv = sk + F_ * d;
+    float* sp = reinterpret_cast<float*>(sv + F_ * d);
+    if (item >= total) return;
+    const int h = static_cast<int>(item % heads);
+    const long long bp = item / heads;
+    const int p = static_cast<int>(bp % P);
+    const int b = static_cast<int>(bp / P);
+    const int vpr = d / 8;
+    for (int i = lane; i < 3 * F_ * vpr; i += 32) {
+        const int m = i / (F_ * vpr);
+        const int rem = i % (F_ * vpr);
+        const int f = rem / vpr, v = rem % vpr;
+        const act_t* src = qkv + ((static_cast<size_t>(b) * F_ + f) * P + p) * (3 * C) + m * C + h * d + v * 8;
+        reinterpret_cast<uint4*>(sq + m * F_ * d)[f * vpr + v] = __ldg(reinterpret_cast<const uint4*>(src));
+    }
+    __syncwarp();
+    const float scale = rsqrtf(static_cast<float>(d));
+    // scores: lane -> (i = lane % F_, j block = lane / F_)
+    constexpr int JB = 32 / F_;       // lanes per query row
+    constexpr int JPL = F_ / JB;      // keys per lane
+    const int qi = lane % F_, jb = lane / F_;
+    float sc[JPL];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int jj = 0; jj < JPL; ++jj) {
+        const int j = jb * JPL + jj;
+        float acc = 0.f;
+        const __half2* qr = reinterpret_cast<const __half2*>(sq + qi * d);
+        const __half2* kr = reinterpret_cast<const __half2*>(sk + j * d);
+        for (int c = 0; c < d / 2; ++c) {
+            const float2 a = __half22float2(qr[c]);
+            const float2 bb = __half22float2(kr[c]);
+            acc += a.x * bb.x + a.y * bb.y;
+        }
+        sc[jj] = acc * scale;
+        mx = fmaxf(mx, sc[jj]);
+    }
+#pragma unroll
+    for (int o = F_; o < 32; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < JPL; ++jj) { sc[jj] = __expf(sc[jj] - mx); sum += sc[jj]; }
+#pragma unroll
+    for (int o = F_; o < 32; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int jj = 0; jj < JPL; ++jj) sp[qi * F_ + jb * JPL + jj] = sc[jj] * inv;
+    __syncwarp();
+    // output: each lane produces 8-channel vectors of (row i, vector v)
+    for (int i = lane; i < F_ * vpr; i += 32) {
+        const int f = i / vpr, v = i % vpr;
+        float acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+        for (int j = 0; j < F_; ++j) {
+            const float pw = sp[f * F_ + j];
+            const uint4 raw = reinterpret_cast<const uint4*>(sv + j * d)[v];
+            const __half2* hv = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 vv = __half22float2(hv[k]);
+                acc[2 * k] += pw * vv.x;
+                acc[2 * k + 1] += pw * vv.y;
+            }
+        }
+        uint4 o;
+        __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) oh[k] = __floats2half2_rn(acc[2 * k], acc[2 * k + 1]);
+        *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(b) * F_ + f) * P + p) * C + h * d + v * 8) = o;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Fused p_sample tail (multimodal_gaussian_diffusion.py:345-350, 215-218, 453-470):
+//   x0 = clamp(a_t x - b_t eps, -1, 1) (clamp optional); mean = c1_t x0 + c2_t x;
+//   sample = mean + nz_t * sigma_t * z.  coef: [B][6] = {a, b, c1, c2, sigma, nonzero}.
+// ---------------------------------------------------------------------------
+__global__ void p_sample_tail_kernel(const float* __restrict__ x, const float* __restrict__ eps,
+                                     const float* __restrict__ z, const float* __restrict__ coef, long long per_sample,
+                                     long long total, int clip, float* __restrict__ sample,
+                                     float* __restrict__ pred_xstart) {
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float* c = coef + (i / per_sample) * 6;
+        const float xv = x[i];
+        float x0 = c[0] * xv - c[1] * eps[i];
+        if (clip) x0 = fminf(fmaxf(x0, -1.f), 1.f);
+        const float mean = c[2] * x0 + c[3] * xv;
+        sample[i] = mean + c[5] * c[4] * z[i];
+        if (pred_xstart) pred_xstart[i] = x0;
+    }
+}
+
+// q_sample (multimodal_gaussian_diffusion.py:187-205): y = a[b] * x0 + s[b] * noise.  coef [B][2].
+__global__ void q_sample_kernel(const float* __restrict__ x0, const float* __restrict__ noise,
+                                const float* __restrict__ coef, long long per_sample, long long total,
+                                float* __restrict__ y) {
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float* c = coef + (i / per_sample) * 2;
+        y[i] = c[0] * x0[i] + c[1] * noise[i];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Weight repacking (once per weight load): fp32 conv weight [Co][Ci][T] -> fp16 [Co][ld]
+// at column col_off with k = t*Ci + ci  (K order of conv_gemm_kernel: tap-major).
+// ---------------------------------------------------------------------------
+__global__ void pack_weight_kernel(const float* __restrict__ w, act_t* __restrict__ dst, int Co, int Ci, int T,
+                                   long long ld, long long col_off) {
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long total = static_cast<long long>(Co) * Ci * T;
+    if (idx >= total) return;
+    const int t = static_cast<int>(idx % T);
+    const long long r = idx / T;
+    const int ci = static_cast<int>(r % Ci);
+    const int co = static_cast<int>(r / Ci);
+    dst[co * ld + col_off + static_cast<long long>(t) * Ci + ci] = __float2half_rn(w[idx]);
+}
+__global__ void pack_identity_kernel(act_t* __restrict__ dst, int C, long long ld, long long col_off) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < C) dst[i * ld + col_off + i] = __float2half_rn(1.0f);
+}
+__global__ void add_vec_kernel(float* __restrict__ dst, const float* __restrict__ src, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] += src[i];
+}
+__global__ void cast_f32_to_f16_kernel(const float* __restrict__ s, act_t* __restrict__ d, long long n) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) d[i] = __float2half_rn(s[i]);
+}
+__global__ void cast_f16_to_f32_kernel(const act_t* __restrict__ s, float* __restrict__ d, long long n) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) d[i] = __half2float(s[i]);
+}
+
+}  // namespace mmd

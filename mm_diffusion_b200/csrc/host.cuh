@@ -1,0 +1,104 @@
+// Host-side plumbing shared by ops.cu / model.cu: error reporting, TMA descriptor
+// encoding, conv-GEMM / attention problem descriptions and their launchers.
+#pragma once
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mmdiff.h"
+#include "attention.cuh"
+#include "common.cuh"
+#include "elementwise.cuh"
+#include "gemm.cuh"
+
+namespace mmd {
+
+// ------------------------------------------------------------------ errors
+std::string& last_error_ref();
+int fail(int code, const char* fmt, ...);
+
+#define MMD_CUDA_OK(expr)                                                                          \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) return ::mmd::fail(MMD_ECUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+#define MMD_TRY(expr)             \
+    do {                          \
+        int _r = (expr);          \
+        if (_r != MMD_OK) return _r; \
+    } while (0)
+
+int num_sms();
+
+// --------------------------------------------------------------- TMA maps
+// dims[0] is the innermost (contiguous) extent; strides_bytes[i] is the stride of dims[i+1].
+int encode_tmap(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                const uint32_t* box);
+
+// ------------------------------------------------------------- conv-GEMM
+struct ConvGeom {
+    int rank = 2;                      // including channel coordinate
+    long long dims[4] = {1, 1, 1, 1};  // token coordinates 1..4 (innermost first)
+    int box[4] = {1, 1, 1, 1};
+    long long tokens() const { return dims[0] * dims[1] * dims[2] * dims[3]; }
+};
+// Fill box[] so that the product is exactly 128 (power-of-two greedy, last coordinate takes the rest).
+void geom_fill_box(ConvGeom& g);
+
+struct GemmProblem {
+    ConvGeom g;
+    int n_src = 0;
+    const act_t* src[GEMM_MAX_SRC] = {};
+    int src_c[GEMM_MAX_SRC] = {};
+    int n_taps = 1;
+    int taps[GEMM_MAX_TAPS][3] = {};
+    const act_t* w = nullptr;  // packed [n_pad][k_total], k = tap*c_total + c
+    const float* bias = nullptr;  // [n_pad]
+    int n = 0;       // logical output channels
+    int bn = 128;    // tile N: 128, 64 or 16
+    act_t* out = nullptr;     // [tokens][n]
+    float* out_f32 = nullptr; // bn == 16 scatter
+    long long ostride[4] = {};
+    long long ostride_c = 0;
+    long long k_total() const {
+        long long c = 0;
+        for (int i = 0; i < n_src; ++i) c += src_c[i];
+        return c * n_taps;
+    }
+    int n_pad() const { return (n + bn - 1) / bn * bn; }
+};
+int pick_bn(int n);
+int build_gemm(const GemmProblem& pr, GemmParams* out);
+int launch_gemm(const GemmParams& p, int bn, cudaStream_t st);
+int gemm_init_attrs();
+
+// ------------------------------------------------------------- attention
+struct AttnProblem {
+    const act_t* q; int q_ld; int q_col0; long long q_rows;
+    const act_t* k; int k_ld; int k_col0; long long k_rows;
+    const act_t* v; int v_ld; int v_col0;
+    act_t* out; int out_ld;
+    int B, heads, d;
+    int n_blocks, q_blk, k_blk, win;
+    const int* shift_dev;  // nullable
+};
+int build_attn(const AttnProblem& pr, AttnParams* out);
+int launch_attn(const AttnParams& p, int d, cudaStream_t st);
+
+// ------------------------------------------------------------ elementwise
+int launch_gn_stats(const GnSrc& s, int ns, int rows, double* sums, cudaStream_t st);
+int launch_gn_apply(const GnSrc& s, int ns, int rows, const double* sums, const float* gamma, const float* beta,
+                    const float* film, int film_ld, int ns_per_batch, int silu, act_t* y, cudaStream_t st);
+int launch_gn_temporal(const act_t* x, act_t* y, const float* gamma, const float* beta, int B, int F, int P, int C,
+                       cudaStream_t st);
+int launch_resample(const act_t* x, act_t* y, int mode, int n, int h, int w, int c, cudaStream_t st);
+int launch_temporal_attn(const act_t* qkv, act_t* out, int B, int F, int P, int C, int heads, cudaStream_t st);
+int launch_pack_weight(const float* w, act_t* dst, int co, int ci, int t, long long ld, long long col_off, cudaStream_t st);
+
+}  // namespace mmd

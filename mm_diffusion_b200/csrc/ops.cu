@@ -1,0 +1,441 @@
+// Host launchers + operator-level C ABI (include/mmdiff.h) for the sm_100a kernels.
+#include "host.cuh"
+
+namespace mmd {
+
+std::string& last_error_ref() {
+    static thread_local std::string s;
+    return s;
+}
+int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    last_error_ref() = buf;
+    return code;
+}
+
+int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+// --------------------------------------------------------------- TMA maps
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }
+    return fn;
+}
+
+int encode_tmap(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                const uint32_t* box) {
+    auto fn = get_encode_fn();
+    if (!fn) return fail(MMD_ECUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    cuuint64_t gdim[5];
+    cuuint64_t gstr[4];
+    cuuint32_t bdim[5];
+    cuuint32_t estr[5];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bdim[i] = box[i];
+        estr[i] = 1;
+        if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+    }
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail(MMD_EINVAL, "tensor map base not 16-byte aligned");
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,
+                    gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        std::string d;
+        for (int i = 0; i < rank; ++i) d += std::to_string(dims[i]) + "/" + std::to_string(box[i]) + " ";
+        return fail(MMD_ECUDA, "cuTensorMapEncodeTiled failed (%d) rank %d dims/box %s", static_cast<int>(r), rank, d.c_str());
+    }
+    return MMD_OK;
+}
+
+// ------------------------------------------------------------- conv-GEMM
+static int pow2_ceil(long long v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+void geom_fill_box(ConvGeom& g) {
+    int remaining = GEMM_BM;
+    const int ncoord = g.rank - 1;
+    for (int i = 0; i < 4; ++i) {
+        if (i >= ncoord) { g.box[i] = 1; continue; }
+        int b = (i == ncoord - 1) ? remaining : std::min(pow2_ceil(g.dims[i]), remaining);
+        g.box[i] = b;
+        remaining /= b;
+    }
+}
+
+int pick_bn(int n) {
+    if (n % 128 == 0) return 128;
+    if (n % 64 == 0) return 64;
+    return 16;
+}
+
+int build_gemm(const GemmProblem& pr, GemmParams* out) {
+    GemmParams& p = *out;
+    memset(&p, 0, sizeof(p));
+    const ConvGeom& g = pr.g;
+    if (g.rank < 2 || g.rank > 5) return fail(MMD_EINVAL, "conv geometry rank %d", g.rank);
+    if (static_cast<long long>(g.box[0]) * g.box[1] * g.box[2] * g.box[3] != GEMM_BM)
+        return fail(MMD_EINVAL, "conv box product must be %d", GEMM_BM);
+    if (pr.n_src < 1 || pr.n_src > GEMM_MAX_SRC || pr.n_taps < 1 || pr.n_taps > GEMM_MAX_TAPS)
+        return fail(MMD_EINVAL, "conv sources/taps out of range");
+    p.n_src = pr.n_src;
+    p.rank = g.rank;
+    p.n_taps = pr.n_taps;
+    long long m_tiles = 1;
+    for (int i = 0; i < 4; ++i) {
+        p.box[i] = g.box[i];
+        p.ntile[i] = static_cast<int>((g.dims[i] + g.box[i] - 1) / g.box[i]);
+        p.dims[i] = static_cast<int>(g.dims[i]);
+        m_tiles *= p.ntile[i];
+    }
+    for (int t = 0; t < pr.n_taps; ++t)
+        for (int j = 0; j < 3; ++j) p.tap[t][j] = pr.taps[t][j];
+    uint64_t dims[5], str[4];
+    uint32_t box[5];
+    for (int s = 0; s < pr.n_src; ++s) {
+        if (pr.src_c[s] % GEMM_BK != 0) return fail(MMD_EINVAL, "conv source channels %d not a multiple of 64", pr.src_c[s]);
+        p.src_chunks[s] = pr.src_c[s] / GEMM_BK;
+        dims[0] = pr.src_c[s];
+        box[0] = GEMM_BK;
+        uint64_t pitch = static_cast<uint64_t>(pr.src_c[s]) * sizeof(act_t);
+        for (int i = 1; i < g.rank; ++i) {
+            dims[i] = g.dims[i - 1];
+            box[i] = g.box[i - 1];
+            str[i - 1] = pitch;
+            pitch *= g.dims[i - 1];
+        }
+        MMD_TRY(encode_tmap(&p.a_map[s], pr.src[s], g.rank, dims, str, box));
+    }
+    const int bn = pr.bn;
+    const long long kt = pr.k_total();
+    dims[0] = kt; dims[1] = pr.n_pad();
+    str[0] = kt * sizeof(act_t);
+    box[0] = GEMM_BK; box[1] = bn;
+    MMD_TRY(encode_tmap(&p.b_map, pr.w, 2, dims, str, box));
+    p.m_tiles = static_cast<int>(m_tiles);
+    p.n_tiles = pr.n_pad() / bn;
+    p.bias = pr.bias;
+    if (bn >= 64) {
+        if (pr.n % 64 != 0 || !pr.out) return fail(MMD_EINVAL, "fp16 conv output needs n %% 64 == 0");
+        p.out_mode = 0;
+        dims[0] = pr.n;
+        box[0] = 64;
+        uint64_t pitch = static_cast<uint64_t>(pr.n) * sizeof(act_t);
+        for (int i = 1; i < g.rank; ++i) {
+            dims[i] = g.dims[i - 1];
+            box[i] = g.box[i - 1];
+            str[i - 1] = pitch;
+            pitch *= g.dims[i - 1];
+        }
+        MMD_TRY(encode_tmap(&p.o_map, pr.out, g.rank, dims, str, box));
+    } else {
+        if (!pr.out_f32 || pr.n > 16) return fail(MMD_EINVAL, "narrow conv output needs out_f32 and n <= 16");
+        p.out_mode = 1;
+        p.out_f32 = pr.out_f32;
+        for (int i = 0; i < 4; ++i) p.ostride[i] = pr.ostride[i];
+        p.ostride_c = pr.ostride_c;
+        p.n_valid = pr.n;
+    }
+    return MMD_OK;
+}
+
+int gemm_init_attrs() {
+    static bool done = false;
+    if (done) return MMD_OK;
+    MMD_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<128>::TOTAL));
+    MMD_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<64>::TOTAL));
+    MMD_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<16>::TOTAL));
+    done = true;
+    return MMD_OK;
+}
+
+int launch_gemm(const GemmParams& p, int bn, cudaStream_t st) {
+    MMD_TRY(gemm_init_attrs());
+    const int tiles = p.m_tiles * p.n_tiles;
+    const int grid = std::min(tiles, num_sms());
+    if (bn == 128) conv_gemm_kernel<128><<<grid, GEMM_THREADS, GemmSmem<128>::TOTAL, st>>>(p);
+    else if (bn == 64) conv_gemm_kernel<64><<<grid, GEMM_THREADS, GemmSmem<64>::TOTAL, st>>>(p);
+    else if (bn == 16) conv_gemm_kernel<16><<<grid, GEMM_THREADS, GemmSmem<16>::TOTAL, st>>>(p);
+    else return fail(MMD_EINVAL, "unsupported BN %d", bn);
+    MMD_CUDA_OK(cudaGetLastError());
+    return MMD_OK;
+}
+
+// ------------------------------------------------------------- attention
+static constexpr int ATT_MIN_SMEM = 120 * 1024;  // keeps one CTA per SM (each CTA allocates all 512 TMEM columns)
+template <int D>
+static int attn_smem_bytes() { return std::max(AttnSmem<D>::TOTAL, ATT_MIN_SMEM); }
+
+int build_attn(const AttnProblem& pr, AttnParams* out) {
+    AttnParams& p = *out;
+    memset(&p, 0, sizeof(p));
+    if (pr.d != 64 && pr.d != 96 && pr.d != 128) return fail(MMD_EINVAL, "attention head_dim %d unsupported (64/96/128)", pr.d);
+    if (pr.q_blk <= 0 || pr.k_blk <= 0 || pr.win < 1 || pr.win > pr.n_blocks) return fail(MMD_EINVAL, "attention block geometry");
+    uint64_t dims[2], str[1];
+    uint32_t box[2] = {64, 128};
+    dims[0] = pr.q_ld; dims[1] = pr.q_rows; str[0] = static_cast<uint64_t>(pr.q_ld) * sizeof(act_t);
+    MMD_TRY(encode_tmap(&p.q_map, pr.q, 2, dims, str, box));
+    dims[0] = pr.k_ld; dims[1] = pr.k_rows; str[0] = static_cast<uint64_t>(pr.k_ld) * sizeof(act_t);
+    MMD_TRY(encode_tmap(&p.k_map, pr.k, 2, dims, str, box));
+    dims[0] = pr.v_ld; dims[1] = pr.k_rows; str[0] = static_cast<uint64_t>(pr.v_ld) * sizeof(act_t);
+    MMD_TRY(encode_tmap(&p.v_map, pr.v, 2, dims, str, box));
+    p.out = pr.out; p.out_ld = pr.out_ld;
+    p.B = pr.B; p.heads = pr.heads;
+    p.q_col0 = pr.q_col0; p.k_col0 = pr.k_col0; p.v_col0 = pr.v_col0;
+    p.n_blocks = pr.n_blocks;
+    p.q_blk = pr.q_blk; p.q_per_batch = pr.q_blk * pr.n_blocks;
+    p.k_blk = pr.k_blk; p.k_per_batch = pr.k_blk * pr.n_blocks;
+    p.win = pr.win;
+    p.shift_ptr = pr.shift_dev;
+    p.q_tiles = (pr.q_blk + ATT_BQ - 1) / ATT_BQ;
+    p.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(pr.d));
+    return MMD_OK;
+}
+
+int launch_attn(const AttnParams& p, int d, cudaStream_t st) {
+    static bool done = false;
+    if (!done) {
+        MMD_CUDA_OK(cudaFuncSetAttribute(attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes<64>()));
+        MMD_CUDA_OK(cudaFuncSetAttribute(attention_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes<96>()));
+        MMD_CUDA_OK(cudaFuncSetAttribute(attention_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes<128>()));
+        done = true;
+    }
+    const int grid = p.B * p.n_blocks * p.heads * p.q_tiles;
+    if (d == 64) attention_kernel<64><<<grid, ATT_THREADS, attn_smem_bytes<64>(), st>>>(p);
+    else if (d == 96) attention_kernel<96><<<grid, ATT_THREADS, attn_smem_bytes<96>(), st>>>(p);
+    else attention_kernel<128><<<grid, ATT_THREADS, attn_smem_bytes<128>(), st>>>(p);
+    MMD_CUDA_OK(cudaGetLastError());
+    return MMD_OK;
+}
+
+// ------------------------------------------------------------ elementwise
+static int gn_rows_per_block(int ns, int rows) {
+    // aim for ~4 blocks per SM overall, at least 32 rows per block
+    const int target_blocks = 4 * num_sms();
+    int per_domain = std::max(1, target_blocks / std::max(1, ns));
+    int rpb = (rows + per_domain - 1) / per_domain;
+    rpb = std::max(rpb, 32);
+    return std::min(rpb, rows);
+}
+
+int launch_gn_stats(const GnSrc& s, int ns, int rows, double* sums, cudaStream_t st) {
+    const int C = s.c1 + s.c2;
+    if (C % 32 != 0 || C % 8 != 0 || s.c1 % 8 != 0 || C / 8 > 256) return fail(MMD_EINVAL, "group norm channels %d unsupported", C);
+    MMD_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(double) * 64 * ns, st));
+    const int rpb = gn_rows_per_block(ns, rows);
+    dim3 grid((rows + rpb - 1) / rpb, ns);
+    gn_stats_kernel<<<grid, 256, 0, st>>>(s, rows, rpb, sums);
+    MMD_CUDA_OK(cudaGetLastError());
+    return MMD_OK;
+}
+
+int launch_gn_apply(const GnSrc& s, int ns, int rows, const double* sums, const float* gamma, const float* beta,
+                    const float* film, int film_ld, int ns_per_batch, int silu, act_t* y, cudaStream_t st) {
+    const int C = s.c1 + s.c2;
+    const int rpb = gn_rows_per_block(ns, rows);
+    dim3 grid((rows + rpb - 1) / rpb, ns);
+    gn_apply_kernel<<<grid, 256, 2 * C * sizeof(float), st>>>(s, rows, rpb, sums, gamma, beta, film, film_ld,
+                                                               ns_per_batch, silu, y);
+    MMD_CUDA_OK(cudaGetLastError());
+    return MMD_OK;
+}
+
+int launch_gn_temporal(const act_t* x, act_t* y, const float* gamma, const float* beta, int B, int F, int P, int C,
+                       cudaStream_t st) {
+    if (C % 64 != 0) return fail(MMD_EINVAL, "temporal group norm channels %d", C);
+    const long long total = static_cast<long long>(B) * P * 32;
+    gn_temporal_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, y, gamma, beta, B, F, P, C);
+    MMD_CUDA_OK(cudaGetLastError());
+    return MMD_OK;
+}
+
+int launch_resample(const act_t* x, act_t* y, int mode, int n, int h, int w, int c, cudaStream_t st) {
+    long long total;
+    const int vpr = c / 8;
+    if (mode == 0) total = static_cast<long long>(n) * (h / 2) * (w / 2) * vpr;
+    else if (mode == 1) total = static_cast<long long>(n) * (h / 4) * vpr;
+    else if (mode == 2) total = static_cast<long long>(n) * (h * 2) * (w * 2) * vpr;
+    else if (mode == 3) total = static_cast<long long>(n) * (h * 4) * vpr;
+    else return fail(MMD_EINVAL, "resample mode %d", mode);
+    resample_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, y, mode, n, h, w, c);
+    MMD_CUDA_OK(cudaGetLastError());
+    return MMD_OK;
+}
+
+int launch_temporal_attn(const act_t* qkv, act_t* out, int B, int F, int P, int C, int heads, cudaStream_t st) {
+    const int d = C / heads;
+    if (d % 8 != 0) return fail(MMD_EINVAL, "temporal attention head dim %d", d);
+    const int wpb = 4;
+    const size_t per_warp = static_cast<size_t>(3) * F * d * sizeof(act_t) + static_cast<size_t>(F) * F * sizeof(float);
+    const size_t smem = per_warp * wpb;
+    const long long items = static_cast<long long>(B) * P * heads;
+    const unsigned grid = static_cast<unsigned>((items + wpb - 1) / wpb);
+    static bool attr_done = false;
+    if (!attr_done) {
+        MMD_CUDA_OK(cudaFuncSetAttribute(temporal_attn_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        MMD_CUDA_OK(cudaFuncSetAttribute(temporal_attn_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        attr_done = true;
+    }
+    if (F == 16) temporal_attn_kernel<16><<<grid, wpb * 32, smem, st>>>(qkv, out, B, P, C, heads);
+    else if (F == 8) temporal_attn_kernel<8><<<grid, wpb * 32, smem, st>>>(qkv, out, B, P, C, heads);
+    else return fail(MMD_EINVAL, "temporal attention supports F in {8,16}, got %d", F);
+    MMD_CUDA_OK(cudaGetLastError());
+    return MMD_OK;
+}
+
+int launch_pack_weight(const float* w, act_t* dst, int co, int ci, int t, long long ld, long long col_off, cudaStream_t st) {
+    const long long total = static_cast<long long>(co) * ci * t;
+    pack_weight_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(w, dst, co, ci, t, ld, col_off);
+    MMD_CUDA_OK(cudaGetLastError());
+    return MMD_OK;
+}
+
+}  // namespace mmd
+
+// ===========================================================================
+//                         operator-level C ABI
+// ===========================================================================
+using namespace mmd;
+
+extern "C" {
+
+const char* mmd_last_error(void) { return last_error_ref().c_str(); }
+const char* mmd_version(void) { return "mmdiff-b200 0.1 (sm_100a)"; }
+
+int mmd_op_group_norm(const void* x1, int c1, const void* x2, int c2, int ns, int rows, const float* gamma,
+                      const float* beta, const float* film, int film_ld, int ns_per_batch, int silu, void* y,
+                      void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    GnSrc s{static_cast<const act_t*>(x1), c1, c1, static_cast<const act_t*>(x2), c2, c2};
+    double* sums = nullptr;
+    MMD_CUDA_OK(cudaMallocAsync(&sums, sizeof(double) * 64 * ns, st));
+    int r = launch_gn_stats(s, ns, rows, sums, st);
+    if (r == MMD_OK)
+        r = launch_gn_apply(s, ns, rows, sums, gamma, beta, film, film_ld, ns_per_batch > 0 ? ns_per_batch : 1, silu,
+                            static_cast<act_t*>(y), st);
+    cudaFreeAsync(sums, st);
+    return r;
+}
+
+int mmd_op_group_norm_temporal(const void* x, void* y, const float* gamma, const float* beta, int B, int F, int P, int C,
+                               void* stream) {
+    return launch_gn_temporal(static_cast<const act_t*>(x), static_cast<act_t*>(y), gamma, beta, B, F, P, C,
+                              static_cast<cudaStream_t>(stream));
+}
+
+int mmd_op_resample(const void* x, void* y, int mode, int n, int h, int w, int c, void* stream) {
+    return launch_resample(static_cast<const act_t*>(x), static_cast<act_t*>(y), mode, n, h, w, c,
+                           static_cast<cudaStream_t>(stream));
+}
+
+int mmd_op_conv(const MmdConvDesc* d, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!d) return fail(MMD_EINVAL, "null conv desc");
+    GemmProblem pr;
+    pr.g.rank = d->rank;
+    for (int i = 0; i < 4; ++i) { pr.g.dims[i] = d->dims[i] > 0 ? d->dims[i] : 1; pr.g.box[i] = d->box[i] > 0 ? d->box[i] : 1; }
+    if (d->box[0] <= 0) geom_fill_box(pr.g);
+    pr.n_src = d->n_src;
+    int ctot = 0;
+    for (int s = 0; s < d->n_src && s < GEMM_MAX_SRC; ++s) {
+        pr.src[s] = static_cast<const act_t*>(d->src[s]);
+        pr.src_c[s] = d->src_channels[s];
+        ctot += d->src_channels[s];
+    }
+    pr.n_taps = d->n_taps;
+    for (int t = 0; t < d->n_taps && t < GEMM_MAX_TAPS; ++t)
+        for (int j = 0; j < 3; ++j) pr.taps[t][j] = d->taps[t][j];
+    pr.n = d->n;
+    pr.bn = d->out_f32 ? 16 : pick_bn(d->n);
+    pr.out = static_cast<act_t*>(d->out);
+    pr.out_f32 = d->out_f32;
+    for (int i = 0; i < 4; ++i) pr.ostride[i] = d->ostride[i];
+    pr.ostride_c = d->ostride_c;
+    const long long kt = pr.k_total();
+    const int npad = pr.n_pad();
+    act_t* wp = nullptr;
+    float* bp = nullptr;
+    MMD_CUDA_OK(cudaMallocAsync(&wp, sizeof(act_t) * kt * npad, st));
+    MMD_CUDA_OK(cudaMallocAsync(&bp, sizeof(float) * npad, st));
+    MMD_CUDA_OK(cudaMemsetAsync(wp, 0, sizeof(act_t) * kt * npad, st));
+    MMD_CUDA_OK(cudaMemsetAsync(bp, 0, sizeof(float) * npad, st));
+    int r = launch_pack_weight(d->weight, wp, d->n, ctot, d->n_taps, kt, 0, st);
+    if (r == MMD_OK && d->bias) {
+        cudaError_t e = cudaMemcpyAsync(bp, d->bias, sizeof(float) * d->n, cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) r = fail(MMD_ECUDA, "bias copy: %s", cudaGetErrorString(e));
+    }
+    pr.w = wp;
+    pr.bias = bp;
+    GemmParams gp;
+    if (r == MMD_OK) r = build_gemm(pr, &gp);
+    if (r == MMD_OK) r = launch_gemm(gp, pr.bn, st);
+    cudaFreeAsync(wp, st);
+    cudaFreeAsync(bp, st);
+    return r;
+}
+
+int mmd_op_attention(const MmdAttnDesc* d, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!d) return fail(MMD_EINVAL, "null attention desc");
+    int* shift_dev = nullptr;
+    MMD_CUDA_OK(cudaMallocAsync(&shift_dev, sizeof(int), st));
+    MMD_CUDA_OK(cudaMemcpyAsync(shift_dev, &d->shift, sizeof(int), cudaMemcpyHostToDevice, st));
+    AttnProblem pr{static_cast<const act_t*>(d->q), d->q_ld, d->q_col0, d->q_rows,
+                   static_cast<const act_t*>(d->k), d->k_ld, d->k_col0, d->k_rows,
+                   static_cast<const act_t*>(d->v), d->v_ld, d->v_col0,
+                   static_cast<act_t*>(d->out), d->out_ld,
+                   d->batch, d->heads, d->head_dim, d->n_blocks, d->q_blk, d->k_blk, d->win, shift_dev};
+    AttnParams ap;
+    int r = build_attn(pr, &ap);
+    if (r == MMD_OK) r = launch_attn(ap, d->head_dim, st);
+    cudaFreeAsync(shift_dev, st);
+    return r;
+}
+
+int mmd_op_temporal_attention(const void* qkv, void* out, int B, int F, int P, int C, int heads, void* stream) {
+    return launch_temporal_attn(static_cast<const act_t*>(qkv), static_cast<act_t*>(out), B, F, P, C, heads,
+                                static_cast<cudaStream_t>(stream));
+}
+
+int mmd_p_sample_tail(const float* x, const float* eps, const float* noise, const float* coef, int batch,
+                      int64_t per_sample, int clip_denoised, float* sample, float* pred_xstart, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long total = static_cast<long long>(batch) * per_sample;
+    const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 8LL * num_sms()));
+    p_sample_tail_kernel<<<grid, 256, 0, st>>>(x, eps, noise, coef, per_sample, total, clip_denoised, sample, pred_xstart);
+    MMD_CUDA_OK(cudaGetLastError());
+    return MMD_OK;
+}
+
+int mmd_q_sample(const float* x_start, const float* noise, const float* coef, int batch, int64_t per_sample, float* out,
+                 void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long total = static_cast<long long>(batch) * per_sample;
+    const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 8LL * num_sms()));
+    q_sample_kernel<<<grid, 256, 0, st>>>(x_start, noise, coef, per_sample, total, out);
+    MMD_CUDA_OK(cudaGetLastError());
+    return MMD_OK;
+}
+
+}  // extern "C"

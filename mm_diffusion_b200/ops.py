@@ -1,0 +1,181 @@
+"""Operator-level Python wrappers over the C-ABI (tensors are channels-last fp16 CUDA tensors).
+
+These mirror the reference's leaf modules so the parity tests read like tests of
+the reference's own ops:
+  conv_*            <-> VideoConv / AudioConv      (mm_diffusion/multimodal_unet.py:68-131)
+  group_norm        <-> GroupNorm32 (+SiLU, +FiLM) (mm_diffusion/nn.py:16-33)
+  attention         <-> QKVAttention / SingleModalQKVAttention (multimodal_unet.py:212-244, 498-564)
+  resample          <-> Upsample / Downsample      (multimodal_unet.py:133-208)
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import MmdAttnDesc, MmdConvDesc, check, current_stream_ptr, ptr
+
+
+def _conv(srcs, weight, bias, n, rank, dims, taps, out=None, out_f32=None, ostride=None, ostride_c=0):
+    lib = _lib.load()
+    d = MmdConvDesc()
+    d.rank = rank
+    for i in range(4):
+        d.dims[i] = dims[i] if i < len(dims) else 1
+        d.box[i] = 0  # let the library pick the 128-token box
+    d.n_src = len(srcs)
+    keep = []
+    for i, s in enumerate(srcs):
+        assert s.dtype == torch.float16 and s.is_contiguous() and s.is_cuda
+        d.src[i] = s.data_ptr()
+        d.src_channels[i] = s.shape[-1]
+        keep.append(s)
+    d.n_taps = len(taps)
+    for t, tp in enumerate(taps):
+        for j in range(3):
+            d.taps[t][j] = int(tp[j])
+    w = weight.detach().to(torch.float32).contiguous()
+    b = None if bias is None else bias.detach().to(torch.float32).contiguous()
+    d.weight = w.data_ptr()
+    d.bias = ptr(b)
+    d.n = n
+    d.out = ptr(out)
+    d.out_f32 = ptr(out_f32)
+    if ostride is not None:
+        for i in range(4):
+            d.ostride[i] = ostride[i] if i < len(ostride) else 0
+    d.ostride_c = ostride_c
+    check(lib.mmd_op_conv(C.byref(d), current_stream_ptr()))
+    return out if out is not None else out_f32
+
+
+def conv_pointwise(srcs, weight, bias):
+    """1x1(x1) conv over token matrices [M, C_i] (channel-concatenated sources) -> [M, Cout] fp16."""
+    m = srcs[0].numel() // srcs[0].shape[-1]
+    n = weight.shape[0]
+    out = torch.empty(srcs[0].shape[:-1] + (n,), dtype=torch.float16, device=srcs[0].device)
+    w = weight.reshape(n, -1, 1)
+    return _conv([s.reshape(m, s.shape[-1]) for s in srcs], w, bias, n, 2, [m], [(0, 0, 0)], out=out)
+
+
+def conv_spatial(x, weight, bias):
+    """3x3 'same' conv per frame: x [N,H,W,C] fp16, weight [Co,Ci,3,3] -> [N,H,W,Co]."""
+    N, H, W, Ci = x.shape
+    n = weight.shape[0]
+    out = torch.empty((N, H, W, n), dtype=torch.float16, device=x.device)
+    taps = [(kx - 1, ky - 1, 0) for ky in range(3) for kx in range(3)]
+    return _conv([x], weight.reshape(n, Ci, 9), bias, n, 4, [W, H, N], taps, out=out)
+
+
+def conv_temporal(x, weight, bias):
+    """k=3 'same' conv along frames: x [B,F,P,C], weight [Co,Ci,3] -> [B,F,P,Co]."""
+    B, F, P, Ci = x.shape
+    n = weight.shape[0]
+    out = torch.empty((B, F, P, n), dtype=torch.float16, device=x.device)
+    taps = [(0, k - 1, 0) for k in range(3)]
+    return _conv([x], weight.reshape(n, Ci, 3), bias, n, 4, [P, F, B], taps, out=out)
+
+
+def conv_audio(x, weight, bias, dilation=1):
+    """k=3 dilated 'same' conv: x [B,L,C], weight [Co,Ci,3] -> [B,L,Co]."""
+    B, L, Ci = x.shape
+    n = weight.shape[0]
+    out = torch.empty((B, L, n), dtype=torch.float16, device=x.device)
+    taps = [((k - 1) * dilation, 0, 0) for k in range(3)]
+    return _conv([x], weight.reshape(n, Ci, 3), bias, n, 3, [L, B], taps, out=out)
+
+
+def conv3d_head(x, weight, bias):
+    """3x3x3 'same' conv to a few channels, fp32 NCHW output: x [B,F,H,W,C] -> [B,F,Co,H,W] fp32."""
+    B, F, H, W, Ci = x.shape
+    n = weight.shape[0]
+    out = torch.empty((B, F, n, H, W), dtype=torch.float32, device=x.device)
+    taps = [(kx - 1, ky - 1, kt - 1) for kt in range(3) for ky in range(3) for kx in range(3)]
+    return _conv([x], weight.reshape(n, Ci, 27), bias, n, 5, [W, H, F, B], taps, out_f32=out,
+                 ostride=[1, W, n * H * W, F * n * H * W], ostride_c=H * W)
+
+
+def conv1d_head(x, weight, bias):
+    """k=3 'same' conv to a few channels, fp32 NCL output: x [B,L,C] -> [B,Co,L] fp32."""
+    B, L, Ci = x.shape
+    n = weight.shape[0]
+    out = torch.empty((B, n, L), dtype=torch.float32, device=x.device)
+    taps = [(k - 1, 0, 0) for k in range(3)]
+    return _conv([x], weight.reshape(n, Ci, 3), bias, n, 3, [L, B], taps, out_f32=out, ostride=[1, n * L],
+                 ostride_c=L)
+
+
+def group_norm(x, gamma, beta, ns, x2=None, film=None, ns_per_batch=1, silu=False):
+    """GroupNorm(32) over `ns` domains of equal row count on [rows_total, C] (optionally concat of x and x2)."""
+    lib = _lib.load()
+    c1 = x.shape[-1]
+    c2 = 0 if x2 is None else x2.shape[-1]
+    rows_total = x.numel() // c1
+    rows = rows_total // ns
+    y = torch.empty(x.shape[:-1] + (c1 + c2,), dtype=torch.float16, device=x.device)
+    g = gamma.detach().float().contiguous()
+    b = beta.detach().float().contiguous()
+    f = None if film is None else film.detach().float().contiguous()
+    check(lib.mmd_op_group_norm(x.data_ptr(), c1, ptr(x2), c2, ns, rows, g.data_ptr(), b.data_ptr(), ptr(f),
+                                0 if f is None else f.shape[-1], ns_per_batch, int(silu), y.data_ptr(),
+                                current_stream_ptr()))
+    return y
+
+
+def group_norm_temporal(x, gamma, beta):
+    """x [B,F,P,C]; statistics per (b, pixel, group) over F x C/32 (temporal attention norm)."""
+    lib = _lib.load()
+    B, F, P, Cc = x.shape
+    y = torch.empty_like(x)
+    g = gamma.detach().float().contiguous()
+    b = beta.detach().float().contiguous()
+    check(lib.mmd_op_group_norm_temporal(x.data_ptr(), y.data_ptr(), g.data_ptr(), b.data_ptr(), B, F, P, Cc,
+                                         current_stream_ptr()))
+    return y
+
+
+def resample(x, mode):
+    """mode: 'vpool' [N,H,W,C]->[N,H/2,W/2,C]; 'apool' [N,L,C]->[N,L/4,C]; 'vup' x2; 'aup' x4."""
+    lib = _lib.load()
+    if mode in ("vpool", "vup"):
+        N, H, W, Cc = x.shape
+        shape = (N, H // 2, W // 2, Cc) if mode == "vpool" else (N, H * 2, W * 2, Cc)
+        m = 0 if mode == "vpool" else 2
+    else:
+        N, H, Cc = x.shape
+        W = 1
+        shape = (N, H // 4, Cc) if mode == "apool" else (N, H * 4, Cc)
+        m = 1 if mode == "apool" else 3
+    y = torch.empty(shape, dtype=torch.float16, device=x.device)
+    check(lib.mmd_op_resample(x.data_ptr(), y.data_ptr(), m, N, H, W, Cc, current_stream_ptr()))
+    return y
+
+
+def attention(q_mat, k_mat, v_mat, q_col0, k_col0, v_col0, batch, heads, head_dim, n_blocks, q_blk, k_blk, win=1,
+              shift=0):
+    """Windowed attention over row-major fp16 matrices (column ranges select q/k/v and heads).
+
+    Query block i (q_blk rows) of sample b attends key blocks (i+shift+j) mod n_blocks, j < win.
+    Returns [q_rows, heads*head_dim] fp16."""
+    lib = _lib.load()
+    d = MmdAttnDesc()
+    d.q, d.q_ld, d.q_col0, d.q_rows = q_mat.data_ptr(), q_mat.shape[1], q_col0, q_mat.shape[0]
+    d.k, d.k_ld, d.k_col0, d.k_rows = k_mat.data_ptr(), k_mat.shape[1], k_col0, k_mat.shape[0]
+    d.v, d.v_ld, d.v_col0 = v_mat.data_ptr(), v_mat.shape[1], v_col0
+    out = torch.empty((q_mat.shape[0], heads * head_dim), dtype=torch.float16, device=q_mat.device)
+    d.out, d.out_ld = out.data_ptr(), heads * head_dim
+    d.batch, d.heads, d.head_dim = batch, heads, head_dim
+    d.n_blocks, d.q_blk, d.k_blk, d.win, d.shift = n_blocks, q_blk, k_blk, win, shift
+    check(lib.mmd_op_attention(C.byref(d), current_stream_ptr()))
+    return out
+
+
+def temporal_attention(qkv, heads):
+    """qkv [B,F,P,3C] -> [B,F,P,C]: attention over the F axis per pixel."""
+    lib = _lib.load()
+    B, F, P, C3 = qkv.shape
+    Cc = C3 // 3
+    out = torch.empty((B, F, P, Cc), dtype=torch.float16, device=qkv.device)
+    check(lib.mmd_op_temporal_attention(qkv.data_ptr(), out.data_ptr(), B, F, P, Cc, heads, current_stream_ptr()))
+    return out
