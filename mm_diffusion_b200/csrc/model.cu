@@ -1,15 +1,927 @@
-// placeholder until the network plan lands (next commit): keeps every symbol of include/mmdiff.h exported.
+// MultimodalUNet as a static launch plan over the sm_100a kernels (C-ABI: mmd_model_*).
+//
+// Restates the reference's model assembly (mm_diffusion/multimodal_unet.py:737-1012 constructor,
+// :1058-1101 forward, :434-495 ResBlock, :655-678 CrossAttentionBlock) as one topology walk that
+//   (create)  registers every parameter under the reference's name / shape / order
+//             and lays out the repacked fp16 weights, and
+//   (plan)    emits, for a batch size, the ordered list of kernel launches on channels-last fp16
+//             activations [B,F,H,W,C] / [B,L,C].
+// The plan is captured into a CUDA graph; per-call inputs (x, t, window shifts) go through
+// fixed staging buffers so the graph is replayable.
+#include <algorithm>
+#include <functional>
+#include <map>
+#include <memory>
+#include <unordered_map>
+
 #include "host.cuh"
-using namespace mmd;
-extern "C" {
-int mmd_model_create(const MmdConfig*, MmdModel**) { return fail(MMD_ESTATE, "model plan not built yet"); }
-int mmd_model_destroy(MmdModel*) { return MMD_OK; }
-int mmd_model_num_params(const MmdModel*) { return 0; }
-int mmd_model_param_info(const MmdModel*, int, const char**, int*, int64_t*) { return fail(MMD_ESTATE, "n/a"); }
-int mmd_model_set_param(MmdModel*, const char*, const float*, int64_t, void*) { return fail(MMD_ESTATE, "n/a"); }
-int mmd_model_num_shifts(const MmdModel*) { return 0; }
-int mmd_model_shift_bound(const MmdModel*, int) { return 0; }
-size_t mmd_model_workspace_bytes(const MmdModel*, int) { return 0; }
-int mmd_model_num_launches(const MmdModel*, int) { return 0; }
-int mmd_model_forward(MmdModel*, int, const float*, const float*, const float*, const int32_t*, float*, float*, void*) { return fail(MMD_ESTATE, "n/a"); }
+
+namespace mmd {
+
+struct ShiftArgs { int n; int v[64]; };
+__global__ void set_shifts_kernel(ShiftArgs a, int* dst) {
+    if (threadIdx.x < a.n) dst[threadIdx.x] = a.v[threadIdx.x];
 }
+
+using LaunchFn = std::function<int(cudaStream_t)>;
+
+struct ParamInfo {
+    std::string name;
+    std::vector<int64_t> shape;
+    size_t offset = 0;  // floats, into the fp32 arena
+    int64_t numel = 0;
+    bool set = false;
+};
+
+struct PackedConv {
+    size_t w_off = 0;     // halves, into packed arena
+    size_t b_off = 0;     // floats, into packed bias arena
+    int n = 0, n_pad = 0, bn = 128;
+    long long k_total = 0;
+};
+
+struct Arena {
+    uint8_t* base = nullptr;
+    size_t cap = 0, top = 0, peak = 0;
+    void* take(size_t bytes) {
+        size_t at = (top + 1023) & ~size_t(1023);
+        top = at + bytes;
+        peak = std::max(peak, top);
+        return base ? base + at : reinterpret_cast<void*>(at);  // dry run when base == nullptr
+    }
+};
+
+struct Plan {
+    int B = 0;
+    std::vector<LaunchFn> steps;
+    uint8_t* ws = nullptr;
+    size_t ws_bytes = 0;
+    float *in_video = nullptr, *in_audio = nullptr, *t_dev = nullptr, *out_video = nullptr, *out_audio = nullptr;
+    int* shifts_dev = nullptr;
+    cudaGraphExec_t graph = nullptr;
+    ~Plan() {
+        if (graph) cudaGraphExecDestroy(graph);
+        if (ws) cudaFree(ws);
+    }
+};
+
+}  // namespace mmd
+
+using namespace mmd;
+
+struct MmdModel {
+    MmdConfig cfg{};
+    std::vector<ParamInfo> params;
+    std::unordered_map<std::string, int> param_index;
+    float* w32 = nullptr;      // fp32 copies of all parameters
+    size_t w32_floats = 0;
+    std::map<std::string, PackedConv> packs;
+    std::vector<LaunchFn> pack_ops;
+    act_t* wpk = nullptr;      // packed fp16 weights
+    size_t wpk_halves = 0;
+    float* bpk = nullptr;      // packed fp32 biases + stacked emb weights
+    size_t bpk_floats = 0;
+    bool dirty = true;
+    std::vector<int> shift_bounds;  // per cross block in execution order; -1 = no draw
+    int emb_rows = 0;               // stacked emb_layers rows
+    size_t emb_w_off = 0, emb_b_off = 0;
+    std::map<int, std::unique_ptr<Plan>> plans;
+    bool use_graph = true;
+    cudaStream_t cap_stream = nullptr;
+    ~MmdModel() {
+        plans.clear();
+        if (w32) cudaFree(w32);
+        if (wpk) cudaFree(wpk);
+        if (bpk) cudaFree(bpk);
+        if (cap_stream) cudaStreamDestroy(cap_stream);
+    }
+};
+
+namespace mmd {
+
+// ---------------------------------------------------------------------------
+// Topology walk.  mode CREATE: registers params + packed layouts (no device work).
+//                 mode PLAN  : emits launches into plan (weights/arenas must exist).
+// ---------------------------------------------------------------------------
+struct VT { act_t* p; int C, H, W; };   // video [B,F,H,W,C]
+struct AT { act_t* p; int C, L; };      // audio [B,L,C]
+
+struct Walker {
+    MmdModel& m;
+    bool create;
+    Plan* plan = nullptr;
+    int B = 1;
+    Arena persist, scratch;
+    int err = MMD_OK;
+    size_t w32_top = 0, wpk_top = 0, bpk_top = 0;
+    int shift_slot = 0;
+    int emb_row_top = 0;
+    float* emb_all = nullptr;   // [B][emb_rows]
+    float* silu_emb = nullptr;  // [B][E]
+
+    Walker(MmdModel& mm, bool c) : m(mm), create(c) {}
+    const MmdConfig& cfg() const { return m.cfg; }
+    int F() const { return m.cfg.video_f; }
+
+    bool bad() const { return err != MMD_OK; }
+    void set_err(int e) { if (err == MMD_OK) err = e; }
+
+    // ---------------- parameters
+    int reg(const std::string& name, std::vector<int64_t> shape) {
+        if (create) {
+            ParamInfo pi;
+            pi.name = name;
+            pi.shape = shape;
+            pi.numel = 1;
+            for (auto s : shape) pi.numel *= s;
+            pi.offset = w32_top;
+            w32_top += (pi.numel + 3) & ~size_t(3);
+            m.param_index[name] = static_cast<int>(m.params.size());
+            m.params.push_back(pi);
+            return static_cast<int>(m.params.size()) - 1;
+        }
+        auto it = m.param_index.find(name);
+        if (it == m.param_index.end()) { set_err(fail(MMD_ENOTFOUND, "internal: param %s", name.c_str())); return 0; }
+        return it->second;
+    }
+    const float* pf(int idx) const { return m.w32 + m.params[idx].offset; }
+    struct ConvP { int w, b; };
+    ConvP reg_conv(const std::string& p, int o, int i, std::vector<int64_t> k) {
+        std::vector<int64_t> ws = {o, i};
+        ws.insert(ws.end(), k.begin(), k.end());
+        ConvP r;
+        r.w = reg(p + ".weight", ws);
+        r.b = reg(p + ".bias", {o});
+        return r;
+    }
+    struct GnP { int g, b; };
+    GnP reg_gn(const std::string& p, int c) {
+        GnP r;
+        r.g = reg(p + ".GroupNorm.weight", {c});
+        r.b = reg(p + ".GroupNorm.bias", {c});
+        return r;
+    }
+
+    // ---------------- packed weights
+    struct Seg { int w; int ci; int T; };
+    const PackedConv* pack(const std::string& key, int n, const std::vector<Seg>& segs, int identity_c,
+                           const std::vector<int>& biases, int force_bn = 0, long long min_k = 0) {
+        if (!create) {
+            auto it = m.packs.find(key);
+            if (it == m.packs.end()) { set_err(fail(MMD_ENOTFOUND, "internal: pack %s", key.c_str())); return nullptr; }
+            return &it->second;
+        }
+        PackedConv pc;
+        pc.n = n;
+        pc.bn = force_bn ? force_bn : pick_bn(n);
+        pc.n_pad = (n + pc.bn - 1) / pc.bn * pc.bn;
+        long long k = 0;
+        for (auto& s : segs) k += static_cast<long long>(s.ci) * s.T;
+        k += identity_c;
+        k = std::max(k, min_k);
+        pc.k_total = k;
+        pc.w_off = wpk_top;
+        wpk_top += (static_cast<size_t>(pc.n_pad) * k + 63) & ~size_t(63);
+        pc.b_off = bpk_top;
+        bpk_top += (pc.n_pad + 63) & ~size_t(63);
+        MmdModel* mp = &m;
+        std::vector<Seg> segs_c = segs;
+        std::vector<int> bias_c = biases;
+        m.pack_ops.push_back([mp, pc, segs_c, identity_c, bias_c](cudaStream_t st) -> int {
+            act_t* dst = mp->wpk + pc.w_off;
+            long long col = 0;
+            for (auto& s : segs_c) {
+                MMD_TRY(launch_pack_weight(mp->w32 + mp->params[s.w].offset, dst, pc.n, s.ci, s.T, pc.k_total, col, st));
+                col += static_cast<long long>(s.ci) * s.T;
+            }
+            if (identity_c > 0) {
+                pack_identity_kernel<<<(identity_c + 255) / 256, 256, 0, st>>>(dst, identity_c, pc.k_total, col);
+                MMD_CUDA_OK(cudaGetLastError());
+            }
+            float* bdst = mp->bpk + pc.b_off;
+            MMD_CUDA_OK(cudaMemsetAsync(bdst, 0, sizeof(float) * pc.n_pad, st));
+            for (int bi : bias_c) {
+                add_vec_kernel<<<(pc.n + 255) / 256, 256, 0, st>>>(bdst, mp->w32 + mp->params[bi].offset, pc.n);
+                MMD_CUDA_OK(cudaGetLastError());
+            }
+            return MMD_OK;
+        });
+        m.packs[key] = pc;
+        return &m.packs[key];
+    }
+
+    // ---------------- activations
+    act_t* alloc_p(size_t elems) { return static_cast<act_t*>(persist.take(elems * sizeof(act_t))); }
+    act_t* alloc_s(size_t elems) { return static_cast<act_t*>(scratch.take(elems * sizeof(act_t))); }
+    void* alloc_s_bytes(size_t bytes) { return scratch.take(bytes); }
+    size_t vtok(const VT& v) const { return static_cast<size_t>(B) * F() * v.H * v.W; }
+    size_t atok(const AT& a) const { return static_cast<size_t>(B) * a.L; }
+    bool emitting() const { return plan != nullptr && persist.base != nullptr; }
+
+    void push(LaunchFn fn) { if (emitting()) plan->steps.push_back(std::move(fn)); }
+
+    // ---------------- emitters
+    void emit_gemm(const ConvGeom& g, const std::vector<std::pair<const act_t*, int>>& srcs,
+                   const std::vector<std::array<int, 3>>& taps, const PackedConv* pc, act_t* out, float* out_f32 = nullptr,
+                   const long long* ostride = nullptr, long long ostride_c = 0) {
+        if (!emitting() || bad() || !pc) return;
+        GemmProblem pr;
+        pr.g = g;
+        pr.n_src = static_cast<int>(srcs.size());
+        long long ctot = 0;
+        for (size_t i = 0; i < srcs.size(); ++i) { pr.src[i] = srcs[i].first; pr.src_c[i] = srcs[i].second; ctot += srcs[i].second; }
+        pr.n_taps = static_cast<int>(taps.size());
+        for (size_t t = 0; t < taps.size(); ++t) for (int j = 0; j < 3; ++j) pr.taps[t][j] = taps[t][j];
+        if (ctot * pr.n_taps != pc->k_total) { set_err(fail(MMD_EINVAL, "internal: K mismatch %lld vs %lld", ctot * pr.n_taps, pc->k_total)); return; }
+        pr.w = m.wpk + pc->w_off;
+        pr.bias = m.bpk + pc->b_off;
+        pr.n = pc->n;
+        pr.bn = pc->bn;
+        pr.out = out;
+        pr.out_f32 = out_f32;
+        if (ostride) for (int i = 0; i < 4; ++i) pr.ostride[i] = ostride[i];
+        pr.ostride_c = ostride_c;
+        auto gp = std::make_shared<GemmParams>();
+        int r = build_gemm(pr, gp.get());
+        if (r != MMD_OK) { set_err(r); return; }
+        const int bn = pc->bn;
+        push([gp, bn](cudaStream_t st) { return launch_gemm(*gp, bn, st); });
+    }
+    static ConvGeom geom2(long long tokens) { ConvGeom g; g.rank = 2; g.dims[0] = tokens; geom_fill_box(g); return g; }
+    ConvGeom geom_spatial(const VT& v) const { ConvGeom g; g.rank = 4; g.dims[0] = v.W; g.dims[1] = v.H; g.dims[2] = static_cast<long long>(B) * F(); geom_fill_box(g); return g; }
+    ConvGeom geom_temporal(const VT& v) const { ConvGeom g; g.rank = 4; g.dims[0] = static_cast<long long>(v.H) * v.W; g.dims[1] = F(); g.dims[2] = B; geom_fill_box(g); return g; }
+    ConvGeom geom_audio(const AT& a) const { ConvGeom g; g.rank = 3; g.dims[0] = a.L; g.dims[1] = B; geom_fill_box(g); return g; }
+
+    // GroupNorm over `ns` domains of `rows` rows on the concat of (x1,c1),(x2,c2)
+    act_t* emit_gn(const act_t* x1, int c1, const act_t* x2, int c2, int ns, int rows, GnP gn, const float* film,
+                   int ns_per_batch, int silu, bool persistent_out = false) {
+        const int C = c1 + c2;
+        act_t* y = persistent_out ? alloc_p(static_cast<size_t>(ns) * rows * C) : alloc_s(static_cast<size_t>(ns) * rows * C);
+        double* sums = static_cast<double*>(alloc_s_bytes(sizeof(double) * 64 * ns));
+        if (!emitting() || bad()) return y;
+        GnSrc s{x1, c1, c1, x2, c2, c2};
+        const float* gamma = pf(gn.g);
+        const float* beta = pf(gn.b);
+        const int film_ld = m.emb_rows;
+        push([=](cudaStream_t st) -> int {
+            MMD_TRY(launch_gn_stats(s, ns, rows, sums, st));
+            return launch_gn_apply(s, ns, rows, sums, gamma, beta, film, film_ld, ns_per_batch, silu, y, st);
+        });
+        return y;
+    }
+
+    void emit_attn(const act_t* q, int q_ld, int q_col0, long long q_rows, const act_t* k, int k_ld, int k_col0,
+                   long long k_rows, const act_t* v, int v_col0, act_t* out, int out_ld, int heads, int d, int n_blocks,
+                   int q_blk, int k_blk, int win, const int* shift_dev) {
+        if (!emitting() || bad()) return;
+        AttnProblem pr{q, q_ld, q_col0, q_rows, k, k_ld, k_col0, k_rows, v, k_ld, v_col0, out, out_ld,
+                       B, heads, d, n_blocks, q_blk, k_blk, win, shift_dev};
+        auto ap = std::make_shared<AttnParams>();
+        int r = build_attn(pr, ap.get());
+        if (r != MMD_OK) { set_err(r); return; }
+        push([ap, d](cudaStream_t st) { return launch_attn(*ap, d, st); });
+    }
+
+    // ---------------- network pieces
+    // SingleModalAtten over sequences: kind 0 spatial (per frame), 1 temporal (per pixel), 2 audio
+    act_t* self_attention(const std::string& p, const act_t* x, int C, int kind, const VT* vt, const AT* at) {
+        GnP gn = reg_gn(p + ".norm", C);
+        ConvP qkv = reg_conv(p + ".qkv", 3 * C, C, {1});
+        ConvP proj = reg_conv(p + ".proj_out", C, C, {1});
+        const int heads = cfg().num_heads;
+        const int d = C / heads;
+        if (create) {
+            if (C % heads != 0) set_err(fail(MMD_EINVAL, "channels %d not divisible by num_heads %d", C, heads));
+            if (kind != 1 && d != 64 && d != 96 && d != 128)
+                set_err(fail(MMD_EINVAL, "self-attention head dim %d unsupported by the tcgen05 kernel (64/96/128)", d));
+        }
+        const PackedConv* pq = pack(p + ".qkv", 3 * C, {{qkv.w, C, 1}}, 0, {qkv.b});
+        const PackedConv* pp = pack(p + ".proj+res", C, {{proj.w, C, 1}}, C, {proj.b});
+        if (create) return nullptr;
+        const size_t tokens = vt ? vtok(*vt) : atok(*at);
+        act_t* out = alloc_p(tokens * C);
+        const size_t mark = scratch.top;
+        act_t* xn;
+        if (kind == 0) {
+            xn = emit_gn(x, C, nullptr, 0, B * F(), vt->H * vt->W, gn, nullptr, 1, 0);
+        } else if (kind == 2) {
+            xn = emit_gn(x, C, nullptr, 0, B, at->L, gn, nullptr, 1, 0);
+        } else {
+            xn = alloc_s(tokens * C);
+            if (emitting()) {
+                const float* gamma = pf(gn.g);
+                const float* beta = pf(gn.b);
+                const int Bc = B, Fc = F(), P = vt->H * vt->W;
+                push([=](cudaStream_t st) { return launch_gn_temporal(x, xn, gamma, beta, Bc, Fc, P, C, st); });
+            }
+        }
+        act_t* qkvb = alloc_s(tokens * 3 * C);
+        emit_gemm(geom2(static_cast<long long>(tokens)), {{xn, C}}, {{0, 0, 0}}, pq, qkvb);
+        act_t* o = alloc_s(tokens * C);
+        if (kind == 0) {
+            const int hw = vt->H * vt->W;
+            emit_attn(qkvb, 3 * C, 0, tokens, qkvb, 3 * C, C, tokens, qkvb, 2 * C, o, C, heads, d, F(), hw, hw, 1, nullptr);
+        } else if (kind == 2) {
+            emit_attn(qkvb, 3 * C, 0, tokens, qkvb, 3 * C, C, tokens, qkvb, 2 * C, o, C, heads, d, 1, at->L, at->L, 1, nullptr);
+        } else if (emitting()) {
+            const int Bc = B, Fc = F(), P = vt->H * vt->W;
+            push([=](cudaStream_t st) { return launch_temporal_attn(qkvb, o, Bc, Fc, P, C, heads, st); });
+        }
+        emit_gemm(geom2(static_cast<long long>(tokens)), {{o, C}, {x, C}}, {{0, 0, 0}}, pp, out);
+        scratch.top = mark;
+        return out;
+    }
+
+    void res_block(const std::string& p, VT& v, const act_t* v2, int vc2, AT& a, const act_t* a2, int ac2, int cout,
+                   int dilation, bool up, bool down, bool vattn, bool aattn) {
+        const int cin = v.C + vc2;
+        const int E = cfg().model_channels;
+        // registration order = module definition order in ResBlock.__init__ (multimodal_unet.py:338-419)
+        GnP vin_gn = reg_gn(p + ".video_in_layers.0", cin);
+        ConvP vsp = reg_conv(p + ".video_in_layers.2.video_conv_spatial", cout, cin, {3, 3});
+        ConvP vtp = reg_conv(p + ".video_in_layers.2.video_conv_temporal", cout, cout, {3});
+        GnP ain_gn = reg_gn(p + ".audio_in_layers.0", cin);
+        ConvP aconv = reg_conv(p + ".audio_in_layers.2.audio_conv", cout, cin, {3});
+        int emb_w = reg(p + ".emb_layers.1.weight", {2 * cout, E});
+        int emb_b = reg(p + ".emb_layers.1.bias", {2 * cout});
+        GnP vout_gn = reg_gn(p + ".video_out_layers.0", cout);
+        ConvP vout = reg_conv(p + ".video_out_layers.3.video_conv", cout, cout, {1, 1, 1});
+        GnP aout_gn = reg_gn(p + ".audio_out_layers.0", cout);
+        ConvP aout = reg_conv(p + ".audio_out_layers.3.audio_conv", cout, cout, {1});
+        ConvP vskip{-1, -1}, askip{-1, -1};
+        if (cin != cout) {
+            vskip = reg_conv(p + ".video_skip_connection.video_conv", cout, cin, {1, 1, 1});
+            askip = reg_conv(p + ".audio_skip_connection.audio_conv", cout, cin, {1});
+        }
+        // stacked emb_layers rows
+        const int emb_row0 = emb_row_top;
+        emb_row_top += 2 * cout;
+        if (create) {
+            MmdModel* mp = &m;
+            const int rows = 2 * cout;
+            m.pack_ops.push_back([mp, emb_w, emb_b, emb_row0, rows, E](cudaStream_t st) -> int {
+                MMD_CUDA_OK(cudaMemcpyAsync(mp->bpk + mp->emb_w_off + static_cast<size_t>(emb_row0) * E,
+                                            mp->w32 + mp->params[emb_w].offset, sizeof(float) * rows * E,
+                                            cudaMemcpyDeviceToDevice, st));
+                MMD_CUDA_OK(cudaMemcpyAsync(mp->bpk + mp->emb_b_off + emb_row0, mp->w32 + mp->params[emb_b].offset,
+                                            sizeof(float) * rows, cudaMemcpyDeviceToDevice, st));
+                return MMD_OK;
+            });
+        }
+        const PackedConv* p_vsp = pack(p + ".v_spatial", cout, {{vsp.w, cin, 9}}, 0, {vsp.b});
+        const PackedConv* p_vtp = pack(p + ".v_temporal", cout, {{vtp.w, cout, 3}}, 0, {vtp.b});
+        const PackedConv* p_ac = pack(p + ".a_conv", cout, {{aconv.w, cin, 3}}, 0, {aconv.b});
+        const PackedConv *p_vo, *p_ao;
+        if (cin != cout) {
+            p_vo = pack(p + ".v_out+skip", cout, {{vout.w, cout, 1}, {vskip.w, cin, 1}}, 0, {vout.b, vskip.b});
+            p_ao = pack(p + ".a_out+skip", cout, {{aout.w, cout, 1}, {askip.w, cin, 1}}, 0, {aout.b, askip.b});
+        } else {
+            p_vo = pack(p + ".v_out+res", cout, {{vout.w, cout, 1}}, cin, {vout.b});
+            p_ao = pack(p + ".a_out+res", cout, {{aout.w, cout, 1}}, cin, {aout.b});
+        }
+
+        VT vo{nullptr, cout, v.H, v.W};
+        AT ao{nullptr, cout, a.L};
+        if (!create) {
+            if ((up || down) && (v2 || a2)) { set_err(fail(MMD_EINVAL, "internal: resampling block with concat input")); return; }
+            const float* film = emb_all ? emb_all + emb_row0 : nullptr;
+            const int Fr = F();
+            // ---------------- video branch
+            {
+                if (down) { vo.H = v.H / 2; vo.W = v.W / 2; }
+                if (up) { vo.H = v.H * 2; vo.W = v.W * 2; }
+                vo.p = alloc_p(static_cast<size_t>(B) * Fr * vo.H * vo.W * cout);
+                const size_t mark = scratch.top;
+                const int hw = v.H * v.W;
+                act_t* h0 = emit_gn(v.p, v.C, v2, vc2, B, Fr * hw, vin_gn, nullptr, 1, 1);
+                act_t* u = alloc_s(vtok(v) * cout);
+                VT vin{h0, cin, v.H, v.W};
+                std::vector<std::array<int, 3>> taps9;
+                for (int ky = 0; ky < 3; ++ky) for (int kx = 0; kx < 3; ++kx) taps9.push_back({kx - 1, ky - 1, 0});
+                emit_gemm(geom_spatial(vin), {{h0, cin}}, taps9, p_vsp, u);
+                act_t* h1 = alloc_s(vtok(v) * cout);
+                emit_gemm(geom_temporal(vin), {{u, cout}}, {{0, -1, 0}, {0, 0, 0}, {0, 1, 0}}, p_vtp, h1);
+                const act_t* xs = v.p;   // skip-path input (single source when resampling)
+                if (up || down) {
+                    act_t* h1r = alloc_s(static_cast<size_t>(B) * Fr * vo.H * vo.W * cout);
+                    act_t* xr = alloc_s(static_cast<size_t>(B) * Fr * vo.H * vo.W * v.C);
+                    if (emitting()) {
+                        const int mode = down ? 0 : 2;
+                        const int n = B * Fr, H = v.H, W = v.W, c_h = cout, c_x = v.C;
+                        const act_t* xin = v.p;
+                        push([=](cudaStream_t st) -> int {
+                            MMD_TRY(launch_resample(h1, h1r, mode, n, H, W, c_h, st));
+                            return launch_resample(xin, xr, mode, n, H, W, c_x, st);
+                        });
+                    }
+                    h1 = h1r;
+                    xs = xr;
+                }
+                const int hwo = vo.H * vo.W;
+                act_t* h2 = emit_gn(h1, cout, nullptr, 0, B, Fr * hwo, vout_gn, film, 1, 1);
+                std::vector<std::pair<const act_t*, int>> srcs = {{h2, cout}, {xs, v.C}};
+                if (v2) srcs.push_back({v2, vc2});
+                emit_gemm(geom2(static_cast<long long>(B) * Fr * hwo), srcs, {{0, 0, 0}}, p_vo, vo.p);
+                scratch.top = mark;
+            }
+            // ---------------- audio branch
+            {
+                if (down) ao.L = a.L / 4;
+                if (up) ao.L = a.L * 4;
+                ao.p = alloc_p(static_cast<size_t>(B) * ao.L * cout);
+                const size_t mark = scratch.top;
+                act_t* h0 = emit_gn(a.p, a.C, a2, ac2, B, a.L, ain_gn, nullptr, 1, 1);
+                act_t* h1 = alloc_s(atok(a) * cout);
+                AT ain{h0, cin, a.L};
+                emit_gemm(geom_audio(ain), {{h0, cin}}, {{-dilation, 0, 0}, {0, 0, 0}, {dilation, 0, 0}}, p_ac, h1);
+                const act_t* xs = a.p;
+                if (up || down) {
+                    act_t* h1r = alloc_s(static_cast<size_t>(B) * ao.L * cout);
+                    act_t* xr = alloc_s(static_cast<size_t>(B) * ao.L * a.C);
+                    if (emitting()) {
+                        const int mode = down ? 1 : 3;
+                        const int n = B, L = a.L, c_h = cout, c_x = a.C;
+                        const act_t* xin = a.p;
+                        push([=](cudaStream_t st) -> int {
+                            MMD_TRY(launch_resample(h1, h1r, mode, n, L, 1, c_h, st));
+                            return launch_resample(xin, xr, mode, n, L, 1, c_x, st);
+                        });
+                    }
+                    h1 = h1r;
+                    xs = xr;
+                }
+                act_t* h2 = emit_gn(h1, cout, nullptr, 0, B, ao.L, aout_gn, film, 1, 1);
+                std::vector<std::pair<const act_t*, int>> srcs = {{h2, cout}, {xs, a.C}};
+                if (a2) srcs.push_back({a2, ac2});
+                emit_gemm(geom2(static_cast<long long>(B) * ao.L), srcs, {{0, 0, 0}}, p_ao, ao.p);
+                scratch.top = mark;
+            }
+        }
+        // ---------------- in-block self attention (multimodal_unet.py:485-493)
+        if (vattn) {
+            act_t* s = self_attention(p + ".spatial_attention_block", vo.p, cout, 0, &vo, nullptr);
+            act_t* t = self_attention(p + ".temporal_attention_block", s, cout, 1, &vo, nullptr);
+            vo.p = t;
+        }
+        if (aattn) {
+            act_t* s = self_attention(p + ".audio_attention_block", ao.p, cout, 2, nullptr, &ao);
+            ao.p = s;
+        }
+        v = vo;
+        a = ao;
+    }
+
+    void cross_block(const std::string& p, VT& v, AT& a, int window, bool shift) {
+        const int C = v.C;
+        GnP vn = reg_gn(p + ".v_norm", C);
+        GnP an = reg_gn(p + ".a_norm", C);
+        ConvP vq = reg_conv(p + ".v_qkv", 3 * C, C, {1});
+        ConvP aq = reg_conv(p + ".a_qkv", 3 * C, C, {1});
+        ConvP vp = reg_conv(p + ".video_proj_out.video_conv", C, C, {1, 1, 1});
+        ConvP apj = reg_conv(p + ".audio_proj_out.audio_conv", C, C, {1});
+        const int heads = cfg().num_head_channels == -1 ? cfg().num_heads : C / cfg().num_head_channels;
+        const int d = C / std::max(heads, 1);
+        const int slot = shift_slot++;
+        if (create) {
+            if (heads < 1 || C % heads != 0 || (d != 64 && d != 96 && d != 128))
+                set_err(fail(MMD_EINVAL, "cross-attention head dim %d unsupported (64/96/128)", d));
+            if (window < 1 || window > F()) set_err(fail(MMD_EINVAL, "cross-attention window %d vs %d frames", window, F()));
+            m.shift_bounds.push_back(shift ? F() - window : -1);
+        }
+        const PackedConv* p_vq = pack(p + ".v_qkv", 3 * C, {{vq.w, C, 1}}, 0, {vq.b});
+        const PackedConv* p_aq = pack(p + ".a_qkv", 3 * C, {{aq.w, C, 1}}, 0, {aq.b});
+        const PackedConv* p_vp = pack(p + ".v_proj+res", C, {{vp.w, C, 1}}, C, {vp.b});
+        const PackedConv* p_ap = pack(p + ".a_proj+res", C, {{apj.w, C, 1}}, C, {apj.b});
+        if (create) return;
+        const int Fr = F();
+        const int hw = v.H * v.W;
+        if (a.L % Fr != 0) { set_err(fail(MMD_EINVAL, "audio length %d not divisible by %d frames (unsupported remainder segment)", a.L, Fr)); return; }
+        const int apf = a.L / Fr;
+        const size_t vt = vtok(v), at = atok(a);
+        act_t* vout = alloc_p(vt * C);
+        act_t* aout = alloc_p(at * C);
+        const size_t mark = scratch.top;
+        act_t* vnrm = emit_gn(v.p, C, nullptr, 0, B, Fr * hw, vn, nullptr, 1, 0);
+        act_t* anrm = emit_gn(a.p, C, nullptr, 0, B, a.L, an, nullptr, 1, 0);
+        act_t* vqkv = alloc_s(vt * 3 * C);
+        act_t* aqkv = alloc_s(at * 3 * C);
+        emit_gemm(geom2(static_cast<long long>(vt)), {{vnrm, C}}, {{0, 0, 0}}, p_vq, vqkv);
+        emit_gemm(geom2(static_cast<long long>(at)), {{anrm, C}}, {{0, 0, 0}}, p_aq, aqkv);
+        act_t* ov = alloc_s(vt * C);
+        act_t* oa = alloc_s(at * C);
+        const int* sdev = (shift && plan) ? plan->shifts_dev + slot : nullptr;
+        // video queries attend audio keys/values and vice versa (multimodal_unet.py:530-559)
+        emit_attn(vqkv, 3 * C, 0, vt, aqkv, 3 * C, C, at, aqkv, 2 * C, ov, C, heads, d, Fr, hw, apf, window, sdev);
+        emit_attn(aqkv, 3 * C, 0, at, vqkv, 3 * C, C, vt, vqkv, 2 * C, oa, C, heads, d, Fr, apf, hw, window, sdev);
+        emit_gemm(geom2(static_cast<long long>(vt)), {{ov, C}, {v.p, C}}, {{0, 0, 0}}, p_vp, vout);
+        emit_gemm(geom2(static_cast<long long>(at)), {{oa, C}, {a.p, C}}, {{0, 0, 0}}, p_ap, aout);
+        scratch.top = mark;
+        v.p = vout;
+        a.p = aout;
+    }
+
+    static bool contains(const int* arr, int n, int v) {
+        for (int i = 0; i < n; ++i) if (arr[i] == v) return true;
+        return false;
+    }
+    static int index_of(const int* arr, int n, int v) {
+        for (int i = 0; i < n; ++i) if (arr[i] == v) return i;
+        return -1;
+    }
+
+    void walk() {
+        const MmdConfig& c = cfg();
+        const int mc = c.model_channels;
+        const int E = mc;
+        // ---- time embedding (multimodal_unet.py:791-795, 1075)
+        int te0w = reg("time_embed.0.weight", {E, mc}), te0b = reg("time_embed.0.bias", {E});
+        int te2w = reg("time_embed.2.weight", {E, E}), te2b = reg("time_embed.2.bias", {E});
+        float* emb = nullptr;
+        if (!create) {
+            emb = static_cast<float*>(persist.take(sizeof(float) * B * E));
+            silu_emb = static_cast<float*>(persist.take(sizeof(float) * B * E));
+            emb_all = static_cast<float*>(persist.take(sizeof(float) * B * std::max(m.emb_rows, 1)));
+            if (emitting()) {
+                const float *w1 = pf(te0w), *b1 = pf(te0b), *w2 = pf(te2w), *b2 = pf(te2b);
+                const float* tdev = plan->t_dev;
+                float* se = silu_emb;
+                float* ea = emb_all;
+                const int Bc = B, rows = m.emb_rows;
+                const float* ew = m.bpk + m.emb_w_off;
+                const float* eb = m.bpk + m.emb_b_off;
+                push([=](cudaStream_t st) -> int {
+                    time_embed_kernel<<<Bc, E, 2 * E * sizeof(float), st>>>(tdev, w1, b1, w2, b2, E, emb, se);
+                    MMD_CUDA_OK(cudaGetLastError());
+                    emb_layers_kernel<<<(rows + 7) / 8, 256, 0, st>>>(se, ew, eb, Bc, E, rows, ea);
+                    MMD_CUDA_OK(cudaGetLastError());
+                    return MMD_OK;
+                });
+            }
+        }
+        // ---- input blocks
+        int ch = c.channel_mult[0] * mc;
+        std::vector<int> chans = {ch};
+        VT v{nullptr, ch, c.video_h, c.video_w};
+        AT a{nullptr, ch, c.audio_l};
+        std::vector<VT> vstack;
+        std::vector<AT> astack;
+        {   // InitialBlock (multimodal_unet.py:680-694)
+            const std::string p = "input_blocks.0.0";
+            ConvP vsp = reg_conv(p + ".video_conv.video_conv_spatial", ch, c.video_c, {3, 3});
+            ConvP vtp = reg_conv(p + ".video_conv.video_conv_temporal", ch, ch, {3});
+            ConvP ac = reg_conv(p + ".audio_conv.audio_conv", ch, c.audio_c, {3});
+            if (create && (9 * c.video_c > 64 || 3 * c.audio_c > 64))
+                set_err(fail(MMD_EINVAL, "input channels too wide for the im2col stem (video_c %d audio_c %d)", c.video_c, c.audio_c));
+            const PackedConv* p_sp = pack(p + ".v_spatial", ch, {{vsp.w, c.video_c, 9}}, 0, {vsp.b}, 0, 64);
+            const PackedConv* p_tp = pack(p + ".v_temporal", ch, {{vtp.w, ch, 3}}, 0, {vtp.b});
+            const PackedConv* p_ac = pack(p + ".a_conv", ch, {{ac.w, c.audio_c, 3}}, 0, {ac.b}, 0, 64);
+            if (!create) {
+                v.p = alloc_p(vtok(v) * ch);
+                a.p = alloc_p(atok(a) * ch);
+                const size_t mark = scratch.top;
+                act_t* colv = alloc_s(vtok(v) * 64);
+                act_t* cola = alloc_s(atok(a) * 64);
+                act_t* u = alloc_s(vtok(v) * ch);
+                if (emitting()) {
+                    const float* vin = plan->in_video;
+                    const float* ain = plan->in_audio;
+                    const int BF = B * F(), Cv = c.video_c, H = c.video_h, W = c.video_w, Bc = B, Ca = c.audio_c, L = c.audio_l;
+                    push([=](cudaStream_t st) -> int {
+                        const long long tv = static_cast<long long>(BF) * H * W * 8;
+                        im2col_video_kernel<<<static_cast<unsigned>((tv + 255) / 256), 256, 0, st>>>(vin, colv, BF, Cv, H, W);
+                        MMD_CUDA_OK(cudaGetLastError());
+                        const long long ta = static_cast<long long>(Bc) * L * 8;
+                        im2col_audio_kernel<<<static_cast<unsigned>((ta + 255) / 256), 256, 0, st>>>(ain, cola, Bc, Ca, L);
+                        MMD_CUDA_OK(cudaGetLastError());
+                        return MMD_OK;
+                    });
+                }
+                emit_gemm(geom2(static_cast<long long>(vtok(v))), {{colv, 64}}, {{0, 0, 0}}, p_sp, u);
+                emit_gemm(geom_temporal(v), {{u, ch}}, {{0, -1, 0}, {0, 0, 0}, {0, 1, 0}}, p_tp, v.p);
+                emit_gemm(geom2(static_cast<long long>(atok(a))), {{cola, 64}}, {{0, 0, 0}}, p_ac, a.p);
+                scratch.top = mark;
+            }
+            vstack.push_back(v);
+            astack.push_back(a);
+        }
+        int ds = 1, dil = 1, idx = 1;
+        for (int level = 0; level < c.n_levels; ++level) {
+            const int mult = c.channel_mult[level];
+            for (int r = 0; r < c.num_res_blocks; ++r) {
+                const std::string p = "input_blocks." + std::to_string(idx);
+                const int cout = mult * mc;
+                res_block(p + ".0", v, nullptr, 0, a, nullptr, 0, cout, 1 << (dil % 10), false, false,
+                          contains(c.video_attention_resolutions, c.n_video_attn, ds),
+                          contains(c.audio_attention_resolutions, c.n_audio_attn, ds));
+                ++dil;
+                ch = cout;
+                if (contains(c.cross_attention_resolutions, c.n_cross, ds)) {
+                    const int wi = index_of(c.cross_attention_resolutions, c.n_cross, ds);
+                    cross_block(p + ".1", v, a, c.cross_attention_windows[wi], c.cross_attention_shift != 0);
+                }
+                vstack.push_back(v);
+                astack.push_back(a);
+                chans.push_back(ch);
+                ++idx;
+                if (bad()) return;
+            }
+            if (level != c.n_levels - 1) {
+                const std::string p = "input_blocks." + std::to_string(idx);
+                res_block(p + ".0", v, nullptr, 0, a, nullptr, 0, ch, 1 << (dil % 10), false, true, false, false);
+                ++dil;
+                vstack.push_back(v);
+                astack.push_back(a);
+                chans.push_back(ch);
+                ds *= 2;
+                ++idx;
+            }
+        }
+        // ---- middle (multimodal_unet.py:875-941)
+        const int mid_dil = 1 << (dil % 10);
+        const bool three_part = c.n_cross == 3 && c.cross_attention_windows[0] == 1 && c.cross_attention_windows[1] == 4 &&
+                                c.cross_attention_windows[2] == 8;
+        res_block("middle_blocks.0", v, nullptr, 0, a, nullptr, 0, ch, mid_dil, false, false, true, true);
+        if (three_part) {
+            cross_block("middle_blocks.1", v, a, c.video_f, false);
+            res_block("middle_blocks.2", v, nullptr, 0, a, nullptr, 0, ch, mid_dil, false, false, true, true);
+        } else {
+            res_block("middle_blocks.1", v, nullptr, 0, a, nullptr, 0, ch, mid_dil, false, false, true, true);
+        }
+        if (bad()) return;
+        // ---- output blocks (multimodal_unet.py:944-1000, 1092-1095)
+        dil -= 1;
+        idx = 0;
+        for (int level = c.n_levels - 1; level >= 0; --level) {
+            const int mult = c.channel_mult[level];
+            for (int i = 0; i <= c.num_res_blocks; ++i) {
+                const std::string p = "output_blocks." + std::to_string(idx);
+                const int ich = chans.back();
+                chans.pop_back();
+                VT vs = vstack.back(); vstack.pop_back();
+                AT as = astack.back(); astack.pop_back();
+                if (!create && (vs.H != v.H || vs.W != v.W || as.L != a.L || vs.C != ich)) {
+                    set_err(fail(MMD_EINVAL, "skip shape mismatch at %s (resblock_updown=False style configs are unsupported)", p.c_str()));
+                    return;
+                }
+                const int cout = mc * mult;
+                int sub = 0;
+                res_block(p + "." + std::to_string(sub++), v, vs.p, ich, a, as.p, ich, cout, 1 << (dil % 10), false, false,
+                          contains(c.video_attention_resolutions, c.n_video_attn, ds),
+                          contains(c.audio_attention_resolutions, c.n_audio_attn, ds));
+                dil -= 1;
+                ch = cout;
+                if (contains(c.cross_attention_resolutions, c.n_cross, ds)) {
+                    const int wi = index_of(c.cross_attention_resolutions, c.n_cross, ds);
+                    cross_block(p + "." + std::to_string(sub++), v, a, c.cross_attention_windows[wi], c.cross_attention_shift != 0);
+                }
+                if (level > 0 && i == c.num_res_blocks) {
+                    res_block(p + "." + std::to_string(sub++), v, nullptr, 0, a, nullptr, 0, ch, 1 << (dil % 10), true, false, false, false);
+                    ds /= 2;
+                }
+                ++idx;
+                if (bad()) return;
+            }
+        }
+        // ---- heads (multimodal_unet.py:1003-1012, 1097-1098); audio_out is registered first
+        const int ch0 = c.channel_mult[0] * mc;
+        GnP agn = reg_gn("audio_out.0", ch);
+        ConvP ahead = reg_conv("audio_out.2.audio_conv", c.audio_out_channels, ch0, {3});
+        GnP vgn = reg_gn("video_out.0", ch);
+        ConvP vhead = reg_conv("video_out.2.video_conv", c.video_out_channels, ch0, {3, 3, 3});
+        if (create && (ch != ch0 || c.video_out_channels > 16 || c.audio_out_channels > 16))
+            set_err(fail(MMD_EINVAL, "head configuration unsupported (ch %d vs %d)", ch, ch0));
+        const PackedConv* p_ah = pack("audio_out.head", c.audio_out_channels, {{ahead.w, ch0, 3}}, 0, {ahead.b}, 16);
+        const PackedConv* p_vh = pack("video_out.head", c.video_out_channels, {{vhead.w, ch0, 27}}, 0, {vhead.b}, 16);
+        if (!create) {
+            const size_t mark = scratch.top;
+            const int Fr = F();
+            act_t* hv = emit_gn(v.p, ch, nullptr, 0, B, Fr * v.H * v.W, vgn, nullptr, 1, 1);
+            ConvGeom g5; g5.rank = 5; g5.dims[0] = v.W; g5.dims[1] = v.H; g5.dims[2] = Fr; g5.dims[3] = B; geom_fill_box(g5);
+            std::vector<std::array<int, 3>> taps27;
+            for (int kt = 0; kt < 3; ++kt) for (int ky = 0; ky < 3; ++ky) for (int kx = 0; kx < 3; ++kx) taps27.push_back({kx - 1, ky - 1, kt - 1});
+            const long long Co = c.video_out_channels, HW = static_cast<long long>(v.H) * v.W;
+            const long long os_v[4] = {1, v.W, Co * HW, Fr * Co * HW};
+            emit_gemm(g5, {{hv, ch}}, taps27, p_vh, nullptr, plan ? plan->out_video : nullptr, os_v, HW);
+            act_t* ha = emit_gn(a.p, ch, nullptr, 0, B, a.L, agn, nullptr, 1, 1);
+            const long long Ca = c.audio_out_channels;
+            const long long os_a[4] = {1, Ca * a.L, 0, 0};
+            emit_gemm(geom_audio(a), {{ha, ch}}, {{-1, 0, 0}, {0, 0, 0}, {1, 0, 0}}, p_ah, nullptr, plan ? plan->out_audio : nullptr, os_a, a.L);
+            scratch.top = mark;
+        }
+        if (create) m.emb_rows = emb_row_top;
+    }
+};
+
+// Device memory is allocated on first use so that the parameter inventory (names / shapes / shift bounds)
+// can be queried on a machine without a GPU.
+static int ensure_device(MmdModel* m) {
+    if (m->w32) return MMD_OK;
+    MMD_CUDA_OK(cudaMalloc(&m->w32, sizeof(float) * std::max<size_t>(m->w32_floats, 4)));
+    MMD_CUDA_OK(cudaMalloc(&m->wpk, sizeof(act_t) * std::max<size_t>(m->wpk_halves, 8)));
+    MMD_CUDA_OK(cudaMalloc(&m->bpk, sizeof(float) * std::max<size_t>(m->bpk_floats, 4)));
+    MMD_CUDA_OK(cudaMemset(m->wpk, 0, sizeof(act_t) * std::max<size_t>(m->wpk_halves, 8)));
+    MMD_CUDA_OK(cudaMemset(m->bpk, 0, sizeof(float) * std::max<size_t>(m->bpk_floats, 4)));
+    MMD_CUDA_OK(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
+    return MMD_OK;
+}
+
+static int validate_cfg(const MmdConfig& c) {
+    if (c.n_levels < 1 || c.n_levels > MMD_MAX_LEVELS || c.n_cross < 0 || c.n_cross > MMD_MAX_LEVELS ||
+        c.n_video_attn < 0 || c.n_video_attn > MMD_MAX_LEVELS || c.n_audio_attn < 0 || c.n_audio_attn > MMD_MAX_LEVELS)
+        return fail(MMD_EINVAL, "config list lengths out of range");
+    if (c.model_channels % 64 != 0) return fail(MMD_EINVAL, "model_channels %d must be a multiple of 64 (64-channel K chunks)", c.model_channels);
+    if (c.video_f != 8 && c.video_f != 16) return fail(MMD_EINVAL, "video frames %d unsupported (8 or 16)", c.video_f);
+    if (c.max_batch < 1) return fail(MMD_EINVAL, "max_batch");
+    const int down = 1 << (c.n_levels - 1);
+    if (c.video_h % down || c.video_w % down) return fail(MMD_EINVAL, "video size not divisible by %d", down);
+    long long adown = 1;
+    for (int i = 1; i < c.n_levels; ++i) adown *= 4;
+    if (c.audio_l % adown) return fail(MMD_EINVAL, "audio length not divisible by %lld", adown);
+    if ((c.video_w & (c.video_w - 1)) || (c.video_h & (c.video_h - 1))) return fail(MMD_EINVAL, "video H/W must be powers of two");
+    return MMD_OK;
+}
+
+static int build_plan(MmdModel* m, int B, Plan** out) {
+    auto it = m->plans.find(B);
+    if (it != m->plans.end()) { *out = it->second.get(); return MMD_OK; }
+    if (B < 1 || B > m->cfg.max_batch) return fail(MMD_EINVAL, "batch %d outside [1, %d]", B, m->cfg.max_batch);
+    const MmdConfig& c = m->cfg;
+    // pass 1: dry run to size the arenas
+    Walker dry(*m, false);
+    dry.B = B;
+    dry.walk();
+    if (dry.bad()) return dry.err;
+    auto plan = std::make_unique<Plan>();
+    plan->B = B;
+    const size_t vin = sizeof(float) * B * c.video_f * c.video_c * c.video_h * c.video_w;
+    const size_t ain = sizeof(float) * B * c.audio_c * c.audio_l;
+    const size_t vout = sizeof(float) * B * c.video_f * c.video_out_channels * c.video_h * c.video_w;
+    const size_t aout = sizeof(float) * B * c.audio_out_channels * c.audio_l;
+    auto al = [](size_t x) { return (x + 1023) & ~size_t(1023); };
+    const size_t io_bytes = al(vin) + al(ain) + al(vout) + al(aout) + al(sizeof(float) * B) + al(sizeof(int) * 64);
+    const size_t p_bytes = al(dry.persist.peak) + 1024, s_bytes = al(dry.scratch.peak) + 1024;
+    plan->ws_bytes = io_bytes + p_bytes + s_bytes;
+    MMD_CUDA_OK(cudaMalloc(&plan->ws, plan->ws_bytes));
+    MMD_CUDA_OK(cudaMemset(plan->ws, 0, plan->ws_bytes));
+    uint8_t* q = plan->ws;
+    plan->in_video = reinterpret_cast<float*>(q); q += al(vin);
+    plan->in_audio = reinterpret_cast<float*>(q); q += al(ain);
+    plan->out_video = reinterpret_cast<float*>(q); q += al(vout);
+    plan->out_audio = reinterpret_cast<float*>(q); q += al(aout);
+    plan->t_dev = reinterpret_cast<float*>(q); q += al(sizeof(float) * B);
+    plan->shifts_dev = reinterpret_cast<int*>(q); q += al(sizeof(int) * 64);
+    Walker w(*m, false);
+    w.B = B;
+    w.plan = plan.get();
+    w.persist.base = q; w.persist.cap = p_bytes;
+    w.scratch.base = q + p_bytes; w.scratch.cap = s_bytes;
+    w.walk();
+    if (w.bad()) return w.err;
+    if (w.persist.peak > p_bytes || w.scratch.peak > s_bytes) return fail(MMD_ESTATE, "internal: arena overflow");
+    *out = plan.get();
+    m->plans[B] = std::move(plan);
+    return MMD_OK;
+}
+
+static size_t dry_workspace(MmdModel* m, int B) {
+    Walker dry(*m, false);
+    dry.B = B;
+    dry.walk();
+    if (dry.bad()) return 0;
+    return dry.persist.peak + dry.scratch.peak + (1 << 20);
+}
+
+}  // namespace mmd
+
+// ===========================================================================
+extern "C" {
+
+int mmd_model_create(const MmdConfig* cfg, MmdModel** out) {
+    if (!cfg || !out) return fail(MMD_EINVAL, "null argument");
+    MMD_TRY(validate_cfg(*cfg));
+    auto m = std::make_unique<MmdModel>();
+    m->cfg = *cfg;
+    const char* ng = getenv("MMD_NO_GRAPH");
+    m->use_graph = !(ng && ng[0] == '1');
+    Walker w(*m, true);
+    w.walk();
+    if (w.bad()) return w.err;
+    if (m->shift_bounds.size() > 64) return fail(MMD_EINVAL, "too many cross-attention blocks");
+    // stacked emb_layers weights/biases live in the fp32 packed arena
+    m->emb_w_off = w.bpk_top;
+    w.bpk_top += static_cast<size_t>(m->emb_rows) * cfg->model_channels;
+    m->emb_b_off = w.bpk_top;
+    w.bpk_top += m->emb_rows;
+    m->w32_floats = w.w32_top;
+    m->wpk_halves = w.wpk_top;
+    m->bpk_floats = w.bpk_top;
+    *out = m.release();
+    return MMD_OK;
+}
+
+int mmd_model_destroy(MmdModel* m) {
+    delete m;
+    return MMD_OK;
+}
+
+int mmd_model_num_params(const MmdModel* m) { return m ? static_cast<int>(m->params.size()) : 0; }
+
+int mmd_model_param_info(const MmdModel* m, int index, const char** name, int* ndim, int64_t shape[5]) {
+    if (!m || index < 0 || index >= static_cast<int>(m->params.size())) return fail(MMD_EINVAL, "param index %d", index);
+    const ParamInfo& p = m->params[index];
+    if (name) *name = p.name.c_str();
+    if (ndim) *ndim = static_cast<int>(p.shape.size());
+    if (shape) for (size_t i = 0; i < p.shape.size() && i < 5; ++i) shape[i] = p.shape[i];
+    return MMD_OK;
+}
+
+int mmd_model_set_param(MmdModel* m, const char* name, const float* data, int64_t numel, void* stream) {
+    if (!m || !name || !data) return fail(MMD_EINVAL, "null argument");
+    auto it = m->param_index.find(name);
+    if (it == m->param_index.end()) return fail(MMD_ENOTFOUND, "unknown parameter %s", name);
+    MMD_TRY(ensure_device(m));
+    ParamInfo& p = m->params[it->second];
+    if (numel != p.numel) return fail(MMD_EINVAL, "parameter %s: %lld elements given, %lld expected", name, (long long)numel, (long long)p.numel);
+    MMD_CUDA_OK(cudaMemcpyAsync(m->w32 + p.offset, data, sizeof(float) * numel, cudaMemcpyDeviceToDevice,
+                                static_cast<cudaStream_t>(stream)));
+    p.set = true;
+    m->dirty = true;
+    return MMD_OK;
+}
+
+int mmd_model_num_shifts(const MmdModel* m) { return m ? static_cast<int>(m->shift_bounds.size()) : 0; }
+int mmd_model_shift_bound(const MmdModel* m, int index) {
+    if (!m || index < 0 || index >= static_cast<int>(m->shift_bounds.size())) return -1;
+    return m->shift_bounds[index];
+}
+
+size_t mmd_model_workspace_bytes(const MmdModel* m, int batch) {
+    if (!m) return 0;
+    return dry_workspace(const_cast<MmdModel*>(m), batch);
+}
+
+int mmd_model_num_launches(const MmdModel* m, int batch) {
+    if (!m) return 0;
+    auto it = m->plans.find(batch);
+    return it == m->plans.end() ? 0 : static_cast<int>(it->second->steps.size());
+}
+
+int mmd_model_forward(MmdModel* m, int batch, const float* video_in, const float* audio_in, const float* timesteps,
+                      const int32_t* shifts, float* video_out, float* audio_out, void* stream) {
+    if (!m || !video_in || !audio_in || !timesteps || !video_out || !audio_out) return fail(MMD_EINVAL, "null argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MMD_TRY(ensure_device(m));
+    for (auto& p : m->params)
+        if (!p.set) return fail(MMD_ESTATE, "parameter %s was never set", p.name.c_str());
+    if (m->dirty) {
+        for (auto& op : m->pack_ops) MMD_TRY(op(st));
+        m->dirty = false;
+    }
+    Plan* plan = nullptr;
+    MMD_TRY(build_plan(m, batch, &plan));
+    const MmdConfig& c = m->cfg;
+    const size_t vin = sizeof(float) * batch * c.video_f * c.video_c * c.video_h * c.video_w;
+    const size_t ain = sizeof(float) * batch * c.audio_c * c.audio_l;
+    const size_t vout = sizeof(float) * batch * c.video_f * c.video_out_channels * c.video_h * c.video_w;
+    const size_t aout = sizeof(float) * batch * c.audio_out_channels * c.audio_l;
+    MMD_CUDA_OK(cudaMemcpyAsync(plan->in_video, video_in, vin, cudaMemcpyDeviceToDevice, st));
+    MMD_CUDA_OK(cudaMemcpyAsync(plan->in_audio, audio_in, ain, cudaMemcpyDeviceToDevice, st));
+    MMD_CUDA_OK(cudaMemcpyAsync(plan->t_dev, timesteps, sizeof(float) * batch, cudaMemcpyDeviceToDevice, st));
+    ShiftArgs sa{};
+    sa.n = static_cast<int>(m->shift_bounds.size());
+    for (int i = 0; i < sa.n; ++i) {
+        int v = shifts ? shifts[i] : 0;
+        const int hi = m->shift_bounds[i];
+        if (hi < 0) v = 0;
+        else if (v < 0 || v > hi) return fail(MMD_EINVAL, "shift %d of block %d outside [0, %d]", v, i, hi);
+        sa.v[i] = v;
+    }
+    if (sa.n > 0) {
+        set_shifts_kernel<<<1, 64, 0, st>>>(sa, plan->shifts_dev);
+        MMD_CUDA_OK(cudaGetLastError());
+    }
+    if (m->use_graph) {
+        if (!plan->graph) {
+            // pack ops (if any) ran on `st`; make sure the capture stream sees a quiescent device
+            MMD_CUDA_OK(cudaStreamSynchronize(st));
+            cudaGraph_t g = nullptr;
+            MMD_CUDA_OK(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal));
+            int r = MMD_OK;
+            for (auto& step : plan->steps) { r = step(m->cap_stream); if (r != MMD_OK) break; }
+            cudaError_t e = cudaStreamEndCapture(m->cap_stream, &g);
+            if (r != MMD_OK) { if (g) cudaGraphDestroy(g); return r; }
+            if (e != cudaSuccess) return fail(MMD_ECUDA, "graph capture: %s", cudaGetErrorString(e));
+            e = cudaGraphInstantiate(&plan->graph, g, 0);
+            cudaGraphDestroy(g);
+            if (e != cudaSuccess) return fail(MMD_ECUDA, "graph instantiate: %s", cudaGetErrorString(e));
+        }
+        MMD_CUDA_OK(cudaGraphLaunch(plan->graph, st));
+    } else {
+        for (auto& step : plan->steps) MMD_TRY(step(st));
+    }
+    MMD_CUDA_OK(cudaMemcpyAsync(video_out, plan->out_video, vout, cudaMemcpyDeviceToDevice, st));
+    MMD_CUDA_OK(cudaMemcpyAsync(audio_out, plan->out_audio, aout, cudaMemcpyDeviceToDevice, st));
+    return MMD_OK;
+}
+
+}  // extern "C"

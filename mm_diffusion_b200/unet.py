@@ -1,0 +1,294 @@
+"""MultimodalUNet: drop-in for mm_diffusion.multimodal_unet.MultimodalUNet (reference
+multimodal_unet.py:697-1101) whose forward is the hand-written sm_100a path in libmmdiff.so.
+
+The module owns nn.Parameters with the reference's names, shapes and registration order
+(SURVEY.md App. F), so checkpoints (`load_state_dict`, `load_state_dict_`), `.parameters()`,
+EMA copies etc. behave like the reference's.  The network topology itself lives in the C
+library (csrc/model.cu); this file only mirrors the Python surface.  There is no PyTorch
+fallback: forward() requires a CUDA device and the built library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import random
+from typing import Dict, List, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import MmdConfig, MmdError, check
+
+# parameters the reference zero-initialises (nn.py:141-147 zero_module call sites,
+# multimodal_unet.py:275,377,385,609-610,1006,1011)
+_ZERO_INIT_MARKERS = (
+    ".video_out_layers.3.", ".audio_out_layers.3.", ".proj_out.", ".video_proj_out.", ".audio_proj_out.",
+    "video_out.2.", "audio_out.2.",
+)
+
+
+def _fill_config(cfg: MmdConfig, video_size, audio_size, model_channels, video_out_channels, audio_out_channels,
+                 num_res_blocks, cross_attention_resolutions, cross_attention_windows, cross_attention_shift,
+                 video_attention_resolutions, audio_attention_resolutions, channel_mult, num_heads,
+                 num_head_channels, max_batch):
+    cfg.video_f, cfg.video_c, cfg.video_h, cfg.video_w = [int(x) for x in video_size]
+    cfg.audio_c, cfg.audio_l = [int(x) for x in audio_size]
+    cfg.model_channels = int(model_channels)
+    cfg.video_out_channels = int(video_out_channels)
+    cfg.audio_out_channels = int(audio_out_channels)
+    cfg.num_res_blocks = int(num_res_blocks)
+
+    def put(dst, values, what):
+        values = [int(v) for v in values]
+        if len(values) > _lib.MMD_MAX_LEVELS:
+            raise ValueError(f"{what}: at most {_lib.MMD_MAX_LEVELS} entries")
+        for i, v in enumerate(values):
+            dst[i] = v
+        return len(values)
+
+    for m in channel_mult:
+        if int(m) != m:
+            raise ValueError("non-integer channel_mult is not supported by the sm_100a path")
+    cfg.n_levels = put(cfg.channel_mult, channel_mult, "channel_mult")
+    cfg.num_heads = int(num_heads)
+    cfg.num_head_channels = int(num_head_channels)
+    cfg.n_cross = put(cfg.cross_attention_resolutions, cross_attention_resolutions, "cross_attention_resolutions")
+    put(cfg.cross_attention_windows, cross_attention_windows, "cross_attention_windows")
+    if len(cross_attention_windows) != len(cross_attention_resolutions):
+        raise ValueError("cross_attention_windows and cross_attention_resolutions differ in length")
+    cfg.cross_attention_shift = int(bool(cross_attention_shift))
+    cfg.n_video_attn = put(cfg.video_attention_resolutions, video_attention_resolutions, "video_attention_resolutions")
+    cfg.n_audio_attn = put(cfg.audio_attention_resolutions, audio_attention_resolutions, "audio_attention_resolutions")
+    cfg.max_batch = int(max_batch)
+
+
+class _Node(nn.Module):
+    """Anonymous container used to rebuild the reference's dotted parameter names."""
+
+
+class MultimodalUNet(nn.Module):
+    """Same constructor signature as the reference (multimodal_unet.py:737-764)."""
+
+    def __init__(self, video_size, audio_size, model_channels, video_out_channels, audio_out_channels, num_res_blocks,
+                 cross_attention_resolutions, cross_attention_windows, cross_attention_shift,
+                 video_attention_resolutions, audio_attention_resolutions, video_type="2d+1d", audio_type="1d",
+                 dropout=0, channel_mult=(1, 2, 3, 4), num_classes=None, use_checkpoint=False, use_fp16=False,
+                 num_heads=1, num_head_channels=-1, num_heads_upsample=-1, use_scale_shift_norm=False,
+                 resblock_updown=True, max_batch=64):
+        super().__init__()
+        if video_type != "2d+1d" or audio_type != "1d":
+            raise NotImplementedError("only video_type='2d+1d' / audio_type='1d' (the shipped configuration)")
+        if num_classes is not None:
+            raise NotImplementedError("class-conditional models are not supported (nor by the reference's scripts)")
+        if not use_scale_shift_norm or not resblock_updown:
+            # the reference's own non-default branches are broken
+            raise NotImplementedError("use_scale_shift_norm=True and resblock_updown=True are required")
+        self.video_size = video_size
+        self.audio_size = audio_size
+        self.model_channels = model_channels
+        self.video_out_channels = video_out_channels
+        self.audio_out_channels = audio_out_channels
+        self.num_res_blocks = num_res_blocks
+        self.cross_attention_resolutions = cross_attention_resolutions
+        self.cross_attention_windows = cross_attention_windows
+        self.cross_attention_shift = cross_attention_shift
+        self.video_attention_resolutions = video_attention_resolutions
+        self.audio_attention_resolutions = audio_attention_resolutions
+        self.dropout = dropout
+        self.channel_mult = channel_mult
+        self.num_classes = num_classes
+        self.use_checkpoint = use_checkpoint
+        self.dtype = torch.float16 if use_fp16 else torch.float32
+        self.num_heads = num_heads
+        self.num_head_channels = num_head_channels
+        self.num_heads_upsample = num_heads if num_heads_upsample == -1 else num_heads_upsample
+
+        self._cfg = MmdConfig()
+        _fill_config(self._cfg, video_size, audio_size, model_channels, video_out_channels, audio_out_channels,
+                     num_res_blocks, cross_attention_resolutions, cross_attention_windows, cross_attention_shift,
+                     video_attention_resolutions, audio_attention_resolutions, channel_mult, num_heads,
+                     num_head_channels, max_batch)
+        self._handle = None          # MmdModel* (created lazily on the parameters' CUDA device)
+        self._handle_device = None
+        self._synced: Dict[str, tuple] = {}
+        self._needs_sync = True
+        self._param_names: List[str] = []
+        self._shift_bounds: List[int] = []
+        self._build_parameters()
+
+    # ------------------------------------------------------------------ construction
+    def _inventory(self):
+        """(name, shape) list + shift bounds from the C library's topology walk (host-only: works without a GPU)."""
+        lib = _lib.load()
+        h = C.c_void_p()
+        check(lib.mmd_model_create(C.byref(self._cfg), C.byref(h)))
+        try:
+            n = lib.mmd_model_num_params(h)
+            out = []
+            name = C.c_char_p()
+            ndim = C.c_int()
+            shape = (C.c_int64 * 5)()
+            for i in range(n):
+                check(lib.mmd_model_param_info(h, i, C.byref(name), C.byref(ndim), shape))
+                out.append((name.value.decode(), tuple(int(shape[j]) for j in range(ndim.value))))
+            bounds = [lib.mmd_model_shift_bound(h, i) for i in range(lib.mmd_model_num_shifts(h))]
+        finally:
+            lib.mmd_model_destroy(h)
+        return out, bounds
+
+    def _build_parameters(self):
+        names_shapes, bounds = self._inventory()
+        self._shift_bounds = bounds
+        for name, shape in names_shapes:
+            parts = name.split(".")
+            node = self
+            for part in parts[:-1]:
+                child = node._modules.get(part)
+                if child is None:
+                    child = _Node()
+                    node.add_module(part, child)
+                node = child
+            p = nn.Parameter(torch.empty(shape, dtype=torch.float32))
+            node.register_parameter(parts[-1], p)
+            self._param_names.append(name)
+        self.reset_parameters()
+
+    @torch.no_grad()
+    def reset_parameters(self):
+        """PyTorch default Conv/Linear/GroupNorm initialisation + the reference's zero_module sites."""
+        params = dict(self.named_parameters())
+        for name, p in params.items():
+            if any(mk in name for mk in _ZERO_INIT_MARKERS):
+                p.zero_()
+            elif ".GroupNorm." in name:
+                p.fill_(1.0 if name.endswith("weight") else 0.0)
+            elif name.endswith(".weight"):
+                nn.init.kaiming_uniform_(p, a=math.sqrt(5))
+            else:  # bias of a conv / linear: U(-1/sqrt(fan_in), 1/sqrt(fan_in))
+                w = params[name[:-len("bias")] + "weight"]
+                fan_in = w[0].numel()
+                bound = 1.0 / math.sqrt(fan_in) if fan_in > 0 else 0.0
+                p.uniform_(-bound, bound)
+        self._needs_sync = True
+
+    # ------------------------------------------------------------------ reference surface
+    def convert_to_fp16(self):
+        """Reference :1013-1021 casts conv weights to fp16 storage.  The sm_100a path always computes in fp16
+        with fp32 accumulation from its own repacked copy, so only the output dtype changes here."""
+        self.dtype = torch.float16
+
+    def convert_to_fp32(self):
+        self.dtype = torch.float32
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        out = super().load_state_dict(state_dict, strict=strict, assign=assign)
+        self._needs_sync = True
+        return out
+
+    def load_state_dict_(self, state_dict, is_strict=False):
+        """Tolerant loader of the reference (:1033-1054): drop shape-mismatched keys, then load."""
+        own = self.state_dict()
+        for key, val in own.items():
+            if key in state_dict and state_dict[key].shape != val.shape:
+                state_dict.pop(key)
+        self.load_state_dict(state_dict, strict=is_strict)
+
+    def _apply(self, fn, recurse=True):
+        out = super()._apply(fn, recurse)
+        self._needs_sync = True
+        return out
+
+    def train(self, mode: bool = True):
+        self._needs_sync = True
+        return super().train(mode)
+
+    # ------------------------------------------------------------------ device handle
+    def _ensure_handle(self, device: torch.device):
+        if self._handle is not None and self._handle_device == device:
+            return
+        lib = _lib.load()
+        if self._handle is not None:
+            lib.mmd_model_destroy(self._handle)
+            self._handle = None
+        with torch.cuda.device(device):
+            h = C.c_void_p()
+            check(lib.mmd_model_create(C.byref(self._cfg), C.byref(h)))
+        self._handle, self._handle_device = h, device
+        self._synced = {}
+        self._needs_sync = True
+
+    def _sync_parameters(self):
+        lib = _lib.load()
+        stream = _lib.current_stream_ptr()
+        for name, p in zip(self._param_names, self.parameters()):
+            key = (p.data_ptr(), p._version, p.dtype)
+            if self._synced.get(name) == key:
+                continue
+            src = p.detach()
+            if src.dtype != torch.float32 or not src.is_contiguous():
+                src = src.float().contiguous()
+            check(lib.mmd_model_set_param(self._handle, name.encode(), src.data_ptr(), src.numel(), stream))
+            self._synced[name] = key
+        self._needs_sync = False
+
+    def __del__(self):
+        try:
+            if self._handle is not None:
+                _lib.load().mmd_model_destroy(self._handle)
+        except Exception:
+            pass
+
+    @property
+    def shift_bounds(self) -> List[int]:
+        return list(self._shift_bounds)
+
+    def draw_shifts(self) -> List[int]:
+        """One random.randint(0, F - window) per shifting cross-attention block, in execution order, from
+        Python's global `random` — exactly the draws CrossAttentionBlock.attention_index makes (:619-622)."""
+        return [random.randint(0, b) if b >= 0 else 0 for b in self._shift_bounds]
+
+    def num_launches(self, batch: int) -> int:
+        return 0 if self._handle is None else _lib.load().mmd_model_num_launches(self._handle, batch)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, video, audio, timesteps, label=None, shifts: Sequence[int] = None):
+        """video [N,F,C,H,W], audio [N,C,L], timesteps [N] -> (video_out, audio_out) of self.dtype.
+
+        `shifts` (optional) pins the random window shifts; by default they are drawn like the reference."""
+        assert (label is not None) == (self.num_classes is not None), \
+            "must specify y if and only if the model is class-conditional"
+        p0 = next(self.parameters())
+        if not p0.is_cuda or not video.is_cuda:
+            raise MmdError("MultimodalUNet.forward needs CUDA tensors: the denoising step is hand-written "
+                           "sm_100a CUDA and has no CPU fallback")
+        if torch.is_grad_enabled() and (video.requires_grad or audio.requires_grad or
+                                        (self.training and any(p.requires_grad for p in self.parameters()))):
+            raise NotImplementedError(
+                "backward through the sm_100a path is not implemented yet; call under torch.no_grad() "
+                "(sampling) — training kernels are scheduled after the forward path (DESIGN.md)")
+        device = p0.device
+        B = video.shape[0]
+        if tuple(video.shape[1:]) != tuple(int(x) for x in self.video_size) or \
+                tuple(audio.shape[1:]) != tuple(int(x) for x in self.audio_size) or audio.shape[0] != B:
+            raise ValueError(f"input shapes {tuple(video.shape)} / {tuple(audio.shape)} do not match the model's "
+                             f"video_size {self.video_size} / audio_size {self.audio_size}")
+        with torch.cuda.device(device):
+            self._ensure_handle(device)
+            if self._needs_sync or self.training:
+                self._sync_parameters()
+            if shifts is None:
+                shifts = self.draw_shifts()
+            v = video.detach().to(torch.float32).contiguous()
+            a = audio.detach().to(torch.float32).contiguous()
+            t = timesteps.detach().to(device=device, dtype=torch.float32).contiguous()
+            vo = torch.empty((B, self._cfg.video_f, self.video_out_channels, self._cfg.video_h, self._cfg.video_w),
+                             dtype=torch.float32, device=device)
+            ao = torch.empty((B, self.audio_out_channels, self._cfg.audio_l), dtype=torch.float32, device=device)
+            n = len(self._shift_bounds)
+            arr = (C.c_int32 * max(n, 1))(*[int(s) for s in shifts][:n])
+            check(_lib.load().mmd_model_forward(self._handle, B, v.data_ptr(), a.data_ptr(), t.data_ptr(), arr,
+                                                vo.data_ptr(), ao.data_ptr(), _lib.current_stream_ptr()))
+        if self.dtype != torch.float32:
+            vo, ao = vo.to(self.dtype), ao.to(self.dtype)
+        return vo, ao

@@ -1,0 +1,79 @@
+"""Whole-forward parity of the sm_100a path (through the MultimodalUNet shim / C-ABI) against
+ (a) fixtures produced by the unmodified reference (tests/golden, fp32 CPU) and
+ (b) the CPU oracle on the same seeded inputs.
+Stated tolerance (fp16 storage, fp32 accumulate vs fp32 reference): rel-L2 <= 2e-2 on eps for the whole network
+(SURVEY.md §8c proposal); measured values are printed."""
+import random
+
+import pytest
+import torch
+
+from oracle.mmdiff_oracle import draw_shifts, synthetic_state_dict, unet_forward
+from tests.util_golden import build_b200_model, cfg_of, golden_inputs, load_golden, rel_l2
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-2
+
+
+def test_forward_small_vs_reference_golden_and_oracle():
+    fx = load_golden("small")
+    cfg = cfg_of(fx)
+    sd = synthetic_state_dict(cfg, seed=fx["weight_seed"])
+    model = build_b200_model(cfg, sd)
+    v, a = golden_inputs(cfg, fx)
+    random.seed(7)  # the shim draws from the same global RNG stream the reference used
+    with torch.no_grad():
+        ev, ea = model(v.cuda(), a.cuda(), fx["t"].cuda())
+    rv, ra = rel_l2(ev, fx["forward_video"]), rel_l2(ea, fx["forward_audio"])
+    print(f"small: rel-L2 vs reference golden video {rv:.3e} audio {ra:.3e}")
+    assert rv < TOL and ra < TOL
+    # oracle on a different seed/shift draw
+    g = torch.Generator().manual_seed(5)
+    v2 = torch.randn(v.shape, generator=g)
+    a2 = torch.randn(a.shape, generator=g)
+    t2 = torch.tensor([999, 0])
+    shifts = draw_shifts(cfg, random.Random(3))
+    with torch.no_grad():
+        ov, oa = unet_forward(sd, cfg, v2, a2, t2, shifts)
+        ev, ea = model(v2.cuda(), a2.cuda(), t2.cuda(), shifts=shifts)
+    rv, ra = rel_l2(ev, ov), rel_l2(ea, oa)
+    print(f"small: rel-L2 vs oracle video {rv:.3e} audio {ra:.3e}")
+    assert rv < TOL and ra < TOL
+
+
+def test_forward_batch_independence_small():
+    fx = load_golden("small")
+    cfg = cfg_of(fx)
+    model = build_b200_model(cfg, synthetic_state_dict(cfg, seed=1))
+    g = torch.Generator().manual_seed(11)
+    v = torch.randn(3, *cfg.video_size, generator=g).cuda()
+    a = torch.randn(3, *cfg.audio_size, generator=g).cuda()
+    t = torch.tensor([10, 500, 900]).cuda()
+    shifts = draw_shifts(cfg, random.Random(1))
+    with torch.no_grad():
+        ev, ea = model(v, a, t, shifts=shifts)
+        e1v, e1a = model(v[1:2], a[1:2], t[1:2], shifts=shifts)
+    assert torch.equal(ev[1:2], e1v) and torch.equal(ea[1:2], e1a)  # batch-shardable: samples do not interact
+
+
+def test_forward_production_vs_reference_golden():
+    fx = load_golden("production")
+    cfg = cfg_of(fx)
+    sd = synthetic_state_dict(cfg, seed=fx["weight_seed"])
+    model = build_b200_model(cfg, sd)
+    del sd
+    v, a = golden_inputs(cfg, fx)
+    random.seed(7)
+    with torch.no_grad():
+        ev, ea = model(v.cuda(), a.cuda(), fx["t"].cuda())
+    rv = rel_l2(ev.flatten()[::8], fx["forward_video_sub"])
+    ra = rel_l2(ea.flatten()[::8], fx["forward_audio_sub"])
+    print(f"production: rel-L2 vs reference golden video {rv:.3e} audio {ra:.3e}; "
+          f"|ev| {ev.float().norm().item():.3f} (ref {fx['forward_video_norm']:.3f})")
+    assert rv < TOL and ra < TOL
+    # fp16 output mode of the reference surface
+    model.convert_to_fp16()
+    random.seed(7)
+    with torch.no_grad():
+        hv, ha = model(v.cuda(), a.cuda(), fx["t"].cuda())
+    assert hv.dtype == torch.float16 and rel_l2(hv, ev) < 1e-3
