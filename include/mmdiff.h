@@ -82,6 +82,13 @@ int mmd_model_num_launches(const MmdModel* m, int batch);
 int mmd_model_forward(MmdModel* m, int batch, const float* video_in, const float* audio_in, const float* timesteps,
                       const int32_t* shifts, float* video_out, float* audio_out, void* stream);
 
+/* ---- measurement hooks (bench.py): per-launch device time of the plan for `batch` (mean of `reps` un-graphed
+ *      executions, CUDA events on `stream`) and each step's kernel family / algorithmic FLOPs / bytes
+ *      (DESIGN.md §kernels).  mmd_model_profile returns the step count (>0) or a negative error. ---- */
+int mmd_model_profile(MmdModel* m, int batch, int reps, float* ms, int cap, void* stream);
+int mmd_model_step_info(const MmdModel* m, int batch, int index, const char** kind, double* flops, double* bytes,
+                        int* kernels);
+
 /* ---- sampler tail: GaussianDiffusion.p_sample after the model call
  *      (multimodal_gaussian_diffusion.py:292-350, :453-470): per element
  *      x0 = clip(a*x - b*eps); mean = c1*x0 + c2*x; sample = mean + nz*sigma*z.

@@ -89,6 +89,10 @@ _PROTOS = [
     ("mmd_model_forward", C.c_int,
      [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p,
       C.c_void_p]),
+    ("mmd_model_profile", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int, C.c_void_p]),
+    ("mmd_model_step_info", C.c_int,
+     [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(C.c_double),
+      C.POINTER(C.c_int)]),
     ("mmd_p_sample_tail", C.c_int,
      [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
       C.c_void_p]),

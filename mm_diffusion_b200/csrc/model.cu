@@ -38,6 +38,7 @@ struct PackedConv {
     size_t b_off = 0;     // floats, into packed bias arena
     int n = 0, n_pad = 0, bn = 128;
     long long k_total = 0;
+    int identity_c = 0;   // trailing identity columns (residual folded into the GEMM)
 };
 
 struct Arena {
@@ -51,9 +52,17 @@ struct Arena {
     }
 };
 
+struct StepInfo {
+    std::string kind;     // kernel family tag
+    double flops = 0;     // algorithmic FLOPs (multiply-add = 2)
+    double bytes = 0;     // algorithmic bytes (inputs + outputs + weights, fp16 activations)
+    int kernels = 1;      // kernel launches inside the step
+};
+
 struct Plan {
     int B = 0;
     std::vector<LaunchFn> steps;
+    std::vector<StepInfo> info;
     uint8_t* ws = nullptr;
     size_t ws_bytes = 0;
     float *in_video = nullptr, *in_audio = nullptr, *t_dev = nullptr, *out_video = nullptr, *out_audio = nullptr;
@@ -180,6 +189,7 @@ struct Walker {
         k += identity_c;
         k = std::max(k, min_k);
         pc.k_total = k;
+        pc.identity_c = identity_c;
         pc.w_off = wpk_top;
         wpk_top += (static_cast<size_t>(pc.n_pad) * k + 63) & ~size_t(63);
         pc.b_off = bpk_top;
@@ -218,10 +228,16 @@ struct Walker {
     size_t atok(const AT& a) const { return static_cast<size_t>(B) * a.L; }
     bool emitting() const { return plan != nullptr && persist.base != nullptr; }
 
-    void push(LaunchFn fn) { if (emitting()) plan->steps.push_back(std::move(fn)); }
+    void push(LaunchFn fn, const char* kind, double flops, double bytes, int kernels = 1) {
+        if (!emitting()) return;
+        plan->steps.push_back(std::move(fn));
+        StepInfo si;
+        si.kind = kind; si.flops = flops; si.bytes = bytes; si.kernels = kernels;
+        plan->info.push_back(si);
+    }
 
     // ---------------- emitters
-    void emit_gemm(const ConvGeom& g, const std::vector<std::pair<const act_t*, int>>& srcs,
+    void emit_gemm(const char* tag, const ConvGeom& g, const std::vector<std::pair<const act_t*, int>>& srcs,
                    const std::vector<std::array<int, 3>>& taps, const PackedConv* pc, act_t* out, float* out_f32 = nullptr,
                    const long long* ostride = nullptr, long long ostride_c = 0) {
         if (!emitting() || bad() || !pc) return;
@@ -245,7 +261,11 @@ struct Walker {
         int r = build_gemm(pr, gp.get());
         if (r != MMD_OK) { set_err(r); return; }
         const int bn = pc->bn;
-        push([gp, bn](cudaStream_t st) { return launch_gemm(*gp, bn, st); });
+        const double tokens = static_cast<double>(g.tokens());
+        const double k_alg = static_cast<double>(pc->k_total - pc->identity_c);
+        const double flops = 2.0 * tokens * k_alg * pc->n;
+        const double bytes = 2.0 * (tokens * static_cast<double>(ctot) + tokens * pc->n * (out_f32 ? 2.0 : 1.0) + k_alg * pc->n);
+        push([gp, bn](cudaStream_t st) { return launch_gemm(*gp, bn, st); }, tag, flops, bytes);
     }
     static ConvGeom geom2(long long tokens) { ConvGeom g; g.rank = 2; g.dims[0] = tokens; geom_fill_box(g); return g; }
     ConvGeom geom_spatial(const VT& v) const { ConvGeom g; g.rank = 4; g.dims[0] = v.W; g.dims[1] = v.H; g.dims[2] = static_cast<long long>(B) * F(); geom_fill_box(g); return g; }
@@ -266,7 +286,7 @@ struct Walker {
         push([=](cudaStream_t st) -> int {
             MMD_TRY(launch_gn_stats(s, ns, rows, sums, st));
             return launch_gn_apply(s, ns, rows, sums, gamma, beta, film, film_ld, ns_per_batch, silu, y, st);
-        });
+        }, "group_norm", 0.0, 2.0 * 2.0 * ns * static_cast<double>(rows) * C, 3);
         return y;
     }
 
@@ -279,7 +299,9 @@ struct Walker {
         auto ap = std::make_shared<AttnParams>();
         int r = build_attn(pr, ap.get());
         if (r != MMD_OK) { set_err(r); return; }
-        push([ap, d](cudaStream_t st) { return launch_attn(*ap, d, st); });
+        const double fl = 4.0 * static_cast<double>(q_rows) * (static_cast<double>(win) * k_blk) * d * heads;
+        const double by = 2.0 * (2.0 * q_rows + 2.0 * k_rows) * d * heads;
+        push([ap, d](cudaStream_t st) { return launch_attn(*ap, d, st); }, win == 1 && shift_dev == nullptr && q_blk == k_blk ? "self_attention" : "cross_attention", fl, by);
     }
 
     // ---------------- network pieces
@@ -312,11 +334,12 @@ struct Walker {
                 const float* gamma = pf(gn.g);
                 const float* beta = pf(gn.b);
                 const int Bc = B, Fc = F(), P = vt->H * vt->W;
-                push([=](cudaStream_t st) { return launch_gn_temporal(x, xn, gamma, beta, Bc, Fc, P, C, st); });
+                push([=](cudaStream_t st) { return launch_gn_temporal(x, xn, gamma, beta, Bc, Fc, P, C, st); },
+                     "group_norm", 0.0, 2.0 * 2.0 * static_cast<double>(tokens) * C);
             }
         }
         act_t* qkvb = alloc_s(tokens * 3 * C);
-        emit_gemm(geom2(static_cast<long long>(tokens)), {{xn, C}}, {{0, 0, 0}}, pq, qkvb);
+        emit_gemm("conv1x1_qkv", geom2(static_cast<long long>(tokens)), {{xn, C}}, {{0, 0, 0}}, pq, qkvb);
         act_t* o = alloc_s(tokens * C);
         if (kind == 0) {
             const int hw = vt->H * vt->W;
@@ -325,9 +348,10 @@ struct Walker {
             emit_attn(qkvb, 3 * C, 0, tokens, qkvb, 3 * C, C, tokens, qkvb, 2 * C, o, C, heads, d, 1, at->L, at->L, 1, nullptr);
         } else if (emitting()) {
             const int Bc = B, Fc = F(), P = vt->H * vt->W;
-            push([=](cudaStream_t st) { return launch_temporal_attn(qkvb, o, Bc, Fc, P, C, heads, st); });
+            push([=](cudaStream_t st) { return launch_temporal_attn(qkvb, o, Bc, Fc, P, C, heads, st); },
+                 "temporal_attention", 4.0 * static_cast<double>(tokens) * Fc * C, 2.0 * 4.0 * static_cast<double>(tokens) * C);
         }
-        emit_gemm(geom2(static_cast<long long>(tokens)), {{o, C}, {x, C}}, {{0, 0, 0}}, pp, out);
+        emit_gemm("conv1x1_proj", geom2(static_cast<long long>(tokens)), {{o, C}, {x, C}}, {{0, 0, 0}}, pp, out);
         scratch.top = mark;
         return out;
     }
@@ -398,9 +422,9 @@ struct Walker {
                 VT vin{h0, cin, v.H, v.W};
                 std::vector<std::array<int, 3>> taps9;
                 for (int ky = 0; ky < 3; ++ky) for (int kx = 0; kx < 3; ++kx) taps9.push_back({kx - 1, ky - 1, 0});
-                emit_gemm(geom_spatial(vin), {{h0, cin}}, taps9, p_vsp, u);
+                emit_gemm("conv3x3_spatial", geom_spatial(vin), {{h0, cin}}, taps9, p_vsp, u);
                 act_t* h1 = alloc_s(vtok(v) * cout);
-                emit_gemm(geom_temporal(vin), {{u, cout}}, {{0, -1, 0}, {0, 0, 0}, {0, 1, 0}}, p_vtp, h1);
+                emit_gemm("conv_temporal", geom_temporal(vin), {{u, cout}}, {{0, -1, 0}, {0, 0, 0}, {0, 1, 0}}, p_vtp, h1);
                 const act_t* xs = v.p;   // skip-path input (single source when resampling)
                 if (up || down) {
                     act_t* h1r = alloc_s(static_cast<size_t>(B) * Fr * vo.H * vo.W * cout);
@@ -409,10 +433,11 @@ struct Walker {
                         const int mode = down ? 0 : 2;
                         const int n = B * Fr, H = v.H, W = v.W, c_h = cout, c_x = v.C;
                         const act_t* xin = v.p;
+                        const double elems = static_cast<double>(n) * H * W * (c_h + c_x);
                         push([=](cudaStream_t st) -> int {
                             MMD_TRY(launch_resample(h1, h1r, mode, n, H, W, c_h, st));
                             return launch_resample(xin, xr, mode, n, H, W, c_x, st);
-                        });
+                        }, "resample", 0.0, 2.0 * elems * (down ? 1.25 : 5.0), 2);
                     }
                     h1 = h1r;
                     xs = xr;
@@ -421,7 +446,7 @@ struct Walker {
                 act_t* h2 = emit_gn(h1, cout, nullptr, 0, B, Fr * hwo, vout_gn, film, 1, 1);
                 std::vector<std::pair<const act_t*, int>> srcs = {{h2, cout}, {xs, v.C}};
                 if (v2) srcs.push_back({v2, vc2});
-                emit_gemm(geom2(static_cast<long long>(B) * Fr * hwo), srcs, {{0, 0, 0}}, p_vo, vo.p);
+                emit_gemm("conv1x1_out", geom2(static_cast<long long>(B) * Fr * hwo), srcs, {{0, 0, 0}}, p_vo, vo.p);
                 scratch.top = mark;
             }
             // ---------------- audio branch
@@ -433,7 +458,7 @@ struct Walker {
                 act_t* h0 = emit_gn(a.p, a.C, a2, ac2, B, a.L, ain_gn, nullptr, 1, 1);
                 act_t* h1 = alloc_s(atok(a) * cout);
                 AT ain{h0, cin, a.L};
-                emit_gemm(geom_audio(ain), {{h0, cin}}, {{-dilation, 0, 0}, {0, 0, 0}, {dilation, 0, 0}}, p_ac, h1);
+                emit_gemm("conv_audio_k3", geom_audio(ain), {{h0, cin}}, {{-dilation, 0, 0}, {0, 0, 0}, {dilation, 0, 0}}, p_ac, h1);
                 const act_t* xs = a.p;
                 if (up || down) {
                     act_t* h1r = alloc_s(static_cast<size_t>(B) * ao.L * cout);
@@ -442,10 +467,11 @@ struct Walker {
                         const int mode = down ? 1 : 3;
                         const int n = B, L = a.L, c_h = cout, c_x = a.C;
                         const act_t* xin = a.p;
+                        const double elems = static_cast<double>(n) * L * (c_h + c_x);
                         push([=](cudaStream_t st) -> int {
                             MMD_TRY(launch_resample(h1, h1r, mode, n, L, 1, c_h, st));
                             return launch_resample(xin, xr, mode, n, L, 1, c_x, st);
-                        });
+                        }, "resample", 0.0, 2.0 * elems * (down ? 1.25 : 5.0), 2);
                     }
                     h1 = h1r;
                     xs = xr;
@@ -453,7 +479,7 @@ struct Walker {
                 act_t* h2 = emit_gn(h1, cout, nullptr, 0, B, ao.L, aout_gn, film, 1, 1);
                 std::vector<std::pair<const act_t*, int>> srcs = {{h2, cout}, {xs, a.C}};
                 if (a2) srcs.push_back({a2, ac2});
-                emit_gemm(geom2(static_cast<long long>(B) * ao.L), srcs, {{0, 0, 0}}, p_ao, ao.p);
+                emit_gemm("conv1x1_out", geom2(static_cast<long long>(B) * ao.L), srcs, {{0, 0, 0}}, p_ao, ao.p);
                 scratch.top = mark;
             }
         }
@@ -505,16 +531,16 @@ struct Walker {
         act_t* anrm = emit_gn(a.p, C, nullptr, 0, B, a.L, an, nullptr, 1, 0);
         act_t* vqkv = alloc_s(vt * 3 * C);
         act_t* aqkv = alloc_s(at * 3 * C);
-        emit_gemm(geom2(static_cast<long long>(vt)), {{vnrm, C}}, {{0, 0, 0}}, p_vq, vqkv);
-        emit_gemm(geom2(static_cast<long long>(at)), {{anrm, C}}, {{0, 0, 0}}, p_aq, aqkv);
+        emit_gemm("conv1x1_qkv", geom2(static_cast<long long>(vt)), {{vnrm, C}}, {{0, 0, 0}}, p_vq, vqkv);
+        emit_gemm("conv1x1_qkv", geom2(static_cast<long long>(at)), {{anrm, C}}, {{0, 0, 0}}, p_aq, aqkv);
         act_t* ov = alloc_s(vt * C);
         act_t* oa = alloc_s(at * C);
         const int* sdev = (shift && plan) ? plan->shifts_dev + slot : nullptr;
         // video queries attend audio keys/values and vice versa (multimodal_unet.py:530-559)
         emit_attn(vqkv, 3 * C, 0, vt, aqkv, 3 * C, C, at, aqkv, 2 * C, ov, C, heads, d, Fr, hw, apf, window, sdev);
         emit_attn(aqkv, 3 * C, 0, at, vqkv, 3 * C, C, vt, vqkv, 2 * C, oa, C, heads, d, Fr, apf, hw, window, sdev);
-        emit_gemm(geom2(static_cast<long long>(vt)), {{ov, C}, {v.p, C}}, {{0, 0, 0}}, p_vp, vout);
-        emit_gemm(geom2(static_cast<long long>(at)), {{oa, C}, {a.p, C}}, {{0, 0, 0}}, p_ap, aout);
+        emit_gemm("conv1x1_proj", geom2(static_cast<long long>(vt)), {{ov, C}, {v.p, C}}, {{0, 0, 0}}, p_vp, vout);
+        emit_gemm("conv1x1_proj", geom2(static_cast<long long>(at)), {{oa, C}, {a.p, C}}, {{0, 0, 0}}, p_ap, aout);
         scratch.top = mark;
         v.p = vout;
         a.p = aout;
@@ -555,7 +581,7 @@ struct Walker {
                     emb_layers_kernel<<<(rows + 7) / 8, 256, 0, st>>>(se, ew, eb, Bc, E, rows, ea);
                     MMD_CUDA_OK(cudaGetLastError());
                     return MMD_OK;
-                });
+                }, "time_embed", 2.0 * Bc * (2.0 * E * E + static_cast<double>(rows) * E), 4.0 * (static_cast<double>(rows) * E + 2.0 * E * E), 2);
             }
         }
         // ---- input blocks
@@ -594,11 +620,11 @@ struct Walker {
                         im2col_audio_kernel<<<static_cast<unsigned>((ta + 255) / 256), 256, 0, st>>>(ain, cola, Bc, Ca, L);
                         MMD_CUDA_OK(cudaGetLastError());
                         return MMD_OK;
-                    });
+                    }, "im2col", 0.0, 4.0 * (static_cast<double>(BF) * Cv * H * W + static_cast<double>(Bc) * Ca * L) + 128.0 * (static_cast<double>(BF) * H * W + static_cast<double>(Bc) * L), 2);
                 }
-                emit_gemm(geom2(static_cast<long long>(vtok(v))), {{colv, 64}}, {{0, 0, 0}}, p_sp, u);
-                emit_gemm(geom_temporal(v), {{u, ch}}, {{0, -1, 0}, {0, 0, 0}, {0, 1, 0}}, p_tp, v.p);
-                emit_gemm(geom2(static_cast<long long>(atok(a))), {{cola, 64}}, {{0, 0, 0}}, p_ac, a.p);
+                emit_gemm("conv_stem", geom2(static_cast<long long>(vtok(v))), {{colv, 64}}, {{0, 0, 0}}, p_sp, u);
+                emit_gemm("conv_temporal", geom_temporal(v), {{u, ch}}, {{0, -1, 0}, {0, 0, 0}, {0, 1, 0}}, p_tp, v.p);
+                emit_gemm("conv_stem", geom2(static_cast<long long>(atok(a))), {{cola, 64}}, {{0, 0, 0}}, p_ac, a.p);
                 scratch.top = mark;
             }
             vstack.push_back(v);
@@ -701,11 +727,11 @@ struct Walker {
             for (int kt = 0; kt < 3; ++kt) for (int ky = 0; ky < 3; ++ky) for (int kx = 0; kx < 3; ++kx) taps27.push_back({kx - 1, ky - 1, kt - 1});
             const long long Co = c.video_out_channels, HW = static_cast<long long>(v.H) * v.W;
             const long long os_v[4] = {1, v.W, Co * HW, Fr * Co * HW};
-            emit_gemm(g5, {{hv, ch}}, taps27, p_vh, nullptr, plan ? plan->out_video : nullptr, os_v, HW);
+            emit_gemm("conv_head", g5, {{hv, ch}}, taps27, p_vh, nullptr, plan ? plan->out_video : nullptr, os_v, HW);
             act_t* ha = emit_gn(a.p, ch, nullptr, 0, B, a.L, agn, nullptr, 1, 1);
             const long long Ca = c.audio_out_channels;
             const long long os_a[4] = {1, Ca * a.L, 0, 0};
-            emit_gemm(geom_audio(a), {{ha, ch}}, {{-1, 0, 0}, {0, 0, 0}, {1, 0, 0}}, p_ah, nullptr, plan ? plan->out_audio : nullptr, os_a, a.L);
+            emit_gemm("conv_head", geom_audio(a), {{ha, ch}}, {{-1, 0, 0}, {0, 0, 0}, {1, 0, 0}}, p_ah, nullptr, plan ? plan->out_audio : nullptr, os_a, a.L);
             scratch.top = mark;
         }
         if (create) m.emb_rows = emb_row_top;
@@ -864,6 +890,54 @@ int mmd_model_num_launches(const MmdModel* m, int batch) {
     if (!m) return 0;
     auto it = m->plans.find(batch);
     return it == m->plans.end() ? 0 : static_cast<int>(it->second->steps.size());
+}
+
+// Per-launch device timing of one forward (no graph): fills ms[i] for plan step i with the mean over `reps`
+// back-to-back executions measured with CUDA events on `stream`.  The plan for `batch` must already exist
+// (call mmd_model_forward once first).  Returns the number of steps.
+int mmd_model_profile(MmdModel* m, int batch, int reps, float* ms, int cap, void* stream) {
+    if (!m || !ms) return fail(MMD_EINVAL, "null argument");
+    auto it = m->plans.find(batch);
+    if (it == m->plans.end()) return fail(MMD_ESTATE, "no plan for batch %d yet (run a forward first)", batch);
+    Plan* plan = it->second.get();
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int n = static_cast<int>(plan->steps.size());
+    if (cap < n) return fail(MMD_EINVAL, "profile buffer too small (%d < %d)", cap, n);
+    if (reps < 1) reps = 1;
+    std::vector<cudaEvent_t> ev(n + 1);
+    for (auto& e : ev) MMD_CUDA_OK(cudaEventCreate(&e));
+    for (int i = 0; i < n; ++i) ms[i] = 0.f;
+    int r = MMD_OK;
+    for (int rep = 0; rep < reps && r == MMD_OK; ++rep) {
+        MMD_CUDA_OK(cudaEventRecord(ev[0], st));
+        for (int i = 0; i < n; ++i) {
+            r = plan->steps[i](st);
+            if (r != MMD_OK) break;
+            MMD_CUDA_OK(cudaEventRecord(ev[i + 1], st));
+        }
+        MMD_CUDA_OK(cudaStreamSynchronize(st));
+        for (int i = 0; i < n && r == MMD_OK; ++i) {
+            float t = 0.f;
+            MMD_CUDA_OK(cudaEventElapsedTime(&t, ev[i], ev[i + 1]));
+            ms[i] += t / reps;
+        }
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    return r == MMD_OK ? n : r;
+}
+
+int mmd_model_step_info(const MmdModel* m, int batch, int index, const char** kind, double* flops, double* bytes, int* kernels) {
+    if (!m) return fail(MMD_EINVAL, "null argument");
+    auto it = m->plans.find(batch);
+    if (it == m->plans.end()) return fail(MMD_ESTATE, "no plan for batch %d", batch);
+    const Plan* plan = it->second.get();
+    if (index < 0 || index >= static_cast<int>(plan->info.size())) return fail(MMD_EINVAL, "step index %d", index);
+    const StepInfo& si = plan->info[index];
+    if (kind) *kind = si.kind.c_str();
+    if (flops) *flops = si.flops;
+    if (bytes) *bytes = si.bytes;
+    if (kernels) *kernels = si.kernels;
+    return MMD_OK;
 }
 
 int mmd_model_forward(MmdModel* m, int batch, const float* video_in, const float* audio_in, const float* timesteps,

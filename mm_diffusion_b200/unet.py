@@ -249,7 +249,36 @@ class MultimodalUNet(nn.Module):
         return [random.randint(0, b) if b >= 0 else 0 for b in self._shift_bounds]
 
     def num_launches(self, batch: int) -> int:
-        return 0 if self._handle is None else _lib.load().mmd_model_num_launches(self._handle, batch)
+        """Kernel launches of one forward at this batch size (0 until the plan has been built by a forward)."""
+        return sum(s["kernels"] for s in self.plan_steps(batch))
+
+    def plan_steps(self, batch: int):
+        """[{kind, flops, bytes, kernels}] of the launch plan (algorithmic work per step)."""
+        if self._handle is None:
+            return []
+        lib = _lib.load()
+        n = lib.mmd_model_num_launches(self._handle, batch)
+        out = []
+        kind = C.c_char_p()
+        fl, by, nk = C.c_double(), C.c_double(), C.c_int()
+        for i in range(n):
+            check(lib.mmd_model_step_info(self._handle, batch, i, C.byref(kind), C.byref(fl), C.byref(by), C.byref(nk)))
+            out.append({"kind": kind.value.decode(), "flops": fl.value, "bytes": by.value, "kernels": nk.value})
+        return out
+
+    def profile(self, batch: int, reps: int = 3):
+        """Per-step device time (ms, CUDA events on the current stream, un-graphed) of the plan for `batch`."""
+        steps = self.plan_steps(batch)
+        if not steps:
+            raise MmdError("profile(): run a forward at this batch size first")
+        buf = (C.c_float * len(steps))()
+        with torch.cuda.device(self._handle_device):
+            r = _lib.load().mmd_model_profile(self._handle, batch, reps, buf, len(steps), _lib.current_stream_ptr())
+        if r < 0:
+            check(r)
+        for s, ms in zip(steps, buf):
+            s["ms"] = float(ms)
+        return steps
 
     # ------------------------------------------------------------------ forward
     def forward(self, video, audio, timesteps, label=None, shifts: Sequence[int] = None):

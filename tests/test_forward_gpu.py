@@ -53,7 +53,12 @@ def test_forward_batch_independence_small():
     with torch.no_grad():
         ev, ea = model(v, a, t, shifts=shifts)
         e1v, e1a = model(v[1:2], a[1:2], t[1:2], shifts=shifts)
-    assert torch.equal(ev[1:2], e1v) and torch.equal(ea[1:2], e1a)  # batch-shardable: samples do not interact
+    # batch-shardable: samples do not interact.  Not bit-identical across batch sizes: the GroupNorm partial sums are
+    # split differently (fp32 partials, double accumulation), which can flip single fp16 roundings downstream.
+    assert rel_l2(ev[1:2], e1v) < 2e-3 and rel_l2(ea[1:2], e1a) < 2e-3
+    with torch.no_grad():
+        e2v, e2a = model(v, a, t, shifts=shifts)
+    assert rel_l2(e2v, ev) < 1e-4 and rel_l2(e2a, ea) < 1e-4  # same batch, replayed graph
 
 
 def test_forward_production_vs_reference_golden():
