@@ -1,0 +1,44 @@
+"""Batch-shard helpers for multi-GPU sampling (one process per GPU, torch.distributed).
+
+The denoising path has no exchange inside a step: every rank holds a full weight replica and runs the
+whole loop on its slice of the batch; the only collective is the gather of finished samples, which replaces the
+per-rank file writes + barrier of the reference's sample script (py_scripts/multimodal_sample_sr.py:174-183,258) and
+the all_gather in TrainLoop.save_video (mm_diffusion/multimodal_train_util.py:424-431)."""
+from __future__ import annotations
+
+from typing import Dict, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(global_batch: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous slice [lo, hi) of the global batch owned by `rank` (sizes differ by at most one)."""
+    base, extra = divmod(global_batch, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def rank_seed(base_seed: int, rank: int) -> int:
+    """Independent RNG stream per rank (x_T, per-step noise, window shifts)."""
+    return base_seed + 1000003 * rank
+
+
+def to_uint8_video(video: torch.Tensor) -> torch.Tensor:
+    """[-1,1] float video -> uint8, the conversion of multimodal_sample_sr.py:159-161."""
+    return ((video + 1) * 127.5).clamp(0, 255).to(torch.uint8)
+
+
+def gather_samples(sample: Dict[str, torch.Tensor], group=None) -> Dict[str, torch.Tensor]:
+    """All ranks receive every rank's finished samples concatenated in rank order: uint8 video + fp32 audio
+    (≈0.3 MB per sample).  Equal per-rank batch sizes are required (weak scaling: fixed batch per GPU)."""
+    video = to_uint8_video(sample["video"]).contiguous()
+    audio = sample["audio"].float().contiguous()
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return {"video": video, "audio": audio}
+    world = dist.get_world_size(group)
+    gv = torch.empty((world * video.shape[0],) + tuple(video.shape[1:]), dtype=video.dtype, device=video.device)
+    ga = torch.empty((world * audio.shape[0],) + tuple(audio.shape[1:]), dtype=audio.dtype, device=audio.device)
+    dist.all_gather_into_tensor(gv, video, group=group)
+    dist.all_gather_into_tensor(ga, audio, group=group)
+    return {"video": gv, "audio": ga}
