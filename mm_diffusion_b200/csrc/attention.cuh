@@ -76,6 +76,16 @@ MMD_DEVINL void attn_tile(const AttnWork& w, int t, int& row, int& valid) {
     }
 }
 
+// D = 64 runs two CTAs per SM (one S buffer, one V stage, 256 TMEM columns): the second CTA's MMAs fill the
+// tensor pipe while the first is in its softmax.  D = 96 / 128 keep the deeper single-CTA configuration.
+template <int D>
+struct AttnCfg {
+    static constexpr int SBUF = (D == 64) ? 1 : 2;      // S accumulators in TMEM
+    static constexpr int VST = (D == 64) ? 1 : 2;       // V stages in shared memory
+    static constexpr int TMEM_COLS = (D == 64) ? 256 : 512;
+    static constexpr int O_COL = SBUF * 128;            // TMEM column of the O tile
+};
+
 template <int D>
 struct AttnSmem {
     static constexpr int NCH = (D + 63) / 64;          // 64-column boxes per operand tile
@@ -83,15 +93,24 @@ struct AttnSmem {
     static constexpr int Q_OFF = 0;
     static constexpr int K_OFF = TILE;
     static constexpr int V_OFF = K_OFF + 2 * TILE;
-    static constexpr int P_OFF = V_OFF + 2 * TILE;
+    static constexpr int P_OFF = V_OFF + AttnCfg<D>::VST * TILE;
     static constexpr int P_BYTES = 2 * ATT_BQ * 128;
     static constexpr int BAR_OFF = P_OFF + P_BYTES;
     static constexpr int TOTAL = BAR_OFF + 256 + 1024;
 };
 
+MMD_DEVINL float ex2_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 template <int D>
-__global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_constant__ AttnParams p) {
+__global__ void __launch_bounds__(ATT_THREADS, (D == 64) ? 2 : 1) attention_kernel(const __grid_constant__ AttnParams p) {
     using S = AttnSmem<D>;
+    using Cfg = AttnCfg<D>;
+    constexpr int SBUF = Cfg::SBUF;
+    constexpr int VST = Cfg::VST;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
@@ -126,13 +145,13 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
         mbar_init(o_full, 1);
         fence_mbar_init();
     }
-    if (warp == 5) tmem_alloc(tmem_slot, 512);
+    if (warp == 5) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_S = tmem_base;        // two 128-column buffers
-    const uint32_t tmem_O = tmem_base + 256;  // D columns
+    const uint32_t tmem_S = tmem_base;                // SBUF 128-column buffers
+    const uint32_t tmem_O = tmem_base + Cfg::O_COL;   // D columns
 
     if (warp == 4) {
         // ===================== TMA producer =====================
@@ -151,10 +170,12 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
                 for (int ch = 0; ch < S::NCH; ++ch)
                     tma_load_2d(smem + S::K_OFF + st * S::TILE + ch * (ATT_BKV * 128), &p.k_map, &k_full[st],
                                 p.k_col0 + w.head * D + ch * 64, krow);
-                mbar_wait(&v_empty[st], ph ^ 1);
-                mbar_expect_tx(&v_full[st], S::TILE);
+                const int vs = (VST == 2) ? st : 0;
+                const uint32_t vph = (VST == 2) ? ph : static_cast<uint32_t>(t & 1);
+                mbar_wait(&v_empty[vs], vph ^ 1);
+                mbar_expect_tx(&v_full[vs], S::TILE);
                 for (int ch = 0; ch < S::NCH; ++ch)
-                    tma_load_2d(smem + S::V_OFF + st * S::TILE + ch * (ATT_BKV * 128), &p.v_map, &v_full[st],
+                    tma_load_2d(smem + S::V_OFF + vs * S::TILE + ch * (ATT_BKV * 128), &p.v_map, &v_full[vs],
                                 p.v_col0 + w.head * D + ch * 64, krow);
             }
         }
@@ -172,35 +193,39 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
                 tc_fence_after();
                 const uint32_t k_addr = smem_u32(smem + S::K_OFF + st * S::TILE);
 #pragma unroll
+                const int sb = (SBUF == 2) ? st : 0;
                 for (int ks = 0; ks < D / 16; ++ks) {
                     const uint32_t off = (ks >> 2) * (ATT_BQ * 128) + (ks & 3) * 32;
-                    umma_f16_ss(tmem_S + st * 128, umma_desc_sw128(q_addr + off, 16, 1024),
+                    umma_f16_ss(tmem_S + sb * 128, umma_desc_sw128(q_addr + off, 16, 1024),
                                 umma_desc_sw128(k_addr + off, 16, 1024), idesc_qk, ks != 0 ? 1u : 0u);
                 }
                 umma_commit(&k_empty[st]);
-                umma_commit(&s_full[st]);
+                umma_commit(&s_full[sb]);
             };
             mbar_wait(q_full, 0);
             tc_fence_after();
             issue_qk(0);
             for (int t = 0; t < T; ++t) {
-                if (t + 1 < T) issue_qk(t + 1);
+                if (SBUF == 2 && t + 1 < T) issue_qk(t + 1);   // look-ahead into the other S buffer
                 const int st = t & 1;
                 const uint32_t ph = (t >> 1) & 1;
+                const int vs = (VST == 2) ? st : 0;
+                const uint32_t vph = (VST == 2) ? ph : static_cast<uint32_t>(t & 1);
                 int krow, kvalid;
                 attn_tile(w, t, krow, kvalid);
-                mbar_wait(p_ready, t & 1);
-                mbar_wait(&v_full[st], ph);
+                mbar_wait(p_ready, t & 1);       // softmax t is done with S (and P is written)
+                mbar_wait(&v_full[vs], vph);
                 tc_fence_after();
-                const uint32_t v_addr = smem_u32(smem + S::V_OFF + st * S::TILE);
+                const uint32_t v_addr = smem_u32(smem + S::V_OFF + vs * S::TILE);
                 const int nks = (kvalid + 15) >> 4;
                 for (int ks = 0; ks < nks; ++ks) {
                     const uint32_t poff = (ks >> 2) * (ATT_BQ * 128) + (ks & 3) * 32;
                     umma_f16_ss(tmem_O, umma_desc_sw128(p_addr + poff, 16, 1024),
                                 umma_desc_sw128(v_addr + ks * 2048, ATT_BKV * 128, 1024), idesc_pv, ks != 0 ? 1u : 0u);
                 }
-                umma_commit(&v_empty[st]);
+                umma_commit(&v_empty[vs]);
                 umma_commit(o_full);
+                if (SBUF == 1 && t + 1 < T) issue_qk(t + 1);   // single S buffer: next logits after this tile's PV
             }
         }
     } else {
@@ -215,26 +240,41 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
         float alpha_prev = 1.f;
         uint8_t* p_smem = smem + S::P_OFF;
         for (int t = 0; t < T; ++t) {
-            const int st = t & 1;
+            const int sb = (SBUF == 2) ? (t & 1) : 0;
+            const uint32_t sph = (SBUF == 2) ? ((t >> 1) & 1) : (t & 1);
             int krow, kvalid;
             attn_tile(w, t, krow, kvalid);
-            mbar_wait(&s_full[st], (t >> 1) & 1);
+            mbar_wait(&s_full[sb], sph);
             tc_fence_after();
-            const uint32_t s_addr = tmem_S + st * 128 + lane_base;
-            // pass 1: row max
+            const uint32_t s_addr = tmem_S + sb * 128 + lane_base;
+            const bool full_tile = (kvalid == ATT_BKV);
+            float psum = 0.f;
+            float m_new, alpha;
+            // pass 1: row max (logits stay in TMEM; the read bandwidth is not the limiter)
             float mx = -INFINITY;
+            if (full_tile) {
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                if (c * 32 >= kvalid) break;
-                uint32_t v[32];
-                tmem_ld32(s_addr + c * 32, v);
-                tmem_ld_wait();
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t v[32];
+                    tmem_ld32(s_addr + c * 32, v);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (c * 32 + i < kvalid) mx = fmaxf(mx, __uint_as_float(v[i]));
+                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+                }
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    if (c * 32 >= kvalid) break;
+                    uint32_t v[32];
+                    tmem_ld32(s_addr + c * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (c * 32 + i < kvalid) mx = fmaxf(mx, __uint_as_float(v[i]));
+                }
             }
-            const float m_new = fmaxf(m_run, mx * p.scale_log2);
-            const float alpha = exp2f(m_run - m_new);  // first tile: exp2(-inf) = 0
+            m_new = fmaxf(m_run, mx * p.scale_log2);
+            alpha = ex2_fast(m_run - m_new);  // first tile: exp2(-inf) = 0
             // fold in the previous tile's PV result (also proves P / O buffers are free again)
             if (t > 0) {
                 mbar_wait(o_full, (t - 1) & 1);
@@ -249,11 +289,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
                 }
             }
             // pass 2: probabilities -> smem (K-major SW128, two 64-key chunks), row sum
-            float psum = 0.f;
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
                 uint32_t v[32];
-                if (c * 32 < kvalid) {
+                const bool live = full_tile || (c * 32 < kvalid);
+                if (live) {
                     tmem_ld32(s_addr + c * 32, v);
                     tmem_ld_wait();
                 }
@@ -266,12 +306,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
                     for (int k = 0; k < 4; ++k) {
                         const int col = c * 32 + j * 8 + 2 * k;
                         float e0 = 0.f, e1 = 0.f;
-                        if (col < kvalid) e0 = exp2f(__uint_as_float(v[j * 8 + 2 * k]) * p.scale_log2 - m_new);
-                        if (col + 1 < kvalid) e1 = exp2f(__uint_as_float(v[j * 8 + 2 * k + 1]) * p.scale_log2 - m_new);
+                        if (full_tile || col < kvalid) e0 = ex2_fast(fmaf(__uint_as_float(v[j * 8 + 2 * k]), p.scale_log2, -m_new));
+                        if (full_tile || col + 1 < kvalid) e1 = ex2_fast(fmaf(__uint_as_float(v[j * 8 + 2 * k + 1]), p.scale_log2, -m_new));
+                        psum += e0 + e1;
                         const __half2 h = __floats2half2_rn(e0, e1);
-                        // accumulate the rounded values so the normaliser matches what the MMA sees
-                        const float2 hr = __half22float2(h);
-                        psum += hr.x + hr.y;
                         pw[k] = *reinterpret_cast<const uint32_t*>(&h);
                     }
                     *reinterpret_cast<uint4*>(chunk + sw128_off(row, (c & 1) * 4 + j)) = pk;
@@ -316,7 +354,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_kernel(const __grid_
     __syncthreads();
     if (warp == 5) {
         __syncwarp();
-        tmem_dealloc(tmem_base, 512);
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
 }
 

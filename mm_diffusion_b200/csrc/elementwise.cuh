@@ -20,7 +20,17 @@ struct GnSrc {
     const act_t* x2; int c2; int ld2;
 };
 
-__global__ void gn_stats_kernel(GnSrc s, int R, int rows_per_block, double* __restrict__ sums) {
+// SiLU through one MUFU op: x * sigmoid(x) = 0.5 x (1 + tanh(x/2)); tanh.approx.f32 abs error ~5e-4, i.e. below
+// the fp16 rounding of the stored result.
+MMD_DEVINL float silu_fast(float x) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+    return 0.5f * x * (1.0f + t);
+}
+
+constexpr int GN_UNROLL = 4;
+
+__global__ void __launch_bounds__(256) gn_stats_kernel(GnSrc s, int R, int rows_per_block, double* __restrict__ sums) {
     const int C = s.c1 + s.c2;
     const int cpg = C / 32;
     const int vpr = C / 8;  // 16-byte vectors per row
@@ -33,30 +43,48 @@ __global__ void gn_stats_kernel(GnSrc s, int R, int rows_per_block, double* __re
     __shared__ float sh[64];
     if (threadIdx.x < 64) sh[threadIdx.x] = 0.f;
     __syncthreads();
-    float sm[8], sq[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { sm[i] = 0.f; sq[i] = 0.f; }
     if (rsub < rows_per_pass) {
+        float sm[8], sq[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { sm[i] = 0.f; sq[i] = 0.f; }
         const int c0 = vec * 8;
         const act_t* base;
-        int ld, cc;
-        if (c0 < s.c1) { base = s.x1; ld = s.ld1; cc = c0; } else { base = s.x2; ld = s.ld2; cc = c0 - s.c1; }
-        for (int r = r0 + rsub; r < r1; r += rows_per_pass) {
-            const uint4 raw = __ldg(reinterpret_cast<const uint4*>(base + (static_cast<size_t>(ns) * R + r) * ld + cc));
-            const __half2* h = reinterpret_cast<const __half2*>(&raw);
+        int ld;
+        if (c0 < s.c1) { base = s.x1 + c0; ld = s.ld1; } else { base = s.x2 + (c0 - s.c1); ld = s.ld2; }
+        base += static_cast<size_t>(ns) * R * ld;
+        for (int r = r0 + rsub; r < r1; r += GN_UNROLL * rows_per_pass) {
+            uint4 raw[GN_UNROLL];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float2 f = __half22float2(h[i]);
-                sm[2 * i] += f.x; sq[2 * i] += f.x * f.x;
-                sm[2 * i + 1] += f.y; sq[2 * i + 1] += f.y * f.y;
+            for (int u = 0; u < GN_UNROLL; ++u) {
+                const int rr = r + u * rows_per_pass;
+                raw[u] = (rr < r1) ? __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(rr) * ld)) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < GN_UNROLL; ++u) {
+                const __half2* h = reinterpret_cast<const __half2*>(&raw[u]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 f = __half22float2(h[i]);
+                    sm[2 * i] += f.x; sq[2 * i] = fmaf(f.x, f.x, sq[2 * i]);
+                    sm[2 * i + 1] += f.y; sq[2 * i + 1] = fmaf(f.y, f.y, sq[2 * i + 1]);
+                }
             }
         }
+        // fold the 8 channels into their (<= 4) groups before touching shared memory
+        int g = c0 / cpg;
+        float as = 0.f, aq = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const int g = (c0 + i) / cpg;
-            atomicAdd(&sh[2 * g], sm[i]);
-            atomicAdd(&sh[2 * g + 1], sq[i]);
+            const int gi = (c0 + i) / cpg;
+            if (gi != g) {
+                atomicAdd(&sh[2 * g], as);
+                atomicAdd(&sh[2 * g + 1], aq);
+                g = gi; as = 0.f; aq = 0.f;
+            }
+            as += sm[i]; aq += sq[i];
         }
+        atomicAdd(&sh[2 * g], as);
+        atomicAdd(&sh[2 * g + 1], aq);
     }
     __syncthreads();
     if (threadIdx.x < 64) atomicAdd(&sums[static_cast<size_t>(ns) * 64 + threadIdx.x], static_cast<double>(sh[threadIdx.x]));
@@ -69,26 +97,29 @@ __global__ void gn_stats_kernel(GnSrc s, int R, int rows_per_block, double* __re
 // film points at [B][film_ld] floats with scale at [0,C) and shift at [C,2C)
 // (th.chunk order, multimodal_unet.py:462,468).
 // ---------------------------------------------------------------------------
-__global__ void gn_apply_kernel(GnSrc s, int R, int rows_per_block, const double* __restrict__ sums,
+__global__ void __launch_bounds__(256) gn_apply_kernel(GnSrc s, int R, int rows_per_block, const double* __restrict__ sums,
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 const float* __restrict__ film, int film_ld, int ns_per_batch, int do_silu,
                                 act_t* __restrict__ y) {
-    extern __shared__ float coef[];  // [2][C]
+    extern __shared__ float coef[];  // [2][C] then [64] group mean / rstd
     const int C = s.c1 + s.c2;
     const int cpg = C / 32;
     const int vpr = C / 8;
     const int ns = blockIdx.y;
-    const double inv_n = 1.0 / (static_cast<double>(R) * cpg);
+    float* gstat = coef + 2 * C;
+    if (threadIdx.x < 32) {  // the only double-precision arithmetic: 32 groups
+        const double inv_n = 1.0 / (static_cast<double>(R) * cpg);
+        const double mean = sums[static_cast<size_t>(ns) * 64 + 2 * threadIdx.x] * inv_n;
+        double var = sums[static_cast<size_t>(ns) * 64 + 2 * threadIdx.x + 1] * inv_n - mean * mean;
+        if (var < 0) var = 0;
+        gstat[2 * threadIdx.x] = static_cast<float>(mean);
+        gstat[2 * threadIdx.x + 1] = rsqrtf(static_cast<float>(var) + 1e-5f);
+    }
+    __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const int g = c / cpg;
-        const double su = sums[static_cast<size_t>(ns) * 64 + 2 * g];
-        const double ss = sums[static_cast<size_t>(ns) * 64 + 2 * g + 1];
-        const double mean = su * inv_n;
-        double var = ss * inv_n - mean * mean;
-        if (var < 0) var = 0;
-        const float rstd = static_cast<float>(1.0 / sqrt(var + 1e-5));
-        float a = rstd * gamma[c];
-        float b = beta[c] - static_cast<float>(mean) * a;
+        float a = gstat[2 * g + 1] * gamma[c];
+        float b = beta[c] - gstat[2 * g] * a;
         if (film != nullptr) {
             const float* fb = film + static_cast<size_t>(ns / ns_per_batch) * film_ld;
             const float sc = 1.f + fb[c];
@@ -99,27 +130,45 @@ __global__ void gn_apply_kernel(GnSrc s, int R, int rows_per_block, const double
         coef[C + c] = b;
     }
     __syncthreads();
+    const int rows_per_pass = blockDim.x / vpr;
+    const int vec = threadIdx.x % vpr;
+    const int rsub = threadIdx.x / vpr;
+    if (rsub >= rows_per_pass) return;
     const int r0 = blockIdx.x * rows_per_block;
     const int r1 = min(R, r0 + rows_per_block);
-    const int total = (r1 - r0) * vpr;
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const int r = r0 + i / vpr;
-        const int c0 = (i % vpr) * 8;
-        const act_t* src = (c0 < s.c1) ? s.x1 + (static_cast<size_t>(ns) * R + r) * s.ld1 + c0
-                                       : s.x2 + (static_cast<size_t>(ns) * R + r) * s.ld2 + (c0 - s.c1);
-        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(src));
-        const __half2* h = reinterpret_cast<const __half2*>(&raw);
-        uint4 outv;
-        __half2* o = reinterpret_cast<__half2*>(&outv);
+    const int c0 = vec * 8;
+    const act_t* base;
+    int ld;
+    if (c0 < s.c1) { base = s.x1 + c0; ld = s.ld1; } else { base = s.x2 + (c0 - s.c1); ld = s.ld2; }
+    base += static_cast<size_t>(ns) * R * ld;
+    act_t* ybase = y + static_cast<size_t>(ns) * R * C + c0;
+    float ca[8], cb[8];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float2 f = __half22float2(h[k]);
-            float u0 = f.x * coef[c0 + 2 * k] + coef[C + c0 + 2 * k];
-            float u1 = f.y * coef[c0 + 2 * k + 1] + coef[C + c0 + 2 * k + 1];
-            if (do_silu) { u0 = silu_f(u0); u1 = silu_f(u1); }
-            o[k] = __floats2half2_rn(u0, u1);
+    for (int i = 0; i < 8; ++i) { ca[i] = coef[c0 + i]; cb[i] = coef[C + c0 + i]; }
+    for (int r = r0 + rsub; r < r1; r += GN_UNROLL * rows_per_pass) {
+        uint4 raw[GN_UNROLL];
+#pragma unroll
+        for (int u = 0; u < GN_UNROLL; ++u) {
+            const int rr = r + u * rows_per_pass;
+            if (rr < r1) raw[u] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(rr) * ld));
         }
-        *reinterpret_cast<uint4*>(y + (static_cast<size_t>(ns) * R + r) * C + c0) = outv;
+#pragma unroll
+        for (int u = 0; u < GN_UNROLL; ++u) {
+            const int rr = r + u * rows_per_pass;
+            if (rr >= r1) break;
+            const __half2* h = reinterpret_cast<const __half2*>(&raw[u]);
+            uint4 outv;
+            __half2* o = reinterpret_cast<__half2*>(&outv);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 f = __half22float2(h[k]);
+                float u0 = fmaf(f.x, ca[2 * k], cb[2 * k]);
+                float u1 = fmaf(f.y, ca[2 * k + 1], cb[2 * k + 1]);
+                if (do_silu) { u0 = silu_fast(u0); u1 = silu_fast(u1); }
+                o[k] = __floats2half2_rn(u0, u1);
+            }
+            *reinterpret_cast<uint4*>(ybase + static_cast<size_t>(rr) * C) = outv;
+        }
     }
 }
 
@@ -343,95 +392,138 @@ __global__ void emb_layers_kernel(const float* __restrict__ silu_emb, const floa
 }
 
 // ---------------------------------------------------------------------------
-// Temporal self-attention core: sequences of F (<=16) tokens per (sample, pixel), heads
-// of width d = C/heads (SingleModalQKVAttention, multimodal_unet.py:221-240; fp32 softmax).
+// Temporal self-attention core: sequences of F (8 or 16) tokens per (sample, pixel), heads of width
+// d = C/heads (SingleModalQKVAttention, multimodal_unet.py:221-240; fp32 softmax).
 // qkv: [B][F][P][3C] (q | k | v on channels, head h = channels [h*d,(h+1)*d)), out: [B][F][P][C].
-// One warp per (b, p, head); bandwidth-bound (8 FLOP/B).
+// Bandwidth-bound (8 FLOP/B): one warp per (b, pixel, head); rows are staged with
+// cp.async, the two 16x16 products run on mma.sync.m16n8k16 (legacy tensor path is plenty here:
+// the kernel moves ~4C*2 bytes per token and does 64*C FLOPs per token).
 // ---------------------------------------------------------------------------
+MMD_DEVINL void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+MMD_DEVINL void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+MMD_DEVINL void mma_16816(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+MMD_DEVINL void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+MMD_DEVINL uint32_t pack_h2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+constexpr int TATT_WARPS = 4;
+
 template <int F_>
-__global__ void temporal_attn_kernel(const act_t* __restrict__ qkv, act_t* __restrict__ out, int B, int P, int C,
-                                     int heads) {
+__global__ void __launch_bounds__(TATT_WARPS * 32) temporal_attn_kernel(const act_t* __restrict__ qkv, act_t* __restrict__ out,
+                                                                         int B, int P, int C, int heads) {
     extern __shared__ __align__(16) uint8_t tsm[];
     const int d = C / heads;
-    const int wpb = blockDim.x >> 5;
+    const int pitch = d + 8;  // halves; 16-byte aligned rows, conflict-free ldmatrix
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long item = static_cast<long long>(blockIdx.x) * wpb + warp;
-    const long long total = static_cast<long long>(B) * P * heads;
-    // per-warp smem: q,k,v [F][d] half + P [F][F] float
-    const size_t per_warp = static_cast<size_t>(3) * F_ * d * sizeof(act_t) + F_ * F_ * sizeof(float);
-    uint8_t* mine = tsm + warp * per_warp;
-    act_t* sq = reinterpret_cast<act_t*>(mine);
-    act_t* sk = sq + F_ * d;
-    act_t* sv = sk + F_ * d;
-    float* sp = reinterpret_cast<float*>(sv + F_ * d);
-    if (item >= total) return;
-    const int h = static_cast<int>(item % heads);
-    const long long bp = item / heads;
-    const int p = static_cast<int>(bp % P);
-    const int b = static_cast<int>(bp / P);
+    act_t* sq = reinterpret_cast<act_t*>(tsm) + static_cast<size_t>(warp) * 3 * 16 * pitch;
+    act_t* sk = sq + 16 * pitch;
+    act_t* sv = sk + 16 * pitch;
+    if (F_ < 16) {  // rows F_..15 of the 16-row tiles stay zero
+        for (int i = lane; i < 3 * 16 * pitch / 8; i += 32) reinterpret_cast<uint4*>(sq)[i] = make_uint4(0, 0, 0, 0);
+        __syncwarp();
+    }
     const int vpr = d / 8;
-    for (int i = lane; i < 3 * F_ * vpr; i += 32) {
-        const int m = i / (F_ * vpr);
-        const int rem = i % (F_ * vpr);
-        const int f = rem / vpr, v = rem % vpr;
-        const act_t* src = qkv + ((static_cast<size_t>(b) * F_ + f) * P + p) * (3 * C) + m * C + h * d + v * 8;
-        reinterpret_cast<uint4*>(sq + m * F_ * d)[f * vpr + v] = __ldg(reinterpret_cast<const uint4*>(src));
-    }
-    __syncwarp();
-    const float scale = rsqrtf(static_cast<float>(d));
-    // scores: lane -> (i = lane % F_, j block = lane / F_)
-    constexpr int JB = 32 / F_;       // lanes per query row
-    constexpr int JPL = F_ / JB;      // keys per lane
-    const int qi = lane % F_, jb = lane / F_;
-    float sc[JPL];
-    float mx = -INFINITY;
-#pragma unroll
-    for (int jj = 0; jj < JPL; ++jj) {
-        const int j = jb * JPL + jj;
-        float acc = 0.f;
-        const __half2* qr = reinterpret_cast<const __half2*>(sq + qi * d);
-        const __half2* kr = reinterpret_cast<const __half2*>(sk + j * d);
-        for (int c = 0; c < d / 2; ++c) {
-            const float2 a = __half22float2(qr[c]);
-            const float2 bb = __half22float2(kr[c]);
-            acc += a.x * bb.x + a.y * bb.y;
+    const long long total = static_cast<long long>(B) * P * heads;
+    const float scale_log2 = 1.4426950408889634f * rsqrtf(static_cast<float>(d));
+    const uint32_t sq_a = smem_u32(sq), sk_a = smem_u32(sk), sv_a = smem_u32(sv);
+    for (long long item = static_cast<long long>(blockIdx.x) * TATT_WARPS + warp; item < total;
+         item += static_cast<long long>(gridDim.x) * TATT_WARPS) {
+        const int h = static_cast<int>(item % heads);
+        const long long bp = item / heads;
+        const int p = static_cast<int>(bp % P);
+        const int b = static_cast<int>(bp / P);
+        for (int i = lane; i < 3 * F_ * vpr; i += 32) {
+            const int m = i / (F_ * vpr);
+            const int rem = i - m * (F_ * vpr);
+            const int f = rem / vpr, v = rem - f * vpr;
+            const act_t* src = qkv + ((static_cast<size_t>(b) * F_ + f) * P + p) * (3 * static_cast<size_t>(C)) + m * C + h * d + v * 8;
+            cp_async16(sq_a + ((m * 16 + f) * pitch + v * 8) * 2, src);
         }
-        sc[jj] = acc * scale;
-        mx = fmaxf(mx, sc[jj]);
-    }
-#pragma unroll
-    for (int o = F_; o < 32; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    float sum = 0.f;
-#pragma unroll
-    for (int jj = 0; jj < JPL; ++jj) { sc[jj] = __expf(sc[jj] - mx); sum += sc[jj]; }
-#pragma unroll
-    for (int o = F_; o < 32; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float inv = 1.f / sum;
-#pragma unroll
-    for (int jj = 0; jj < JPL; ++jj) sp[qi * F_ + jb * JPL + jj] = sc[jj] * inv;
-    __syncwarp();
-    // output: each lane produces 8-channel vectors of (row i, vector v)
-    for (int i = lane; i < F_ * vpr; i += 32) {
-        const int f = i / vpr, v = i % vpr;
-        float acc[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-        for (int j = 0; j < F_; ++j) {
-            const float pw = sp[f * F_ + j];
-            const uint4 raw = reinterpret_cast<const uint4*>(sv + j * d)[v];
-            const __half2* hv = reinterpret_cast<const __half2*>(&raw);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float2 vv = __half22float2(hv[k]);
-                acc[2 * k] += pw * vv.x;
-                acc[2 * k + 1] += pw * vv.y;
-            }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        // ---- S = Q K^T (16 x 16, two n-tiles of 8 keys)
+        float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+        const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int lcol = (lane >> 4) * 8;
+        const int krow = (lane & 7) + (lane >> 4) * 8;
+        const int kcol = ((lane >> 3) & 1) * 8;
+        for (int k0 = 0; k0 < d; k0 += 16) {
+            uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
+            ldmatrix_x4(sq_a + (lrow * pitch + k0 + lcol) * 2, a0, a1, a2, a3);
+            ldmatrix_x4(sk_a + (krow * pitch + k0 + kcol) * 2, b0, b1, b2, b3);
+            mma_16816(s0, a0, a1, a2, a3, b0, b1);
+            mma_16816(s1, a0, a1, a2, a3, b2, b3);
         }
-        uint4 o;
-        __half2* oh = reinterpret_cast<__half2*>(&o);
+        // ---- softmax over the 16 keys of rows (lane/4) and (lane/4 + 8)
+        const int c0 = (lane & 3) * 2;
+        float pr[2][4];  // [n-tile][c0..c3]
 #pragma unroll
-        for (int k = 0; k < 4; ++k) oh[k] = __floats2half2_rn(acc[2 * k], acc[2 * k + 1]);
-        *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(b) * F_ + f) * P + p) * C + h * d + v * 8) = o;
+        for (int j = 0; j < 4; ++j) { pr[0][j] = s0[j]; pr[1][j] = s1[j]; }
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (t * 8 + c0 + (j & 1) >= F_) pr[t][j] = -INFINITY;
+        float mx0 = fmaxf(fmaxf(pr[0][0], pr[0][1]), fmaxf(pr[1][0], pr[1][1]));
+        float mx1 = fmaxf(fmaxf(pr[0][2], pr[0][3]), fmaxf(pr[1][2], pr[1][3]));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            pr[t][0] = exp2f((pr[t][0] - mx0) * scale_log2); pr[t][1] = exp2f((pr[t][1] - mx0) * scale_log2);
+            pr[t][2] = exp2f((pr[t][2] - mx1) * scale_log2); pr[t][3] = exp2f((pr[t][3] - mx1) * scale_log2);
+            sum0 += pr[t][0] + pr[t][1];
+            sum1 += pr[t][2] + pr[t][3];
+        }
+        sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+        sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+        const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
+        const uint32_t pa0 = pack_h2(pr[0][0] * inv0, pr[0][1] * inv0);
+        const uint32_t pa1 = pack_h2(pr[0][2] * inv1, pr[0][3] * inv1);
+        const uint32_t pa2 = pack_h2(pr[1][0] * inv0, pr[1][1] * inv0);
+        const uint32_t pa3 = pack_h2(pr[1][2] * inv1, pr[1][3] * inv1);
+        // ---- O = P V, 16 output channels per iteration; staged into the (now free) Q tile
+        __syncwarp();
+        const int r = lane >> 2;
+        for (int n0 = 0; n0 < d; n0 += 16) {
+            uint32_t v0, v1, v2, v3;
+            ldmatrix_x4_trans(sv_a + (lrow * pitch + n0 + lcol) * 2, v0, v1, v2, v3);
+            float oa[4] = {0.f, 0.f, 0.f, 0.f}, ob[4] = {0.f, 0.f, 0.f, 0.f};
+            mma_16816(oa, pa0, pa1, pa2, pa3, v0, v1);
+            mma_16816(ob, pa0, pa1, pa2, pa3, v2, v3);
+            *reinterpret_cast<uint32_t*>(sq + r * pitch + n0 + c0) = pack_h2(oa[0], oa[1]);
+            *reinterpret_cast<uint32_t*>(sq + (r + 8) * pitch + n0 + c0) = pack_h2(oa[2], oa[3]);
+            *reinterpret_cast<uint32_t*>(sq + r * pitch + n0 + 8 + c0) = pack_h2(ob[0], ob[1]);
+            *reinterpret_cast<uint32_t*>(sq + (r + 8) * pitch + n0 + 8 + c0) = pack_h2(ob[2], ob[3]);
+        }
+        __syncwarp();
+        for (int i = lane; i < F_ * vpr; i += 32) {
+            const int f = i / vpr, v = i - f * vpr;
+            *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(b) * F_ + f) * P + p) * C + h * d + v * 8) =
+                *reinterpret_cast<const uint4*>(sq + f * pitch + v * 8);
+        }
+        __syncwarp();
+        if (F_ < 16) {  // restore the zero rows of Q clobbered by the staging writes
+            for (int i = lane; i < (16 - F_) * pitch / 8; i += 32)
+                reinterpret_cast<uint4*>(sq + F_ * pitch)[i] = make_uint4(0, 0, 0, 0);
+            __syncwarp();
+        }
     }
 }
 

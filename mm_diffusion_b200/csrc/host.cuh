@@ -92,7 +92,7 @@ int build_attn(const AttnProblem& pr, AttnParams* out);
 int launch_attn(const AttnParams& p, int d, cudaStream_t st);
 
 // ------------------------------------------------------------ elementwise
-int launch_gn_stats(const GnSrc& s, int ns, int rows, double* sums, cudaStream_t st);
+int launch_gn_stats(const GnSrc& s, int ns, int rows, double* sums, cudaStream_t st, bool zero_sums = true);
 int launch_gn_apply(const GnSrc& s, int ns, int rows, const double* sums, const float* gamma, const float* beta,
                     const float* film, int film_ld, int ns_per_batch, int silu, act_t* y, cudaStream_t st);
 int launch_gn_temporal(const act_t* x, act_t* y, const float* gamma, const float* beta, int B, int F, int P, int C,

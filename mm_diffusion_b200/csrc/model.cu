@@ -120,7 +120,7 @@ struct Walker {
     bool create;
     Plan* plan = nullptr;
     int B = 1;
-    Arena persist, scratch;
+    Arena persist, scratch, stats;   // stats: GroupNorm accumulators, zeroed once per forward
     int err = MMD_OK;
     size_t w32_top = 0, wpk_top = 0, bpk_top = 0;
     int shift_slot = 0;
@@ -277,16 +277,16 @@ struct Walker {
                    int ns_per_batch, int silu, bool persistent_out = false) {
         const int C = c1 + c2;
         act_t* y = persistent_out ? alloc_p(static_cast<size_t>(ns) * rows * C) : alloc_s(static_cast<size_t>(ns) * rows * C);
-        double* sums = static_cast<double*>(alloc_s_bytes(sizeof(double) * 64 * ns));
+        double* sums = static_cast<double*>(stats.take(sizeof(double) * 64 * ns));
         if (!emitting() || bad()) return y;
         GnSrc s{x1, c1, c1, x2, c2, c2};
         const float* gamma = pf(gn.g);
         const float* beta = pf(gn.b);
         const int film_ld = m.emb_rows;
         push([=](cudaStream_t st) -> int {
-            MMD_TRY(launch_gn_stats(s, ns, rows, sums, st));
+            MMD_TRY(launch_gn_stats(s, ns, rows, sums, st, false));
             return launch_gn_apply(s, ns, rows, sums, gamma, beta, film, film_ld, ns_per_batch, silu, y, st);
-        }, "group_norm", 0.0, 2.0 * 2.0 * ns * static_cast<double>(rows) * C, 3);
+        }, "group_norm", 0.0, 2.0 * 2.0 * ns * static_cast<double>(rows) * C, 2);
         return y;
     }
 
@@ -563,6 +563,14 @@ struct Walker {
         int te0w = reg("time_embed.0.weight", {E, mc}), te0b = reg("time_embed.0.bias", {E});
         int te2w = reg("time_embed.2.weight", {E, E}), te2b = reg("time_embed.2.bias", {E});
         float* emb = nullptr;
+        if (!create && emitting()) {
+            uint8_t* sbase = stats.base;
+            const size_t sbytes = stats.cap;
+            push([=](cudaStream_t st) -> int {
+                MMD_CUDA_OK(cudaMemsetAsync(sbase, 0, sbytes, st));
+                return MMD_OK;
+            }, "memset", 0.0, static_cast<double>(sbytes), 0);
+        }
         if (!create) {
             emb = static_cast<float*>(persist.take(sizeof(float) * B * E));
             silu_emb = static_cast<float*>(persist.take(sizeof(float) * B * E));
@@ -786,7 +794,8 @@ static int build_plan(MmdModel* m, int B, Plan** out) {
     auto al = [](size_t x) { return (x + 1023) & ~size_t(1023); };
     const size_t io_bytes = al(vin) + al(ain) + al(vout) + al(aout) + al(sizeof(float) * B) + al(sizeof(int) * 64);
     const size_t p_bytes = al(dry.persist.peak) + 1024, s_bytes = al(dry.scratch.peak) + 1024;
-    plan->ws_bytes = io_bytes + p_bytes + s_bytes;
+    const size_t st_bytes = al(dry.stats.peak) + 1024;
+    plan->ws_bytes = io_bytes + p_bytes + s_bytes + st_bytes;
     MMD_CUDA_OK(cudaMalloc(&plan->ws, plan->ws_bytes));
     MMD_CUDA_OK(cudaMemset(plan->ws, 0, plan->ws_bytes));
     uint8_t* q = plan->ws;
@@ -801,9 +810,10 @@ static int build_plan(MmdModel* m, int B, Plan** out) {
     w.plan = plan.get();
     w.persist.base = q; w.persist.cap = p_bytes;
     w.scratch.base = q + p_bytes; w.scratch.cap = s_bytes;
+    w.stats.base = q + p_bytes + s_bytes; w.stats.cap = st_bytes;
     w.walk();
     if (w.bad()) return w.err;
-    if (w.persist.peak > p_bytes || w.scratch.peak > s_bytes) return fail(MMD_ESTATE, "internal: arena overflow");
+    if (w.persist.peak > p_bytes || w.scratch.peak > s_bytes || w.stats.peak > st_bytes) return fail(MMD_ESTATE, "internal: arena overflow");
     *out = plan.get();
     m->plans[B] = std::move(plan);
     return MMD_OK;
@@ -814,7 +824,7 @@ static size_t dry_workspace(MmdModel* m, int B) {
     dry.B = B;
     dry.walk();
     if (dry.bad()) return 0;
-    return dry.persist.peak + dry.scratch.peak + (1 << 20);
+    return dry.persist.peak + dry.scratch.peak + dry.stats.peak + (1 << 20);
 }
 
 }  // namespace mmd

@@ -183,9 +183,9 @@ int launch_gemm(const GemmParams& p, int bn, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------- attention
-static constexpr int ATT_MIN_SMEM = 120 * 1024;  // keeps one CTA per SM (each CTA allocates all 512 TMEM columns)
+// D = 64: ~98 KB and 256 TMEM columns per CTA -> two CTAs per SM.  D = 96/128: > 114 KB, one CTA (512 TMEM columns).
 template <int D>
-static int attn_smem_bytes() { return std::max(AttnSmem<D>::TOTAL, ATT_MIN_SMEM); }
+static int attn_smem_bytes() { return AttnSmem<D>::TOTAL; }
 
 int build_attn(const AttnProblem& pr, AttnParams* out) {
     AttnParams& p = *out;
@@ -230,20 +230,21 @@ int launch_attn(const AttnParams& p, int d, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------ elementwise
-static int gn_rows_per_block(int ns, int rows) {
-    // aim for ~4 blocks per SM overall, at least 32 rows per block
-    const int target_blocks = 4 * num_sms();
-    int per_domain = std::max(1, target_blocks / std::max(1, ns));
+static int gn_rows_per_block(int ns, int rows, int C) {
+    // ~6 blocks per SM over all domains; every thread streams at least two unrolled batches of rows
+    const int rows_per_pass = std::max(1, 256 / (C / 8));
+    const int target_blocks = 6 * num_sms();
+    const int per_domain = std::max(1, target_blocks / std::max(1, ns));
     int rpb = (rows + per_domain - 1) / per_domain;
-    rpb = std::max(rpb, 32);
+    rpb = std::max(rpb, 2 * GN_UNROLL * rows_per_pass);
     return std::min(rpb, rows);
 }
 
-int launch_gn_stats(const GnSrc& s, int ns, int rows, double* sums, cudaStream_t st) {
+int launch_gn_stats(const GnSrc& s, int ns, int rows, double* sums, cudaStream_t st, bool zero_sums) {
     const int C = s.c1 + s.c2;
     if (C % 32 != 0 || C % 8 != 0 || s.c1 % 8 != 0 || C / 8 > 256) return fail(MMD_EINVAL, "group norm channels %d unsupported", C);
-    MMD_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(double) * 64 * ns, st));
-    const int rpb = gn_rows_per_block(ns, rows);
+    if (zero_sums) MMD_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(double) * 64 * ns, st));
+    const int rpb = gn_rows_per_block(ns, rows, C);
     dim3 grid((rows + rpb - 1) / rpb, ns);
     gn_stats_kernel<<<grid, 256, 0, st>>>(s, rows, rpb, sums);
     MMD_CUDA_OK(cudaGetLastError());
@@ -253,10 +254,10 @@ int launch_gn_stats(const GnSrc& s, int ns, int rows, double* sums, cudaStream_t
 int launch_gn_apply(const GnSrc& s, int ns, int rows, const double* sums, const float* gamma, const float* beta,
                     const float* film, int film_ld, int ns_per_batch, int silu, act_t* y, cudaStream_t st) {
     const int C = s.c1 + s.c2;
-    const int rpb = gn_rows_per_block(ns, rows);
+    const int rpb = gn_rows_per_block(ns, rows, C);
     dim3 grid((rows + rpb - 1) / rpb, ns);
-    gn_apply_kernel<<<grid, 256, 2 * C * sizeof(float), st>>>(s, rows, rpb, sums, gamma, beta, film, film_ld,
-                                                               ns_per_batch, silu, y);
+    gn_apply_kernel<<<grid, 256, (2 * C + 64) * sizeof(float), st>>>(s, rows, rpb, sums, gamma, beta, film, film_ld,
+                                                                      ns_per_batch, silu, y);
     MMD_CUDA_OK(cudaGetLastError());
     return MMD_OK;
 }
@@ -285,20 +286,19 @@ int launch_resample(const act_t* x, act_t* y, int mode, int n, int h, int w, int
 
 int launch_temporal_attn(const act_t* qkv, act_t* out, int B, int F, int P, int C, int heads, cudaStream_t st) {
     const int d = C / heads;
-    if (d % 8 != 0) return fail(MMD_EINVAL, "temporal attention head dim %d", d);
-    const int wpb = 4;
-    const size_t per_warp = static_cast<size_t>(3) * F * d * sizeof(act_t) + static_cast<size_t>(F) * F * sizeof(float);
-    const size_t smem = per_warp * wpb;
+    if (d % 16 != 0 || C % heads != 0) return fail(MMD_EINVAL, "temporal attention head dim %d (must be a multiple of 16)", d);
+    const size_t smem = static_cast<size_t>(TATT_WARPS) * 3 * 16 * (d + 8) * sizeof(act_t);
     const long long items = static_cast<long long>(B) * P * heads;
-    const unsigned grid = static_cast<unsigned>((items + wpb - 1) / wpb);
+    const unsigned grid = static_cast<unsigned>(std::min<long long>((items + TATT_WARPS - 1) / TATT_WARPS, 8LL * num_sms()));
     static bool attr_done = false;
     if (!attr_done) {
         MMD_CUDA_OK(cudaFuncSetAttribute(temporal_attn_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         MMD_CUDA_OK(cudaFuncSetAttribute(temporal_attn_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         attr_done = true;
     }
-    if (F == 16) temporal_attn_kernel<16><<<grid, wpb * 32, smem, st>>>(qkv, out, B, P, C, heads);
-    else if (F == 8) temporal_attn_kernel<8><<<grid, wpb * 32, smem, st>>>(qkv, out, B, P, C, heads);
+    if (smem > 96 * 1024) return fail(MMD_EINVAL, "temporal attention head dim %d too large", d);
+    if (F == 16) temporal_attn_kernel<16><<<grid, TATT_WARPS * 32, smem, st>>>(qkv, out, B, P, C, heads);
+    else if (F == 8) temporal_attn_kernel<8><<<grid, TATT_WARPS * 32, smem, st>>>(qkv, out, B, P, C, heads);
     else return fail(MMD_EINVAL, "temporal attention supports F in {8,16}, got %d", F);
     MMD_CUDA_OK(cudaGetLastError());
     return MMD_OK;
