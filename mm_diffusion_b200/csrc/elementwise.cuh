@@ -100,17 +100,22 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(GnSrc s, int R, int rows_
 __global__ void __launch_bounds__(256) gn_apply_kernel(GnSrc s, int R, int rows_per_block, const double* __restrict__ sums,
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 const float* __restrict__ film, int film_ld, int ns_per_batch, int do_silu,
-                                act_t* __restrict__ y) {
+                                act_t* __restrict__ y, int nsub, long long stat_rows) {
     extern __shared__ float coef[];  // [2][C] then [64] group mean / rstd
     const int C = s.c1 + s.c2;
     const int cpg = C / 32;
     const int vpr = C / 8;
     const int ns = blockIdx.y;
     float* gstat = coef + 2 * C;
-    if (threadIdx.x < 32) {  // the only double-precision arithmetic: 32 groups
-        const double inv_n = 1.0 / (static_cast<double>(R) * cpg);
-        const double mean = sums[static_cast<size_t>(ns) * 64 + 2 * threadIdx.x] * inv_n;
-        double var = sums[static_cast<size_t>(ns) * 64 + 2 * threadIdx.x + 1] * inv_n - mean * mean;
+    if (threadIdx.x < 32) {  // the only double-precision arithmetic: 32 groups (x nsub partial slots)
+        const double inv_n = 1.0 / (static_cast<double>(stat_rows) * cpg);
+        double su = 0.0, sq = 0.0;
+        for (int k = 0; k < nsub; ++k) {
+            su += sums[(static_cast<size_t>(ns) * nsub + k) * 64 + 2 * threadIdx.x];
+            sq += sums[(static_cast<size_t>(ns) * nsub + k) * 64 + 2 * threadIdx.x + 1];
+        }
+        const double mean = su * inv_n;
+        double var = sq * inv_n - mean * mean;
         if (var < 0) var = 0;
         gstat[2 * threadIdx.x] = static_cast<float>(mean);
         gstat[2 * threadIdx.x + 1] = rsqrtf(static_cast<float>(var) + 1e-5f);
@@ -177,9 +182,21 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnSrc s, int R, int rows_
 // input rearranged "(b h w) c f", multimodal_unet.py:489-490 -> stats over C/32 x F).
 // x, y: [B][F][P][C].  One thread per (pixel, group).
 // ---------------------------------------------------------------------------
-__global__ void gn_temporal_kernel(const act_t* __restrict__ x, act_t* __restrict__ y, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, int B, int F, int P, int C) {
-    const int cpg = C / 32;
+// Register-resident: a thread loads its whole (F x C/32) domain with wide independent loads (all in flight
+// at once), reduces and normalises from registers.  Consecutive threads own consecutive groups of one pixel,
+// so a warp reads / writes complete channel rows.
+template <int HALVES> struct GnVec;
+template <> struct GnVec<8> { using type = uint4; };
+template <> struct GnVec<4> { using type = uint2; };
+template <> struct GnVec<2> { using type = uint32_t; };
+
+template <int CPG, int F_>
+__global__ void __launch_bounds__(128) gn_temporal_kernel(const act_t* __restrict__ x, act_t* __restrict__ y,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          int B, int P, int C) {
+    constexpr int VEC = (CPG % 8 == 0) ? 8 : ((CPG % 4 == 0) ? 4 : 2);
+    constexpr int NV = CPG / VEC;
+    using V = typename GnVec<VEC>::type;
     const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     const long long total = static_cast<long long>(B) * P * 32;
     if (idx >= total) return;
@@ -188,30 +205,50 @@ __global__ void gn_temporal_kernel(const act_t* __restrict__ x, act_t* __restric
     const int p = static_cast<int>(bp % P);
     const int b = static_cast<int>(bp / P);
     const size_t fstride = static_cast<size_t>(P) * C;
-    const size_t base = (static_cast<size_t>(b) * F * P + p) * C + g * cpg;
+    const size_t base = (static_cast<size_t>(b) * F_ * P + p) * C + g * CPG;
+    V v[F_][NV];
+#pragma unroll
+    for (int f = 0; f < F_; ++f)
+#pragma unroll
+        for (int k = 0; k < NV; ++k) v[f][k] = __ldg(reinterpret_cast<const V*>(x + base + f * fstride) + k);
     float su = 0.f, ss = 0.f;
-    for (int f = 0; f < F; ++f) {
-        const __half2* row = reinterpret_cast<const __half2*>(x + base + f * fstride);
-        for (int k = 0; k < cpg / 2; ++k) {
-            const float2 v = __half22float2(row[k]);
-            su += v.x + v.y;
-            ss += v.x * v.x + v.y * v.y;
+#pragma unroll
+    for (int f = 0; f < F_; ++f)
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const __half2* h = reinterpret_cast<const __half2*>(&v[f][k]);
+#pragma unroll
+            for (int i = 0; i < VEC / 2; ++i) {
+                const float2 t = __half22float2(h[i]);
+                su += t.x + t.y;
+                ss = fmaf(t.x, t.x, fmaf(t.y, t.y, ss));
+            }
         }
-    }
-    const float inv_n = 1.f / (F * cpg);
+    const float inv_n = 1.f / (F_ * CPG);
     const float mean = su * inv_n;
     const float var = fmaxf(ss * inv_n - mean * mean, 0.f);
     const float rstd = rsqrtf(var + 1e-5f);
-    for (int f = 0; f < F; ++f) {
-        const __half2* row = reinterpret_cast<const __half2*>(x + base + f * fstride);
-        __half2* orow = reinterpret_cast<__half2*>(y + base + f * fstride);
-        for (int k = 0; k < cpg / 2; ++k) {
-            const float2 v = __half22float2(row[k]);
-            const int c = g * cpg + 2 * k;
-            orow[k] = __floats2half2_rn((v.x - mean) * rstd * gamma[c] + beta[c],
-                                        (v.y - mean) * rstd * gamma[c + 1] + beta[c + 1]);
-        }
+    float ca[CPG], cb[CPG];
+#pragma unroll
+    for (int i = 0; i < CPG; ++i) {
+        ca[i] = rstd * gamma[g * CPG + i];
+        cb[i] = beta[g * CPG + i] - mean * ca[i];
     }
+#pragma unroll
+    for (int f = 0; f < F_; ++f)
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            V o;
+            const __half2* h = reinterpret_cast<const __half2*>(&v[f][k]);
+            __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+            for (int i = 0; i < VEC / 2; ++i) {
+                const float2 t = __half22float2(h[i]);
+                const int c = k * VEC + 2 * i;
+                oh[i] = __floats2half2_rn(fmaf(t.x, ca[c], cb[c]), fmaf(t.y, ca[c + 1], cb[c + 1]));
+            }
+            *(reinterpret_cast<V*>(y + base + f * fstride) + k) = o;
+        }
 }
 
 // ---------------------------------------------------------------------------

@@ -40,6 +40,14 @@ struct alignas(64) GemmParams {
     long long ostride_c;
     int dims[4];
     int n_valid;
+    // fused GroupNorm statistics of the (fp16-rounded) output: per (domain, group) sum / sum of squares
+    // accumulated into double slots [domain][32][2]; domain = base(tile) + row / stats_rows
+    double* stats;          // null = off
+    int stats_cpg;          // channels per group = N / 32
+    int stats_rows;         // rows of one domain inside a tile (64 or 128)
+    int stats_mul[4];       // domain base = sum_i origin[i+1] * stats_mul[i] / stats_div
+    int stats_div;
+    int stats_valid_coord;  // >= 0: rows >= dims[c] - origin[c+1] of the tile are padding (ragged last tile)
 };
 
 template <int BN>
@@ -50,7 +58,7 @@ struct GemmSmem {
     static constexpr int OUT_CHUNKS = (BN >= 64) ? BN / 64 : 0;
     static constexpr int OUT_BYTES = OUT_CHUNKS * GEMM_BM * 128;
     static constexpr int STAGES = (BN >= 256) ? 3 : ((BN >= 128) ? 5 : 8);
-    static constexpr int BAR_BYTES = 256;
+    static constexpr int BAR_BYTES = 256 + 2 * 32 * 2 * 4;   // barriers + GroupNorm bins [2 domains][32 groups][2]
     static constexpr int TOTAL = STAGES * STAGE_BYTES + OUT_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
     static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : ((2 * BN <= 64) ? 64 : ((2 * BN <= 128) ? 128 : ((2 * BN <= 256) ? 256 : 512)));
 };
@@ -79,6 +87,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
     uint64_t* tfull_bar = bars + 2 * S::STAGES;
     uint64_t* tempty_bar = bars + 2 * S::STAGES + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::STAGES + 4);
+    float* gn_bins = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -189,6 +198,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
 
             if constexpr (BN >= 64) {
                 if (leader) tma_store_wait_read0();  // previous tile's store has drained the staging buffer
+                if (p.stats != nullptr) gn_bins[threadIdx.x - 64] = 0.f;
                 named_bar_sync(1, 128);
 #pragma unroll 1
                 for (int cc = 0; cc < BN / 32; ++cc) {
@@ -225,6 +235,60 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                         tma_store_nd(p.rank, &p.o_map, out_stage + ch * (GEMM_BM * 128), c);
                     }
                     tma_store_commit();
+                }
+                if (p.stats != nullptr) {
+                    // column sums of the staged fp16 tile: thread = (8-column octet, run of NOCT rows)
+                    constexpr int NOCT = BN / 8;
+                    const int et = threadIdx.x - 64;
+                    const int oct = et % NOCT;
+                    const int r_begin = (et / NOCT) * NOCT;
+                    int valid_rows = GEMM_BM;
+                    if (p.stats_valid_coord >= 0)
+                        valid_rows = min(GEMM_BM, p.dims[p.stats_valid_coord] - org[p.stats_valid_coord + 1]);
+                    float sm[8], sq[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { sm[i] = 0.f; sq[i] = 0.f; }
+                    const uint8_t* chunk = out_stage + (oct >> 3) * (GEMM_BM * 128);
+#pragma unroll 4
+                    for (int rr = 0; rr < NOCT; ++rr) {
+                        const int r = r_begin + rr;
+                        if (r < valid_rows) {
+                            const uint4 raw = *reinterpret_cast<const uint4*>(chunk + sw128_off(r, oct & 7));
+                            const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float2 f = __half22float2(h[i]);
+                                sm[2 * i] += f.x; sq[2 * i] = fmaf(f.x, f.x, sq[2 * i]);
+                                sm[2 * i + 1] += f.y; sq[2 * i + 1] = fmaf(f.y, f.y, sq[2 * i + 1]);
+                            }
+                        }
+                    }
+                    const int col0 = n_idx * BN + oct * 8;
+                    const int g0 = (n_idx * BN) / p.stats_cpg;
+                    const int dl = r_begin / p.stats_rows;   // 0 or 1: domain inside the tile
+                    float* bins = gn_bins + dl * 64;
+                    int g = col0 / p.stats_cpg;
+                    float as = 0.f, aq = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int gi = (col0 + i) / p.stats_cpg;
+                        if (gi != g) {
+                            atomicAdd(&bins[2 * (g - g0)], as);
+                            atomicAdd(&bins[2 * (g - g0) + 1], aq);
+                            g = gi; as = 0.f; aq = 0.f;
+                        }
+                        as += sm[i]; aq += sq[i];
+                    }
+                    atomicAdd(&bins[2 * (g - g0)], as);
+                    atomicAdd(&bins[2 * (g - g0) + 1], aq);
+                    named_bar_sync(1, 128);
+                    const int dom_base = (org[1] * p.stats_mul[0] + org[2] * p.stats_mul[1] + org[3] * p.stats_mul[2] +
+                                          org[4] * p.stats_mul[3]) / p.stats_div;
+                    const int bdl = et >> 6, bg = (et & 63) >> 1;
+                    const float val = gn_bins[et];
+                    if (g0 + bg < 32 && (bdl == 0 || p.stats_rows < GEMM_BM) && val != 0.f)
+                        atomicAdd(&p.stats[(static_cast<size_t>(dom_base + bdl) * 32 + (g0 + bg)) * 2 + (et & 1)],
+                                  static_cast<double>(val));
                 }
             } else {
                 // narrow-N head: fp32 scatter, row -> token coordinates via the box decomposition

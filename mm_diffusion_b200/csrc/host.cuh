@@ -66,6 +66,12 @@ struct GemmProblem {
     float* out_f32 = nullptr; // bn == 16 scatter
     long long ostride[4] = {};
     long long ostride_c = 0;
+    // fused GroupNorm statistics of the output (see GemmParams)
+    double* stats = nullptr;
+    int stats_rows = 128;
+    int stats_mul[4] = {0, 0, 0, 0};
+    int stats_div = 1;
+    int stats_valid_coord = -1;
     long long k_total() const {
         long long c = 0;
         for (int i = 0; i < n_src; ++i) c += src_c[i];
@@ -93,8 +99,11 @@ int launch_attn(const AttnParams& p, int d, cudaStream_t st);
 
 // ------------------------------------------------------------ elementwise
 int launch_gn_stats(const GnSrc& s, int ns, int rows, double* sums, cudaStream_t st, bool zero_sums = true);
+// sums: [ns * nsub][32][2]; the statistics of domain i are the sum of its nsub consecutive slots, taken over
+// stat_rows rows in total (0 = rows; differs for nearest-upsampled inputs whose statistics come from the source).
 int launch_gn_apply(const GnSrc& s, int ns, int rows, const double* sums, const float* gamma, const float* beta,
-                    const float* film, int film_ld, int ns_per_batch, int silu, act_t* y, cudaStream_t st);
+                    const float* film, int film_ld, int ns_per_batch, int silu, act_t* y, cudaStream_t st,
+                    int nsub = 1, long long stat_rows = 0);
 int launch_gn_temporal(const act_t* x, act_t* y, const float* gamma, const float* beta, int B, int F, int P, int C,
                        cudaStream_t st);
 int launch_resample(const act_t* x, act_t* y, int mode, int n, int h, int w, int c, cudaStream_t st);

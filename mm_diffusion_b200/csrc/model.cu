@@ -112,8 +112,11 @@ namespace mmd {
 // Topology walk.  mode CREATE: registers params + packed layouts (no device work).
 //                 mode PLAN  : emits launches into plan (weights/arenas must exist).
 // ---------------------------------------------------------------------------
-struct VT { act_t* p; int C, H, W; };   // video [B,F,H,W,C]
-struct AT { act_t* p; int C, L; };      // audio [B,L,C]
+// Fused GroupNorm statistics attached to a tensor by its producer: `slots` [B*nsub][32][2] doubles
+// (video: one slot per frame, nsub = F; audio: one per sample), `rows` = rows per sample the sums cover.
+struct Stat { double* slots = nullptr; int nsub = 1; long long rows = 0; };
+struct VT { act_t* p; int C, H, W; Stat st; };   // video [B,F,H,W,C]
+struct AT { act_t* p; int C, L; Stat st; };      // audio [B,L,C]
 
 struct Walker {
     MmdModel& m;
@@ -125,10 +128,22 @@ struct Walker {
     size_t w32_top = 0, wpk_top = 0, bpk_top = 0;
     int shift_slot = 0;
     int emb_row_top = 0;
+    bool wide_n = true;         // MMD_NO_BN256=1 keeps 128-wide GEMM tiles
+    bool fuse_stats = true;     // MMD_NO_FUSED_STATS=1 keeps every GroupNorm on the standalone statistics kernel
     float* emb_all = nullptr;   // [B][emb_rows]
     float* silu_emb = nullptr;  // [B][E]
 
-    Walker(MmdModel& mm, bool c) : m(mm), create(c) {}
+    Walker(MmdModel& mm, bool c) : m(mm), create(c) {
+        const char* e = getenv("MMD_NO_FUSED_STATS");
+        fuse_stats = !(e && e[0] == '1');
+        const char* w = getenv("MMD_NO_BN256");
+        wide_n = !(w && w[0] == '1');
+    }
+    double* stat_slots_video() { return static_cast<double*>(stats.take(sizeof(double) * 64 * B * F())); }
+    double* stat_slots_audio() { return static_cast<double*>(stats.take(sizeof(double) * 64 * B)); }
+    // fused statistics need the 64- or 128-row domain runs the GEMM epilogue reduces over
+    bool can_fuse_video(int hw) const { return fuse_stats && hw >= 64; }
+    bool can_fuse_audio(int L) const { return fuse_stats && L >= 128; }   // one sample per 128-row tile
     const MmdConfig& cfg() const { return m.cfg; }
     int F() const { return m.cfg.video_f; }
 
@@ -237,9 +252,12 @@ struct Walker {
     }
 
     // ---------------- emitters
+    // stat_kind: 0 none, 1 video tokens (2-D geometry, one domain per frame of `stat_hw` rows),
+    //            2 video temporal geometry (P,F,B), 3 audio geometry (L,B)
     void emit_gemm(const char* tag, const ConvGeom& g, const std::vector<std::pair<const act_t*, int>>& srcs,
                    const std::vector<std::array<int, 3>>& taps, const PackedConv* pc, act_t* out, float* out_f32 = nullptr,
-                   const long long* ostride = nullptr, long long ostride_c = 0) {
+                   const long long* ostride = nullptr, long long ostride_c = 0, double* stat_slots = nullptr,
+                   int stat_kind = 0, int stat_hw = 0) {
         if (!emitting() || bad() || !pc) return;
         GemmProblem pr;
         pr.g = g;
@@ -253,14 +271,28 @@ struct Walker {
         pr.bias = m.bpk + pc->b_off;
         pr.n = pc->n;
         pr.bn = pc->bn;
+        // wide-N tiles halve the A re-reads and the shared-memory traffic per FLOP; only when the tile count
+        // still fills the machine a couple of times over
+        {
+            long long mt = 1;
+            for (int i = 0; i < 4; ++i) mt *= (g.dims[i] + g.box[i] - 1) / g.box[i];
+            if (wide_n && pc->bn == 128 && pc->n % 256 == 0 && mt * (pc->n / 256) >= 2LL * num_sms()) pr.bn = 256;
+        }
         pr.out = out;
         pr.out_f32 = out_f32;
         if (ostride) for (int i = 0; i < 4; ++i) pr.ostride[i] = ostride[i];
         pr.ostride_c = ostride_c;
+        if (stat_slots && stat_kind == 1) {
+            pr.stats = stat_slots; pr.stats_rows = std::min(stat_hw, 128); pr.stats_mul[0] = 1; pr.stats_div = stat_hw;
+        } else if (stat_slots && stat_kind == 2) {
+            pr.stats = stat_slots; pr.stats_rows = g.box[0]; pr.stats_mul[1] = 1; pr.stats_mul[2] = F(); pr.stats_div = 1;
+        } else if (stat_slots && stat_kind == 3) {
+            pr.stats = stat_slots; pr.stats_rows = 128; pr.stats_mul[1] = 1; pr.stats_div = 1; pr.stats_valid_coord = 0;
+        }
         auto gp = std::make_shared<GemmParams>();
         int r = build_gemm(pr, gp.get());
         if (r != MMD_OK) { set_err(r); return; }
-        const int bn = pc->bn;
+        const int bn = pr.bn;
         const double tokens = static_cast<double>(g.tokens());
         const double k_alg = static_cast<double>(pc->k_total - pc->identity_c);
         const double flops = 2.0 * tokens * k_alg * pc->n;
@@ -273,12 +305,27 @@ struct Walker {
     ConvGeom geom_audio(const AT& a) const { ConvGeom g; g.rank = 3; g.dims[0] = a.L; g.dims[1] = B; geom_fill_box(g); return g; }
 
     // GroupNorm over `ns` domains of `rows` rows on the concat of (x1,c1),(x2,c2)
+    // `st` (optional): statistics already accumulated by the producer of x1 (single-source only);
+    // per_frame selects one slot per domain instead of the nsub slots of a sample.
     act_t* emit_gn(const act_t* x1, int c1, const act_t* x2, int c2, int ns, int rows, GnP gn, const float* film,
-                   int ns_per_batch, int silu, bool persistent_out = false) {
+                   int ns_per_batch, int silu, const Stat* st = nullptr, bool per_frame = false) {
         const int C = c1 + c2;
-        act_t* y = persistent_out ? alloc_p(static_cast<size_t>(ns) * rows * C) : alloc_s(static_cast<size_t>(ns) * rows * C);
-        double* sums = static_cast<double*>(stats.take(sizeof(double) * 64 * ns));
+        act_t* y = alloc_s(static_cast<size_t>(ns) * rows * C);
+        const bool fused = fuse_stats && st && st->slots && !x2;
+        double* sums = fused ? st->slots : static_cast<double*>(stats.take(sizeof(double) * 64 * ns));
         if (!emitting() || bad()) return y;
+        if (fused) {
+            GnSrc s{x1, c1, c1, nullptr, 0, 0};
+            const float* gamma = pf(gn.g);
+            const float* beta = pf(gn.b);
+            const int film_ld = m.emb_rows;
+            const int nsub = per_frame ? 1 : st->nsub;
+            const long long srows = per_frame ? st->rows / st->nsub : st->rows;
+            push([=](cudaStream_t stx) -> int {
+                return launch_gn_apply(s, ns, rows, sums, gamma, beta, film, film_ld, ns_per_batch, silu, y, stx, nsub, srows);
+            }, "group_norm", 0.0, 2.0 * 2.0 * ns * static_cast<double>(rows) * C, 1);
+            return y;
+        }
         GnSrc s{x1, c1, c1, x2, c2, c2};
         const float* gamma = pf(gn.g);
         const float* beta = pf(gn.b);
@@ -306,7 +353,8 @@ struct Walker {
 
     // ---------------- network pieces
     // SingleModalAtten over sequences: kind 0 spatial (per frame), 1 temporal (per pixel), 2 audio
-    act_t* self_attention(const std::string& p, const act_t* x, int C, int kind, const VT* vt, const AT* at) {
+    act_t* self_attention(const std::string& p, const act_t* x, int C, int kind, const VT* vt, const AT* at,
+                          const Stat* in_st, Stat* out_st) {
         GnP gn = reg_gn(p + ".norm", C);
         ConvP qkv = reg_conv(p + ".qkv", 3 * C, C, {1});
         ConvP proj = reg_conv(p + ".proj_out", C, C, {1});
@@ -325,9 +373,9 @@ struct Walker {
         const size_t mark = scratch.top;
         act_t* xn;
         if (kind == 0) {
-            xn = emit_gn(x, C, nullptr, 0, B * F(), vt->H * vt->W, gn, nullptr, 1, 0);
+            xn = emit_gn(x, C, nullptr, 0, B * F(), vt->H * vt->W, gn, nullptr, 1, 0, in_st, true);
         } else if (kind == 2) {
-            xn = emit_gn(x, C, nullptr, 0, B, at->L, gn, nullptr, 1, 0);
+            xn = emit_gn(x, C, nullptr, 0, B, at->L, gn, nullptr, 1, 0, in_st, false);
         } else {
             xn = alloc_s(tokens * C);
             if (emitting()) {
@@ -339,7 +387,9 @@ struct Walker {
             }
         }
         act_t* qkvb = alloc_s(tokens * 3 * C);
-        emit_gemm("conv1x1_qkv", geom2(static_cast<long long>(tokens)), {{xn, C}}, {{0, 0, 0}}, pq, qkvb);
+        AT aview{nullptr, C, at ? at->L : 0};
+        const ConvGeom gtok = at ? geom_audio(aview) : geom2(static_cast<long long>(tokens));
+        emit_gemm("conv1x1_qkv", gtok, {{xn, C}}, {{0, 0, 0}}, pq, qkvb);
         act_t* o = alloc_s(tokens * C);
         if (kind == 0) {
             const int hw = vt->H * vt->W;
@@ -351,7 +401,19 @@ struct Walker {
             push([=](cudaStream_t st) { return launch_temporal_attn(qkvb, o, Bc, Fc, P, C, heads, st); },
                  "temporal_attention", 4.0 * static_cast<double>(tokens) * Fc * C, 2.0 * 4.0 * static_cast<double>(tokens) * C);
         }
-        emit_gemm("conv1x1_proj", geom2(static_cast<long long>(tokens)), {{o, C}, {x, C}}, {{0, 0, 0}}, pp, out);
+        // statistics of the block output for its consumer's GroupNorm (the spatial output only feeds the
+        // per-pixel temporal norm, which computes its own)
+        double* slots = nullptr;
+        int skind = 0, shw = 0;
+        if (out_st) *out_st = Stat{};
+        if (kind == 1 && can_fuse_video(vt->H * vt->W)) {
+            slots = stat_slots_video(); skind = 1; shw = vt->H * vt->W;
+            if (out_st) *out_st = Stat{slots, F(), static_cast<long long>(F()) * shw};
+        } else if (kind == 2 && can_fuse_audio(at->L)) {
+            slots = stat_slots_audio(); skind = 3;
+            if (out_st) *out_st = Stat{slots, 1, at->L};
+        }
+        emit_gemm("conv1x1_proj", gtok, {{o, C}, {x, C}}, {{0, 0, 0}}, pp, out, nullptr, nullptr, 0, slots, skind, shw);
         scratch.top = mark;
         return out;
     }
@@ -417,14 +479,18 @@ struct Walker {
                 vo.p = alloc_p(static_cast<size_t>(B) * Fr * vo.H * vo.W * cout);
                 const size_t mark = scratch.top;
                 const int hw = v.H * v.W;
-                act_t* h0 = emit_gn(v.p, v.C, v2, vc2, B, Fr * hw, vin_gn, nullptr, 1, 1);
+                act_t* h0 = emit_gn(v.p, v.C, v2, vc2, B, Fr * hw, vin_gn, nullptr, 1, 1, &v.st, false);
                 act_t* u = alloc_s(vtok(v) * cout);
                 VT vin{h0, cin, v.H, v.W};
                 std::vector<std::array<int, 3>> taps9;
                 for (int ky = 0; ky < 3; ++ky) for (int kx = 0; kx < 3; ++kx) taps9.push_back({kx - 1, ky - 1, 0});
                 emit_gemm("conv3x3_spatial", geom_spatial(vin), {{h0, cin}}, taps9, p_vsp, u);
                 act_t* h1 = alloc_s(vtok(v) * cout);
-                emit_gemm("conv_temporal", geom_temporal(vin), {{u, cout}}, {{0, -1, 0}, {0, 0, 0}, {0, 1, 0}}, p_vtp, h1);
+                // GN2 statistics from the temporal conv's epilogue (nearest upsampling keeps them; pooling does not)
+                Stat h1st;
+                if (!down && can_fuse_video(hw)) h1st = Stat{stat_slots_video(), Fr, static_cast<long long>(Fr) * hw};
+                emit_gemm("conv_temporal", geom_temporal(vin), {{u, cout}}, {{0, -1, 0}, {0, 0, 0}, {0, 1, 0}}, p_vtp, h1,
+                          nullptr, nullptr, 0, h1st.slots, 2, 0);
                 const act_t* xs = v.p;   // skip-path input (single source when resampling)
                 if (up || down) {
                     act_t* h1r = alloc_s(static_cast<size_t>(B) * Fr * vo.H * vo.W * cout);
@@ -443,10 +509,12 @@ struct Walker {
                     xs = xr;
                 }
                 const int hwo = vo.H * vo.W;
-                act_t* h2 = emit_gn(h1, cout, nullptr, 0, B, Fr * hwo, vout_gn, film, 1, 1);
+                act_t* h2 = emit_gn(h1, cout, nullptr, 0, B, Fr * hwo, vout_gn, film, 1, 1, &h1st, false);
                 std::vector<std::pair<const act_t*, int>> srcs = {{h2, cout}, {xs, v.C}};
                 if (v2) srcs.push_back({v2, vc2});
-                emit_gemm("conv1x1_out", geom2(static_cast<long long>(B) * Fr * hwo), srcs, {{0, 0, 0}}, p_vo, vo.p);
+                if (can_fuse_video(hwo)) vo.st = Stat{stat_slots_video(), Fr, static_cast<long long>(Fr) * hwo};
+                emit_gemm("conv1x1_out", geom2(static_cast<long long>(B) * Fr * hwo), srcs, {{0, 0, 0}}, p_vo, vo.p,
+                          nullptr, nullptr, 0, vo.st.slots, 1, hwo);
                 scratch.top = mark;
             }
             // ---------------- audio branch
@@ -455,10 +523,13 @@ struct Walker {
                 if (up) ao.L = a.L * 4;
                 ao.p = alloc_p(static_cast<size_t>(B) * ao.L * cout);
                 const size_t mark = scratch.top;
-                act_t* h0 = emit_gn(a.p, a.C, a2, ac2, B, a.L, ain_gn, nullptr, 1, 1);
+                act_t* h0 = emit_gn(a.p, a.C, a2, ac2, B, a.L, ain_gn, nullptr, 1, 1, &a.st, false);
                 act_t* h1 = alloc_s(atok(a) * cout);
                 AT ain{h0, cin, a.L};
-                emit_gemm("conv_audio_k3", geom_audio(ain), {{h0, cin}}, {{-dilation, 0, 0}, {0, 0, 0}, {dilation, 0, 0}}, p_ac, h1);
+                Stat h1st;
+                if (!down && can_fuse_audio(a.L)) h1st = Stat{stat_slots_audio(), 1, a.L};
+                emit_gemm("conv_audio_k3", geom_audio(ain), {{h0, cin}}, {{-dilation, 0, 0}, {0, 0, 0}, {dilation, 0, 0}}, p_ac, h1,
+                          nullptr, nullptr, 0, h1st.slots, 3, 0);
                 const act_t* xs = a.p;
                 if (up || down) {
                     act_t* h1r = alloc_s(static_cast<size_t>(B) * ao.L * cout);
@@ -476,22 +547,27 @@ struct Walker {
                     h1 = h1r;
                     xs = xr;
                 }
-                act_t* h2 = emit_gn(h1, cout, nullptr, 0, B, ao.L, aout_gn, film, 1, 1);
+                act_t* h2 = emit_gn(h1, cout, nullptr, 0, B, ao.L, aout_gn, film, 1, 1, &h1st, false);
                 std::vector<std::pair<const act_t*, int>> srcs = {{h2, cout}, {xs, a.C}};
                 if (a2) srcs.push_back({a2, ac2});
-                emit_gemm("conv1x1_out", geom2(static_cast<long long>(B) * ao.L), srcs, {{0, 0, 0}}, p_ao, ao.p);
+                if (can_fuse_audio(ao.L)) ao.st = Stat{stat_slots_audio(), 1, ao.L};
+                emit_gemm("conv1x1_out", geom_audio(ao), srcs, {{0, 0, 0}}, p_ao, ao.p, nullptr, nullptr, 0, ao.st.slots, 3, 0);
                 scratch.top = mark;
             }
         }
         // ---------------- in-block self attention (multimodal_unet.py:485-493)
         if (vattn) {
-            act_t* s = self_attention(p + ".spatial_attention_block", vo.p, cout, 0, &vo, nullptr);
-            act_t* t = self_attention(p + ".temporal_attention_block", s, cout, 1, &vo, nullptr);
+            Stat tst;
+            act_t* s = self_attention(p + ".spatial_attention_block", vo.p, cout, 0, &vo, nullptr, &vo.st, nullptr);
+            act_t* t = self_attention(p + ".temporal_attention_block", s, cout, 1, &vo, nullptr, nullptr, &tst);
             vo.p = t;
+            vo.st = tst;
         }
         if (aattn) {
-            act_t* s = self_attention(p + ".audio_attention_block", ao.p, cout, 2, nullptr, &ao);
+            Stat ast;
+            act_t* s = self_attention(p + ".audio_attention_block", ao.p, cout, 2, nullptr, &ao, &ao.st, &ast);
             ao.p = s;
+            ao.st = ast;
         }
         v = vo;
         a = ao;
@@ -527,23 +603,30 @@ struct Walker {
         act_t* vout = alloc_p(vt * C);
         act_t* aout = alloc_p(at * C);
         const size_t mark = scratch.top;
-        act_t* vnrm = emit_gn(v.p, C, nullptr, 0, B, Fr * hw, vn, nullptr, 1, 0);
-        act_t* anrm = emit_gn(a.p, C, nullptr, 0, B, a.L, an, nullptr, 1, 0);
+        act_t* vnrm = emit_gn(v.p, C, nullptr, 0, B, Fr * hw, vn, nullptr, 1, 0, &v.st, false);
+        act_t* anrm = emit_gn(a.p, C, nullptr, 0, B, a.L, an, nullptr, 1, 0, &a.st, false);
         act_t* vqkv = alloc_s(vt * 3 * C);
         act_t* aqkv = alloc_s(at * 3 * C);
         emit_gemm("conv1x1_qkv", geom2(static_cast<long long>(vt)), {{vnrm, C}}, {{0, 0, 0}}, p_vq, vqkv);
-        emit_gemm("conv1x1_qkv", geom2(static_cast<long long>(at)), {{anrm, C}}, {{0, 0, 0}}, p_aq, aqkv);
+        emit_gemm("conv1x1_qkv", geom_audio(a), {{anrm, C}}, {{0, 0, 0}}, p_aq, aqkv);
         act_t* ov = alloc_s(vt * C);
         act_t* oa = alloc_s(at * C);
         const int* sdev = (shift && plan) ? plan->shifts_dev + slot : nullptr;
         // video queries attend audio keys/values and vice versa (multimodal_unet.py:530-559)
         emit_attn(vqkv, 3 * C, 0, vt, aqkv, 3 * C, C, at, aqkv, 2 * C, ov, C, heads, d, Fr, hw, apf, window, sdev);
         emit_attn(aqkv, 3 * C, 0, at, vqkv, 3 * C, C, vt, vqkv, 2 * C, oa, C, heads, d, Fr, apf, hw, window, sdev);
-        emit_gemm("conv1x1_proj", geom2(static_cast<long long>(vt)), {{ov, C}, {v.p, C}}, {{0, 0, 0}}, p_vp, vout);
-        emit_gemm("conv1x1_proj", geom2(static_cast<long long>(at)), {{oa, C}, {a.p, C}}, {{0, 0, 0}}, p_ap, aout);
+        Stat vst, ast;
+        if (can_fuse_video(hw)) vst = Stat{stat_slots_video(), Fr, static_cast<long long>(Fr) * hw};
+        if (can_fuse_audio(a.L)) ast = Stat{stat_slots_audio(), 1, a.L};
+        emit_gemm("conv1x1_proj", geom2(static_cast<long long>(vt)), {{ov, C}, {v.p, C}}, {{0, 0, 0}}, p_vp, vout,
+                  nullptr, nullptr, 0, vst.slots, 1, hw);
+        emit_gemm("conv1x1_proj", geom_audio(a), {{oa, C}, {a.p, C}}, {{0, 0, 0}}, p_ap, aout, nullptr, nullptr, 0,
+                  ast.slots, 3, 0);
         scratch.top = mark;
         v.p = vout;
         a.p = aout;
+        v.st = vst;
+        a.st = ast;
     }
 
     static bool contains(const int* arr, int n, int v) {
@@ -631,8 +714,12 @@ struct Walker {
                     }, "im2col", 0.0, 4.0 * (static_cast<double>(BF) * Cv * H * W + static_cast<double>(Bc) * Ca * L) + 128.0 * (static_cast<double>(BF) * H * W + static_cast<double>(Bc) * L), 2);
                 }
                 emit_gemm("conv_stem", geom2(static_cast<long long>(vtok(v))), {{colv, 64}}, {{0, 0, 0}}, p_sp, u);
-                emit_gemm("conv_temporal", geom_temporal(v), {{u, ch}}, {{0, -1, 0}, {0, 0, 0}, {0, 1, 0}}, p_tp, v.p);
-                emit_gemm("conv_stem", geom2(static_cast<long long>(atok(a))), {{cola, 64}}, {{0, 0, 0}}, p_ac, a.p);
+                const int hw0 = v.H * v.W;
+                if (can_fuse_video(hw0)) v.st = Stat{stat_slots_video(), F(), static_cast<long long>(F()) * hw0};
+                if (can_fuse_audio(a.L)) a.st = Stat{stat_slots_audio(), 1, a.L};
+                emit_gemm("conv_temporal", geom_temporal(v), {{u, ch}}, {{0, -1, 0}, {0, 0, 0}, {0, 1, 0}}, p_tp, v.p,
+                          nullptr, nullptr, 0, v.st.slots, 2, 0);
+                emit_gemm("conv_stem", geom_audio(a), {{cola, 64}}, {{0, 0, 0}}, p_ac, a.p, nullptr, nullptr, 0, a.st.slots, 3, 0);
                 scratch.top = mark;
             }
             vstack.push_back(v);
@@ -729,14 +816,14 @@ struct Walker {
         if (!create) {
             const size_t mark = scratch.top;
             const int Fr = F();
-            act_t* hv = emit_gn(v.p, ch, nullptr, 0, B, Fr * v.H * v.W, vgn, nullptr, 1, 1);
+            act_t* hv = emit_gn(v.p, ch, nullptr, 0, B, Fr * v.H * v.W, vgn, nullptr, 1, 1, &v.st, false);
             ConvGeom g5; g5.rank = 5; g5.dims[0] = v.W; g5.dims[1] = v.H; g5.dims[2] = Fr; g5.dims[3] = B; geom_fill_box(g5);
             std::vector<std::array<int, 3>> taps27;
             for (int kt = 0; kt < 3; ++kt) for (int ky = 0; ky < 3; ++ky) for (int kx = 0; kx < 3; ++kx) taps27.push_back({kx - 1, ky - 1, kt - 1});
             const long long Co = c.video_out_channels, HW = static_cast<long long>(v.H) * v.W;
             const long long os_v[4] = {1, v.W, Co * HW, Fr * Co * HW};
             emit_gemm("conv_head", g5, {{hv, ch}}, taps27, p_vh, nullptr, plan ? plan->out_video : nullptr, os_v, HW);
-            act_t* ha = emit_gn(a.p, ch, nullptr, 0, B, a.L, agn, nullptr, 1, 1);
+            act_t* ha = emit_gn(a.p, ch, nullptr, 0, B, a.L, agn, nullptr, 1, 1, &a.st, false);
             const long long Ca = c.audio_out_channels;
             const long long os_a[4] = {1, Ca * a.L, 0, 0};
             emit_gemm("conv_head", geom_audio(a), {{ha, ch}}, {{-1, 0, 0}, {0, 0, 0}, {1, 0, 0}}, p_ah, nullptr, plan ? plan->out_audio : nullptr, os_a, a.L);

@@ -157,12 +157,23 @@ int build_gemm(const GemmProblem& pr, GemmParams* out) {
         p.ostride_c = pr.ostride_c;
         p.n_valid = pr.n;
     }
+    if (pr.stats) {
+        if (bn < 64 || pr.n % 32 != 0) return fail(MMD_EINVAL, "fused GroupNorm statistics need a wide fp16 output");
+        p.stats = pr.stats;
+        p.stats_cpg = pr.n / 32;
+        p.stats_rows = pr.stats_rows;
+        for (int i = 0; i < 4; ++i) p.stats_mul[i] = pr.stats_mul[i];
+        p.stats_div = pr.stats_div;
+        p.stats_valid_coord = pr.stats_valid_coord;
+        if (pr.stats_rows != 128 && pr.stats_rows != 64) return fail(MMD_EINVAL, "stats_rows %d", pr.stats_rows);
+    }
     return MMD_OK;
 }
 
 int gemm_init_attrs() {
     static bool done = false;
     if (done) return MMD_OK;
+    MMD_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<256>::TOTAL));
     MMD_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<128>::TOTAL));
     MMD_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<64>::TOTAL));
     MMD_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<16>::TOTAL));
@@ -174,7 +185,8 @@ int launch_gemm(const GemmParams& p, int bn, cudaStream_t st) {
     MMD_TRY(gemm_init_attrs());
     const int tiles = p.m_tiles * p.n_tiles;
     const int grid = std::min(tiles, num_sms());
-    if (bn == 128) conv_gemm_kernel<128><<<grid, GEMM_THREADS, GemmSmem<128>::TOTAL, st>>>(p);
+    if (bn == 256) conv_gemm_kernel<256><<<grid, GEMM_THREADS, GemmSmem<256>::TOTAL, st>>>(p);
+    else if (bn == 128) conv_gemm_kernel<128><<<grid, GEMM_THREADS, GemmSmem<128>::TOTAL, st>>>(p);
     else if (bn == 64) conv_gemm_kernel<64><<<grid, GEMM_THREADS, GemmSmem<64>::TOTAL, st>>>(p);
     else if (bn == 16) conv_gemm_kernel<16><<<grid, GEMM_THREADS, GemmSmem<16>::TOTAL, st>>>(p);
     else return fail(MMD_EINVAL, "unsupported BN %d", bn);
@@ -252,23 +264,40 @@ int launch_gn_stats(const GnSrc& s, int ns, int rows, double* sums, cudaStream_t
 }
 
 int launch_gn_apply(const GnSrc& s, int ns, int rows, const double* sums, const float* gamma, const float* beta,
-                    const float* film, int film_ld, int ns_per_batch, int silu, act_t* y, cudaStream_t st) {
+                    const float* film, int film_ld, int ns_per_batch, int silu, act_t* y, cudaStream_t st, int nsub,
+                    long long stat_rows) {
     const int C = s.c1 + s.c2;
     const int rpb = gn_rows_per_block(ns, rows, C);
     dim3 grid((rows + rpb - 1) / rpb, ns);
     gn_apply_kernel<<<grid, 256, (2 * C + 64) * sizeof(float), st>>>(s, rows, rpb, sums, gamma, beta, film, film_ld,
-                                                                      ns_per_batch, silu, y);
+                                                                      ns_per_batch, silu, y, nsub,
+                                                                      stat_rows > 0 ? stat_rows : rows);
+    MMD_CUDA_OK(cudaGetLastError());
+    return MMD_OK;
+}
+
+template <int CPG>
+static int launch_gn_temporal_cpg(const act_t* x, act_t* y, const float* gamma, const float* beta, int B, int F, int P, int C,
+                                  cudaStream_t st) {
+    const long long total = static_cast<long long>(B) * P * 32;
+    const unsigned grid = static_cast<unsigned>((total + 127) / 128);
+    if (F == 16) gn_temporal_kernel<CPG, 16><<<grid, 128, 0, st>>>(x, y, gamma, beta, B, P, C);
+    else if (F == 8) gn_temporal_kernel<CPG, 8><<<grid, 128, 0, st>>>(x, y, gamma, beta, B, P, C);
+    else return fail(MMD_EINVAL, "temporal group norm supports 8 or 16 frames, got %d", F);
     MMD_CUDA_OK(cudaGetLastError());
     return MMD_OK;
 }
 
 int launch_gn_temporal(const act_t* x, act_t* y, const float* gamma, const float* beta, int B, int F, int P, int C,
                        cudaStream_t st) {
-    if (C % 64 != 0) return fail(MMD_EINVAL, "temporal group norm channels %d", C);
-    const long long total = static_cast<long long>(B) * P * 32;
-    gn_temporal_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, y, gamma, beta, B, F, P, C);
-    MMD_CUDA_OK(cudaGetLastError());
-    return MMD_OK;
+    switch (C / 32) {
+        case 2: return launch_gn_temporal_cpg<2>(x, y, gamma, beta, B, F, P, C, st);
+        case 4: return launch_gn_temporal_cpg<4>(x, y, gamma, beta, B, F, P, C, st);
+        case 8: return launch_gn_temporal_cpg<8>(x, y, gamma, beta, B, F, P, C, st);
+        case 12: return launch_gn_temporal_cpg<12>(x, y, gamma, beta, B, F, P, C, st);
+        case 16: return launch_gn_temporal_cpg<16>(x, y, gamma, beta, B, F, P, C, st);
+        default: return fail(MMD_EINVAL, "temporal group norm channels %d unsupported (64/128/256/384/512)", C);
+    }
 }
 
 int launch_resample(const act_t* x, act_t* y, int mode, int n, int h, int w, int c, cudaStream_t st) {
