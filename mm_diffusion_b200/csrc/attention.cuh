@@ -358,4 +358,289 @@ __global__ void __launch_bounds__(ATT_THREADS, (D == 64) ? 2 : 1) attention_kern
     }
 }
 
+
+// ===========================================================================
+// attention64_kernel — head_dim 64 specialisation (all cross-modal sites and the 32x32 spatial self-attention,
+// i.e. > 90 % of the attention FLOPs).  Differences to the generic kernel, all aimed at the softmax warps, which
+// are the limiter at d = 64 (MUFU 16 ex2/clk/SM vs 512 tensor clocks per 128x128 tile):
+//   * O and the row sums l accumulate in TMEM across KV tiles (P·V and P·1 MMAs with accumulate), so the per-tile
+//     "fold previous O into registers" step disappears; O is rescaled in place only when the running maximum
+//     moves by more than 2^8 (warp-uniform decision), which after the first tiles is rare;
+//   * probabilities come from ex2.approx.f16x2 on packed half2 logits: one MUFU op per TWO elements and the result
+//     is already the fp16 operand of the P·V MMA (the row sum is taken by the tensor core from the same rounded P);
+//   * logits are read from TMEM with the next chunk's load in flight.
+// ===========================================================================
+struct Attn64Smem {
+    static constexpr int Q_OFF = 0;
+    static constexpr int K_OFF = 16384;                 // 2 stages
+    static constexpr int V_OFF = K_OFF + 2 * 16384;     // 1 stage
+    static constexpr int P_OFF = V_OFF + 16384;         // 128 x 128 fp16, two 64-key chunks
+    static constexpr int ONES_OFF = P_OFF + 32768;      // K-major ones tile [16][128]: two chunks of 16 rows x 128 B
+    static constexpr int BAR_OFF = ONES_OFF + 4096;
+    static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+    static constexpr int TMEM_COLS = 256;               // S 0..127 | O 128..191 | l 192..207
+};
+
+MMD_DEVINL void tmem_st32(uint32_t taddr, const uint32_t* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+        "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+        "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+MMD_DEVINL void tmem_st16(uint32_t taddr, const uint32_t* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+MMD_DEVINL void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// exp2 of two fp32 logits through one MUFU op: pack to half2, ex2.approx.f16x2
+MMD_DEVINL uint32_t ex2_h2(float lo, float hi) {
+    const __half2 x = __floats2half2_rn(lo, hi);
+    uint32_t r;
+    asm("ex2.approx.f16x2 %0, %1;" : "=r"(r) : "r"(*reinterpret_cast<const uint32_t*>(&x)));
+    return r;
+}
+
+__global__ void __launch_bounds__(ATT_THREADS, 2) attention64_kernel(const __grid_constant__ AttnParams p) {
+    using S = Attn64Smem;
+    constexpr int D = 64;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
+    uint64_t* q_full = bars;        // 1
+    uint64_t* k_full = bars + 1;    // 2
+    uint64_t* k_empty = bars + 3;   // 2
+    uint64_t* v_full = bars + 5;    // 1
+    uint64_t* v_empty = bars + 6;   // 1
+    uint64_t* s_full = bars + 7;    // 1
+    uint64_t* p_ready = bars + 8;   // 1 (128 arrivals)
+    uint64_t* o_full = bars + 9;    // 1
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const AttnWork w = attn_decode(p, blockIdx.x);
+    const int T = w.n_tiles;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&p.q_map);
+        tma_prefetch_desc(&p.k_map);
+        tma_prefetch_desc(&p.v_map);
+        mbar_init(q_full, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
+        mbar_init(v_full, 1);
+        mbar_init(v_empty, 1);
+        mbar_init(s_full, 1);
+        mbar_init(p_ready, 128);
+        mbar_init(o_full, 1);
+        fence_mbar_init();
+    }
+    // constant ones tile for the row-sum MMA
+    for (int i = threadIdx.x; i < 4096 / 16; i += ATT_THREADS)
+        reinterpret_cast<uint4*>(smem + S::ONES_OFF)[i] = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
+    fence_proxy_async_smem();
+    if (warp == 5) tmem_alloc(tmem_slot, S::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_S = tmem_base;
+    const uint32_t tmem_O = tmem_base + 128;
+    const uint32_t tmem_L = tmem_base + 192;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            mbar_expect_tx(q_full, 16384);
+            tma_load_2d(smem + S::Q_OFF, &p.q_map, q_full, p.q_col0 + w.head * D, w.q_row0);
+            for (int t = 0; t < T; ++t) {
+                const int st = t & 1;
+                const uint32_t ph = (t >> 1) & 1;
+                int krow, kvalid;
+                attn_tile(w, t, krow, kvalid);
+                mbar_wait(&k_empty[st], ph ^ 1);
+                mbar_expect_tx(&k_full[st], 16384);
+                tma_load_2d(smem + S::K_OFF + st * 16384, &p.k_map, &k_full[st], p.k_col0 + w.head * D, krow);
+                mbar_wait(v_empty, (t & 1) ^ 1);
+                mbar_expect_tx(v_full, 16384);
+                tma_load_2d(smem + S::V_OFF, &p.v_map, v_full, p.v_col0 + w.head * D, krow);
+            }
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {
+            constexpr uint32_t idesc_qk = umma_idesc_f16(ATT_BQ, ATT_BKV, 0, 0);
+            constexpr uint32_t idesc_pv = umma_idesc_f16(ATT_BQ, D, 0, 1);   // V is MN-major
+            constexpr uint32_t idesc_l = umma_idesc_f16(ATT_BQ, 16, 0, 0);   // P x ones^T
+            const uint32_t q_addr = smem_u32(smem + S::Q_OFF);
+            const uint32_t p_addr = smem_u32(smem + S::P_OFF);
+            const uint32_t v_addr = smem_u32(smem + S::V_OFF);
+            const uint32_t one_addr = smem_u32(smem + S::ONES_OFF);
+            auto issue_qk = [&](int t) {
+                const int st = t & 1;
+                mbar_wait(&k_full[st], (t >> 1) & 1);
+                tc_fence_after();
+                const uint32_t k_addr = smem_u32(smem + S::K_OFF + st * 16384);
+#pragma unroll
+                for (int ks = 0; ks < D / 16; ++ks)
+                    umma_f16_ss(tmem_S, umma_desc_sw128(q_addr + ks * 32, 16, 1024), umma_desc_sw128(k_addr + ks * 32, 16, 1024),
+                                idesc_qk, ks != 0 ? 1u : 0u);
+                umma_commit(&k_empty[st]);
+                umma_commit(s_full);
+            };
+            mbar_wait(q_full, 0);
+            tc_fence_after();
+            issue_qk(0);
+            for (int t = 0; t < T; ++t) {
+                int krow, kvalid;
+                attn_tile(w, t, krow, kvalid);
+                mbar_wait(p_ready, t & 1);
+                mbar_wait(v_full, t & 1);
+                tc_fence_after();
+                const int nks = (kvalid + 15) >> 4;
+                for (int ks = 0; ks < nks; ++ks) {
+                    const uint32_t poff = (ks >> 2) * (ATT_BQ * 128) + (ks & 3) * 32;
+                    umma_f16_ss(tmem_O, umma_desc_sw128(p_addr + poff, 16, 1024),
+                                umma_desc_sw128(v_addr + ks * 2048, ATT_BKV * 128, 1024), idesc_pv, (t | ks) != 0 ? 1u : 0u);
+                }
+                for (int ks = 0; ks < nks; ++ks) {
+                    const uint32_t poff = (ks >> 2) * (ATT_BQ * 128) + (ks & 3) * 32;
+                    const uint32_t ooff = (ks >> 2) * 2048 + (ks & 3) * 32;
+                    umma_f16_ss(tmem_L, umma_desc_sw128(p_addr + poff, 16, 1024), umma_desc_sw128(one_addr + ooff, 16, 1024),
+                                idesc_l, (t | ks) != 0 ? 1u : 0u);
+                }
+                umma_commit(v_empty);
+                umma_commit(o_full);
+                if (t + 1 < T) issue_qk(t + 1);
+            }
+        }
+    } else {
+        const int row = warp * 32 + lane;
+        const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+        const uint32_t s_addr = tmem_S + lane_base;
+        uint8_t* p_smem = smem + S::P_OFF;
+        float m_used = 0.f;
+        for (int t = 0; t < T; ++t) {
+            int krow, kvalid;
+            attn_tile(w, t, krow, kvalid);
+            mbar_wait(s_full, t & 1);
+            tc_fence_after();
+            const bool full_tile = (kvalid == ATT_BKV);
+            // ---- pass 1: row maximum, next chunk's TMEM load in flight
+            uint32_t va[32], vb[32];
+            float mx = -INFINITY;
+            tmem_ld32(s_addr, va);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                tmem_ld_wait();
+                uint32_t* cur = (c & 1) ? vb : va;
+                if (c < 3) tmem_ld32(s_addr + (c + 1) * 32, (c & 1) ? va : vb);
+                if (full_tile) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(cur[i]));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (c * 32 + i < kvalid) mx = fmaxf(mx, __uint_as_float(cur[i]));
+                }
+            }
+            const float mxs = mx * p.scale_log2;
+            if (t == 0) {
+                m_used = mxs;
+            } else {
+                mbar_wait(o_full, (t - 1) & 1);   // P·V of the previous tile is done: P and O may be touched
+                tc_fence_after();
+                if (__any_sync(0xffffffffu, mxs > m_used + 8.0f)) {
+                    const float m_new = fmaxf(m_used, mxs);
+                    const float alpha = ex2_fast(m_used - m_new);
+                    m_used = m_new;
+                    uint32_t o[32];
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        tmem_ld32(tmem_O + lane_base + c * 32, o);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        tmem_st32(tmem_O + lane_base + c * 32, o);
+                    }
+                    tmem_ld16(tmem_L + lane_base, o);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                    tmem_st16(tmem_L + lane_base, o);
+                    tmem_st_wait();
+                }
+            }
+            // ---- pass 2: probabilities (fp16, via ex2.f16x2) -> shared memory
+            const float nm = -m_used;
+            tmem_ld32(s_addr, va);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                tmem_ld_wait();
+                uint32_t* cur = (c & 1) ? vb : va;
+                if (c < 3) tmem_ld32(s_addr + (c + 1) * 32, (c & 1) ? va : vb);
+                uint8_t* chunk = p_smem + (c >> 1) * (ATT_BQ * 128);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint4 pk;
+                    uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int col = c * 32 + j * 8 + 2 * k;
+                        float x0 = fmaf(__uint_as_float(cur[j * 8 + 2 * k]), p.scale_log2, nm);
+                        float x1 = fmaf(__uint_as_float(cur[j * 8 + 2 * k + 1]), p.scale_log2, nm);
+                        if (!full_tile) {
+                            if (col >= kvalid) x0 = -INFINITY;
+                            if (col + 1 >= kvalid) x1 = -INFINITY;
+                        }
+                        pw[k] = ex2_h2(x0, x1);
+                    }
+                    *reinterpret_cast<uint4*>(chunk + sw128_off(row, (c & 1) * 4 + j)) = pk;
+                }
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(p_ready);
+        }
+        mbar_wait(o_full, (T - 1) & 1);
+        tc_fence_after();
+        uint32_t lv[16];
+        tmem_ld16(tmem_L + lane_base, lv);
+        tmem_ld_wait();
+        const float inv_l = 1.f / __uint_as_float(lv[0]);
+        act_t* orow = p.out + static_cast<size_t>(w.q_row0 + row) * p.out_ld + w.head * D;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            tmem_ld32(tmem_O + lane_base + c * 32, v);
+            tmem_ld_wait();
+            if (row < w.q_valid) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint4 pk;
+                    __half2* ph2 = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        ph2[k] = __floats2half2_rn(__uint_as_float(v[j * 8 + 2 * k]) * inv_l, __uint_as_float(v[j * 8 + 2 * k + 1]) * inv_l);
+                    *reinterpret_cast<uint4*>(orow + c * 32 + j * 8) = pk;
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, S::TMEM_COLS);
+    }
+}
+
 }  // namespace mmd

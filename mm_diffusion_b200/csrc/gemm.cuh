@@ -55,8 +55,12 @@ struct GemmSmem {
     static constexpr int A_BYTES = GEMM_BM * 128;
     static constexpr int B_BYTES = BN * 128;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int OUT_CHUNKS = (BN >= 64) ? BN / 64 : 0;
-    static constexpr int OUT_BYTES = OUT_CHUNKS * GEMM_BM * 128;
+    // epilogue staging: two buffers of HALF columns each, rotated per half-tile, so the TMA store of one half
+    // drains while the next half is being converted (a single buffer serialises store latency with the epilogue)
+    static constexpr int HALF = (BN >= 128) ? 128 : BN;          // columns per staging buffer / TMA store group
+    static constexpr int NHALF = (BN >= 64) ? BN / HALF : 0;
+    static constexpr int OUT_BUF = (BN >= 64) ? (HALF / 64) * GEMM_BM * 128 : 0;
+    static constexpr int OUT_BYTES = 2 * OUT_BUF;
     static constexpr int STAGES = (BN >= 256) ? 3 : ((BN >= 128) ? 5 : 8);
     static constexpr int BAR_BYTES = 256 + 2 * 32 * 2 * 4;   // barriers + GroupNorm bins [2 domains][32 groups][2]
     static constexpr int TOTAL = STAGES * STAGE_BYTES + OUT_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
@@ -184,6 +188,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
         const int row = quad * 32 + lane;
         const bool leader = (threadIdx.x == 64);
         int it = 0;
+        uint32_t obuf_sel = 0;   // staging buffer rotation (leader's bulk-group order matches it)
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
@@ -197,91 +202,104 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
             const float* bias = p.bias + n_idx * BN;
 
             if constexpr (BN >= 64) {
-                if (leader) tma_store_wait_read0();  // previous tile's store has drained the staging buffer
+                constexpr int HALF = S::HALF;
                 if (p.stats != nullptr) gn_bins[threadIdx.x - 64] = 0.f;
-                named_bar_sync(1, 128);
+                int valid_rows = GEMM_BM;
+                if (p.stats != nullptr && p.stats_valid_coord >= 0)
+                    valid_rows = min(GEMM_BM, p.dims[p.stats_valid_coord] - org[p.stats_valid_coord + 1]);
 #pragma unroll 1
-                for (int cc = 0; cc < BN / 32; ++cc) {
-                    uint32_t v[32];
-                    tmem_ld32(t_addr + cc * 32, v);
-                    tmem_ld_wait();
-                    uint8_t* chunk = out_stage + (cc >> 1) * (GEMM_BM * 128);
+                for (int hf = 0; hf < S::NHALF; ++hf) {
+                    uint8_t* obuf = out_stage + (obuf_sel & 1) * S::OUT_BUF;
+                    ++obuf_sel;
+                    if (leader) tma_store_wait_read1();  // the store issued two halves ago has drained this buffer
+                    named_bar_sync(1, 128);
+#pragma unroll 1
+                    for (int cc = 0; cc < HALF / 32; ++cc) {
+                        uint32_t v[32];
+                        tmem_ld32(t_addr + hf * HALF + cc * 32, v);
+                        tmem_ld_wait();
+                        uint8_t* chunk = obuf + (cc >> 1) * (GEMM_BM * 128);
+                        const float* bcol = bias + hf * HALF + cc * 32;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + cc * 32 + j * 8));
-                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + cc * 32 + j * 8 + 4));
-                        __half2 h0 = __floats2half2_rn(__uint_as_float(v[j * 8 + 0]) + b0.x, __uint_as_float(v[j * 8 + 1]) + b0.y);
-                        __half2 h1 = __floats2half2_rn(__uint_as_float(v[j * 8 + 2]) + b0.z, __uint_as_float(v[j * 8 + 3]) + b0.w);
-                        __half2 h2 = __floats2half2_rn(__uint_as_float(v[j * 8 + 4]) + b1.x, __uint_as_float(v[j * 8 + 5]) + b1.y);
-                        __half2 h3 = __floats2half2_rn(__uint_as_float(v[j * 8 + 6]) + b1.z, __uint_as_float(v[j * 8 + 7]) + b1.w);
-                        uint4 pk;
-                        pk.x = *reinterpret_cast<uint32_t*>(&h0);
-                        pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                        pk.z = *reinterpret_cast<uint32_t*>(&h2);
-                        pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                        *reinterpret_cast<uint4*>(chunk + sw128_off(row, (cc & 1) * 4 + j)) = pk;
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bcol + j * 8));
+                            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bcol + j * 8 + 4));
+                            __half2 h0 = __floats2half2_rn(__uint_as_float(v[j * 8 + 0]) + b0.x, __uint_as_float(v[j * 8 + 1]) + b0.y);
+                            __half2 h1 = __floats2half2_rn(__uint_as_float(v[j * 8 + 2]) + b0.z, __uint_as_float(v[j * 8 + 3]) + b0.w);
+                            __half2 h2 = __floats2half2_rn(__uint_as_float(v[j * 8 + 4]) + b1.x, __uint_as_float(v[j * 8 + 5]) + b1.y);
+                            __half2 h3 = __floats2half2_rn(__uint_as_float(v[j * 8 + 6]) + b1.z, __uint_as_float(v[j * 8 + 7]) + b1.w);
+                            uint4 pk;
+                            pk.x = *reinterpret_cast<uint32_t*>(&h0);
+                            pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                            pk.z = *reinterpret_cast<uint32_t*>(&h2);
+                            pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                            *reinterpret_cast<uint4*>(chunk + sw128_off(row, (cc & 1) * 4 + j)) = pk;
+                        }
                     }
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-                fence_proxy_async_smem();
-                named_bar_sync(1, 128);
-                if (leader) {
-                    int c[5] = {0, org[1], org[2], org[3], org[4]};
-#pragma unroll
-                    for (int ch = 0; ch < BN / 64; ++ch) {
-                        c[0] = n_idx * BN + ch * 64;
-                        tma_store_nd(p.rank, &p.o_map, out_stage + ch * (GEMM_BM * 128), c);
+                    if (hf == S::NHALF - 1) {   // all accumulator columns have been read: hand the TMEM stage back
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
                     }
-                    tma_store_commit();
-                }
-                if (p.stats != nullptr) {
-                    // column sums of the staged fp16 tile: thread = (8-column octet, run of NOCT rows)
-                    constexpr int NOCT = BN / 8;
-                    const int et = threadIdx.x - 64;
-                    const int oct = et % NOCT;
-                    const int r_begin = (et / NOCT) * NOCT;
-                    int valid_rows = GEMM_BM;
-                    if (p.stats_valid_coord >= 0)
-                        valid_rows = min(GEMM_BM, p.dims[p.stats_valid_coord] - org[p.stats_valid_coord + 1]);
-                    float sm[8], sq[8];
+                    fence_proxy_async_smem();
+                    named_bar_sync(1, 128);
+                    if (leader) {
+                        int c[5] = {0, org[1], org[2], org[3], org[4]};
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) { sm[i] = 0.f; sq[i] = 0.f; }
-                    const uint8_t* chunk = out_stage + (oct >> 3) * (GEMM_BM * 128);
+                        for (int ch = 0; ch < HALF / 64; ++ch) {
+                            c[0] = n_idx * BN + hf * HALF + ch * 64;
+                            tma_store_nd(p.rank, &p.o_map, obuf + ch * (GEMM_BM * 128), c);
+                        }
+                        tma_store_commit();
+                    }
+                    if (p.stats != nullptr) {
+                        // column sums of the staged fp16 half-tile: thread = (8-column octet, run of NOCT rows)
+                        constexpr int NOCT = HALF / 8;
+                        const int et = threadIdx.x - 64;
+                        const int oct = et % NOCT;
+                        const int r_begin = (et / NOCT) * NOCT;
+                        float sm[8], sq[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { sm[i] = 0.f; sq[i] = 0.f; }
+                        const uint8_t* chunk = obuf + (oct >> 3) * (GEMM_BM * 128);
 #pragma unroll 4
-                    for (int rr = 0; rr < NOCT; ++rr) {
-                        const int r = r_begin + rr;
-                        if (r < valid_rows) {
-                            const uint4 raw = *reinterpret_cast<const uint4*>(chunk + sw128_off(r, oct & 7));
-                            const __half2* h = reinterpret_cast<const __half2*>(&raw);
+                        for (int rr = 0; rr < NOCT; ++rr) {
+                            const int r = r_begin + rr;
+                            if (r < valid_rows) {
+                                const uint4 raw = *reinterpret_cast<const uint4*>(chunk + sw128_off(r, oct & 7));
+                                const __half2* h = reinterpret_cast<const __half2*>(&raw);
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const float2 f = __half22float2(h[i]);
-                                sm[2 * i] += f.x; sq[2 * i] = fmaf(f.x, f.x, sq[2 * i]);
-                                sm[2 * i + 1] += f.y; sq[2 * i + 1] = fmaf(f.y, f.y, sq[2 * i + 1]);
+                                for (int i = 0; i < 4; ++i) {
+                                    const float2 f = __half22float2(h[i]);
+                                    sm[2 * i] += f.x; sq[2 * i] = fmaf(f.x, f.x, sq[2 * i]);
+                                    sm[2 * i + 1] += f.y; sq[2 * i + 1] = fmaf(f.y, f.y, sq[2 * i + 1]);
+                                }
                             }
                         }
-                    }
-                    const int col0 = n_idx * BN + oct * 8;
-                    const int g0 = (n_idx * BN) / p.stats_cpg;
-                    const int dl = r_begin / p.stats_rows;   // 0 or 1: domain inside the tile
-                    float* bins = gn_bins + dl * 64;
-                    int g = col0 / p.stats_cpg;
-                    float as = 0.f, aq = 0.f;
+                        const int col0 = n_idx * BN + hf * HALF + oct * 8;
+                        const int g0 = (n_idx * BN) / p.stats_cpg;
+                        const int dl = r_begin / p.stats_rows;   // 0 or 1: domain inside the tile
+                        float* bins = gn_bins + dl * 64;
+                        int g = col0 / p.stats_cpg;
+                        float as = 0.f, aq = 0.f;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int gi = (col0 + i) / p.stats_cpg;
-                        if (gi != g) {
-                            atomicAdd(&bins[2 * (g - g0)], as);
-                            atomicAdd(&bins[2 * (g - g0) + 1], aq);
-                            g = gi; as = 0.f; aq = 0.f;
+                        for (int i = 0; i < 8; ++i) {
+                            const int gi = (col0 + i) / p.stats_cpg;
+                            if (gi != g) {
+                                atomicAdd(&bins[2 * (g - g0)], as);
+                                atomicAdd(&bins[2 * (g - g0) + 1], aq);
+                                g = gi; as = 0.f; aq = 0.f;
+                            }
+                            as += sm[i]; aq += sq[i];
                         }
-                        as += sm[i]; aq += sq[i];
+                        atomicAdd(&bins[2 * (g - g0)], as);
+                        atomicAdd(&bins[2 * (g - g0) + 1], aq);
                     }
-                    atomicAdd(&bins[2 * (g - g0)], as);
-                    atomicAdd(&bins[2 * (g - g0) + 1], aq);
+                }
+                if (p.stats != nullptr) {
                     named_bar_sync(1, 128);
+                    const int et = threadIdx.x - 64;
+                    const int g0 = (n_idx * BN) / p.stats_cpg;
                     const int dom_base = (org[1] * p.stats_mul[0] + org[2] * p.stats_mul[1] + org[3] * p.stats_mul[2] +
                                           org[4] * p.stats_mul[3]) / p.stats_div;
                     const int bdl = et >> 6, bg = (et & 63) >> 1;

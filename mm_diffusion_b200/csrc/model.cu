@@ -57,6 +57,7 @@ struct StepInfo {
     double flops = 0;     // algorithmic FLOPs (multiply-add = 2)
     double bytes = 0;     // algorithmic bytes (inputs + outputs + weights, fp16 activations)
     int kernels = 1;      // kernel launches inside the step
+    int stream = 0;       // 0 = video / main branch, 1 = audio branch, -1 = cross-stream sync point
 };
 
 struct Plan {
@@ -68,8 +69,10 @@ struct Plan {
     float *in_video = nullptr, *in_audio = nullptr, *t_dev = nullptr, *out_video = nullptr, *out_audio = nullptr;
     int* shifts_dev = nullptr;
     cudaGraphExec_t graph = nullptr;
+    std::vector<cudaEvent_t> events;   // fork / join events of the two-branch capture
     ~Plan() {
         if (graph) cudaGraphExecDestroy(graph);
+        for (auto e : events) cudaEventDestroy(e);
         if (ws) cudaFree(ws);
     }
 };
@@ -96,13 +99,15 @@ struct MmdModel {
     size_t emb_w_off = 0, emb_b_off = 0;
     std::map<int, std::unique_ptr<Plan>> plans;
     bool use_graph = true;
-    cudaStream_t cap_stream = nullptr;
+    bool two_streams = true;   // MMD_ONE_STREAM=1 captures everything on one stream
+    cudaStream_t cap_stream = nullptr, cap_stream2 = nullptr;
     ~MmdModel() {
         plans.clear();
         if (w32) cudaFree(w32);
         if (wpk) cudaFree(wpk);
         if (bpk) cudaFree(bpk);
         if (cap_stream) cudaStreamDestroy(cap_stream);
+        if (cap_stream2) cudaStreamDestroy(cap_stream2);
     }
 };
 
@@ -123,7 +128,10 @@ struct Walker {
     bool create;
     Plan* plan = nullptr;
     int B = 1;
-    Arena persist, scratch, stats;   // stats: GroupNorm accumulators, zeroed once per forward
+    Arena persist, scratch, scratch_a, stats;   // scratch per branch (video / audio run concurrently); stats: GroupNorm
+                                                // accumulators, zeroed once per forward
+    int cur = 0;                                // branch being emitted: 0 video (main stream), 1 audio
+    Arena& S() { return cur == 1 ? scratch_a : scratch; }
     int err = MMD_OK;
     size_t w32_top = 0, wpk_top = 0, bpk_top = 0;
     int shift_slot = 0;
@@ -237,8 +245,8 @@ struct Walker {
 
     // ---------------- activations
     act_t* alloc_p(size_t elems) { return static_cast<act_t*>(persist.take(elems * sizeof(act_t))); }
-    act_t* alloc_s(size_t elems) { return static_cast<act_t*>(scratch.take(elems * sizeof(act_t))); }
-    void* alloc_s_bytes(size_t bytes) { return scratch.take(bytes); }
+    act_t* alloc_s(size_t elems) { return static_cast<act_t*>(S().take(elems * sizeof(act_t))); }
+    void* alloc_s_bytes(size_t bytes) { return S().take(bytes); }
     size_t vtok(const VT& v) const { return static_cast<size_t>(B) * F() * v.H * v.W; }
     size_t atok(const AT& a) const { return static_cast<size_t>(B) * a.L; }
     bool emitting() const { return plan != nullptr && persist.base != nullptr; }
@@ -247,7 +255,15 @@ struct Walker {
         if (!emitting()) return;
         plan->steps.push_back(std::move(fn));
         StepInfo si;
-        si.kind = kind; si.flops = flops; si.bytes = bytes; si.kernels = kernels;
+        si.kind = kind; si.flops = flops; si.bytes = bytes; si.kernels = kernels; si.stream = cur;
+        plan->info.push_back(si);
+    }
+    // both branches wait for each other (graph edges; a no-op when the plan runs on one stream)
+    void sync_branches() {
+        if (!emitting()) return;
+        plan->steps.push_back([](cudaStream_t) { return MMD_OK; });
+        StepInfo si;
+        si.kind = "sync"; si.kernels = 0; si.stream = -1;
         plan->info.push_back(si);
     }
 
@@ -370,7 +386,8 @@ struct Walker {
         if (create) return nullptr;
         const size_t tokens = vt ? vtok(*vt) : atok(*at);
         act_t* out = alloc_p(tokens * C);
-        const size_t mark = scratch.top;
+        cur = (kind == 2) ? 1 : 0;
+        const size_t mark = S().top;
         act_t* xn;
         if (kind == 0) {
             xn = emit_gn(x, C, nullptr, 0, B * F(), vt->H * vt->W, gn, nullptr, 1, 0, in_st, true);
@@ -414,7 +431,8 @@ struct Walker {
             if (out_st) *out_st = Stat{slots, 1, at->L};
         }
         emit_gemm("conv1x1_proj", gtok, {{o, C}, {x, C}}, {{0, 0, 0}}, pp, out, nullptr, nullptr, 0, slots, skind, shw);
-        scratch.top = mark;
+        S().top = mark;
+        cur = 0;
         return out;
     }
 
@@ -477,7 +495,8 @@ struct Walker {
                 if (down) { vo.H = v.H / 2; vo.W = v.W / 2; }
                 if (up) { vo.H = v.H * 2; vo.W = v.W * 2; }
                 vo.p = alloc_p(static_cast<size_t>(B) * Fr * vo.H * vo.W * cout);
-                const size_t mark = scratch.top;
+                cur = 0;
+                const size_t mark = S().top;
                 const int hw = v.H * v.W;
                 act_t* h0 = emit_gn(v.p, v.C, v2, vc2, B, Fr * hw, vin_gn, nullptr, 1, 1, &v.st, false);
                 act_t* u = alloc_s(vtok(v) * cout);
@@ -515,14 +534,15 @@ struct Walker {
                 if (can_fuse_video(hwo)) vo.st = Stat{stat_slots_video(), Fr, static_cast<long long>(Fr) * hwo};
                 emit_gemm("conv1x1_out", geom2(static_cast<long long>(B) * Fr * hwo), srcs, {{0, 0, 0}}, p_vo, vo.p,
                           nullptr, nullptr, 0, vo.st.slots, 1, hwo);
-                scratch.top = mark;
+                S().top = mark;
             }
             // ---------------- audio branch
             {
                 if (down) ao.L = a.L / 4;
                 if (up) ao.L = a.L * 4;
                 ao.p = alloc_p(static_cast<size_t>(B) * ao.L * cout);
-                const size_t mark = scratch.top;
+                cur = 1;
+                const size_t mark = S().top;
                 act_t* h0 = emit_gn(a.p, a.C, a2, ac2, B, a.L, ain_gn, nullptr, 1, 1, &a.st, false);
                 act_t* h1 = alloc_s(atok(a) * cout);
                 AT ain{h0, cin, a.L};
@@ -552,7 +572,8 @@ struct Walker {
                 if (a2) srcs.push_back({a2, ac2});
                 if (can_fuse_audio(ao.L)) ao.st = Stat{stat_slots_audio(), 1, ao.L};
                 emit_gemm("conv1x1_out", geom_audio(ao), srcs, {{0, 0, 0}}, p_ao, ao.p, nullptr, nullptr, 0, ao.st.slots, 3, 0);
-                scratch.top = mark;
+                S().top = mark;
+                cur = 0;
             }
         }
         // ---------------- in-block self attention (multimodal_unet.py:485-493)
@@ -602,27 +623,38 @@ struct Walker {
         const size_t vt = vtok(v), at = atok(a);
         act_t* vout = alloc_p(vt * C);
         act_t* aout = alloc_p(at * C);
-        const size_t mark = scratch.top;
+        const size_t mark_v = scratch.top, mark_a = scratch_a.top;
+        cur = 0;
         act_t* vnrm = emit_gn(v.p, C, nullptr, 0, B, Fr * hw, vn, nullptr, 1, 0, &v.st, false);
-        act_t* anrm = emit_gn(a.p, C, nullptr, 0, B, a.L, an, nullptr, 1, 0, &a.st, false);
         act_t* vqkv = alloc_s(vt * 3 * C);
-        act_t* aqkv = alloc_s(at * 3 * C);
         emit_gemm("conv1x1_qkv", geom2(static_cast<long long>(vt)), {{vnrm, C}}, {{0, 0, 0}}, p_vq, vqkv);
-        emit_gemm("conv1x1_qkv", geom_audio(a), {{anrm, C}}, {{0, 0, 0}}, p_aq, aqkv);
         act_t* ov = alloc_s(vt * C);
+        cur = 1;
+        act_t* anrm = emit_gn(a.p, C, nullptr, 0, B, a.L, an, nullptr, 1, 0, &a.st, false);
+        act_t* aqkv = alloc_s(at * 3 * C);
+        emit_gemm("conv1x1_qkv", geom_audio(a), {{anrm, C}}, {{0, 0, 0}}, p_aq, aqkv);
         act_t* oa = alloc_s(at * C);
         const int* sdev = (shift && plan) ? plan->shifts_dev + slot : nullptr;
-        // video queries attend audio keys/values and vice versa (multimodal_unet.py:530-559)
+        // video queries attend audio keys/values and vice versa (multimodal_unet.py:530-559): each branch needs the
+        // other's qkv projection, and nobody may recycle its qkv scratch before both attention kernels are done
+        sync_branches();
+        cur = 0;
         emit_attn(vqkv, 3 * C, 0, vt, aqkv, 3 * C, C, at, aqkv, 2 * C, ov, C, heads, d, Fr, hw, apf, window, sdev);
+        cur = 1;
         emit_attn(aqkv, 3 * C, 0, at, vqkv, 3 * C, C, vt, vqkv, 2 * C, oa, C, heads, d, Fr, apf, hw, window, sdev);
+        sync_branches();
+        cur = 0;
         Stat vst, ast;
         if (can_fuse_video(hw)) vst = Stat{stat_slots_video(), Fr, static_cast<long long>(Fr) * hw};
         if (can_fuse_audio(a.L)) ast = Stat{stat_slots_audio(), 1, a.L};
         emit_gemm("conv1x1_proj", geom2(static_cast<long long>(vt)), {{ov, C}, {v.p, C}}, {{0, 0, 0}}, p_vp, vout,
                   nullptr, nullptr, 0, vst.slots, 1, hw);
+        cur = 1;
         emit_gemm("conv1x1_proj", geom_audio(a), {{oa, C}, {a.p, C}}, {{0, 0, 0}}, p_ap, aout, nullptr, nullptr, 0,
                   ast.slots, 3, 0);
-        scratch.top = mark;
+        cur = 0;
+        scratch.top = mark_v;
+        scratch_a.top = mark_a;
         v.p = vout;
         a.p = aout;
         v.st = vst;
@@ -673,6 +705,7 @@ struct Walker {
                     MMD_CUDA_OK(cudaGetLastError());
                     return MMD_OK;
                 }, "time_embed", 2.0 * Bc * (2.0 * E * E + static_cast<double>(rows) * E), 4.0 * (static_cast<double>(rows) * E + 2.0 * E * E), 2);
+                sync_branches();   // the statistics memset and the FiLM table precede both branches
             }
         }
         // ---- input blocks
@@ -695,32 +728,47 @@ struct Walker {
             if (!create) {
                 v.p = alloc_p(vtok(v) * ch);
                 a.p = alloc_p(atok(a) * ch);
-                const size_t mark = scratch.top;
-                act_t* colv = alloc_s(vtok(v) * 64);
-                act_t* cola = alloc_s(atok(a) * 64);
-                act_t* u = alloc_s(vtok(v) * ch);
-                if (emitting()) {
-                    const float* vin = plan->in_video;
-                    const float* ain = plan->in_audio;
-                    const int BF = B * F(), Cv = c.video_c, H = c.video_h, W = c.video_w, Bc = B, Ca = c.audio_c, L = c.audio_l;
-                    push([=](cudaStream_t st) -> int {
-                        const long long tv = static_cast<long long>(BF) * H * W * 8;
-                        im2col_video_kernel<<<static_cast<unsigned>((tv + 255) / 256), 256, 0, st>>>(vin, colv, BF, Cv, H, W);
-                        MMD_CUDA_OK(cudaGetLastError());
-                        const long long ta = static_cast<long long>(Bc) * L * 8;
-                        im2col_audio_kernel<<<static_cast<unsigned>((ta + 255) / 256), 256, 0, st>>>(ain, cola, Bc, Ca, L);
-                        MMD_CUDA_OK(cudaGetLastError());
-                        return MMD_OK;
-                    }, "im2col", 0.0, 4.0 * (static_cast<double>(BF) * Cv * H * W + static_cast<double>(Bc) * Ca * L) + 128.0 * (static_cast<double>(BF) * H * W + static_cast<double>(Bc) * L), 2);
-                }
-                emit_gemm("conv_stem", geom2(static_cast<long long>(vtok(v))), {{colv, 64}}, {{0, 0, 0}}, p_sp, u);
                 const int hw0 = v.H * v.W;
-                if (can_fuse_video(hw0)) v.st = Stat{stat_slots_video(), F(), static_cast<long long>(F()) * hw0};
-                if (can_fuse_audio(a.L)) a.st = Stat{stat_slots_audio(), 1, a.L};
-                emit_gemm("conv_temporal", geom_temporal(v), {{u, ch}}, {{0, -1, 0}, {0, 0, 0}, {0, 1, 0}}, p_tp, v.p,
-                          nullptr, nullptr, 0, v.st.slots, 2, 0);
-                emit_gemm("conv_stem", geom_audio(a), {{cola, 64}}, {{0, 0, 0}}, p_ac, a.p, nullptr, nullptr, 0, a.st.slots, 3, 0);
-                scratch.top = mark;
+                {   // video branch
+                    cur = 0;
+                    const size_t mark = S().top;
+                    act_t* colv = alloc_s(vtok(v) * 64);
+                    act_t* u = alloc_s(vtok(v) * ch);
+                    if (emitting()) {
+                        const float* vin = plan->in_video;
+                        const int BF = B * F(), Cv = c.video_c, H = c.video_h, W = c.video_w;
+                        push([=](cudaStream_t st) -> int {
+                            const long long tv = static_cast<long long>(BF) * H * W * 8;
+                            im2col_video_kernel<<<static_cast<unsigned>((tv + 255) / 256), 256, 0, st>>>(vin, colv, BF, Cv, H, W);
+                            MMD_CUDA_OK(cudaGetLastError());
+                            return MMD_OK;
+                        }, "im2col", 0.0, (4.0 * Cv + 128.0) * static_cast<double>(BF) * H * W, 1);
+                    }
+                    emit_gemm("conv_stem", geom2(static_cast<long long>(vtok(v))), {{colv, 64}}, {{0, 0, 0}}, p_sp, u);
+                    if (can_fuse_video(hw0)) v.st = Stat{stat_slots_video(), F(), static_cast<long long>(F()) * hw0};
+                    emit_gemm("conv_temporal", geom_temporal(v), {{u, ch}}, {{0, -1, 0}, {0, 0, 0}, {0, 1, 0}}, p_tp, v.p,
+                              nullptr, nullptr, 0, v.st.slots, 2, 0);
+                    S().top = mark;
+                }
+                {   // audio branch
+                    cur = 1;
+                    const size_t mark = S().top;
+                    act_t* cola = alloc_s(atok(a) * 64);
+                    if (emitting()) {
+                        const float* ain = plan->in_audio;
+                        const int Bc = B, Ca = c.audio_c, L = c.audio_l;
+                        push([=](cudaStream_t st) -> int {
+                            const long long ta = static_cast<long long>(Bc) * L * 8;
+                            im2col_audio_kernel<<<static_cast<unsigned>((ta + 255) / 256), 256, 0, st>>>(ain, cola, Bc, Ca, L);
+                            MMD_CUDA_OK(cudaGetLastError());
+                            return MMD_OK;
+                        }, "im2col", 0.0, (4.0 * Ca + 128.0) * static_cast<double>(Bc) * L, 1);
+                    }
+                    if (can_fuse_audio(a.L)) a.st = Stat{stat_slots_audio(), 1, a.L};
+                    emit_gemm("conv_stem", geom_audio(a), {{cola, 64}}, {{0, 0, 0}}, p_ac, a.p, nullptr, nullptr, 0, a.st.slots, 3, 0);
+                    S().top = mark;
+                    cur = 0;
+                }
             }
             vstack.push_back(v);
             astack.push_back(a);
@@ -814,8 +862,9 @@ struct Walker {
         const PackedConv* p_ah = pack("audio_out.head", c.audio_out_channels, {{ahead.w, ch0, 3}}, 0, {ahead.b}, 16);
         const PackedConv* p_vh = pack("video_out.head", c.video_out_channels, {{vhead.w, ch0, 27}}, 0, {vhead.b}, 16);
         if (!create) {
-            const size_t mark = scratch.top;
+            const size_t mark = scratch.top, mark_a = scratch_a.top;
             const int Fr = F();
+            cur = 0;
             act_t* hv = emit_gn(v.p, ch, nullptr, 0, B, Fr * v.H * v.W, vgn, nullptr, 1, 1, &v.st, false);
             ConvGeom g5; g5.rank = 5; g5.dims[0] = v.W; g5.dims[1] = v.H; g5.dims[2] = Fr; g5.dims[3] = B; geom_fill_box(g5);
             std::vector<std::array<int, 3>> taps27;
@@ -823,11 +872,15 @@ struct Walker {
             const long long Co = c.video_out_channels, HW = static_cast<long long>(v.H) * v.W;
             const long long os_v[4] = {1, v.W, Co * HW, Fr * Co * HW};
             emit_gemm("conv_head", g5, {{hv, ch}}, taps27, p_vh, nullptr, plan ? plan->out_video : nullptr, os_v, HW);
+            cur = 1;
             act_t* ha = emit_gn(a.p, ch, nullptr, 0, B, a.L, agn, nullptr, 1, 1, &a.st, false);
             const long long Ca = c.audio_out_channels;
             const long long os_a[4] = {1, Ca * a.L, 0, 0};
             emit_gemm("conv_head", geom_audio(a), {{ha, ch}}, {{-1, 0, 0}, {0, 0, 0}, {1, 0, 0}}, p_ah, nullptr, plan ? plan->out_audio : nullptr, os_a, a.L);
+            cur = 0;
+            sync_branches();   // join: the caller's stream continues after both heads
             scratch.top = mark;
+            scratch_a.top = mark_a;
         }
         if (create) m.emb_rows = emb_row_top;
     }
@@ -843,6 +896,7 @@ static int ensure_device(MmdModel* m) {
     MMD_CUDA_OK(cudaMemset(m->wpk, 0, sizeof(act_t) * std::max<size_t>(m->wpk_halves, 8)));
     MMD_CUDA_OK(cudaMemset(m->bpk, 0, sizeof(float) * std::max<size_t>(m->bpk_floats, 4)));
     MMD_CUDA_OK(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
+    MMD_CUDA_OK(cudaStreamCreateWithFlags(&m->cap_stream2, cudaStreamNonBlocking));
     return MMD_OK;
 }
 
@@ -881,8 +935,9 @@ static int build_plan(MmdModel* m, int B, Plan** out) {
     auto al = [](size_t x) { return (x + 1023) & ~size_t(1023); };
     const size_t io_bytes = al(vin) + al(ain) + al(vout) + al(aout) + al(sizeof(float) * B) + al(sizeof(int) * 64);
     const size_t p_bytes = al(dry.persist.peak) + 1024, s_bytes = al(dry.scratch.peak) + 1024;
+    const size_t sa_bytes = al(dry.scratch_a.peak) + 1024;
     const size_t st_bytes = al(dry.stats.peak) + 1024;
-    plan->ws_bytes = io_bytes + p_bytes + s_bytes + st_bytes;
+    plan->ws_bytes = io_bytes + p_bytes + s_bytes + sa_bytes + st_bytes;
     MMD_CUDA_OK(cudaMalloc(&plan->ws, plan->ws_bytes));
     MMD_CUDA_OK(cudaMemset(plan->ws, 0, plan->ws_bytes));
     uint8_t* q = plan->ws;
@@ -897,10 +952,12 @@ static int build_plan(MmdModel* m, int B, Plan** out) {
     w.plan = plan.get();
     w.persist.base = q; w.persist.cap = p_bytes;
     w.scratch.base = q + p_bytes; w.scratch.cap = s_bytes;
-    w.stats.base = q + p_bytes + s_bytes; w.stats.cap = st_bytes;
+    w.scratch_a.base = q + p_bytes + s_bytes; w.scratch_a.cap = sa_bytes;
+    w.stats.base = q + p_bytes + s_bytes + sa_bytes; w.stats.cap = st_bytes;
     w.walk();
     if (w.bad()) return w.err;
-    if (w.persist.peak > p_bytes || w.scratch.peak > s_bytes || w.stats.peak > st_bytes) return fail(MMD_ESTATE, "internal: arena overflow");
+    if (w.persist.peak > p_bytes || w.scratch.peak > s_bytes || w.scratch_a.peak > sa_bytes || w.stats.peak > st_bytes)
+        return fail(MMD_ESTATE, "internal: arena overflow");
     *out = plan.get();
     m->plans[B] = std::move(plan);
     return MMD_OK;
@@ -911,7 +968,7 @@ static size_t dry_workspace(MmdModel* m, int B) {
     dry.B = B;
     dry.walk();
     if (dry.bad()) return 0;
-    return dry.persist.peak + dry.scratch.peak + dry.stats.peak + (1 << 20);
+    return dry.persist.peak + dry.scratch.peak + dry.scratch_a.peak + dry.stats.peak + (1 << 20);
 }
 
 }  // namespace mmd
@@ -926,6 +983,8 @@ int mmd_model_create(const MmdConfig* cfg, MmdModel** out) {
     m->cfg = *cfg;
     const char* ng = getenv("MMD_NO_GRAPH");
     m->use_graph = !(ng && ng[0] == '1');
+    const char* os = getenv("MMD_ONE_STREAM");
+    m->two_streams = !(os && os[0] == '1');
     Walker w(*m, true);
     w.walk();
     if (w.bad()) return w.err;
@@ -1076,10 +1135,42 @@ int mmd_model_forward(MmdModel* m, int batch, const float* video_in, const float
             // pack ops (if any) ran on `st`; make sure the capture stream sees a quiescent device
             MMD_CUDA_OK(cudaStreamSynchronize(st));
             cudaGraph_t g = nullptr;
+            // two-branch capture: video / main steps on cap_stream, audio steps on cap_stream2; "sync" steps make the
+            // branches wait for each other (graph edges), so small audio kernels overlap the video ones
+            const bool two = m->two_streams;
+            auto new_event = [&]() -> cudaEvent_t {
+                cudaEvent_t ev = nullptr;
+                cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+                plan->events.push_back(ev);
+                return ev;
+            };
             MMD_CUDA_OK(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal));
             int r = MMD_OK;
-            for (auto& step : plan->steps) { r = step(m->cap_stream); if (r != MMD_OK) break; }
+            cudaError_t ce = cudaSuccess;
+            auto cross_sync = [&]() {
+                cudaEvent_t e0 = new_event(), e1 = new_event();
+                ce = cudaEventRecord(e0, m->cap_stream);
+                if (ce == cudaSuccess) ce = cudaEventRecord(e1, m->cap_stream2);
+                if (ce == cudaSuccess) ce = cudaStreamWaitEvent(m->cap_stream, e1, 0);
+                if (ce == cudaSuccess) ce = cudaStreamWaitEvent(m->cap_stream2, e0, 0);
+            };
+            if (two) {   // fork: pull the second stream into the capture
+                cudaEvent_t e0 = new_event();
+                ce = cudaEventRecord(e0, m->cap_stream);
+                if (ce == cudaSuccess) ce = cudaStreamWaitEvent(m->cap_stream2, e0, 0);
+            }
+            for (size_t i = 0; i < plan->steps.size() && r == MMD_OK && ce == cudaSuccess; ++i) {
+                const int sid = plan->info[i].stream;
+                if (sid < 0) { if (two) cross_sync(); continue; }
+                r = plan->steps[i]((two && sid == 1) ? m->cap_stream2 : m->cap_stream);
+            }
+            if (two && ce == cudaSuccess) {   // join (the plan ends with a sync step, this only closes the fork)
+                cudaEvent_t e1 = new_event();
+                ce = cudaEventRecord(e1, m->cap_stream2);
+                if (ce == cudaSuccess) ce = cudaStreamWaitEvent(m->cap_stream, e1, 0);
+            }
             cudaError_t e = cudaStreamEndCapture(m->cap_stream, &g);
+            if (ce != cudaSuccess) { if (g) cudaGraphDestroy(g); return fail(MMD_ECUDA, "two-branch capture: %s", cudaGetErrorString(ce)); }
             if (r != MMD_OK) { if (g) cudaGraphDestroy(g); return r; }
             if (e != cudaSuccess) return fail(MMD_ECUDA, "graph capture: %s", cudaGetErrorString(e));
             e = cudaGraphInstantiate(&plan->graph, g, 0);
