@@ -410,32 +410,35 @@ MMD_DEVINL uint32_t ex2_h2(float lo, float hi) {
     return r;
 }
 
-__global__ void __launch_bounds__(ATT_THREADS, 2) attention64_kernel(const __grid_constant__ AttnParams p) {
+__global__ void __launch_bounds__(ATT_THREADS, 2) attention64_kernel(const __grid_constant__ AttnParams p, int n_items) {
+    // Persistent: a CTA walks work items blockIdx.x, +gridDim.x, ... ; the TMA warp runs ahead into the next item
+    // (Q as soon as the last Q·K^T of the current item has been issued, K/V as stages free up), so the per-item
+    // start-up latency (Q/K fetch, barrier set-up, TMEM allocation) is paid once per CTA instead of once per item.
     using S = Attn64Smem;
     constexpr int D = 64;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
     uint64_t* q_full = bars;        // 1
-    uint64_t* k_full = bars + 1;    // 2
-    uint64_t* k_empty = bars + 3;   // 2
-    uint64_t* v_full = bars + 5;    // 1
-    uint64_t* v_empty = bars + 6;   // 1
-    uint64_t* s_full = bars + 7;    // 1
-    uint64_t* p_ready = bars + 8;   // 1 (128 arrivals)
-    uint64_t* o_full = bars + 9;    // 1
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+    uint64_t* q_empty = bars + 1;   // 1
+    uint64_t* k_full = bars + 2;    // 2
+    uint64_t* k_empty = bars + 4;   // 2
+    uint64_t* v_full = bars + 6;    // 1
+    uint64_t* v_empty = bars + 7;   // 1
+    uint64_t* s_full = bars + 8;    // 1
+    uint64_t* p_ready = bars + 9;   // 1 (128 arrivals)
+    uint64_t* o_full = bars + 10;   // 1
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const AttnWork w = attn_decode(p, blockIdx.x);
-    const int T = w.n_tiles;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&p.q_map);
         tma_prefetch_desc(&p.k_map);
         tma_prefetch_desc(&p.v_map);
         mbar_init(q_full, 1);
+        mbar_init(q_empty, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
         mbar_init(v_full, 1);
         mbar_init(v_empty, 1);
@@ -458,23 +461,30 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention64_kernel(const __gri
     const uint32_t tmem_L = tmem_base + 192;
 
     if (warp == 4) {
+        // ===================== TMA producer =====================
         if (lane == 0) {
-            mbar_expect_tx(q_full, 16384);
-            tma_load_2d(smem + S::Q_OFF, &p.q_map, q_full, p.q_col0 + w.head * D, w.q_row0);
-            for (int t = 0; t < T; ++t) {
-                const int st = t & 1;
-                const uint32_t ph = (t >> 1) & 1;
-                int krow, kvalid;
-                attn_tile(w, t, krow, kvalid);
-                mbar_wait(&k_empty[st], ph ^ 1);
-                mbar_expect_tx(&k_full[st], 16384);
-                tma_load_2d(smem + S::K_OFF + st * 16384, &p.k_map, &k_full[st], p.k_col0 + w.head * D, krow);
-                mbar_wait(v_empty, (t & 1) ^ 1);
-                mbar_expect_tx(v_full, 16384);
-                tma_load_2d(smem + S::V_OFF, &p.v_map, v_full, p.v_col0 + w.head * D, krow);
+            int g = 0;   // KV tiles issued so far (all items)
+            int it = 0;  // items started
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                const AttnWork w = attn_decode(p, item);
+                mbar_wait(q_empty, (it & 1) ^ 1);   // last Q·K^T of the previous item has been issued and retired
+                mbar_expect_tx(q_full, 16384);
+                tma_load_2d(smem + S::Q_OFF, &p.q_map, q_full, p.q_col0 + w.head * D, w.q_row0);
+                for (int t = 0; t < w.n_tiles; ++t, ++g) {
+                    const int st = g & 1;
+                    int krow, kvalid;
+                    attn_tile(w, t, krow, kvalid);
+                    mbar_wait(&k_empty[st], ((g >> 1) & 1) ^ 1);
+                    mbar_expect_tx(&k_full[st], 16384);
+                    tma_load_2d(smem + S::K_OFF + st * 16384, &p.k_map, &k_full[st], p.k_col0 + w.head * D, krow);
+                    mbar_wait(v_empty, (g & 1) ^ 1);
+                    mbar_expect_tx(v_full, 16384);
+                    tma_load_2d(smem + S::V_OFF, &p.v_map, v_full, p.v_col0 + w.head * D, krow);
+                }
             }
         }
     } else if (warp == 5) {
+        // ===================== MMA issuer =====================
         if (lane == 0) {
             constexpr uint32_t idesc_qk = umma_idesc_f16(ATT_BQ, ATT_BKV, 0, 0);
             constexpr uint32_t idesc_pv = umma_idesc_f16(ATT_BQ, D, 0, 1);   // V is MN-major
@@ -483,9 +493,16 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention64_kernel(const __gri
             const uint32_t p_addr = smem_u32(smem + S::P_OFF);
             const uint32_t v_addr = smem_u32(smem + S::V_OFF);
             const uint32_t one_addr = smem_u32(smem + S::ONES_OFF);
-            auto issue_qk = [&](int t) {
-                const int st = t & 1;
-                mbar_wait(&k_full[st], (t >> 1) & 1);
+            int gq = 0;   // Q·K^T tiles issued
+            int itq = 0;  // items whose first Q·K^T has been issued
+            // issues Q·K^T of tile t of the item `w` (first tile waits for that item's Q; last tile releases Q)
+            auto issue_qk = [&](const AttnWork& w, int t) {
+                if (t == 0) {
+                    mbar_wait(q_full, itq & 1);
+                    ++itq;
+                }
+                const int st = gq & 1;
+                mbar_wait(&k_full[st], (gq >> 1) & 1);
                 tc_fence_after();
                 const uint32_t k_addr = smem_u32(smem + S::K_OFF + st * 16384);
 #pragma unroll
@@ -493,145 +510,164 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention64_kernel(const __gri
                     umma_f16_ss(tmem_S, umma_desc_sw128(q_addr + ks * 32, 16, 1024), umma_desc_sw128(k_addr + ks * 32, 16, 1024),
                                 idesc_qk, ks != 0 ? 1u : 0u);
                 umma_commit(&k_empty[st]);
+                if (t == w.n_tiles - 1) umma_commit(q_empty);
                 umma_commit(s_full);
+                ++gq;
             };
-            mbar_wait(q_full, 0);
-            tc_fence_after();
-            issue_qk(0);
-            for (int t = 0; t < T; ++t) {
-                int krow, kvalid;
-                attn_tile(w, t, krow, kvalid);
-                mbar_wait(p_ready, t & 1);
-                mbar_wait(v_full, t & 1);
-                tc_fence_after();
-                const int nks = (kvalid + 15) >> 4;
-                for (int ks = 0; ks < nks; ++ks) {
-                    const uint32_t poff = (ks >> 2) * (ATT_BQ * 128) + (ks & 3) * 32;
-                    umma_f16_ss(tmem_O, umma_desc_sw128(p_addr + poff, 16, 1024),
-                                umma_desc_sw128(v_addr + ks * 2048, ATT_BKV * 128, 1024), idesc_pv, (t | ks) != 0 ? 1u : 0u);
+            int g = 0;
+            bool first = true;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const AttnWork w = attn_decode(p, item);
+                if (first) { issue_qk(w, 0); first = false; }
+                for (int t = 0; t < w.n_tiles; ++t, ++g) {
+                    int krow, kvalid;
+                    attn_tile(w, t, krow, kvalid);
+                    mbar_wait(p_ready, g & 1);
+                    mbar_wait(v_full, g & 1);
+                    tc_fence_after();
+                    const int nks = (kvalid + 15) >> 4;
+                    for (int ks = 0; ks < nks; ++ks) {
+                        const uint32_t poff = (ks >> 2) * (ATT_BQ * 128) + (ks & 3) * 32;
+                        umma_f16_ss(tmem_O, umma_desc_sw128(p_addr + poff, 16, 1024),
+                                    umma_desc_sw128(v_addr + ks * 2048, ATT_BKV * 128, 1024), idesc_pv, (t | ks) != 0 ? 1u : 0u);
+                    }
+                    for (int ks = 0; ks < nks; ++ks) {
+                        const uint32_t poff = (ks >> 2) * (ATT_BQ * 128) + (ks & 3) * 32;
+                        const uint32_t ooff = (ks >> 2) * 2048 + (ks & 3) * 32;
+                        umma_f16_ss(tmem_L, umma_desc_sw128(p_addr + poff, 16, 1024), umma_desc_sw128(one_addr + ooff, 16, 1024),
+                                    idesc_l, (t | ks) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(v_empty);
+                    umma_commit(o_full);
+                    // next logits: same item, or the first tile of the next item (S is free: softmax of this tile is done)
+                    if (t + 1 < w.n_tiles) {
+                        issue_qk(w, t + 1);
+                    } else if (item + static_cast<int>(gridDim.x) < n_items) {
+                        const AttnWork wn = attn_decode(p, item + gridDim.x);
+                        issue_qk(wn, 0);
+                    }
                 }
-                for (int ks = 0; ks < nks; ++ks) {
-                    const uint32_t poff = (ks >> 2) * (ATT_BQ * 128) + (ks & 3) * 32;
-                    const uint32_t ooff = (ks >> 2) * 2048 + (ks & 3) * 32;
-                    umma_f16_ss(tmem_L, umma_desc_sw128(p_addr + poff, 16, 1024), umma_desc_sw128(one_addr + ooff, 16, 1024),
-                                idesc_l, (t | ks) != 0 ? 1u : 0u);
-                }
-                umma_commit(v_empty);
-                umma_commit(o_full);
-                if (t + 1 < T) issue_qk(t + 1);
             }
         }
     } else {
+        // ===================== softmax warps (thread = query row) =====================
         const int row = warp * 32 + lane;
         const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
         const uint32_t s_addr = tmem_S + lane_base;
         uint8_t* p_smem = smem + S::P_OFF;
-        float m_used = 0.f;
-        for (int t = 0; t < T; ++t) {
-            int krow, kvalid;
-            attn_tile(w, t, krow, kvalid);
-            mbar_wait(s_full, t & 1);
-            tc_fence_after();
-            const bool full_tile = (kvalid == ATT_BKV);
-            // ---- pass 1: row maximum, next chunk's TMEM load in flight
-            uint32_t va[32], vb[32];
-            float mx = -INFINITY;
-            tmem_ld32(s_addr, va);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                tmem_ld_wait();
-                uint32_t* cur = (c & 1) ? vb : va;
-                if (c < 3) tmem_ld32(s_addr + (c + 1) * 32, (c & 1) ? va : vb);
-                if (full_tile) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(cur[i]));
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (c * 32 + i < kvalid) mx = fmaxf(mx, __uint_as_float(cur[i]));
-                }
-            }
-            const float mxs = mx * p.scale_log2;
-            if (t == 0) {
-                m_used = mxs;
-            } else {
-                mbar_wait(o_full, (t - 1) & 1);   // P·V of the previous tile is done: P and O may be touched
+        int g = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const AttnWork w = attn_decode(p, item);
+            const int T = w.n_tiles;
+            float m_used = 0.f;
+            for (int t = 0; t < T; ++t, ++g) {
+                int krow, kvalid;
+                attn_tile(w, t, krow, kvalid);
+                mbar_wait(s_full, g & 1);
                 tc_fence_after();
-                if (__any_sync(0xffffffffu, mxs > m_used + 8.0f)) {
-                    const float m_new = fmaxf(m_used, mxs);
-                    const float alpha = ex2_fast(m_used - m_new);
-                    m_used = m_new;
-                    uint32_t o[32];
+                const bool full_tile = (kvalid == ATT_BKV);
+                // ---- pass 1: row maximum, next chunk's TMEM load in flight
+                uint32_t va[32], vb[32];
+                float mx = -INFINITY;
+                tmem_ld32(s_addr, va);
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        tmem_ld32(tmem_O + lane_base + c * 32, o);
+                for (int c = 0; c < 4; ++c) {
+                    tmem_ld_wait();
+                    uint32_t* cur = (c & 1) ? vb : va;
+                    if (c < 3) tmem_ld32(s_addr + (c + 1) * 32, (c & 1) ? va : vb);
+                    if (full_tile) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(cur[i]));
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (c * 32 + i < kvalid) mx = fmaxf(mx, __uint_as_float(cur[i]));
+                    }
+                }
+                const float mxs = mx * p.scale_log2;
+                if (t == 0) {
+                    m_used = mxs;
+                } else {
+                    mbar_wait(o_full, (g - 1) & 1);   // P·V of the previous tile is done: P and O may be touched
+                    tc_fence_after();
+                    if (__any_sync(0xffffffffu, mxs > m_used + 8.0f)) {
+                        const float m_new = fmaxf(m_used, mxs);
+                        const float alpha = ex2_fast(m_used - m_new);
+                        m_used = m_new;
+                        uint32_t o[32];
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            tmem_ld32(tmem_O + lane_base + c * 32, o);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                            tmem_st32(tmem_O + lane_base + c * 32, o);
+                        }
+                        tmem_ld16(tmem_L + lane_base, o);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                        tmem_st32(tmem_O + lane_base + c * 32, o);
+                        for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        tmem_st16(tmem_L + lane_base, o);
+                        tmem_st_wait();
                     }
-                    tmem_ld16(tmem_L + lane_base, o);
+                }
+                // ---- pass 2: probabilities (fp16, via ex2.f16x2) -> shared memory
+                const float nm = -m_used;
+                tmem_ld32(s_addr, va);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
                     tmem_ld_wait();
+                    uint32_t* cur = (c & 1) ? vb : va;
+                    if (c < 3) tmem_ld32(s_addr + (c + 1) * 32, (c & 1) ? va : vb);
+                    uint8_t* chunk = p_smem + (c >> 1) * (ATT_BQ * 128);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                    tmem_st16(tmem_L + lane_base, o);
-                    tmem_st_wait();
-                }
-            }
-            // ---- pass 2: probabilities (fp16, via ex2.f16x2) -> shared memory
-            const float nm = -m_used;
-            tmem_ld32(s_addr, va);
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 pk;
+                        uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                tmem_ld_wait();
-                uint32_t* cur = (c & 1) ? vb : va;
-                if (c < 3) tmem_ld32(s_addr + (c + 1) * 32, (c & 1) ? va : vb);
-                uint8_t* chunk = p_smem + (c >> 1) * (ATT_BQ * 128);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    uint4 pk;
-                    uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int col = c * 32 + j * 8 + 2 * k;
-                        float x0 = fmaf(__uint_as_float(cur[j * 8 + 2 * k]), p.scale_log2, nm);
-                        float x1 = fmaf(__uint_as_float(cur[j * 8 + 2 * k + 1]), p.scale_log2, nm);
-                        if (!full_tile) {
-                            if (col >= kvalid) x0 = -INFINITY;
-                            if (col + 1 >= kvalid) x1 = -INFINITY;
+                        for (int k = 0; k < 4; ++k) {
+                            const int col = c * 32 + j * 8 + 2 * k;
+                            float x0 = fmaf(__uint_as_float(cur[j * 8 + 2 * k]), p.scale_log2, nm);
+                            float x1 = fmaf(__uint_as_float(cur[j * 8 + 2 * k + 1]), p.scale_log2, nm);
+                            if (!full_tile) {
+                                if (col >= kvalid) x0 = -INFINITY;
+                                if (col + 1 >= kvalid) x1 = -INFINITY;
+                            }
+                            pw[k] = ex2_h2(x0, x1);
                         }
-                        pw[k] = ex2_h2(x0, x1);
+                        *reinterpret_cast<uint4*>(chunk + sw128_off(row, (c & 1) * 4 + j)) = pk;
                     }
-                    *reinterpret_cast<uint4*>(chunk + sw128_off(row, (c & 1) * 4 + j)) = pk;
                 }
+                fence_proxy_async_smem();
+                tc_fence_before();
+                mbar_arrive(p_ready);
             }
-            fence_proxy_async_smem();
-            tc_fence_before();
-            mbar_arrive(p_ready);
-        }
-        mbar_wait(o_full, (T - 1) & 1);
-        tc_fence_after();
-        uint32_t lv[16];
-        tmem_ld16(tmem_L + lane_base, lv);
-        tmem_ld_wait();
-        const float inv_l = 1.f / __uint_as_float(lv[0]);
-        act_t* orow = p.out + static_cast<size_t>(w.q_row0 + row) * p.out_ld + w.head * D;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            uint32_t v[32];
-            tmem_ld32(tmem_O + lane_base + c * 32, v);
+            // ---- item epilogue: O / l -> global (the next item's first P·V waits for our next p_ready arrival)
+            mbar_wait(o_full, (g - 1) & 1);
+            tc_fence_after();
+            uint32_t lv[16];
+            tmem_ld16(tmem_L + lane_base, lv);
             tmem_ld_wait();
-            if (row < w.q_valid) {
+            const float inv_l = 1.f / __uint_as_float(lv[0]);
+            act_t* orow = p.out + static_cast<size_t>(w.q_row0 + row) * p.out_ld + w.head * D;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    uint4 pk;
-                    __half2* ph2 = reinterpret_cast<__half2*>(&pk);
+            for (int c = 0; c < 2; ++c) {
+                uint32_t v[32];
+                tmem_ld32(tmem_O + lane_base + c * 32, v);
+                tmem_ld_wait();
+                if (row < w.q_valid) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        ph2[k] = __floats2half2_rn(__uint_as_float(v[j * 8 + 2 * k]) * inv_l, __uint_as_float(v[j * 8 + 2 * k + 1]) * inv_l);
-                    *reinterpret_cast<uint4*>(orow + c * 32 + j * 8) = pk;
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 pk;
+                        __half2* ph2 = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            ph2[k] = __floats2half2_rn(__uint_as_float(v[j * 8 + 2 * k]) * inv_l, __uint_as_float(v[j * 8 + 2 * k + 1]) * inv_l);
+                        *reinterpret_cast<uint4*>(orow + c * 32 + j * 8) = pk;
+                    }
                 }
             }
+            tc_fence_before();   // O / l reads are complete before this thread's next p_ready arrival
         }
     }
 

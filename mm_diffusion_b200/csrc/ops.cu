@@ -236,7 +236,7 @@ int launch_attn(const AttnParams& p, int d, cudaStream_t st) {
     }
     const int grid = p.B * p.n_blocks * p.heads * p.q_tiles;
     static const bool generic64 = [] { const char* e = getenv("MMD_ATTN_GENERIC"); return e && e[0] == '1'; }();
-    if (d == 64 && !generic64) attention64_kernel<<<grid, ATT_THREADS, Attn64Smem::TOTAL, st>>>(p);
+    if (d == 64 && !generic64) attention64_kernel<<<std::min(grid, 2 * num_sms()), ATT_THREADS, Attn64Smem::TOTAL, st>>>(p, grid);
     else if (d == 64) attention_kernel<64><<<grid, ATT_THREADS, attn_smem_bytes<64>(), st>>>(p);
     else if (d == 96) attention_kernel<96><<<grid, ATT_THREADS, attn_smem_bytes<96>(), st>>>(p);
     else attention_kernel<128><<<grid, ATT_THREADS, attn_smem_bytes<128>(), st>>>(p);
