@@ -114,7 +114,12 @@ int mmd_op_resample(const void* x, void* y, int mode, int n, int h, int w, int c
  * geometry: rank-1 token coordinates (innermost first) with extents dims[] and box[] (product 128);
  * taps: n_taps x 3 coordinate deltas; sources are concatenated along channels.
  * weight: fp32 [n][c_total][n_taps] (reference layout, flattened kernel dims), bias fp32 [n].
- * out: fp16 [tokens][n] (out_f32 == NULL) or fp32 scatter with strides (heads). */
+ * out: fp16 [tokens][n] (out_f32 == NULL) or fp32 scatter with strides (heads).
+ * gn_sums (optional): GroupNorm(32) statistics of the output, reduced in the GEMM epilogue and ADDED to
+ *   double [domains][32][2] = (sum, sum of squares) per (domain, group); the caller zeroes it.  gn_rows = tokens of
+ *   one domain.  rank 2: domain = token / gn_rows (gn_rows 64 or a multiple of 128); rank 3 (L,B): one domain per
+ *   sample (gn_rows == dims[0]); rank 4 (P,F,B): one domain per (b,f) (gn_rows == dims[0] >= 64).  Needs n % 128 == 0.
+ *   (normalization() statistics of multimodal_unet.py's GroupNorm32 consumers, nn.py:93-100.) */
 typedef struct MmdConvDesc {
     int rank;          /* 2..5 including the channel coordinate */
     int64_t dims[4];
@@ -131,6 +136,8 @@ typedef struct MmdConvDesc {
     float* out_f32;
     int64_t ostride[4];
     int64_t ostride_c;
+    double* gn_sums;
+    int64_t gn_rows;
 } MmdConvDesc;
 int mmd_op_conv(const MmdConvDesc* d, void* stream);
 

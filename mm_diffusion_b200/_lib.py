@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmmdiff.so")
+LIB_PATH = os.environ.get("MMD_LIB", os.path.join(_HERE, "libmmdiff.so"))   # MMD_LIB: debug builds
 
 MMD_MAX_LEVELS = 8
 
@@ -58,6 +58,8 @@ class MmdConvDesc(C.Structure):
         ("out_f32", C.c_void_p),
         ("ostride", C.c_int64 * 4),
         ("ostride_c", C.c_int64),
+        ("gn_sums", C.c_void_p),
+        ("gn_rows", C.c_int64),
     ]
 
 

@@ -36,7 +36,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest_mtime(files + headers):
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, *files, "-o", LIB]
+    extra = os.environ.get("MMD_NVCC_EXTRA", "").split()
+    out = os.environ.get("MMD_LIB_OUT", LIB)
+    cmd = [nvcc, *NVCC_FLAGS, *extra, *files, "-o", out]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
@@ -46,7 +48,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr, file=sys.stderr)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

@@ -366,8 +366,8 @@ __global__ void __launch_bounds__(ATT_THREADS, (D == 64) ? 2 : 1) attention_kern
 //   * O and the row sums l accumulate in TMEM across KV tiles (P·V and P·1 MMAs with accumulate), so the per-tile
 //     "fold previous O into registers" step disappears; O is rescaled in place only when the running maximum
 //     moves by more than 2^8 (warp-uniform decision), which after the first tiles is rare;
-//   * probabilities come from ex2.approx.f16x2 on packed half2 logits: one MUFU op per TWO elements and the result
-//     is already the fp16 operand of the P·V MMA (the row sum is taken by the tensor core from the same rounded P);
+//   * the row sum is taken by the tensor core from the same rounded fp16 P that feeds P·V (no FADD chain, no
+//     second conversion); full 128-key tiles run a mask-free instantiation of both passes;
 //   * logits are read from TMEM with the next chunk's load in flight.
 // ===========================================================================
 struct Attn64Smem {
@@ -408,6 +408,57 @@ MMD_DEVINL uint32_t ex2_h2(float lo, float hi) {
     uint32_t r;
     asm("ex2.approx.f16x2 %0, %1;" : "=r"(r) : "r"(*reinterpret_cast<const uint32_t*>(&x)));
     return r;
+}
+
+// Row maximum of a 128-column logit tile in TMEM (thread = row); the next 32-column load is in flight while
+// the current one is reduced.  FULL tiles carry no masking code at all.
+template <bool FULL>
+MMD_DEVINL float attn64_rowmax(uint32_t s_addr, int kvalid) {
+    uint32_t va[32], vb[32];
+    float mx = -INFINITY;
+    tmem_ld32(s_addr, va);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint32_t* cur = (c & 1) ? vb : va;
+        tmem_ld_wait();
+        if (c < 3) tmem_ld32(s_addr + (c + 1) * 32, (c & 1) ? va : vb);
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (FULL || c * 32 + i < kvalid) mx = fmaxf(mx, __uint_as_float(cur[i]));
+    }
+    return mx;
+}
+
+// p = exp2(s * scale - m) as fp16 into the swizzled P tile (two 64-key chunks).
+template <bool FULL>
+MMD_DEVINL void attn64_write_p(uint32_t s_addr, int kvalid, float scale_log2, float nm, uint8_t* p_smem, int row) {
+    uint32_t va[32], vb[32];
+    tmem_ld32(s_addr, va);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint32_t* cur = (c & 1) ? vb : va;
+        tmem_ld_wait();
+        if (c < 3) tmem_ld32(s_addr + (c + 1) * 32, (c & 1) ? va : vb);
+        uint8_t* chunk = p_smem + (c >> 1) * (ATT_BQ * 128);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint4 pk;
+            uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int col = c * 32 + j * 8 + 2 * k;
+                float e0 = ex2_fast(fmaf(__uint_as_float(cur[j * 8 + 2 * k]), scale_log2, nm));
+                float e1 = ex2_fast(fmaf(__uint_as_float(cur[j * 8 + 2 * k + 1]), scale_log2, nm));
+                if (!FULL) {
+                    if (col >= kvalid) e0 = 0.f;
+                    if (col + 1 >= kvalid) e1 = 0.f;
+                }
+                const __half2 h = __floats2half2_rn(e0, e1);
+                pw[k] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(chunk + sw128_off(row, (c & 1) * 4 + j)) = pk;
+        }
+    }
 }
 
 __global__ void __launch_bounds__(ATT_THREADS, 2) attention64_kernel(const __grid_constant__ AttnParams p, int n_items) {
@@ -489,10 +540,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention64_kernel(const __gri
             constexpr uint32_t idesc_qk = umma_idesc_f16(ATT_BQ, ATT_BKV, 0, 0);
             constexpr uint32_t idesc_pv = umma_idesc_f16(ATT_BQ, D, 0, 1);   // V is MN-major
             constexpr uint32_t idesc_l = umma_idesc_f16(ATT_BQ, 16, 0, 0);   // P x ones^T
-            const uint32_t q_addr = smem_u32(smem + S::Q_OFF);
-            const uint32_t p_addr = smem_u32(smem + S::P_OFF);
-            const uint32_t v_addr = smem_u32(smem + S::V_OFF);
-            const uint32_t one_addr = smem_u32(smem + S::ONES_OFF);
+            const uint64_t qd0 = umma_desc_sw128(smem_u32(smem + S::Q_OFF), 16, 1024);
+            const uint64_t kd0 = umma_desc_sw128(smem_u32(smem + S::K_OFF), 16, 1024);
+            const uint64_t pd0 = umma_desc_sw128(smem_u32(smem + S::P_OFF), 16, 1024);
+            const uint64_t vd0 = umma_desc_sw128(smem_u32(smem + S::V_OFF), ATT_BKV * 128, 1024);   // MN-major V
+            const uint64_t od0 = umma_desc_sw128(smem_u32(smem + S::ONES_OFF), 16, 1024);
             int gq = 0;   // Q·K^T tiles issued
             int itq = 0;  // items whose first Q·K^T has been issued
             // issues Q·K^T of tile t of the item `w` (first tile waits for that item's Q; last tile releases Q)
@@ -504,11 +556,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention64_kernel(const __gri
                 const int st = gq & 1;
                 mbar_wait(&k_full[st], (gq >> 1) & 1);
                 tc_fence_after();
-                const uint32_t k_addr = smem_u32(smem + S::K_OFF + st * 16384);
+                const uint64_t kd = kd0 + static_cast<uint64_t>(st) * (16384 >> 4);
 #pragma unroll
                 for (int ks = 0; ks < D / 16; ++ks)
-                    umma_f16_ss(tmem_S, umma_desc_sw128(q_addr + ks * 32, 16, 1024), umma_desc_sw128(k_addr + ks * 32, 16, 1024),
-                                idesc_qk, ks != 0 ? 1u : 0u);
+                    umma_f16_ss(tmem_S, qd0 + 2 * ks, kd + 2 * ks, idesc_qk, ks != 0 ? 1u : 0u);
                 umma_commit(&k_empty[st]);
                 if (t == w.n_tiles - 1) umma_commit(q_empty);
                 umma_commit(s_full);
@@ -526,16 +577,33 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention64_kernel(const __gri
                     mbar_wait(v_full, g & 1);
                     tc_fence_after();
                     const int nks = (kvalid + 15) >> 4;
-                    for (int ks = 0; ks < nks; ++ks) {
-                        const uint32_t poff = (ks >> 2) * (ATT_BQ * 128) + (ks & 3) * 32;
-                        umma_f16_ss(tmem_O, umma_desc_sw128(p_addr + poff, 16, 1024),
-                                    umma_desc_sw128(v_addr + ks * 2048, ATT_BKV * 128, 1024), idesc_pv, (t | ks) != 0 ? 1u : 0u);
-                    }
-                    for (int ks = 0; ks < nks; ++ks) {
-                        const uint32_t poff = (ks >> 2) * (ATT_BQ * 128) + (ks & 3) * 32;
-                        const uint32_t ooff = (ks >> 2) * 2048 + (ks & 3) * 32;
-                        umma_f16_ss(tmem_L, umma_desc_sw128(p_addr + poff, 16, 1024), umma_desc_sw128(one_addr + ooff, 16, 1024),
-                                    idesc_l, (t | ks) != 0 ? 1u : 0u);
+                    // descriptors are base + compile-time increments (16-byte units), so the single issuing thread
+                    // spends its time on tcgen05.mma issue, not on address arithmetic
+                    if (nks == ATT_BKV / 16) {
+                        // full tile: straight-line issue with compile-time descriptor increments
+#pragma unroll
+                        for (int ks = 0; ks < ATT_BKV / 16; ++ks)
+                            umma_f16_ss(tmem_O, pd0 + ((ks >> 2) * (ATT_BQ * 128 >> 4) + (ks & 3) * 2), vd0 + ks * (2048 >> 4),
+                                        idesc_pv, (t | ks) != 0 ? 1u : 0u);
+#pragma unroll
+                        for (int ks = 0; ks < ATT_BKV / 16; ++ks)
+                            umma_f16_ss(tmem_L, pd0 + ((ks >> 2) * (ATT_BQ * 128 >> 4) + (ks & 3) * 2),
+                                        od0 + ((ks >> 2) * (2048 >> 4) + (ks & 3) * 2), idesc_l, (t | ks) != 0 ? 1u : 0u);
+                    } else {
+                        // ragged tile: running descriptors (a 64-column chunk boundary after ks = 3)
+                        uint64_t pd = pd0, vd = vd0;
+                        for (int ks = 0; ks < nks; ++ks) {
+                            umma_f16_ss(tmem_O, pd, vd, idesc_pv, (t | ks) != 0 ? 1u : 0u);
+                            vd += 2048 >> 4;
+                            pd += (ks == 3) ? (ATT_BQ * 128 >> 4) - 6 : 2;
+                        }
+                        uint64_t od = od0;
+                        pd = pd0;
+                        for (int ks = 0; ks < nks; ++ks) {
+                            umma_f16_ss(tmem_L, pd, od, idesc_l, (t | ks) != 0 ? 1u : 0u);
+                            pd += (ks == 3) ? (ATT_BQ * 128 >> 4) - 6 : 2;
+                            od += (ks == 3) ? (2048 >> 4) - 6 : 2;
+                        }
                     }
                     umma_commit(v_empty);
                     umma_commit(o_full);
@@ -566,24 +634,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention64_kernel(const __gri
                 mbar_wait(s_full, g & 1);
                 tc_fence_after();
                 const bool full_tile = (kvalid == ATT_BKV);
-                // ---- pass 1: row maximum, next chunk's TMEM load in flight
-                uint32_t va[32], vb[32];
-                float mx = -INFINITY;
-                tmem_ld32(s_addr, va);
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    tmem_ld_wait();
-                    uint32_t* cur = (c & 1) ? vb : va;
-                    if (c < 3) tmem_ld32(s_addr + (c + 1) * 32, (c & 1) ? va : vb);
-                    if (full_tile) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(cur[i]));
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (c * 32 + i < kvalid) mx = fmaxf(mx, __uint_as_float(cur[i]));
-                    }
-                }
+                // ---- pass 1: row maximum
+                const float mx = full_tile ? attn64_rowmax<true>(s_addr, kvalid) : attn64_rowmax<false>(s_addr, kvalid);
                 const float mxs = mx * p.scale_log2;
                 if (t == 0) {
                     m_used = mxs;
@@ -611,33 +663,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention64_kernel(const __gri
                         tmem_st_wait();
                     }
                 }
-                // ---- pass 2: probabilities (fp16, via ex2.f16x2) -> shared memory
-                const float nm = -m_used;
-                tmem_ld32(s_addr, va);
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    tmem_ld_wait();
-                    uint32_t* cur = (c & 1) ? vb : va;
-                    if (c < 3) tmem_ld32(s_addr + (c + 1) * 32, (c & 1) ? va : vb);
-                    uint8_t* chunk = p_smem + (c >> 1) * (ATT_BQ * 128);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint4 pk;
-                        uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const int col = c * 32 + j * 8 + 2 * k;
-                            float x0 = fmaf(__uint_as_float(cur[j * 8 + 2 * k]), p.scale_log2, nm);
-                            float x1 = fmaf(__uint_as_float(cur[j * 8 + 2 * k + 1]), p.scale_log2, nm);
-                            if (!full_tile) {
-                                if (col >= kvalid) x0 = -INFINITY;
-                                if (col + 1 >= kvalid) x1 = -INFINITY;
-                            }
-                            pw[k] = ex2_h2(x0, x1);
-                        }
-                        *reinterpret_cast<uint4*>(chunk + sw128_off(row, (c & 1) * 4 + j)) = pk;
-                    }
-                }
+                // ---- pass 2: probabilities (fp16) -> shared memory
+                if (full_tile) attn64_write_p<true>(s_addr, kvalid, p.scale_log2, -m_used, p_smem, row);
+                else attn64_write_p<false>(s_addr, kvalid, p.scale_log2, -m_used, p_smem, row);
                 fence_proxy_async_smem();
                 tc_fence_before();
                 mbar_arrive(p_ready);

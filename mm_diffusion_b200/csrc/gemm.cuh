@@ -18,7 +18,8 @@ constexpr int GEMM_BM = 128;       // tokens per tile (UMMA M)
 constexpr int GEMM_BK = 64;        // channels per k-iteration (one 128-byte swizzle atom)
 constexpr int GEMM_MAX_SRC = 4;
 constexpr int GEMM_MAX_TAPS = 27;
-constexpr int GEMM_THREADS = 192;  // warp0 TMA, warp1 MMA, warps2-5 epilogue
+constexpr int GEMM_THREADS = 320;  // warp0 TMA, warp1 MMA, warps2-5 epilogue, warps6-9 A-operand transform
+constexpr int GEMM_XF_MAXC = 512;  // widest source the fused GroupNorm apply supports
 
 struct alignas(64) GemmParams {
     CUtensorMap a_map[GEMM_MAX_SRC];  // activation sources, rank `rank`, box (64, box[0..3])
@@ -48,6 +49,20 @@ struct alignas(64) GemmParams {
     int stats_mul[4];       // domain base = sum_i origin[i+1] * stats_mul[i] / stats_div
     int stats_div;
     int stats_valid_coord;  // >= 0: rows >= dims[c] - origin[c+1] of the tile are padding (ragged last tile)
+    // fused GroupNorm apply on the A operand of source xf_src (pointwise GEMMs only):
+    //   a <- act(gn(a) * (1 + scale) + shift), done in shared memory between the TMA landing and the MMA
+    //   (reference: nn.py:22-33 + multimodal_unet.py:459-470 out_layers / :284,664 attention norms)
+    const double* xf_sums;  // statistics slots [domains * xf_nsub][32][2]; null = off
+    const float* xf_gamma;
+    const float* xf_beta;
+    const float* xf_film;   // [batch][xf_film_ld]: scale at [0,C), shift at [C,2C); may be null
+    int xf_film_ld;
+    int xf_dom_per_batch;   // FiLM row = domain / xf_dom_per_batch
+    int xf_src, xf_c, xf_nsub, xf_silu;
+    double xf_inv_n;        // 1 / (rows * channels-per-group) of one statistics domain
+    int xf_rows;            // rows of one domain inside a tile (64 or 128)
+    int xf_mul[4];          // domain base = sum_i origin[i+1] * xf_mul[i] / xf_div
+    int xf_div;
 };
 
 template <int BN>
@@ -61,9 +76,12 @@ struct GemmSmem {
     static constexpr int NHALF = (BN >= 64) ? BN / HALF : 0;
     static constexpr int OUT_BUF = (BN >= 64) ? (HALF / 64) * GEMM_BM * 128 : 0;
     static constexpr int OUT_BYTES = 2 * OUT_BUF;
-    static constexpr int STAGES = (BN >= 256) ? 3 : ((BN >= 128) ? 5 : 8);
-    static constexpr int BAR_BYTES = 256 + 2 * 32 * 2 * 4;   // barriers + GroupNorm bins [2 domains][32 groups][2]
+    static constexpr int STAGES = (BN >= 256) ? 3 : ((BN >= 128) ? 4 : 6);
+    // barriers | GroupNorm partials [2 halves][4 bands][32 quads][2] | transform coefficients [2 domains][2][512] + group stats
+    static constexpr int XF_OFF = 256 + 2 * 4 * 32 * 2 * 4;
+    static constexpr int BAR_BYTES = XF_OFF + 2 * 2 * GEMM_XF_MAXC * 4 + 512;
     static constexpr int TOTAL = STAGES * STAGE_BYTES + OUT_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
+    static_assert(TOTAL <= 232448, "exceeds the 227 KB dynamic shared memory limit");
     static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : ((2 * BN <= 64) ? 64 : ((2 * BN <= 128) ? 128 : ((2 * BN <= 256) ? 256 : 512)));
 };
 
@@ -90,8 +108,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
     uint64_t* empty_bar = bars + S::STAGES;
     uint64_t* tfull_bar = bars + 2 * S::STAGES;
     uint64_t* tempty_bar = bars + 2 * S::STAGES + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::STAGES + 4);
-    float* gn_bins = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
+    uint64_t* xf_bar = bars + 2 * S::STAGES + 4;   // [STAGES]: A tile transformed, MMA may read it
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S::STAGES + 4);
+    float* xf_coef = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + S::XF_OFF);   // [dl][a|b][c]
+    float* xf_gstat = xf_coef + 2 * 2 * GEMM_XF_MAXC;                                          // [dl][32][mean|rstd]
+    float* gn_part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -107,6 +128,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
         for (int i = 0; i < S::STAGES; ++i) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
+            mbar_init(&xf_bar[i], 4);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
@@ -166,20 +188,115 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
+                    mbar_wait(p.xf_sums != nullptr ? &xf_bar[stage] : &full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(stage_base + stage * S::STAGE_BYTES);
-                    const uint32_t b_addr = a_addr + S::A_BYTES;
+                    // one descriptor per operand and k-iteration; the 16-element k-steps only bump the 16-byte-unit
+                    // start-address field (+32 bytes = +2), keeping the single issuing thread off the critical path
+                    const uint64_t ad0 = umma_desc_sw128(a_addr, 16, 1024);
+                    const uint64_t bd0 = umma_desc_sw128(a_addr + S::A_BYTES, 16, 1024);
 #pragma unroll
-                    for (int k = 0; k < GEMM_BK / 16; ++k) {
-                        const uint64_t ad = umma_desc_sw128(a_addr + k * 32, 16, 1024);
-                        const uint64_t bd = umma_desc_sw128(b_addr + k * 32, 16, 1024);
-                        umma_f16_ss(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
-                    }
+                    for (int k = 0; k < GEMM_BK / 16; ++k)
+                        umma_f16_ss(d_tmem, ad0 + 2 * k, bd0 + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
                     umma_commit(&empty_bar[stage]);
                     if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&tfull_bar[acc]);
+            }
+        }
+    } else if (warp >= 6) {
+        // ================= A-operand transform (4 warps): fused GroupNorm apply =================
+        if (p.xf_sums != nullptr) {
+            const int tt = threadIdx.x - 192;           // 0..127
+            const int oct = tt & 7, rg = tt >> 3;       // 16-byte column unit, group of 8 rows
+            const int C = p.xf_c;
+            const int cpg = C / 32;
+            const int ndom = (p.xf_rows < GEMM_BM) ? 2 : 1;
+            const int dl = (rg * 8) / p.xf_rows;
+            int stage = 0;
+            uint32_t phase = 0;
+            int cached_dom = -1;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int m_idx = tile / p.n_tiles;
+                int org[5];
+                gemm_tile_origin(p, m_idx, org);
+                const int dom_base = (org[1] * p.xf_mul[0] + org[2] * p.xf_mul[1] + org[3] * p.xf_mul[2] +
+                                      org[4] * p.xf_mul[3]) / p.xf_div;
+                if (dom_base != cached_dom) {   // (re)build the per-channel affine table of this tile's domain(s)
+                    named_bar_sync(2, 128);
+                    if (tt < 32 * ndom) {
+                        const int d = tt >> 5, g = tt & 31;
+                        double su = 0.0, sq = 0.0;
+                        for (int k = 0; k < p.xf_nsub; ++k) {
+                            const double* sl = p.xf_sums + (static_cast<size_t>(dom_base + d) * p.xf_nsub + k) * 64;
+                            su += sl[2 * g];
+                            sq += sl[2 * g + 1];
+                        }
+                        const double mean = su * p.xf_inv_n;
+                        double var = sq * p.xf_inv_n - mean * mean;
+                        if (var < 0) var = 0;
+                        xf_gstat[(d * 32 + g) * 2] = static_cast<float>(mean);
+                        xf_gstat[(d * 32 + g) * 2 + 1] = rsqrtf(static_cast<float>(var) + 1e-5f);
+                    }
+                    named_bar_sync(2, 128);
+                    for (int i = tt; i < ndom * C; i += 128) {
+                        const int d = i / C, c = i - d * C;
+                        const int g = c / cpg;
+                        float a = xf_gstat[(d * 32 + g) * 2 + 1] * __ldg(p.xf_gamma + c);
+                        float b = __ldg(p.xf_beta + c) - xf_gstat[(d * 32 + g) * 2] * a;
+                        if (p.xf_film != nullptr) {
+                            const float* fb = p.xf_film + static_cast<size_t>((dom_base + d) / p.xf_dom_per_batch) * p.xf_film_ld;
+                            const float sc = 1.f + __ldg(fb + c);
+                            a *= sc;
+                            b = b * sc + __ldg(fb + C + c);
+                        }
+                        xf_coef[(d * 2 + 0) * GEMM_XF_MAXC + c] = a;
+                        xf_coef[(d * 2 + 1) * GEMM_XF_MAXC + c] = b;
+                    }
+                    named_bar_sync(2, 128);
+                    cached_dom = dom_base;
+                }
+                for (int t = 0; t < p.n_taps; ++t) {
+                    for (int sidx = 0; sidx < p.n_src; ++sidx) {
+                        for (int ch = 0; ch < p.src_chunks[sidx]; ++ch) {
+                            mbar_wait(&full_bar[stage], phase);
+                            if (sidx == p.xf_src) {
+                                uint8_t* a_tile = stage_base + stage * S::STAGE_BYTES;
+                                const float* ca = xf_coef + (dl * 2 + 0) * GEMM_XF_MAXC + ch * GEMM_BK + oct * 8;
+                                const float* cb = xf_coef + (dl * 2 + 1) * GEMM_XF_MAXC + ch * GEMM_BK + oct * 8;
+                                const float4 a0 = *reinterpret_cast<const float4*>(ca), a1 = *reinterpret_cast<const float4*>(ca + 4);
+                                const float4 b0 = *reinterpret_cast<const float4*>(cb), b1 = *reinterpret_cast<const float4*>(cb + 4);
+                                const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                                const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    uint4* ptr = reinterpret_cast<uint4*>(a_tile + sw128_off(rg * 8 + j, oct));
+                                    uint4 raw = *ptr;
+                                    __half2* h = reinterpret_cast<__half2*>(&raw);
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) {
+                                        const float2 f = __half22float2(h[k]);
+                                        float u0 = fmaf(f.x, av[2 * k], bv[2 * k]);
+                                        float u1 = fmaf(f.y, av[2 * k + 1], bv[2 * k + 1]);
+                                        if (p.xf_silu) {
+                                            float t0, t1;
+                                            asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(0.5f * u0));
+                                            asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(0.5f * u1));
+                                            u0 = 0.5f * u0 * (1.0f + t0);
+                                            u1 = 0.5f * u1 * (1.0f + t1);
+                                        }
+                                        h[k] = __floats2half2_rn(u0, u1);
+                                    }
+                                    *ptr = raw;
+                                }
+                                fence_proxy_async_smem();
+                            }
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&xf_bar[stage]);
+                            if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                }
             }
         }
     } else {
@@ -203,7 +320,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
 
             if constexpr (BN >= 64) {
                 constexpr int HALF = S::HALF;
-                if (p.stats != nullptr) gn_bins[threadIdx.x - 64] = 0.f;
                 int valid_rows = GEMM_BM;
                 if (p.stats != nullptr && p.stats_valid_coord >= 0)
                     valid_rows = min(GEMM_BM, p.dims[p.stats_valid_coord] - org[p.stats_valid_coord + 1]);
@@ -213,11 +329,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                     ++obuf_sel;
                     if (leader) tma_store_wait_read1();  // the store issued two halves ago has drained this buffer
                     named_bar_sync(1, 128);
-#pragma unroll 1
+                    // accumulator -> fp16 staging, 32 columns at a time with the next TMEM load already in flight
+                    uint32_t va[32], vb[32];
+                    tmem_ld32(t_addr + hf * HALF, va);
+#pragma unroll
                     for (int cc = 0; cc < HALF / 32; ++cc) {
-                        uint32_t v[32];
-                        tmem_ld32(t_addr + hf * HALF + cc * 32, v);
+                        uint32_t* v = (cc & 1) ? vb : va;
                         tmem_ld_wait();
+                        if (cc + 1 < HALF / 32) tmem_ld32(t_addr + hf * HALF + (cc + 1) * 32, (cc & 1) ? va : vb);
                         uint8_t* chunk = obuf + (cc >> 1) * (GEMM_BM * 128);
                         const float* bcol = bias + hf * HALF + cc * 32;
 #pragma unroll
@@ -253,60 +372,68 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                         tma_store_commit();
                     }
                     if (p.stats != nullptr) {
-                        // column sums of the staged fp16 half-tile: thread = (8-column octet, run of NOCT rows)
-                        constexpr int NOCT = HALF / 8;
-                        const int et = threadIdx.x - 64;
-                        const int oct = et % NOCT;
-                        const int r_begin = (et / NOCT) * NOCT;
-                        float sm[8], sq[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) { sm[i] = 0.f; sq[i] = 0.f; }
-                        const uint8_t* chunk = obuf + (oct >> 3) * (GEMM_BM * 128);
-#pragma unroll 4
-                        for (int rr = 0; rr < NOCT; ++rr) {
-                            const int r = r_begin + rr;
-                            if (r < valid_rows) {
-                                const uint4 raw = *reinterpret_cast<const uint4*>(chunk + sw128_off(r, oct & 7));
-                                const __half2* h = reinterpret_cast<const __half2*>(&raw);
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    const float2 f = __half22float2(h[i]);
-                                    sm[2 * i] += f.x; sq[2 * i] = fmaf(f.x, f.x, sq[2 * i]);
-                                    sm[2 * i + 1] += f.y; sq[2 * i + 1] = fmaf(f.y, f.y, sq[2 * i + 1]);
+                        // Column sums of the staged fp16 half-tile without atomics: lane = 4-column quad (8 bytes of
+                        // a row; a warp reads whole 256-byte rows, conflict-free), warp = 32-row band.  The per-(band,
+                        // quad) partials are folded into groups by the write-out pass below.
+                        if constexpr (HALF == 128) {
+                            const int et = threadIdx.x - 64;
+                            const int band = et >> 5, quad = et & 31;
+                            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+                            const uint8_t* chunk = obuf + (quad >> 4) * (GEMM_BM * 128);
+                            const int unit = (quad & 15) >> 1, sub = (quad & 1) * 8;
+#pragma unroll 8
+                            for (int rr = 0; rr < 32; ++rr) {
+                                const int r = band * 32 + rr;
+                                if (r < valid_rows) {
+                                    const uint2 raw = *reinterpret_cast<const uint2*>(chunk + sw128_off(r, unit) + sub);
+                                    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+                                    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+                                    s0 += a.x; q0 = fmaf(a.x, a.x, q0);
+                                    s1 += a.y; q1 = fmaf(a.y, a.y, q1);
+                                    s2 += b.x; q2 = fmaf(b.x, b.x, q2);
+                                    s3 += b.y; q3 = fmaf(b.y, b.y, q3);
                                 }
                             }
+                            // gn_part[hf][band][quad][2]
+                            float* part = gn_part + ((hf * 4 + band) * 32 + quad) * 2;
+                            part[0] = (s0 + s1) + (s2 + s3);
+                            part[1] = (q0 + q1) + (q2 + q3);
                         }
-                        const int col0 = n_idx * BN + hf * HALF + oct * 8;
-                        const int g0 = (n_idx * BN) / p.stats_cpg;
-                        const int dl = r_begin / p.stats_rows;   // 0 or 1: domain inside the tile
-                        float* bins = gn_bins + dl * 64;
-                        int g = col0 / p.stats_cpg;
-                        float as = 0.f, aq = 0.f;
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int gi = (col0 + i) / p.stats_cpg;
-                            if (gi != g) {
-                                atomicAdd(&bins[2 * (g - g0)], as);
-                                atomicAdd(&bins[2 * (g - g0) + 1], aq);
-                                g = gi; as = 0.f; aq = 0.f;
-                            }
-                            as += sm[i]; aq += sq[i];
-                        }
-                        atomicAdd(&bins[2 * (g - g0)], as);
-                        atomicAdd(&bins[2 * (g - g0) + 1], aq);
                     }
                 }
                 if (p.stats != nullptr) {
-                    named_bar_sync(1, 128);
-                    const int et = threadIdx.x - 64;
-                    const int g0 = (n_idx * BN) / p.stats_cpg;
-                    const int dom_base = (org[1] * p.stats_mul[0] + org[2] * p.stats_mul[1] + org[3] * p.stats_mul[2] +
-                                          org[4] * p.stats_mul[3]) / p.stats_div;
-                    const int bdl = et >> 6, bg = (et & 63) >> 1;
-                    const float val = gn_bins[et];
-                    if (g0 + bg < 32 && (bdl == 0 || p.stats_rows < GEMM_BM) && val != 0.f)
-                        atomicAdd(&p.stats[(static_cast<size_t>(dom_base + bdl) * 32 + (g0 + bg)) * 2 + (et & 1)],
-                                  static_cast<double>(val));
+                    if constexpr (HALF == 128) {
+                        named_bar_sync(1, 128);
+                        // thread = (domain-in-tile, local group, statistic): fold bands x quads of that group
+                        const int et = threadIdx.x - 64;
+                        const int cpg = p.stats_cpg;                 // multiple of 4
+                        const int qpg = cpg >> 2;                    // quads per group
+                        const int ndom = (p.stats_rows < GEMM_BM) ? 2 : 1;
+                        const int bands_per_dom = 4 / ndom;
+                        const int col_base = n_idx * BN;
+                        const int g_first = col_base / cpg;
+                        const int groups_tile = (col_base + BN - 1) / cpg - g_first + 1;   // groups intersecting this tile
+                        const int dom_base = (org[1] * p.stats_mul[0] + org[2] * p.stats_mul[1] + org[3] * p.stats_mul[2] +
+                                              org[4] * p.stats_mul[3]) / p.stats_div;
+                        for (int item = et; item < ndom * groups_tile * 2; item += 128) {
+                            const int st = item & 1;
+                            const int gl = (item >> 1) % groups_tile;
+                            const int dl = (item >> 1) / groups_tile;
+                            const int g = g_first + gl;
+                            if (g >= 32) continue;
+                            // quads of group g inside this tile: global quad index = column / 4
+                            const int q_lo = max(g * qpg, col_base >> 2), q_hi = min((g + 1) * qpg, (col_base + BN) >> 2);
+                            float acc = 0.f;
+                            for (int q = q_lo; q < q_hi; ++q) {
+                                const int ql = q - (col_base >> 2);           // 0 .. BN/4-1
+                                const int hfq = ql >> 5, quad = ql & 31;
+                                for (int b = 0; b < bands_per_dom; ++b)
+                                    acc += gn_part[((hfq * 4 + dl * bands_per_dom + b) * 32 + quad) * 2 + st];
+                            }
+                            if (q_hi > q_lo)
+                                atomicAdd(&p.stats[(static_cast<size_t>(dom_base + dl) * 32 + g) * 2 + st], static_cast<double>(acc));
+                        }
+                    }
                 }
             } else {
                 // narrow-N head: fp32 scatter, row -> token coordinates via the box decomposition

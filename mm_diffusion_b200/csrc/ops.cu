@@ -167,6 +167,16 @@ int build_gemm(const GemmProblem& pr, GemmParams* out) {
         p.stats_valid_coord = pr.stats_valid_coord;
         if (pr.stats_rows != 128 && pr.stats_rows != 64) return fail(MMD_EINVAL, "stats_rows %d", pr.stats_rows);
     }
+    if (pr.xf_sums) {
+        const int xc = pr.src_c[pr.xf_src];
+        if (pr.n_taps != 1 || xc > GEMM_XF_MAXC || xc % 64 != 0 || xc % 32 != 0 || (pr.xf_rows != 64 && pr.xf_rows != 128))
+            return fail(MMD_EINVAL, "fused GroupNorm apply: unsupported shape (taps %d, channels %d, rows %d)", pr.n_taps, xc, pr.xf_rows);
+        p.xf_sums = pr.xf_sums; p.xf_gamma = pr.xf_gamma; p.xf_beta = pr.xf_beta; p.xf_film = pr.xf_film;
+        p.xf_film_ld = pr.xf_film_ld; p.xf_dom_per_batch = pr.xf_dom_per_batch; p.xf_src = pr.xf_src; p.xf_c = xc;
+        p.xf_nsub = pr.xf_nsub; p.xf_silu = pr.xf_silu; p.xf_inv_n = pr.xf_inv_n; p.xf_rows = pr.xf_rows;
+        for (int i = 0; i < 4; ++i) p.xf_mul[i] = pr.xf_mul[i];
+        p.xf_div = pr.xf_div;
+    }
     return MMD_OK;
 }
 
@@ -400,10 +410,30 @@ int mmd_op_conv(const MmdConvDesc* d, void* stream) {
         for (int j = 0; j < 3; ++j) pr.taps[t][j] = d->taps[t][j];
     pr.n = d->n;
     pr.bn = d->out_f32 ? 16 : pick_bn(d->n);
+    {   // same wide-tile rule as the model plan: 256-wide N tiles once there are at least two waves of them
+        const long long mt = (pr.g.tokens() + GEMM_BM - 1) / GEMM_BM;
+        if (pr.bn == 128 && d->n % 256 == 0 && mt * (d->n / 256) >= 2LL * num_sms()) pr.bn = 256;
+    }
     pr.out = static_cast<act_t*>(d->out);
     pr.out_f32 = d->out_f32;
     for (int i = 0; i < 4; ++i) pr.ostride[i] = d->ostride[i];
     pr.ostride_c = d->ostride_c;
+    if (d->gn_sums) {
+        if (d->out_f32 || d->n % 128 != 0) return fail(MMD_EINVAL, "fused GroupNorm statistics need fp16 output and n %% 128 == 0");
+        pr.stats = d->gn_sums;
+        if (d->rank == 2 && (d->gn_rows == 64 || (d->gn_rows > 0 && d->gn_rows % 128 == 0))) {
+            pr.stats_rows = static_cast<int>(d->gn_rows < 128 ? d->gn_rows : 128);
+            pr.stats_mul[0] = 1;
+            pr.stats_div = static_cast<int>(d->gn_rows);
+        } else if (d->rank == 3 && d->gn_rows == d->dims[0] && pr.g.box[0] == GEMM_BM) {
+            pr.stats_rows = 128; pr.stats_mul[1] = 1; pr.stats_div = 1; pr.stats_valid_coord = 0;
+        } else if (d->rank == 4 && d->gn_rows == d->dims[0] && pr.g.box[0] >= 64) {
+            pr.stats_rows = pr.g.box[0]; pr.stats_mul[1] = 1; pr.stats_mul[2] = static_cast<int>(d->dims[1]); pr.stats_div = 1;
+        } else {
+            return fail(MMD_EINVAL, "fused GroupNorm statistics: unsupported geometry (rank %d, gn_rows %lld)", d->rank,
+                        static_cast<long long>(d->gn_rows));
+        }
+    }
     const long long kt = pr.k_total();
     const int npad = pr.n_pad();
     act_t* wp = nullptr;

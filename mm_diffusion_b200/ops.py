@@ -17,7 +17,8 @@ from . import _lib
 from ._lib import MmdAttnDesc, MmdConvDesc, check, current_stream_ptr, ptr
 
 
-def _conv(srcs, weight, bias, n, rank, dims, taps, out=None, out_f32=None, ostride=None, ostride_c=0):
+def _conv(srcs, weight, bias, n, rank, dims, taps, out=None, out_f32=None, ostride=None, ostride_c=0, gn_sums=None,
+          gn_rows=0):
     lib = _lib.load()
     d = MmdConvDesc()
     d.rank = rank
@@ -46,17 +47,25 @@ def _conv(srcs, weight, bias, n, rank, dims, taps, out=None, out_f32=None, ostri
         for i in range(4):
             d.ostride[i] = ostride[i] if i < len(ostride) else 0
     d.ostride_c = ostride_c
+    if gn_sums is not None:
+        assert gn_sums.dtype == torch.float64 and gn_sums.is_contiguous() and gn_sums.is_cuda
+        d.gn_sums = gn_sums.data_ptr()
+        d.gn_rows = gn_rows
     check(lib.mmd_op_conv(C.byref(d), current_stream_ptr()))
     return out if out is not None else out_f32
 
 
-def conv_pointwise(srcs, weight, bias):
-    """1x1(x1) conv over token matrices [M, C_i] (channel-concatenated sources) -> [M, Cout] fp16."""
+def conv_pointwise(srcs, weight, bias, gn_sums=None, gn_rows=0):
+    """1x1(x1) conv over token matrices [M, C_i] (channel-concatenated sources) -> [M, Cout] fp16.
+
+    gn_sums (float64 [M / gn_rows, 32, 2], zeroed by the caller) receives the GroupNorm(32) sum / sum of squares of
+    the output per run of gn_rows tokens, reduced inside the GEMM epilogue."""
     m = srcs[0].numel() // srcs[0].shape[-1]
     n = weight.shape[0]
     out = torch.empty(srcs[0].shape[:-1] + (n,), dtype=torch.float16, device=srcs[0].device)
     w = weight.reshape(n, -1, 1)
-    return _conv([s.reshape(m, s.shape[-1]) for s in srcs], w, bias, n, 2, [m], [(0, 0, 0)], out=out)
+    return _conv([s.reshape(m, s.shape[-1]) for s in srcs], w, bias, n, 2, [m], [(0, 0, 0)], out=out, gn_sums=gn_sums,
+                 gn_rows=gn_rows)
 
 
 def conv_spatial(x, weight, bias):
@@ -68,22 +77,26 @@ def conv_spatial(x, weight, bias):
     return _conv([x], weight.reshape(n, Ci, 9), bias, n, 4, [W, H, N], taps, out=out)
 
 
-def conv_temporal(x, weight, bias):
-    """k=3 'same' conv along frames: x [B,F,P,C], weight [Co,Ci,3] -> [B,F,P,Co]."""
+def conv_temporal(x, weight, bias, gn_sums=None):
+    """k=3 'same' conv along frames: x [B,F,P,C], weight [Co,Ci,3] -> [B,F,P,Co].
+
+    gn_sums: optional float64 [B*F, 32, 2] fused output statistics (one domain per frame)."""
     B, F, P, Ci = x.shape
     n = weight.shape[0]
     out = torch.empty((B, F, P, n), dtype=torch.float16, device=x.device)
     taps = [(0, k - 1, 0) for k in range(3)]
-    return _conv([x], weight.reshape(n, Ci, 3), bias, n, 4, [P, F, B], taps, out=out)
+    return _conv([x], weight.reshape(n, Ci, 3), bias, n, 4, [P, F, B], taps, out=out, gn_sums=gn_sums, gn_rows=P)
 
 
-def conv_audio(x, weight, bias, dilation=1):
-    """k=3 dilated 'same' conv: x [B,L,C], weight [Co,Ci,3] -> [B,L,Co]."""
+def conv_audio(x, weight, bias, dilation=1, gn_sums=None):
+    """k=3 dilated 'same' conv: x [B,L,C], weight [Co,Ci,3] -> [B,L,Co].
+
+    gn_sums: optional float64 [B, 32, 2] fused output statistics (one domain per sample)."""
     B, L, Ci = x.shape
     n = weight.shape[0]
     out = torch.empty((B, L, n), dtype=torch.float16, device=x.device)
     taps = [((k - 1) * dilation, 0, 0) for k in range(3)]
-    return _conv([x], weight.reshape(n, Ci, 3), bias, n, 3, [L, B], taps, out=out)
+    return _conv([x], weight.reshape(n, Ci, 3), bias, n, 3, [L, B], taps, out=out, gn_sums=gn_sums, gn_rows=L)
 
 
 def conv3d_head(x, weight, bias):

@@ -30,7 +30,8 @@ def _rand(*shape, scale=1.0, seed=0):
 
 
 @pytest.mark.parametrize("m,cins,cout", [(256, [128], 128), (1000, [64], 64), (4096, [256, 128], 256),
-                                          (300, [128, 64, 64], 384), (16384, [512], 1536)])
+                                          (300, [128, 64, 64], 384), (16384, [512], 1536),
+                                          (65536, [128], 512), (40000, [192, 64], 256)])
 def test_conv_pointwise(ops, m, cins, cout):
     xs = [_rand(m, c, seed=i).half() for i, c in enumerate(cins)]
     w = _rand(cout, sum(cins), scale=0.05, seed=7)
@@ -38,6 +39,53 @@ def test_conv_pointwise(ops, m, cins, cout):
     y = ops.conv_pointwise(xs, w, b)
     ref = torch.cat([x.float() for x in xs], dim=1) @ w.t() + b
     assert rel_l2(y, ref) < 2e-3
+
+
+def _ref_gn_sums(y, domains):
+    """(sum, sum of squares) per (domain, group of C/32 channels) of the fp16 result the kernel stored."""
+    c = y.shape[-1]
+    yd = y.double().reshape(domains, -1, 32, c // 32)
+    return torch.stack([yd.sum(dim=(1, 3)), (yd * yd).sum(dim=(1, 3))], dim=-1)
+
+
+def _check_sums(got, y, domains):
+    ref = _ref_gn_sums(y, domains)
+    err = (got - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 1e-5, err
+
+
+@pytest.mark.parametrize("m,cin,cout,rows", [(1024, 128, 128, 128), (1024, 128, 128, 64), (4096, 64, 256, 1024),
+                                             (8192, 128, 384, 4096), (65536, 128, 512, 4096), (40960, 256, 256, 64)])
+def test_conv_pointwise_fused_gn_statistics(ops, m, cin, cout, rows):
+    """GEMM-epilogue GroupNorm statistics (128- and 256-wide tiles, 1 or 2 domains per tile) == sums over the output."""
+    x = _rand(m, cin, seed=21).half()
+    w = _rand(cout, cin, scale=0.05, seed=22)
+    b = _rand(cout, seed=23)
+    sums = torch.zeros(m // rows, 32, 2, dtype=torch.float64, device="cuda")
+    y = ops.conv_pointwise([x], w, b, gn_sums=sums, gn_rows=rows)
+    assert rel_l2(y, x.float() @ w.t() + b) < 2e-3
+    _check_sums(sums, y, m // rows)
+
+
+@pytest.mark.parametrize("b,f,p,c", [(2, 16, 256, 128), (1, 16, 64, 128), (1, 8, 1024, 256)])
+def test_conv_temporal_fused_gn_statistics(ops, b, f, p, c):
+    x = _rand(b, f, p, c, seed=4).half()
+    wt = _rand(c, c, 3, scale=0.05, seed=5)
+    bias = _rand(c, seed=6)
+    sums = torch.zeros(b * f, 32, 2, dtype=torch.float64, device="cuda")
+    y = ops.conv_temporal(x, wt, bias, gn_sums=sums)
+    _check_sums(sums, y, b * f)
+
+
+@pytest.mark.parametrize("b,l,ci,co,dil", [(2, 1600, 128, 128, 1), (3, 400, 128, 256, 4), (1, 25600, 128, 128, 2)])
+def test_conv_audio_fused_gn_statistics(ops, b, l, ci, co, dil):
+    """ragged last tile (L % 128 != 0): padding rows must not enter the statistics"""
+    x = _rand(b, l, ci, seed=9).half()
+    wt = _rand(co, ci, 3, scale=0.05, seed=10)
+    bias = _rand(co, seed=11)
+    sums = torch.zeros(b, 32, 2, dtype=torch.float64, device="cuda")
+    y = ops.conv_audio(x, wt, bias, dil, gn_sums=sums)
+    _check_sums(sums, y, b)
 
 
 @pytest.mark.parametrize("n,h,w,ci,co", [(2, 64, 64, 128, 128), (3, 32, 32, 256, 128), (5, 16, 16, 64, 64),
