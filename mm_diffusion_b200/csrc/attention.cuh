@@ -129,6 +129,7 @@ __global__ void __launch_bounds__(ATT_THREADS, (D == 64) ? 2 : 1) attention_kern
     const AttnWork w = attn_decode(p, blockIdx.x);
     const int T = w.n_tiles;
 
+    pdl_trigger();
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&p.q_map);
         tma_prefetch_desc(&p.k_map);
@@ -150,6 +151,7 @@ __global__ void __launch_bounds__(ATT_THREADS, (D == 64) ? 2 : 1) attention_kern
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();   // q/k/v come from the previous kernel
     const uint32_t tmem_S = tmem_base;                // SBUF 128-column buffers
     const uint32_t tmem_O = tmem_base + Cfg::O_COL;   // D columns
 
@@ -484,6 +486,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention64_kernel(const __gri
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
+    pdl_trigger();
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&p.q_map);
         tma_prefetch_desc(&p.k_map);
@@ -507,6 +510,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention64_kernel(const __gri
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();   // q/k/v come from the previous kernel
     const uint32_t tmem_S = tmem_base;
     const uint32_t tmem_O = tmem_base + 128;
     const uint32_t tmem_L = tmem_base + 192;

@@ -253,6 +253,12 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, int a_mn_maj
 // SWIZZLE_128B tile (tile base 1024-B aligned).
 MMD_DEVINL uint32_t sw128_off(uint32_t r, uint32_t c16) { return r * 128u + ((c16 ^ (r & 7u)) << 4); }
 
+// Programmatic dependent launch: the next kernel of the stream may start its prologue while this one drains;
+// every kernel that is launched with the PDL attribute calls pdl_wait() before its first global access.
+// (Both are no-ops for a kernel launched without the attribute.)
+MMD_DEVINL void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+MMD_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 MMD_DEVINL void named_bar_sync(uint32_t id, uint32_t nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

@@ -31,6 +31,8 @@ MMD_DEVINL float silu_fast(float x) {
 constexpr int GN_UNROLL = 4;
 
 __global__ void __launch_bounds__(256) gn_stats_kernel(GnSrc s, int R, int rows_per_block, double* __restrict__ sums) {
+    pdl_trigger();
+    pdl_wait();
     const int C = s.c1 + s.c2;
     const int cpg = C / 32;
     const int vpr = C / 8;  // 16-byte vectors per row
@@ -101,6 +103,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnSrc s, int R, int rows_
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 const float* __restrict__ film, int film_ld, int ns_per_batch, int do_silu,
                                 act_t* __restrict__ y, int nsub, long long stat_rows) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float coef[];  // [2][C] then [64] group mean / rstd
     const int C = s.c1 + s.c2;
     const int cpg = C / 32;
@@ -194,6 +198,8 @@ template <int CPG, int F_>
 __global__ void __launch_bounds__(128) gn_temporal_kernel(const act_t* __restrict__ x, act_t* __restrict__ y,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           int B, int P, int C) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int VEC = (CPG % 8 == 0) ? 8 : ((CPG % 4 == 0) ? 4 : 2);
     constexpr int NV = CPG / VEC;
     using V = typename GnVec<VEC>::type;
@@ -258,6 +264,8 @@ __global__ void __launch_bounds__(128) gn_temporal_kernel(const act_t* __restric
 // ---------------------------------------------------------------------------
 __global__ void resample_kernel(const act_t* __restrict__ x, act_t* __restrict__ y, int mode, int N, int H, int W,
                                 int C) {
+    pdl_trigger();
+    pdl_wait();
     // video: x [N][H][W][C]; audio: x [N][H(=L)][C] with W unused
     const int vpr = C / 8;
     const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -327,6 +335,8 @@ __global__ void resample_kernel(const act_t* __restrict__ x, act_t* __restrict__
 // audio fp32 [B][1][L]     -> A [B*L][64]    with k = tap.
 // ---------------------------------------------------------------------------
 __global__ void im2col_video_kernel(const float* __restrict__ x, act_t* __restrict__ a, int BF, int Cin, int H, int W) {
+    pdl_trigger();
+    pdl_wait();
     const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     const long long total = static_cast<long long>(BF) * H * W * 8;  // 8 vectors of 8 per token
     if (idx >= total) return;
@@ -352,6 +362,8 @@ __global__ void im2col_video_kernel(const float* __restrict__ x, act_t* __restri
 }
 
 __global__ void im2col_audio_kernel(const float* __restrict__ x, act_t* __restrict__ a, int B, int Cin, int L) {
+    pdl_trigger();
+    pdl_wait();
     const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     const long long total = static_cast<long long>(B) * L * 8;
     if (idx >= total) return;
@@ -384,6 +396,8 @@ __global__ void im2col_audio_kernel(const float* __restrict__ x, act_t* __restri
 __global__ void time_embed_kernel(const float* __restrict__ t, const float* __restrict__ w1, const float* __restrict__ b1,
                                   const float* __restrict__ w2, const float* __restrict__ b2, int dim,
                                   float* __restrict__ emb_out, float* __restrict__ silu_emb_out) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float sh[];  // [2][dim]
     float* e0 = sh;
     float* e1 = sh + dim;
@@ -416,6 +430,8 @@ __global__ void time_embed_kernel(const float* __restrict__ t, const float* __re
 // (rows of all 28 emb_layers.1 Linear layers stacked).  One warp per row j.
 __global__ void emb_layers_kernel(const float* __restrict__ silu_emb, const float* __restrict__ w,
                                   const float* __restrict__ bias, int B, int dim, int rows, float* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
     const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (j >= rows) return;
@@ -462,6 +478,8 @@ constexpr int TATT_WARPS = 4;
 template <int F_>
 __global__ void __launch_bounds__(TATT_WARPS * 32) temporal_attn_kernel(const act_t* __restrict__ qkv, act_t* __restrict__ out,
                                                                          int B, int P, int C, int heads) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(16) uint8_t tsm[];
     const int d = C / heads;
     const int pitch = d + 8;  // halves; 16-byte aligned rows, conflict-free ldmatrix

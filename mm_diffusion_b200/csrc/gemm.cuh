@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
     for (int s = 0; s < p.n_src; ++s) total_chunks += p.src_chunks[s];
     const int num_kb = p.n_taps * total_chunks;
 
+    pdl_trigger();   // the next kernel of the stream may start its own prologue from here on
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.n_src; ++s) tma_prefetch_desc(&p.a_map[s]);
         tma_prefetch_desc(&p.b_map);
@@ -141,12 +142,26 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (warp != 0) pdl_wait();   // the producer thread waits after it has requested the first weight tiles
 
     if (warp == 0) {
         // ================= TMA producer (one thread) =================
         if (lane == 0) {
+            // Weights are constants of the plan, activations come from the previous kernel: the B halves of the first
+            // pipeline stages are requested before the grid dependency resolves, the A halves after it.
+            int pre = 0;
+            if (static_cast<int>(blockIdx.x) < total_tiles) {
+                const int n_idx0 = blockIdx.x % p.n_tiles;
+                pre = min(S::STAGES, num_kb);
+                for (int kb = 0; kb < pre; ++kb) {
+                    mbar_expect_tx(&full_bar[kb], S::STAGE_BYTES);
+                    tma_load_2d(stage_base + kb * S::STAGE_BYTES + S::A_BYTES, &p.b_map, &full_bar[kb], kb * GEMM_BK, n_idx0 * BN);
+                }
+            }
+            pdl_wait();
             int stage = 0;
             uint32_t phase = 0;
+            int gk = 0;   // k-blocks issued by this CTA (the first `pre` already have their B half in flight)
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int m_idx = tile / p.n_tiles;
                 const int n_idx = tile - m_idx * p.n_tiles;
@@ -160,14 +175,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                     c[3] = org[3] + p.tap[t][2];
                     c[4] = org[4];
                     for (int s = 0; s < p.n_src; ++s) {
-                        for (int ch = 0; ch < p.src_chunks[s]; ++ch, ++kb) {
+                        for (int ch = 0; ch < p.src_chunks[s]; ++ch, ++kb, ++gk) {
                             mbar_wait(&empty_bar[stage], phase ^ 1);
                             uint8_t* a_dst = stage_base + stage * S::STAGE_BYTES;
                             uint8_t* b_dst = a_dst + S::A_BYTES;
-                            mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+                            if (gk >= pre) mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
                             c[0] = ch * GEMM_BK;
                             tma_load_nd(p.rank, a_dst, &p.a_map[s], &full_bar[stage], c);
-                            tma_load_2d(b_dst, &p.b_map, &full_bar[stage], kb * GEMM_BK, n_idx * BN);
+                            if (gk >= pre) tma_load_2d(b_dst, &p.b_map, &full_bar[stage], kb * GEMM_BK, n_idx * BN);
                             if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
                         }
                     }

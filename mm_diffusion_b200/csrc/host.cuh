@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/mmdiff.h"
@@ -35,6 +36,46 @@ int fail(int code, const char* fmt, ...);
     } while (0)
 
 int num_sms();
+
+// ------------------------------------------- programmatic dependent launch
+// Inside a PdlScope, a kernel launched on one of the scope's streams right after another kernel of ours carries the
+// programmatic-stream-serialization attribute: its CTAs may become resident (barrier init, TMEM allocation,
+// descriptor prefetch) while the predecessor drains, and block in griddepcontrol.wait until it has completed.
+// Any other operation on the stream (memset, copy, event wait) disarms the next launch.  MMD_NO_PDL=1 disables it.
+struct PdlState {
+    bool active = false;
+    cudaStream_t streams[2] = {nullptr, nullptr};
+    bool armed[2] = {false, false};
+};
+PdlState& pdl_state();
+struct PdlScope {
+    PdlScope(cudaStream_t s0, cudaStream_t s1);
+    ~PdlScope();
+};
+void pdl_break(cudaStream_t st);   // a non-kernel operation went onto `st`
+void pdl_break_all();
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    PdlState& ps = pdl_state();
+    int idx = -1;
+    if (ps.active) idx = (st == ps.streams[0]) ? 0 : ((st == ps.streams[1]) ? 1 : -1);
+    if (idx >= 0 && ps.armed[idx]) {
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
+    if (idx >= 0) ps.armed[idx] = (e == cudaSuccess);
+    return e;
+}
 
 // --------------------------------------------------------------- TMA maps
 // dims[0] is the innermost (contiguous) extent; strides_bytes[i] is the stride of dims[i+1].

@@ -770,6 +770,7 @@ struct Walker {
             const size_t sbytes = stats.cap;
             push([=](cudaStream_t st) -> int {
                 MMD_CUDA_OK(cudaMemsetAsync(sbase, 0, sbytes, st));
+                pdl_break(st);
                 return MMD_OK;
             }, "memset", 0.0, static_cast<double>(sbytes), 0);
         }
@@ -786,10 +787,8 @@ struct Walker {
                 const float* ew = m.bpk + m.emb_w_off;
                 const float* eb = m.bpk + m.emb_b_off;
                 push([=](cudaStream_t st) -> int {
-                    time_embed_kernel<<<Bc, E, 2 * E * sizeof(float), st>>>(tdev, w1, b1, w2, b2, E, emb, se);
-                    MMD_CUDA_OK(cudaGetLastError());
-                    emb_layers_kernel<<<(rows + 7) / 8, 256, 0, st>>>(se, ew, eb, Bc, E, rows, ea);
-                    MMD_CUDA_OK(cudaGetLastError());
+                    MMD_CUDA_OK(launch_kernel(time_embed_kernel, Bc, E, 2 * E * sizeof(float), st, tdev, w1, b1, w2, b2, E, emb, se));
+                    MMD_CUDA_OK(launch_kernel(emb_layers_kernel, (rows + 7) / 8, 256, 0, st, se, ew, eb, Bc, E, rows, ea));
                     return MMD_OK;
                 }, "time_embed", 2.0 * Bc * (2.0 * E * E + static_cast<double>(rows) * E), 4.0 * (static_cast<double>(rows) * E + 2.0 * E * E), 2);
                 sync_branches();   // the statistics memset and the FiLM table precede both branches
@@ -826,8 +825,8 @@ struct Walker {
                         const int BF = B * F(), Cv = c.video_c, H = c.video_h, W = c.video_w;
                         push([=](cudaStream_t st) -> int {
                             const long long tv = static_cast<long long>(BF) * H * W * 8;
-                            im2col_video_kernel<<<static_cast<unsigned>((tv + 255) / 256), 256, 0, st>>>(vin, colv, BF, Cv, H, W);
-                            MMD_CUDA_OK(cudaGetLastError());
+                            MMD_CUDA_OK(launch_kernel(im2col_video_kernel, static_cast<unsigned>((tv + 255) / 256), 256, 0, st, vin, colv,
+                                                      BF, Cv, H, W));
                             return MMD_OK;
                         }, "im2col", 0.0, (4.0 * Cv + 128.0) * static_cast<double>(BF) * H * W, 1);
                     }
@@ -846,8 +845,8 @@ struct Walker {
                         const int Bc = B, Ca = c.audio_c, L = c.audio_l;
                         push([=](cudaStream_t st) -> int {
                             const long long ta = static_cast<long long>(Bc) * L * 8;
-                            im2col_audio_kernel<<<static_cast<unsigned>((ta + 255) / 256), 256, 0, st>>>(ain, cola, Bc, Ca, L);
-                            MMD_CUDA_OK(cudaGetLastError());
+                            MMD_CUDA_OK(launch_kernel(im2col_audio_kernel, static_cast<unsigned>((ta + 255) / 256), 256, 0, st, ain, cola,
+                                                      Bc, Ca, L));
                             return MMD_OK;
                         }, "im2col", 0.0, (4.0 * Ca + 128.0) * static_cast<double>(Bc) * L, 1);
                     }
@@ -1232,9 +1231,11 @@ int mmd_model_forward(MmdModel* m, int batch, const float* video_in, const float
                 return ev;
             };
             MMD_CUDA_OK(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal));
+            PdlScope pdl(m->cap_stream, two ? m->cap_stream2 : nullptr);
             int r = MMD_OK;
             cudaError_t ce = cudaSuccess;
             auto cross_sync = [&]() {
+                pdl_break_all();   // the kernels after a join have two predecessors: plain launches
                 cudaEvent_t e0 = new_event(), e1 = new_event();
                 ce = cudaEventRecord(e0, m->cap_stream);
                 if (ce == cudaSuccess) ce = cudaEventRecord(e1, m->cap_stream2);
@@ -1266,6 +1267,7 @@ int mmd_model_forward(MmdModel* m, int batch, const float* video_in, const float
         }
         MMD_CUDA_OK(cudaGraphLaunch(plan->graph, st));
     } else {
+        PdlScope pdl(st, nullptr);
         for (auto& step : plan->steps) MMD_TRY(step(st));
     }
     MMD_CUDA_OK(cudaMemcpyAsync(video_out, plan->out_video, vout, cudaMemcpyDeviceToDevice, st));

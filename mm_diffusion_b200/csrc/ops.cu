@@ -191,16 +191,35 @@ int gemm_init_attrs() {
     return MMD_OK;
 }
 
+PdlState& pdl_state() {
+    static thread_local PdlState s;
+    return s;
+}
+PdlScope::PdlScope(cudaStream_t s0, cudaStream_t s1) {
+    static const bool off = [] { const char* e = getenv("MMD_NO_PDL"); return e && e[0] == '1'; }();
+    PdlState& ps = pdl_state();
+    ps.active = !off;
+    ps.streams[0] = s0;
+    ps.streams[1] = s1;
+    ps.armed[0] = ps.armed[1] = false;
+}
+PdlScope::~PdlScope() { pdl_state().active = false; }
+void pdl_break(cudaStream_t st) {
+    PdlState& ps = pdl_state();
+    for (int i = 0; i < 2; ++i)
+        if (ps.streams[i] == st) ps.armed[i] = false;
+}
+void pdl_break_all() { pdl_state().armed[0] = pdl_state().armed[1] = false; }
+
 int launch_gemm(const GemmParams& p, int bn, cudaStream_t st) {
     MMD_TRY(gemm_init_attrs());
     const int tiles = p.m_tiles * p.n_tiles;
     const int grid = std::min(tiles, num_sms());
-    if (bn == 256) conv_gemm_kernel<256><<<grid, GEMM_THREADS, GemmSmem<256>::TOTAL, st>>>(p);
-    else if (bn == 128) conv_gemm_kernel<128><<<grid, GEMM_THREADS, GemmSmem<128>::TOTAL, st>>>(p);
-    else if (bn == 64) conv_gemm_kernel<64><<<grid, GEMM_THREADS, GemmSmem<64>::TOTAL, st>>>(p);
-    else if (bn == 16) conv_gemm_kernel<16><<<grid, GEMM_THREADS, GemmSmem<16>::TOTAL, st>>>(p);
+    if (bn == 256) MMD_CUDA_OK(launch_kernel(conv_gemm_kernel<256>, grid, GEMM_THREADS, GemmSmem<256>::TOTAL, st, p));
+    else if (bn == 128) MMD_CUDA_OK(launch_kernel(conv_gemm_kernel<128>, grid, GEMM_THREADS, GemmSmem<128>::TOTAL, st, p));
+    else if (bn == 64) MMD_CUDA_OK(launch_kernel(conv_gemm_kernel<64>, grid, GEMM_THREADS, GemmSmem<64>::TOTAL, st, p));
+    else if (bn == 16) MMD_CUDA_OK(launch_kernel(conv_gemm_kernel<16>, grid, GEMM_THREADS, GemmSmem<16>::TOTAL, st, p));
     else return fail(MMD_EINVAL, "unsupported BN %d", bn);
-    MMD_CUDA_OK(cudaGetLastError());
     return MMD_OK;
 }
 
@@ -246,11 +265,11 @@ int launch_attn(const AttnParams& p, int d, cudaStream_t st) {
     }
     const int grid = p.B * p.n_blocks * p.heads * p.q_tiles;
     static const bool generic64 = [] { const char* e = getenv("MMD_ATTN_GENERIC"); return e && e[0] == '1'; }();
-    if (d == 64 && !generic64) attention64_kernel<<<std::min(grid, 2 * num_sms()), ATT_THREADS, Attn64Smem::TOTAL, st>>>(p, grid);
-    else if (d == 64) attention_kernel<64><<<grid, ATT_THREADS, attn_smem_bytes<64>(), st>>>(p);
-    else if (d == 96) attention_kernel<96><<<grid, ATT_THREADS, attn_smem_bytes<96>(), st>>>(p);
-    else attention_kernel<128><<<grid, ATT_THREADS, attn_smem_bytes<128>(), st>>>(p);
-    MMD_CUDA_OK(cudaGetLastError());
+    if (d == 64 && !generic64)
+        MMD_CUDA_OK(launch_kernel(attention64_kernel, std::min(grid, 2 * num_sms()), ATT_THREADS, Attn64Smem::TOTAL, st, p, grid));
+    else if (d == 64) MMD_CUDA_OK(launch_kernel(attention_kernel<64>, grid, ATT_THREADS, attn_smem_bytes<64>(), st, p));
+    else if (d == 96) MMD_CUDA_OK(launch_kernel(attention_kernel<96>, grid, ATT_THREADS, attn_smem_bytes<96>(), st, p));
+    else MMD_CUDA_OK(launch_kernel(attention_kernel<128>, grid, ATT_THREADS, attn_smem_bytes<128>(), st, p));
     return MMD_OK;
 }
 
@@ -268,11 +287,13 @@ static int gn_rows_per_block(int ns, int rows, int C) {
 int launch_gn_stats(const GnSrc& s, int ns, int rows, double* sums, cudaStream_t st, bool zero_sums) {
     const int C = s.c1 + s.c2;
     if (C % 32 != 0 || C % 8 != 0 || s.c1 % 8 != 0 || C / 8 > 256) return fail(MMD_EINVAL, "group norm channels %d unsupported", C);
-    if (zero_sums) MMD_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(double) * 64 * ns, st));
+    if (zero_sums) {
+        MMD_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(double) * 64 * ns, st));
+        pdl_break(st);
+    }
     const int rpb = gn_rows_per_block(ns, rows, C);
     dim3 grid((rows + rpb - 1) / rpb, ns);
-    gn_stats_kernel<<<grid, 256, 0, st>>>(s, rows, rpb, sums);
-    MMD_CUDA_OK(cudaGetLastError());
+    MMD_CUDA_OK(launch_kernel(gn_stats_kernel, grid, 256, 0, st, s, rows, rpb, sums));
     return MMD_OK;
 }
 
@@ -282,10 +303,8 @@ int launch_gn_apply(const GnSrc& s, int ns, int rows, const double* sums, const 
     const int C = s.c1 + s.c2;
     const int rpb = gn_rows_per_block(ns, rows, C);
     dim3 grid((rows + rpb - 1) / rpb, ns);
-    gn_apply_kernel<<<grid, 256, (2 * C + 64) * sizeof(float), st>>>(s, rows, rpb, sums, gamma, beta, film, film_ld,
-                                                                      ns_per_batch, silu, y, nsub,
-                                                                      stat_rows > 0 ? stat_rows : rows);
-    MMD_CUDA_OK(cudaGetLastError());
+    MMD_CUDA_OK(launch_kernel(gn_apply_kernel, grid, 256, (2 * C + 64) * sizeof(float), st, s, rows, rpb, sums, gamma, beta, film,
+                              film_ld, ns_per_batch, silu, y, nsub, stat_rows > 0 ? stat_rows : static_cast<long long>(rows)));
     return MMD_OK;
 }
 
@@ -294,10 +313,9 @@ static int launch_gn_temporal_cpg(const act_t* x, act_t* y, const float* gamma, 
                                   cudaStream_t st) {
     const long long total = static_cast<long long>(B) * P * 32;
     const unsigned grid = static_cast<unsigned>((total + 127) / 128);
-    if (F == 16) gn_temporal_kernel<CPG, 16><<<grid, 128, 0, st>>>(x, y, gamma, beta, B, P, C);
-    else if (F == 8) gn_temporal_kernel<CPG, 8><<<grid, 128, 0, st>>>(x, y, gamma, beta, B, P, C);
+    if (F == 16) MMD_CUDA_OK(launch_kernel(gn_temporal_kernel<CPG, 16>, grid, 128, 0, st, x, y, gamma, beta, B, P, C));
+    else if (F == 8) MMD_CUDA_OK(launch_kernel(gn_temporal_kernel<CPG, 8>, grid, 128, 0, st, x, y, gamma, beta, B, P, C));
     else return fail(MMD_EINVAL, "temporal group norm supports 8 or 16 frames, got %d", F);
-    MMD_CUDA_OK(cudaGetLastError());
     return MMD_OK;
 }
 
@@ -321,8 +339,7 @@ int launch_resample(const act_t* x, act_t* y, int mode, int n, int h, int w, int
     else if (mode == 2) total = static_cast<long long>(n) * (h * 2) * (w * 2) * vpr;
     else if (mode == 3) total = static_cast<long long>(n) * (h * 4) * vpr;
     else return fail(MMD_EINVAL, "resample mode %d", mode);
-    resample_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(x, y, mode, n, h, w, c);
-    MMD_CUDA_OK(cudaGetLastError());
+    MMD_CUDA_OK(launch_kernel(resample_kernel, static_cast<unsigned>((total + 255) / 256), 256, 0, st, x, y, mode, n, h, w, c));
     return MMD_OK;
 }
 
@@ -339,10 +356,9 @@ int launch_temporal_attn(const act_t* qkv, act_t* out, int B, int F, int P, int 
         attr_done = true;
     }
     if (smem > 96 * 1024) return fail(MMD_EINVAL, "temporal attention head dim %d too large", d);
-    if (F == 16) temporal_attn_kernel<16><<<grid, TATT_WARPS * 32, smem, st>>>(qkv, out, B, P, C, heads);
-    else if (F == 8) temporal_attn_kernel<8><<<grid, TATT_WARPS * 32, smem, st>>>(qkv, out, B, P, C, heads);
+    if (F == 16) MMD_CUDA_OK(launch_kernel(temporal_attn_kernel<16>, grid, TATT_WARPS * 32, smem, st, qkv, out, B, P, C, heads));
+    else if (F == 8) MMD_CUDA_OK(launch_kernel(temporal_attn_kernel<8>, grid, TATT_WARPS * 32, smem, st, qkv, out, B, P, C, heads));
     else return fail(MMD_EINVAL, "temporal attention supports F in {8,16}, got %d", F);
-    MMD_CUDA_OK(cudaGetLastError());
     return MMD_OK;
 }
 

@@ -13,3 +13,11 @@ print("ms/step", d["ms_per_step"], "value", d["value"], "e2e", d["e2e"]["value"]
 for k,v in d["families"].items(): print(f"  {k:20s} {v['ms']:8.3f} ms  {v['launches']:4d} launches  {v['tflops']:8.1f} TF/s  {v['gbs']:8.1f} GB/s")
 print(d["clocks"])
 PY
+if [ -n "$COMPARE_ENV" ]; then
+  env $COMPARE_ENV timeout 600 python bench.py --steps ${STEPS:-20} --warmup 3 --batch ${BATCH:-4} --no-cpu-baseline > gpurun_out/bench_cmp.json 2> gpurun_out/bench_cmp.err
+  python - <<'PY'
+import json,os
+d=json.load(open("gpurun_out/bench_cmp.json"))
+print(os.environ.get("COMPARE_ENV"), "-> ms/step", d["ms_per_step"], "value", d["value"], "e2e", d["e2e"]["value"])
+PY
+fi
