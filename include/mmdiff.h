@@ -99,6 +99,17 @@ int mmd_p_sample_tail(const float* x, const float* eps, const float* noise, cons
 int mmd_q_sample(const float* x_start, const float* noise, const float* coef, int batch, int64_t per_sample, float* out,
                  void* stream);
 
+/* ---- DPM-Solver state arithmetic (DPM_Solver, multimodal_dpm_solver_plus.py:373-1298) ----
+ * Every solver update and the eps -> x0 conversion is a linear combination of at most four fp32 tensors with
+ * step-wide scalar coefficients (:532-1036, :419-430): out = sum_i coef[i] * src[i].  src: host array of device
+ * pointers; coef: host array.  out may alias a source. */
+int mmd_lincomb(int n_terms, const float* const* src, const float* coef, int64_t numel, float* out, void* stream);
+/* Dynamic thresholding tail (:431-438): x0 = clamp(x0, -s[b], s[b]) / (s[b] / max_val), in place; s device [B]. */
+int mmd_dpm_threshold(float* x0, const float* s, int batch, int64_t per_sample, float max_val, void* stream);
+/* Adaptive step-size error (:1134-1138): out[b] = sum_i ((hi-lo) / max(atol, rtol*max(|lo|,|prev|)))^2, device double [B]. */
+int mmd_dpm_error_sq(const float* hi, const float* lo, const float* prev, int batch, int64_t per_sample, float atol,
+                     float rtol, double* out, void* stream);
+
 /* ---- operator-level entry points (used by the parity tests; same kernels the model plan launches) ---- */
 
 /* GroupNorm32 (+SiLU, +FiLM) on channels-last fp16: x [ns*rows, c1(+c2)] -> y.  nn.py:16-33. */

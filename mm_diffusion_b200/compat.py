@@ -1,9 +1,10 @@
 """Drop-in installation under the reference's module names.
 
 `install()` registers this package's modules in sys.modules as
-    mm_diffusion.multimodal_unet / multimodal_gaussian_diffusion / multimodal_respace / multimodal_script_util
+    mm_diffusion.multimodal_unet / multimodal_gaussian_diffusion / multimodal_respace / multimodal_script_util /
+    multimodal_dpm_solver_plus
 so the reference's unchanged scripts (py_scripts/multimodal_sample_sr.py, multimodal_train.py, ...) and its
-remaining modules (dist_util, logger, multimodal_dpm_solver_plus, ...) pick up the B200-native hot path.
+remaining modules (dist_util, logger, ...) pick up the B200-native hot path.
 The reference checkout must be importable (sys.path) for the modules this package does not replace; call
 install() before anything imports them.  See INTEGRATION.md.
 """
@@ -17,6 +18,7 @@ _MAP = {
     "mm_diffusion.multimodal_gaussian_diffusion": "mm_diffusion_b200.gaussian_diffusion",
     "mm_diffusion.multimodal_respace": "mm_diffusion_b200.respace",
     "mm_diffusion.multimodal_script_util": "mm_diffusion_b200.script_util",
+    "mm_diffusion.multimodal_dpm_solver_plus": "mm_diffusion_b200.dpm_solver",
 }
 
 

@@ -516,4 +516,45 @@ int mmd_q_sample(const float* x_start, const float* noise, const float* coef, in
     return MMD_OK;
 }
 
+int mmd_lincomb(int n_terms, const float* const* src, const float* coef, int64_t numel, float* out, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (n_terms < 1 || n_terms > 4 || !src || !coef || !out) return fail(MMD_EINVAL, "lincomb: 1..4 terms, non-null arguments");
+    LinCombArgs a{};
+    a.n = n_terms;
+    bool aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    for (int i = 0; i < n_terms; ++i) {
+        if (!src[i]) return fail(MMD_EINVAL, "lincomb: null source %d", i);
+        a.src[i] = src[i];
+        a.coef[i] = coef[i];
+        aligned = aligned && (reinterpret_cast<uintptr_t>(src[i]) & 15) == 0;
+    }
+    const long long n4 = aligned ? numel / 4 : 0;
+    const long long work = std::max<long long>(n4, numel - n4 * 4);
+    const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>((work + 255) / 256, 8LL * num_sms())));
+    lincomb_kernel<<<grid, 256, 0, st>>>(a, n4, numel, out);
+    MMD_CUDA_OK(cudaGetLastError());
+    return MMD_OK;
+}
+
+int mmd_dpm_threshold(float* x0, const float* s, int batch, int64_t per_sample, float max_val, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!x0 || !s || batch <= 0 || per_sample <= 0) return fail(MMD_EINVAL, "dpm_threshold: bad arguments");
+    const long long total = static_cast<long long>(batch) * per_sample;
+    const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 8LL * num_sms()));
+    dpm_threshold_kernel<<<grid, 256, 0, st>>>(x0, s, per_sample, total, max_val);
+    MMD_CUDA_OK(cudaGetLastError());
+    return MMD_OK;
+}
+
+int mmd_dpm_error_sq(const float* hi, const float* lo, const float* prev, int batch, int64_t per_sample, float atol,
+                     float rtol, double* out, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!hi || !lo || !prev || !out || batch <= 0 || per_sample <= 0) return fail(MMD_EINVAL, "dpm_error_sq: bad arguments");
+    MMD_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(double) * batch, st));
+    const int gx = static_cast<int>(std::max<long long>(1, std::min<long long>((per_sample + 255) / 256, 2LL * num_sms())));
+    dpm_error_kernel<<<dim3(gx, batch), 256, 0, st>>>(hi, lo, prev, per_sample, atol, rtol, out);
+    MMD_CUDA_OK(cudaGetLastError());
+    return MMD_OK;
+}
+
 }  // extern "C"
