@@ -122,6 +122,29 @@ def build_b200(device, seed=0):
     return model, diffusion
 
 
+# step family (model.cu StepInfo.kind) -> kernel function that executes it
+KERNEL_OF = {"conv3x3_spatial": "conv_gemm_kernel", "conv1x1_qkv": "conv_gemm_kernel", "conv1x1_out": "conv_gemm_kernel",
+             "conv1x1_proj": "conv_gemm_kernel", "conv_temporal": "conv_gemm_kernel", "conv_audio_k3": "conv_gemm_kernel",
+             "conv_head": "conv_gemm_kernel", "conv_stem": "conv_gemm_kernel",
+             "cross_attention": "attention64_kernel", "self_attention": "attention64_kernel",
+             "group_norm": "gn_apply_kernel+gn_stats_kernel", "temporal_attention": "temporal_attn_kernel",
+             "resample": "resample_kernel", "im2col": "im2col_kernel", "time_embed": "time_embed_kernel"}
+
+
+def ncu_traffic(kernel, batch):
+    """Measured DRAM bytes per launch of `kernel` (ncu dram__bytes_read.sum + dram__bytes_write.sum averaged over the
+    launches of one forward at this batch), from the committed summary of the capture; None if not captured."""
+    path = os.path.join(ROOT, "profiles", "r01_dram_traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)
+        if t.get("batch") != batch:
+            return None
+        return t["kernels"][kernel]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def family_summary(steps):
     fam = {}
     for s in steps:
@@ -224,22 +247,42 @@ def run_b200(args):
         steps = model.profile(B, reps=args.profile_reps)
         fam = family_summary(steps)
         fwd_ms = sum(s["ms"] for s in steps)
-        dom = max(fam.items(), key=lambda kv: kv[1]["ms"])
-        dname, d = dom
+        # group the step families by the kernel function that runs them; the roofline is the dominant kernel's
+        kern = {}
+        for k, v in fam.items():
+            kk = kern.setdefault(KERNEL_OF.get(k, k), {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
+            for f in ("ms", "flops", "bytes", "launches"):
+                kk[f] += v[f]
+        dname, d = max(((k, v) for k, v in kern.items() if v["launches"] > 0), key=lambda kv: kv[1]["ms"])
         tflops = d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0
         gbs = d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["ms"] > 0 else 0.0
-        tensor_bound = (d["flops"] / max(d["bytes"], 1.0)) > (peaks["bf16_tflops_sustained"] * 1e12) / (peaks["hbm_gbs"] * 1e9)
+        ridge = (peaks["bf16_tflops_sustained"] * 1e12) / (peaks["hbm_gbs"] * 1e9)
+        tensor_bound = (d["flops"] / max(d["bytes"], 1.0)) > ridge
         if tensor_bound:
             roof = {"bound": "tensor", "achieved": round(tflops, 2), "peak": peaks["bf16_tflops_sustained"],
                     "unit": "TFLOP/s", "frac": round(tflops / peaks["bf16_tflops_sustained"], 4)}
         else:
             roof = {"bound": "hbm", "achieved": round(gbs, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": round(gbs / peaks["hbm_gbs"], 4)}
+        traffic = ncu_traffic(dname, B)
         roof.update({"kernel": dname, "launches_per_step": d["launches"], "share_of_step": round(d["ms"] / fwd_ms, 4),
-                     "peak_source": peaks["source"] + (" (sustained cuBLAS fp16-class GEMM)" if tensor_bound else " (copy)"),
-                     "traffic": None,
-                     "how": "algorithmic FLOPs/bytes of the family's launches / their summed CUDA-event durations, "
-                            f"mean of {args.profile_reps} un-graphed passes after the timed region"})
+                     "algorithmic_gflop_per_launch": round(d["flops"] / d["launches"] / 1e9, 3),
+                     "algorithmic_mb_per_launch": round(d["bytes"] / d["launches"] / 1e6, 3),
+                     "us_per_launch": round(d["ms"] * 1e3 / d["launches"], 2),
+                     "intensity_flop_per_byte": round(d["flops"] / max(d["bytes"], 1.0), 1), "ridge_flop_per_byte": round(ridge, 1),
+                     "hbm_gbs": round(gbs, 1), "hbm_frac": round(gbs / peaks["hbm_gbs"], 4),
+                     "peak_source": peaks["source"] + (" (sustained cuBLAS bf16 GEMM; fp16 runs at the same rate)"
+                                                       if tensor_bound else " (copy)"),
+                     "traffic": traffic,
+                     "traffic_note": "mean dram__bytes_read+write per launch of this kernel over one forward, ncu capture "
+                                     "summarised in profiles/r01_dram_traffic.json" if traffic is not None else None,
+                     "how": "sum of the algorithmic FLOPs/bytes of this kernel's launches in one forward / sum of their "
+                            f"CUDA-event durations on the launch stream, mean of {args.profile_reps} un-graphed passes "
+                            "after the timed region"})
+        kernels = {k: {"ms": round(v["ms"], 4), "launches": v["launches"],
+                       "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2) if v["ms"] > 0 else 0.0,
+                       "gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else 0.0}
+                   for k, v in sorted(kern.items(), key=lambda kv: -kv[1]["ms"]) if v["launches"] > 0}
         families = {k: {"ms": round(v["ms"], 4), "launches": v["launches"],
                         "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2) if v["ms"] > 0 else 0.0,
                         "gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else 0.0}
@@ -264,7 +307,7 @@ def run_b200(args):
             "launches_per_step": launches_fwd + 3,
             "model_tflops": round(step_flops * K / (ms_total * 1e-3) / 1e12, 2),
             "forward_ms_ungraphed": round(fwd_ms, 3),
-            "roofline": roof, "families": families, "clocks": clk, "finite": finite,
+            "roofline": roof, "kernels": kernels, "families": families, "clocks": clk, "finite": finite,
         }
         if world == 1 and not args.no_cpu_baseline:
             result["cpu_baseline"] = cpu_baseline(max_seconds=40.0)

@@ -9,6 +9,13 @@
 // U-Net skip connections (multimodal_unet.py:1093-1094) without materialising it and
 // (b) residual / skip-conv accumulation (multimodal_unet.py:482-483) as extra K
 // segments (identity weights for an identity skip).
+//
+// Shared-memory budget (227 KB): the mainloop is bound by how many operand bytes are in flight against the
+// ~0.7 us L2 latency, not by the tensor pipe, so everything that is not pipeline stages is
+// kept small.  Two epilogue shapes (template parameter OC = staged output columns per chunk, double buffered):
+//   OC=64  (K-heavy GEMMs, the mainloop hides the epilogue): 2 x 16 KB staging -> BN=128: 6 x 32 KB stages, BN=256: 4 x 48 KB
+//   OC=128 (short-K GEMMs, store/epilogue bound: fewer barrier rounds): 2 x 32 KB -> BN=128: 5 stages, BN=256: 3 stages
+//   BN=64: 8 x 24 KB, BN=16 (heads, no staging): 8 x 18 KB
 #pragma once
 #include "common.cuh"
 
@@ -18,8 +25,7 @@ constexpr int GEMM_BM = 128;       // tokens per tile (UMMA M)
 constexpr int GEMM_BK = 64;        // channels per k-iteration (one 128-byte swizzle atom)
 constexpr int GEMM_MAX_SRC = 4;
 constexpr int GEMM_MAX_TAPS = 27;
-constexpr int GEMM_THREADS = 320;  // warp0 TMA, warp1 MMA, warps2-5 epilogue, warps6-9 A-operand transform
-constexpr int GEMM_XF_MAXC = 512;  // widest source the fused GroupNorm apply supports
+constexpr int GEMM_THREADS = 192;  // warp0 TMA, warp1 MMA, warps2-5 epilogue
 
 struct alignas(64) GemmParams {
     CUtensorMap a_map[GEMM_MAX_SRC];  // activation sources, rank `rank`, box (64, box[0..3])
@@ -32,7 +38,7 @@ struct alignas(64) GemmParams {
     int ntile[4];                     // tiles along coordinates 1..4
     int n_taps;
     int tap[GEMM_MAX_TAPS][3];        // coordinate deltas on coordinates 1..3
-    int m_tiles, n_tiles;
+    int m_tiles, n_tiles;             // 128-token tiles, BN-column tiles
     const float* bias;                // [n_tiles*BN] fp32 (padded)
     // out_mode 1: fp32 strided scatter (network heads write NCHW fp32 directly)
     int out_mode;
@@ -44,44 +50,34 @@ struct alignas(64) GemmParams {
     // fused GroupNorm statistics of the (fp16-rounded) output: per (domain, group) sum / sum of squares
     // accumulated into double slots [domain][32][2]; domain = base(tile) + row / stats_rows
     double* stats;          // null = off
-    int stats_cpg;          // channels per group = N / 32
+    int stats_cpg;          // channels per group = N / 32 (multiple of 4)
     int stats_rows;         // rows of one domain inside a tile (64 or 128)
     int stats_mul[4];       // domain base = sum_i origin[i+1] * stats_mul[i] / stats_div
     int stats_div;
     int stats_valid_coord;  // >= 0: rows >= dims[c] - origin[c+1] of the tile are padding (ragged last tile)
-    // fused GroupNorm apply on the A operand of source xf_src (pointwise GEMMs only):
-    //   a <- act(gn(a) * (1 + scale) + shift), done in shared memory between the TMA landing and the MMA
-    //   (reference: nn.py:22-33 + multimodal_unet.py:459-470 out_layers / :284,664 attention norms)
-    const double* xf_sums;  // statistics slots [domains * xf_nsub][32][2]; null = off
-    const float* xf_gamma;
-    const float* xf_beta;
-    const float* xf_film;   // [batch][xf_film_ld]: scale at [0,C), shift at [C,2C); may be null
-    int xf_film_ld;
-    int xf_dom_per_batch;   // FiLM row = domain / xf_dom_per_batch
-    int xf_src, xf_c, xf_nsub, xf_silu;
-    double xf_inv_n;        // 1 / (rows * channels-per-group) of one statistics domain
-    int xf_rows;            // rows of one domain inside a tile (64 or 128)
-    int xf_mul[4];          // domain base = sum_i origin[i+1] * xf_mul[i] / xf_div
-    int xf_div;
 };
 
-template <int BN>
+template <int BN, int OC>
 struct GemmSmem {
     static constexpr int A_BYTES = GEMM_BM * 128;
     static constexpr int B_BYTES = BN * 128;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    // epilogue staging: two buffers of HALF columns each, rotated per half-tile, so the TMA store of one half
-    // drains while the next half is being converted (a single buffer serialises store latency with the epilogue)
-    static constexpr int HALF = (BN >= 128) ? 128 : BN;          // columns per staging buffer / TMA store group
-    static constexpr int NHALF = (BN >= 64) ? BN / HALF : 0;
-    static constexpr int OUT_BUF = (BN >= 64) ? (HALF / 64) * GEMM_BM * 128 : 0;
-    static constexpr int OUT_BYTES = 2 * OUT_BUF;
-    static constexpr int STAGES = (BN >= 256) ? 3 : ((BN >= 128) ? 4 : 6);
-    // barriers | GroupNorm partials [2 halves][4 bands][32 quads][2] | transform coefficients [2 domains][2][512] + group stats
-    static constexpr int XF_OFF = 256 + 2 * 4 * 32 * 2 * 4;
-    static constexpr int BAR_BYTES = XF_OFF + 2 * 2 * GEMM_XF_MAXC * 4 + 512;
-    static constexpr int TOTAL = STAGES * STAGE_BYTES + OUT_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
-    static_assert(TOTAL <= 232448, "exceeds the 227 KB dynamic shared memory limit");
+    // epilogue staging: two buffers of OC columns (OC/64 swizzled 16 KB units each), rotated per chunk, so the TMA
+    // store of one chunk drains while the next is converted
+    static constexpr int NCHUNK = (BN >= 64) ? BN / OC : 0;
+    static constexpr int UNITS = OC / 64;
+    static constexpr int OUT_BUF = UNITS * GEMM_BM * 128;
+    static constexpr int OUT_BYTES = (BN >= 64) ? 2 * OUT_BUF : 0;
+    // barriers (256 B) | GroupNorm partials [BN/64 units][4 bands][16 quads][2] floats
+    static constexpr int GN_BYTES = (BN >= 64) ? (BN / 64) * 4 * 16 * 2 * 4 : 0;
+    static constexpr int BAR_BYTES = 256 + GN_BYTES;
+    static constexpr int LIMIT = 232448;   // 227 KB
+    static constexpr int FIT = (LIMIT - OUT_BYTES - BAR_BYTES) / STAGE_BYTES;
+    static constexpr int STAGES = FIT > 8 ? 8 : FIT;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + OUT_BYTES + BAR_BYTES;   // base is 1024-aligned (checked)
+    static_assert(BN < 64 || (OC % 64 == 0 && BN % OC == 0), "staging chunk");
+    static_assert(STAGES >= 3 && TOTAL <= LIMIT, "shared memory budget");
+    static_assert(2 * STAGES + 4 <= 30, "barrier block");
     static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : ((2 * BN <= 64) ? 64 : ((2 * BN <= 128) ? 128 : ((2 * BN <= 256) ? 256 : 512)));
 };
 
@@ -96,11 +92,10 @@ MMD_DEVINL void gemm_tile_origin(const GemmParams& p, int m_idx, int* c /*[5]*/)
     c[0] = 0;
 }
 
-template <int BN>
+template <int BN, int OC>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid_constant__ GemmParams p) {
-    using S = GemmSmem<BN>;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    using S = GemmSmem<BN, OC>;
+    extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* stage_base = smem;
     uint8_t* out_stage = smem + S::STAGES * S::STAGE_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + S::OUT_BYTES);
@@ -108,10 +103,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
     uint64_t* empty_bar = bars + S::STAGES;
     uint64_t* tfull_bar = bars + 2 * S::STAGES;
     uint64_t* tempty_bar = bars + 2 * S::STAGES + 2;
-    uint64_t* xf_bar = bars + 2 * S::STAGES + 4;   // [STAGES]: A tile transformed, MMA may read it
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S::STAGES + 4);
-    float* xf_coef = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + S::XF_OFF);   // [dl][a|b][c]
-    float* xf_gstat = xf_coef + 2 * 2 * GEMM_XF_MAXC;                                          // [dl][32][mean|rstd]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::STAGES + 4);
     float* gn_part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
 
     const int warp = threadIdx.x >> 5;
@@ -123,13 +115,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
 
     pdl_trigger();   // the next kernel of the stream may start its own prologue from here on
     if (threadIdx.x == 0) {
+        if ((smem_u32(smem) & 1023u) != 0) {   // the 128-byte swizzle atoms need a 1024-byte aligned base
+            printf("conv_gemm_kernel: dynamic shared memory base not 1024-byte aligned\n");
+            __trap();
+        }
         for (int s = 0; s < p.n_src; ++s) tma_prefetch_desc(&p.a_map[s]);
         tma_prefetch_desc(&p.b_map);
         if (p.out_mode == 0) tma_prefetch_desc(&p.o_map);
         for (int i = 0; i < S::STAGES; ++i) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
-            mbar_init(&xf_bar[i], 4);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
@@ -178,11 +173,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                         for (int ch = 0; ch < p.src_chunks[s]; ++ch, ++kb, ++gk) {
                             mbar_wait(&empty_bar[stage], phase ^ 1);
                             uint8_t* a_dst = stage_base + stage * S::STAGE_BYTES;
-                            uint8_t* b_dst = a_dst + S::A_BYTES;
                             if (gk >= pre) mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
                             c[0] = ch * GEMM_BK;
                             tma_load_nd(p.rank, a_dst, &p.a_map[s], &full_bar[stage], c);
-                            if (gk >= pre) tma_load_2d(b_dst, &p.b_map, &full_bar[stage], kb * GEMM_BK, n_idx * BN);
+                            if (gk >= pre) tma_load_2d(a_dst + S::A_BYTES, &p.b_map, &full_bar[stage], kb * GEMM_BK, n_idx * BN);
                             if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
                         }
                     }
@@ -203,7 +197,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(p.xf_sums != nullptr ? &xf_bar[stage] : &full_bar[stage], phase);
+                    mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(stage_base + stage * S::STAGE_BYTES);
                     // one descriptor per operand and k-iteration; the 16-element k-steps only bump the 16-byte-unit
@@ -219,106 +213,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                 umma_commit(&tfull_bar[acc]);
             }
         }
-    } else if (warp >= 6) {
-        // ================= A-operand transform (4 warps): fused GroupNorm apply =================
-        if (p.xf_sums != nullptr) {
-            const int tt = threadIdx.x - 192;           // 0..127
-            const int oct = tt & 7, rg = tt >> 3;       // 16-byte column unit, group of 8 rows
-            const int C = p.xf_c;
-            const int cpg = C / 32;
-            const int ndom = (p.xf_rows < GEMM_BM) ? 2 : 1;
-            const int dl = (rg * 8) / p.xf_rows;
-            int stage = 0;
-            uint32_t phase = 0;
-            int cached_dom = -1;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int m_idx = tile / p.n_tiles;
-                int org[5];
-                gemm_tile_origin(p, m_idx, org);
-                const int dom_base = (org[1] * p.xf_mul[0] + org[2] * p.xf_mul[1] + org[3] * p.xf_mul[2] +
-                                      org[4] * p.xf_mul[3]) / p.xf_div;
-                if (dom_base != cached_dom) {   // (re)build the per-channel affine table of this tile's domain(s)
-                    named_bar_sync(2, 128);
-                    if (tt < 32 * ndom) {
-                        const int d = tt >> 5, g = tt & 31;
-                        double su = 0.0, sq = 0.0;
-                        for (int k = 0; k < p.xf_nsub; ++k) {
-                            const double* sl = p.xf_sums + (static_cast<size_t>(dom_base + d) * p.xf_nsub + k) * 64;
-                            su += sl[2 * g];
-                            sq += sl[2 * g + 1];
-                        }
-                        const double mean = su * p.xf_inv_n;
-                        double var = sq * p.xf_inv_n - mean * mean;
-                        if (var < 0) var = 0;
-                        xf_gstat[(d * 32 + g) * 2] = static_cast<float>(mean);
-                        xf_gstat[(d * 32 + g) * 2 + 1] = rsqrtf(static_cast<float>(var) + 1e-5f);
-                    }
-                    named_bar_sync(2, 128);
-                    for (int i = tt; i < ndom * C; i += 128) {
-                        const int d = i / C, c = i - d * C;
-                        const int g = c / cpg;
-                        float a = xf_gstat[(d * 32 + g) * 2 + 1] * __ldg(p.xf_gamma + c);
-                        float b = __ldg(p.xf_beta + c) - xf_gstat[(d * 32 + g) * 2] * a;
-                        if (p.xf_film != nullptr) {
-                            const float* fb = p.xf_film + static_cast<size_t>((dom_base + d) / p.xf_dom_per_batch) * p.xf_film_ld;
-                            const float sc = 1.f + __ldg(fb + c);
-                            a *= sc;
-                            b = b * sc + __ldg(fb + C + c);
-                        }
-                        xf_coef[(d * 2 + 0) * GEMM_XF_MAXC + c] = a;
-                        xf_coef[(d * 2 + 1) * GEMM_XF_MAXC + c] = b;
-                    }
-                    named_bar_sync(2, 128);
-                    cached_dom = dom_base;
-                }
-                for (int t = 0; t < p.n_taps; ++t) {
-                    for (int sidx = 0; sidx < p.n_src; ++sidx) {
-                        for (int ch = 0; ch < p.src_chunks[sidx]; ++ch) {
-                            mbar_wait(&full_bar[stage], phase);
-                            if (sidx == p.xf_src) {
-                                uint8_t* a_tile = stage_base + stage * S::STAGE_BYTES;
-                                const float* ca = xf_coef + (dl * 2 + 0) * GEMM_XF_MAXC + ch * GEMM_BK + oct * 8;
-                                const float* cb = xf_coef + (dl * 2 + 1) * GEMM_XF_MAXC + ch * GEMM_BK + oct * 8;
-                                const float4 a0 = *reinterpret_cast<const float4*>(ca), a1 = *reinterpret_cast<const float4*>(ca + 4);
-                                const float4 b0 = *reinterpret_cast<const float4*>(cb), b1 = *reinterpret_cast<const float4*>(cb + 4);
-                                const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-                                const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    uint4* ptr = reinterpret_cast<uint4*>(a_tile + sw128_off(rg * 8 + j, oct));
-                                    uint4 raw = *ptr;
-                                    __half2* h = reinterpret_cast<__half2*>(&raw);
-#pragma unroll
-                                    for (int k = 0; k < 4; ++k) {
-                                        const float2 f = __half22float2(h[k]);
-                                        float u0 = fmaf(f.x, av[2 * k], bv[2 * k]);
-                                        float u1 = fmaf(f.y, av[2 * k + 1], bv[2 * k + 1]);
-                                        if (p.xf_silu) {
-                                            float t0, t1;
-                                            asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(0.5f * u0));
-                                            asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(0.5f * u1));
-                                            u0 = 0.5f * u0 * (1.0f + t0);
-                                            u1 = 0.5f * u1 * (1.0f + t1);
-                                        }
-                                        h[k] = __floats2half2_rn(u0, u1);
-                                    }
-                                    *ptr = raw;
-                                }
-                                fence_proxy_async_smem();
-                            }
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&xf_bar[stage]);
-                            if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
-                        }
-                    }
-                }
-            }
-        }
     } else {
         // ================= epilogue (4 warps, thread = accumulator row) =================
         const int quad = warp & 3;
         const int row = quad * 32 + lane;
-        const bool leader = (threadIdx.x == 64);
+        const int et = threadIdx.x - 64;   // 0..127
+        const bool leader = (et == 0);
         int it = 0;
         uint32_t obuf_sel = 0;   // staging buffer rotation (leader's bulk-group order matches it)
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -334,43 +234,42 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
             const float* bias = p.bias + n_idx * BN;
 
             if constexpr (BN >= 64) {
-                constexpr int HALF = S::HALF;
                 int valid_rows = GEMM_BM;
                 if (p.stats != nullptr && p.stats_valid_coord >= 0)
                     valid_rows = min(GEMM_BM, p.dims[p.stats_valid_coord] - org[p.stats_valid_coord + 1]);
 #pragma unroll 1
-                for (int hf = 0; hf < S::NHALF; ++hf) {
+                for (int cc = 0; cc < S::NCHUNK; ++cc) {
                     uint8_t* obuf = out_stage + (obuf_sel & 1) * S::OUT_BUF;
                     ++obuf_sel;
-                    if (leader) tma_store_wait_read1();  // the store issued two halves ago has drained this buffer
+                    if (leader) tma_store_wait_read1();  // the store issued two chunks ago has drained this buffer
                     named_bar_sync(1, 128);
                     // accumulator -> fp16 staging, 32 columns at a time with the next TMEM load already in flight
                     uint32_t va[32], vb[32];
-                    tmem_ld32(t_addr + hf * HALF, va);
+                    tmem_ld32(t_addr + cc * OC, va);
 #pragma unroll
-                    for (int cc = 0; cc < HALF / 32; ++cc) {
-                        uint32_t* v = (cc & 1) ? vb : va;
+                    for (int l = 0; l < OC / 32; ++l) {
+                        uint32_t* v = (l & 1) ? vb : va;
                         tmem_ld_wait();
-                        if (cc + 1 < HALF / 32) tmem_ld32(t_addr + hf * HALF + (cc + 1) * 32, (cc & 1) ? va : vb);
-                        uint8_t* chunk = obuf + (cc >> 1) * (GEMM_BM * 128);
-                        const float* bcol = bias + hf * HALF + cc * 32;
+                        if (l + 1 < OC / 32) tmem_ld32(t_addr + cc * OC + (l + 1) * 32, (l & 1) ? va : vb);
+                        uint8_t* unit_base = obuf + (l >> 1) * (GEMM_BM * 128);
+                        const float* bcol = bias + cc * OC + l * 32;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bcol + j * 8));
-                            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bcol + j * 8 + 4));
-                            __half2 h0 = __floats2half2_rn(__uint_as_float(v[j * 8 + 0]) + b0.x, __uint_as_float(v[j * 8 + 1]) + b0.y);
-                            __half2 h1 = __floats2half2_rn(__uint_as_float(v[j * 8 + 2]) + b0.z, __uint_as_float(v[j * 8 + 3]) + b0.w);
-                            __half2 h2 = __floats2half2_rn(__uint_as_float(v[j * 8 + 4]) + b1.x, __uint_as_float(v[j * 8 + 5]) + b1.y);
-                            __half2 h3 = __floats2half2_rn(__uint_as_float(v[j * 8 + 6]) + b1.z, __uint_as_float(v[j * 8 + 7]) + b1.w);
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bcol + q * 8));
+                            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bcol + q * 8 + 4));
+                            __half2 h0 = __floats2half2_rn(__uint_as_float(v[q * 8 + 0]) + b0.x, __uint_as_float(v[q * 8 + 1]) + b0.y);
+                            __half2 h1 = __floats2half2_rn(__uint_as_float(v[q * 8 + 2]) + b0.z, __uint_as_float(v[q * 8 + 3]) + b0.w);
+                            __half2 h2 = __floats2half2_rn(__uint_as_float(v[q * 8 + 4]) + b1.x, __uint_as_float(v[q * 8 + 5]) + b1.y);
+                            __half2 h3 = __floats2half2_rn(__uint_as_float(v[q * 8 + 6]) + b1.z, __uint_as_float(v[q * 8 + 7]) + b1.w);
                             uint4 pk;
                             pk.x = *reinterpret_cast<uint32_t*>(&h0);
                             pk.y = *reinterpret_cast<uint32_t*>(&h1);
                             pk.z = *reinterpret_cast<uint32_t*>(&h2);
                             pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                            *reinterpret_cast<uint4*>(chunk + sw128_off(row, (cc & 1) * 4 + j)) = pk;
+                            *reinterpret_cast<uint4*>(unit_base + sw128_off(row, (l & 1) * 4 + q)) = pk;
                         }
                     }
-                    if (hf == S::NHALF - 1) {   // all accumulator columns have been read: hand the TMEM stage back
+                    if (cc == S::NCHUNK - 1) {   // all accumulator columns have been read: hand the TMEM stage back
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -380,27 +279,27 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                     if (leader) {
                         int c[5] = {0, org[1], org[2], org[3], org[4]};
 #pragma unroll
-                        for (int ch = 0; ch < HALF / 64; ++ch) {
-                            c[0] = n_idx * BN + hf * HALF + ch * 64;
-                            tma_store_nd(p.rank, &p.o_map, obuf + ch * (GEMM_BM * 128), c);
+                        for (int u = 0; u < S::UNITS; ++u) {
+                            c[0] = n_idx * BN + cc * OC + u * 64;
+                            tma_store_nd(p.rank, &p.o_map, obuf + u * (GEMM_BM * 128), c);
                         }
                         tma_store_commit();
                     }
                     if (p.stats != nullptr) {
-                        // Column sums of the staged fp16 half-tile without atomics: lane = 4-column quad (8 bytes of
-                        // a row; a warp reads whole 256-byte rows, conflict-free), warp = 32-row band.  The per-(band,
-                        // quad) partials are folded into groups by the write-out pass below.
-                        if constexpr (HALF == 128) {
-                            const int et = threadIdx.x - 64;
-                            const int band = et >> 5, quad = et & 31;
+                        // Column sums of the staged fp16 chunk without atomics, one 64-column unit at a time: lane & 15 =
+                        // 4-column quad (8 bytes of a 128-byte row), the two half-warps take 16 rows each of the warp's
+                        // 32-row band; per (band, quad) partials are folded into groups by the write-out pass below.
+                        const int band = et >> 5, quad4 = lane & 15, half = lane >> 4;
+                        const int unit = quad4 >> 1, sub = (quad4 & 1) * 8;
+#pragma unroll 1
+                        for (int u = 0; u < S::UNITS; ++u) {
+                            const uint8_t* ub = obuf + u * (GEMM_BM * 128);
                             float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
-                            const uint8_t* chunk = obuf + (quad >> 4) * (GEMM_BM * 128);
-                            const int unit = (quad & 15) >> 1, sub = (quad & 1) * 8;
 #pragma unroll 8
-                            for (int rr = 0; rr < 32; ++rr) {
-                                const int r = band * 32 + rr;
+                            for (int rr = 0; rr < 16; ++rr) {
+                                const int r = band * 32 + half * 16 + rr;
                                 if (r < valid_rows) {
-                                    const uint2 raw = *reinterpret_cast<const uint2*>(chunk + sw128_off(r, unit) + sub);
+                                    const uint2 raw = *reinterpret_cast<const uint2*>(ub + sw128_off(r, unit) + sub);
                                     const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
                                     const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
                                     s0 += a.x; q0 = fmaf(a.x, a.x, q0);
@@ -409,46 +308,48 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                                     s3 += b.y; q3 = fmaf(b.y, b.y, q3);
                                 }
                             }
-                            // gn_part[hf][band][quad][2]
-                            float* part = gn_part + ((hf * 4 + band) * 32 + quad) * 2;
-                            part[0] = (s0 + s1) + (s2 + s3);
-                            part[1] = (q0 + q1) + (q2 + q3);
+                            float su = (s0 + s1) + (s2 + s3), sq = (q0 + q1) + (q2 + q3);
+                            su += __shfl_xor_sync(0xffffffffu, su, 16);
+                            sq += __shfl_xor_sync(0xffffffffu, sq, 16);
+                            if (half == 0) {   // gn_part[64-column unit of the tile][band][quad][2]
+                                float* part = gn_part + (((cc * S::UNITS + u) * 4 + band) * 16 + quad4) * 2;
+                                part[0] = su;
+                                part[1] = sq;
+                            }
                         }
                     }
                 }
                 if (p.stats != nullptr) {
-                    if constexpr (HALF == 128) {
-                        named_bar_sync(1, 128);
-                        // thread = (domain-in-tile, local group, statistic): fold bands x quads of that group
-                        const int et = threadIdx.x - 64;
-                        const int cpg = p.stats_cpg;                 // multiple of 4
-                        const int qpg = cpg >> 2;                    // quads per group
-                        const int ndom = (p.stats_rows < GEMM_BM) ? 2 : 1;
-                        const int bands_per_dom = 4 / ndom;
-                        const int col_base = n_idx * BN;
-                        const int g_first = col_base / cpg;
-                        const int groups_tile = (col_base + BN - 1) / cpg - g_first + 1;   // groups intersecting this tile
-                        const int dom_base = (org[1] * p.stats_mul[0] + org[2] * p.stats_mul[1] + org[3] * p.stats_mul[2] +
-                                              org[4] * p.stats_mul[3]) / p.stats_div;
-                        for (int item = et; item < ndom * groups_tile * 2; item += 128) {
-                            const int st = item & 1;
-                            const int gl = (item >> 1) % groups_tile;
-                            const int dl = (item >> 1) / groups_tile;
-                            const int g = g_first + gl;
-                            if (g >= 32) continue;
-                            // quads of group g inside this tile: global quad index = column / 4
-                            const int q_lo = max(g * qpg, col_base >> 2), q_hi = min((g + 1) * qpg, (col_base + BN) >> 2);
-                            float acc = 0.f;
-                            for (int q = q_lo; q < q_hi; ++q) {
-                                const int ql = q - (col_base >> 2);           // 0 .. BN/4-1
-                                const int hfq = ql >> 5, quad = ql & 31;
-                                for (int b = 0; b < bands_per_dom; ++b)
-                                    acc += gn_part[((hfq * 4 + dl * bands_per_dom + b) * 32 + quad) * 2 + st];
-                            }
-                            if (q_hi > q_lo)
-                                atomicAdd(&p.stats[(static_cast<size_t>(dom_base + dl) * 32 + g) * 2 + st], static_cast<double>(acc));
+                    named_bar_sync(1, 128);
+                    // thread = (domain-in-tile, local group, statistic): fold bands x quads of that group
+                    const int cpg = p.stats_cpg;                 // multiple of 4
+                    const int qpg = cpg >> 2;                    // quads per group
+                    const int ndom = (p.stats_rows < GEMM_BM) ? 2 : 1;
+                    const int bands_per_dom = 4 / ndom;
+                    const int col_base = n_idx * BN;
+                    const int g_first = col_base / cpg;
+                    const int groups_tile = (col_base + BN - 1) / cpg - g_first + 1;   // groups intersecting this tile
+                    const int dom_base = (org[1] * p.stats_mul[0] + org[2] * p.stats_mul[1] + org[3] * p.stats_mul[2] +
+                                          org[4] * p.stats_mul[3]) / p.stats_div;
+                    for (int item = et; item < ndom * groups_tile * 2; item += 128) {
+                        const int st = item & 1;
+                        const int gl = (item >> 1) % groups_tile;
+                        const int dl = (item >> 1) / groups_tile;
+                        const int g = g_first + gl;
+                        if (g >= 32) continue;
+                        // quads of group g inside this tile: global quad index = column / 4
+                        const int q_lo = max(g * qpg, col_base >> 2), q_hi = min((g + 1) * qpg, (col_base + BN) >> 2);
+                        float a = 0.f;
+                        for (int q = q_lo; q < q_hi; ++q) {
+                            const int ql = q - (col_base >> 2);           // 0 .. BN/4-1
+                            const int uq = ql >> 4, qq = ql & 15;
+                            for (int b = 0; b < bands_per_dom; ++b)
+                                a += gn_part[((uq * 4 + dl * bands_per_dom + b) * 16 + qq) * 2 + st];
                         }
+                        if (q_hi > q_lo)
+                            atomicAdd(&p.stats[(static_cast<size_t>(dom_base + dl) * 32 + g) * 2 + st], static_cast<double>(a));
                     }
+                    // (the next tile's named barriers order these reads before gn_part is rewritten)
                 }
             } else {
                 // narrow-N head: fp32 scatter, row -> token coordinates via the box decomposition
@@ -483,6 +384,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
+        tc_fence_after();
         __syncwarp();
         tmem_dealloc(tmem_base, S::TMEM_COLS);
     }

@@ -113,15 +113,6 @@ struct GemmProblem {
     int stats_mul[4] = {0, 0, 0, 0};
     int stats_div = 1;
     int stats_valid_coord = -1;
-    // fused GroupNorm apply on source xf_src (see GemmParams)
-    const double* xf_sums = nullptr;
-    const float* xf_gamma = nullptr;
-    const float* xf_beta = nullptr;
-    const float* xf_film = nullptr;
-    int xf_film_ld = 0, xf_dom_per_batch = 1, xf_src = 0, xf_nsub = 1, xf_silu = 0, xf_rows = 128;
-    double xf_inv_n = 0.0;
-    int xf_mul[4] = {0, 0, 0, 0};
-    int xf_div = 1;
     long long k_total() const {
         long long c = 0;
         for (int i = 0; i < n_src; ++i) c += src_c[i];
@@ -130,6 +121,7 @@ struct GemmProblem {
     int n_pad() const { return (n + bn - 1) / bn * bn; }
 };
 int pick_bn(int n);
+int pick_oc(int bn, long long num_kb);
 int build_gemm(const GemmProblem& pr, GemmParams* out);
 int launch_gemm(const GemmParams& p, int bn, cudaStream_t st);
 int gemm_init_attrs();

@@ -136,8 +136,6 @@ struct Walker {
     size_t w32_top = 0, wpk_top = 0, bpk_top = 0;
     int shift_slot = 0;
     int emb_row_top = 0;
-    bool fuse_apply = false;    // MMD_FUSED_APPLY=1: GroupNorm apply inside the consuming GEMM's A path (experimental:
-                                // the transform is repeated per N tile and currently costs more than the pass it removes)
     bool wide_n = true;         // MMD_NO_BN256=1 keeps 128-wide GEMM tiles
     bool fuse_stats = true;     // MMD_NO_FUSED_STATS=1 keeps every GroupNorm on the standalone statistics kernel
     float* emb_all = nullptr;   // [B][emb_rows]
@@ -146,8 +144,6 @@ struct Walker {
     Walker(MmdModel& mm, bool c) : m(mm), create(c) {
         const char* e = getenv("MMD_NO_FUSED_STATS");
         fuse_stats = !(e && e[0] == '1');
-        const char* fa = getenv("MMD_FUSED_APPLY");
-        fuse_apply = fa && fa[0] == '1';
         const char* w = getenv("MMD_NO_BN256");
         wide_n = !(w && w[0] == '1');
     }
@@ -273,35 +269,12 @@ struct Walker {
     }
 
     // ---------------- emitters
-    // GroupNorm apply fused into the GEMM's A path (source 0): statistics `st`, affine `gn`, optional FiLM + SiLU.
-    // kind 1: video tokens in 2-D geometry (per-sample domain, or per-frame with `per_frame`), 3: audio geometry (L,B)
-    struct XfReq { Stat st; GnP gn; const float* film = nullptr; int silu = 0; int kind = 1; bool per_frame = false; int hw = 0; };
-    // can the GroupNorm feeding a pointwise GEMM be applied inside that GEMM?
-    bool can_fuse_apply_video(int c, int hw, bool per_frame) const {
-        return fuse_apply && c <= GEMM_XF_MAXC && c % 64 == 0 && (per_frame ? hw >= 64 : static_cast<long long>(F()) * hw >= 128);
-    }
-    bool can_fuse_apply_audio(int c, int L) const { return fuse_apply && c <= GEMM_XF_MAXC && c % 64 == 0 && L >= 128; }
-    // statistics of x for a fused apply: reuse the producer's, or run the standalone reduction into fresh slots
-    Stat ensure_stats(const act_t* x, int C, int ns, int rows, const Stat* have, bool per_frame) {
-        if (fuse_stats && have && have->slots) {
-            if (!per_frame) return *have;
-            return Stat{have->slots, 1, have->rows / have->nsub};
-        }
-        Stat st{static_cast<double*>(stats.take(sizeof(double) * 64 * ns)), 1, rows};
-        if (emitting() && !bad()) {
-            GnSrc src{x, C, C, nullptr, 0, 0};
-            double* sums = st.slots;
-            push([=](cudaStream_t stx) -> int { return launch_gn_stats(src, ns, rows, sums, stx, false); }, "group_norm", 0.0,
-                 2.0 * ns * static_cast<double>(rows) * C, 1);
-        }
-        return st;
-    }
     // stat_kind: 0 none, 1 video tokens (2-D geometry, one domain per frame of `stat_hw` rows),
     //            2 video temporal geometry (P,F,B), 3 audio geometry (L,B)
     void emit_gemm(const char* tag, const ConvGeom& g, const std::vector<std::pair<const act_t*, int>>& srcs,
                    const std::vector<std::array<int, 3>>& taps, const PackedConv* pc, act_t* out, float* out_f32 = nullptr,
                    const long long* ostride = nullptr, long long ostride_c = 0, double* stat_slots = nullptr,
-                   int stat_kind = 0, int stat_hw = 0, const XfReq* xf = nullptr) {
+                   int stat_kind = 0, int stat_hw = 0) {
         if (!emitting() || bad() || !pc) return;
         GemmProblem pr;
         pr.g = g;
@@ -332,26 +305,6 @@ struct Walker {
             pr.stats = stat_slots; pr.stats_rows = g.box[0]; pr.stats_mul[1] = 1; pr.stats_mul[2] = F(); pr.stats_div = 1;
         } else if (stat_slots && stat_kind == 3) {
             pr.stats = stat_slots; pr.stats_rows = 128; pr.stats_mul[1] = 1; pr.stats_div = 1; pr.stats_valid_coord = 0;
-        }
-        if (xf) {
-            const int xc = srcs[0].second;
-            const int cpg = xc / 32;
-            pr.xf_sums = xf->st.slots;
-            pr.xf_gamma = pf(xf->gn.g);
-            pr.xf_beta = pf(xf->gn.b);
-            pr.xf_film = xf->film;
-            pr.xf_film_ld = m.emb_rows;
-            pr.xf_src = 0;
-            pr.xf_silu = xf->silu;
-            pr.xf_nsub = xf->st.nsub;
-            pr.xf_inv_n = 1.0 / (static_cast<double>(xf->st.rows) * cpg);
-            if (xf->kind == 1 && !xf->per_frame) {        // one domain per sample
-                pr.xf_rows = 128; pr.xf_mul[0] = 1; pr.xf_div = F() * xf->hw; pr.xf_dom_per_batch = 1;
-            } else if (xf->kind == 1) {                   // one domain per frame
-                pr.xf_rows = std::min(xf->hw, 128); pr.xf_mul[0] = 1; pr.xf_div = xf->hw; pr.xf_dom_per_batch = F();
-            } else {                                      // audio geometry (L, B): domain = sample coordinate
-                pr.xf_rows = 128; pr.xf_mul[1] = 1; pr.xf_div = 1; pr.xf_dom_per_batch = 1;
-            }
         }
         auto gp = std::make_shared<GemmParams>();
         int r = build_gemm(pr, gp.get());
@@ -436,18 +389,8 @@ struct Walker {
         act_t* out = alloc_p(tokens * C);
         cur = (kind == 2) ? 1 : 0;
         const size_t mark = S().top;
-        act_t* xn = nullptr;
-        XfReq xq;
-        bool use_xf = false;
-        if (kind == 0 && can_fuse_apply_video(C, vt->H * vt->W, true)) {
-            xq.st = ensure_stats(x, C, B * F(), vt->H * vt->W, in_st, true);
-            xq.gn = gn; xq.kind = 1; xq.per_frame = true; xq.hw = vt->H * vt->W;
-            use_xf = true;
-        } else if (kind == 2 && can_fuse_apply_audio(C, at->L)) {
-            xq.st = ensure_stats(x, C, B, at->L, in_st, false);
-            xq.gn = gn; xq.kind = 3;
-            use_xf = true;
-        } else if (kind == 0) {
+        act_t* xn;
+        if (kind == 0) {
             xn = emit_gn(x, C, nullptr, 0, B * F(), vt->H * vt->W, gn, nullptr, 1, 0, in_st, true);
         } else if (kind == 2) {
             xn = emit_gn(x, C, nullptr, 0, B, at->L, gn, nullptr, 1, 0, in_st, false);
@@ -464,8 +407,7 @@ struct Walker {
         act_t* qkvb = alloc_s(tokens * 3 * C);
         AT aview{nullptr, C, at ? at->L : 0};
         const ConvGeom gtok = at ? geom_audio(aview) : geom2(static_cast<long long>(tokens));
-        emit_gemm("conv1x1_qkv", gtok, {{use_xf ? x : xn, C}}, {{0, 0, 0}}, pq, qkvb, nullptr, nullptr, 0, nullptr, 0, 0,
-                  use_xf ? &xq : nullptr);
+        emit_gemm("conv1x1_qkv", gtok, {{xn, C}}, {{0, 0, 0}}, pq, qkvb);
         act_t* o = alloc_s(tokens * C);
         if (kind == 0) {
             const int hw = vt->H * vt->W;
@@ -587,22 +529,12 @@ struct Walker {
                     xs = xr;
                 }
                 const int hwo = vo.H * vo.W;
-                // GN2 * (1 + scale) + shift -> SiLU applied to h1 inside the out-conv GEMM's A path when possible
-                XfReq xq;
-                const bool use_xf = can_fuse_apply_video(cout, hwo, false);
-                const act_t* h2;
-                if (use_xf) {
-                    xq.st = ensure_stats(h1, cout, B, Fr * hwo, &h1st, false);
-                    xq.gn = vout_gn; xq.film = film; xq.silu = 1; xq.kind = 1; xq.hw = hwo;
-                    h2 = h1;
-                } else {
-                    h2 = emit_gn(h1, cout, nullptr, 0, B, Fr * hwo, vout_gn, film, 1, 1, &h1st, false);
-                }
+                act_t* h2 = emit_gn(h1, cout, nullptr, 0, B, Fr * hwo, vout_gn, film, 1, 1, &h1st, false);
                 std::vector<std::pair<const act_t*, int>> srcs = {{h2, cout}, {xs, v.C}};
                 if (v2) srcs.push_back({v2, vc2});
                 if (can_fuse_video(hwo, cout)) vo.st = Stat{stat_slots_video(), Fr, static_cast<long long>(Fr) * hwo};
                 emit_gemm("conv1x1_out", geom2(static_cast<long long>(B) * Fr * hwo), srcs, {{0, 0, 0}}, p_vo, vo.p,
-                          nullptr, nullptr, 0, vo.st.slots, 1, hwo, use_xf ? &xq : nullptr);
+                          nullptr, nullptr, 0, vo.st.slots, 1, hwo);
                 S().top = mark;
             }
             // ---------------- audio branch
@@ -636,21 +568,11 @@ struct Walker {
                     h1 = h1r;
                     xs = xr;
                 }
-                XfReq xq;
-                const bool use_xf = can_fuse_apply_audio(cout, ao.L);
-                const act_t* h2;
-                if (use_xf) {
-                    xq.st = ensure_stats(h1, cout, B, ao.L, &h1st, false);
-                    xq.gn = aout_gn; xq.film = film; xq.silu = 1; xq.kind = 3;
-                    h2 = h1;
-                } else {
-                    h2 = emit_gn(h1, cout, nullptr, 0, B, ao.L, aout_gn, film, 1, 1, &h1st, false);
-                }
+                act_t* h2 = emit_gn(h1, cout, nullptr, 0, B, ao.L, aout_gn, film, 1, 1, &h1st, false);
                 std::vector<std::pair<const act_t*, int>> srcs = {{h2, cout}, {xs, a.C}};
                 if (a2) srcs.push_back({a2, ac2});
                 if (can_fuse_audio(ao.L, cout)) ao.st = Stat{stat_slots_audio(), 1, ao.L};
-                emit_gemm("conv1x1_out", geom_audio(ao), srcs, {{0, 0, 0}}, p_ao, ao.p, nullptr, nullptr, 0, ao.st.slots, 3, 0,
-                          use_xf ? &xq : nullptr);
+                emit_gemm("conv1x1_out", geom_audio(ao), srcs, {{0, 0, 0}}, p_ao, ao.p, nullptr, nullptr, 0, ao.st.slots, 3, 0);
                 S().top = mark;
                 cur = 0;
             }
@@ -704,22 +626,14 @@ struct Walker {
         act_t* aout = alloc_p(at * C);
         const size_t mark_v = scratch.top, mark_a = scratch_a.top;
         cur = 0;
-        XfReq xv, xa;
-        const bool xf_v = can_fuse_apply_video(C, hw, false), xf_a = can_fuse_apply_audio(C, a.L);
-        const act_t* vnrm;
-        if (xf_v) { xv.st = ensure_stats(v.p, C, B, Fr * hw, &v.st, false); xv.gn = vn; xv.kind = 1; xv.hw = hw; vnrm = v.p; }
-        else vnrm = emit_gn(v.p, C, nullptr, 0, B, Fr * hw, vn, nullptr, 1, 0, &v.st, false);
+        act_t* vnrm = emit_gn(v.p, C, nullptr, 0, B, Fr * hw, vn, nullptr, 1, 0, &v.st, false);
         act_t* vqkv = alloc_s(vt * 3 * C);
-        emit_gemm("conv1x1_qkv", geom2(static_cast<long long>(vt)), {{vnrm, C}}, {{0, 0, 0}}, p_vq, vqkv, nullptr, nullptr, 0,
-                  nullptr, 0, 0, xf_v ? &xv : nullptr);
+        emit_gemm("conv1x1_qkv", geom2(static_cast<long long>(vt)), {{vnrm, C}}, {{0, 0, 0}}, p_vq, vqkv);
         act_t* ov = alloc_s(vt * C);
         cur = 1;
-        const act_t* anrm;
-        if (xf_a) { xa.st = ensure_stats(a.p, C, B, a.L, &a.st, false); xa.gn = an; xa.kind = 3; anrm = a.p; }
-        else anrm = emit_gn(a.p, C, nullptr, 0, B, a.L, an, nullptr, 1, 0, &a.st, false);
+        act_t* anrm = emit_gn(a.p, C, nullptr, 0, B, a.L, an, nullptr, 1, 0, &a.st, false);
         act_t* aqkv = alloc_s(at * 3 * C);
-        emit_gemm("conv1x1_qkv", geom_audio(a), {{anrm, C}}, {{0, 0, 0}}, p_aq, aqkv, nullptr, nullptr, 0, nullptr, 0, 0,
-                  xf_a ? &xa : nullptr);
+        emit_gemm("conv1x1_qkv", geom_audio(a), {{anrm, C}}, {{0, 0, 0}}, p_aq, aqkv);
         act_t* oa = alloc_s(at * C);
         const int* sdev = (shift && plan) ? plan->shifts_dev + slot : nullptr;
         // video queries attend audio keys/values and vice versa (multimodal_unet.py:530-559): each branch needs the

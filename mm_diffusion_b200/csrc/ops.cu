@@ -167,28 +167,34 @@ int build_gemm(const GemmProblem& pr, GemmParams* out) {
         p.stats_valid_coord = pr.stats_valid_coord;
         if (pr.stats_rows != 128 && pr.stats_rows != 64) return fail(MMD_EINVAL, "stats_rows %d", pr.stats_rows);
     }
-    if (pr.xf_sums) {
-        const int xc = pr.src_c[pr.xf_src];
-        if (pr.n_taps != 1 || xc > GEMM_XF_MAXC || xc % 64 != 0 || xc % 32 != 0 || (pr.xf_rows != 64 && pr.xf_rows != 128))
-            return fail(MMD_EINVAL, "fused GroupNorm apply: unsupported shape (taps %d, channels %d, rows %d)", pr.n_taps, xc, pr.xf_rows);
-        p.xf_sums = pr.xf_sums; p.xf_gamma = pr.xf_gamma; p.xf_beta = pr.xf_beta; p.xf_film = pr.xf_film;
-        p.xf_film_ld = pr.xf_film_ld; p.xf_dom_per_batch = pr.xf_dom_per_batch; p.xf_src = pr.xf_src; p.xf_c = xc;
-        p.xf_nsub = pr.xf_nsub; p.xf_silu = pr.xf_silu; p.xf_inv_n = pr.xf_inv_n; p.xf_rows = pr.xf_rows;
-        for (int i = 0; i < 4; ++i) p.xf_mul[i] = pr.xf_mul[i];
-        p.xf_div = pr.xf_div;
-    }
+    return MMD_OK;
+}
+
+template <int BN, int OC>
+static int gemm_attr() {
+    MMD_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<BN, OC>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN, OC>::TOTAL));
     return MMD_OK;
 }
 
 int gemm_init_attrs() {
     static bool done = false;
     if (done) return MMD_OK;
-    MMD_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<256>::TOTAL));
-    MMD_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<128>::TOTAL));
-    MMD_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<64>::TOTAL));
-    MMD_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<16>::TOTAL));
+    MMD_TRY((gemm_attr<256, 64>()));
+    MMD_TRY((gemm_attr<256, 128>()));
+    MMD_TRY((gemm_attr<128, 64>()));
+    MMD_TRY((gemm_attr<128, 128>()));
+    MMD_TRY((gemm_attr<64, 64>()));
+    MMD_TRY((gemm_attr<16, 64>()));
     done = true;
     return MMD_OK;
+}
+
+// Staged output columns per epilogue chunk: K-heavy GEMMs hide the epilogue under the mainloop and want every spare
+// kilobyte as pipeline stages (64); short-K GEMMs are epilogue / store bound and want fewer barrier rounds (128).
+int pick_oc(int bn, long long num_kb) {
+    static const int min_kb = [] { const char* e = getenv("MMD_OC64_MIN_KB"); return e ? atoi(e) : 16; }();
+    if (bn < 128) return 64;
+    return num_kb >= min_kb ? 64 : 128;
 }
 
 PdlState& pdl_state() {
@@ -215,10 +221,16 @@ int launch_gemm(const GemmParams& p, int bn, cudaStream_t st) {
     MMD_TRY(gemm_init_attrs());
     const int tiles = p.m_tiles * p.n_tiles;
     const int grid = std::min(tiles, num_sms());
-    if (bn == 256) MMD_CUDA_OK(launch_kernel(conv_gemm_kernel<256>, grid, GEMM_THREADS, GemmSmem<256>::TOTAL, st, p));
-    else if (bn == 128) MMD_CUDA_OK(launch_kernel(conv_gemm_kernel<128>, grid, GEMM_THREADS, GemmSmem<128>::TOTAL, st, p));
-    else if (bn == 64) MMD_CUDA_OK(launch_kernel(conv_gemm_kernel<64>, grid, GEMM_THREADS, GemmSmem<64>::TOTAL, st, p));
-    else if (bn == 16) MMD_CUDA_OK(launch_kernel(conv_gemm_kernel<16>, grid, GEMM_THREADS, GemmSmem<16>::TOTAL, st, p));
+    long long num_kb = 0;
+    for (int s = 0; s < p.n_src; ++s) num_kb += p.src_chunks[s];
+    num_kb *= p.n_taps;
+    const int oc = pick_oc(bn, num_kb);
+    if (bn == 256 && oc == 64) MMD_CUDA_OK(launch_kernel(conv_gemm_kernel<256, 64>, grid, GEMM_THREADS, GemmSmem<256, 64>::TOTAL, st, p));
+    else if (bn == 256) MMD_CUDA_OK(launch_kernel(conv_gemm_kernel<256, 128>, grid, GEMM_THREADS, GemmSmem<256, 128>::TOTAL, st, p));
+    else if (bn == 128 && oc == 64) MMD_CUDA_OK(launch_kernel(conv_gemm_kernel<128, 64>, grid, GEMM_THREADS, GemmSmem<128, 64>::TOTAL, st, p));
+    else if (bn == 128) MMD_CUDA_OK(launch_kernel(conv_gemm_kernel<128, 128>, grid, GEMM_THREADS, GemmSmem<128, 128>::TOTAL, st, p));
+    else if (bn == 64) MMD_CUDA_OK(launch_kernel(conv_gemm_kernel<64, 64>, grid, GEMM_THREADS, GemmSmem<64, 64>::TOTAL, st, p));
+    else if (bn == 16) MMD_CUDA_OK(launch_kernel(conv_gemm_kernel<16, 64>, grid, GEMM_THREADS, GemmSmem<16, 64>::TOTAL, st, p));
     else return fail(MMD_EINVAL, "unsupported BN %d", bn);
     return MMD_OK;
 }

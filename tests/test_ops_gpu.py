@@ -31,7 +31,8 @@ def _rand(*shape, scale=1.0, seed=0):
 
 @pytest.mark.parametrize("m,cins,cout", [(256, [128], 128), (1000, [64], 64), (4096, [256, 128], 256),
                                           (300, [128, 64, 64], 384), (16384, [512], 1536),
-                                          (65536, [128], 512), (40000, [192, 64], 256)])
+                                          (65536, [128], 512), (40000, [192, 64], 256),
+                                          (90000, [64], 128), (80000, [128, 64], 128)])   # last two: > 4 waves of tiles, even / odd tile count
 def test_conv_pointwise(ops, m, cins, cout):
     xs = [_rand(m, c, seed=i).half() for i, c in enumerate(cins)]
     w = _rand(cout, sum(cins), scale=0.05, seed=7)
@@ -55,7 +56,8 @@ def _check_sums(got, y, domains):
 
 
 @pytest.mark.parametrize("m,cin,cout,rows", [(1024, 128, 128, 128), (1024, 128, 128, 64), (4096, 64, 256, 1024),
-                                             (8192, 128, 384, 4096), (65536, 128, 512, 4096), (40960, 256, 256, 64)])
+                                             (8192, 128, 384, 4096), (65536, 128, 512, 4096), (40960, 256, 256, 64),
+                                             (81920, 128, 128, 4096), (77824, 64, 128, 64)])
 def test_conv_pointwise_fused_gn_statistics(ops, m, cin, cout, rows):
     """GEMM-epilogue GroupNorm statistics (128- and 256-wide tiles, 1 or 2 domains per tile) == sums over the output."""
     x = _rand(m, cin, seed=21).half()
@@ -89,7 +91,7 @@ def test_conv_audio_fused_gn_statistics(ops, b, l, ci, co, dil):
 
 
 @pytest.mark.parametrize("n,h,w,ci,co", [(2, 64, 64, 128, 128), (3, 32, 32, 256, 128), (5, 16, 16, 64, 64),
-                                          (16, 8, 8, 128, 256), (8, 4, 4, 64, 128)])
+                                          (16, 8, 8, 128, 256), (8, 4, 4, 64, 128), (20, 64, 64, 64, 128)])
 def test_conv_spatial(ops, n, h, w, ci, co):
     x = _rand(n, h, w, ci, seed=1).half()
     wt = _rand(co, ci, 3, 3, scale=0.03, seed=2)

@@ -13,11 +13,12 @@ print("ms/step", d["ms_per_step"], "value", d["value"], "e2e", d["e2e"]["value"]
 for k,v in d["families"].items(): print(f"  {k:20s} {v['ms']:8.3f} ms  {v['launches']:4d} launches  {v['tflops']:8.1f} TF/s  {v['gbs']:8.1f} GB/s")
 print(d["clocks"])
 PY
-if [ -n "$COMPARE_ENV" ]; then
-  env $COMPARE_ENV timeout 600 python bench.py --steps ${STEPS:-20} --warmup 3 --batch ${BATCH:-4} --no-cpu-baseline > gpurun_out/bench_cmp.json 2> gpurun_out/bench_cmp.err
-  python - <<'PY'
+for ce in $COMPARE_ENV; do
+  env $ce timeout 600 python bench.py --steps ${STEPS:-20} --warmup 3 --batch ${BATCH:-4} --no-cpu-baseline > gpurun_out/bench_cmp.json 2> gpurun_out/bench_cmp.err
+  CE=$ce python - <<'PY'
 import json,os
 d=json.load(open("gpurun_out/bench_cmp.json"))
-print(os.environ.get("COMPARE_ENV"), "-> ms/step", d["ms_per_step"], "value", d["value"], "e2e", d["e2e"]["value"])
+f=d["families"]
+print(os.environ.get("CE"), "-> ms/step", d["ms_per_step"], "value", d["value"], "| 3x3", f["conv3x3_spatial"]["ms"], "qkv", f["conv1x1_qkv"]["ms"], "out", f["conv1x1_out"]["ms"], "proj", f["conv1x1_proj"]["ms"], "tconv", f["conv_temporal"]["ms"], "audio", f["conv_audio_k3"]["ms"])
 PY
-fi
+done
