@@ -82,6 +82,23 @@ int mmd_model_num_launches(const MmdModel* m, int batch);
 int mmd_model_forward(MmdModel* m, int batch, const float* video_in, const float* audio_in, const float* timesteps,
                       const int32_t* shifts, float* video_out, float* audio_out, void* stream);
 
+/* ---- training / input gradients: MultimodalUNet.forward under autograd (multimodal_gaussian_diffusion.py:1141 training
+ *      losses, :815 gradient-guided conditional sampling).  mmd_model_forward_train is mmd_model_forward with every
+ *      intermediate kept (no CUDA graph); mmd_model_backward consumes the gradients of its two outputs (fp32, same
+ *      layouts) and writes
+ *        param_grads  fp32 [mmd_model_param_floats()], parameter i at mmd_model_param_offset(i), reference layout
+ *                     [Cout,Cin,k...] (overwritten, not accumulated; may be NULL),
+ *        d_video_in / d_audio_in  fp32 gradients wrt the inputs (may be NULL).
+ *      One backward per forward_train; activation gradients are fp16 with one internal power-of-two scale. ---- */
+int mmd_model_forward_train(MmdModel* m, int batch, const float* video_in, const float* audio_in, const float* timesteps,
+                            const int32_t* shifts, float* video_out, float* audio_out, void* stream);
+int mmd_model_backward(MmdModel* m, int batch, const float* d_video_out, const float* d_audio_out, float* param_grads,
+                       float* d_video_in, float* d_audio_in, void* stream);
+size_t mmd_model_train_workspace_bytes(const MmdModel* m, int batch);
+int64_t mmd_model_param_offset(const MmdModel* m, int index);
+int64_t mmd_model_param_floats(const MmdModel* m);
+int mmd_model_num_backward_launches(const MmdModel* m, int batch);
+
 /* ---- measurement hooks (bench.py): per-launch device time of the plan for `batch` (mean of `reps` un-graphed
  *      executions, CUDA events on `stream`) and each step's kernel family / algorithmic FLOPs / bytes
  *      (DESIGN.md §kernels).  mmd_model_profile returns the step count (>0) or a negative error. ---- */
@@ -166,6 +183,37 @@ typedef struct MmdAttnDesc {
 int mmd_op_attention(const MmdAttnDesc* d, void* stream);
 /* 16-token temporal attention: qkv [B,F,P,3C] -> out [B,F,P,C]. */
 int mmd_op_temporal_attention(const void* qkv, void* out, int B, int F, int P, int C, int heads, void* stream);
+
+/* ---- operator-level backward entry points (training; parity tests of the backward
+ *      kernels against torch.autograd of the reference ops; same kernels the model's backward plan launches) ---- */
+
+/* Weight / bias gradient of mmd_op_conv: same descriptor (geometry, sources, taps, n; weight/bias/out unused);
+ * dy fp16 [tokens][n]; dweight fp32 [n][c_total][n_taps] and dbias fp32 [n] are ACCUMULATED into.
+ * (autograd of F.conv1d/2d/3d in VideoConv / AudioConv, multimodal_unet.py:68-131.) */
+int mmd_op_conv_wgrad(const MmdConvDesc* d, const void* dy, float* dweight, float* dbias, void* stream);
+/* Data gradient wrt source `src_index`: dx fp16 [tokens][src_channels[src_index]] = conv of dy with the transposed,
+ * tap-mirrored weights (runs on the forward implicit-GEMM kernel).  Needs n % 64 == 0. */
+int mmd_op_conv_dgrad(const MmdConvDesc* d, const void* dy, int src_index, void* dx, void* stream);
+/* GroupNorm32 (+FiLM, +SiLU) backward of mmd_op_group_norm (nn.py:16-33, multimodal_unet.py:459-470): dy fp16
+ * [ns*rows][c1+c2]; dx1 [..][c1], dx2 [..][c2] (may be NULL when c2 == 0); dgamma/dbeta [C] and dfilm [B][film_ld]
+ * (scale grads at [c], shift grads at [C + c]) are ACCUMULATED into (dfilm may be NULL without film). */
+int mmd_op_group_norm_bwd(const void* x1, int c1, const void* x2, int c2, int ns, int rows, const float* gamma, const float* beta,
+                          const float* film, int film_ld, int ns_per_batch, int silu, const void* dy, void* dx1, void* dx2,
+                          float* dgamma, float* dbeta, float* dfilm, void* stream);
+int mmd_op_group_norm_temporal_bwd(const void* x, const void* dy, void* dx, const float* gamma, float* dgamma, float* dbeta, int B,
+                                   int F, int P, int C, void* stream);
+/* Adjoint of mmd_op_resample; (n, h, w, c) are the FORWARD INPUT extents, dy has the forward output shape. */
+int mmd_op_resample_bwd(const void* dy, void* dx, int mode, int n, int h, int w, int c, void* stream);
+int mmd_op_temporal_attention_bwd(const void* qkv, const void* d_out, void* dqkv, int B, int F, int P, int C, int heads, void* stream);
+/* Attention forward (writes d->out and lse fp32 [heads][q_rows]) followed by its backward: d_out fp16 [q_rows][heads*d];
+ * dq / dk / dv are written into column ranges (start dq_col0 / dk_col0 / dv_col0, head h at + h*d) of row-major fp16
+ * matrices with leading dimension grad_ld (QKVAttention / SingleModalQKVAttention autograd, multimodal_unet.py:212-244, 507-564). */
+int mmd_op_attention_fwd_bwd(const MmdAttnDesc* d, const void* d_out, float* lse, void* dq, void* dk, void* dv, int grad_ld,
+                             int dq_col0, int dk_col0, int dv_col0, void* stream);
+/* Narrow output heads (video_out / audio_out, multimodal_unet.py:1003-1012): descriptor as for the forward head call
+ * (fp32 strided output layout); dout fp32 in that layout; dx fp16 [tokens][C] (NULL = skip); dweight fp32
+ * [n][C][n_taps] / dbias [n] ACCUMULATED into (NULL = skip). */
+int mmd_op_head_bwd(const MmdConvDesc* d, const float* dout, void* dx, float* dweight, float* dbias, void* stream);
 
 #ifdef __cplusplus
 }

@@ -91,6 +91,15 @@ _PROTOS = [
     ("mmd_model_forward", C.c_int,
      [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p,
       C.c_void_p]),
+    ("mmd_model_forward_train", C.c_int,
+     [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p,
+      C.c_void_p]),
+    ("mmd_model_backward", C.c_int,
+     [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("mmd_model_train_workspace_bytes", C.c_size_t, [C.c_void_p, C.c_int]),
+    ("mmd_model_param_offset", C.c_int64, [C.c_void_p, C.c_int]),
+    ("mmd_model_param_floats", C.c_int64, [C.c_void_p]),
+    ("mmd_model_num_backward_launches", C.c_int, [C.c_void_p, C.c_int]),
     ("mmd_model_profile", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int, C.c_void_p]),
     ("mmd_model_step_info", C.c_int,
      [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(C.c_double),
@@ -113,6 +122,20 @@ _PROTOS = [
     ("mmd_op_attention", C.c_int, [C.POINTER(MmdAttnDesc), C.c_void_p]),
     ("mmd_op_temporal_attention", C.c_int,
      [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    ("mmd_op_conv_wgrad", C.c_int, [C.POINTER(MmdConvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("mmd_op_conv_dgrad", C.c_int, [C.POINTER(MmdConvDesc), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    ("mmd_op_group_norm_bwd", C.c_int,
+     [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+      C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("mmd_op_group_norm_temporal_bwd", C.c_int,
+     [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    ("mmd_op_resample_bwd", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    ("mmd_op_temporal_attention_bwd", C.c_int,
+     [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    ("mmd_op_attention_fwd_bwd", C.c_int,
+     [C.POINTER(MmdAttnDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+      C.c_void_p]),
+    ("mmd_op_head_bwd", C.c_int, [C.POINTER(MmdConvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 ]
 
 EXPORTED_SYMBOLS = [p[0] for p in _PROTOS]

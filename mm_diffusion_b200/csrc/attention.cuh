@@ -35,6 +35,10 @@ struct alignas(64) AttnParams {
     const int* shift_ptr;             // device scalar (random window shift), may be null
     int q_tiles;                      // ceil(q_blk / 128)
     float scale_log2;                 // d^-1/2 * log2(e)
+    // training only: log2-sum-exp of the scaled logits per (head, query row), lse[head * lse_ld + row]; the backward
+    // kernels rebuild P = exp2(s * scale_log2 - lse) from it (null = not written)
+    float* lse;
+    long long lse_ld;
 };
 
 struct AttnWork {
@@ -328,6 +332,8 @@ __global__ void __launch_bounds__(ATT_THREADS, (D == 64) ? 2 : 1) attention_kern
         mbar_wait(o_full, (T - 1) & 1);
         tc_fence_after();
         const float inv_l = 1.f / l_run;
+        if (p.lse != nullptr && row < w.q_valid)
+            p.lse[static_cast<size_t>(w.head) * p.lse_ld + w.q_row0 + row] = m_run + log2f(l_run);
         act_t* orow = p.out + static_cast<size_t>(w.q_row0 + row) * p.out_ld + w.head * D;
 #pragma unroll
         for (int c = 0; c < D / 32; ++c) {
@@ -681,6 +687,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention64_kernel(const __gri
             tmem_ld16(tmem_L + lane_base, lv);
             tmem_ld_wait();
             const float inv_l = 1.f / __uint_as_float(lv[0]);
+            if (p.lse != nullptr && row < w.q_valid)
+                p.lse[static_cast<size_t>(w.head) * p.lse_ld + w.q_row0 + row] = m_used + log2f(__uint_as_float(lv[0]));
             act_t* orow = p.out + static_cast<size_t>(w.q_row0 + row) * p.out_ld + w.head * D;
 #pragma unroll
             for (int c = 0; c < 2; ++c) {

@@ -14,9 +14,12 @@
 
 #include "../../include/mmdiff.h"
 #include "attention.cuh"
+#include "attention_bwd.cuh"
+#include "backward.cuh"
 #include "common.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
+#include "wgrad.cuh"
 
 namespace mmd {
 
@@ -151,5 +154,74 @@ int launch_gn_temporal(const act_t* x, act_t* y, const float* gamma, const float
 int launch_resample(const act_t* x, act_t* y, int mode, int n, int h, int w, int c, cudaStream_t st);
 int launch_temporal_attn(const act_t* qkv, act_t* out, int B, int F, int P, int C, int heads, cudaStream_t st);
 int launch_pack_weight(const float* w, act_t* dst, int co, int ci, int t, long long ld, long long col_off, cudaStream_t st);
+
+// ------------------------------------------------------------- backward
+// Weight gradient of a conv-GEMM: same geometry / sources / taps as the forward GemmProblem; dy is the fp16 output
+// gradient [tokens][n]; dw is the packed fp32 gradient [n][ld] (column order of the forward's packed weights), zeroed
+// by the caller.
+struct WgradProblem {
+    ConvGeom g;
+    int n_src = 0;
+    const act_t* src[GEMM_MAX_SRC] = {};
+    int src_c[GEMM_MAX_SRC] = {};
+    int n_taps = 1;
+    int taps[GEMM_MAX_TAPS][3] = {};
+    const act_t* dy = nullptr;
+    int n = 0;
+    float* dw = nullptr;
+    long long ld = 0;
+};
+int build_wgrad(const WgradProblem& pr, WgradParams* out, int* n_items);
+int launch_wgrad(const WgradParams& p, int n_items, cudaStream_t st);
+int launch_unpack_wgrad(const float* dwpk, float* g, int co, int ci, int t, long long ld, long long col_off, float scale,
+                        cudaStream_t st, const float* gscale = nullptr);
+int launch_pack_weight_t(const float* w, act_t* dst, int co, int ci, int t, int c_lo, int cs, long long ld, long long col_off,
+                         cudaStream_t st);
+int launch_colsum(const act_t* x, long long rows, int C, float scale, float* out, cudaStream_t st, float* out2 = nullptr,
+                  const float* gscale = nullptr);
+int launch_grad_add(const act_t* x, act_t* y, long long n, int accumulate, cudaStream_t st);
+int launch_grad_add2d(const act_t* x, long long ldx, act_t* y, long long ldy, long long rows, int C, int accumulate, cudaStream_t st);
+
+// Attention backward: `fwd` describes the forward call (out = forward output O); gradients land in column ranges of
+// row-major fp16 matrices like q / k / v themselves.  lse / delta: [heads][stat_ld] floats (lse from the forward).
+struct AttnBwdOut {
+    act_t* dq; int dq_ld; int dq_col0;
+    act_t* dk; int dk_ld; int dk_col0;
+    act_t* dv; int dv_ld; int dv_col0;
+};
+int build_attn_bwd(const AttnProblem& fwd, const act_t* d_out, int d_out_ld, const float* lse, const float* delta,
+                   long long stat_ld, const AttnBwdOut& o, AttnBwdParams* pq, AttnBwdParams* pkv);
+int launch_attn_bwd(const AttnBwdParams& pq, const AttnBwdParams& pkv, int d, cudaStream_t st);
+int launch_attn_delta(const act_t* d_out, const act_t* out, long long rows, int C, int heads, float* delta, long long delta_ld,
+                      cudaStream_t st);
+int launch_attn_lse(const AttnParams& p, int d, float* lse, long long lse_ld, cudaStream_t st);   // forward + lse output
+
+// GroupNorm backward (three launches: reduce, apply, finalize).  T: fp32 [ns][C][2] scratch zeroed by the caller.
+struct GnBwdProblem {
+    GnSrc s;
+    int ns = 0, rows = 0;
+    const double* sums = nullptr;
+    int nsub = 1;
+    long long stat_rows = 0;
+    const float* gamma = nullptr;
+    const float* beta = nullptr;
+    const float* film = nullptr;
+    int film_ld = 0, ns_per_batch = 1, silu = 0;
+    const act_t* dy = nullptr;
+    float* T = nullptr;
+    GnBwdOut out{};
+    float* dgamma = nullptr;
+    float* dbeta = nullptr;
+    float* dfilm = nullptr;
+    const float* gscale = nullptr;
+};
+int launch_gn_bwd(const GnBwdProblem& pr, cudaStream_t st);
+int launch_gn_temporal_bwd(const act_t* x, const act_t* dy, act_t* dx, const float* gamma, float* dgamma, float* dbeta, int B,
+                           int F, int P, int C, const float* gscale, cudaStream_t st);
+int launch_temporal_attn_bwd(const act_t* qkv, const act_t* d_out, act_t* dqkv, int B, int F, int P, int C, int heads,
+                             cudaStream_t st);
+int launch_resample_bwd(const act_t* dy, act_t* dx, int mode, int n, int h, int w, int c, int accumulate, cudaStream_t st);
+int launch_head_dgrad(const HeadGeom& g, const float* dout, const float* w, act_t* dx, const float* gscale, cudaStream_t st);
+int launch_head_wgrad(const HeadGeom& g, const float* dout, const act_t* a, float* dw, float* db, cudaStream_t st);
 
 }  // namespace mmd

@@ -33,7 +33,11 @@ struct ParamInfo {
     bool set = false;
 };
 
+struct Seg { int w; int ci; int T; };   // one weight tensor of a packed GEMM: param index, input channels, taps
+
 struct PackedConv {
+    std::vector<Seg> segs;        // conv segments in K order (identity columns follow them)
+    std::vector<int> biases;      // bias parameters summed into the packed bias
     size_t w_off = 0;     // halves, into packed arena
     size_t b_off = 0;     // floats, into packed bias arena
     int n = 0, n_pad = 0, bn = 128;
@@ -44,11 +48,12 @@ struct PackedConv {
 struct Arena {
     uint8_t* base = nullptr;
     size_t cap = 0, top = 0, peak = 0;
+    uintptr_t fake = 0;   // dry runs hand out distinct non-null fake addresses per arena (the backward tape keys on them)
     void* take(size_t bytes) {
         size_t at = (top + 1023) & ~size_t(1023);
         top = at + bytes;
         peak = std::max(peak, top);
-        return base ? base + at : reinterpret_cast<void*>(at);  // dry run when base == nullptr
+        return base ? base + at : reinterpret_cast<void*>(fake + at);  // dry run when base == nullptr
     }
 };
 
@@ -70,11 +75,54 @@ struct Plan {
     int* shifts_dev = nullptr;
     cudaGraphExec_t graph = nullptr;
     std::vector<cudaEvent_t> events;   // fork / join events of the two-branch capture
+    // ---- training plan only (every intermediate kept; backward launch list built from the tape)
+    bool train = false;
+    std::vector<LaunchFn> bwd_steps;
+    std::vector<LaunchFn> tpack_ops;   // transposed weight packs for the data gradients (re-run when weights change)
+    bool tpack_dirty = true;
+    float *d_out_video = nullptr, *d_out_audio = nullptr;   // staged output gradients (fp32, API layout)
+    float *d_in_video = nullptr, *d_in_audio = nullptr;     // input gradients (fp32, API layout)
+    float* gscale = nullptr;            // {s, 1/s}
+    unsigned int* amax_bits = nullptr;
+    float* g32 = nullptr;               // parameter gradients, same offsets as MmdModel::w32
+    float* d_emb_all = nullptr;         // [B][emb_rows]
+    act_t* wpk_t = nullptr;             // transposed packs
+    float* zero_bias = nullptr;
+    bool fwd_done = false;
     ~Plan() {
         if (graph) cudaGraphExecDestroy(graph);
         for (auto e : events) cudaEventDestroy(e);
         if (ws) cudaFree(ws);
+        if (wpk_t) cudaFree(wpk_t);
     }
+};
+
+// One forward launch as the backward needs to see it.
+struct TapeOp {
+    enum Kind { GEMM, GN, GN_TEMPORAL, TATTN, ATTN, RESAMPLE } kind = GEMM;
+    // GEMM
+    std::string tag;
+    ConvGeom g;
+    std::vector<std::pair<const act_t*, int>> srcs;
+    std::vector<std::array<int, 3>> taps;
+    const PackedConv* pc = nullptr;
+    act_t* out = nullptr;
+    float* out_f32 = nullptr;
+    long long ostride[4] = {0, 0, 0, 0};
+    long long ostride_c = 0;
+    int stem = 0;             // 1 video im2col stem, 2 audio im2col stem (source is the im2col buffer)
+    // GN
+    const act_t *x1 = nullptr, *x2 = nullptr;
+    int c1 = 0, c2 = 0, ns = 0, rows = 0, gn_g = -1, gn_b = -1, emb_row0 = -1, silu = 0, nsub = 1, ns_per_batch = 1;
+    const double* sums = nullptr;
+    long long stat_rows = 0;
+    act_t* y = nullptr;
+    // GN_TEMPORAL / TATTN / RESAMPLE
+    const act_t* in = nullptr;
+    int B = 0, F = 0, P = 0, C = 0, heads = 0, mode = 0, n_ = 0, h_ = 0, w_ = 0;
+    // ATTN
+    AttnProblem ap{};
+    float* lse = nullptr;
 };
 
 }  // namespace mmd
@@ -98,11 +146,13 @@ struct MmdModel {
     int emb_rows = 0;               // stacked emb_layers rows
     size_t emb_w_off = 0, emb_b_off = 0;
     std::map<int, std::unique_ptr<Plan>> plans;
+    std::map<int, std::unique_ptr<Plan>> train_plans;
     bool use_graph = true;
     bool two_streams = true;   // MMD_ONE_STREAM=1 captures everything on one stream
     cudaStream_t cap_stream = nullptr, cap_stream2 = nullptr;
     ~MmdModel() {
         plans.clear();
+        train_plans.clear();
         if (w32) cudaFree(w32);
         if (wpk) cudaFree(wpk);
         if (bpk) cudaFree(bpk);
@@ -130,6 +180,16 @@ struct Walker {
     int B = 1;
     Arena persist, scratch, scratch_a, stats;   // scratch per branch (video / audio run concurrently); stats: GroupNorm
                                                 // accumulators, zeroed once per forward
+    // training: nothing is recycled (scratch marks are ignored), every launch is taped, activation gradients live in
+    // `grads`, per-op backward temporaries in `bscratch` (reset per op: the backward runs on one stream)
+    bool train = false;
+    Arena grads, bscratch, tpack;
+    std::vector<TapeOp> tape;
+    std::map<const act_t*, std::pair<act_t*, bool>> grad_map;   // activation -> (gradient buffer, written yet)
+    struct EmbBlk { int w, b, row0, rows; };
+    std::vector<EmbBlk> emb_blocks;
+    int te_idx[4] = {-1, -1, -1, -1};
+    void release(Arena& a, size_t mark) { if (!train) a.top = mark; }
     int cur = 0;                                // branch being emitted: 0 video (main stream), 1 audio
     Arena& S() { return cur == 1 ? scratch_a : scratch; }
     int err = MMD_OK;
@@ -142,6 +202,9 @@ struct Walker {
     float* silu_emb = nullptr;  // [B][E]
 
     Walker(MmdModel& mm, bool c) : m(mm), create(c) {
+        persist.fake = uintptr_t(1) << 40; scratch.fake = uintptr_t(2) << 40; scratch_a.fake = uintptr_t(3) << 40;
+        stats.fake = uintptr_t(4) << 40; grads.fake = uintptr_t(5) << 40; bscratch.fake = uintptr_t(6) << 40;
+        tpack.fake = uintptr_t(7) << 40;
         const char* e = getenv("MMD_NO_FUSED_STATS");
         fuse_stats = !(e && e[0] == '1');
         const char* w = getenv("MMD_NO_BN256");
@@ -196,7 +259,6 @@ struct Walker {
     }
 
     // ---------------- packed weights
-    struct Seg { int w; int ci; int T; };
     const PackedConv* pack(const std::string& key, int n, const std::vector<Seg>& segs, int identity_c,
                            const std::vector<int>& biases, int force_bn = 0, long long min_k = 0) {
         if (!create) {
@@ -205,6 +267,8 @@ struct Walker {
             return &it->second;
         }
         PackedConv pc;
+        pc.segs = segs;
+        pc.biases = biases;
         pc.n = n;
         pc.bn = force_bn ? force_bn : pick_bn(n);
         pc.n_pad = (n + pc.bn - 1) / pc.bn * pc.bn;
@@ -274,7 +338,16 @@ struct Walker {
     void emit_gemm(const char* tag, const ConvGeom& g, const std::vector<std::pair<const act_t*, int>>& srcs,
                    const std::vector<std::array<int, 3>>& taps, const PackedConv* pc, act_t* out, float* out_f32 = nullptr,
                    const long long* ostride = nullptr, long long ostride_c = 0, double* stat_slots = nullptr,
-                   int stat_kind = 0, int stat_hw = 0) {
+                   int stat_kind = 0, int stat_hw = 0, int stem = 0) {
+        if (train && pc) {
+            TapeOp op;
+            op.kind = TapeOp::GEMM;
+            op.tag = tag; op.g = g; op.srcs = srcs; op.taps = taps; op.pc = pc; op.out = out; op.out_f32 = out_f32;
+            if (ostride) for (int i = 0; i < 4; ++i) op.ostride[i] = ostride[i];
+            op.ostride_c = ostride_c;
+            op.stem = stem;
+            tape.push_back(op);
+        }
         if (!emitting() || bad() || !pc) return;
         GemmProblem pr;
         pr.g = g;
@@ -330,6 +403,16 @@ struct Walker {
         act_t* y = alloc_s(static_cast<size_t>(ns) * rows * C);
         const bool fused = fuse_stats && st && st->slots && !x2;
         double* sums = fused ? st->slots : static_cast<double*>(stats.take(sizeof(double) * 64 * ns));
+        if (train) {
+            TapeOp op;
+            op.kind = TapeOp::GN;
+            op.x1 = x1; op.c1 = c1; op.x2 = x2; op.c2 = c2; op.ns = ns; op.rows = rows; op.gn_g = gn.g; op.gn_b = gn.b;
+            op.emb_row0 = film ? static_cast<int>(film - emb_all) : -1;
+            op.silu = silu; op.ns_per_batch = ns_per_batch; op.sums = sums; op.y = y;
+            op.nsub = fused ? (per_frame ? 1 : st->nsub) : 1;
+            op.stat_rows = fused ? (per_frame ? st->rows / st->nsub : st->rows) : rows;
+            tape.push_back(op);
+        }
         if (!emitting() || bad()) return y;
         if (fused) {
             GnSrc s{x1, c1, c1, nullptr, 0, 0};
@@ -357,12 +440,22 @@ struct Walker {
     void emit_attn(const act_t* q, int q_ld, int q_col0, long long q_rows, const act_t* k, int k_ld, int k_col0,
                    long long k_rows, const act_t* v, int v_col0, act_t* out, int out_ld, int heads, int d, int n_blocks,
                    int q_blk, int k_blk, int win, const int* shift_dev) {
-        if (!emitting() || bad()) return;
         AttnProblem pr{q, q_ld, q_col0, q_rows, k, k_ld, k_col0, k_rows, v, k_ld, v_col0, out, out_ld,
                        B, heads, d, n_blocks, q_blk, k_blk, win, shift_dev};
+        float* lse = nullptr;
+        if (train) {
+            lse = static_cast<float*>(persist.take(sizeof(float) * heads * (q_rows + 128)));
+            TapeOp op;
+            op.kind = TapeOp::ATTN;
+            op.ap = pr; op.lse = lse;
+            tape.push_back(op);
+        }
+        if (!emitting() || bad()) return;
         auto ap = std::make_shared<AttnParams>();
         int r = build_attn(pr, ap.get());
         if (r != MMD_OK) { set_err(r); return; }
+        ap->lse = lse;
+        ap->lse_ld = q_rows;
         const double fl = 4.0 * static_cast<double>(q_rows) * (static_cast<double>(win) * k_blk) * d * heads;
         const double by = 2.0 * (2.0 * q_rows + 2.0 * k_rows) * d * heads;
         push([ap, d](cudaStream_t st) { return launch_attn(*ap, d, st); }, win == 1 && shift_dev == nullptr && q_blk == k_blk ? "self_attention" : "cross_attention", fl, by);
@@ -396,6 +489,12 @@ struct Walker {
             xn = emit_gn(x, C, nullptr, 0, B, at->L, gn, nullptr, 1, 0, in_st, false);
         } else {
             xn = alloc_s(tokens * C);
+            if (train) {
+                TapeOp op;
+                op.kind = TapeOp::GN_TEMPORAL;
+                op.in = x; op.y = xn; op.gn_g = gn.g; op.gn_b = gn.b; op.B = B; op.F = F(); op.P = vt->H * vt->W; op.C = C;
+                tape.push_back(op);
+            }
             if (emitting()) {
                 const float* gamma = pf(gn.g);
                 const float* beta = pf(gn.b);
@@ -414,8 +513,15 @@ struct Walker {
             emit_attn(qkvb, 3 * C, 0, tokens, qkvb, 3 * C, C, tokens, qkvb, 2 * C, o, C, heads, d, F(), hw, hw, 1, nullptr);
         } else if (kind == 2) {
             emit_attn(qkvb, 3 * C, 0, tokens, qkvb, 3 * C, C, tokens, qkvb, 2 * C, o, C, heads, d, 1, at->L, at->L, 1, nullptr);
-        } else if (emitting()) {
+        } else {
+            if (train) {
+                TapeOp op;
+                op.kind = TapeOp::TATTN;
+                op.in = qkvb; op.y = o; op.B = B; op.F = F(); op.P = vt->H * vt->W; op.C = C; op.heads = heads;
+                tape.push_back(op);
+            }
             const int Bc = B, Fc = F(), P = vt->H * vt->W;
+            if (emitting())
             push([=](cudaStream_t st) { return launch_temporal_attn(qkvb, o, Bc, Fc, P, C, heads, st); },
                  "temporal_attention", 4.0 * static_cast<double>(tokens) * Fc * C, 2.0 * 4.0 * static_cast<double>(tokens) * C);
         }
@@ -432,7 +538,7 @@ struct Walker {
             if (out_st) *out_st = Stat{slots, 1, at->L};
         }
         emit_gemm("conv1x1_proj", gtok, {{o, C}, {x, C}}, {{0, 0, 0}}, pp, out, nullptr, nullptr, 0, slots, skind, shw);
-        S().top = mark;
+        release(S(), mark);
         cur = 0;
         return out;
     }
@@ -461,6 +567,7 @@ struct Walker {
         // stacked emb_layers rows
         const int emb_row0 = emb_row_top;
         emb_row_top += 2 * cout;
+        if (train) emb_blocks.push_back(EmbBlk{emb_w, emb_b, emb_row0, 2 * cout});
         if (create) {
             MmdModel* mp = &m;
             const int rows = 2 * cout;
@@ -515,6 +622,15 @@ struct Walker {
                 if (up || down) {
                     act_t* h1r = alloc_s(static_cast<size_t>(B) * Fr * vo.H * vo.W * cout);
                     act_t* xr = alloc_s(static_cast<size_t>(B) * Fr * vo.H * vo.W * v.C);
+                    if (train) {
+                        TapeOp op;
+                        op.kind = TapeOp::RESAMPLE;
+                        op.mode = down ? 0 : 2; op.n_ = B * Fr; op.h_ = v.H; op.w_ = v.W;
+                        op.in = h1; op.y = h1r; op.C = cout;
+                        tape.push_back(op);
+                        op.in = v.p; op.y = xr; op.C = v.C;
+                        tape.push_back(op);
+                    }
                     if (emitting()) {
                         const int mode = down ? 0 : 2;
                         const int n = B * Fr, H = v.H, W = v.W, c_h = cout, c_x = v.C;
@@ -535,7 +651,7 @@ struct Walker {
                 if (can_fuse_video(hwo, cout)) vo.st = Stat{stat_slots_video(), Fr, static_cast<long long>(Fr) * hwo};
                 emit_gemm("conv1x1_out", geom2(static_cast<long long>(B) * Fr * hwo), srcs, {{0, 0, 0}}, p_vo, vo.p,
                           nullptr, nullptr, 0, vo.st.slots, 1, hwo);
-                S().top = mark;
+                release(S(), mark);
             }
             // ---------------- audio branch
             {
@@ -555,6 +671,15 @@ struct Walker {
                 if (up || down) {
                     act_t* h1r = alloc_s(static_cast<size_t>(B) * ao.L * cout);
                     act_t* xr = alloc_s(static_cast<size_t>(B) * ao.L * a.C);
+                    if (train) {
+                        TapeOp op;
+                        op.kind = TapeOp::RESAMPLE;
+                        op.mode = down ? 1 : 3; op.n_ = B; op.h_ = a.L; op.w_ = 1;
+                        op.in = h1; op.y = h1r; op.C = cout;
+                        tape.push_back(op);
+                        op.in = a.p; op.y = xr; op.C = a.C;
+                        tape.push_back(op);
+                    }
                     if (emitting()) {
                         const int mode = down ? 1 : 3;
                         const int n = B, L = a.L, c_h = cout, c_x = a.C;
@@ -573,7 +698,7 @@ struct Walker {
                 if (a2) srcs.push_back({a2, ac2});
                 if (can_fuse_audio(ao.L, cout)) ao.st = Stat{stat_slots_audio(), 1, ao.L};
                 emit_gemm("conv1x1_out", geom_audio(ao), srcs, {{0, 0, 0}}, p_ao, ao.p, nullptr, nullptr, 0, ao.st.slots, 3, 0);
-                S().top = mark;
+                release(S(), mark);
                 cur = 0;
             }
         }
@@ -654,8 +779,8 @@ struct Walker {
         emit_gemm("conv1x1_proj", geom_audio(a), {{oa, C}, {a.p, C}}, {{0, 0, 0}}, p_ap, aout, nullptr, nullptr, 0,
                   ast.slots, 3, 0);
         cur = 0;
-        scratch.top = mark_v;
-        scratch_a.top = mark_a;
+        release(scratch, mark_v);
+        release(scratch_a, mark_a);
         v.p = vout;
         a.p = aout;
         v.st = vst;
@@ -679,6 +804,7 @@ struct Walker {
         int te0w = reg("time_embed.0.weight", {E, mc}), te0b = reg("time_embed.0.bias", {E});
         int te2w = reg("time_embed.2.weight", {E, E}), te2b = reg("time_embed.2.bias", {E});
         float* emb = nullptr;
+        te_idx[0] = te0w; te_idx[1] = te0b; te_idx[2] = te2w; te_idx[3] = te2b;
         if (!create && emitting()) {
             uint8_t* sbase = stats.base;
             const size_t sbytes = stats.cap;
@@ -744,11 +870,11 @@ struct Walker {
                             return MMD_OK;
                         }, "im2col", 0.0, (4.0 * Cv + 128.0) * static_cast<double>(BF) * H * W, 1);
                     }
-                    emit_gemm("conv_stem", geom2(static_cast<long long>(vtok(v))), {{colv, 64}}, {{0, 0, 0}}, p_sp, u);
+                    emit_gemm("conv_stem", geom2(static_cast<long long>(vtok(v))), {{colv, 64}}, {{0, 0, 0}}, p_sp, u, nullptr, nullptr, 0, nullptr, 0, 0, 1);
                     if (can_fuse_video(hw0, ch)) v.st = Stat{stat_slots_video(), F(), static_cast<long long>(F()) * hw0};
                     emit_gemm("conv_temporal", geom_temporal(v), {{u, ch}}, {{0, -1, 0}, {0, 0, 0}, {0, 1, 0}}, p_tp, v.p,
                               nullptr, nullptr, 0, v.st.slots, 2, 0);
-                    S().top = mark;
+                    release(S(), mark);
                 }
                 {   // audio branch
                     cur = 1;
@@ -765,8 +891,8 @@ struct Walker {
                         }, "im2col", 0.0, (4.0 * Ca + 128.0) * static_cast<double>(Bc) * L, 1);
                     }
                     if (can_fuse_audio(a.L, ch)) a.st = Stat{stat_slots_audio(), 1, a.L};
-                    emit_gemm("conv_stem", geom_audio(a), {{cola, 64}}, {{0, 0, 0}}, p_ac, a.p, nullptr, nullptr, 0, a.st.slots, 3, 0);
-                    S().top = mark;
+                    emit_gemm("conv_stem", geom_audio(a), {{cola, 64}}, {{0, 0, 0}}, p_ac, a.p, nullptr, nullptr, 0, a.st.slots, 3, 0, 2);
+                    release(S(), mark);
                     cur = 0;
                 }
             }
@@ -879,10 +1005,392 @@ struct Walker {
             emit_gemm("conv_head", geom_audio(a), {{ha, ch}}, {{-1, 0, 0}, {0, 0, 0}, {1, 0, 0}}, p_ah, nullptr, plan ? plan->out_audio : nullptr, os_a, a.L);
             cur = 0;
             sync_branches();   // join: the caller's stream continues after both heads
-            scratch.top = mark;
-            scratch_a.top = mark_a;
+            release(scratch, mark);
+            release(scratch_a, mark_a);
         }
         if (create) m.emb_rows = emb_row_top;
+    }
+
+    // =====================================================================================================
+    // Backward launch list from the tape (training plans).  Runs in the dry pass too (it sizes the gradient,
+    // temporary and transposed-pack arenas); closures are only built when emitting.
+    // =====================================================================================================
+    float* g32_of(int param) const { return plan->g32 + m.params[param].offset; }
+    act_t* grad_buf(const act_t* x, size_t elems) {
+        auto it = grad_map.find(x);
+        if (it != grad_map.end()) return it->second.first;
+        act_t* gbuf = static_cast<act_t*>(grads.take(elems * sizeof(act_t)));
+        grad_map[x] = {gbuf, false};
+        return gbuf;
+    }
+    bool grad_written(const act_t* x) const {
+        auto it = grad_map.find(x);
+        return it != grad_map.end() && it->second.second;
+    }
+    void mark_written(const act_t* x) { grad_map[x].second = true; }
+    void bpush(LaunchFn fn) { if (emitting()) plan->bwd_steps.push_back(std::move(fn)); }
+    // gradient of an op output; every forward tensor has a consumer, so it must have been produced already
+    act_t* need_grad(const act_t* y, const char* what) {
+        if (!grad_written(y)) { set_err(fail(MMD_ESTATE, "internal: backward of %s has no incoming gradient", what)); return nullptr; }
+        return grad_map[y].first;
+    }
+
+    void bwd_gemm(const TapeOp& op) {
+        const PackedConv* pc = op.pc;
+        const long long tokens = op.g.tokens();
+        const int n = pc->n;
+        const float* gs = plan ? plan->gscale : nullptr;
+        if (op.tag == "conv_head") {   // narrow fp32 heads: CUDA-core adjoints straight from the API-layout gradient
+            const bool video = op.g.rank == 5;
+            const act_t* x = op.srcs[0].first;
+            const int C = op.srcs[0].second;
+            act_t* dx = grad_buf(x, static_cast<size_t>(tokens) * C);
+            if (grad_written(x)) { set_err(fail(MMD_ESTATE, "internal: head input gradient already written")); return; }
+            mark_written(x);
+            if (!emitting()) return;
+            HeadGeom hg{};
+            hg.ncoord = op.g.rank - 1;
+            for (int i = 0; i < 4; ++i) { hg.dims[i] = static_cast<int>(op.g.dims[i]); hg.ostride[i] = op.ostride[i]; }
+            hg.ostride_c = op.ostride_c;
+            hg.n_out = n;
+            hg.n_taps = static_cast<int>(op.taps.size());
+            for (size_t t = 0; t < op.taps.size(); ++t) for (int j = 0; j < 3; ++j) hg.tap[t][j] = op.taps[t][j];
+            hg.C = C;
+            const float* dout = video ? plan->d_out_video : plan->d_out_audio;
+            const float* w = pf(pc->segs[0].w);
+            float* dw = g32_of(pc->segs[0].w);
+            float* db = g32_of(pc->biases[0]);
+            bpush([=](cudaStream_t st) -> int {
+                MMD_TRY(launch_head_dgrad(hg, dout, w, dx, gs, st));
+                return launch_head_wgrad(hg, dout, x, dw, db, st);
+            });
+            return;
+        }
+        act_t* dy = need_grad(op.out, op.tag.c_str());
+        if (!dy) return;
+        const size_t bmark = bscratch.top;
+        // ---- sources: conv segments first, identity (residual) columns after them
+        long long conv_cols = 0;
+        for (auto& sg : pc->segs) conv_cols += sg.ci;
+        if (op.stem) conv_cols = op.srcs[0].second;
+        struct SrcInfo { const act_t* p; int c; long long off; bool conv; };
+        std::vector<SrcInfo> si;
+        long long a = 0;
+        for (auto& sc : op.srcs) {
+            const bool conv = a < conv_cols;
+            if (conv && a + sc.second > conv_cols) { set_err(fail(MMD_ESTATE, "internal: source straddles conv/identity columns")); return; }
+            si.push_back(SrcInfo{sc.first, sc.second, conv ? a : a - conv_cols, conv});
+            a += sc.second;
+        }
+        // ---- bias gradients: column sums of dY
+        if (pc->biases.size() > 2) { set_err(fail(MMD_ESTATE, "internal: more than two biases in one GEMM")); return; }
+        if (emitting() && !pc->biases.empty()) {
+            float* b0 = g32_of(pc->biases[0]);
+            float* b1 = pc->biases.size() > 1 ? g32_of(pc->biases[1]) : nullptr;
+            bpush([=](cudaStream_t st) { return launch_colsum(dy, tokens, n, 1.0f, b0, st, b1, gs); });
+        }
+        // ---- weight gradients: one tcgen05 wgrad over the conv sources, unpacked per parameter
+        {
+            WgradProblem wp;
+            wp.g = op.g;
+            for (auto& x : si) if (x.conv) { wp.src[wp.n_src] = x.p; wp.src_c[wp.n_src] = x.c; ++wp.n_src; }
+            wp.n_taps = static_cast<int>(op.taps.size());
+            for (size_t t = 0; t < op.taps.size(); ++t) for (int j = 0; j < 3; ++j) wp.taps[t][j] = op.taps[t][j];
+            wp.dy = dy;
+            wp.n = n;
+            wp.ld = conv_cols * wp.n_taps;
+            const size_t dw_bytes = sizeof(float) * static_cast<size_t>(n) * wp.ld;
+            float* dwpk = static_cast<float*>(bscratch.take(dw_bytes));
+            wp.dw = dwpk;
+            if (emitting()) {
+                auto wpar = std::make_shared<WgradParams>();
+                int items = 0;
+                int r = build_wgrad(wp, wpar.get(), &items);
+                if (r != MMD_OK) { set_err(r); return; }
+                std::vector<Seg> segs = pc->segs;
+                std::vector<float*> gdst;
+                for (auto& sg : segs) gdst.push_back(g32_of(sg.w));
+                const long long ld = wp.ld;
+                bpush([=](cudaStream_t st) -> int {
+                    MMD_CUDA_OK(cudaMemsetAsync(dwpk, 0, dw_bytes, st));
+                    MMD_TRY(launch_wgrad(*wpar, items, st));
+                    long long col = 0;
+                    for (size_t i = 0; i < segs.size(); ++i) {
+                        MMD_TRY(launch_unpack_wgrad(dwpk, gdst[i], n, segs[i].ci, segs[i].T, ld, col, 1.0f, st, gs));
+                        col += static_cast<long long>(segs[i].ci) * segs[i].T;
+                    }
+                    return MMD_OK;
+                });
+            }
+        }
+        // ---- data gradients
+        if (op.stem) {
+            // input gradient (gradient-guided sampling): dcol = dY * Wpk, then the im2col adjoint into the fp32 API layout
+            const int Ci = (op.stem == 1) ? cfg().video_c : cfg().audio_c;
+            const int T = pc->segs[0].T;
+            act_t* wt = static_cast<act_t*>(tpack.take(sizeof(act_t) * 64 * static_cast<size_t>(n)));
+            act_t* dcol = static_cast<act_t*>(bscratch.take(sizeof(act_t) * static_cast<size_t>(tokens) * 64));
+            if (emitting()) {
+                const float* w32p = pf(pc->segs[0].w);
+                const int Co = n;
+                plan->tpack_ops.push_back([=](cudaStream_t st) -> int {
+                    MMD_CUDA_OK(cudaMemsetAsync(wt, 0, sizeof(act_t) * 64 * static_cast<size_t>(Co), st));
+                    const long long total = static_cast<long long>(Co) * Ci * T;
+                    pack_stem_t_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(w32p, wt, Co, Ci, T, Co);
+                    MMD_CUDA_OK(cudaGetLastError());
+                    return MMD_OK;
+                });
+                GemmProblem pr;
+                pr.g = op.g;
+                pr.n_src = 1; pr.src[0] = dy; pr.src_c[0] = n;
+                pr.n_taps = 1;
+                pr.w = wt; pr.bias = plan->zero_bias; pr.n = 64; pr.bn = 64; pr.out = dcol;
+                auto gp = std::make_shared<GemmParams>();
+                int r = build_gemm(pr, gp.get());
+                if (r != MMD_OK) { set_err(r); return; }
+                const int Bc = B, Fr = F(), H = cfg().video_h, W = cfg().video_w, L = cfg().audio_l;
+                float* dxin = (op.stem == 1) ? plan->d_in_video : plan->d_in_audio;
+                const int stem = op.stem;
+                bpush([=](cudaStream_t st) -> int {
+                    MMD_TRY(launch_gemm(*gp, 64, st));
+                    pdl_break(st);
+                    if (stem == 1) {
+                        const long long total = static_cast<long long>(Bc) * Fr * Ci * H * W;
+                        col2im_video_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(dcol, dxin, Bc * Fr, Ci, H, W, gs);
+                    } else {
+                        const long long total = static_cast<long long>(Bc) * Ci * L;
+                        col2im_audio_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(dcol, dxin, Bc, Ci, L, gs);
+                    }
+                    MMD_CUDA_OK(cudaGetLastError());
+                    return MMD_OK;
+                });
+            }
+            release_b(bmark);
+            return;
+        }
+        long long seg_start = 0;
+        for (auto& x : si) {
+            act_t* gx = grad_buf(x.p, static_cast<size_t>(tokens) * x.c);
+            const bool acc = grad_written(x.p);
+            mark_written(x.p);
+            if (!x.conv) {   // residual / identity columns: dX += dY[:, off : off + c]
+                const long long off = x.off;
+                const int c = x.c;
+                bpush([=](cudaStream_t st) { return launch_grad_add2d(dy + off, n, gx, c, tokens, c, acc ? 1 : 0, st); });
+                continue;
+            }
+            // segment that holds this source's channel range
+            const Seg* sg = nullptr;
+            seg_start = 0;
+            for (auto& cand : pc->segs) {
+                if (x.off >= seg_start && x.off + x.c <= seg_start + cand.ci) { sg = &cand; break; }
+                seg_start += cand.ci;
+            }
+            if (!sg) { set_err(fail(MMD_ESTATE, "internal: source does not fit a weight segment")); return; }
+            const int T = sg->T, Ci = sg->ci, c_lo = static_cast<int>(x.off - seg_start), cs = x.c;
+            if (n % 64 != 0 || cs % 64 != 0) { set_err(fail(MMD_EINVAL, "backward: channels %d -> %d not multiples of 64", cs, n)); return; }
+            const long long kt = static_cast<long long>(T) * n;
+            act_t* wt = static_cast<act_t*>(tpack.take(sizeof(act_t) * static_cast<size_t>(cs) * kt));
+            act_t* tmp = acc ? static_cast<act_t*>(bscratch.take(sizeof(act_t) * static_cast<size_t>(tokens) * cs)) : nullptr;
+            if (emitting()) {
+                const float* w32p = pf(sg->w);
+                const int Co = n;
+                plan->tpack_ops.push_back([=](cudaStream_t st) { return launch_pack_weight_t(w32p, wt, Co, Ci, T, c_lo, cs, kt, 0, st); });
+                GemmProblem pr;
+                pr.g = op.g;
+                pr.n_src = 1; pr.src[0] = dy; pr.src_c[0] = n;
+                pr.n_taps = static_cast<int>(op.taps.size());
+                for (size_t t = 0; t < op.taps.size(); ++t) for (int j = 0; j < 3; ++j) pr.taps[t][j] = -op.taps[t][j];
+                pr.w = wt; pr.bias = plan->zero_bias; pr.n = cs; pr.bn = pick_bn(cs);
+                {
+                    long long mt = 1;
+                    for (int i = 0; i < 4; ++i) mt *= (op.g.dims[i] + op.g.box[i] - 1) / op.g.box[i];
+                    if (wide_n && pr.bn == 128 && cs % 256 == 0 && mt * (cs / 256) >= 2LL * num_sms()) pr.bn = 256;
+                }
+                pr.out = acc ? tmp : gx;
+                auto gp = std::make_shared<GemmParams>();
+                int r = build_gemm(pr, gp.get());
+                if (r != MMD_OK) { set_err(r); return; }
+                const int bn = pr.bn;
+                const long long elems = tokens * cs;
+                bpush([=](cudaStream_t st) -> int {
+                    MMD_TRY(launch_gemm(*gp, bn, st));
+                    pdl_break(st);
+                    if (acc) return launch_grad_add(tmp, gx, elems, 1, st);
+                    return MMD_OK;
+                });
+            }
+        }
+        release_b(bmark);
+    }
+    void release_b(size_t mark) { bscratch.top = mark; }
+
+    void bwd_gn(const TapeOp& op) {
+        const int C = op.c1 + op.c2;
+        act_t* dy = need_grad(op.y, "group_norm");
+        if (!dy) return;
+        const size_t per = static_cast<size_t>(op.ns) * op.rows;
+        act_t* g1 = grad_buf(op.x1, per * op.c1);
+        const bool a1 = grad_written(op.x1);
+        mark_written(op.x1);
+        act_t* g2 = nullptr;
+        bool a2 = false;
+        if (op.x2) { g2 = grad_buf(op.x2, per * op.c2); a2 = grad_written(op.x2); mark_written(op.x2); }
+        const size_t bmark = bscratch.top;
+        const size_t t_bytes = sizeof(float) * 2 * C * op.ns;
+        float* T = static_cast<float*>(bscratch.take(t_bytes));
+        if (emitting()) {
+            GnBwdProblem pr;
+            pr.s = GnSrc{op.x1, op.c1, op.c1, op.x2, op.c2, op.c2};
+            pr.ns = op.ns; pr.rows = op.rows; pr.sums = op.sums; pr.nsub = op.nsub; pr.stat_rows = op.stat_rows;
+            pr.gamma = pf(op.gn_g); pr.beta = pf(op.gn_b);
+            pr.film = op.emb_row0 >= 0 ? emb_all + op.emb_row0 : nullptr;
+            pr.film_ld = m.emb_rows; pr.ns_per_batch = op.ns_per_batch; pr.silu = op.silu;
+            pr.dy = dy; pr.T = T;
+            pr.out = GnBwdOut{g1, op.c1, a1 ? 1 : 0, g2, op.c2, a2 ? 1 : 0};
+            pr.dgamma = g32_of(op.gn_g); pr.dbeta = g32_of(op.gn_b);
+            pr.dfilm = op.emb_row0 >= 0 ? plan->d_emb_all + op.emb_row0 : nullptr;
+            pr.gscale = plan->gscale;
+            bpush([=](cudaStream_t st) -> int {
+                MMD_CUDA_OK(cudaMemsetAsync(T, 0, t_bytes, st));
+                return launch_gn_bwd(pr, st);
+            });
+        }
+        release_b(bmark);
+    }
+
+    void bwd_gn_temporal(const TapeOp& op) {
+        act_t* dy = need_grad(op.y, "temporal group_norm");
+        if (!dy) return;
+        const size_t elems = static_cast<size_t>(op.B) * op.F * op.P * op.C;
+        act_t* gx = grad_buf(op.in, elems);
+        const bool acc = grad_written(op.in);
+        mark_written(op.in);
+        const size_t bmark = bscratch.top;
+        act_t* tmp = acc ? static_cast<act_t*>(bscratch.take(elems * sizeof(act_t))) : nullptr;
+        if (emitting()) {
+            const act_t* x = op.in;
+            const float* gamma = pf(op.gn_g);
+            float* dg = g32_of(op.gn_g);
+            float* db = g32_of(op.gn_b);
+            const float* gs = plan->gscale;
+            const int Bc = op.B, Fc = op.F, P = op.P, C = op.C;
+            bpush([=](cudaStream_t st) -> int {
+                MMD_TRY(launch_gn_temporal_bwd(x, dy, acc ? tmp : gx, gamma, dg, db, Bc, Fc, P, C, gs, st));
+                if (acc) return launch_grad_add(tmp, gx, static_cast<long long>(elems), 1, st);
+                return MMD_OK;
+            });
+        }
+        release_b(bmark);
+    }
+
+    void bwd_tattn(const TapeOp& op) {
+        act_t* d_out = need_grad(op.y, "temporal attention");
+        if (!d_out) return;
+        const size_t tokens = static_cast<size_t>(op.B) * op.F * op.P;
+        act_t* dqkv = grad_buf(op.in, tokens * 3 * op.C);
+        if (grad_written(op.in)) { set_err(fail(MMD_ESTATE, "internal: qkv gradient already written")); return; }
+        mark_written(op.in);
+        if (!emitting()) return;
+        const act_t* qkv = op.in;
+        const int Bc = op.B, Fc = op.F, P = op.P, C = op.C, heads = op.heads;
+        bpush([=](cudaStream_t st) { return launch_temporal_attn_bwd(qkv, d_out, dqkv, Bc, Fc, P, C, heads, st); });
+    }
+
+    void bwd_attn(const TapeOp& op) {
+        const AttnProblem& ap = op.ap;
+        act_t* d_out = need_grad(ap.out, "attention");
+        if (!d_out) return;
+        const int C = ap.heads * ap.d;
+        act_t* gq = grad_buf(ap.q, static_cast<size_t>(ap.q_rows) * ap.q_ld);
+        act_t* gk = grad_buf(ap.k, static_cast<size_t>(ap.k_rows) * ap.k_ld);
+        mark_written(ap.q);
+        mark_written(ap.k);
+        const size_t bmark = bscratch.top;
+        float* delta = static_cast<float*>(bscratch.take(sizeof(float) * ap.heads * (ap.q_rows + 128)));
+        if (emitting()) {
+            auto pq = std::make_shared<AttnBwdParams>();
+            auto pkv = std::make_shared<AttnBwdParams>();
+            AttnBwdOut o{gq, ap.q_ld, ap.q_col0, gk, ap.k_ld, ap.k_col0, gk, ap.k_ld, ap.v_col0};
+            int r = build_attn_bwd(ap, d_out, C, op.lse, delta, ap.q_rows, o, pq.get(), pkv.get());
+            if (r != MMD_OK) { set_err(r); return; }
+            const act_t* out = ap.out;
+            const long long q_rows = ap.q_rows;
+            const int heads = ap.heads, d = ap.d;
+            bpush([=](cudaStream_t st) -> int {
+                MMD_TRY(launch_attn_delta(d_out, out, q_rows, C, heads, delta, q_rows, st));
+                return launch_attn_bwd(*pq, *pkv, d, st);
+            });
+        }
+        release_b(bmark);
+    }
+
+    void bwd_resample(const TapeOp& op) {
+        act_t* dy = need_grad(op.y, "resample");
+        if (!dy) return;
+        const size_t in_elems = (op.mode == 0 || op.mode == 2) ? static_cast<size_t>(op.n_) * op.h_ * op.w_ * op.C
+                                                                : static_cast<size_t>(op.n_) * op.h_ * op.C;
+        act_t* gx = grad_buf(op.in, in_elems);
+        const bool acc = grad_written(op.in);
+        mark_written(op.in);
+        if (!emitting()) return;
+        const int mode = op.mode, n = op.n_, h = op.h_, w = op.w_, c = op.C;
+        bpush([=](cudaStream_t st) { return launch_resample_bwd(dy, gx, mode, n, h, w, c, acc ? 1 : 0, st); });
+    }
+
+    void emit_backward() {
+        if (bad()) return;
+        for (auto it = tape.rbegin(); it != tape.rend() && !bad(); ++it) {
+            switch (it->kind) {
+                case TapeOp::GEMM: bwd_gemm(*it); break;
+                case TapeOp::GN: bwd_gn(*it); break;
+                case TapeOp::GN_TEMPORAL: bwd_gn_temporal(*it); break;
+                case TapeOp::TATTN: bwd_tattn(*it); break;
+                case TapeOp::ATTN: bwd_attn(*it); break;
+                case TapeOp::RESAMPLE: bwd_resample(*it); break;
+            }
+        }
+        if (bad()) return;
+        // ---- FiLM table -> emb_layers -> time_embed MLP (all fp32)
+        const int E = cfg().model_channels, rows = m.emb_rows;
+        const size_t bmark = bscratch.top;
+        float* dw_stack = static_cast<float*>(bscratch.take(sizeof(float) * (static_cast<size_t>(rows) * E + rows)));
+        float* dsilu = static_cast<float*>(bscratch.take(sizeof(float) * B * E));
+        float* te_scratch = static_cast<float*>(bscratch.take(sizeof(float) * B * 4 * E));
+        if (emitting()) {
+            const float* demb = plan->d_emb_all;
+            const float* se = silu_emb;
+            const float* ew = m.bpk + m.emb_w_off;
+            const float* gs = plan->gscale;
+            const int Bc = B;
+            float* db_stack = dw_stack + static_cast<size_t>(rows) * E;
+            std::vector<EmbBlk> blks = emb_blocks;
+            std::vector<float*> gw, gb;
+            for (auto& eb : blks) { gw.push_back(g32_of(eb.w)); gb.push_back(g32_of(eb.b)); }
+            const float *w1 = pf(te_idx[0]), *b1 = pf(te_idx[1]), *w2 = pf(te_idx[2]), *b2 = pf(te_idx[3]);
+            float *dw1 = g32_of(te_idx[0]), *db1 = g32_of(te_idx[1]), *dw2 = g32_of(te_idx[2]), *db2 = g32_of(te_idx[3]);
+            const float* tdev = plan->t_dev;
+            bpush([=](cudaStream_t st) -> int {
+                MMD_CUDA_OK(cudaMemsetAsync(dw_stack, 0, sizeof(float) * (static_cast<size_t>(rows) * E + rows), st));
+                const long long tot = static_cast<long long>(rows) * E;
+                emb_layers_bwd_w_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, st>>>(demb, se, Bc, E, rows, dw_stack, db_stack, gs);
+                MMD_CUDA_OK(cudaGetLastError());
+                for (size_t i = 0; i < blks.size(); ++i) {
+                    const long long nw = static_cast<long long>(blks[i].rows) * E;
+                    axpy_f32_kernel<<<static_cast<unsigned>((nw + 255) / 256), 256, 0, st>>>(dw_stack + static_cast<size_t>(blks[i].row0) * E, gw[i], nw, nullptr);
+                    axpy_f32_kernel<<<(blks[i].rows + 255) / 256, 256, 0, st>>>(db_stack + blks[i].row0, gb[i], blks[i].rows, nullptr);
+                }
+                MMD_CUDA_OK(cudaGetLastError());
+                emb_layers_bwd_x_kernel<<<dim3((E + 31) / 32, Bc), 256, 0, st>>>(demb, ew, E, rows, dsilu);
+                MMD_CUDA_OK(cudaGetLastError());
+                time_embed_bwd_kernel<<<Bc, E, 4 * E * sizeof(float), st>>>(tdev, w1, b1, w2, b2, E, dsilu, te_scratch);
+                MMD_CUDA_OK(cudaGetLastError());
+                time_embed_bwd_reduce_kernel<<<(E * E + 255) / 256, 256, 0, st>>>(te_scratch, Bc, E, dw1, db1, dw2, db2, gs);
+                MMD_CUDA_OK(cudaGetLastError());
+                return MMD_OK;
+            });
+        }
+        release_b(bmark);
     }
 };
 
@@ -963,6 +1471,103 @@ static int build_plan(MmdModel* m, int B, Plan** out) {
     return MMD_OK;
 }
 
+
+// Training plan: same topology walk with nothing recycled, plus the backward launch list built from the tape.
+static int build_train_plan(MmdModel* m, int B, Plan** out) {
+    auto it = m->train_plans.find(B);
+    if (it != m->train_plans.end()) { *out = it->second.get(); return MMD_OK; }
+    if (B < 1 || B > m->cfg.max_batch) return fail(MMD_EINVAL, "batch %d outside [1, %d]", B, m->cfg.max_batch);
+    const MmdConfig& c = m->cfg;
+    Walker dry(*m, false);
+    dry.B = B;
+    dry.train = true;
+    dry.walk();
+    dry.emit_backward();
+    if (dry.bad()) return dry.err;
+    auto plan = std::make_unique<Plan>();
+    plan->B = B;
+    plan->train = true;
+    const size_t vin = sizeof(float) * B * c.video_f * c.video_c * c.video_h * c.video_w;
+    const size_t ain = sizeof(float) * B * c.audio_c * c.audio_l;
+    const size_t vout = sizeof(float) * B * c.video_f * c.video_out_channels * c.video_h * c.video_w;
+    const size_t aout = sizeof(float) * B * c.audio_out_channels * c.audio_l;
+    auto al = [](size_t x) { return (x + 1023) & ~size_t(1023); };
+    const size_t g32_bytes = al(sizeof(float) * std::max<size_t>(m->w32_floats, 4));
+    const size_t demb_bytes = al(sizeof(float) * B * std::max(m->emb_rows, 1));
+    const size_t zb_bytes = al(sizeof(float) * 4096);
+    const size_t io_bytes = 2 * (al(vin) + al(ain) + al(vout) + al(aout)) + al(sizeof(float) * B) + al(sizeof(int) * 64) + 1024 +
+                            g32_bytes + demb_bytes + zb_bytes;
+    const size_t p_bytes = al(dry.persist.peak) + 1024, s_bytes = al(dry.scratch.peak) + 1024;
+    const size_t sa_bytes = al(dry.scratch_a.peak) + 1024, st_bytes = al(dry.stats.peak) + 1024;
+    const size_t g_bytes = al(dry.grads.peak) + 1024, b_bytes = al(dry.bscratch.peak) + 1024;
+    const size_t t_bytes = al(dry.tpack.peak) + 1024;
+    plan->ws_bytes = io_bytes + p_bytes + s_bytes + sa_bytes + st_bytes + g_bytes + b_bytes;
+    MMD_CUDA_OK(cudaMalloc(&plan->ws, plan->ws_bytes));
+    MMD_CUDA_OK(cudaMemset(plan->ws, 0, plan->ws_bytes));
+    MMD_CUDA_OK(cudaMalloc(&plan->wpk_t, t_bytes));
+    MMD_CUDA_OK(cudaMemset(plan->wpk_t, 0, t_bytes));
+    uint8_t* q = plan->ws;
+    plan->in_video = reinterpret_cast<float*>(q); q += al(vin);
+    plan->in_audio = reinterpret_cast<float*>(q); q += al(ain);
+    plan->out_video = reinterpret_cast<float*>(q); q += al(vout);
+    plan->out_audio = reinterpret_cast<float*>(q); q += al(aout);
+    plan->d_in_video = reinterpret_cast<float*>(q); q += al(vin);
+    plan->d_in_audio = reinterpret_cast<float*>(q); q += al(ain);
+    plan->d_out_video = reinterpret_cast<float*>(q); q += al(vout);
+    plan->d_out_audio = reinterpret_cast<float*>(q); q += al(aout);
+    plan->t_dev = reinterpret_cast<float*>(q); q += al(sizeof(float) * B);
+    plan->shifts_dev = reinterpret_cast<int*>(q); q += al(sizeof(int) * 64);
+    plan->gscale = reinterpret_cast<float*>(q);
+    plan->amax_bits = reinterpret_cast<unsigned int*>(q + 64); q += 1024;
+    plan->g32 = reinterpret_cast<float*>(q); q += g32_bytes;
+    plan->d_emb_all = reinterpret_cast<float*>(q); q += demb_bytes;
+    plan->zero_bias = reinterpret_cast<float*>(q); q += zb_bytes;
+    Walker w(*m, false);
+    w.B = B;
+    w.train = true;
+    w.plan = plan.get();
+    w.persist.base = q; w.persist.cap = p_bytes; q += p_bytes;
+    w.scratch.base = q; w.scratch.cap = s_bytes; q += s_bytes;
+    w.scratch_a.base = q; w.scratch_a.cap = sa_bytes; q += sa_bytes;
+    w.stats.base = q; w.stats.cap = st_bytes; q += st_bytes;
+    w.grads.base = q; w.grads.cap = g_bytes; q += g_bytes;
+    w.bscratch.base = q; w.bscratch.cap = b_bytes; q += b_bytes;
+    w.tpack.base = reinterpret_cast<uint8_t*>(plan->wpk_t); w.tpack.cap = t_bytes;
+    w.walk();
+    w.emit_backward();
+    if (w.bad()) return w.err;
+    if (w.persist.peak > p_bytes || w.scratch.peak > s_bytes || w.scratch_a.peak > sa_bytes || w.stats.peak > st_bytes ||
+        w.grads.peak > g_bytes || w.bscratch.peak > b_bytes || w.tpack.peak > t_bytes)
+        return fail(MMD_ESTATE, "internal: training arena overflow");
+    *out = plan.get();
+    m->train_plans[B] = std::move(plan);
+    return MMD_OK;
+}
+
+static int stage_inputs(MmdModel* m, Plan* plan, int batch, const float* video_in, const float* audio_in, const float* timesteps,
+                        const int32_t* shifts, cudaStream_t st) {
+    const MmdConfig& c = m->cfg;
+    const size_t vin = sizeof(float) * batch * c.video_f * c.video_c * c.video_h * c.video_w;
+    const size_t ain = sizeof(float) * batch * c.audio_c * c.audio_l;
+    MMD_CUDA_OK(cudaMemcpyAsync(plan->in_video, video_in, vin, cudaMemcpyDeviceToDevice, st));
+    MMD_CUDA_OK(cudaMemcpyAsync(plan->in_audio, audio_in, ain, cudaMemcpyDeviceToDevice, st));
+    MMD_CUDA_OK(cudaMemcpyAsync(plan->t_dev, timesteps, sizeof(float) * batch, cudaMemcpyDeviceToDevice, st));
+    ShiftArgs sa{};
+    sa.n = static_cast<int>(m->shift_bounds.size());
+    for (int i = 0; i < sa.n; ++i) {
+        int v = shifts ? shifts[i] : 0;
+        const int hi = m->shift_bounds[i];
+        if (hi < 0) v = 0;
+        else if (v < 0 || v > hi) return fail(MMD_EINVAL, "shift %d of block %d outside [0, %d]", v, i, hi);
+        sa.v[i] = v;
+    }
+    if (sa.n > 0) {
+        set_shifts_kernel<<<1, 64, 0, st>>>(sa, plan->shifts_dev);
+        MMD_CUDA_OK(cudaGetLastError());
+    }
+    return MMD_OK;
+}
+
 static size_t dry_workspace(MmdModel* m, int B) {
     Walker dry(*m, false);
     dry.B = B;
@@ -1040,6 +1645,20 @@ int mmd_model_shift_bound(const MmdModel* m, int index) {
 size_t mmd_model_workspace_bytes(const MmdModel* m, int batch) {
     if (!m) return 0;
     return dry_workspace(const_cast<MmdModel*>(m), batch);
+}
+
+/* Device bytes of a training plan (kept activations + activation gradients + backward temporaries + transposed weight
+ * packs); host-only dry run of the forward walk AND the backward tape, 0 on error (see mmd_last_error). */
+size_t mmd_model_train_workspace_bytes(const MmdModel* m, int batch) {
+    if (!m) return 0;
+    Walker dry(*const_cast<MmdModel*>(m), false);
+    dry.B = batch;
+    dry.train = true;
+    dry.walk();
+    dry.emit_backward();
+    if (dry.bad()) return 0;
+    return dry.persist.peak + dry.scratch.peak + dry.scratch_a.peak + dry.stats.peak + dry.grads.peak + dry.bscratch.peak +
+           dry.tpack.peak + sizeof(float) * m->w32_floats + (1 << 20);
 }
 
 int mmd_model_num_launches(const MmdModel* m, int batch) {
@@ -1187,6 +1806,83 @@ int mmd_model_forward(MmdModel* m, int batch, const float* video_in, const float
     MMD_CUDA_OK(cudaMemcpyAsync(video_out, plan->out_video, vout, cudaMemcpyDeviceToDevice, st));
     MMD_CUDA_OK(cudaMemcpyAsync(audio_out, plan->out_audio, aout, cudaMemcpyDeviceToDevice, st));
     return MMD_OK;
+}
+
+// ---- training: forward that keeps every intermediate + backward ----
+int mmd_model_forward_train(MmdModel* m, int batch, const float* video_in, const float* audio_in, const float* timesteps,
+                            const int32_t* shifts, float* video_out, float* audio_out, void* stream) {
+    if (!m || !video_in || !audio_in || !timesteps || !video_out || !audio_out) return fail(MMD_EINVAL, "null argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MMD_TRY(ensure_device(m));
+    for (auto& p : m->params)
+        if (!p.set) return fail(MMD_ESTATE, "parameter %s was never set", p.name.c_str());
+    if (m->dirty) {
+        for (auto& op : m->pack_ops) MMD_TRY(op(st));
+        m->dirty = false;
+        for (auto& tp : m->train_plans) tp.second->tpack_dirty = true;
+    }
+    Plan* plan = nullptr;
+    MMD_TRY(build_train_plan(m, batch, &plan));
+    MMD_TRY(stage_inputs(m, plan, batch, video_in, audio_in, timesteps, shifts, st));
+    {
+        PdlScope pdl(st, nullptr);
+        for (auto& step : plan->steps) MMD_TRY(step(st));
+    }
+    const MmdConfig& c = m->cfg;
+    const size_t vout = sizeof(float) * batch * c.video_f * c.video_out_channels * c.video_h * c.video_w;
+    const size_t aout = sizeof(float) * batch * c.audio_out_channels * c.audio_l;
+    MMD_CUDA_OK(cudaMemcpyAsync(video_out, plan->out_video, vout, cudaMemcpyDeviceToDevice, st));
+    MMD_CUDA_OK(cudaMemcpyAsync(audio_out, plan->out_audio, aout, cudaMemcpyDeviceToDevice, st));
+    plan->fwd_done = true;
+    return MMD_OK;
+}
+
+int mmd_model_backward(MmdModel* m, int batch, const float* d_video_out, const float* d_audio_out, float* param_grads,
+                       float* d_video_in, float* d_audio_in, void* stream) {
+    if (!m || !d_video_out || !d_audio_out) return fail(MMD_EINVAL, "null argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    auto it = m->train_plans.find(batch);
+    if (it == m->train_plans.end() || !it->second->fwd_done)
+        return fail(MMD_ESTATE, "mmd_model_backward: no mmd_model_forward_train at batch %d precedes this call", batch);
+    Plan* plan = it->second.get();
+    const MmdConfig& c = m->cfg;
+    const long long vout_n = static_cast<long long>(batch) * c.video_f * c.video_out_channels * c.video_h * c.video_w;
+    const long long aout_n = static_cast<long long>(batch) * c.audio_out_channels * c.audio_l;
+    const size_t vin = sizeof(float) * batch * c.video_f * c.video_c * c.video_h * c.video_w;
+    const size_t ain = sizeof(float) * batch * c.audio_c * c.audio_l;
+    MMD_CUDA_OK(cudaMemcpyAsync(plan->d_out_video, d_video_out, sizeof(float) * vout_n, cudaMemcpyDeviceToDevice, st));
+    MMD_CUDA_OK(cudaMemcpyAsync(plan->d_out_audio, d_audio_out, sizeof(float) * aout_n, cudaMemcpyDeviceToDevice, st));
+    MMD_CUDA_OK(cudaMemsetAsync(plan->amax_bits, 0, sizeof(unsigned int), st));
+    MMD_CUDA_OK(cudaMemsetAsync(plan->g32, 0, sizeof(float) * m->w32_floats, st));
+    MMD_CUDA_OK(cudaMemsetAsync(plan->d_emb_all, 0, sizeof(float) * batch * std::max(m->emb_rows, 1), st));
+    const int blocks = 2 * num_sms();
+    absmax_kernel<<<blocks, 256, 0, st>>>(plan->d_out_video, vout_n, plan->amax_bits);
+    absmax_kernel<<<blocks, 256, 0, st>>>(plan->d_out_audio, aout_n, plan->amax_bits);
+    make_gscale_kernel<<<1, 1, 0, st>>>(plan->amax_bits, plan->gscale);
+    MMD_CUDA_OK(cudaGetLastError());
+    if (plan->tpack_dirty) {
+        for (auto& op : plan->tpack_ops) MMD_TRY(op(st));
+        plan->tpack_dirty = false;
+    }
+    for (auto& step : plan->bwd_steps) MMD_TRY(step(st));
+    if (param_grads)
+        MMD_CUDA_OK(cudaMemcpyAsync(param_grads, plan->g32, sizeof(float) * m->w32_floats, cudaMemcpyDeviceToDevice, st));
+    if (d_video_in) MMD_CUDA_OK(cudaMemcpyAsync(d_video_in, plan->d_in_video, vin, cudaMemcpyDeviceToDevice, st));
+    if (d_audio_in) MMD_CUDA_OK(cudaMemcpyAsync(d_audio_in, plan->d_in_audio, ain, cudaMemcpyDeviceToDevice, st));
+    plan->fwd_done = false;
+    return MMD_OK;
+}
+
+/* Offset (in floats) of parameter `index` inside the flat gradient buffer of mmd_model_backward, and its total length. */
+int64_t mmd_model_param_offset(const MmdModel* m, int index) {
+    if (!m || index < 0 || index >= static_cast<int>(m->params.size())) return -1;
+    return static_cast<int64_t>(m->params[index].offset);
+}
+int64_t mmd_model_param_floats(const MmdModel* m) { return m ? static_cast<int64_t>(m->w32_floats) : 0; }
+int mmd_model_num_backward_launches(const MmdModel* m, int batch) {
+    if (!m) return 0;
+    auto it = m->train_plans.find(batch);
+    return it == m->train_plans.end() ? 0 : static_cast<int>(it->second->bwd_steps.size());
 }
 
 }  // extern "C"

@@ -189,6 +189,8 @@ class GaussianDiffusion:
         return out
 
     def _fusable(self, x, denoised_fn, cond_fn):
+        if th.is_grad_enabled() and (x["video"].requires_grad or x["audio"].requires_grad):
+            return False   # gradient-guided sampling differentiates through the tail: generic torch statement
         return (denoised_fn is None and cond_fn is None and self.model_mean_type == ModelMeanType.EPSILON and
                 x["video"].is_cuda and x["video"].dtype == th.float32 and x["audio"].dtype == th.float32)
 
@@ -227,7 +229,10 @@ class GaussianDiffusion:
     def _p_sample_generic(self, model, x, t, clip_denoised, denoised_fn, cond_fn, model_kwargs, noise):
         out = self.p_mean_variance(model, x, t, clip_denoised=clip_denoised, denoised_fn=denoised_fn,
                                    model_kwargs=model_kwargs)
-        zv, za = th.randn_like(x["video"]), th.randn_like(x["audio"])
+        if isinstance(noise, dict) and "video" in noise and noise["video"].shape == x["video"].shape:
+            zv, za = noise["video"], noise["audio"]
+        else:
+            zv, za = th.randn_like(x["video"]), th.randn_like(x["audio"])
         if cond_fn is not None:
             raise NotImplementedError("cond_fn guidance is not part of the multimodal scripts")
         res = {"sample": {}, "pred_start": out["pred_xstart"], "pred_noise": out["model_predict"]}
@@ -273,12 +278,12 @@ class GaussianDiffusion:
     # ------------------------------------------------------------------ zero-shot conditional sampling
     def conditional_p_sample_loop(self, model, shape, use_fp16, noise=None, clip_denoised=True, denoised_fn=None,
                                   cond_fn=None, model_kwargs=None, device=None, progress=True, class_scale=0.0):
-        """Reference :584-639.  class_scale == 0 -> replacement method (:642-720); class_scale > 0 (gradient
-        guidance, :722-819) needs d(model)/d(input) and is not available on the sm_100a path yet."""
-        if class_scale != 0:
-            raise NotImplementedError("gradient-guided conditional sampling needs the backward kernels (DESIGN.md, next)")
+        """Reference :584-639.  class_scale == 0 -> replacement method (:642-720); class_scale > 0 -> gradient
+        guidance (:722-819), which backpropagates through the model to the target modality's input."""
         final = None
-        for sample in self.conditional_p_sample_loop_progressive_unscale(
+        loop = self.conditional_p_sample_loop_progressive_unscale if class_scale == 0 else \
+            self.conditional_p_sample_loop_progressive_scale
+        for sample in loop(
                 model, shape, use_fp16, noise=noise, clip_denoised=clip_denoised, denoised_fn=denoised_fn,
                 cond_fn=cond_fn, model_kwargs=model_kwargs, device=device, progress=progress, class_scale=class_scale):
             final = sample
@@ -308,6 +313,50 @@ class GaussianDiffusion:
                                     model_kwargs=model_kwargs)
                 yield out["sample"]
                 x = out["sample"]
+
+    def conditional_p_sample_loop_progressive_scale(self, model, shape, use_fp16, noise=None, clip_denoised=True,
+                                                    denoised_fn=None, cond_fn=None, model_kwargs=None, device=None,
+                                                    progress=False, class_scale=3.0):
+        """Gradient-guided zero-shot conditional sampling (reference :722-819): each step overwrites the conditioned
+        modality with q(x_t | condition) under the fixed noise, takes one ancestral step with the target modality's
+        input requiring grad, and moves the target by -class_scale * sqrt(alpha_bar_i) * d/dx_target of the MSE between
+        the predicted and the true x_{t-1} of the conditioned modality.  Quirks kept: the 2^20 loss scale of the fp16
+        path is not divided out again (:813-816), and t - 1 wraps to the last table entry at t = 0 (masked anyway)."""
+        if device is None:
+            device = _default_device()
+        if noise is None:
+            noise = self._initial_noise(shape, device)
+        x = dict(noise)
+        model_kwargs = model_kwargs if model_kwargs is not None else {}
+        cond = {k: model_kwargs.pop(k) for k in ("video", "audio") if k in model_kwargs}
+        if len(cond) != 1:
+            raise ValueError("gradient-guided sampling needs exactly one of model_kwargs['video'] / ['audio'] as the condition")
+        condition = next(iter(cond))
+        target = "audio" if condition == "video" else "video"
+        c = cond[condition].to(device=device, dtype=th.float32)
+        indices = list(range(self.num_timesteps))[::-1]
+        if progress:
+            from tqdm.auto import tqdm
+            indices = tqdm(indices)
+        B = shape["video"][0]
+        sqrt_ab = np.sqrt(self.alphas_cumprod)
+        for i in indices:
+            t = th.full((B,), i, device=device, dtype=th.long)
+            with th.no_grad():
+                x[condition] = self.q_sample(c, t, noise=noise[condition])
+                prev_cond = self.q_sample(c, (t - 1) % self.num_timesteps, noise=noise[condition])
+            with th.enable_grad():
+                nzm = (t != 0).float().reshape(-1, *([1] * (x[target].dim() - 1)))
+                x[target] = x[target].detach().requires_grad_()
+                out = self.p_sample(model, x, t, clip_denoised=clip_denoised, denoised_fn=denoised_fn, cond_fn=cond_fn,
+                                    model_kwargs=model_kwargs)
+                pred = out["sample"]
+                loss = mean_flat((pred[condition] - prev_cond) ** 2)
+                loss_scale = float(2 ** 20) if use_fp16 else 1.0
+                grad = th.autograd.grad(loss.mean() * loss_scale, x[target])[0]
+                x = {condition: pred[condition].detach(),
+                     target: (pred[target] - nzm * grad * class_scale * float(sqrt_ab[i])).detach()}
+            yield x
 
     # ------------------------------------------------------------------ DDIM
     def ddim_sample(self, model, x, t, clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=None, eta=0.0):
@@ -346,8 +395,8 @@ class GaussianDiffusion:
 
     # ------------------------------------------------------------------ training objective
     def multimodal_training_losses(self, model, x_start, t, model_kwargs=None, noise=None):
-        """eps-MSE per modality (reference :1114-1203): {"loss","mse_video","mse_audio"} of shape [N].
-        Forward only on the sm_100a path for now (the model raises under autograd)."""
+        """eps-MSE per modality (reference :1114-1203): {"loss","mse_video","mse_audio"} of shape [N]; differentiable
+        wrt the model parameters through the sm_100a backward (unet._UNetFunction)."""
         model_kwargs = model_kwargs or {}
         if noise is None:
             noise = {"video": th.randn_like(x_start["video"]), "audio": th.randn_like(x_start["audio"])}

@@ -192,3 +192,158 @@ def temporal_attention(qkv, heads):
     out = torch.empty((B, F, P, Cc), dtype=torch.float16, device=qkv.device)
     check(lib.mmd_op_temporal_attention(qkv.data_ptr(), out.data_ptr(), B, F, P, Cc, heads, current_stream_ptr()))
     return out
+
+
+# --------------------------------------------------------------------------- backward operators (training)
+def _conv_desc(srcs, n, rank, dims, taps, weight=None, out_f32_strides=None, ostride_c=0):
+    d = MmdConvDesc()
+    d.rank = rank
+    for i in range(4):
+        d.dims[i] = dims[i] if i < len(dims) else 1
+        d.box[i] = 0
+    d.n_src = len(srcs)
+    for i, s in enumerate(srcs):
+        assert s.dtype == torch.float16 and s.is_contiguous() and s.is_cuda
+        d.src[i] = s.data_ptr()
+        d.src_channels[i] = s.shape[-1]
+    d.n_taps = len(taps)
+    for t, tp in enumerate(taps):
+        for j in range(3):
+            d.taps[t][j] = int(tp[j])
+    d.n = n
+    if weight is not None:
+        d.weight = weight.data_ptr()
+    if out_f32_strides is not None:
+        for i in range(4):
+            d.ostride[i] = out_f32_strides[i] if i < len(out_f32_strides) else 0
+    d.ostride_c = ostride_c
+    return d
+
+
+def conv_wgrad(srcs, dy, rank, dims, taps):
+    """Weight / bias gradient of a conv over channels-last fp16 sources: returns (dW fp32 [n, c_total, n_taps], db [n])."""
+    lib = _lib.load()
+    n = dy.shape[-1]
+    ctot = sum(s.shape[-1] for s in srcs)
+    dw = torch.zeros((n, ctot, len(taps)), dtype=torch.float32, device=dy.device)
+    db = torch.zeros((n,), dtype=torch.float32, device=dy.device)
+    d = _conv_desc(srcs, n, rank, dims, taps)
+    check(lib.mmd_op_conv_wgrad(C.byref(d), dy.data_ptr(), dw.data_ptr(), db.data_ptr(), current_stream_ptr()))
+    return dw, db
+
+
+def conv_dgrad(src_channels, dy, weight, rank, dims, taps, src_index=0):
+    """Data gradient wrt source `src_index`: weight fp32 [n, c_total, n_taps]; returns fp16 [..., c_src]."""
+    lib = _lib.load()
+    n = dy.shape[-1]
+    w = weight.detach().to(torch.float32).contiguous()
+    d = MmdConvDesc()
+    d.rank = rank
+    for i in range(4):
+        d.dims[i] = dims[i] if i < len(dims) else 1
+        d.box[i] = 0
+    d.n_src = len(src_channels)
+    for i, c in enumerate(src_channels):
+        d.src_channels[i] = c
+    d.n_taps = len(taps)
+    for t, tp in enumerate(taps):
+        for j in range(3):
+            d.taps[t][j] = int(tp[j])
+    d.n = n
+    d.weight = w.data_ptr()
+    dx = torch.empty(dy.shape[:-1] + (src_channels[src_index],), dtype=torch.float16, device=dy.device)
+    check(lib.mmd_op_conv_dgrad(C.byref(d), dy.data_ptr(), src_index, dx.data_ptr(), current_stream_ptr()))
+    return dx
+
+
+def group_norm_bwd(x, gamma, beta, ns, dy, x2=None, film=None, ns_per_batch=1, silu=False):
+    """Backward of group_norm(): returns (dx, dx2 | None, dgamma, dbeta, dfilm | None)."""
+    lib = _lib.load()
+    c1 = x.shape[-1]
+    c2 = 0 if x2 is None else x2.shape[-1]
+    Cc = c1 + c2
+    rows = (x.numel() // c1) // ns
+    g = gamma.detach().float().contiguous()
+    b = beta.detach().float().contiguous()
+    f = None if film is None else film.detach().float().contiguous()
+    dx = torch.empty_like(x)
+    dx2 = None if x2 is None else torch.empty_like(x2)
+    dg = torch.zeros(Cc, dtype=torch.float32, device=x.device)
+    db = torch.zeros(Cc, dtype=torch.float32, device=x.device)
+    dfilm = None if f is None else torch.zeros_like(f)
+    check(lib.mmd_op_group_norm_bwd(x.data_ptr(), c1, ptr(x2), c2, ns, rows, g.data_ptr(), b.data_ptr(), ptr(f),
+                                    0 if f is None else f.shape[-1], ns_per_batch, int(silu), dy.data_ptr(), dx.data_ptr(),
+                                    ptr(dx2), dg.data_ptr(), db.data_ptr(), ptr(dfilm), current_stream_ptr()))
+    return dx, dx2, dg, db, dfilm
+
+
+def group_norm_temporal_bwd(x, gamma, dy):
+    lib = _lib.load()
+    B, F, P, Cc = x.shape
+    g = gamma.detach().float().contiguous()
+    dx = torch.empty_like(x)
+    dg = torch.zeros(Cc, dtype=torch.float32, device=x.device)
+    db = torch.zeros(Cc, dtype=torch.float32, device=x.device)
+    check(lib.mmd_op_group_norm_temporal_bwd(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), g.data_ptr(), dg.data_ptr(),
+                                             db.data_ptr(), B, F, P, Cc, current_stream_ptr()))
+    return dx, dg, db
+
+
+def resample_bwd(dy, mode, in_shape):
+    """Adjoint of resample(x, mode) for x of shape in_shape."""
+    lib = _lib.load()
+    if mode in ("vpool", "vup"):
+        N, H, W, Cc = in_shape
+        m = 0 if mode == "vpool" else 2
+    else:
+        N, H, Cc = in_shape
+        W = 1
+        m = 1 if mode == "apool" else 3
+    dx = torch.empty(in_shape, dtype=torch.float16, device=dy.device)
+    check(lib.mmd_op_resample_bwd(dy.data_ptr(), dx.data_ptr(), m, N, H, W, Cc, current_stream_ptr()))
+    return dx
+
+
+def temporal_attention_bwd(qkv, d_out, heads):
+    lib = _lib.load()
+    B, F, P, C3 = qkv.shape
+    dqkv = torch.empty_like(qkv)
+    check(lib.mmd_op_temporal_attention_bwd(qkv.data_ptr(), d_out.data_ptr(), dqkv.data_ptr(), B, F, P, C3 // 3, heads,
+                                            current_stream_ptr()))
+    return dqkv
+
+
+def attention_fwd_bwd(q_mat, k_mat, v_mat, q_col0, k_col0, v_col0, batch, heads, head_dim, n_blocks, q_blk, k_blk, d_out,
+                      win=1, shift=0):
+    """Forward + backward of attention(): returns (out, lse [heads, q_rows], dq [q_rows, C], dk [k_rows, C], dv [k_rows, C])."""
+    lib = _lib.load()
+    Cc = heads * head_dim
+    d = MmdAttnDesc()
+    d.q, d.q_ld, d.q_col0, d.q_rows = q_mat.data_ptr(), q_mat.shape[1], q_col0, q_mat.shape[0]
+    d.k, d.k_ld, d.k_col0, d.k_rows = k_mat.data_ptr(), k_mat.shape[1], k_col0, k_mat.shape[0]
+    d.v, d.v_ld, d.v_col0 = v_mat.data_ptr(), v_mat.shape[1], v_col0
+    out = torch.empty((q_mat.shape[0], Cc), dtype=torch.float16, device=q_mat.device)
+    d.out, d.out_ld = out.data_ptr(), Cc
+    d.batch, d.heads, d.head_dim = batch, heads, head_dim
+    d.n_blocks, d.q_blk, d.k_blk, d.win, d.shift = n_blocks, q_blk, k_blk, win, shift
+    lse = torch.zeros((heads, q_mat.shape[0]), dtype=torch.float32, device=q_mat.device)
+    dq = torch.zeros((q_mat.shape[0], Cc), dtype=torch.float16, device=q_mat.device)
+    dk = torch.zeros((k_mat.shape[0], Cc), dtype=torch.float16, device=q_mat.device)
+    dv = torch.zeros((k_mat.shape[0], Cc), dtype=torch.float16, device=q_mat.device)
+    # dq / dk / dv are separate matrices here (leading dimension C, column 0)
+    check(lib.mmd_op_attention_fwd_bwd(C.byref(d), d_out.data_ptr(), lse.data_ptr(), dq.data_ptr(), dk.data_ptr(),
+                                       dv.data_ptr(), Cc, 0, 0, 0, current_stream_ptr()))
+    return out, lse, dq, dk, dv
+
+
+def head_bwd(x, weight, dout, rank, dims, taps, ostride, ostride_c, need_dx=True):
+    """Adjoint of conv3d_head / conv1d_head: returns (dx fp16 | None, dW fp32 [n, C, taps], db [n])."""
+    lib = _lib.load()
+    n = weight.shape[0]
+    w = weight.detach().to(torch.float32).reshape(n, x.shape[-1], len(taps)).contiguous()
+    d = _conv_desc([x], n, rank, dims, taps, weight=w, out_f32_strides=ostride, ostride_c=ostride_c)
+    dx = torch.empty_like(x) if need_dx else None
+    dw = torch.zeros_like(w)
+    db = torch.zeros(n, dtype=torch.float32, device=x.device)
+    check(lib.mmd_op_head_bwd(C.byref(d), dout.data_ptr(), ptr(dx), dw.data_ptr(), db.data_ptr(), current_stream_ptr()))
+    return dx, dw, db

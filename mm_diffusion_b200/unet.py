@@ -67,6 +67,48 @@ class _Node(nn.Module):
     """Anonymous container used to rebuild the reference's dotted parameter names."""
 
 
+class _UNetFunction(torch.autograd.Function):
+    """MultimodalUNet.forward under autograd: forward = mmd_model_forward_train (every intermediate kept on the
+    device), backward = mmd_model_backward (hand-written sm_100a dgrad / wgrad / attention / GroupNorm adjoints).
+    Parameters are passed as inputs so their gradients flow through autograd into the same nn.Parameter objects
+    (DDP reducer hooks, MixedPrecisionTrainer and EMA of the reference's TrainLoop keep working)."""
+
+    @staticmethod
+    def forward(ctx, model, shifts, video, audio, timesteps, *params):
+        vo, ao = model._run(video, audio, timesteps, shifts, train=True)
+        ctx.model = model
+        ctx.batch = video.shape[0]
+        ctx.in_shapes = (tuple(video.shape), tuple(audio.shape))
+        ctx.need_inputs = (video.requires_grad, audio.requires_grad)
+        ctx.param_meta = [(p.requires_grad, tuple(p.shape)) for p in params]
+        return vo, ao
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d_vo, d_ao):
+        model = ctx.model
+        lib = _lib.load()
+        dev = model._handle_device
+        B = ctx.batch
+        with torch.cuda.device(dev):
+            vshape = (B, model._cfg.video_f, model.video_out_channels, model._cfg.video_h, model._cfg.video_w)
+            ashape = (B, model.audio_out_channels, model._cfg.audio_l)
+            d_vo = torch.zeros(vshape, dtype=torch.float32, device=dev) if d_vo is None else d_vo.to(torch.float32).contiguous()
+            d_ao = torch.zeros(ashape, dtype=torch.float32, device=dev) if d_ao is None else d_ao.to(torch.float32).contiguous()
+            flat = torch.empty(int(lib.mmd_model_param_floats(model._handle)), dtype=torch.float32, device=dev)
+            d_vi = torch.empty(ctx.in_shapes[0], dtype=torch.float32, device=dev) if ctx.need_inputs[0] else None
+            d_ai = torch.empty(ctx.in_shapes[1], dtype=torch.float32, device=dev) if ctx.need_inputs[1] else None
+            check(lib.mmd_model_backward(model._handle, B, d_vo.data_ptr(), d_ao.data_ptr(), flat.data_ptr(),
+                                         _lib.ptr(d_vi), _lib.ptr(d_ai), _lib.current_stream_ptr()))
+        grads = []
+        for (needs, shape), off in zip(ctx.param_meta, model._param_offsets()):
+            n = 1
+            for d in shape:
+                n *= d
+            grads.append(flat[off:off + n].view(shape) if needs else None)
+        return (None, None, d_vi, d_ai, None, *grads)
+
+
 class MultimodalUNet(nn.Module):
     """Same constructor signature as the reference (multimodal_unet.py:737-764)."""
 
@@ -281,33 +323,23 @@ class MultimodalUNet(nn.Module):
         return steps
 
     # ------------------------------------------------------------------ forward
-    def forward(self, video, audio, timesteps, label=None, shifts: Sequence[int] = None):
-        """video [N,F,C,H,W], audio [N,C,L], timesteps [N] -> (video_out, audio_out) of self.dtype.
+    def _param_offsets(self) -> List[int]:
+        if getattr(self, "_offsets", None) is None:
+            lib = _lib.load()
+            self._offsets = [int(lib.mmd_model_param_offset(self._handle, i)) for i in range(len(self._param_names))]
+        return self._offsets
 
-        `shifts` (optional) pins the random window shifts; by default they are drawn like the reference."""
-        assert (label is not None) == (self.num_classes is not None), \
-            "must specify y if and only if the model is class-conditional"
-        p0 = next(self.parameters())
-        if not p0.is_cuda or not video.is_cuda:
-            raise MmdError("MultimodalUNet.forward needs CUDA tensors: the denoising step is hand-written "
-                           "sm_100a CUDA and has no CPU fallback")
-        if torch.is_grad_enabled() and (video.requires_grad or audio.requires_grad or
-                                        (self.training and any(p.requires_grad for p in self.parameters()))):
-            raise NotImplementedError(
-                "backward through the sm_100a path is not implemented yet; call under torch.no_grad() "
-                "(sampling) — training kernels are scheduled after the forward path (DESIGN.md)")
-        device = p0.device
+    def num_backward_launches(self, batch: int) -> int:
+        return 0 if self._handle is None else int(_lib.load().mmd_model_num_backward_launches(self._handle, batch))
+
+    def _run(self, video, audio, timesteps, shifts, train: bool):
+        """One library forward on detached fp32 inputs -> (video_out, audio_out) fp32."""
+        device = next(self.parameters()).device
         B = video.shape[0]
-        if tuple(video.shape[1:]) != tuple(int(x) for x in self.video_size) or \
-                tuple(audio.shape[1:]) != tuple(int(x) for x in self.audio_size) or audio.shape[0] != B:
-            raise ValueError(f"input shapes {tuple(video.shape)} / {tuple(audio.shape)} do not match the model's "
-                             f"video_size {self.video_size} / audio_size {self.audio_size}")
         with torch.cuda.device(device):
             self._ensure_handle(device)
-            if self._needs_sync or self.training:
+            if self._needs_sync or self.training or train:
                 self._sync_parameters()
-            if shifts is None:
-                shifts = self.draw_shifts()
             v = video.detach().to(torch.float32).contiguous()
             a = audio.detach().to(torch.float32).contiguous()
             t = timesteps.detach().to(device=device, dtype=torch.float32).contiguous()
@@ -316,8 +348,39 @@ class MultimodalUNet(nn.Module):
             ao = torch.empty((B, self.audio_out_channels, self._cfg.audio_l), dtype=torch.float32, device=device)
             n = len(self._shift_bounds)
             arr = (C.c_int32 * max(n, 1))(*[int(s) for s in shifts][:n])
-            check(_lib.load().mmd_model_forward(self._handle, B, v.data_ptr(), a.data_ptr(), t.data_ptr(), arr,
-                                                vo.data_ptr(), ao.data_ptr(), _lib.current_stream_ptr()))
+            fn = _lib.load().mmd_model_forward_train if train else _lib.load().mmd_model_forward
+            check(fn(self._handle, B, v.data_ptr(), a.data_ptr(), t.data_ptr(), arr, vo.data_ptr(), ao.data_ptr(),
+                     _lib.current_stream_ptr()))
+        return vo, ao
+
+    def forward(self, video, audio, timesteps, label=None, shifts: Sequence[int] = None):
+        """video [N,F,C,H,W], audio [N,C,L], timesteps [N] -> (video_out, audio_out) of self.dtype.
+
+        `shifts` (optional) pins the random window shifts; by default they are drawn like the reference.
+        Under autograd (parameters or inputs requiring grad, grad mode on) the call is differentiable: training
+        (multimodal_gaussian_diffusion.py:1141) and gradient-guided conditional sampling (:815)."""
+        assert (label is not None) == (self.num_classes is not None), \
+            "must specify y if and only if the model is class-conditional"
+        p0 = next(self.parameters())
+        if not p0.is_cuda or not video.is_cuda:
+            raise MmdError("MultimodalUNet.forward needs CUDA tensors: the denoising step is hand-written "
+                           "sm_100a CUDA and has no CPU fallback")
+        B = video.shape[0]
+        if tuple(video.shape[1:]) != tuple(int(x) for x in self.video_size) or \
+                tuple(audio.shape[1:]) != tuple(int(x) for x in self.audio_size) or audio.shape[0] != B:
+            raise ValueError(f"input shapes {tuple(video.shape)} / {tuple(audio.shape)} do not match the model's "
+                             f"video_size {self.video_size} / audio_size {self.audio_size}")
+        if shifts is None:
+            shifts = self.draw_shifts()
+        params = list(self.parameters())
+        differentiable = torch.is_grad_enabled() and (video.requires_grad or audio.requires_grad or
+                                                      any(p.requires_grad for p in params))
+        if differentiable:
+            if self.dropout and self.training:
+                raise NotImplementedError("dropout > 0 is not implemented on the sm_100a training path")
+            vo, ao = _UNetFunction.apply(self, list(shifts), video, audio, timesteps, *params)
+        else:
+            vo, ao = self._run(video, audio, timesteps, shifts, train=False)
         if self.dtype != torch.float32:
             vo, ao = vo.to(self.dtype), ao.to(self.dtype)
         return vo, ao

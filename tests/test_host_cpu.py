@@ -143,3 +143,27 @@ def test_compat_install_aliases_reference_module_names():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+def test_training_plan_dry_run_is_consistent():
+    """Host-only dry run of the training plan: the forward walk plus the backward tape (every tensor's gradient has a
+    producer before its consumer's backward, segments / sources line up) for the small and the production topology."""
+    import ctypes as C
+    from mm_diffusion_b200 import _lib
+    from oracle.make_golden import PRODUCTION, SMALL
+    from tests.util_golden import build_b200_model
+    lib = _lib.load()
+    for cfg in (SMALL, PRODUCTION):
+        m = build_b200_model(cfg, None, device="cpu")
+        h = C.c_void_p()
+        _lib.check(lib.mmd_model_create(C.byref(m._cfg), C.byref(h)))
+        try:
+            fwd = lib.mmd_model_workspace_bytes(h, 2)
+            train = lib.mmd_model_train_workspace_bytes(h, 2)
+            assert train > 0, lib.mmd_last_error()
+            assert train > fwd   # kept activations + gradients
+            assert lib.mmd_model_param_floats(h) >= sum(p.numel() for p in m.parameters())
+            offs = [lib.mmd_model_param_offset(h, i) for i in range(lib.mmd_model_num_params(h))]
+            assert offs == sorted(offs) and offs[0] == 0
+        finally:
+            lib.mmd_model_destroy(h)
