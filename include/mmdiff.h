@@ -98,6 +98,9 @@ size_t mmd_model_train_workspace_bytes(const MmdModel* m, int batch);
 int64_t mmd_model_param_offset(const MmdModel* m, int index);
 int64_t mmd_model_param_floats(const MmdModel* m);
 int mmd_model_num_backward_launches(const MmdModel* m, int batch);
+/* measurement hooks of the backward plan (per-step device time, kernel-family tag of a step) */
+int mmd_model_profile_backward(MmdModel* m, int batch, int reps, float* ms, int cap, void* stream);
+const char* mmd_model_backward_step_kind(const MmdModel* m, int batch, int index);
 
 /* ---- measurement hooks (bench.py): per-launch device time of the plan for `batch` (mean of `reps` un-graphed
  *      executions, CUDA events on `stream`) and each step's kernel family / algorithmic FLOPs / bytes

@@ -100,6 +100,8 @@ _PROTOS = [
     ("mmd_model_param_offset", C.c_int64, [C.c_void_p, C.c_int]),
     ("mmd_model_param_floats", C.c_int64, [C.c_void_p]),
     ("mmd_model_num_backward_launches", C.c_int, [C.c_void_p, C.c_int]),
+    ("mmd_model_profile_backward", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int, C.c_void_p]),
+    ("mmd_model_backward_step_kind", C.c_char_p, [C.c_void_p, C.c_int, C.c_int]),
     ("mmd_model_profile", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int, C.c_void_p]),
     ("mmd_model_step_info", C.c_int,
      [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(C.c_double),

@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(GnBwdArgs g, GnBwdOut
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int c = c0 + i;
-            const int grp = (cpg >= 8) ? grp0 : c / cpg;
+            const int grp = (cpg % 8 == 0) ? grp0 : c / cpg;
             const float x = __half2float(xh[i]);
             float du = __half2float(dh[i]);
             if (g.do_silu) du *= dsilu_f(fmaf(x, coef[c], coef[C + c]));

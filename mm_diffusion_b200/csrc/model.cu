@@ -78,6 +78,7 @@ struct Plan {
     // ---- training plan only (every intermediate kept; backward launch list built from the tape)
     bool train = false;
     std::vector<LaunchFn> bwd_steps;
+    std::vector<std::string> bwd_kind;   // kernel family tag per backward step (profiling)
     std::vector<LaunchFn> tpack_ops;   // transposed weight packs for the data gradients (re-run when weights change)
     bool tpack_dirty = true;
     float *d_out_video = nullptr, *d_out_audio = nullptr;   // staged output gradients (fp32, API layout)
@@ -1028,7 +1029,11 @@ struct Walker {
         return it != grad_map.end() && it->second.second;
     }
     void mark_written(const act_t* x) { grad_map[x].second = true; }
-    void bpush(LaunchFn fn) { if (emitting()) plan->bwd_steps.push_back(std::move(fn)); }
+    void bpush(LaunchFn fn, const std::string& kind) {
+        if (!emitting()) return;
+        plan->bwd_steps.push_back(std::move(fn));
+        plan->bwd_kind.push_back(kind);
+    }
     // gradient of an op output; every forward tensor has a consumer, so it must have been produced already
     act_t* need_grad(const act_t* y, const char* what) {
         if (!grad_written(y)) { set_err(fail(MMD_ESTATE, "internal: backward of %s has no incoming gradient", what)); return nullptr; }
@@ -1063,7 +1068,7 @@ struct Walker {
             bpush([=](cudaStream_t st) -> int {
                 MMD_TRY(launch_head_dgrad(hg, dout, w, dx, gs, st));
                 return launch_head_wgrad(hg, dout, x, dw, db, st);
-            });
+            }, "head_bwd");
             return;
         }
         act_t* dy = need_grad(op.out, op.tag.c_str());
@@ -1087,7 +1092,7 @@ struct Walker {
         if (emitting() && !pc->biases.empty()) {
             float* b0 = g32_of(pc->biases[0]);
             float* b1 = pc->biases.size() > 1 ? g32_of(pc->biases[1]) : nullptr;
-            bpush([=](cudaStream_t st) { return launch_colsum(dy, tokens, n, 1.0f, b0, st, b1, gs); });
+            bpush([=](cudaStream_t st) { return launch_colsum(dy, tokens, n, 1.0f, b0, st, b1, gs); }, "bias_grad");
         }
         // ---- weight gradients: one tcgen05 wgrad over the conv sources, unpacked per parameter
         {
@@ -1120,7 +1125,7 @@ struct Walker {
                         col += static_cast<long long>(segs[i].ci) * segs[i].T;
                     }
                     return MMD_OK;
-                });
+                }, "wgrad:" + op.tag);
             }
         }
         // ---- data gradients
@@ -1163,7 +1168,7 @@ struct Walker {
                     }
                     MMD_CUDA_OK(cudaGetLastError());
                     return MMD_OK;
-                });
+                }, "dgrad:stem");
             }
             release_b(bmark);
             return;
@@ -1176,7 +1181,7 @@ struct Walker {
             if (!x.conv) {   // residual / identity columns: dX += dY[:, off : off + c]
                 const long long off = x.off;
                 const int c = x.c;
-                bpush([=](cudaStream_t st) { return launch_grad_add2d(dy + off, n, gx, c, tokens, c, acc ? 1 : 0, st); });
+                bpush([=](cudaStream_t st) { return launch_grad_add2d(dy + off, n, gx, c, tokens, c, acc ? 1 : 0, st); }, "residual_add");
                 continue;
             }
             // segment that holds this source's channel range
@@ -1218,7 +1223,7 @@ struct Walker {
                     pdl_break(st);
                     if (acc) return launch_grad_add(tmp, gx, elems, 1, st);
                     return MMD_OK;
-                });
+                }, "dgrad:" + op.tag);
             }
         }
         release_b(bmark);
@@ -1254,7 +1259,7 @@ struct Walker {
             bpush([=](cudaStream_t st) -> int {
                 MMD_CUDA_OK(cudaMemsetAsync(T, 0, t_bytes, st));
                 return launch_gn_bwd(pr, st);
-            });
+            }, "group_norm_bwd");
         }
         release_b(bmark);
     }
@@ -1279,7 +1284,7 @@ struct Walker {
                 MMD_TRY(launch_gn_temporal_bwd(x, dy, acc ? tmp : gx, gamma, dg, db, Bc, Fc, P, C, gs, st));
                 if (acc) return launch_grad_add(tmp, gx, static_cast<long long>(elems), 1, st);
                 return MMD_OK;
-            });
+            }, "gn_temporal_bwd");
         }
         release_b(bmark);
     }
@@ -1294,7 +1299,7 @@ struct Walker {
         if (!emitting()) return;
         const act_t* qkv = op.in;
         const int Bc = op.B, Fc = op.F, P = op.P, C = op.C, heads = op.heads;
-        bpush([=](cudaStream_t st) { return launch_temporal_attn_bwd(qkv, d_out, dqkv, Bc, Fc, P, C, heads, st); });
+        bpush([=](cudaStream_t st) { return launch_temporal_attn_bwd(qkv, d_out, dqkv, Bc, Fc, P, C, heads, st); }, "temporal_attention_bwd");
     }
 
     void bwd_attn(const TapeOp& op) {
@@ -1320,7 +1325,7 @@ struct Walker {
             bpush([=](cudaStream_t st) -> int {
                 MMD_TRY(launch_attn_delta(d_out, out, q_rows, C, heads, delta, q_rows, st));
                 return launch_attn_bwd(*pq, *pkv, d, st);
-            });
+            }, (ap.win == 1 && ap.shift_dev == nullptr && ap.q_blk == ap.k_blk) ? "self_attention_bwd" : "cross_attention_bwd");
         }
         release_b(bmark);
     }
@@ -1335,7 +1340,7 @@ struct Walker {
         mark_written(op.in);
         if (!emitting()) return;
         const int mode = op.mode, n = op.n_, h = op.h_, w = op.w_, c = op.C;
-        bpush([=](cudaStream_t st) { return launch_resample_bwd(dy, gx, mode, n, h, w, c, acc ? 1 : 0, st); });
+        bpush([=](cudaStream_t st) { return launch_resample_bwd(dy, gx, mode, n, h, w, c, acc ? 1 : 0, st); }, "resample_bwd");
     }
 
     void emit_backward() {
@@ -1388,7 +1393,7 @@ struct Walker {
                 time_embed_bwd_reduce_kernel<<<(E * E + 255) / 256, 256, 0, st>>>(te_scratch, Bc, E, dw1, db1, dw2, db2, gs);
                 MMD_CUDA_OK(cudaGetLastError());
                 return MMD_OK;
-            });
+            }, "time_embed_bwd");
         }
         release_b(bmark);
     }
@@ -1883,6 +1888,45 @@ int mmd_model_num_backward_launches(const MmdModel* m, int batch) {
     if (!m) return 0;
     auto it = m->train_plans.find(batch);
     return it == m->train_plans.end() ? 0 : static_cast<int>(it->second->bwd_steps.size());
+}
+
+// Per-step device time of the backward plan (mean of `reps` executions, CUDA events on `stream`); a forward_train at
+// this batch must have run.  Gradients accumulate across repetitions: profiling only.  Returns the step count.
+int mmd_model_profile_backward(MmdModel* m, int batch, int reps, float* ms, int cap, void* stream) {
+    if (!m || !ms) return fail(MMD_EINVAL, "null argument");
+    auto it = m->train_plans.find(batch);
+    if (it == m->train_plans.end()) return fail(MMD_ESTATE, "no training plan for batch %d yet", batch);
+    Plan* plan = it->second.get();
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int n = static_cast<int>(plan->bwd_steps.size());
+    if (cap < n) return fail(MMD_EINVAL, "profile buffer too small (%d < %d)", cap, n);
+    if (reps < 1) reps = 1;
+    std::vector<cudaEvent_t> ev(n + 1);
+    for (auto& e : ev) MMD_CUDA_OK(cudaEventCreate(&e));
+    for (int i = 0; i < n; ++i) ms[i] = 0.f;
+    int r = MMD_OK;
+    for (int rep = 0; rep < reps && r == MMD_OK; ++rep) {
+        MMD_CUDA_OK(cudaEventRecord(ev[0], st));
+        for (int i = 0; i < n; ++i) {
+            r = plan->bwd_steps[i](st);
+            if (r != MMD_OK) break;
+            MMD_CUDA_OK(cudaEventRecord(ev[i + 1], st));
+        }
+        MMD_CUDA_OK(cudaStreamSynchronize(st));
+        for (int i = 0; i < n && r == MMD_OK; ++i) {
+            float t = 0.f;
+            MMD_CUDA_OK(cudaEventElapsedTime(&t, ev[i], ev[i + 1]));
+            ms[i] += t / reps;
+        }
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    return r == MMD_OK ? n : r;
+}
+const char* mmd_model_backward_step_kind(const MmdModel* m, int batch, int index) {
+    if (!m) return "";
+    auto it = m->train_plans.find(batch);
+    if (it == m->train_plans.end() || index < 0 || index >= static_cast<int>(it->second->bwd_kind.size())) return "";
+    return it->second->bwd_kind[index].c_str();
 }
 
 }  // extern "C"

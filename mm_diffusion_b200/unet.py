@@ -332,6 +332,17 @@ class MultimodalUNet(nn.Module):
     def num_backward_launches(self, batch: int) -> int:
         return 0 if self._handle is None else int(_lib.load().mmd_model_num_backward_launches(self._handle, batch))
 
+    def profile_backward(self, batch: int, reps: int = 1):
+        """[{kind, ms}] per backward step (un-graphed, CUDA events); needs a preceding differentiable forward."""
+        lib = _lib.load()
+        n = self.num_backward_launches(batch)
+        buf = (C.c_float * max(n, 1))()
+        with torch.cuda.device(self._handle_device):
+            r = lib.mmd_model_profile_backward(self._handle, batch, reps, buf, n, _lib.current_stream_ptr())
+        if r < 0:
+            check(r)
+        return [{"kind": lib.mmd_model_backward_step_kind(self._handle, batch, i).decode(), "ms": float(buf[i])} for i in range(n)]
+
     def _run(self, video, audio, timesteps, shifts, train: bool):
         """One library forward on detached fp32 inputs -> (video_out, audio_out) fp32."""
         device = next(self.parameters()).device

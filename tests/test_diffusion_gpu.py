@@ -120,6 +120,8 @@ def test_p_sample_loop_api_and_replacement_conditioning(setup):
     out = diff.conditional_p_sample_loop(model, shape, use_fp16=True, model_kwargs={"audio": cond.cuda()},
                                          device=torch.device("cuda"), progress=False, class_scale=0.0)
     assert out["video"].shape == shape["video"] and torch.isfinite(out["audio"]).all()
-    with pytest.raises(NotImplementedError):
-        diff.conditional_p_sample_loop(model, shape, use_fp16=True, model_kwargs={"audio": cond.cuda()},
-                                       device=torch.device("cuda"), progress=False, class_scale=3.0)
+    # gradient guidance (class_scale > 0, reference :722-819) backpropagates through the sm_100a path to the video input
+    torch.manual_seed(2)
+    out = diff.conditional_p_sample_loop(model, shape, use_fp16=False, model_kwargs={"audio": cond.cuda()},
+                                         device=torch.device("cuda"), progress=False, class_scale=3.0)
+    assert out["video"].shape == shape["video"] and torch.isfinite(out["video"]).all() and torch.isfinite(out["audio"]).all()
