@@ -318,6 +318,118 @@ def run_b200(args):
         print(json.dumps(result))
 
 
+def run_b200_train(args):
+    """BASELINE.json configs[3]: multimodal_training_losses forward + backward, batch 8 per GPU, synthetic
+    Landscape-shape data, batch-sharded over the GPUs of the box (DDP gradient all-reduce over NCCL when N > 1).
+    A step = one forward + backward over one batch (no optimizer: the config names fwd+bwd); value = samples x steps / s."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    B, K, W = (args.batch if args.batch_set else 8), args.steps, max(args.warmup, 3)
+    model, diffusion = build_b200(device)
+    model.convert_to_fp32()
+    model.train()
+    net = model
+    if world > 1:
+        from torch.nn.parallel import DistributedDataParallel as DDP
+        net = DDP(model, device_ids=[local_rank], broadcast_buffers=False, bucket_cap_mb=128)
+    import random
+    random.seed(4321 + rank)
+    gen = torch.Generator().manual_seed(1234 + rank)
+    xv_h = torch.randn(B, *VIDEO_SIZE, generator=gen).clamp(-1, 1).pin_memory()
+    xa_h = torch.randn(B, *AUDIO_SIZE, generator=gen).clamp(-1, 1).pin_memory()
+    t = torch.randint(0, diffusion.num_timesteps, (B,), generator=torch.Generator().manual_seed(99 + rank)).to(device)
+    torch.manual_seed(7 + rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(x0):
+        model.zero_grad(set_to_none=True)
+        terms = diffusion.multimodal_training_losses(net, x0, t)
+        loss = terms["loss"].mean()
+        loss.backward()
+        return loss
+
+    x0 = {"video": xv_h.to(device), "audio": xa_h.to(device)}
+    for _ in range(W):
+        step(x0)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        loss = step(x0)
+    e1.record()
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    ms_total = e0.elapsed_time(e1)
+    finite = bool(torch.isfinite(loss).item() and all(torch.isfinite(p.grad).all().item() for p in model.parameters()))
+    # end to end: host batch -> device, step, loss back to the host
+    for _ in range(W):
+        step({"video": xv_h.to(device, non_blocking=True), "audio": xa_h.to(device, non_blocking=True)}).item()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(K):
+        step({"video": xv_h.to(device, non_blocking=True), "audio": xa_h.to(device, non_blocking=True)}).item()
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    if world > 1:
+        tmax = torch.tensor([ms_total, ms_e2e], device=device)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms_total, ms_e2e = tmax[0].item(), tmax[1].item()
+    if rank == 0:
+        peaks = load_peaks()
+        fwd_steps = model.plan_steps(B)   # inference plan may be absent; launch counts come from the training plan below
+        bwd = model.profile_backward(B, reps=1) if args.profile_reps > 0 else []
+        fam = {}
+        for s_ in bwd:
+            f = fam.setdefault(s_["kind"], {"ms": 0.0, "steps": 0})
+            f["ms"] += s_["ms"]; f["steps"] += 1
+        flops_fwd = 1.3288e12 * B   # SURVEY.md 8(d): algorithmic FLOPs per model evaluation per sample
+        step_flops = 3.0 * flops_fwd  # forward + dgrad + wgrad
+        value = world * B * K / (ms_total * 1e-3)
+        result = {
+            "metric": "training_losses forward+backward samples/sec (16fx64x64 video + 25600 audio)", "value": round(value, 3),
+            "unit": "sample-steps/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": round(ms_total / K, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": "multimodal_training_losses forward+backward (BASELINE.json configs[3])",
+                       "batch_per_gpu": B, "global_batch": B * world, "video": VIDEO_SIZE, "audio": AUDIO_SIZE,
+                       "params_m": round(sum(p.numel() for p in model.parameters()) / 1e6, 2),
+                       "parallelism": f"batch-shard x{world}" + (" (DDP, NCCL gradient all-reduce)" if world > 1 else ""),
+                       "l2_note": "kept activations + gradients (~48 GB at B=8) exceed the 126 MB L2", "cuda_graph": False},
+            "e2e": {"value": round(world * B * K / (ms_e2e * 1e-3), 3), "unit": "sample-steps/s", "ms_per_step": round(ms_e2e / K, 3),
+                    "h2d_bytes_per_step": (xv_h.numel() + xa_h.numel()) * 4, "d2h_bytes_per_step": 4},
+            "gpu_launches": K * (model.num_backward_launches(B) + len(fwd_steps)),
+            "model_tflops": round(step_flops * K / (ms_total * 1e-3) / 1e12, 2),
+            "roofline": {"bound": "tensor", "achieved": round(step_flops * K / (ms_total * 1e-3) / 1e12, 2),
+                         "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                         "frac": round(step_flops * K / (ms_total * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"], 4),
+                         "kernel": "whole step (forward + dgrad + wgrad, 3 x 1.3288 TFLOP per sample)", "traffic": None},
+            "backward_families": {k: {"ms": round(v["ms"], 3), "steps": v["steps"]} for k, v in
+                                  sorted(fam.items(), key=lambda kv: -kv[1]["ms"])},
+            "clocks": clk, "finite": finite,
+        }
+        print(json.dumps(result))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 # ----------------------------------------------------------------------------- CPU arms (oracle = checker / baseline only)
 def usable_cores():
     """Host cores this process may actually use: affinity mask, capped by the cgroup CPU quota if there is one."""
@@ -415,17 +527,25 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=4, help="samples per GPU (configs[1] uses 4)")
+    ap.add_argument("--batch", type=int, default=None, help="samples per GPU (configs[1] uses 4, the training config 8)")
+    ap.add_argument("--workload", default="sample", choices=["sample", "train"],
+                    help="sample: p_sample step of configs[1] (the headline metric); train: training_losses fwd+bwd of configs[3]")
     ap.add_argument("--profile-reps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    args.batch_set = args.batch is not None
+    if args.batch is None:
+        args.batch = 4
     if args.impl == "reference":
         run_reference(args)
     else:
         world = int(os.environ.get("WORLD_SIZE", "1"))
         if args.gpus != world and world == 1 and args.gpus > 1:
             raise SystemExit(f"--gpus {args.gpus} needs torchrun (one process per GPU); WORLD_SIZE is {world}")
-        run_b200(args)
+        if args.workload == "train":
+            run_b200_train(args)
+        else:
+            run_b200(args)
 
 
 if __name__ == "__main__":

@@ -14,6 +14,14 @@ MMD_DEVINL float dsilu_f(float u) {
     const float s = 1.0f / (1.0f + __expf(-u));
     return s * (1.0f + u * (1.0f - s));
 }
+// silu'(u) through one MUFU op (sigmoid = 0.5 (1 + tanh(u / 2)), tanh.approx abs error ~5e-4: below the fp16 rounding
+// of the gradients it multiplies)
+MMD_DEVINL float dsilu_fast(float u) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * u));
+    const float s = fmaf(0.5f, t, 0.5f);
+    return s * fmaf(u, 1.0f - s, 1.0f);
+}
 
 // ---------------------------------------------------------------------------
 // Gradient scale: gscale = {s, 1/s}, s = 2^floor(log2(16 / amax |dY|)) over both modalities.
@@ -159,22 +167,38 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(GnBwdArgs g) {
         if (c0 < g.s.c1) { base = g.s.x1 + c0; ld = g.s.ld1; } else { base = g.s.x2 + (c0 - g.s.c1); ld = g.s.ld2; }
         base += static_cast<size_t>(ns) * g.R * ld;
         const act_t* dyb = g.dy + static_cast<size_t>(ns) * g.R * C + c0;
+        float ca[8], cb[8], crs[8], cmr[8];   // this thread's 8 channels: u = x a + b, xh = x rs - mr
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { ca[i] = coef[c0 + i]; cb[i] = coef[C + c0 + i]; crs[i] = coef[2 * C + c0 + i]; cmr[i] = coef[3 * C + c0 + i]; }
         float t1[8], t2[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) { t1[i] = 0.f; t2[i] = 0.f; }
-        for (int r = r0 + rsub; r < r1; r += rows_per_pass) {
-            const uint4 xr = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(r) * ld));
-            const uint4 dr = __ldg(reinterpret_cast<const uint4*>(dyb + static_cast<size_t>(r) * C));
-            const __half* xh = reinterpret_cast<const __half*>(&xr);
-            const __half* dh = reinterpret_cast<const __half*>(&dr);
+        for (int r = r0 + rsub; r < r1; r += GN_UNROLL * rows_per_pass) {
+            uint4 xr[GN_UNROLL], dr[GN_UNROLL];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float x = __half2float(xh[i]);
-                float du = __half2float(dh[i]);
-                if (g.do_silu) du *= dsilu_f(fmaf(x, coef[c0 + i], coef[C + c0 + i]));
-                const float xn = fmaf(x, coef[2 * C + c0 + i], -coef[3 * C + c0 + i]);
-                t1[i] += du;
-                t2[i] = fmaf(du, xn, t2[i]);
+            for (int u = 0; u < GN_UNROLL; ++u) {
+                const int rr = r + u * rows_per_pass;
+                if (rr < r1) {
+                    xr[u] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(rr) * ld));
+                    dr[u] = __ldg(reinterpret_cast<const uint4*>(dyb + static_cast<size_t>(rr) * C));
+                } else {
+                    xr[u] = make_uint4(0, 0, 0, 0);
+                    dr[u] = make_uint4(0, 0, 0, 0);   // dy = 0: contributes nothing
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < GN_UNROLL; ++u) {
+                const __half* xh = reinterpret_cast<const __half*>(&xr[u]);
+                const __half* dh = reinterpret_cast<const __half*>(&dr[u]);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float x = __half2float(xh[i]);
+                    float du = __half2float(dh[i]);
+                    if (g.do_silu) du *= dsilu_fast(fmaf(x, ca[i], cb[i]));
+                    const float xn = fmaf(x, crs[i], -cmr[i]);
+                    t1[i] += du;
+                    t2[i] = fmaf(du, xn, t2[i]);
+                }
             }
         }
 #pragma unroll
@@ -245,31 +269,46 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(GnBwdArgs g, GnBwdOut
     base += static_cast<size_t>(ns) * g.R * ld;
     dbase += static_cast<size_t>(ns) * g.R * dld;
     const act_t* dyb = g.dy + static_cast<size_t>(ns) * g.R * C + c0;
-    const int grp0 = c0 / cpg;
-    for (int r = r0 + rsub; r < r1; r += rows_per_pass) {
-        const uint4 xr = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(r) * ld));
-        const uint4 dr = __ldg(reinterpret_cast<const uint4*>(dyb + static_cast<size_t>(r) * C));
-        uint4* dst = reinterpret_cast<uint4*>(dbase + static_cast<size_t>(r) * dld);
-        uint4 prev = make_uint4(0, 0, 0, 0);
-        if (dacc) prev = *dst;
-        const __half* xh = reinterpret_cast<const __half*>(&xr);
-        const __half* dh = reinterpret_cast<const __half*>(&dr);
-        const __half* ph = reinterpret_cast<const __half*>(&prev);
-        uint4 outv;
-        __half* oh = reinterpret_cast<__half*>(&outv);
+    float ca[8], cb[8], crs[8], cmr[8], cp[8], cq[8], cr[8];   // dx = p du - q - xh r
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int c = c0 + i;
-            const int grp = (cpg % 8 == 0) ? grp0 : c / cpg;
-            const float x = __half2float(xh[i]);
-            float du = __half2float(dh[i]);
-            if (g.do_silu) du *= dsilu_f(fmaf(x, coef[c], coef[C + c]));
-            const float xn = fmaf(x, coef[2 * C + c], -coef[3 * C + c]);
-            float dx = pc[c] * du - qr[2 * grp] - xn * qr[2 * grp + 1];
-            if (dacc) dx += __half2float(ph[i]);
-            oh[i] = __float2half_rn(dx);
+    for (int i = 0; i < 8; ++i) {
+        const int c = c0 + i;
+        const int grp = c / cpg;
+        ca[i] = coef[c]; cb[i] = coef[C + c]; crs[i] = coef[2 * C + c]; cmr[i] = coef[3 * C + c];
+        cp[i] = pc[c]; cq[i] = qr[2 * grp]; cr[i] = qr[2 * grp + 1];
+    }
+    for (int r = r0 + rsub; r < r1; r += GN_UNROLL * rows_per_pass) {
+        uint4 xr[GN_UNROLL], dr[GN_UNROLL], pv[GN_UNROLL];
+#pragma unroll
+        for (int u = 0; u < GN_UNROLL; ++u) {
+            const int rr = r + u * rows_per_pass;
+            if (rr < r1) {
+                xr[u] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(rr) * ld));
+                dr[u] = __ldg(reinterpret_cast<const uint4*>(dyb + static_cast<size_t>(rr) * C));
+                if (dacc) pv[u] = *reinterpret_cast<const uint4*>(dbase + static_cast<size_t>(rr) * dld);
+            }
         }
-        *dst = outv;
+#pragma unroll
+        for (int u = 0; u < GN_UNROLL; ++u) {
+            const int rr = r + u * rows_per_pass;
+            if (rr >= r1) break;
+            const __half* xh = reinterpret_cast<const __half*>(&xr[u]);
+            const __half* dh = reinterpret_cast<const __half*>(&dr[u]);
+            const __half* ph = reinterpret_cast<const __half*>(&pv[u]);
+            uint4 outv;
+            __half* oh = reinterpret_cast<__half*>(&outv);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float x = __half2float(xh[i]);
+                float du = __half2float(dh[i]);
+                if (g.do_silu) du *= dsilu_fast(fmaf(x, ca[i], cb[i]));
+                const float xn = fmaf(x, crs[i], -cmr[i]);
+                float dx = cp[i] * du - cq[i] - xn * cr[i];
+                if (dacc) dx += __half2float(ph[i]);
+                oh[i] = __float2half_rn(dx);
+            }
+            *reinterpret_cast<uint4*>(dbase + static_cast<size_t>(rr) * dld) = outv;
+        }
     }
 }
 
@@ -658,6 +697,78 @@ __global__ void head_wgrad_kernel(HeadGeom g, const float* __restrict__ dout, co
         if (tp < g.n_taps) atomicAdd(&dw[(static_cast<size_t>(n) * g.C + c) * g.n_taps + tp], acc[t]);
     }
     if (db != nullptr && c < g.n_out) atomicAdd(&db[c], bsum);
+}
+
+// Tensor-core path of the head adjoints: G[tok][t * n_out + n] = s * dout[n][tok - delta(t)] (fp16, zero outside the
+// tensor and in the padding columns).  Then dX = G * Wt (forward implicit-GEMM kernel, one tap) and
+// dW[(t, n)][c] = sum_tok G[tok][(t, n)] * A[tok][c] (conv_wgrad_kernel): both adjoints become plain token GEMMs.
+__global__ void head_im2col_bwd_kernel(HeadGeom g, const float* __restrict__ dout, act_t* __restrict__ G, int ldG, long long tokens,
+                                       const float* __restrict__ gscale) {
+    const int vpr = ldG / 8;
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= tokens * vpr) return;
+    const int v = static_cast<int>(idx % vpr);
+    long long tok = idx / vpr;
+    int co[4];
+    long long r = tok;
+    for (int i = 0; i < 4; ++i) { co[i] = static_cast<int>(r % g.dims[i]); r /= g.dims[i]; }
+    const float s = gscale ? gscale[0] : 1.0f;
+    const int terms = g.n_taps * g.n_out;
+    uint4 o;
+    __half* oh = reinterpret_cast<__half*>(&o);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int k = v * 8 + i;
+        float val = 0.f;
+        if (k < terms) {
+            const int t = k / g.n_out, n = k - t * g.n_out;
+            const int c0 = co[0] - g.tap[t][0], c1 = co[1] - g.tap[t][1], c2 = co[2] - g.tap[t][2];
+            if (c0 >= 0 && c0 < g.dims[0] && c1 >= 0 && c1 < g.dims[1] && c2 >= 0 && c2 < g.dims[2])
+                val = s * __ldg(dout + c0 * g.ostride[0] + c1 * g.ostride[1] + c2 * g.ostride[2] + co[3] * g.ostride[3] + n * g.ostride_c);
+        }
+        oh[i] = __float2half_rn(val);
+    }
+    reinterpret_cast<uint4*>(G)[idx] = o;
+}
+// dst[c][t * n_out + n] = w[n][c][t]  (fp32 [n_out][C][T] -> fp16 [C][ld]; padding columns stay zero)
+__global__ void pack_head_t_kernel(const float* __restrict__ w, act_t* __restrict__ dst, int n_out, int C, int T, int ld) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_out * C * T) return;
+    const int t = idx % T;
+    const int r = idx / T;
+    const int c = r % C, n = r / C;
+    dst[static_cast<size_t>(c) * ld + t * n_out + n] = __float2half_rn(w[idx]);
+}
+// g[n][c][t] += inv_s * dwpk[(t * n_out + n)][c]
+__global__ void unpack_head_wgrad_kernel(const float* __restrict__ dwpk, float* __restrict__ gw, int n_out, int C, int T,
+                                         const float* __restrict__ gscale) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_out * C * T) return;
+    const int t = idx % T;
+    const int r = idx / T;
+    const int c = r % C, n = r / C;
+    gw[idx] += (gscale ? gscale[1] : 1.0f) * dwpk[static_cast<size_t>(t * n_out + n) * C + c];
+}
+// db[n] += sum over all tokens of dout[n][tok] (unscaled fp32); grid.y = n
+__global__ void __launch_bounds__(256) head_bias_kernel(HeadGeom g, const float* __restrict__ dout, float* __restrict__ db, long long tokens) {
+    const int n = blockIdx.y;
+    float acc = 0.f;
+    for (long long tok = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; tok < tokens;
+         tok += static_cast<long long>(gridDim.x) * blockDim.x) {
+        long long r = tok, off = 0;
+        for (int i = 0; i < 4; ++i) { off += (r % g.dims[i]) * g.ostride[i]; r /= g.dims[i]; }
+        acc += dout[off + n * g.ostride_c];
+    }
+    __shared__ float red[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += red[i];
+        atomicAdd(&db[n], t);
+    }
 }
 
 // ---------------------------------------------------------------------------

@@ -170,6 +170,7 @@ struct WgradProblem {
     int n = 0;
     float* dw = nullptr;
     long long ld = 0;
+    float* db = nullptr;   // optional fp32 [n] column sums of dy (bias gradient), zeroed by the caller
 };
 int build_wgrad(const WgradProblem& pr, WgradParams* out, int* n_items);
 int launch_wgrad(const WgradParams& p, int n_items, cudaStream_t st);

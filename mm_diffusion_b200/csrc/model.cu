@@ -1052,6 +1052,15 @@ struct Walker {
             act_t* dx = grad_buf(x, static_cast<size_t>(tokens) * C);
             if (grad_written(x)) { set_err(fail(MMD_ESTATE, "internal: head input gradient already written")); return; }
             mark_written(x);
+            const int terms = static_cast<int>(op.taps.size()) * n;
+            if (terms > 128 || C % 64 != 0) { set_err(fail(MMD_EINVAL, "head backward: %d taps x %d outputs over %d channels unsupported", static_cast<int>(op.taps.size()), n, C)); return; }
+            const int ldG = terms <= 64 ? 64 : 128;
+            const size_t hmark = bscratch.top;
+            act_t* G = static_cast<act_t*>(bscratch.take(sizeof(act_t) * static_cast<size_t>(tokens) * ldG));
+            const size_t dw_bytes = sizeof(float) * static_cast<size_t>(ldG) * C;
+            float* dwpk = static_cast<float*>(bscratch.take(dw_bytes));
+            act_t* wt = static_cast<act_t*>(tpack.take(sizeof(act_t) * static_cast<size_t>(C) * ldG));
+            release_b(hmark);
             if (!emitting()) return;
             HeadGeom hg{};
             hg.ncoord = op.g.rank - 1;
@@ -1065,9 +1074,44 @@ struct Walker {
             const float* w = pf(pc->segs[0].w);
             float* dw = g32_of(pc->segs[0].w);
             float* db = g32_of(pc->biases[0]);
+            // tensor-core path: G = shifted, scaled fp16 copy of dout; dX = G Wt (forward kernel), dW = G^T A (wgrad kernel)
+            GemmProblem pr;
+            pr.g = geom2(tokens);
+            pr.n_src = 1; pr.src[0] = G; pr.src_c[0] = ldG;
+            pr.n_taps = 1;
+            pr.w = wt; pr.bias = plan->zero_bias; pr.n = C; pr.bn = pick_bn(C); pr.out = dx;
+            auto gp = std::make_shared<GemmParams>();
+            int r = build_gemm(pr, gp.get());
+            if (r != MMD_OK) { set_err(r); return; }
+            const int bn = pr.bn;
+            WgradProblem wp;
+            wp.g = geom2(tokens);
+            wp.n_src = 1; wp.src[0] = x; wp.src_c[0] = C;
+            wp.n_taps = 1;
+            wp.dy = G; wp.n = ldG; wp.dw = dwpk; wp.ld = C;
+            auto wpar = std::make_shared<WgradParams>();
+            int items = 0;
+            r = build_wgrad(wp, wpar.get(), &items);
+            if (r != MMD_OK) { set_err(r); return; }
+            const int n_out = n, T = hg.n_taps;
+            plan->tpack_ops.push_back([=](cudaStream_t st) -> int {
+                pack_head_t_kernel<<<(n_out * C * T + 255) / 256, 256, 0, st>>>(w, wt, n_out, C, T, ldG);
+                MMD_CUDA_OK(cudaGetLastError());
+                return MMD_OK;
+            });
             bpush([=](cudaStream_t st) -> int {
-                MMD_TRY(launch_head_dgrad(hg, dout, w, dx, gs, st));
-                return launch_head_wgrad(hg, dout, x, dw, db, st);
+                const long long total = tokens * (ldG / 8);
+                head_im2col_bwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(hg, dout, G, ldG, tokens, gs);
+                head_bias_kernel<<<dim3(static_cast<unsigned>(std::min<long long>((tokens + 255) / 256, 2LL * num_sms())), n_out), 256, 0, st>>>(hg, dout, db, tokens);
+                MMD_CUDA_OK(cudaGetLastError());
+                pdl_break(st);
+                MMD_TRY(launch_gemm(*gp, bn, st));
+                pdl_break(st);
+                MMD_CUDA_OK(cudaMemsetAsync(dwpk, 0, dw_bytes, st));
+                MMD_TRY(launch_wgrad(*wpar, items, st));
+                unpack_head_wgrad_kernel<<<(n_out * C * T + 255) / 256, 256, 0, st>>>(dwpk, dw, n_out, C, T, gs);
+                MMD_CUDA_OK(cudaGetLastError());
+                return MMD_OK;
             }, "head_bwd");
             return;
         }
@@ -1089,11 +1133,7 @@ struct Walker {
         }
         // ---- bias gradients: column sums of dY
         if (pc->biases.size() > 2) { set_err(fail(MMD_ESTATE, "internal: more than two biases in one GEMM")); return; }
-        if (emitting() && !pc->biases.empty()) {
-            float* b0 = g32_of(pc->biases[0]);
-            float* b1 = pc->biases.size() > 1 ? g32_of(pc->biases[1]) : nullptr;
-            bpush([=](cudaStream_t st) { return launch_colsum(dy, tokens, n, 1.0f, b0, st, b1, gs); }, "bias_grad");
-        }
+        // (reduced inside the wgrad kernel by an extra ones-operand MMA on the dY tiles it already holds)
         // ---- weight gradients: one tcgen05 wgrad over the conv sources, unpacked per parameter
         {
             WgradProblem wp;
@@ -1104,10 +1144,15 @@ struct Walker {
             wp.dy = dy;
             wp.n = n;
             wp.ld = conv_cols * wp.n_taps;
-            const size_t dw_bytes = sizeof(float) * static_cast<size_t>(n) * wp.ld;
+            const size_t dw_floats = static_cast<size_t>(n) * wp.ld;
+            const size_t dw_bytes = sizeof(float) * (dw_floats + n);
             float* dwpk = static_cast<float*>(bscratch.take(dw_bytes));
             wp.dw = dwpk;
+            float* dbpk = dwpk + dw_floats;
+            if (!pc->biases.empty()) wp.db = dbpk;
             if (emitting()) {
+                std::vector<float*> bdst;
+                for (int bi : pc->biases) bdst.push_back(g32_of(bi));
                 auto wpar = std::make_shared<WgradParams>();
                 int items = 0;
                 int r = build_wgrad(wp, wpar.get(), &items);
@@ -1124,6 +1169,8 @@ struct Walker {
                         MMD_TRY(launch_unpack_wgrad(dwpk, gdst[i], n, segs[i].ci, segs[i].T, ld, col, 1.0f, st, gs));
                         col += static_cast<long long>(segs[i].ci) * segs[i].T;
                     }
+                    for (float* bd : bdst) axpy_f32_kernel<<<(n + 255) / 256, 256, 0, st>>>(dbpk, bd, n, gs);
+                    MMD_CUDA_OK(cudaGetLastError());
                     return MMD_OK;
                 }, "wgrad:" + op.tag);
             }
@@ -1669,7 +1716,9 @@ size_t mmd_model_train_workspace_bytes(const MmdModel* m, int batch) {
 int mmd_model_num_launches(const MmdModel* m, int batch) {
     if (!m) return 0;
     auto it = m->plans.find(batch);
-    return it == m->plans.end() ? 0 : static_cast<int>(it->second->steps.size());
+    if (it != m->plans.end()) return static_cast<int>(it->second->steps.size());
+    auto tt = m->train_plans.find(batch);   // only a training plan exists at this batch: same forward launch list
+    return tt == m->train_plans.end() ? 0 : static_cast<int>(tt->second->steps.size());
 }
 
 // Per-launch device timing of one forward (no graph): fills ms[i] for plan step i with the mean over `reps`
@@ -1709,8 +1758,13 @@ int mmd_model_profile(MmdModel* m, int batch, int reps, float* ms, int cap, void
 int mmd_model_step_info(const MmdModel* m, int batch, int index, const char** kind, double* flops, double* bytes, int* kernels) {
     if (!m) return fail(MMD_EINVAL, "null argument");
     auto it = m->plans.find(batch);
-    if (it == m->plans.end()) return fail(MMD_ESTATE, "no plan for batch %d", batch);
-    const Plan* plan = it->second.get();
+    const Plan* plan = nullptr;
+    if (it != m->plans.end()) plan = it->second.get();
+    else {
+        auto tt = m->train_plans.find(batch);
+        if (tt == m->train_plans.end()) return fail(MMD_ESTATE, "no plan for batch %d", batch);
+        plan = tt->second.get();
+    }
     if (index < 0 || index >= static_cast<int>(plan->info.size())) return fail(MMD_EINVAL, "step index %d", index);
     const StepInfo& si = plan->info[index];
     if (kind) *kind = si.kind.c_str();

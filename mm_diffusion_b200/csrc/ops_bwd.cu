@@ -71,6 +71,7 @@ int build_wgrad(const WgradProblem& pr, WgradParams* out, int* n_items) {
     p.splits = static_cast<int>(splits);
     p.dw = pr.dw;
     p.ld = pr.ld;
+    p.db = pr.db;
     *n_items = static_cast<int>(base_items * splits);
     return MMD_OK;
 }
@@ -108,9 +109,12 @@ int launch_pack_weight_t(const float* w, act_t* dst, int co, int ci, int t, int 
 
 int launch_colsum(const act_t* x, long long rows, int C, float scale, float* out, cudaStream_t st, float* out2, const float* gscale) {
     if (C % 8 != 0 || C / 8 > 256) return fail(MMD_EINVAL, "colsum channels %d unsupported", C);
-    const long long blocks = std::max<long long>(1, std::min<long long>(4LL * num_sms(), (rows + 63) / 64));
+    const int rows_per_pass = std::max(1, 256 / (C / 8));
+    // every thread streams at least ~8 batches of 4 rows; at most two blocks per SM
+    const long long min_rpb = 32LL * rows_per_pass;
+    long long blocks = std::max<long long>(1, std::min<long long>(2LL * num_sms(), (rows + min_rpb - 1) / min_rpb));
     const long long rpb = (rows + blocks - 1) / blocks;
-    colsum_kernel<<<static_cast<unsigned>((rows + rpb - 1) / rpb), 256, 0, st>>>(x, rows, C, rpb, scale, out, out2, gscale);
+    colsum_kernel<<<static_cast<unsigned>((rows + rpb - 1) / rpb), 256, C * sizeof(float), st>>>(x, rows, C, rpb, scale, out, out2, gscale);
     MMD_CUDA_OK(cudaGetLastError());
     pdl_break(st);
     return MMD_OK;
@@ -229,7 +233,7 @@ static int gn_bwd_rows_per_block(int ns, int rows, int C) {
     const int target_blocks = 4 * num_sms();
     const int per_domain = std::max(1, target_blocks / std::max(1, ns));
     int rpb = (rows + per_domain - 1) / per_domain;
-    rpb = std::max(rpb, 4 * rows_per_pass);
+    rpb = std::max(rpb, 2 * GN_UNROLL * rows_per_pass);
     return std::min(rpb, rows);
 }
 
@@ -394,16 +398,21 @@ int mmd_op_conv_wgrad(const MmdConvDesc* d, const void* dy, float* dweight, floa
     pr.n = d->n;
     pr.ld = static_cast<long long>(ctot) * d->n_taps;
     float* dwpk = nullptr;
-    MMD_CUDA_OK(cudaMallocAsync(&dwpk, sizeof(float) * pr.ld * d->n, st));
-    MMD_CUDA_OK(cudaMemsetAsync(dwpk, 0, sizeof(float) * pr.ld * d->n, st));
+    const size_t dw_floats = static_cast<size_t>(pr.ld) * d->n;
+    MMD_CUDA_OK(cudaMallocAsync(&dwpk, sizeof(float) * (dw_floats + d->n), st));
+    MMD_CUDA_OK(cudaMemsetAsync(dwpk, 0, sizeof(float) * (dw_floats + d->n), st));
     pr.dw = dwpk;
+    if (dbias) pr.db = dwpk + dw_floats;   // bias gradient reduced by the wgrad kernel itself (ones-operand MMA)
     WgradParams wp;
     int items = 0;
     int r = build_wgrad(pr, &wp, &items);
     if (r == MMD_OK) r = launch_wgrad(wp, items, st);
     // caller's dweight is [n][ctot][taps] (reference layout), accumulated into
     if (r == MMD_OK) r = launch_unpack_wgrad(dwpk, dweight, d->n, ctot, d->n_taps, pr.ld, 0, 1.0f, st);
-    if (r == MMD_OK && dbias) r = launch_colsum(pr.dy, pr.g.tokens(), d->n, 1.0f, dbias, st);
+    if (r == MMD_OK && dbias) {
+        axpy_f32_kernel<<<(d->n + 255) / 256, 256, 0, st>>>(dwpk + dw_floats, dbias, d->n, nullptr);
+        if (cudaGetLastError() != cudaSuccess) r = fail(MMD_ECUDA, "bias gradient accumulate");
+    }
     cudaFreeAsync(dwpk, st);
     return r;
 }

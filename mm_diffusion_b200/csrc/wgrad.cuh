@@ -24,7 +24,8 @@ constexpr int WG_STAGES = 3;
 constexpr int WG_DY_BYTES = 2 * GEMM_BM * 128;   // two 64-channel chunks of 128 tokens
 constexpr int WG_A_BYTES = 2 * GEMM_BM * 128;
 constexpr int WG_STAGE_BYTES = WG_DY_BYTES + WG_A_BYTES;
-constexpr int WG_SMEM = WG_STAGES * WG_STAGE_BYTES + 256 + 1024;
+constexpr int WG_ONES_BYTES = 2048;   // 16 tokens x 128 B of fp16 ones: B operand of the bias-gradient MMA (any layout)
+constexpr int WG_SMEM = WG_STAGES * WG_STAGE_BYTES + WG_ONES_BYTES + 256 + 1024;
 
 struct alignas(64) WgradParams {
     CUtensorMap dy_map;               // dY [tokens][n], same token geometry as the activations, box (64, box[0..3])
@@ -44,10 +45,12 @@ struct alignas(64) WgradParams {
     int splits;           // token splits
     float* dw;            // [n][ld] fp32, packed column order k = (tap * total_chunks + chunk) * 64 + c
     long long ld;
+    float* db;            // [n] fp32 bias gradient = column sums of dY (null = off), accumulated with atomics
 };
 
 struct WgradItem {
     int n_tile, tap, src, chunk0, ncols, col0, m_begin, m_end;
+    bool bias;   // this item also reduces dY over its tokens (first column block of every (n tile, split))
 };
 
 MMD_DEVINL WgradItem wgrad_decode(const WgradParams& p, int item) {
@@ -56,6 +59,7 @@ MMD_DEVINL WgradItem wgrad_decode(const WgradParams& p, int item) {
     int r = item / p.splits;
     const int cb = r % (p.blocks_per_tap * p.n_taps);
     w.n_tile = r / (p.blocks_per_tap * p.n_taps);
+    w.bias = (p.db != nullptr) && (cb == 0);
     w.tap = cb / p.blocks_per_tap;
     int b = cb % p.blocks_per_tap;
     int chunk_base = 0;
@@ -93,7 +97,8 @@ MMD_DEVINL void wgrad_tile_origin(const WgradParams& p, int m_idx, int* c /*[5]*
 __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_kernel(const __grid_constant__ WgradParams p, int n_items) {
     extern __shared__ uint8_t wg_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(wg_smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE_BYTES);
+    uint8_t* ones = smem + WG_STAGES * WG_STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ones + WG_ONES_BYTES);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + WG_STAGES;
     uint64_t* tfull_bar = bars + 2 * WG_STAGES;
@@ -116,7 +121,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_kernel(const __grid_
         }
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 256);
+    for (int i = threadIdx.x; i < WG_ONES_BYTES / 16; i += WG_THREADS)
+        reinterpret_cast<uint4*>(ones)[i] = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
+    fence_proxy_async_smem();
+    if (warp == 1) tmem_alloc(tmem_slot, 512);   // two accumulators [0,128) [128,256) + their bias columns [256,272) [272,288)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -157,6 +165,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_kernel(const __grid_
         if (lane == 0) {
             constexpr uint32_t idesc128 = umma_idesc_f16(128, 128, 1, 1);
             constexpr uint32_t idesc64 = umma_idesc_f16(128, 64, 1, 1);
+            constexpr uint32_t idesc16 = umma_idesc_f16(128, 16, 1, 1);
+            const uint64_t ones_d = umma_desc_sw128(smem_u32(ones), GEMM_BM * 128, 1024);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -180,6 +190,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_kernel(const __grid_
 #pragma unroll
                     for (int ks = 0; ks < GEMM_BM / 16; ++ks) {
                         umma_f16_ss(d_tmem, ad0 + ks * (2048 >> 4), bd0 + ks * (2048 >> 4), idesc, first ? 0u : 1u);
+                        if (w.bias) umma_f16_ss(tmem_base + 256 + acc * 16, ad0 + ks * (2048 >> 4), ones_d, idesc16, first ? 0u : 1u);
                         first = false;
                     }
                     umma_commit(&empty_bar[stage]);
@@ -223,6 +234,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_kernel(const __grid_
                     }
                 }
             }
+            if (w.bias) {
+                uint32_t bv[16];
+                tmem_ld16(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + 256 + acc * 16, bv);
+                tmem_ld_wait();
+                if (n_row < p.n && !empty_range) atomicAdd(&p.db[n_row], __uint_as_float(bv[0]));
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -234,7 +251,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_kernel(const __grid_
     if (warp == 1) {
         tc_fence_after();
         __syncwarp();
-        tmem_dealloc(tmem_base, 256);
+        tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -271,33 +288,50 @@ __global__ void pack_weight_t_kernel(const float* __restrict__ w, act_t* __restr
 }
 
 // Column sums of a [rows][C] fp16 matrix into fp32 (bias gradient): out[c] += scale * sum_r x[r][c].
+// Rows are streamed with four independent 16-byte loads in flight per thread; the per-thread partials are folded in shared
+// memory so a block issues ONE global atomic per channel.
 __global__ void __launch_bounds__(256) colsum_kernel(const act_t* __restrict__ x, long long rows, int C, long long rows_per_block,
                                                      float scale, float* __restrict__ out, float* __restrict__ out2,
                                                      const float* __restrict__ gscale) {
+    extern __shared__ float csh[];   // [C]
     if (gscale) scale *= gscale[1];
+    for (int i = threadIdx.x; i < C; i += blockDim.x) csh[i] = 0.f;
+    __syncthreads();
     const int vpr = C / 8;
     const int rows_per_pass = blockDim.x / vpr;
     const int vec = threadIdx.x % vpr, rsub = threadIdx.x / vpr;
-    if (rsub >= rows_per_pass) return;
-    const long long r0 = blockIdx.x * rows_per_block;
-    const long long r1 = min(rows, r0 + rows_per_block);
-    float acc[8];
+    if (rsub < rows_per_pass) {
+        const long long r0 = blockIdx.x * rows_per_block;
+        const long long r1 = min(rows, r0 + rows_per_block);
+        float acc[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    for (long long r = r0 + rsub; r < r1; r += rows_per_pass) {
-        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(x + r * C + vec * 8));
-        const __half2* h = reinterpret_cast<const __half2*>(&raw);
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        for (long long r = r0 + rsub; r < r1; r += 4LL * rows_per_pass) {
+            uint4 raw[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float2 f = __half22float2(h[i]);
-            acc[2 * i] += f.x;
-            acc[2 * i + 1] += f.y;
+            for (int u = 0; u < 4; ++u) {
+                const long long rr = r + static_cast<long long>(u) * rows_per_pass;
+                raw[u] = (rr < r1) ? __ldg(reinterpret_cast<const uint4*>(x + rr * C + vec * 8)) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const __half2* h = reinterpret_cast<const __half2*>(&raw[u]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 f = __half22float2(h[i]);
+                    acc[2 * i] += f.x;
+                    acc[2 * i + 1] += f.y;
+                }
+            }
         }
-    }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        atomicAdd(&out[vec * 8 + i], scale * acc[i]);
-        if (out2) atomicAdd(&out2[vec * 8 + i], scale * acc[i]);   // two biases folded into one GEMM (out-conv + skip-conv)
+        for (int i = 0; i < 8; ++i) atomicAdd(&csh[vec * 8 + i], acc[i]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        const float v = scale * csh[i];
+        atomicAdd(&out[i], v);
+        if (out2) atomicAdd(&out2[i], v);   // two biases folded into one GEMM (out-conv + skip-conv)
     }
 }
 // dst[k][co] = w[co][ci][t] with k = t * Ci + ci: transpose of the stem's packed [Co][64] matrix (rows >= T * Ci stay zero)
