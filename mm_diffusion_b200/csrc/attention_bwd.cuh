@@ -39,35 +39,38 @@ struct alignas(64) AttnBwdParams {
     float rs;                                     // d^-1/2
 };
 
+constexpr int AB_THREADS = 320;   // warps 0-7 gradient math (two column halves x four lane quarters), warp 8 TMA, warp 9 MMA
+
 template <int D>
 struct AttnBwdSmem {
     static constexpr int NCH = (D + 63) / 64;
     static constexpr int TILE = NCH * 128 * 128;
+    static constexpr int YST = (D == 64) ? 2 : 1;      // Y stages: the next Y tile streams in under the current one's math
     static constexpr int X1_OFF = 0;
     static constexpr int X2_OFF = TILE;
-    static constexpr int Y1_OFF = 2 * TILE;
-    static constexpr int Y2_OFF = 3 * TILE;
-    static constexpr int DS_OFF = 4 * TILE;          // 128 x 128 fp16 (two 64-column chunks)
+    static constexpr int Y_OFF = 2 * TILE;             // per stage: Y1 | Y2
+    static constexpr int DS_OFF = Y_OFF + YST * 2 * TILE;   // 128 x 128 fp16 (two 64-column chunks)
     static constexpr int P_OFF = DS_OFF + 32768;
-    static constexpr int STAT_OFF = P_OFF + 32768;   // lse[128] delta[128] floats (KV pass: per Y column)
+    static constexpr int STAT_OFF = P_OFF + 32768;     // lse[128] delta[128] floats (KV pass: per Y column)
     static constexpr int BAR_OFF = STAT_OFF + 1024;
     static constexpr int TOTAL = BAR_OFF + 256 + 1024;
     static_assert(TOTAL <= 232448, "attention backward shared memory budget");
 };
 
 template <int D, bool KV>
-__global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
+__global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
     using S = AttnBwdSmem<D>;
+    constexpr int YST = S::YST;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
     uint64_t* x_full = bars;        // X1 + X2 landed
-    uint64_t* y_full = bars + 1;    // Y1 + Y2 of the current tile landed
-    uint64_t* y_empty = bars + 2;   // accumulate MMAs of the current tile retired (Y, dS, P reusable)
-    uint64_t* s_full = bars + 3;    // S and dP of the current tile are in TMEM
-    uint64_t* p_ready = bars + 4;   // 128 arrivals: dS (and P) written, S / dP consumed
-    uint64_t* acc_full = bars + 5;  // all accumulate MMAs retired
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+    uint64_t* y_full = bars + 1;    // [2] Y1 + Y2 of a stage landed
+    uint64_t* y_empty = bars + 3;   // [2] accumulate MMAs that read the stage retired (also frees dS / P)
+    uint64_t* s_full = bars + 5;    // S and dP of the current tile are in TMEM
+    uint64_t* p_ready = bars + 6;   // 256 arrivals: dS (and P) written, S / dP consumed
+    uint64_t* acc_full = bars + 7;  // all accumulate MMAs retired
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
     float* s_lse = reinterpret_cast<float*>(smem + S::STAT_OFF);
     float* s_delta = s_lse + 128;
 
@@ -103,14 +106,13 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
         tma_prefetch_desc(&p.y1_map);
         tma_prefetch_desc(&p.y2_map);
         mbar_init(x_full, 1);
-        mbar_init(y_full, 1);
-        mbar_init(y_empty, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&y_full[i], 1); mbar_init(&y_empty[i], 1); }
         mbar_init(s_full, 1);
-        mbar_init(p_ready, 128);
+        mbar_init(p_ready, 256);
         mbar_init(acc_full, 1);
         fence_mbar_init();
     }
-    if (warp == 5) tmem_alloc(tmem_slot, 512);
+    if (warp == 9) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -120,7 +122,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
     const uint32_t tmem_A1 = tmem_base + 256;     // D columns
     const uint32_t tmem_A2 = tmem_base + 384;     // D columns (KV)
 
-    if (warp == 4) {
+    if (warp == 8) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             mbar_expect_tx(x_full, 2 * S::TILE);
@@ -129,33 +131,32 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
                 tma_load_2d(smem + S::X2_OFF + ch * 16384, &p.x2_map, x_full, p.x2_col0 + head * D + ch * 64, x_row0);
             }
             for (int t = 0; t < T; ++t) {
+                const int st = t % YST;
+                const uint32_t use = static_cast<uint32_t>(t / YST);
                 int yrow, yvalid;
                 y_tile(t, yrow, yvalid);
-                mbar_wait(y_empty, (t & 1) ^ 1);
-                mbar_expect_tx(y_full, 2 * S::TILE);
+                mbar_wait(&y_empty[st], (use & 1) ^ 1);
+                mbar_expect_tx(&y_full[st], 2 * S::TILE);
+                uint8_t* y1 = smem + S::Y_OFF + st * 2 * S::TILE;
                 for (int ch = 0; ch < S::NCH; ++ch) {
-                    tma_load_2d(smem + S::Y1_OFF + ch * 16384, &p.y1_map, y_full, p.y1_col0 + head * D + ch * 64, yrow);
-                    tma_load_2d(smem + S::Y2_OFF + ch * 16384, &p.y2_map, y_full, p.y2_col0 + head * D + ch * 64, yrow);
+                    tma_load_2d(y1 + ch * 16384, &p.y1_map, &y_full[st], p.y1_col0 + head * D + ch * 64, yrow);
+                    tma_load_2d(y1 + S::TILE + ch * 16384, &p.y2_map, &y_full[st], p.y2_col0 + head * D + ch * 64, yrow);
                 }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == 9) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
             constexpr uint32_t idesc_s = umma_idesc_f16(128, 128, 0, 0);
             constexpr uint32_t idesc_acc = umma_idesc_f16(128, D, 0, 1);   // B (Y tile) is MN-major
             const uint32_t x1 = smem_u32(smem + S::X1_OFF), x2 = smem_u32(smem + S::X2_OFF);
-            const uint32_t y1 = smem_u32(smem + S::Y1_OFF), y2 = smem_u32(smem + S::Y2_OFF);
             const uint64_t dsd0 = umma_desc_sw128(smem_u32(smem + S::DS_OFF), 16, 1024);
             const uint64_t pd0 = umma_desc_sw128(smem_u32(smem + S::P_OFF), 16, 1024);
-            const uint64_t y1m = umma_desc_sw128(y1, 128 * 128, 1024);   // MN-major views of the Y tiles
-            const uint64_t y2m = umma_desc_sw128(y2, 128 * 128, 1024);
-            mbar_wait(x_full, 0);
-            for (int t = 0; t < T; ++t) {
-                int yrow, yvalid;
-                y_tile(t, yrow, yvalid);
-                mbar_wait(y_full, t & 1);
+            auto issue_s = [&](int t) {   // S = X1 Y1^T, dP = X2 Y2^T of tile t
+                const int st = t % YST;
+                mbar_wait(&y_full[st], (t / YST) & 1);
                 tc_fence_after();
+                const uint32_t y1 = smem_u32(smem + S::Y_OFF + st * 2 * S::TILE), y2 = y1 + S::TILE;
 #pragma unroll
                 for (int ks = 0; ks < D / 16; ++ks) {
                     const uint32_t off = (ks >> 2) * 16384 + (ks & 3) * 32;
@@ -169,8 +170,18 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
                                 ks != 0 ? 1u : 0u);
                 }
                 umma_commit(s_full);
+            };
+            mbar_wait(x_full, 0);
+            issue_s(0);
+            for (int t = 0; t < T; ++t) {
+                const int st = t % YST;
+                int yrow, yvalid;
+                y_tile(t, yrow, yvalid);
                 mbar_wait(p_ready, t & 1);
                 tc_fence_after();
+                const uint32_t y1 = smem_u32(smem + S::Y_OFF + st * 2 * S::TILE);
+                const uint64_t y1m = umma_desc_sw128(y1, 128 * 128, 1024);   // MN-major views of the Y tiles
+                const uint64_t y2m = umma_desc_sw128(y1 + S::TILE, 128 * 128, 1024);
                 const int nks = (yvalid + 15) >> 4;
                 for (int ks = 0; ks < nks; ++ks) {
                     const uint64_t aoff = static_cast<uint64_t>((ks >> 2) * (16384 >> 4) + (ks & 3) * 2);
@@ -178,14 +189,16 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
                     if (KV)
                         umma_f16_ss(tmem_A2, pd0 + aoff, y2m + static_cast<uint64_t>(ks) * (2048 >> 4), idesc_acc, (t | ks) != 0 ? 1u : 0u);
                 }
-                umma_commit(y_empty);
+                umma_commit(&y_empty[st]);
                 if (t == T - 1) umma_commit(acc_full);
+                else issue_s(t + 1);   // S / dP are free (p_ready(t)); queued right behind the accumulate MMAs
             }
         }
     } else {
-        // ===================== gradient math (thread = X row) =====================
-        const int row = warp * 32 + lane;
-        const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+        // ===================== gradient math (thread = X row, half of the Y columns) =====================
+        const int quarter = warp & 3, half = warp >> 2;
+        const int row = quarter * 32 + lane;
+        const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
         const float* lse_h = p.lse + static_cast<size_t>(head) * p.stat_ld;
         const float* delta_h = p.delta + static_cast<size_t>(head) * p.stat_ld;
         float my_lse = 0.f, my_delta = 0.f;
@@ -194,31 +207,32 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
             my_lse = lse_h[qr];
             my_delta = delta_h[qr];
         }
-        uint8_t* ds_smem = smem + S::DS_OFF;
-        uint8_t* p_smem = smem + S::P_OFF;
+        uint8_t* ds_chunk = smem + S::DS_OFF + half * 16384;   // this half's 64-column chunk
+        uint8_t* p_chunk = smem + S::P_OFF + half * 16384;
         for (int t = 0; t < T; ++t) {
             int yrow, yvalid;
             y_tile(t, yrow, yvalid);
             if (KV) {
                 // per-column (query) statistics of this Y tile; the previous tile's readers are past their p_ready arrival
-                named_bar_sync(1, 128);
-                const long long qr = min(static_cast<long long>(yrow + row), p.q_rows_total - 1);
-                s_lse[row] = lse_h[qr];
-                s_delta[row] = delta_h[qr];
-                named_bar_sync(1, 128);
+                named_bar_sync(1, 256);
+                if (half == 0) {
+                    const long long qr = min(static_cast<long long>(yrow + row), p.q_rows_total - 1);
+                    s_lse[row] = lse_h[qr];
+                    s_delta[row] = delta_h[qr];
+                }
+                named_bar_sync(1, 256);
             }
             mbar_wait(s_full, t & 1);
             tc_fence_after();
             // dS / P buffers are free once the accumulate MMAs of the previous tile have retired
-            if (t > 0) mbar_wait(y_empty, (t - 1) & 1);
+            if (t > 0) mbar_wait(&y_empty[(t - 1) % YST], ((t - 1) / YST) & 1);
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
+            for (int cc = 0; cc < 2; ++cc) {
+                const int c = half * 2 + cc;   // 32-column chunk of the tile
                 uint32_t sv[32], dv[32];
                 tmem_ld32(tmem_S + lane_base + c * 32, sv);
                 tmem_ld32(tmem_DP + lane_base + c * 32, dv);
                 tmem_ld_wait();
-                uint8_t* ds_chunk = ds_smem + (c >> 1) * 16384;
-                uint8_t* p_chunk = p_smem + (c >> 1) * 16384;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     uint4 dpk, ppk;
@@ -243,38 +257,39 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
                             pw[k] = *reinterpret_cast<const uint32_t*>(&hp);
                         }
                     }
-                    *reinterpret_cast<uint4*>(ds_chunk + sw128_off(row, (c & 1) * 4 + j)) = dpk;
-                    if (KV) *reinterpret_cast<uint4*>(p_chunk + sw128_off(row, (c & 1) * 4 + j)) = ppk;
+                    *reinterpret_cast<uint4*>(ds_chunk + sw128_off(row, cc * 4 + j)) = dpk;
+                    if (KV) *reinterpret_cast<uint4*>(p_chunk + sw128_off(row, cc * 4 + j)) = ppk;
                 }
             }
             fence_proxy_async_smem();
             tc_fence_before();
             mbar_arrive(p_ready);
         }
-        // ---- epilogue: accumulators -> fp16 gradients
+        // ---- epilogue: accumulators -> fp16 gradients (each half stores D / 2 columns of its row)
         mbar_wait(acc_full, 0);
         tc_fence_after();
+        constexpr int HC = D / 2;
 #pragma unroll 1
         for (int which = 0; which < (KV ? 2 : 1); ++which) {
-            const uint32_t t_acc = (which == 0 ? tmem_A1 : tmem_A2) + lane_base;
+            const uint32_t t_acc = (which == 0 ? tmem_A1 : tmem_A2) + lane_base + half * HC;
             act_t* obase = (which == 0) ? p.out1 : p.out2;
             const int old = (which == 0) ? p.out1_ld : p.out2_ld;
             const int ocol = (which == 0) ? p.out1_col0 : p.out2_col0;
-            act_t* orow = obase + static_cast<size_t>(x_row0 + row) * old + ocol + head * D;
+            act_t* orow = obase + static_cast<size_t>(x_row0 + row) * old + ocol + head * D + half * HC;
 #pragma unroll
-            for (int c = 0; c < D / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld32(t_acc + c * 32, v);
+            for (int c = 0; c < HC / 16; ++c) {
+                uint32_t v[16];
+                tmem_ld16(t_acc + c * 16, v);
                 tmem_ld_wait();
                 if (row < x_valid) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
+                    for (int j = 0; j < 2; ++j) {
                         uint4 pk;
                         __half2* ph2 = reinterpret_cast<__half2*>(&pk);
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
                             ph2[k] = __floats2half2_rn(__uint_as_float(v[j * 8 + 2 * k]), __uint_as_float(v[j * 8 + 2 * k + 1]));
-                        *reinterpret_cast<uint4*>(orow + c * 32 + j * 8) = pk;
+                        *reinterpret_cast<uint4*>(orow + c * 16 + j * 8) = pk;
                     }
                 }
             }
@@ -283,7 +298,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_kernel(const __grid_c
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) {
+    if (warp == 9) {
         __syncwarp();
         tmem_dealloc(tmem_base, 512);
     }

@@ -212,9 +212,9 @@ static int attn_bwd_launch_d(const AttnBwdParams& pq, const AttnBwdParams& pkv, 
     }
     const int gq = pq.B * pq.n_blocks * pq.heads * pq.x_tiles;
     const int gk = pkv.B * pkv.n_blocks * pkv.heads * pkv.x_tiles;
-    attn_bwd_kernel<D, false><<<gq, ATT_THREADS, AttnBwdSmem<D>::TOTAL, st>>>(pq);
+    attn_bwd_kernel<D, false><<<gq, AB_THREADS, AttnBwdSmem<D>::TOTAL, st>>>(pq);
     MMD_CUDA_OK(cudaGetLastError());
-    attn_bwd_kernel<D, true><<<gk, ATT_THREADS, AttnBwdSmem<D>::TOTAL, st>>>(pkv);
+    attn_bwd_kernel<D, true><<<gk, AB_THREADS, AttnBwdSmem<D>::TOTAL, st>>>(pkv);
     MMD_CUDA_OK(cudaGetLastError());
     pdl_break(st);
     return MMD_OK;
