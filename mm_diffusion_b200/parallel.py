@@ -1,4 +1,4 @@
-"""Batch-shard helpers for multi-GPU sampling (one process per GPU, torch.distributed).
+"""Batch-shard helpers for multi-GPU sampling and training (one process per GPU, torch.distributed).
 
 The denoising path has no exchange inside a step: every rank holds a full weight replica and runs the
 whole loop on its slice of the batch; the only collective is the gather of finished samples, which replaces the
@@ -42,3 +42,29 @@ def gather_samples(sample: Dict[str, torch.Tensor], group=None) -> Dict[str, tor
     dist.all_gather_into_tensor(gv, video, group=group)
     dist.all_gather_into_tensor(ga, audio, group=group)
     return {"video": gv, "audio": ga}
+
+
+def allreduce_flat_gradients(model, group=None, average: bool = True) -> bool:
+    """Data-parallel gradient exchange of a training step in ONE collective: the sm_100a backward hands every parameter
+    gradient out as a view of a single flat fp32 buffer (`model.flat_grad`, 0.53 GB for the production network), so the
+    all-reduce over NCCL / NVLink is one call on that buffer instead of DDP's per-bucket calls
+    (reference: DistributedDataParallel in TrainLoop, mm_diffusion/multimodal_train_util.py:120-136).
+    Returns True if the parameters' `.grad` alias the reduced buffer (the normal case: autograd adopts the views), and
+    copies the reduced values into `.grad` otherwise."""
+    flat = getattr(model, "flat_grad", None)
+    if flat is None:
+        raise RuntimeError("allreduce_flat_gradients: no backward has run on this model yet")
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        if average:
+            flat.div_(dist.get_world_size(group))
+    lo = flat.data_ptr()
+    hi = lo + flat.numel() * flat.element_size()
+    aliased = True
+    for p, view in zip(model.parameters(), model.flat_grad_views):
+        if p.grad is None or view is None:
+            continue
+        if not (lo <= p.grad.data_ptr() < hi):
+            aliased = False
+            p.grad.copy_(view)
+    return aliased

@@ -106,6 +106,8 @@ class _UNetFunction(torch.autograd.Function):
             for d in shape:
                 n *= d
             grads.append(flat[off:off + n].view(shape) if needs else None)
+        # kept for parallel.allreduce_flat_gradients: one collective over the flat buffer exchanges every gradient
+        model.flat_grad, model.flat_grad_views = flat, grads
         return (None, None, d_vi, d_ai, None, *grads)
 
 

@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from mm_diffusion_b200.parallel import gather_samples, rank_seed, shard_bounds, to_uint8_video
+from mm_diffusion_b200.parallel import allreduce_flat_gradients, gather_samples, rank_seed, shard_bounds, to_uint8_video
 
 
 def _free_port():
@@ -57,3 +57,43 @@ def test_shard_bounds_partition_the_batch():
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
     assert len({rank_seed(7, r) for r in range(8)}) == 8
+
+
+class _FlatGradModel(torch.nn.Module):
+    """Stand-in with the gradient layout the sm_100a backward produces: .grad tensors are views of one flat buffer."""
+
+    def __init__(self, rank, alias=True):
+        super().__init__()
+        self.a = torch.nn.Parameter(torch.zeros(3, 4))
+        self.b = torch.nn.Parameter(torch.zeros(5))
+        self.flat_grad = torch.arange(20, dtype=torch.float32) * (rank + 1)   # 12 + pad to 15 + 5
+        self.flat_grad_views = [self.flat_grad[0:12].view(3, 4), self.flat_grad[15:20]]
+        self.a.grad = self.flat_grad_views[0] if alias else self.flat_grad_views[0].clone()
+        self.b.grad = self.flat_grad_views[1] if alias else self.flat_grad_views[1].clone()
+
+
+def _grad_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ok = True
+        for alias in (True, False):
+            m = _FlatGradModel(rank, alias)
+            aliased = allreduce_flat_gradients(m)
+            mean = torch.arange(20, dtype=torch.float32) * (sum(range(1, world + 1)) / world)
+            ok = ok and aliased == alias and torch.allclose(m.a.grad, mean[0:12].view(3, 4)) and torch.allclose(m.b.grad, mean[15:20])
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_world2_gloo():
+    """The training step's only collective: one all-reduce over the flat gradient buffer averages every parameter
+    gradient on every rank (views alias the buffer; non-aliased .grad tensors are refreshed by copy)."""
+    world = 2
+    port = _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_grad_worker, args=(world, port, ret), nprocs=world, join=True)
+        assert dict(ret) == {0: True, 1: True}
