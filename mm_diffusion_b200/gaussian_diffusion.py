@@ -354,7 +354,8 @@ class GaussianDiffusion:
                 loss = mean_flat((pred[condition] - prev_cond) ** 2)
                 loss_scale = float(2 ** 20) if use_fp16 else 1.0
                 grad = th.autograd.grad(loss.mean() * loss_scale, x[target])[0]
-                x = {condition: pred[condition].detach(),
+                # like the reference, the yielded dict keeps q(x_t | condition) for the conditioned modality (:760-770, 816)
+                x = {condition: x[condition],
                      target: (pred[target] - nzm * grad * class_scale * float(sqrt_ab[i])).detach()}
             yield x
 

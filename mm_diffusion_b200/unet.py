@@ -90,6 +90,11 @@ class _UNetFunction(torch.autograd.Function):
         lib = _lib.load()
         dev = model._handle_device
         B = ctx.batch
+        if model.checkpoint_rng_compat:
+            # The reference re-runs every (always checkpointed) CrossAttentionBlock in backward and draws a fresh
+            # random.randint there (multimodal_unet.py:619-622 under nn.py:233-279).  We differentiate the function
+            # that was evaluated, but consume the same number of draws so the global `random` stream stays aligned.
+            model.draw_shifts()
         with torch.cuda.device(dev):
             vshape = (B, model._cfg.video_f, model.video_out_channels, model._cfg.video_h, model._cfg.video_w)
             ashape = (B, model.audio_out_channels, model._cfg.audio_l)
@@ -153,6 +158,7 @@ class MultimodalUNet(nn.Module):
                      num_res_blocks, cross_attention_resolutions, cross_attention_windows, cross_attention_shift,
                      video_attention_resolutions, audio_attention_resolutions, channel_mult, num_heads,
                      num_head_channels, max_batch)
+        self.checkpoint_rng_compat = True   # see _UNetFunction.backward
         self._handle = None          # MmdModel* (created lazily on the parameters' CUDA device)
         self._handle_device = None
         self._synced: Dict[str, tuple] = {}
