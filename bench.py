@@ -140,7 +140,8 @@ def ncu_traffic(kernel, batch):
             t = json.load(f)
         if t.get("batch") != batch:
             return None
-        return t["kernels"][kernel]["dram_bytes_per_launch"]
+        ks = t["kernels"]
+        return (ks.get(kernel) or ks["mmd::" + kernel])["dram_bytes_per_launch"]
     except Exception:
         return None
 

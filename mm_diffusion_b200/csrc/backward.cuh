@@ -269,13 +269,16 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(GnBwdArgs g, GnBwdOut
     base += static_cast<size_t>(ns) * g.R * ld;
     dbase += static_cast<size_t>(ns) * g.R * dld;
     const act_t* dyb = g.dy + static_cast<size_t>(ns) * g.R * C + c0;
-    float ca[8], cb[8], crs[8], cmr[8], cp[8], cq[8], cr[8];   // dx = p du - q - xh r
+    // dx = p du - q - xh r with xh = x rs - mr  ==>  dx = p du + x (-rs r) + (mr r - q): five coefficient rows in registers
+    float ca[8], cb[8], cp[8], cx[8], cc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int c = c0 + i;
         const int grp = c / cpg;
-        ca[i] = coef[c]; cb[i] = coef[C + c]; crs[i] = coef[2 * C + c]; cmr[i] = coef[3 * C + c];
-        cp[i] = pc[c]; cq[i] = qr[2 * grp]; cr[i] = qr[2 * grp + 1];
+        ca[i] = coef[c]; cb[i] = coef[C + c];
+        cp[i] = pc[c];
+        cx[i] = -coef[2 * C + c] * qr[2 * grp + 1];
+        cc[i] = coef[3 * C + c] * qr[2 * grp + 1] - qr[2 * grp];
     }
     for (int r = r0 + rsub; r < r1; r += GN_UNROLL * rows_per_pass) {
         uint4 xr[GN_UNROLL], dr[GN_UNROLL], pv[GN_UNROLL];
@@ -302,8 +305,7 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(GnBwdArgs g, GnBwdOut
                 const float x = __half2float(xh[i]);
                 float du = __half2float(dh[i]);
                 if (g.do_silu) du *= dsilu_fast(fmaf(x, ca[i], cb[i]));
-                const float xn = fmaf(x, crs[i], -cmr[i]);
-                float dx = cp[i] * du - cq[i] - xn * cr[i];
+                float dx = fmaf(cp[i], du, fmaf(x, cx[i], cc[i]));
                 if (dacc) dx += __half2float(ph[i]);
                 oh[i] = __float2half_rn(dx);
             }

@@ -55,8 +55,11 @@ struct WgradItem {
 
 MMD_DEVINL WgradItem wgrad_decode(const WgradParams& p, int item) {
     WgradItem w;
-    const int split = item % p.splits;
-    int r = item / p.splits;
+    // split-major item order: CTAs that run at the same time work on the SAME token range for different taps / column
+    // blocks / n tiles, so the dY and activation tiles they share are served by L2 instead of being re-read from HBM
+    const int per_split = p.n_tiles * p.blocks_per_tap * p.n_taps;
+    const int split = item / per_split;
+    int r = item % per_split;
     const int cb = r % (p.blocks_per_tap * p.n_taps);
     w.n_tile = r / (p.blocks_per_tap * p.n_taps);
     w.bias = (p.db != nullptr) && (cb == 0);
