@@ -603,7 +603,8 @@ __global__ void resample_bwd_kernel(const act_t* __restrict__ dy, act_t* __restr
 // ---------------------------------------------------------------------------
 // Narrow output heads (video_out Conv3d 3x3x3 -> 3 channels, audio_out Conv1d k3 -> 1 channel; forward: conv_gemm BN = 16
 // with an fp32 strided scatter).  dout is the fp32 gradient in the API layout; token coordinates follow the forward
-// geometry (dims[0..3], innermost first); `gscale[0]` scales it into the fp16 gradient range.
+// geometry (dims[0..3], innermost first); `gscale[0]` scales it into the fp16 gradient range.  Both adjoints run on the
+// tensor-core kernels (see head_im2col_bwd_kernel below).
 // ---------------------------------------------------------------------------
 struct HeadGeom {
     int ncoord;                 // token coordinates used (1..4)
@@ -615,91 +616,6 @@ struct HeadGeom {
     int tap[27][3];
     int C;                      // input channels (multiple of 8)
 };
-
-// dx[tok][c] = s * sum_{tap, n} dout[n][tok - delta(tap)] * w[n][c][tap]      (w: fp32 [n_out][C][n_taps])
-__global__ void __launch_bounds__(256) head_dgrad_kernel(HeadGeom g, const float* __restrict__ dout, const float* __restrict__ w,
-                                                         act_t* __restrict__ dx, long long tokens, const float* __restrict__ gscale) {
-    extern __shared__ float hw[];   // [n_taps * n_out][C]
-    const int terms = g.n_taps * g.n_out;
-    for (int i = threadIdx.x; i < terms * g.C; i += blockDim.x) {
-        const int c = i % g.C, tn = i / g.C;
-        const int n = tn % g.n_out, t = tn / g.n_out;
-        hw[i] = w[(static_cast<size_t>(n) * g.C + c) * g.n_taps + t];
-    }
-    __syncthreads();
-    const float s = gscale ? gscale[0] : 1.0f;
-    const int vpr = g.C / 8;
-    const long long total = tokens * vpr;
-    for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
-         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int v = static_cast<int>(idx % vpr);
-        long long tok = idx / vpr;
-        int co[4];
-        long long r = tok;
-        for (int i = 0; i < 4; ++i) { co[i] = static_cast<int>(r % g.dims[i]); r /= g.dims[i]; }
-        float acc[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-        for (int t = 0; t < g.n_taps; ++t) {
-            const int c0 = co[0] - g.tap[t][0], c1 = co[1] - g.tap[t][1], c2 = co[2] - g.tap[t][2];
-            if (c0 < 0 || c0 >= g.dims[0] || c1 < 0 || c1 >= g.dims[1] || c2 < 0 || c2 >= g.dims[2]) continue;
-            const long long off = c0 * g.ostride[0] + c1 * g.ostride[1] + c2 * g.ostride[2] + co[3] * g.ostride[3];
-            for (int n = 0; n < g.n_out; ++n) {
-                const float dv = __ldg(dout + off + n * g.ostride_c) * s;
-                const float* wr = hw + (t * g.n_out + n) * g.C + v * 8;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) acc[i] = fmaf(dv, wr[i], acc[i]);
-            }
-        }
-        uint4 o;
-        __half2* oh = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) oh[i] = __floats2half2_rn(acc[2 * i], acc[2 * i + 1]);
-        reinterpret_cast<uint4*>(dx)[idx] = o;
-    }
-}
-
-// dw[n][c][tap] += sum_tok dout[n][tok] * a[tok + delta(tap)][c];  db[n] += sum_tok dout[n][tok]   (unscaled fp32 in/out)
-// blockDim.x == C; thread = channel; every block walks a token range and keeps its n_out * n_taps partials in registers.
-template <int TERMS>
-__global__ void head_wgrad_kernel(HeadGeom g, const float* __restrict__ dout, const act_t* __restrict__ a, float* __restrict__ dw,
-                                  float* __restrict__ db, long long tokens, long long tokens_per_block) {
-    const int c = threadIdx.x;
-    float acc[TERMS];
-#pragma unroll
-    for (int i = 0; i < TERMS; ++i) acc[i] = 0.f;
-    float bsum = 0.f;
-    const long long t0 = blockIdx.x * tokens_per_block;
-    const long long t1 = min(tokens, t0 + tokens_per_block);
-    for (long long tok = t0; tok < t1; ++tok) {
-        int co[4];
-        long long r = tok;
-        for (int i = 0; i < 4; ++i) { co[i] = static_cast<int>(r % g.dims[i]); r /= g.dims[i]; }
-        // a-token `tok` contributes to output tokens tok - delta(tap)
-        const float av = __half2float(a[tok * g.C + c]);
-#pragma unroll
-        for (int t = 0; t < TERMS; ++t) {
-            const int tp = t / g.n_out, n = t - tp * g.n_out;
-            if (tp < g.n_taps) {
-                const int c0 = co[0] - g.tap[tp][0], c1 = co[1] - g.tap[tp][1], c2 = co[2] - g.tap[tp][2];
-                if (c0 >= 0 && c0 < g.dims[0] && c1 >= 0 && c1 < g.dims[1] && c2 >= 0 && c2 < g.dims[2]) {
-                    const long long off = c0 * g.ostride[0] + c1 * g.ostride[1] + c2 * g.ostride[2] + co[3] * g.ostride[3];
-                    acc[t] = fmaf(__ldg(dout + off + n * g.ostride_c), av, acc[t]);
-                }
-            }
-        }
-        if (db != nullptr && c < g.n_out) {
-            const long long off = co[0] * g.ostride[0] + co[1] * g.ostride[1] + co[2] * g.ostride[2] + co[3] * g.ostride[3];
-            bsum += dout[off + c * g.ostride_c];
-        }
-    }
-#pragma unroll
-    for (int t = 0; t < TERMS; ++t) {
-        const int tp = t / g.n_out, n = t - tp * g.n_out;
-        if (tp < g.n_taps) atomicAdd(&dw[(static_cast<size_t>(n) * g.C + c) * g.n_taps + tp], acc[t]);
-    }
-    if (db != nullptr && c < g.n_out) atomicAdd(&db[c], bsum);
-}
 
 // Tensor-core path of the head adjoints: G[tok][t * n_out + n] = s * dout[n][tok - delta(t)] (fp16, zero outside the
 // tensor and in the padding columns).  Then dX = G * Wt (forward implicit-GEMM kernel, one tap) and

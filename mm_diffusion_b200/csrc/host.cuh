@@ -222,7 +222,22 @@ int launch_gn_temporal_bwd(const act_t* x, const act_t* dy, act_t* dx, const flo
 int launch_temporal_attn_bwd(const act_t* qkv, const act_t* d_out, act_t* dqkv, int B, int F, int P, int C, int heads,
                              cudaStream_t st);
 int launch_resample_bwd(const act_t* dy, act_t* dx, int mode, int n, int h, int w, int c, int accumulate, cudaStream_t st);
-int launch_head_dgrad(const HeadGeom& g, const float* dout, const float* w, act_t* dx, const float* gscale, cudaStream_t st);
-int launch_head_wgrad(const HeadGeom& g, const float* dout, const act_t* a, float* dw, float* db, cudaStream_t st);
+// Head adjoints on the tensor-core kernels: G (fp16 [tokens][ldG]) = shifted, scaled copy of dout; dX = G Wt (forward
+// implicit-GEMM kernel, token GEMM), dW = G^T A (conv_wgrad_kernel), bias gradient by a strided fp32 reduction.
+struct HeadBwdPlan {
+    HeadGeom hg{};
+    long long tokens = 0;
+    int ldG = 0, bn = 0, items = 0;
+    act_t* G = nullptr;        // [tokens][ldG] scratch
+    float* dwpk = nullptr;     // [ldG][C] fp32 scratch
+    GemmParams gemm;           // dX = G * wt^T   (unused when dx == nullptr)
+    WgradParams wgrad;
+    bool want_dx = false;
+};
+inline int head_ld(int terms) { return terms <= 64 ? 64 : 128; }
+int build_head_bwd(const HeadGeom& hg, const act_t* x, act_t* G, const act_t* wt /*[C][ldG]*/, const float* zero_bias, act_t* dx,
+                   float* dwpk, HeadBwdPlan* out);
+int run_head_bwd(const HeadBwdPlan& hp, const float* dout, float* dw, float* db, const float* gscale, cudaStream_t st);
+int launch_pack_head_t(const float* w, act_t* wt, int n_out, int C, int T, int ldG, cudaStream_t st);
 
 }  // namespace mmd

@@ -1045,7 +1045,7 @@ struct Walker {
         const long long tokens = op.g.tokens();
         const int n = pc->n;
         const float* gs = plan ? plan->gscale : nullptr;
-        if (op.tag == "conv_head") {   // narrow fp32 heads: CUDA-core adjoints straight from the API-layout gradient
+        if (op.tag == "conv_head") {   // narrow fp32 heads: im2col of the API-layout gradient, then the tensor-core GEMM / wgrad kernels
             const bool video = op.g.rank == 5;
             const act_t* x = op.srcs[0].first;
             const int C = op.srcs[0].second;
@@ -1054,11 +1054,10 @@ struct Walker {
             mark_written(x);
             const int terms = static_cast<int>(op.taps.size()) * n;
             if (terms > 128 || C % 64 != 0) { set_err(fail(MMD_EINVAL, "head backward: %d taps x %d outputs over %d channels unsupported", static_cast<int>(op.taps.size()), n, C)); return; }
-            const int ldG = terms <= 64 ? 64 : 128;
+            const int ldG = head_ld(terms);
             const size_t hmark = bscratch.top;
             act_t* G = static_cast<act_t*>(bscratch.take(sizeof(act_t) * static_cast<size_t>(tokens) * ldG));
-            const size_t dw_bytes = sizeof(float) * static_cast<size_t>(ldG) * C;
-            float* dwpk = static_cast<float*>(bscratch.take(dw_bytes));
+            float* dwpk = static_cast<float*>(bscratch.take(sizeof(float) * static_cast<size_t>(ldG) * C));
             act_t* wt = static_cast<act_t*>(tpack.take(sizeof(act_t) * static_cast<size_t>(C) * ldG));
             release_b(hmark);
             if (!emitting()) return;
@@ -1074,45 +1073,13 @@ struct Walker {
             const float* w = pf(pc->segs[0].w);
             float* dw = g32_of(pc->segs[0].w);
             float* db = g32_of(pc->biases[0]);
-            // tensor-core path: G = shifted, scaled fp16 copy of dout; dX = G Wt (forward kernel), dW = G^T A (wgrad kernel)
-            GemmProblem pr;
-            pr.g = geom2(tokens);
-            pr.n_src = 1; pr.src[0] = G; pr.src_c[0] = ldG;
-            pr.n_taps = 1;
-            pr.w = wt; pr.bias = plan->zero_bias; pr.n = C; pr.bn = pick_bn(C); pr.out = dx;
-            auto gp = std::make_shared<GemmParams>();
-            int r = build_gemm(pr, gp.get());
-            if (r != MMD_OK) { set_err(r); return; }
-            const int bn = pr.bn;
-            WgradProblem wp;
-            wp.g = geom2(tokens);
-            wp.n_src = 1; wp.src[0] = x; wp.src_c[0] = C;
-            wp.n_taps = 1;
-            wp.dy = G; wp.n = ldG; wp.dw = dwpk; wp.ld = C;
-            auto wpar = std::make_shared<WgradParams>();
-            int items = 0;
-            r = build_wgrad(wp, wpar.get(), &items);
+            // tensor-core path shared with mmd_op_head_bwd: G = shifted, scaled fp16 copy of dout; dX = G Wt, dW = G^T A
+            auto hp = std::make_shared<HeadBwdPlan>();
+            int r = build_head_bwd(hg, x, G, wt, plan->zero_bias, dx, dwpk, hp.get());
             if (r != MMD_OK) { set_err(r); return; }
             const int n_out = n, T = hg.n_taps;
-            plan->tpack_ops.push_back([=](cudaStream_t st) -> int {
-                pack_head_t_kernel<<<(n_out * C * T + 255) / 256, 256, 0, st>>>(w, wt, n_out, C, T, ldG);
-                MMD_CUDA_OK(cudaGetLastError());
-                return MMD_OK;
-            });
-            bpush([=](cudaStream_t st) -> int {
-                const long long total = tokens * (ldG / 8);
-                head_im2col_bwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(hg, dout, G, ldG, tokens, gs);
-                head_bias_kernel<<<dim3(static_cast<unsigned>(std::min<long long>((tokens + 255) / 256, 2LL * num_sms())), n_out), 256, 0, st>>>(hg, dout, db, tokens);
-                MMD_CUDA_OK(cudaGetLastError());
-                pdl_break(st);
-                MMD_TRY(launch_gemm(*gp, bn, st));
-                pdl_break(st);
-                MMD_CUDA_OK(cudaMemsetAsync(dwpk, 0, dw_bytes, st));
-                MMD_TRY(launch_wgrad(*wpar, items, st));
-                unpack_head_wgrad_kernel<<<(n_out * C * T + 255) / 256, 256, 0, st>>>(dwpk, dw, n_out, C, T, gs);
-                MMD_CUDA_OK(cudaGetLastError());
-                return MMD_OK;
-            }, "head_bwd");
+            plan->tpack_ops.push_back([=](cudaStream_t st) { return launch_pack_head_t(w, wt, n_out, C, T, ldG, st); });
+            bpush([=](cudaStream_t st) { return run_head_bwd(*hp, dout, dw, db, gs, st); }, "head_bwd");
             return;
         }
         act_t* dy = need_grad(op.out, op.tag.c_str());

@@ -331,36 +331,67 @@ static long long head_tokens(const HeadGeom& g) {
     return t;
 }
 
-int launch_head_dgrad(const HeadGeom& g, const float* dout, const float* w, act_t* dx, const float* gscale, cudaStream_t st) {
-    const size_t sm = static_cast<size_t>(g.n_taps) * g.n_out * g.C * sizeof(float);
-    if (sm > 160 * 1024 || g.C % 8 != 0) return fail(MMD_EINVAL, "head dgrad: %d taps x %d outputs x %d channels unsupported", g.n_taps, g.n_out, g.C);
-    static bool attr_done = false;
-    if (!attr_done) {
-        MMD_CUDA_OK(cudaFuncSetAttribute(head_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        attr_done = true;
-    }
-    const long long tokens = head_tokens(g);
-    const unsigned grid = static_cast<unsigned>(std::max<long long>(1, std::min<long long>((tokens * (g.C / 8) + 255) / 256, 4LL * num_sms())));
-    head_dgrad_kernel<<<grid, 256, sm, st>>>(g, dout, w, dx, tokens, gscale);
+int launch_pack_head_t(const float* w, act_t* wt, int n_out, int C, int T, int ldG, cudaStream_t st) {
+    MMD_CUDA_OK(cudaMemsetAsync(wt, 0, sizeof(act_t) * static_cast<size_t>(C) * ldG, st));
+    pack_head_t_kernel<<<(n_out * C * T + 255) / 256, 256, 0, st>>>(w, wt, n_out, C, T, ldG);
     MMD_CUDA_OK(cudaGetLastError());
     pdl_break(st);
     return MMD_OK;
 }
 
-int launch_head_wgrad(const HeadGeom& g, const float* dout, const act_t* a, float* dw, float* db, cudaStream_t st) {
-    const int terms = g.n_taps * g.n_out;
-    if (g.C > 1024 || g.C < g.n_out) return fail(MMD_EINVAL, "head wgrad: %d channels unsupported", g.C);
-    const long long tokens = head_tokens(g);
-    const long long blocks = std::max<long long>(1, std::min<long long>(8LL * num_sms(), (tokens + 127) / 128));
-    const long long tpb = (tokens + blocks - 1) / blocks;
-    const unsigned grid = static_cast<unsigned>((tokens + tpb - 1) / tpb);
-    if (terms <= 3) head_wgrad_kernel<3><<<grid, g.C, 0, st>>>(g, dout, a, dw, db, tokens, tpb);
-    else if (terms <= 9) head_wgrad_kernel<9><<<grid, g.C, 0, st>>>(g, dout, a, dw, db, tokens, tpb);
-    else if (terms <= 27) head_wgrad_kernel<27><<<grid, g.C, 0, st>>>(g, dout, a, dw, db, tokens, tpb);
-    else if (terms <= 81) head_wgrad_kernel<81><<<grid, g.C, 0, st>>>(g, dout, a, dw, db, tokens, tpb);
-    else return fail(MMD_EINVAL, "head wgrad: %d taps x %d outputs unsupported (learn_sigma heads are not trainable yet)", g.n_taps, g.n_out);
+int build_head_bwd(const HeadGeom& hg, const act_t* x, act_t* G, const act_t* wt, const float* zero_bias, act_t* dx, float* dwpk,
+                   HeadBwdPlan* out) {
+    HeadBwdPlan& hp = *out;
+    const int terms = hg.n_taps * hg.n_out;
+    if (terms > 128 || hg.C % 64 != 0)
+        return fail(MMD_EINVAL, "head backward: %d taps x %d outputs over %d channels unsupported", hg.n_taps, hg.n_out, hg.C);
+    hp.hg = hg;
+    hp.tokens = head_tokens(hg);
+    hp.ldG = head_ld(terms);
+    hp.G = G;
+    hp.dwpk = dwpk;
+    hp.want_dx = dx != nullptr;
+    ConvGeom g2;
+    g2.rank = 2;
+    g2.dims[0] = hp.tokens;
+    geom_fill_box(g2);
+    if (dx) {
+        GemmProblem pr;
+        pr.g = g2;
+        pr.n_src = 1; pr.src[0] = G; pr.src_c[0] = hp.ldG;
+        pr.n_taps = 1;
+        pr.w = wt; pr.bias = zero_bias; pr.n = hg.C; pr.bn = pick_bn(hg.C); pr.out = dx;
+        MMD_TRY(build_gemm(pr, &hp.gemm));
+        hp.bn = pr.bn;
+    }
+    WgradProblem wp;
+    wp.g = g2;
+    wp.n_src = 1; wp.src[0] = x; wp.src_c[0] = hg.C;
+    wp.n_taps = 1;
+    wp.dy = G; wp.n = hp.ldG; wp.dw = dwpk; wp.ld = hg.C;
+    return build_wgrad(wp, &hp.wgrad, &hp.items);
+}
+
+int run_head_bwd(const HeadBwdPlan& hp, const float* dout, float* dw, float* db, const float* gscale, cudaStream_t st) {
+    const HeadGeom& hg = hp.hg;
+    const long long total = hp.tokens * (hp.ldG / 8);
+    head_im2col_bwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(hg, dout, hp.G, hp.ldG, hp.tokens, gscale);
+    if (db)
+        head_bias_kernel<<<dim3(static_cast<unsigned>(std::min<long long>((hp.tokens + 255) / 256, 2LL * num_sms())), hg.n_out), 256, 0, st>>>(
+            hg, dout, db, hp.tokens);
     MMD_CUDA_OK(cudaGetLastError());
     pdl_break(st);
+    if (hp.want_dx) {
+        MMD_TRY(launch_gemm(hp.gemm, hp.bn, st));
+        pdl_break(st);
+    }
+    if (dw) {
+        MMD_CUDA_OK(cudaMemsetAsync(hp.dwpk, 0, sizeof(float) * static_cast<size_t>(hp.ldG) * hg.C, st));
+        MMD_TRY(launch_wgrad(hp.wgrad, hp.items, st));
+        const int n = hg.n_out * hg.C * hg.n_taps;
+        unpack_head_wgrad_kernel<<<(n + 255) / 256, 256, 0, st>>>(hp.dwpk, dw, hg.n_out, hg.C, hg.n_taps, gscale);
+        MMD_CUDA_OK(cudaGetLastError());
+    }
     return MMD_OK;
 }
 
@@ -530,9 +561,10 @@ int mmd_op_attention_fwd_bwd(const MmdAttnDesc* d, const void* d_out, float* lse
 }
 
 // Narrow-head adjoints: geometry from the forward descriptor (out_f32 layout strides); dx fp16 [tokens][C] (scale 1).
+// Same tensor-core path as the model's backward plan (build_head_bwd / run_head_bwd).
 int mmd_op_head_bwd(const MmdConvDesc* d, const float* dout, void* dx, float* dweight, float* dbias, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (!d || !dout || d->n_src != 1) return fail(MMD_EINVAL, "head_bwd: bad argument");
+    if (!d || !dout || d->n_src != 1 || !d->weight) return fail(MMD_EINVAL, "head_bwd: bad argument");
     HeadGeom g{};
     g.ncoord = d->rank - 1;
     for (int i = 0; i < 4; ++i) { g.dims[i] = d->dims[i] > 0 ? static_cast<int>(d->dims[i]) : 1; g.ostride[i] = d->ostride[i]; }
@@ -542,9 +574,24 @@ int mmd_op_head_bwd(const MmdConvDesc* d, const float* dout, void* dx, float* dw
     for (int t = 0; t < d->n_taps; ++t)
         for (int j = 0; j < 3; ++j) g.tap[t][j] = d->taps[t][j];
     g.C = d->src_channels[0];
-    int r = MMD_OK;
-    if (dx) r = launch_head_dgrad(g, dout, d->weight, static_cast<act_t*>(dx), nullptr, st);
-    if (r == MMD_OK && dweight) r = launch_head_wgrad(g, dout, static_cast<const act_t*>(d->src[0]), dweight, dbias, st);
+    const int ldG = head_ld(g.n_taps * g.n_out);
+    long long tokens = 1;
+    for (int i = 0; i < 4; ++i) tokens *= g.dims[i];
+    act_t *G = nullptr, *wt = nullptr;
+    float *dwpk = nullptr, *zb = nullptr;
+    MMD_CUDA_OK(cudaMallocAsync(&G, sizeof(act_t) * static_cast<size_t>(tokens) * ldG, st));
+    MMD_CUDA_OK(cudaMallocAsync(&wt, sizeof(act_t) * static_cast<size_t>(g.C) * ldG, st));
+    MMD_CUDA_OK(cudaMallocAsync(&dwpk, sizeof(float) * static_cast<size_t>(ldG) * g.C, st));
+    MMD_CUDA_OK(cudaMallocAsync(&zb, sizeof(float) * 1024, st));
+    MMD_CUDA_OK(cudaMemsetAsync(zb, 0, sizeof(float) * 1024, st));
+    int r = launch_pack_head_t(d->weight, wt, g.n_out, g.C, g.n_taps, ldG, st);
+    HeadBwdPlan hp;
+    if (r == MMD_OK) r = build_head_bwd(g, static_cast<const act_t*>(d->src[0]), G, wt, zb, static_cast<act_t*>(dx), dwpk, &hp);
+    if (r == MMD_OK) r = run_head_bwd(hp, dout, dweight, dbias, nullptr, st);
+    cudaFreeAsync(G, st);
+    cudaFreeAsync(wt, st);
+    cudaFreeAsync(dwpk, st);
+    cudaFreeAsync(zb, st);
     return r;
 }
 
