@@ -416,7 +416,8 @@ def run_b200_train(args):
                        "params_m": round(sum(p.numel() for p in model.parameters()) / 1e6, 2),
                        "parallelism": f"batch-shard x{world}" + ((" (torch DDP buckets over NCCL)" if args.ddp else
                                                                   " (one flat fp32 gradient all-reduce over NCCL per step)") if world > 1 else ""),
-                       "l2_note": "kept activations + gradients (~48 GB at B=8) exceed the 126 MB L2", "cuda_graph": False},
+                       "l2_note": "kept activations + gradients (~48 GB at B=8) exceed the 126 MB L2",
+                       "cuda_graph": os.environ.get("MMD_TRAIN_GRAPH", "1") != "0"},
             "e2e": {"value": round(world * B * K / (ms_e2e * 1e-3), 3), "unit": "sample-steps/s", "ms_per_step": round(ms_e2e / K, 3),
                     "h2d_bytes_per_step": (xv_h.numel() + xa_h.numel()) * 4, "d2h_bytes_per_step": 4},
             "gpu_launches": K * (model.num_backward_launches(B) + len(fwd_steps)),

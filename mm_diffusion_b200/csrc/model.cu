@@ -74,6 +74,7 @@ struct Plan {
     float *in_video = nullptr, *in_audio = nullptr, *t_dev = nullptr, *out_video = nullptr, *out_audio = nullptr;
     int* shifts_dev = nullptr;
     cudaGraphExec_t graph = nullptr;
+    cudaGraphExec_t bwd_graph = nullptr;   // training plans: the backward launch list
     std::vector<cudaEvent_t> events;   // fork / join events of the two-branch capture
     // ---- training plan only (every intermediate kept; backward launch list built from the tape)
     bool train = false;
@@ -92,6 +93,7 @@ struct Plan {
     bool fwd_done = false;
     ~Plan() {
         if (graph) cudaGraphExecDestroy(graph);
+        if (bwd_graph) cudaGraphExecDestroy(bwd_graph);
         for (auto e : events) cudaEventDestroy(e);
         if (ws) cudaFree(ws);
         if (wpk_t) cudaFree(wpk_t);
@@ -1595,7 +1597,80 @@ static size_t dry_workspace(MmdModel* m, int B) {
     return dry.persist.peak + dry.scratch.peak + dry.scratch_a.peak + dry.stats.peak + (1 << 20);
 }
 
+// Capture the forward launch list of a plan into a CUDA graph.  Two-branch capture: video / main steps on cap_stream,
+// audio steps on cap_stream2; "sync" steps make the branches wait for each other (graph edges), so the small audio
+// kernels overlap the video ones.
+static int capture_forward_graph(MmdModel* m, Plan* plan, cudaStream_t st) {
+    // pack ops (if any) ran on `st`; make sure the capture stream sees a quiescent device
+    MMD_CUDA_OK(cudaStreamSynchronize(st));
+    cudaGraph_t g = nullptr;
+    const bool two = m->two_streams;
+    auto new_event = [&]() -> cudaEvent_t {
+        cudaEvent_t ev = nullptr;
+        cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        plan->events.push_back(ev);
+        return ev;
+    };
+    MMD_CUDA_OK(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal));
+    PdlScope pdl(m->cap_stream, two ? m->cap_stream2 : nullptr);
+    int r = MMD_OK;
+    cudaError_t ce = cudaSuccess;
+    auto cross_sync = [&]() {
+        pdl_break_all();   // the kernels after a join have two predecessors: plain launches
+        cudaEvent_t e0 = new_event(), e1 = new_event();
+        ce = cudaEventRecord(e0, m->cap_stream);
+        if (ce == cudaSuccess) ce = cudaEventRecord(e1, m->cap_stream2);
+        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(m->cap_stream, e1, 0);
+        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(m->cap_stream2, e0, 0);
+    };
+    if (two) {   // fork: pull the second stream into the capture
+        cudaEvent_t e0 = new_event();
+        ce = cudaEventRecord(e0, m->cap_stream);
+        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(m->cap_stream2, e0, 0);
+    }
+    for (size_t i = 0; i < plan->steps.size() && r == MMD_OK && ce == cudaSuccess; ++i) {
+        const int sid = plan->info[i].stream;
+        if (sid < 0) { if (two) cross_sync(); continue; }
+        r = plan->steps[i]((two && sid == 1) ? m->cap_stream2 : m->cap_stream);
+    }
+    if (two && ce == cudaSuccess) {   // join (the plan ends with a sync step, this only closes the fork)
+        cudaEvent_t e1 = new_event();
+        ce = cudaEventRecord(e1, m->cap_stream2);
+        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(m->cap_stream, e1, 0);
+    }
+    cudaError_t e = cudaStreamEndCapture(m->cap_stream, &g);
+    if (ce != cudaSuccess) { if (g) cudaGraphDestroy(g); return fail(MMD_ECUDA, "two-branch capture: %s", cudaGetErrorString(ce)); }
+    if (r != MMD_OK) { if (g) cudaGraphDestroy(g); return r; }
+    if (e != cudaSuccess) return fail(MMD_ECUDA, "graph capture: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&plan->graph, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return fail(MMD_ECUDA, "graph instantiate: %s", cudaGetErrorString(e));
+    return MMD_OK;
+}
+
+// Backward launch list of a training plan as one graph (single branch: the tape order is a valid serial schedule).
+static int capture_backward_graph(MmdModel* m, Plan* plan, cudaStream_t st) {
+    MMD_CUDA_OK(cudaStreamSynchronize(st));
+    cudaGraph_t g = nullptr;
+    MMD_CUDA_OK(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal));
+    int r = MMD_OK;
+    for (size_t i = 0; i < plan->bwd_steps.size() && r == MMD_OK; ++i) r = plan->bwd_steps[i](m->cap_stream);
+    cudaError_t e = cudaStreamEndCapture(m->cap_stream, &g);
+    if (r != MMD_OK) { if (g) cudaGraphDestroy(g); return r; }
+    if (e != cudaSuccess) return fail(MMD_ECUDA, "backward graph capture: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&plan->bwd_graph, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return fail(MMD_ECUDA, "backward graph instantiate: %s", cudaGetErrorString(e));
+    return MMD_OK;
+}
+
+static bool train_graphs_enabled() {
+    static const bool on = [] { const char* e = getenv("MMD_TRAIN_GRAPH"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 }  // namespace mmd
+
 
 // ===========================================================================
 extern "C" {
@@ -1776,54 +1851,7 @@ int mmd_model_forward(MmdModel* m, int batch, const float* video_in, const float
         MMD_CUDA_OK(cudaGetLastError());
     }
     if (m->use_graph) {
-        if (!plan->graph) {
-            // pack ops (if any) ran on `st`; make sure the capture stream sees a quiescent device
-            MMD_CUDA_OK(cudaStreamSynchronize(st));
-            cudaGraph_t g = nullptr;
-            // two-branch capture: video / main steps on cap_stream, audio steps on cap_stream2; "sync" steps make the
-            // branches wait for each other (graph edges), so small audio kernels overlap the video ones
-            const bool two = m->two_streams;
-            auto new_event = [&]() -> cudaEvent_t {
-                cudaEvent_t ev = nullptr;
-                cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-                plan->events.push_back(ev);
-                return ev;
-            };
-            MMD_CUDA_OK(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal));
-            PdlScope pdl(m->cap_stream, two ? m->cap_stream2 : nullptr);
-            int r = MMD_OK;
-            cudaError_t ce = cudaSuccess;
-            auto cross_sync = [&]() {
-                pdl_break_all();   // the kernels after a join have two predecessors: plain launches
-                cudaEvent_t e0 = new_event(), e1 = new_event();
-                ce = cudaEventRecord(e0, m->cap_stream);
-                if (ce == cudaSuccess) ce = cudaEventRecord(e1, m->cap_stream2);
-                if (ce == cudaSuccess) ce = cudaStreamWaitEvent(m->cap_stream, e1, 0);
-                if (ce == cudaSuccess) ce = cudaStreamWaitEvent(m->cap_stream2, e0, 0);
-            };
-            if (two) {   // fork: pull the second stream into the capture
-                cudaEvent_t e0 = new_event();
-                ce = cudaEventRecord(e0, m->cap_stream);
-                if (ce == cudaSuccess) ce = cudaStreamWaitEvent(m->cap_stream2, e0, 0);
-            }
-            for (size_t i = 0; i < plan->steps.size() && r == MMD_OK && ce == cudaSuccess; ++i) {
-                const int sid = plan->info[i].stream;
-                if (sid < 0) { if (two) cross_sync(); continue; }
-                r = plan->steps[i]((two && sid == 1) ? m->cap_stream2 : m->cap_stream);
-            }
-            if (two && ce == cudaSuccess) {   // join (the plan ends with a sync step, this only closes the fork)
-                cudaEvent_t e1 = new_event();
-                ce = cudaEventRecord(e1, m->cap_stream2);
-                if (ce == cudaSuccess) ce = cudaStreamWaitEvent(m->cap_stream, e1, 0);
-            }
-            cudaError_t e = cudaStreamEndCapture(m->cap_stream, &g);
-            if (ce != cudaSuccess) { if (g) cudaGraphDestroy(g); return fail(MMD_ECUDA, "two-branch capture: %s", cudaGetErrorString(ce)); }
-            if (r != MMD_OK) { if (g) cudaGraphDestroy(g); return r; }
-            if (e != cudaSuccess) return fail(MMD_ECUDA, "graph capture: %s", cudaGetErrorString(e));
-            e = cudaGraphInstantiate(&plan->graph, g, 0);
-            cudaGraphDestroy(g);
-            if (e != cudaSuccess) return fail(MMD_ECUDA, "graph instantiate: %s", cudaGetErrorString(e));
-        }
+        if (!plan->graph) MMD_TRY(capture_forward_graph(m, plan, st));
         MMD_CUDA_OK(cudaGraphLaunch(plan->graph, st));
     } else {
         PdlScope pdl(st, nullptr);
@@ -1850,7 +1878,10 @@ int mmd_model_forward_train(MmdModel* m, int batch, const float* video_in, const
     Plan* plan = nullptr;
     MMD_TRY(build_train_plan(m, batch, &plan));
     MMD_TRY(stage_inputs(m, plan, batch, video_in, audio_in, timesteps, shifts, st));
-    {
+    if (m->use_graph && train_graphs_enabled()) {
+        if (!plan->graph) MMD_TRY(capture_forward_graph(m, plan, st));
+        MMD_CUDA_OK(cudaGraphLaunch(plan->graph, st));
+    } else {
         PdlScope pdl(st, nullptr);
         for (auto& step : plan->steps) MMD_TRY(step(st));
     }
@@ -1890,7 +1921,12 @@ int mmd_model_backward(MmdModel* m, int batch, const float* d_video_out, const f
         for (auto& op : plan->tpack_ops) MMD_TRY(op(st));
         plan->tpack_dirty = false;
     }
-    for (auto& step : plan->bwd_steps) MMD_TRY(step(st));
+    if (m->use_graph && train_graphs_enabled()) {
+        if (!plan->bwd_graph) MMD_TRY(capture_backward_graph(m, plan, st));
+        MMD_CUDA_OK(cudaGraphLaunch(plan->bwd_graph, st));
+    } else {
+        for (auto& step : plan->bwd_steps) MMD_TRY(step(st));
+    }
     if (param_grads)
         MMD_CUDA_OK(cudaMemcpyAsync(param_grads, plan->g32, sizeof(float) * m->w32_floats, cudaMemcpyDeviceToDevice, st));
     if (d_video_in) MMD_CUDA_OK(cudaMemcpyAsync(d_video_in, plan->d_in_video, vin, cudaMemcpyDeviceToDevice, st));
