@@ -1523,7 +1523,21 @@ static int build_train_plan(MmdModel* m, int B, Plan** out) {
     const size_t g_bytes = al(dry.grads.peak) + 1024, b_bytes = al(dry.bscratch.peak) + 1024;
     const size_t t_bytes = al(dry.tpack.peak) + 1024;
     plan->ws_bytes = io_bytes + p_bytes + s_bytes + sa_bytes + st_bytes + g_bytes + b_bytes;
-    MMD_CUDA_OK(cudaMalloc(&plan->ws, plan->ws_bytes));
+    if (cudaMalloc(&plan->ws, plan->ws_bytes) != cudaSuccess) {
+        // a training plan keeps every intermediate (tens of GB): before giving up, drop the cached plans of other batch
+        // sizes (e.g. the ragged last batch of an epoch) and try once more
+        cudaGetLastError();
+        plan->ws = nullptr;
+        MMD_CUDA_OK(cudaDeviceSynchronize());
+        m->train_plans.clear();
+        m->plans.clear();
+        if (cudaMalloc(&plan->ws, plan->ws_bytes) != cudaSuccess) {
+            cudaGetLastError();
+            plan->ws = nullptr;
+            return fail(MMD_ECUDA, "training plan for batch %d needs %.1f GB of device memory (kept activations + gradients)", B,
+                        plan->ws_bytes / 1e9);
+        }
+    }
     MMD_CUDA_OK(cudaMemset(plan->ws, 0, plan->ws_bytes));
     MMD_CUDA_OK(cudaMalloc(&plan->wpk_t, t_bytes));
     MMD_CUDA_OK(cudaMemset(plan->wpk_t, 0, t_bytes));
@@ -1661,6 +1675,16 @@ static int capture_backward_graph(MmdModel* m, Plan* plan, cudaStream_t st) {
     e = cudaGraphInstantiate(&plan->bwd_graph, g, 0);
     cudaGraphDestroy(g);
     if (e != cudaSuccess) return fail(MMD_ECUDA, "backward graph instantiate: %s", cudaGetErrorString(e));
+    return MMD_OK;
+}
+
+// Re-derive every packed weight layout after a parameter update: the forward's K-major fp16 packs now, the transposed
+// packs of the training plans lazily at their next backward (whichever entry point notices the update first).
+static int repack_if_dirty(MmdModel* m, cudaStream_t st) {
+    if (!m->dirty) return MMD_OK;
+    for (auto& op : m->pack_ops) MMD_TRY(op(st));
+    m->dirty = false;
+    for (auto& tp : m->train_plans) tp.second->tpack_dirty = true;
     return MMD_OK;
 }
 
@@ -1823,10 +1847,7 @@ int mmd_model_forward(MmdModel* m, int batch, const float* video_in, const float
     MMD_TRY(ensure_device(m));
     for (auto& p : m->params)
         if (!p.set) return fail(MMD_ESTATE, "parameter %s was never set", p.name.c_str());
-    if (m->dirty) {
-        for (auto& op : m->pack_ops) MMD_TRY(op(st));
-        m->dirty = false;
-    }
+    MMD_TRY(repack_if_dirty(m, st));
     Plan* plan = nullptr;
     MMD_TRY(build_plan(m, batch, &plan));
     const MmdConfig& c = m->cfg;
@@ -1870,11 +1891,7 @@ int mmd_model_forward_train(MmdModel* m, int batch, const float* video_in, const
     MMD_TRY(ensure_device(m));
     for (auto& p : m->params)
         if (!p.set) return fail(MMD_ESTATE, "parameter %s was never set", p.name.c_str());
-    if (m->dirty) {
-        for (auto& op : m->pack_ops) MMD_TRY(op(st));
-        m->dirty = false;
-        for (auto& tp : m->train_plans) tp.second->tpack_dirty = true;
-    }
+    MMD_TRY(repack_if_dirty(m, st));
     Plan* plan = nullptr;
     MMD_TRY(build_train_plan(m, batch, &plan));
     MMD_TRY(stage_inputs(m, plan, batch, video_in, audio_in, timesteps, shifts, st));

@@ -181,3 +181,46 @@ def test_production_backward_matches_oracle():
     assert glob < 3e-2, glob
     big = [r for r in rows if r[1] > 1e-3 * (den ** 0.5)]
     assert all(e < 6e-2 for e, _, _ in big), [r for r in big if r[0] >= 6e-2][:5]
+
+
+def test_parameter_update_reaches_every_packed_layout(setup):
+    """A training loop changes the parameters every step: after an in-place update (and an interleaved no-grad forward,
+    as in EMA / sampling during training) the next step must use the new weights in the forward packs AND in the
+    transposed packs of the data gradients.  Gradients after the update vs oracle autograd at the updated weights."""
+    fx, cfg, sd, model, diffusion = setup
+    B = 2
+    x0, noise = _data(cfg, B, 55)
+    t = torch.tensor([250, 900])
+    shifts = draw_shifts(cfg, random.Random(6))
+    model.train()
+    model.zero_grad(set_to_none=True)
+    random.seed(6)
+    diffusion.multimodal_training_losses(model, {k: v.cuda() for k, v in x0.items()}, t.cuda(),
+                                         noise={k: v.cuda() for k, v in noise.items()})["loss"].mean().backward()
+    g = torch.Generator().manual_seed(8)
+    new_sd = {}
+    with torch.no_grad():
+        for name, p in model.named_parameters():   # a large, structured update (a plain SGD step would be tiny)
+            delta = 0.02 * torch.randn(p.shape, generator=g)
+            p.add_(delta.cuda())
+            new_sd[name] = sd[name] + delta
+        model.eval()
+        model(x0["video"].cuda(), x0["audio"].cuda(), t.cuda(), shifts=shifts)   # no-grad forward sees the update first
+    try:
+        ref_terms, ref_grads, _, _ = _oracle_grads(cfg, new_sd, x0, noise, t, shifts)
+        model.train()
+        model.zero_grad(set_to_none=True)
+        random.seed(6)
+        loss = diffusion.multimodal_training_losses(model, {k: v.cuda() for k, v in x0.items()}, t.cuda(),
+                                                    noise={k: v.cuda() for k, v in noise.items()})["loss"].mean()
+        loss.backward()
+        torch.cuda.synchronize()
+        num = sum((p.grad.float().cpu() - ref_grads[n]).double().pow(2).sum().item() for n, p in model.named_parameters())
+        den = sum(ref_grads[n].double().pow(2).sum().item() for n, _ in model.named_parameters())
+        glob = (num / den) ** 0.5
+        lerr = abs(loss.item() - ref_terms["loss"].mean().item()) / abs(ref_terms["loss"].mean().item())
+        print(f"[bwd-model] after parameter update: loss rel-err {lerr:.2e}, global grad rel-L2 {glob:.3e}")
+        assert lerr < 1e-2 and glob < 3e-2, (lerr, glob)
+    finally:
+        model.eval()
+        model.load_state_dict(sd, strict=True)   # the module-scoped fixture is shared
