@@ -1,0 +1,48 @@
+"""CPU: the built library really is Blackwell-native — the tensor-core kernels of the path contain tcgen05.mma
+(SASS UTCHMMA), TMA loads (UTMALDG) and TMEM loads (LDTM) for sm_100a, read from libmmdiff.so with cuobjdump
+(B200_PROFILING.md: the mnemonics that prove tcgen05 / TMA).  No GPU needed."""
+import re
+import shutil
+import subprocess
+
+import pytest
+
+from mm_diffusion_b200 import _lib
+
+CUOBJDUMP = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+
+
+@pytest.fixture(scope="module")
+def sass_by_function():
+    try:
+        out = subprocess.run([CUOBJDUMP, "-sass", _lib.LIB_PATH], capture_output=True, text=True, timeout=300)
+    except FileNotFoundError:
+        pytest.skip("cuobjdump not available")
+    assert out.returncode == 0, out.stderr[:500]
+    assert "sm_100a" in out.stdout or "SM100a" in out.stdout.replace("_", "") or "sm_100" in out.stdout
+    funcs = {}
+    for chunk in re.split(r"\n\s*Function : ", out.stdout)[1:]:
+        name, _, body = chunk.partition("\n")
+        funcs[name.strip()] = body
+    return funcs
+
+
+@pytest.mark.parametrize("kernel,needs", [
+    ("conv_gemm_kernel", ("UTCHMMA", "UTMALDG", "LDTM", "UTMASTG")),   # implicit-GEMM conv: tcgen05.mma, TMA load / store, TMEM epilogue
+    ("conv_wgrad_kernel", ("UTCHMMA", "UTMALDG", "LDTM")),             # weight gradient
+    ("attention64_kernel", ("UTCHMMA", "UTMALDG", "LDTM", "STTM")),    # flash attention d = 64 (O rescale in TMEM)
+    ("attention_kernel", ("UTCHMMA", "UTMALDG", "LDTM")),
+    ("attn_bwd_kernel", ("UTCHMMA", "UTMALDG", "LDTM")),               # flash attention backward
+])
+def test_tensor_core_kernels_use_tcgen05_and_tma(sass_by_function, kernel, needs):
+    def is_instance(name):
+        if kernel not in name or "temporal" in name:
+            return False
+        return not (kernel == "attention_kernel" and "attention64" in name)
+    bodies = {n: b for n, b in sass_by_function.items() if is_instance(n)}
+    assert bodies, f"{kernel} not found in the library"
+    for name, body in bodies.items():
+        req = [m for m in needs if not (m == "UTMASTG" and "ILi16E" in name)]   # the BN = 16 head variant scatters fp32 with plain stores
+        missing = [m for m in req if m not in body]
+        assert not missing, f"{name}: SASS lacks {missing}"
+        assert "HMMA.16816" not in body, f"{name} contains legacy mma.sync"
