@@ -178,8 +178,6 @@ int launch_unpack_wgrad(const float* dwpk, float* g, int co, int ci, int t, long
                         cudaStream_t st, const float* gscale = nullptr);
 int launch_pack_weight_t(const float* w, act_t* dst, int co, int ci, int t, int c_lo, int cs, long long ld, long long col_off,
                          cudaStream_t st);
-int launch_colsum(const act_t* x, long long rows, int C, float scale, float* out, cudaStream_t st, float* out2 = nullptr,
-                  const float* gscale = nullptr);
 int launch_grad_add(const act_t* x, act_t* y, long long n, int accumulate, cudaStream_t st);
 int launch_grad_add2d(const act_t* x, long long ldx, act_t* y, long long ldy, long long rows, int C, int accumulate, cudaStream_t st);
 

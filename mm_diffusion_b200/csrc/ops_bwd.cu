@@ -107,19 +107,6 @@ int launch_pack_weight_t(const float* w, act_t* dst, int co, int ci, int t, int 
     return MMD_OK;
 }
 
-int launch_colsum(const act_t* x, long long rows, int C, float scale, float* out, cudaStream_t st, float* out2, const float* gscale) {
-    if (C % 8 != 0 || C / 8 > 256) return fail(MMD_EINVAL, "colsum channels %d unsupported", C);
-    const int rows_per_pass = std::max(1, 256 / (C / 8));
-    // every thread streams at least ~8 batches of 4 rows; at most two blocks per SM
-    const long long min_rpb = 32LL * rows_per_pass;
-    long long blocks = std::max<long long>(1, std::min<long long>(2LL * num_sms(), (rows + min_rpb - 1) / min_rpb));
-    const long long rpb = (rows + blocks - 1) / blocks;
-    colsum_kernel<<<static_cast<unsigned>((rows + rpb - 1) / rpb), 256, C * sizeof(float), st>>>(x, rows, C, rpb, scale, out, out2, gscale);
-    MMD_CUDA_OK(cudaGetLastError());
-    pdl_break(st);
-    return MMD_OK;
-}
-
 int launch_grad_add(const act_t* x, act_t* y, long long n, int accumulate, cudaStream_t st) {
     if (n % 8 != 0) return fail(MMD_EINVAL, "grad_add: element count %lld not a multiple of 8", n);
     const long long n8 = n / 8;

@@ -290,53 +290,6 @@ __global__ void pack_weight_t_kernel(const float* __restrict__ w, act_t* __restr
         __float2half_rn(w[(static_cast<long long>(co) * Ci + c_lo + c) * T + t]);
 }
 
-// Column sums of a [rows][C] fp16 matrix into fp32 (bias gradient): out[c] += scale * sum_r x[r][c].
-// Rows are streamed with four independent 16-byte loads in flight per thread; the per-thread partials are folded in shared
-// memory so a block issues ONE global atomic per channel.
-__global__ void __launch_bounds__(256) colsum_kernel(const act_t* __restrict__ x, long long rows, int C, long long rows_per_block,
-                                                     float scale, float* __restrict__ out, float* __restrict__ out2,
-                                                     const float* __restrict__ gscale) {
-    extern __shared__ float csh[];   // [C]
-    if (gscale) scale *= gscale[1];
-    for (int i = threadIdx.x; i < C; i += blockDim.x) csh[i] = 0.f;
-    __syncthreads();
-    const int vpr = C / 8;
-    const int rows_per_pass = blockDim.x / vpr;
-    const int vec = threadIdx.x % vpr, rsub = threadIdx.x / vpr;
-    if (rsub < rows_per_pass) {
-        const long long r0 = blockIdx.x * rows_per_block;
-        const long long r1 = min(rows, r0 + rows_per_block);
-        float acc[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-        for (long long r = r0 + rsub; r < r1; r += 4LL * rows_per_pass) {
-            uint4 raw[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const long long rr = r + static_cast<long long>(u) * rows_per_pass;
-                raw[u] = (rr < r1) ? __ldg(reinterpret_cast<const uint4*>(x + rr * C + vec * 8)) : make_uint4(0, 0, 0, 0);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const __half2* h = reinterpret_cast<const __half2*>(&raw[u]);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float2 f = __half22float2(h[i]);
-                    acc[2 * i] += f.x;
-                    acc[2 * i + 1] += f.y;
-                }
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) atomicAdd(&csh[vec * 8 + i], acc[i]);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < C; i += blockDim.x) {
-        const float v = scale * csh[i];
-        atomicAdd(&out[i], v);
-        if (out2) atomicAdd(&out2[i], v);   // two biases folded into one GEMM (out-conv + skip-conv)
-    }
-}
 // dst[k][co] = w[co][ci][t] with k = t * Ci + ci: transpose of the stem's packed [Co][64] matrix (rows >= T * Ci stay zero)
 __global__ void pack_stem_t_kernel(const float* __restrict__ w, act_t* __restrict__ dst, int Co, int Ci, int T, long long ld) {
     const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
