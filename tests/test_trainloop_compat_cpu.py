@@ -61,3 +61,26 @@ def test_reference_mixed_precision_trainer_drives_the_shim(use_fp16):
     assert sum(m.numel() for m in masters) == sum(p.numel() for p in model.parameters())
     trainer.zero_grad()
     assert all(p.grad is None or float(p.grad.abs().sum()) == 0.0 for p in model.parameters())
+
+
+def test_script_util_surface_matches_reference():
+    """model_and_diffusion_defaults(): same keys, same default values; argparse helpers behave the same; the factory
+    accepts exactly the reference's keyword set (every script builds its parser from these)."""
+    _import_fp16_util()
+    import argparse
+    import inspect
+    from mm_diffusion import multimodal_script_util as ref
+    from mm_diffusion_b200 import script_util as ours
+    rd, od = ref.model_and_diffusion_defaults(), ours.model_and_diffusion_defaults()
+    assert list(rd.keys()) == list(od.keys())
+    assert rd == od
+    assert set(inspect.signature(ref.create_model_and_diffusion).parameters) == \
+        set(inspect.signature(ours.create_model_and_diffusion).parameters)
+    pr, po = argparse.ArgumentParser(), argparse.ArgumentParser()
+    ref.add_dict_to_argparser(pr, rd)
+    ours.add_dict_to_argparser(po, od)
+    argv = ["--use_fp16", "False", "--video_size", "16,3,64,64", "--cross_attention_windows", "1,4,8", "--num_channels", "128"]
+    assert vars(pr.parse_args(argv)) == vars(po.parse_args(argv))
+    assert ref.args_to_dict(pr.parse_args(argv), rd.keys()) == ours.args_to_dict(po.parse_args(argv), od.keys())
+    for v in ("yes", "True", "0", "n"):
+        assert ref.str2bool(v) == ours.str2bool(v)
