@@ -94,6 +94,22 @@ int mmd_model_forward_train(MmdModel* m, int batch, const float* video_in, const
                             const int32_t* shifts, float* video_out, float* audio_out, void* stream);
 int mmd_model_backward(MmdModel* m, int batch, const float* d_video_out, const float* d_audio_out, float* param_grads,
                        float* d_video_in, float* d_audio_in, void* stream);
+/* nn.Dropout of the ResBlock out_layers (multimodal_unet.py:370-386; `--dropout 0.1` in ssh_scripts/multimodal_train.sh:4):
+ * probability and 64-bit seed used by the NEXT mmd_model_forward_train calls (p = 0, the default, disables dropout).
+ * An element is kept iff Philox4x32-10(seed, site, element index) >= p and scaled by 1 / (1 - p); mmd_model_backward
+ * regenerates the same mask.  Inference (mmd_model_forward) never drops. */
+int mmd_model_set_dropout(MmdModel* m, float p, uint64_t seed);
+/* Training-forward counter of the plan for `batch` (0 = none yet).  A backward belongs to the forward after which this
+ * value was read; a later forward at the same batch size overwrites the kept activations (callers compare). */
+int64_t mmd_model_train_generation(const MmdModel* m, int batch);
+/* Dropout sites of the training plan for `batch` in execution order (per ResBlock: video out_layers, then audio), and
+ * the keep mask the LAST training forward used at site `index`: uint8 [rows][channels], channels-last like the
+ * activation (video rows = B*F*H*W, audio rows = B*L); modality 0 = video, 1 = audio.  (Parity tests hand the masks to
+ * the oracle.) */
+int mmd_model_num_dropout_sites(const MmdModel* m, int batch);
+int mmd_model_dropout_site(const MmdModel* m, int batch, int index, int64_t* rows, int* channels, int* modality);
+int mmd_model_dropout_mask(const MmdModel* m, int batch, int index, unsigned char* keep, void* stream);
+
 size_t mmd_model_train_workspace_bytes(const MmdModel* m, int batch);
 int64_t mmd_model_param_offset(const MmdModel* m, int index);
 int64_t mmd_model_param_floats(const MmdModel* m);
@@ -171,6 +187,13 @@ typedef struct MmdConvDesc {
     int64_t gn_rows;
 } MmdConvDesc;
 int mmd_op_conv(const MmdConvDesc* d, void* stream);
+/* Pointwise convolution (n_taps == 1) whose source 0 is first normalised: conv(act(GroupNorm32(src0) * (1 + scale) +
+ * shift) ++ src1..) — the ResBlock out_layers (multimodal_unet.py:459-470) and the attention norms (:284, :664) with
+ * the GroupNorm apply done on the GEMM's A operand in shared memory (no normalised tensor in HBM).  ns domains:
+ * rank 2: tokens / ns consecutive rows each (64 or a multiple of 128); rank 3 (L,B): one per sample (ns == dims[1]).
+ * film: [ns / ns_per_batch][film_ld] with scale at [0,C) and shift at [C,2C), or NULL. */
+int mmd_op_conv_gn(const MmdConvDesc* d, const float* gamma, const float* beta, const float* film, int film_ld, int ns,
+                   int ns_per_batch, int silu, void* stream);
 
 /* Attention core.  q/k/v are column ranges of row-major fp16 matrices.
  * Query block i of sample b attends key blocks (i+shift+j) mod n_blocks, j<win

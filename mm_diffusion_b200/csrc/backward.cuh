@@ -107,6 +107,8 @@ struct GnBwdArgs {
     int do_silu;
     const act_t* dy;       // [ns * R][C]
     float* T;              // [ns][C][2]
+    const DropState* drop; // dropout applied to the forward output (null = none): dy is masked / scaled on the fly
+    uint32_t drop_site;
 };
 
 // shared layout: a[C] b[C] rs[C] mr[C] (u = x a + b, xh = x rs - mr) | gstat[64]
@@ -153,6 +155,10 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(GnBwdArgs g) {
     float* gstat = gsh + 4 * C;
     float* red = gstat + 64;
     const int ns = blockIdx.y;
+    DropState ds{0u, 0u, 0u, 0u};
+    if (g.drop != nullptr) ds = *g.drop;
+    const bool dropping = ds.thresh16 != 0u;
+    const float drop_scale = __uint_as_float(ds.scale_bits);
     for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) red[i] = 0.f;
     gn_bwd_prologue(g, ns, coef, gstat);
     const int vpr = C / 8;
@@ -190,10 +196,16 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(GnBwdArgs g) {
             for (int u = 0; u < GN_UNROLL; ++u) {
                 const __half* xh = reinterpret_cast<const __half*>(&xr[u]);
                 const __half* dh = reinterpret_cast<const __half*>(&dr[u]);
+                uint32_t keep = 0xFFu;
+                if (dropping) {
+                    const int rr = r + u * rows_per_pass;
+                    keep = dropout_keep8(ds, g.drop_site, ((static_cast<unsigned long long>(ns) * g.R + rr) * C + c0) >> 3);
+                }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const float x = __half2float(xh[i]);
                     float du = __half2float(dh[i]);
+                    if (dropping) du = ((keep >> i) & 1u) ? du * drop_scale : 0.f;
                     if (g.do_silu) du *= dsilu_fast(fmaf(x, ca[i], cb[i]));
                     const float xn = fmaf(x, crs[i], -cmr[i]);
                     t1[i] += du;
@@ -225,6 +237,10 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(GnBwdArgs g, GnBwdOut
     float* pc = gstat + 64;
     float* qr = pc + C;
     const int ns = blockIdx.y;
+    DropState ds{0u, 0u, 0u, 0u};
+    if (g.drop != nullptr) ds = *g.drop;
+    const bool dropping = ds.thresh16 != 0u;
+    const float drop_scale = __uint_as_float(ds.scale_bits);
     gn_bwd_prologue(g, ns, coef, gstat);
     const float* T = g.T + static_cast<size_t>(ns) * 2 * C;
     if (threadIdx.x < 32) {
@@ -300,10 +316,13 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(GnBwdArgs g, GnBwdOut
             const __half* ph = reinterpret_cast<const __half*>(&pv[u]);
             uint4 outv;
             __half* oh = reinterpret_cast<__half*>(&outv);
+            uint32_t keep = 0xFFu;
+            if (dropping) keep = dropout_keep8(ds, g.drop_site, ((static_cast<unsigned long long>(ns) * g.R + rr) * C + c0) >> 3);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float x = __half2float(xh[i]);
                 float du = __half2float(dh[i]);
+                if (dropping) du = ((keep >> i) & 1u) ? du * drop_scale : 0.f;
                 if (g.do_silu) du *= dsilu_fast(fmaf(x, ca[i], cb[i]));
                 float dx = fmaf(cp[i], du, fmaf(x, cx[i], cc[i]));
                 if (dacc) dx += __half2float(ph[i]);

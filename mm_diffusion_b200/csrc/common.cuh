@@ -138,6 +138,17 @@ MMD_DEVINL void tma_load_nd(int rank, void* dst, const CUtensorMap* m, uint64_t*
     }
 }
 
+// L2 prefetch of a tile (no shared-memory destination, no completion tracking)
+MMD_DEVINL void tma_prefetch_nd(int rank, const CUtensorMap* m, const int* c) {
+    const uint64_t mp = reinterpret_cast<uint64_t>(m);
+    switch (rank) {
+        case 2: asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(mp), "r"(c[0]), "r"(c[1]) : "memory"); break;
+        case 3: asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(mp), "r"(c[0]), "r"(c[1]), "r"(c[2]) : "memory"); break;
+        case 4: asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(mp), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]) : "memory"); break;
+        default: asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];" ::"l"(mp), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]) : "memory"); break;
+    }
+}
+
 MMD_DEVINL void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                      reinterpret_cast<uint64_t>(m)),
@@ -264,5 +275,38 @@ MMD_DEVINL void named_bar_sync(uint32_t id, uint32_t nthreads) {
 }
 
 MMD_DEVINL float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+
+// ------------------------------------------------------------------ dropout
+// Counter-based Philox4x32-10 (Salmon et al., SC'11): 128 random bits per (key, counter).  The training path uses it
+// for nn.Dropout (multimodal_unet.py:376,384): the mask of an element depends only on (seed, site, element index), so
+// the backward regenerates it instead of storing it.
+MMD_DEVINL uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += 0x9E3779B9u;
+        key.y += 0xBB67AE85u;
+    }
+    return ctr;
+}
+// Dropout parameters of one training forward, in device memory (the captured graphs read them at replay):
+// {seed lo, seed hi, drop threshold on 16-bit uniforms (0 = dropout off), float bits of 1 / (1 - p)}.
+struct DropState { uint32_t seed_lo, seed_hi, thresh16, scale_bits; };
+// Keep mask (bit i = keep channel c0 + i) of the 8 consecutive elements starting at element index 8 * idx8 of dropout
+// site `site`: element kept iff its 16-bit uniform >= thresh16, i.e. P(drop) = thresh16 / 65536.
+MMD_DEVINL uint32_t dropout_keep8(const DropState& d, uint32_t site, unsigned long long idx8) {
+    const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(idx8), static_cast<uint32_t>(idx8 >> 32), site, 0x6d6d64u),
+                                  make_uint2(d.seed_lo, d.seed_hi));
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+    uint32_t keep = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        keep |= ((w[i] & 0xFFFFu) >= d.thresh16 ? 1u : 0u) << (2 * i);
+        keep |= ((w[i] >> 16) >= d.thresh16 ? 1u : 0u) << (2 * i + 1);
+    }
+    return keep;
+}
 
 }  // namespace mmd

@@ -102,9 +102,15 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(GnSrc s, int R, int rows_
 __global__ void __launch_bounds__(256) gn_apply_kernel(GnSrc s, int R, int rows_per_block, const double* __restrict__ sums,
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 const float* __restrict__ film, int film_ld, int ns_per_batch, int do_silu,
-                                act_t* __restrict__ y, int nsub, long long stat_rows) {
+                                act_t* __restrict__ y, int nsub, long long stat_rows,
+                                const DropState* __restrict__ drop, uint32_t drop_site) {
     pdl_trigger();
     pdl_wait();
+    // nn.Dropout after the SiLU of the ResBlock out_layers (multimodal_unet.py:376,384), training forwards only
+    DropState ds{0u, 0u, 0u, 0u};
+    if (drop != nullptr) ds = *drop;
+    const bool dropping = ds.thresh16 != 0u;
+    const float drop_scale = __uint_as_float(ds.scale_bits);
     extern __shared__ float coef[];  // [2][C] then [64] group mean / rstd
     const int C = s.c1 + s.c2;
     const int cpg = C / 32;
@@ -168,12 +174,19 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnSrc s, int R, int rows_
             const __half2* h = reinterpret_cast<const __half2*>(&raw[u]);
             uint4 outv;
             __half2* o = reinterpret_cast<__half2*>(&outv);
+            uint32_t keep = 0xFFu;
+            if (dropping)
+                keep = dropout_keep8(ds, drop_site, ((static_cast<unsigned long long>(ns) * R + rr) * C + c0) >> 3);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const float2 f = __half22float2(h[k]);
                 float u0 = fmaf(f.x, ca[2 * k], cb[2 * k]);
                 float u1 = fmaf(f.y, ca[2 * k + 1], cb[2 * k + 1]);
                 if (do_silu) { u0 = silu_fast(u0); u1 = silu_fast(u1); }
+                if (dropping) {
+                    u0 = ((keep >> (2 * k)) & 1u) ? u0 * drop_scale : 0.f;
+                    u1 = ((keep >> (2 * k + 1)) & 1u) ? u1 * drop_scale : 0.f;
+                }
                 o[k] = __floats2half2_rn(u0, u1);
             }
             *reinterpret_cast<uint4*>(ybase + static_cast<size_t>(rr) * C) = outv;

@@ -26,6 +26,8 @@ constexpr int GEMM_BK = 64;        // channels per k-iteration (one 128-byte swi
 constexpr int GEMM_MAX_SRC = 4;
 constexpr int GEMM_MAX_TAPS = 27;
 constexpr int GEMM_THREADS = 192;  // warp0 TMA, warp1 MMA, warps2-5 epilogue
+constexpr int GEMM_THREADS_XF = 320;  // + warps6-9: A-operand transform (fused GroupNorm apply)
+constexpr int GEMM_XF_MAXC = 512;  // widest source the fused GroupNorm apply supports
 
 struct alignas(64) GemmParams {
     CUtensorMap a_map[GEMM_MAX_SRC];  // activation sources, rank `rank`, box (64, box[0..3])
@@ -55,9 +57,27 @@ struct alignas(64) GemmParams {
     int stats_mul[4];       // domain base = sum_i origin[i+1] * stats_mul[i] / stats_div
     int stats_div;
     int stats_valid_coord;  // >= 0: rows >= dims[c] - origin[c+1] of the tile are padding (ragged last tile)
+    // fused GroupNorm apply on the A operand of source 0 (XF kernels, pointwise GEMMs):
+    //   a <- act(gn(a) * (1 + scale) + shift), done in shared memory between the TMA landing and the MMA
+    //   (reference: nn.py:22-33 + multimodal_unet.py:459-470 out_layers / :284,664 attention norms)
+    const double* xf_sums;  // statistics slots [domains * xf_nsub][32][2]; null = off
+    const float* xf_gamma;
+    const float* xf_beta;
+    const float* xf_film;   // [batch][xf_film_ld]: scale at [0,C), shift at [C,2C); may be null
+    int xf_film_ld;
+    int xf_dom_per_batch;   // FiLM row = domain / xf_dom_per_batch
+    int xf_c, xf_nsub, xf_silu;
+    double xf_inv_n;        // 1 / (rows * channels-per-group) the statistics of one domain cover
+    int xf_rows;            // rows of one domain inside a tile (64 or 128)
+    int xf_mul[4];          // domain base = sum_i origin[i+1] * xf_mul[i] / xf_div
+    int xf_div;
+    // L2 prefetch distance of the A operand in tiles of this CTA's tile sequence (0 = off): short-K GEMMs are bound by
+    // the bytes in flight against DRAM latency, not by the tensor pipe; prefetching the tiles this CTA will load a
+    // few iterations from now turns the pipeline's TMA loads into L2 hits.
+    int pf_tiles;
 };
 
-template <int BN, int OC>
+template <int BN, int OC, bool XF = false>
 struct GemmSmem {
     static constexpr int A_BYTES = GEMM_BM * 128;
     static constexpr int B_BYTES = BN * 128;
@@ -70,14 +90,17 @@ struct GemmSmem {
     static constexpr int OUT_BYTES = (BN >= 64) ? 2 * OUT_BUF : 0;
     // barriers (256 B) | GroupNorm partials [BN/64 units][4 bands][16 quads][2] floats
     static constexpr int GN_BYTES = (BN >= 64) ? (BN / 64) * 4 * 16 * 2 * 4 : 0;
-    static constexpr int BAR_BYTES = 256 + GN_BYTES;
+    // XF: per-channel affine table [2 domains][a|b][GEMM_XF_MAXC] floats + group mean / rstd [2][32][2]
+    static constexpr int XF_OFF = 256 + GN_BYTES;
+    static constexpr int XF_BYTES = XF ? (2 * 2 * GEMM_XF_MAXC * 4 + 512) : 0;
+    static constexpr int BAR_BYTES = 256 + GN_BYTES + XF_BYTES;
     static constexpr int LIMIT = 232448;   // 227 KB
     static constexpr int FIT = (LIMIT - OUT_BYTES - BAR_BYTES) / STAGE_BYTES;
     static constexpr int STAGES = FIT > 8 ? 8 : FIT;
     static constexpr int TOTAL = STAGES * STAGE_BYTES + OUT_BYTES + BAR_BYTES;   // base is 1024-aligned (checked)
     static_assert(BN < 64 || (OC % 64 == 0 && BN % OC == 0), "staging chunk");
     static_assert(STAGES >= 3 && TOTAL <= LIMIT, "shared memory budget");
-    static_assert(2 * STAGES + 4 <= 30, "barrier block");
+    static_assert(3 * STAGES + 4 <= 30, "barrier block");
     static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : ((2 * BN <= 64) ? 64 : ((2 * BN <= 128) ? 128 : ((2 * BN <= 256) ? 256 : 512)));
 };
 
@@ -92,9 +115,9 @@ MMD_DEVINL void gemm_tile_origin(const GemmParams& p, int m_idx, int* c /*[5]*/)
     c[0] = 0;
 }
 
-template <int BN, int OC>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid_constant__ GemmParams p) {
-    using S = GemmSmem<BN, OC>;
+template <int BN, int OC, bool XF>
+__global__ void __launch_bounds__(XF ? GEMM_THREADS_XF : GEMM_THREADS, 1) conv_gemm_kernel(const __grid_constant__ GemmParams p) {
+    using S = GemmSmem<BN, OC, XF>;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* stage_base = smem;
     uint8_t* out_stage = smem + S::STAGES * S::STAGE_BYTES;
@@ -103,7 +126,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
     uint64_t* empty_bar = bars + S::STAGES;
     uint64_t* tfull_bar = bars + 2 * S::STAGES;
     uint64_t* tempty_bar = bars + 2 * S::STAGES + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::STAGES + 4);
+    uint64_t* xf_bar = bars + 2 * S::STAGES + 4;   // [STAGES] (XF only): A tile transformed, the MMA may read it
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S::STAGES + 4);
     float* gn_part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
 
     const int warp = threadIdx.x >> 5;
@@ -125,6 +149,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
         for (int i = 0; i < S::STAGES; ++i) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
+            if constexpr (XF) mbar_init(&xf_bar[i], 4);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
@@ -154,6 +179,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                 }
             }
             pdl_wait();
+            // A tiles of the next pf_tiles-1 tiles of this CTA go to L2 right away; inside the loop every k-block load
+            // is paired with the prefetch of the same k-block pf_tiles tiles ahead
+            const int pf = p.pf_tiles;
+            for (int d = 1; d < pf; ++d) {
+                const int tile = blockIdx.x + d * gridDim.x;
+                if (tile >= total_tiles) break;
+                int org[5];
+                gemm_tile_origin(p, tile / p.n_tiles, org);
+                for (int t = 0; t < p.n_taps; ++t) {
+                    int c[5] = {0, org[1] + p.tap[t][0], org[2] + p.tap[t][1], org[3] + p.tap[t][2], org[4]};
+                    for (int s = 0; s < p.n_src; ++s)
+                        for (int ch = 0; ch < p.src_chunks[s]; ++ch) {
+                            c[0] = ch * GEMM_BK;
+                            tma_prefetch_nd(p.rank, &p.a_map[s], c);
+                        }
+                }
+            }
             int stage = 0;
             uint32_t phase = 0;
             int gk = 0;   // k-blocks issued by this CTA (the first `pre` already have their B half in flight)
@@ -162,6 +204,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                 const int n_idx = tile - m_idx * p.n_tiles;
                 int org[5];
                 gemm_tile_origin(p, m_idx, org);
+                const int pf_tile = tile + pf * static_cast<int>(gridDim.x);
+                const bool pf_on = pf > 0 && pf_tile < total_tiles;
+                int porg[5] = {0, 0, 0, 0, 0};
+                if (pf_on) gemm_tile_origin(p, pf_tile / p.n_tiles, porg);
                 int kb = 0;
                 for (int t = 0; t < p.n_taps; ++t) {
                     int c[5];
@@ -169,8 +215,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                     c[2] = org[2] + p.tap[t][1];
                     c[3] = org[3] + p.tap[t][2];
                     c[4] = org[4];
+                    int pc[5] = {0, porg[1] + p.tap[t][0], porg[2] + p.tap[t][1], porg[3] + p.tap[t][2], porg[4]};
                     for (int s = 0; s < p.n_src; ++s) {
                         for (int ch = 0; ch < p.src_chunks[s]; ++ch, ++kb, ++gk) {
+                            if (pf_on) {
+                                pc[0] = ch * GEMM_BK;
+                                tma_prefetch_nd(p.rank, &p.a_map[s], pc);
+                            }
                             mbar_wait(&empty_bar[stage], phase ^ 1);
                             uint8_t* a_dst = stage_base + stage * S::STAGE_BYTES;
                             if (gk >= pre) mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
@@ -189,6 +240,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
             constexpr uint32_t idesc = umma_idesc_f16(GEMM_BM, BN, 0, 0);
             int stage = 0;
             uint32_t phase = 0;
+            uint32_t xf_bits = 0;   // per-stage phase parity of xf_bar (a stage's xf barrier only cycles when it held a transformed block)
+            const int xf_chunks = (XF && p.xf_sums != nullptr) ? p.src_chunks[0] : 0;   // pointwise: the first k-blocks of a tile
             int it = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
                 const int acc = it & 1;
@@ -197,7 +250,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
+                    if (XF && kb < xf_chunks) {
+                        mbar_wait(&xf_bar[stage], (xf_bits >> stage) & 1u);
+                        xf_bits ^= 1u << stage;
+                    } else {
+                        mbar_wait(&full_bar[stage], phase);
+                    }
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(stage_base + stage * S::STAGE_BYTES);
                     // one descriptor per operand and k-iteration; the 16-element k-steps only bump the 16-byte-unit
@@ -211,6 +269,106 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                     if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&tfull_bar[acc]);
+            }
+        }
+    } else if (XF && warp >= 6) {
+        // ================= A-operand transform (4 warps): fused GroupNorm apply (+FiLM, +SiLU) on source 0 =================
+        // thread = (16-byte column unit `oct` of the 128-byte row, group of 8 rows `rg`): a warp touches four complete
+        // rows per access (conflict-free in the 128-byte swizzle), and every thread needs just 8 channels of the affine
+        // table per k-block.  y = act(x * a[c] + b[c]) in fp32, stored back in place; SiLU = h + h tanh(h), h = y / 2
+        // (one MUFU op per element; the 1/2 is folded into the table).
+        if (p.xf_sums != nullptr) {
+            float* xf_coef = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + S::XF_OFF);   // [dl][a|b][c]
+            float* xf_gstat = xf_coef + 2 * 2 * GEMM_XF_MAXC;                                          // [dl][32][mean|rstd]
+            const int tt = threadIdx.x - 192;           // 0..127
+            const int oct = tt & 7, rg = tt >> 3;
+            const int C = p.xf_c;
+            const int cpg = C / 32;
+            const int ndom = (p.xf_rows < GEMM_BM) ? 2 : 1;
+            const int dl = (rg * 8) / p.xf_rows;
+            const int xf_chunks = p.src_chunks[0];
+            const bool do_silu = p.xf_silu != 0;
+            const float pre = do_silu ? 0.5f : 1.0f;
+            int stage = 0;
+            uint32_t phase = 0;
+            int cached_dom = -1;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int m_idx = tile / p.n_tiles;
+                int org[5];
+                gemm_tile_origin(p, m_idx, org);
+                const int dom_base = (org[1] * p.xf_mul[0] + org[2] * p.xf_mul[1] + org[3] * p.xf_mul[2] +
+                                      org[4] * p.xf_mul[3]) / p.xf_div;
+                if (dom_base != cached_dom) {   // (re)build the per-channel affine table of this tile's domain(s)
+                    named_bar_sync(2, 128);
+                    if (tt < 32 * ndom) {
+                        const int d = tt >> 5, g = tt & 31;
+                        double su = 0.0, sq = 0.0;
+                        for (int k = 0; k < p.xf_nsub; ++k) {
+                            const double* sl = p.xf_sums + (static_cast<size_t>(dom_base + d) * p.xf_nsub + k) * 64;
+                            su += sl[2 * g];
+                            sq += sl[2 * g + 1];
+                        }
+                        const double mean = su * p.xf_inv_n;
+                        double var = sq * p.xf_inv_n - mean * mean;
+                        if (var < 0) var = 0;
+                        xf_gstat[(d * 32 + g) * 2] = static_cast<float>(mean);
+                        xf_gstat[(d * 32 + g) * 2 + 1] = rsqrtf(static_cast<float>(var) + 1e-5f);
+                    }
+                    named_bar_sync(2, 128);
+                    for (int i = tt; i < ndom * C; i += 128) {
+                        const int d = i / C, c = i - d * C;
+                        const int g = c / cpg;
+                        float a = xf_gstat[(d * 32 + g) * 2 + 1] * __ldg(p.xf_gamma + c);
+                        float b = __ldg(p.xf_beta + c) - xf_gstat[(d * 32 + g) * 2] * a;
+                        if (p.xf_film != nullptr) {
+                            const float* fb = p.xf_film + static_cast<size_t>((dom_base + d) / p.xf_dom_per_batch) * p.xf_film_ld;
+                            const float sc = 1.f + __ldg(fb + c);
+                            a *= sc;
+                            b = b * sc + __ldg(fb + C + c);
+                        }
+                        xf_coef[(d * 2 + 0) * GEMM_XF_MAXC + c] = a * pre;
+                        xf_coef[(d * 2 + 1) * GEMM_XF_MAXC + c] = b * pre;
+                    }
+                    named_bar_sync(2, 128);
+                    cached_dom = dom_base;
+                }
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    if (kb < xf_chunks) {
+                        const float* ca = xf_coef + (dl * 2 + 0) * GEMM_XF_MAXC + kb * GEMM_BK + oct * 8;
+                        const float* cb = xf_coef + (dl * 2 + 1) * GEMM_XF_MAXC + kb * GEMM_BK + oct * 8;
+                        const float4 a0 = *reinterpret_cast<const float4*>(ca), a1 = *reinterpret_cast<const float4*>(ca + 4);
+                        const float4 b0 = *reinterpret_cast<const float4*>(cb), b1 = *reinterpret_cast<const float4*>(cb + 4);
+                        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                        mbar_wait(&full_bar[stage], phase);
+                        uint8_t* a_tile = stage_base + stage * S::STAGE_BYTES;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            uint4* ptr = reinterpret_cast<uint4*>(a_tile + sw128_off(rg * 8 + j, oct));
+                            uint4 raw = *ptr;
+                            __half2* h = reinterpret_cast<__half2*>(&raw);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const float2 f = __half22float2(h[k]);
+                                float u0 = fmaf(f.x, av[2 * k], bv[2 * k]);
+                                float u1 = fmaf(f.y, av[2 * k + 1], bv[2 * k + 1]);
+                                if (do_silu) {
+                                    float t0, t1;
+                                    asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(u0));
+                                    asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(u1));
+                                    u0 = fmaf(u0, t0, u0);
+                                    u1 = fmaf(u1, t1, u1);
+                                }
+                                h[k] = __floats2half2_rn(u0, u1);
+                            }
+                            *ptr = raw;
+                        }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&xf_bar[stage]);
+                    }
+                    if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+                }
             }
         }
     } else {

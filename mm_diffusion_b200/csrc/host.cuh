@@ -116,6 +116,16 @@ struct GemmProblem {
     int stats_mul[4] = {0, 0, 0, 0};
     int stats_div = 1;
     int stats_valid_coord = -1;
+    // fused GroupNorm apply (+FiLM, +SiLU) on source 0 (pointwise GEMMs; see GemmParams::xf_*)
+    const double* xf_sums = nullptr;
+    const float* xf_gamma = nullptr;
+    const float* xf_beta = nullptr;
+    const float* xf_film = nullptr;
+    int xf_film_ld = 0, xf_dom_per_batch = 1, xf_nsub = 1, xf_silu = 0;
+    long long xf_stat_rows = 0;   // rows the statistics of one domain cover
+    int xf_rows = 128;            // rows of one domain inside a tile (64 or 128)
+    int xf_mul[4] = {0, 0, 0, 0};
+    int xf_div = 1;
     long long k_total() const {
         long long c = 0;
         for (int i = 0; i < n_src; ++i) c += src_c[i];
@@ -148,7 +158,10 @@ int launch_gn_stats(const GnSrc& s, int ns, int rows, double* sums, cudaStream_t
 // stat_rows rows in total (0 = rows; differs for nearest-upsampled inputs whose statistics come from the source).
 int launch_gn_apply(const GnSrc& s, int ns, int rows, const double* sums, const float* gamma, const float* beta,
                     const float* film, int film_ld, int ns_per_batch, int silu, act_t* y, cudaStream_t st,
-                    int nsub = 1, long long stat_rows = 0);
+                    int nsub = 1, long long stat_rows = 0, const DropState* drop = nullptr, uint32_t drop_site = 0);
+// nn.Dropout parameters of a training forward -> device DropState (p == 0 disables); keep mask export for the tests
+int launch_set_dropout(DropState* dev, float p, unsigned long long seed, cudaStream_t st);
+int launch_dropout_mask(const DropState* dev, uint32_t site, long long elems, unsigned char* keep, cudaStream_t st);
 int launch_gn_temporal(const act_t* x, act_t* y, const float* gamma, const float* beta, int B, int F, int P, int C,
                        cudaStream_t st);
 int launch_resample(const act_t* x, act_t* y, int mode, int n, int h, int w, int c, cudaStream_t st);
@@ -213,6 +226,8 @@ struct GnBwdProblem {
     float* dbeta = nullptr;
     float* dfilm = nullptr;
     const float* gscale = nullptr;
+    const DropState* drop = nullptr;   // dropout of the forward output (training): regenerated from (seed, site, index)
+    uint32_t drop_site = 0;
 };
 int launch_gn_bwd(const GnBwdProblem& pr, cudaStream_t st);
 int launch_gn_temporal_bwd(const act_t* x, const act_t* dy, act_t* dx, const float* gamma, float* dgamma, float* dbeta, int B,

@@ -91,6 +91,12 @@ struct Plan {
     act_t* wpk_t = nullptr;             // transposed packs
     float* zero_bias = nullptr;
     bool fwd_done = false;
+    long long generation = 0;           // bumped by every training forward: a backward must match the forward it follows
+    // nn.Dropout of the ResBlock out_layers (multimodal_unet.py:376,384): parameters of the current training forward in
+    // device memory (read by the captured graphs), and the sites in execution order (tests export their masks)
+    DropState* drop_dev = nullptr;
+    struct DropSite { uint32_t site; long long rows; int C; int modality; };
+    std::vector<DropSite> drop_sites;
     ~Plan() {
         if (graph) cudaGraphExecDestroy(graph);
         if (bwd_graph) cudaGraphExecDestroy(bwd_graph);
@@ -120,6 +126,7 @@ struct TapeOp {
     const double* sums = nullptr;
     long long stat_rows = 0;
     act_t* y = nullptr;
+    int drop_site = -1;       // >= 0: the forward applied dropout to y (site id of the Philox stream)
     // GN_TEMPORAL / TATTN / RESAMPLE
     const act_t* in = nullptr;
     int B = 0, F = 0, P = 0, C = 0, heads = 0, mode = 0, n_ = 0, h_ = 0, w_ = 0;
@@ -145,6 +152,8 @@ struct MmdModel {
     float* bpk = nullptr;      // packed fp32 biases + stacked emb weights
     size_t bpk_floats = 0;
     bool dirty = true;
+    float drop_p = 0.f;                    // dropout of the next training forward (mmd_model_set_dropout)
+    unsigned long long drop_seed = 0;
     std::vector<int> shift_bounds;  // per cross block in execution order; -1 = no draw
     int emb_rows = 0;               // stacked emb_layers rows
     size_t emb_w_off = 0, emb_b_off = 0;
@@ -175,6 +184,18 @@ namespace mmd {
 struct Stat { double* slots = nullptr; int nsub = 1; long long rows = 0; };
 struct VT { act_t* p; int C, H, W; Stat st; };   // video [B,F,H,W,C]
 struct AT { act_t* p; int C, L; Stat st; };      // audio [B,L,C]
+// A GroupNorm whose apply is deferred into the A path of the pointwise GEMM that consumes it (inference plans):
+// kind 1 = rank-2 token geometry (domain = token / rows), 3 = audio geometry (L,B) (domain = sample).
+struct XfSpec {
+    bool on = false;
+    int kind = 0;
+    const double* sums = nullptr;
+    int nsub = 1;
+    long long stat_rows = 0;
+    int gn_g = -1, gn_b = -1;
+    const float* film = nullptr;
+    int ns_per_batch = 1, silu = 0, ns = 0, rows = 0;
+};
 
 struct Walker {
     MmdModel& m;
@@ -198,9 +219,12 @@ struct Walker {
     int err = MMD_OK;
     size_t w32_top = 0, wpk_top = 0, bpk_top = 0;
     int shift_slot = 0;
+    int drop_site_top = 0;
     int emb_row_top = 0;
     bool wide_n = true;         // MMD_NO_BN256=1 keeps 128-wide GEMM tiles
     bool fuse_stats = true;     // MMD_NO_FUSED_STATS=1 keeps every GroupNorm on the standalone statistics kernel
+    int xf_mask = 7;            // MMD_XF bitmask: GroupNorm apply folded into the consumer GEMM's A path for
+                                // 1 = ResBlock out_layers, 2 = self-attention norms, 4 = cross-attention norms
     float* emb_all = nullptr;   // [B][emb_rows]
     float* silu_emb = nullptr;  // [B][E]
 
@@ -212,6 +236,8 @@ struct Walker {
         fuse_stats = !(e && e[0] == '1');
         const char* w = getenv("MMD_NO_BN256");
         wide_n = !(w && w[0] == '1');
+        const char* x = getenv("MMD_XF");
+        if (x) xf_mask = atoi(x);
     }
     double* stat_slots_video() { return static_cast<double*>(stats.take(sizeof(double) * 64 * B * F())); }
     double* stat_slots_audio() { return static_cast<double*>(stats.take(sizeof(double) * 64 * B)); }
@@ -341,7 +367,7 @@ struct Walker {
     void emit_gemm(const char* tag, const ConvGeom& g, const std::vector<std::pair<const act_t*, int>>& srcs,
                    const std::vector<std::array<int, 3>>& taps, const PackedConv* pc, act_t* out, float* out_f32 = nullptr,
                    const long long* ostride = nullptr, long long ostride_c = 0, double* stat_slots = nullptr,
-                   int stat_kind = 0, int stat_hw = 0, int stem = 0) {
+                   int stat_kind = 0, int stat_hw = 0, int stem = 0, const XfSpec* xf = nullptr) {
         if (train && pc) {
             TapeOp op;
             op.kind = TapeOp::GEMM;
@@ -382,6 +408,13 @@ struct Walker {
         } else if (stat_slots && stat_kind == 3) {
             pr.stats = stat_slots; pr.stats_rows = 128; pr.stats_mul[1] = 1; pr.stats_div = 1; pr.stats_valid_coord = 0;
         }
+        if (xf && xf->on) {
+            pr.xf_sums = xf->sums; pr.xf_gamma = pf(xf->gn_g); pr.xf_beta = pf(xf->gn_b); pr.xf_film = xf->film;
+            pr.xf_film_ld = m.emb_rows; pr.xf_dom_per_batch = xf->ns_per_batch; pr.xf_nsub = xf->nsub; pr.xf_silu = xf->silu;
+            pr.xf_stat_rows = xf->stat_rows;
+            if (xf->kind == 1) { pr.xf_rows = std::min(xf->rows, 128); pr.xf_mul[0] = 1; pr.xf_div = xf->rows; }
+            else { pr.xf_rows = 128; pr.xf_mul[1] = 1; pr.xf_div = 1; }
+        }
         auto gp = std::make_shared<GemmParams>();
         int r = build_gemm(pr, gp.get());
         if (r != MMD_OK) { set_err(r); return; }
@@ -400,11 +433,36 @@ struct Walker {
     // GroupNorm over `ns` domains of `rows` rows on the concat of (x1,c1),(x2,c2)
     // `st` (optional): statistics already accumulated by the producer of x1 (single-source only);
     // per_frame selects one slot per domain instead of the nsub slots of a sample.
+    // xf (optional, inference plans): the consumer is a pointwise GEMM of geometry xf_kind that can apply the norm on
+    // its A operand; then nothing is written here (only the statistics, if the producer did not fuse them) and the
+    // raw input is returned for the GEMM to read.
     act_t* emit_gn(const act_t* x1, int c1, const act_t* x2, int c2, int ns, int rows, GnP gn, const float* film,
-                   int ns_per_batch, int silu, const Stat* st = nullptr, bool per_frame = false) {
+                   int ns_per_batch, int silu, const Stat* st = nullptr, bool per_frame = false, XfSpec* xf = nullptr,
+                   int xf_kind = 0, int drop_modality = -1) {
         const int C = c1 + c2;
-        act_t* y = alloc_s(static_cast<size_t>(ns) * rows * C);
+        // training plans: the out_layers' Dropout rides on this kernel (mask from a counter-based generator, so the
+        // backward regenerates it); inference plans never drop
+        const int drop_site = (train && drop_modality >= 0) ? drop_site_top++ : -1;
+        const DropState* drop_dev = (drop_site >= 0 && plan) ? plan->drop_dev : nullptr;
+        if (drop_site >= 0 && emitting())
+            plan->drop_sites.push_back(Plan::DropSite{static_cast<uint32_t>(drop_site), static_cast<long long>(ns) * rows, C, drop_modality});
         const bool fused = fuse_stats && st && st->slots && !x2;
+        const bool defer = xf && xf_kind != 0 && !train && !x2 && C % 64 == 0 && C <= GEMM_XF_MAXC &&
+                           (xf_kind == 3 ? (ns == B && rows >= 128) : (rows == 64 || rows % 128 == 0));
+        if (defer) {
+            double* sums = fused ? st->slots : static_cast<double*>(stats.take(sizeof(double) * 64 * ns));
+            xf->on = true; xf->kind = xf_kind; xf->sums = sums; xf->gn_g = gn.g; xf->gn_b = gn.b; xf->film = film;
+            xf->ns_per_batch = ns_per_batch; xf->silu = silu; xf->ns = ns; xf->rows = rows;
+            xf->nsub = fused ? (per_frame ? 1 : st->nsub) : 1;
+            xf->stat_rows = fused ? (per_frame ? st->rows / st->nsub : st->rows) : rows;
+            if (!fused && emitting() && !bad()) {
+                GnSrc s{x1, c1, c1, nullptr, 0, 0};
+                push([=](cudaStream_t stx) -> int { return launch_gn_stats(s, ns, rows, sums, stx, false); },
+                     "group_norm", 0.0, 2.0 * ns * static_cast<double>(rows) * C, 1);
+            }
+            return const_cast<act_t*>(x1);
+        }
+        act_t* y = alloc_s(static_cast<size_t>(ns) * rows * C);
         double* sums = fused ? st->slots : static_cast<double*>(stats.take(sizeof(double) * 64 * ns));
         if (train) {
             TapeOp op;
@@ -414,6 +472,7 @@ struct Walker {
             op.silu = silu; op.ns_per_batch = ns_per_batch; op.sums = sums; op.y = y;
             op.nsub = fused ? (per_frame ? 1 : st->nsub) : 1;
             op.stat_rows = fused ? (per_frame ? st->rows / st->nsub : st->rows) : rows;
+            op.drop_site = drop_site;
             tape.push_back(op);
         }
         if (!emitting() || bad()) return y;
@@ -424,8 +483,10 @@ struct Walker {
             const int film_ld = m.emb_rows;
             const int nsub = per_frame ? 1 : st->nsub;
             const long long srows = per_frame ? st->rows / st->nsub : st->rows;
+            const uint32_t dsite = drop_site >= 0 ? static_cast<uint32_t>(drop_site) : 0u;
             push([=](cudaStream_t stx) -> int {
-                return launch_gn_apply(s, ns, rows, sums, gamma, beta, film, film_ld, ns_per_batch, silu, y, stx, nsub, srows);
+                return launch_gn_apply(s, ns, rows, sums, gamma, beta, film, film_ld, ns_per_batch, silu, y, stx, nsub, srows,
+                                       drop_dev, dsite);
             }, "group_norm", 0.0, 2.0 * 2.0 * ns * static_cast<double>(rows) * C, 1);
             return y;
         }
@@ -433,9 +494,10 @@ struct Walker {
         const float* gamma = pf(gn.g);
         const float* beta = pf(gn.b);
         const int film_ld = m.emb_rows;
+        const uint32_t dsite = drop_site >= 0 ? static_cast<uint32_t>(drop_site) : 0u;
         push([=](cudaStream_t st) -> int {
             MMD_TRY(launch_gn_stats(s, ns, rows, sums, st, false));
-            return launch_gn_apply(s, ns, rows, sums, gamma, beta, film, film_ld, ns_per_batch, silu, y, st);
+            return launch_gn_apply(s, ns, rows, sums, gamma, beta, film, film_ld, ns_per_batch, silu, y, st, 1, 0, drop_dev, dsite);
         }, "group_norm", 0.0, 2.0 * 2.0 * ns * static_cast<double>(rows) * C, 2);
         return y;
     }
@@ -486,10 +548,12 @@ struct Walker {
         cur = (kind == 2) ? 1 : 0;
         const size_t mark = S().top;
         act_t* xn;
+        XfSpec xf;
+        XfSpec* xfp = (xf_mask & 2) ? &xf : nullptr;
         if (kind == 0) {
-            xn = emit_gn(x, C, nullptr, 0, B * F(), vt->H * vt->W, gn, nullptr, 1, 0, in_st, true);
+            xn = emit_gn(x, C, nullptr, 0, B * F(), vt->H * vt->W, gn, nullptr, 1, 0, in_st, true, xfp, 1);
         } else if (kind == 2) {
-            xn = emit_gn(x, C, nullptr, 0, B, at->L, gn, nullptr, 1, 0, in_st, false);
+            xn = emit_gn(x, C, nullptr, 0, B, at->L, gn, nullptr, 1, 0, in_st, false, xfp, 3);
         } else {
             xn = alloc_s(tokens * C);
             if (train) {
@@ -509,7 +573,7 @@ struct Walker {
         act_t* qkvb = alloc_s(tokens * 3 * C);
         AT aview{nullptr, C, at ? at->L : 0};
         const ConvGeom gtok = at ? geom_audio(aview) : geom2(static_cast<long long>(tokens));
-        emit_gemm("conv1x1_qkv", gtok, {{xn, C}}, {{0, 0, 0}}, pq, qkvb);
+        emit_gemm("conv1x1_qkv", gtok, {{xn, C}}, {{0, 0, 0}}, pq, qkvb, nullptr, nullptr, 0, nullptr, 0, 0, 0, &xf);
         act_t* o = alloc_s(tokens * C);
         if (kind == 0) {
             const int hw = vt->H * vt->W;
@@ -648,12 +712,14 @@ struct Walker {
                     xs = xr;
                 }
                 const int hwo = vo.H * vo.W;
-                act_t* h2 = emit_gn(h1, cout, nullptr, 0, B, Fr * hwo, vout_gn, film, 1, 1, &h1st, false);
+                XfSpec xfv;
+                act_t* h2 = emit_gn(h1, cout, nullptr, 0, B, Fr * hwo, vout_gn, film, 1, 1, &h1st, false,
+                                    (xf_mask & 1) ? &xfv : nullptr, 1, 0);
                 std::vector<std::pair<const act_t*, int>> srcs = {{h2, cout}, {xs, v.C}};
                 if (v2) srcs.push_back({v2, vc2});
                 if (can_fuse_video(hwo, cout)) vo.st = Stat{stat_slots_video(), Fr, static_cast<long long>(Fr) * hwo};
                 emit_gemm("conv1x1_out", geom2(static_cast<long long>(B) * Fr * hwo), srcs, {{0, 0, 0}}, p_vo, vo.p,
-                          nullptr, nullptr, 0, vo.st.slots, 1, hwo);
+                          nullptr, nullptr, 0, vo.st.slots, 1, hwo, 0, &xfv);
                 release(S(), mark);
             }
             // ---------------- audio branch
@@ -696,11 +762,14 @@ struct Walker {
                     h1 = h1r;
                     xs = xr;
                 }
-                act_t* h2 = emit_gn(h1, cout, nullptr, 0, B, ao.L, aout_gn, film, 1, 1, &h1st, false);
+                XfSpec xfa;
+                act_t* h2 = emit_gn(h1, cout, nullptr, 0, B, ao.L, aout_gn, film, 1, 1, &h1st, false,
+                                    (xf_mask & 1) ? &xfa : nullptr, 3, 1);
                 std::vector<std::pair<const act_t*, int>> srcs = {{h2, cout}, {xs, a.C}};
                 if (a2) srcs.push_back({a2, ac2});
                 if (can_fuse_audio(ao.L, cout)) ao.st = Stat{stat_slots_audio(), 1, ao.L};
-                emit_gemm("conv1x1_out", geom_audio(ao), srcs, {{0, 0, 0}}, p_ao, ao.p, nullptr, nullptr, 0, ao.st.slots, 3, 0);
+                emit_gemm("conv1x1_out", geom_audio(ao), srcs, {{0, 0, 0}}, p_ao, ao.p, nullptr, nullptr, 0, ao.st.slots, 3, 0,
+                          0, &xfa);
                 release(S(), mark);
                 cur = 0;
             }
@@ -754,14 +823,17 @@ struct Walker {
         act_t* aout = alloc_p(at * C);
         const size_t mark_v = scratch.top, mark_a = scratch_a.top;
         cur = 0;
-        act_t* vnrm = emit_gn(v.p, C, nullptr, 0, B, Fr * hw, vn, nullptr, 1, 0, &v.st, false);
+        XfSpec xfv, xfa;
+        act_t* vnrm = emit_gn(v.p, C, nullptr, 0, B, Fr * hw, vn, nullptr, 1, 0, &v.st, false, (xf_mask & 4) ? &xfv : nullptr, 1);
         act_t* vqkv = alloc_s(vt * 3 * C);
-        emit_gemm("conv1x1_qkv", geom2(static_cast<long long>(vt)), {{vnrm, C}}, {{0, 0, 0}}, p_vq, vqkv);
+        emit_gemm("conv1x1_qkv", geom2(static_cast<long long>(vt)), {{vnrm, C}}, {{0, 0, 0}}, p_vq, vqkv, nullptr, nullptr, 0,
+                  nullptr, 0, 0, 0, &xfv);
         act_t* ov = alloc_s(vt * C);
         cur = 1;
-        act_t* anrm = emit_gn(a.p, C, nullptr, 0, B, a.L, an, nullptr, 1, 0, &a.st, false);
+        act_t* anrm = emit_gn(a.p, C, nullptr, 0, B, a.L, an, nullptr, 1, 0, &a.st, false, (xf_mask & 4) ? &xfa : nullptr, 3);
         act_t* aqkv = alloc_s(at * 3 * C);
-        emit_gemm("conv1x1_qkv", geom_audio(a), {{anrm, C}}, {{0, 0, 0}}, p_aq, aqkv);
+        emit_gemm("conv1x1_qkv", geom_audio(a), {{anrm, C}}, {{0, 0, 0}}, p_aq, aqkv, nullptr, nullptr, 0, nullptr, 0, 0, 0,
+                  &xfa);
         act_t* oa = alloc_s(at * C);
         const int* sdev = (shift && plan) ? plan->shifts_dev + slot : nullptr;
         // video queries attend audio keys/values and vice versa (multimodal_unet.py:530-559): each branch needs the
@@ -1272,6 +1344,7 @@ struct Walker {
             pr.dgamma = g32_of(op.gn_g); pr.dbeta = g32_of(op.gn_b);
             pr.dfilm = op.emb_row0 >= 0 ? plan->d_emb_all + op.emb_row0 : nullptr;
             pr.gscale = plan->gscale;
+            if (op.drop_site >= 0) { pr.drop = plan->drop_dev; pr.drop_site = static_cast<uint32_t>(op.drop_site); }
             bpush([=](cudaStream_t st) -> int {
                 MMD_CUDA_OK(cudaMemsetAsync(T, 0, t_bytes, st));
                 return launch_gn_bwd(pr, st);
@@ -1553,7 +1626,8 @@ static int build_train_plan(MmdModel* m, int B, Plan** out) {
     plan->t_dev = reinterpret_cast<float*>(q); q += al(sizeof(float) * B);
     plan->shifts_dev = reinterpret_cast<int*>(q); q += al(sizeof(int) * 64);
     plan->gscale = reinterpret_cast<float*>(q);
-    plan->amax_bits = reinterpret_cast<unsigned int*>(q + 64); q += 1024;
+    plan->amax_bits = reinterpret_cast<unsigned int*>(q + 64);
+    plan->drop_dev = reinterpret_cast<DropState*>(q + 128); q += 1024;
     plan->g32 = reinterpret_cast<float*>(q); q += g32_bytes;
     plan->d_emb_all = reinterpret_cast<float*>(q); q += demb_bytes;
     plan->zero_bias = reinterpret_cast<float*>(q); q += zb_bytes;
@@ -1895,6 +1969,7 @@ int mmd_model_forward_train(MmdModel* m, int batch, const float* video_in, const
     Plan* plan = nullptr;
     MMD_TRY(build_train_plan(m, batch, &plan));
     MMD_TRY(stage_inputs(m, plan, batch, video_in, audio_in, timesteps, shifts, st));
+    MMD_TRY(launch_set_dropout(plan->drop_dev, m->drop_p, m->drop_seed, st));
     if (m->use_graph && train_graphs_enabled()) {
         if (!plan->graph) MMD_TRY(capture_forward_graph(m, plan, st));
         MMD_CUDA_OK(cudaGraphLaunch(plan->graph, st));
@@ -1908,7 +1983,52 @@ int mmd_model_forward_train(MmdModel* m, int batch, const float* video_in, const
     MMD_CUDA_OK(cudaMemcpyAsync(video_out, plan->out_video, vout, cudaMemcpyDeviceToDevice, st));
     MMD_CUDA_OK(cudaMemcpyAsync(audio_out, plan->out_audio, aout, cudaMemcpyDeviceToDevice, st));
     plan->fwd_done = true;
+    ++plan->generation;
     return MMD_OK;
+}
+
+/* nn.Dropout of the ResBlock out_layers (multimodal_unet.py:376,384; --dropout 0.1 in ssh_scripts/multimodal_train.sh):
+ * probability and seed of the NEXT mmd_model_forward_train calls (p = 0, the default, disables it).  The mask of an
+ * element is Philox4x32-10(seed, site, element index) >= p, regenerated by the backward. */
+int mmd_model_set_dropout(MmdModel* m, float p, uint64_t seed) {
+    if (!m) return fail(MMD_EINVAL, "null model");
+    if (!(p >= 0.f) || p >= 1.f) return fail(MMD_EINVAL, "dropout probability %f out of [0, 1)", p);
+    m->drop_p = p;
+    m->drop_seed = seed;
+    return MMD_OK;
+}
+/* Training-forward counter of the plan for `batch` (0 = none yet): a backward belongs to the forward that returned the
+ * same value (unet._UNetFunction checks it; a second forward before the backward overwrites the kept activations). */
+int64_t mmd_model_train_generation(const MmdModel* m, int batch) {
+    if (!m) return 0;
+    auto it = m->train_plans.find(batch);
+    return it == m->train_plans.end() ? 0 : static_cast<int64_t>(it->second->generation);
+}
+/* Dropout sites of the training plan in execution order (video then audio out_layers of every ResBlock) and the keep
+ * mask (uint8 [rows][channels], channels-last like the activation) the LAST training forward used at site `index`. */
+int mmd_model_num_dropout_sites(const MmdModel* m, int batch) {
+    if (!m) return 0;
+    auto it = m->train_plans.find(batch);
+    return it == m->train_plans.end() ? 0 : static_cast<int>(it->second->drop_sites.size());
+}
+int mmd_model_dropout_site(const MmdModel* m, int batch, int index, int64_t* rows, int* channels, int* modality) {
+    if (!m) return fail(MMD_EINVAL, "null model");
+    auto it = m->train_plans.find(batch);
+    if (it == m->train_plans.end() || index < 0 || index >= static_cast<int>(it->second->drop_sites.size()))
+        return fail(MMD_EINVAL, "dropout site %d of batch %d does not exist", index, batch);
+    const auto& s = it->second->drop_sites[index];
+    if (rows) *rows = s.rows;
+    if (channels) *channels = s.C;
+    if (modality) *modality = s.modality;
+    return MMD_OK;
+}
+int mmd_model_dropout_mask(const MmdModel* m, int batch, int index, unsigned char* keep, void* stream) {
+    if (!m || !keep) return fail(MMD_EINVAL, "null argument");
+    auto it = m->train_plans.find(batch);
+    if (it == m->train_plans.end() || index < 0 || index >= static_cast<int>(it->second->drop_sites.size()))
+        return fail(MMD_EINVAL, "dropout site %d of batch %d does not exist", index, batch);
+    const auto& s = it->second->drop_sites[index];
+    return launch_dropout_mask(it->second->drop_dev, s.site, s.rows * s.C, keep, static_cast<cudaStream_t>(stream));
 }
 
 int mmd_model_backward(MmdModel* m, int batch, const float* d_video_out, const float* d_audio_out, float* param_grads,

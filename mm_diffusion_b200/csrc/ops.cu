@@ -167,12 +167,37 @@ int build_gemm(const GemmProblem& pr, GemmParams* out) {
         p.stats_valid_coord = pr.stats_valid_coord;
         if (pr.stats_rows != 128 && pr.stats_rows != 64) return fail(MMD_EINVAL, "stats_rows %d", pr.stats_rows);
     }
+    if (pr.xf_sums) {
+        const int C = pr.src_c[0];
+        if (bn < 64 || pr.n_taps != 1) return fail(MMD_EINVAL, "fused GroupNorm apply needs a pointwise GEMM with a wide fp16 output");
+        if (C % 64 != 0 || C > GEMM_XF_MAXC) return fail(MMD_EINVAL, "fused GroupNorm apply: %d channels unsupported", C);
+        if (pr.xf_rows != 128 && pr.xf_rows != 64) return fail(MMD_EINVAL, "xf_rows %d", pr.xf_rows);
+        if (pr.xf_stat_rows <= 0 || pr.xf_div <= 0 || pr.xf_dom_per_batch <= 0) return fail(MMD_EINVAL, "fused GroupNorm apply: bad domain geometry");
+        p.xf_sums = pr.xf_sums;
+        p.xf_gamma = pr.xf_gamma;
+        p.xf_beta = pr.xf_beta;
+        p.xf_film = pr.xf_film;
+        p.xf_film_ld = pr.xf_film_ld;
+        p.xf_dom_per_batch = pr.xf_dom_per_batch;
+        p.xf_c = C;
+        p.xf_nsub = pr.xf_nsub;
+        p.xf_silu = pr.xf_silu;
+        p.xf_inv_n = 1.0 / (static_cast<double>(pr.xf_stat_rows) * (C / 32));
+        p.xf_rows = pr.xf_rows;
+        for (int i = 0; i < 4; ++i) p.xf_mul[i] = pr.xf_mul[i];
+        p.xf_div = pr.xf_div;
+    }
+    {   // L2 prefetch distance: short-K GEMMs only (K-heavy ones re-read their taps from L2 anyway)
+        static const int pf_kb = [] { const char* e = getenv("MMD_PF_KB"); return e ? atoi(e) : 16; }();
+        const long long num_kb = kt / GEMM_BK;
+        p.pf_tiles = (pf_kb > 0 && num_kb <= pf_kb) ? static_cast<int>((pf_kb + num_kb - 1) / num_kb) : 0;
+    }
     return MMD_OK;
 }
 
-template <int BN, int OC>
+template <int BN, int OC, bool XF = false>
 static int gemm_attr() {
-    MMD_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<BN, OC>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN, OC>::TOTAL));
+    MMD_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<BN, OC, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN, OC, XF>::TOTAL));
     return MMD_OK;
 }
 
@@ -185,6 +210,11 @@ int gemm_init_attrs() {
     MMD_TRY((gemm_attr<128, 128>()));
     MMD_TRY((gemm_attr<64, 64>()));
     MMD_TRY((gemm_attr<16, 64>()));
+    MMD_TRY((gemm_attr<256, 64, true>()));
+    MMD_TRY((gemm_attr<256, 128, true>()));
+    MMD_TRY((gemm_attr<128, 64, true>()));
+    MMD_TRY((gemm_attr<128, 128, true>()));
+    MMD_TRY((gemm_attr<64, 64, true>()));
     done = true;
     return MMD_OK;
 }
@@ -225,13 +255,26 @@ int launch_gemm(const GemmParams& p, int bn, cudaStream_t st) {
     for (int s = 0; s < p.n_src; ++s) num_kb += p.src_chunks[s];
     num_kb *= p.n_taps;
     const int oc = pick_oc(bn, num_kb);
-    if (bn == 256 && oc == 64) MMD_CUDA_OK(launch_kernel(conv_gemm_kernel<256, 64>, grid, GEMM_THREADS, GemmSmem<256, 64>::TOTAL, st, p));
-    else if (bn == 256) MMD_CUDA_OK(launch_kernel(conv_gemm_kernel<256, 128>, grid, GEMM_THREADS, GemmSmem<256, 128>::TOTAL, st, p));
-    else if (bn == 128 && oc == 64) MMD_CUDA_OK(launch_kernel(conv_gemm_kernel<128, 64>, grid, GEMM_THREADS, GemmSmem<128, 64>::TOTAL, st, p));
-    else if (bn == 128) MMD_CUDA_OK(launch_kernel(conv_gemm_kernel<128, 128>, grid, GEMM_THREADS, GemmSmem<128, 128>::TOTAL, st, p));
-    else if (bn == 64) MMD_CUDA_OK(launch_kernel(conv_gemm_kernel<64, 64>, grid, GEMM_THREADS, GemmSmem<64, 64>::TOTAL, st, p));
-    else if (bn == 16) MMD_CUDA_OK(launch_kernel(conv_gemm_kernel<16, 64>, grid, GEMM_THREADS, GemmSmem<16, 64>::TOTAL, st, p));
+#define MMD_GEMM_CASE(BN_, OC_, XF_)                                                                                         \
+    MMD_CUDA_OK(launch_kernel(conv_gemm_kernel<BN_, OC_, XF_>, grid, (XF_) ? GEMM_THREADS_XF : GEMM_THREADS,                  \
+                              GemmSmem<BN_, OC_, XF_>::TOTAL, st, p))
+    if (p.xf_sums != nullptr) {   // fused GroupNorm apply on the A operand: the variant with the four transform warps
+        if (bn == 256 && oc == 64) MMD_GEMM_CASE(256, 64, true);
+        else if (bn == 256) MMD_GEMM_CASE(256, 128, true);
+        else if (bn == 128 && oc == 64) MMD_GEMM_CASE(128, 64, true);
+        else if (bn == 128) MMD_GEMM_CASE(128, 128, true);
+        else if (bn == 64) MMD_GEMM_CASE(64, 64, true);
+        else return fail(MMD_EINVAL, "fused GroupNorm apply: unsupported BN %d", bn);
+        return MMD_OK;
+    }
+    if (bn == 256 && oc == 64) MMD_GEMM_CASE(256, 64, false);
+    else if (bn == 256) MMD_GEMM_CASE(256, 128, false);
+    else if (bn == 128 && oc == 64) MMD_GEMM_CASE(128, 64, false);
+    else if (bn == 128) MMD_GEMM_CASE(128, 128, false);
+    else if (bn == 64) MMD_GEMM_CASE(64, 64, false);
+    else if (bn == 16) MMD_GEMM_CASE(16, 64, false);
     else return fail(MMD_EINVAL, "unsupported BN %d", bn);
+#undef MMD_GEMM_CASE
     return MMD_OK;
 }
 
@@ -311,12 +354,50 @@ int launch_gn_stats(const GnSrc& s, int ns, int rows, double* sums, cudaStream_t
 
 int launch_gn_apply(const GnSrc& s, int ns, int rows, const double* sums, const float* gamma, const float* beta,
                     const float* film, int film_ld, int ns_per_batch, int silu, act_t* y, cudaStream_t st, int nsub,
-                    long long stat_rows) {
+                    long long stat_rows, const DropState* drop, uint32_t drop_site) {
     const int C = s.c1 + s.c2;
     const int rpb = gn_rows_per_block(ns, rows, C);
     dim3 grid((rows + rpb - 1) / rpb, ns);
     MMD_CUDA_OK(launch_kernel(gn_apply_kernel, grid, 256, (2 * C + 64) * sizeof(float), st, s, rows, rpb, sums, gamma, beta, film,
-                              film_ld, ns_per_batch, silu, y, nsub, stat_rows > 0 ? stat_rows : static_cast<long long>(rows)));
+                              film_ld, ns_per_batch, silu, y, nsub, stat_rows > 0 ? stat_rows : static_cast<long long>(rows),
+                              drop, drop_site));
+    return MMD_OK;
+}
+
+__global__ void set_dropout_kernel(DropState* dev, DropState v) { *dev = v; }
+
+int launch_set_dropout(DropState* dev, float p, unsigned long long seed, cudaStream_t st) {
+    if (!(p >= 0.f) || p >= 1.f) return fail(MMD_EINVAL, "dropout probability %f out of [0, 1)", p);
+    DropState v{};
+    v.seed_lo = static_cast<uint32_t>(seed);
+    v.seed_hi = static_cast<uint32_t>(seed >> 32);
+    // 16-bit uniforms: P(drop) = thresh16 / 65536 (p = 0.1 -> 6554 / 65536 = 0.100006); the survivors are scaled by the
+    // reciprocal of the probability actually used, so E[y] is exact
+    v.thresh16 = static_cast<uint32_t>(p * 65536.0f + 0.5f);
+    const float keep_p = 1.0f - static_cast<float>(v.thresh16) / 65536.0f;
+    const float scale = v.thresh16 ? 1.0f / keep_p : 1.0f;
+    memcpy(&v.scale_bits, &scale, sizeof(float));
+    set_dropout_kernel<<<1, 1, 0, st>>>(dev, v);
+    MMD_CUDA_OK(cudaGetLastError());
+    return MMD_OK;
+}
+
+__global__ void dropout_mask_kernel(const DropState* __restrict__ dev, uint32_t site, long long n8, unsigned char* __restrict__ keep) {
+    const DropState ds = *dev;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const uint32_t k = ds.thresh16 ? dropout_keep8(ds, site, static_cast<unsigned long long>(i)) : 0xFFu;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) keep[i * 8 + j] = (k >> j) & 1u;
+    }
+}
+
+int launch_dropout_mask(const DropState* dev, uint32_t site, long long elems, unsigned char* keep, cudaStream_t st) {
+    if (elems % 8 != 0) return fail(MMD_EINVAL, "dropout mask: element count must be a multiple of 8");
+    const long long n8 = elems / 8;
+    const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>((n8 + 255) / 256, 8LL * num_sms())));
+    dropout_mask_kernel<<<grid, 256, 0, st>>>(dev, site, n8, keep);
+    MMD_CUDA_OK(cudaGetLastError());
     return MMD_OK;
 }
 
@@ -419,7 +500,11 @@ int mmd_op_resample(const void* x, void* y, int mode, int n, int h, int w, int c
                            static_cast<cudaStream_t>(stream));
 }
 
-int mmd_op_conv(const MmdConvDesc* d, void* stream) {
+struct OpConvGn {
+    const float* gamma; const float* beta; const float* film; int film_ld; int ns; int ns_per_batch; int silu;
+};
+
+static int op_conv_impl(const MmdConvDesc* d, const OpConvGn* gn, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (!d) return fail(MMD_EINVAL, "null conv desc");
     GemmProblem pr;
@@ -477,12 +562,48 @@ int mmd_op_conv(const MmdConvDesc* d, void* stream) {
     }
     pr.w = wp;
     pr.bias = bp;
+    double* xsums = nullptr;
+    if (r == MMD_OK && gn) {
+        // GroupNorm32 of source 0 folded into the GEMM's A path: statistics by the standalone kernel, apply in shared memory
+        const long long tokens = pr.g.tokens();
+        const int C = d->src_channels[0];
+        long long rows = 0;
+        if (d->n_taps != 1 || gn->ns <= 0) r = fail(MMD_EINVAL, "conv_gn: pointwise convolutions only");
+        else if (d->rank == 2 && tokens % gn->ns == 0 && ((tokens / gn->ns) == 64 || (tokens / gn->ns) % 128 == 0)) {
+            rows = tokens / gn->ns;
+            pr.xf_rows = static_cast<int>(rows < 128 ? rows : 128); pr.xf_mul[0] = 1; pr.xf_div = static_cast<int>(rows);
+        } else if (d->rank == 3 && gn->ns == d->dims[1] && pr.g.box[0] == GEMM_BM) {
+            rows = d->dims[0];
+            pr.xf_rows = 128; pr.xf_mul[1] = 1; pr.xf_div = 1;
+        } else r = fail(MMD_EINVAL, "conv_gn: unsupported domain geometry (rank %d, ns %d)", d->rank, gn->ns);
+        if (r == MMD_OK) {
+            cudaError_t e = cudaMallocAsync(&xsums, sizeof(double) * 64 * gn->ns, st);
+            if (e != cudaSuccess) r = fail(MMD_ECUDA, "conv_gn: %s", cudaGetErrorString(e));
+        }
+        if (r == MMD_OK) {
+            GnSrc gs{static_cast<const act_t*>(d->src[0]), C, C, nullptr, 0, 0};
+            r = launch_gn_stats(gs, gn->ns, static_cast<int>(rows), xsums, st);
+            pr.xf_sums = xsums; pr.xf_gamma = gn->gamma; pr.xf_beta = gn->beta; pr.xf_film = gn->film;
+            pr.xf_film_ld = gn->film_ld; pr.xf_dom_per_batch = gn->ns_per_batch > 0 ? gn->ns_per_batch : 1;
+            pr.xf_nsub = 1; pr.xf_silu = gn->silu; pr.xf_stat_rows = rows;
+        }
+    }
     GemmParams gp;
     if (r == MMD_OK) r = build_gemm(pr, &gp);
     if (r == MMD_OK) r = launch_gemm(gp, pr.bn, st);
     cudaFreeAsync(wp, st);
     cudaFreeAsync(bp, st);
+    if (xsums) cudaFreeAsync(xsums, st);
     return r;
+}
+
+int mmd_op_conv(const MmdConvDesc* d, void* stream) { return op_conv_impl(d, nullptr, stream); }
+
+int mmd_op_conv_gn(const MmdConvDesc* d, const float* gamma, const float* beta, const float* film, int film_ld, int ns,
+                   int ns_per_batch, int silu, void* stream) {
+    if (!gamma || !beta) return fail(MMD_EINVAL, "conv_gn: gamma / beta required");
+    OpConvGn gn{gamma, beta, film, film_ld, ns, ns_per_batch, silu};
+    return op_conv_impl(d, &gn, stream);
 }
 
 int mmd_op_attention(const MmdAttnDesc* d, void* stream) {

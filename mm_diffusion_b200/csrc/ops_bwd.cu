@@ -239,6 +239,8 @@ int launch_gn_bwd(const GnBwdProblem& pr, cudaStream_t st) {
     a.do_silu = pr.silu;
     a.dy = pr.dy;
     a.T = pr.T;
+    a.drop = pr.drop;
+    a.drop_site = pr.drop_site;
     dim3 grid((pr.rows + a.rows_per_block - 1) / a.rows_per_block, pr.ns);
     const size_t sm_a = (6 * C + 64) * sizeof(float), sm_b = (5 * C + 128) * sizeof(float);
     gn_bwd_reduce_kernel<<<grid, 256, sm_a, st>>>(a);

@@ -18,7 +18,7 @@ from ._lib import MmdAttnDesc, MmdConvDesc, check, current_stream_ptr, ptr
 
 
 def _conv(srcs, weight, bias, n, rank, dims, taps, out=None, out_f32=None, ostride=None, ostride_c=0, gn_sums=None,
-          gn_rows=0):
+          gn_rows=0, gn_in=None):
     lib = _lib.load()
     d = MmdConvDesc()
     d.rank = rank
@@ -51,7 +51,15 @@ def _conv(srcs, weight, bias, n, rank, dims, taps, out=None, out_f32=None, ostri
         assert gn_sums.dtype == torch.float64 and gn_sums.is_contiguous() and gn_sums.is_cuda
         d.gn_sums = gn_sums.data_ptr()
         d.gn_rows = gn_rows
-    check(lib.mmd_op_conv(C.byref(d), current_stream_ptr()))
+    if gn_in is not None:   # GroupNorm32 (+FiLM, +SiLU) of source 0 applied on the GEMM's A operand
+        g = gn_in["gamma"].detach().float().contiguous()
+        b2 = gn_in["beta"].detach().float().contiguous()
+        f = None if gn_in.get("film") is None else gn_in["film"].detach().float().contiguous()
+        check(lib.mmd_op_conv_gn(C.byref(d), g.data_ptr(), b2.data_ptr(), ptr(f), 0 if f is None else f.shape[-1],
+                                 int(gn_in["ns"]), int(gn_in.get("ns_per_batch", 1)), int(bool(gn_in.get("silu", False))),
+                                 current_stream_ptr()))
+    else:
+        check(lib.mmd_op_conv(C.byref(d), current_stream_ptr()))
     return out if out is not None else out_f32
 
 
@@ -66,6 +74,21 @@ def conv_pointwise(srcs, weight, bias, gn_sums=None, gn_rows=0):
     w = weight.reshape(n, -1, 1)
     return _conv([s.reshape(m, s.shape[-1]) for s in srcs], w, bias, n, 2, [m], [(0, 0, 0)], out=out, gn_sums=gn_sums,
                  gn_rows=gn_rows)
+
+
+def conv_pointwise_gn(srcs, weight, bias, gamma, beta, ns, film=None, ns_per_batch=1, silu=False, gn_sums=None, gn_rows=0):
+    """conv_pointwise whose first source is GroupNorm32-normalised (+FiLM, +SiLU) on the fly: the ResBlock out_layers /
+    attention-norm -> 1x1 conv pairs (multimodal_unet.py:459-470, :284, :664) without the normalised tensor in HBM.
+    srcs[0]: [M, C] (ns domains of M / ns consecutive rows) or [B, L, C] (one domain per sample, ns == B)."""
+    n = weight.shape[0]
+    out = torch.empty(srcs[0].shape[:-1] + (n,), dtype=torch.float16, device=srcs[0].device)
+    w = weight.reshape(n, -1, 1)
+    gn_in = {"gamma": gamma, "beta": beta, "ns": ns, "film": film, "ns_per_batch": ns_per_batch, "silu": silu}
+    if srcs[0].dim() == 3:
+        B, L, _ = srcs[0].shape
+        return _conv(list(srcs), w, bias, n, 3, [L, B], [(0, 0, 0)], out=out, gn_sums=gn_sums, gn_rows=gn_rows, gn_in=gn_in)
+    m = srcs[0].shape[0]
+    return _conv(list(srcs), w, bias, n, 2, [m], [(0, 0, 0)], out=out, gn_sums=gn_sums, gn_rows=gn_rows, gn_in=gn_in)
 
 
 def conv_spatial(x, weight, bias):

@@ -44,27 +44,48 @@ def gather_samples(sample: Dict[str, torch.Tensor], group=None) -> Dict[str, tor
     return {"video": gv, "audio": ga}
 
 
-def allreduce_flat_gradients(model, group=None, average: bool = True) -> bool:
-    """Data-parallel gradient exchange of a training step in ONE collective: the sm_100a backward hands every parameter
-    gradient out as a view of a single flat fp32 buffer (`model.flat_grad`, 0.53 GB for the production network), so the
-    all-reduce over NCCL / NVLink is one call on that buffer instead of DDP's per-bucket calls
-    (reference: DistributedDataParallel in TrainLoop, mm_diffusion/multimodal_train_util.py:120-136).
-    Returns True if the parameters' `.grad` alias the reduced buffer (the normal case: autograd adopts the views), and
-    copies the reduced values into `.grad` otherwise."""
+def _grads_alias(model) -> bool:
+    """True when every existing .grad is the matching view of model.flat_grad (flat-gradient mode of the backward)."""
     flat = getattr(model, "flat_grad", None)
-    if flat is None:
-        raise RuntimeError("allreduce_flat_gradients: no backward has run on this model yet")
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+    views = getattr(model, "flat_grad_views", None)
+    if flat is None or not views:
+        return False
+    for p, view in zip(model.parameters(), views):
+        if p.grad is None:
+            continue
+        if view is None or p.grad.data_ptr() != view.data_ptr() or p.grad.shape != view.shape:
+            return False
+    return True
+
+
+def allreduce_flat_gradients(model, group=None, average: bool = True) -> bool:
+    """Data-parallel gradient exchange of a training step (reference: DistributedDataParallel in TrainLoop,
+    mm_diffusion/multimodal_train_util.py:120-136).
+
+    Flat-gradient mode (`model.use_flat_gradients(True)`): every `.grad` is a view of the model's persistent fp32
+    buffer `model.flat_grad` (0.53 GB for the production network; micro-batches accumulate into it), so the exchange is
+    ONE all-reduce over NCCL / NVLink on that buffer.  Returns True.
+
+    Otherwise (gradients delivered through autograd: each `.grad` is its own tensor and may hold an accumulation over
+    micro-batches) the `.grad` tensors themselves are flattened, reduced in one collective and written back — the
+    accumulated values are what gets averaged, nothing is overwritten from a scratch buffer.  Returns False."""
+    active = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    world = dist.get_world_size(group) if active else 1
+    if _grads_alias(model):
+        if active:
+            dist.all_reduce(model.flat_grad, op=dist.ReduceOp.SUM, group=group)
+            if average:
+                model.flat_grad.div_(world)
+        return True
+    grads = [p.grad for p in model.parameters() if p.grad is not None]
+    if not grads:
+        raise RuntimeError("allreduce_flat_gradients: no parameter has a gradient (run backward first)")
+    if active:
+        from torch._utils import _flatten_dense_tensors, _unflatten_dense_tensors
+        flat = _flatten_dense_tensors(grads)
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
         if average:
-            flat.div_(dist.get_world_size(group))
-    lo = flat.data_ptr()
-    hi = lo + flat.numel() * flat.element_size()
-    aliased = True
-    for p, view in zip(model.parameters(), model.flat_grad_views):
-        if p.grad is None or view is None:
-            continue
-        if not (lo <= p.grad.data_ptr() < hi):
-            aliased = False
-            p.grad.copy_(view)
-    return aliased
+            flat.div_(world)
+        for g, r in zip(grads, _unflatten_dense_tensors(flat, grads)):
+            g.copy_(r)
+    return False

@@ -78,6 +78,8 @@ class _UNetFunction(torch.autograd.Function):
         vo, ao = model._run(video, audio, timesteps, shifts, train=True)
         ctx.model = model
         ctx.batch = video.shape[0]
+        # the library keeps ONE tape per batch size: remember which forward this backward belongs to
+        ctx.generation = int(_lib.load().mmd_model_train_generation(model._handle, ctx.batch))
         ctx.in_shapes = (tuple(video.shape), tuple(audio.shape))
         ctx.need_inputs = (video.requires_grad, audio.requires_grad)
         ctx.param_meta = [(p.requires_grad, tuple(p.shape)) for p in params]
@@ -90,20 +92,42 @@ class _UNetFunction(torch.autograd.Function):
         lib = _lib.load()
         dev = model._handle_device
         B = ctx.batch
+        if int(lib.mmd_model_train_generation(model._handle, B)) != ctx.generation:
+            raise MmdError("backward of a stale forward: another differentiable forward at this batch size ran after the "
+                           "one being differentiated and overwrote its kept activations (run forward -> backward "
+                           "pairs one at a time, or use torch.no_grad() for evaluation forwards)")
         if model.checkpoint_rng_compat:
             # The reference re-runs every (always checkpointed) CrossAttentionBlock in backward and draws a fresh
-            # random.randint there (multimodal_unet.py:619-622 under nn.py:233-279).  We differentiate the function
-            # that was evaluated, but consume the same number of draws so the global `random` stream stays aligned.
-            model.draw_shifts()
+            # random.randint there (multimodal_unet.py:619-622 under nn.py:233-279), last block first (autograd visits
+            # the checkpoints in reverse).  We differentiate the function that was evaluated, but consume the same
+            # draws with the same bounds in the same order, so the global `random` stream stays aligned.
+            model.draw_shifts(reverse=True)
         with torch.cuda.device(dev):
             vshape = (B, model._cfg.video_f, model.video_out_channels, model._cfg.video_h, model._cfg.video_w)
             ashape = (B, model.audio_out_channels, model._cfg.audio_l)
             d_vo = torch.zeros(vshape, dtype=torch.float32, device=dev) if d_vo is None else d_vo.to(torch.float32).contiguous()
             d_ao = torch.zeros(ashape, dtype=torch.float32, device=dev) if d_ao is None else d_ao.to(torch.float32).contiguous()
-            flat = torch.empty(int(lib.mmd_model_param_floats(model._handle)), dtype=torch.float32, device=dev)
+            n_flat = int(lib.mmd_model_param_floats(model._handle))
             d_vi = torch.empty(ctx.in_shapes[0], dtype=torch.float32, device=dev) if ctx.need_inputs[0] else None
             d_ai = torch.empty(ctx.in_shapes[1], dtype=torch.float32, device=dev) if ctx.need_inputs[1] else None
-            check(lib.mmd_model_backward(model._handle, B, d_vo.data_ptr(), d_ao.data_ptr(), flat.data_ptr(),
+            wants_params = any(needs for needs, _ in ctx.param_meta)
+            if model._flat_mode and wants_params:
+                # flat-gradient mode: ONE persistent fp32 buffer owns every parameter gradient; .grad are views of it
+                # (set here, not by autograd's AccumulateGrad, which would clone them).  A later backward without
+                # zero_grad accumulates into the same buffer (micro-batches), like autograd does.
+                buf, views = model._grad_buffer(dev, n_flat)
+                fresh = model._plist[0].grad is None
+                dst = buf if fresh else torch.empty(n_flat, dtype=torch.float32, device=dev)
+                check(lib.mmd_model_backward(model._handle, B, d_vo.data_ptr(), d_ao.data_ptr(), dst.data_ptr(),
+                                             _lib.ptr(d_vi), _lib.ptr(d_ai), _lib.current_stream_ptr()))
+                if fresh:
+                    for p, v, (needs, _) in zip(model._plist, views, ctx.param_meta):
+                        p.grad = v if needs else None
+                else:
+                    buf.add_(dst)
+                return (None, None, d_vi, d_ai, None, *([None] * len(ctx.param_meta)))
+            flat = torch.empty(n_flat, dtype=torch.float32, device=dev) if wants_params else None
+            check(lib.mmd_model_backward(model._handle, B, d_vo.data_ptr(), d_ao.data_ptr(), _lib.ptr(flat),
                                          _lib.ptr(d_vi), _lib.ptr(d_ai), _lib.current_stream_ptr()))
         grads = []
         for (needs, shape), off in zip(ctx.param_meta, model._param_offsets()):
@@ -111,7 +135,8 @@ class _UNetFunction(torch.autograd.Function):
             for d in shape:
                 n *= d
             grads.append(flat[off:off + n].view(shape) if needs else None)
-        # kept for parallel.allreduce_flat_gradients: one collective over the flat buffer exchanges every gradient
+        # autograd mode: the gradients reach the nn.Parameters through AccumulateGrad (DDP reducer hooks and the
+        # reference's MixedPrecisionTrainer see them as usual); `flat_grad` is this backward's buffer only
         model.flat_grad, model.flat_grad_views = flat, grads
         return (None, None, d_vi, d_ai, None, *grads)
 
@@ -162,7 +187,14 @@ class MultimodalUNet(nn.Module):
         self._handle = None          # MmdModel* (created lazily on the parameters' CUDA device)
         self._handle_device = None
         self._synced: Dict[str, tuple] = {}
+        self._synced_vsum = -1
+        self._plist = None   # cached parameter list (the per-forward staleness check walks it)
         self._needs_sync = True
+        self._drop_calls = 0
+        self._flat_mode = False
+        self._flat_views_ok = False
+        self.flat_grad = None          # fp32 buffer holding every parameter gradient (see use_flat_gradients)
+        self.flat_grad_views: List = []
         self._param_names: List[str] = []
         self._shift_bounds: List[int] = []
         self._build_parameters()
@@ -234,6 +266,8 @@ class MultimodalUNet(nn.Module):
     def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
         out = super().load_state_dict(state_dict, strict=strict, assign=assign)
         self._needs_sync = True
+        self._plist = None
+        self._flat_views_ok = False
         return out
 
     def load_state_dict_(self, state_dict, is_strict=False):
@@ -247,6 +281,7 @@ class MultimodalUNet(nn.Module):
     def _apply(self, fn, recurse=True):
         out = super()._apply(fn, recurse)
         self._needs_sync = True
+        self._plist = None
         return out
 
     def train(self, mode: bool = True):
@@ -293,10 +328,69 @@ class MultimodalUNet(nn.Module):
     def shift_bounds(self) -> List[int]:
         return list(self._shift_bounds)
 
-    def draw_shifts(self) -> List[int]:
-        """One random.randint(0, F - window) per shifting cross-attention block, in execution order, from
-        Python's global `random` — exactly the draws CrossAttentionBlock.attention_index makes (:619-622)."""
-        return [random.randint(0, b) if b >= 0 else 0 for b in self._shift_bounds]
+    def draw_shifts(self, reverse: bool = False) -> List[int]:
+        """One random.randint(0, F - window) per shifting cross-attention block, in execution order (reverse=True: last
+        block first, the order of the reference's checkpoint recomputation in backward), from Python's global
+        `random` — exactly the draws CrossAttentionBlock.attention_index makes (:619-622)."""
+        bounds = list(reversed(self._shift_bounds)) if reverse else self._shift_bounds
+        out = [random.randint(0, b) if b >= 0 else 0 for b in bounds]
+        return list(reversed(out)) if reverse else out
+
+    def use_flat_gradients(self, enable: bool = True):
+        """Gradient hand-off of the training backward.
+        False (default): parameter gradients flow through autograd into each nn.Parameter (DDP's reducer hooks, the
+        reference's TrainLoop / MixedPrecisionTrainer work unchanged).
+        True: the backward writes into ONE persistent flat fp32 buffer (`flat_grad`) and sets every `.grad` to a view of
+        it — no per-parameter kernels, micro-batch accumulation in one add, and `parallel.allreduce_flat_gradients`
+        exchanges all gradients in a single collective.  Not compatible with DistributedDataParallel (no autograd
+        hooks fire for the parameters)."""
+        self._flat_mode = bool(enable)
+        return self
+
+    def _grad_buffer(self, device, n_flat):
+        if self._plist is None:
+            self._plist = list(self.parameters())
+        if self.flat_grad is None or self.flat_grad.numel() != n_flat or self.flat_grad.device != device or \
+                not self._flat_views_ok:
+            self.flat_grad = torch.zeros(n_flat, dtype=torch.float32, device=device)
+            views = []
+            for p, off in zip(self._plist, self._param_offsets()):
+                views.append(self.flat_grad[off:off + p.numel()].view(p.shape))
+            self.flat_grad_views = views
+            self._flat_views_ok = True
+        return self.flat_grad, self.flat_grad_views
+
+    def _next_dropout_seed(self) -> int:
+        """64-bit Philox seed of one training forward: a function of torch's CUDA seed (torch.manual_seed makes runs
+        repeatable), the rank and a per-model call counter — no RNG state is consumed and nothing syncs."""
+        self._drop_calls += 1
+        rank = torch.distributed.get_rank() if (torch.distributed.is_available() and torch.distributed.is_initialized()) else 0
+        x = (torch.cuda.initial_seed() + 0x9E3779B97F4A7C15 * (self._drop_calls + (rank << 40))) & 0xFFFFFFFFFFFFFFFF
+        x ^= x >> 31
+        return (x * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+
+    def dropout_masks(self, batch: int):
+        """Keep masks of the last training forward at this batch size, one (video [B,F,C,H,W], audio [B,C,L]) bool pair
+        per ResBlock in execution order (test hook: the oracle applies the same masks)."""
+        lib = _lib.load()
+        n = lib.mmd_model_num_dropout_sites(self._handle, batch)
+        out, pair = [], {}
+        rows, ch, mod = C.c_int64(), C.c_int(), C.c_int()
+        with torch.cuda.device(self._handle_device):
+            for i in range(n):
+                check(lib.mmd_model_dropout_site(self._handle, batch, i, C.byref(rows), C.byref(ch), C.byref(mod)))
+                keep = torch.empty((rows.value, ch.value), dtype=torch.uint8, device=self._handle_device)
+                check(lib.mmd_model_dropout_mask(self._handle, batch, i, keep.data_ptr(), _lib.current_stream_ptr()))
+                if mod.value == 0:
+                    hw = rows.value // (batch * self._cfg.video_f)
+                    h = int(round((hw * self._cfg.video_h / self._cfg.video_w) ** 0.5))
+                    pair["video"] = keep.view(batch, self._cfg.video_f, h, hw // h, ch.value).permute(0, 1, 4, 2, 3).bool()
+                else:
+                    pair["audio"] = keep.view(batch, rows.value // batch, ch.value).permute(0, 2, 1).bool()
+                if len(pair) == 2:
+                    out.append((pair["video"], pair["audio"]))
+                    pair = {}
+        return out
 
     def num_launches(self, batch: int) -> int:
         """Kernel launches of one forward at this batch size (0 until the plan has been built by a forward)."""
@@ -357,8 +451,17 @@ class MultimodalUNet(nn.Module):
         B = video.shape[0]
         with torch.cuda.device(device):
             self._ensure_handle(device)
-            if self._needs_sync or self.training or train:
+            # in-place updates that bypass load_state_dict / _apply / train() (an EMA swap through p.copy_(ema), an
+            # optimizer step) bump the tensors' version counters: one cheap sum decides whether to look closer
+            if self._plist is None:
+                self._plist = list(self.parameters())
+            vsum = sum(p._version for p in self._plist) + sum(p.data_ptr() for p in self._plist[:4])
+            if self._needs_sync or self.training or train or vsum != self._synced_vsum:
                 self._sync_parameters()
+                self._synced_vsum = vsum
+            if train:
+                p_drop = float(self.dropout) if (self.training and self.dropout) else 0.0
+                check(_lib.load().mmd_model_set_dropout(self._handle, p_drop, self._next_dropout_seed() if p_drop > 0 else 0))
             v = video.detach().to(torch.float32).contiguous()
             a = audio.detach().to(torch.float32).contiguous()
             t = timesteps.detach().to(device=device, dtype=torch.float32).contiguous()
@@ -395,8 +498,6 @@ class MultimodalUNet(nn.Module):
         differentiable = torch.is_grad_enabled() and (video.requires_grad or audio.requires_grad or
                                                       any(p.requires_grad for p in params))
         if differentiable:
-            if self.dropout and self.training:
-                raise NotImplementedError("dropout > 0 is not implemented on the sm_100a training path")
             vo, ao = _UNetFunction.apply(self, list(shifts), video, audio, timesteps, *params)
         else:
             vo, ao = self._run(video, audio, timesteps, shifts, train=False)

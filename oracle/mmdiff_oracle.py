@@ -221,9 +221,10 @@ def single_modal_attention(x: torch.Tensor, sd, prefix: str, heads: int) -> torc
     return x + h
 
 
-def res_block(v, a, emb, sd, s: ResSpec, heads: int):
-    """ResBlock._forward (multimodal_unet.py:434-495), use_scale_shift_norm=True,
-    dropout inactive (eval).  v [B,F,C,H,W], a [B,C,L], emb [B,E]."""
+def res_block(v, a, emb, sd, s: ResSpec, heads: int, drop=None):
+    """ResBlock._forward (multimodal_unet.py:434-495), use_scale_shift_norm=True.
+    v [B,F,C,H,W], a [B,C,L], emb [B,E].  drop = None (eval: Dropout is the identity) or (video keep mask, audio keep
+    mask, scale): nn.Dropout between the SiLU and the out conv (:376,384) with the masks supplied by the caller."""
     p = s.prefix
     B, Fr, C, H, W = v.shape
     vh = video_conv_2d1d(F.silu(group_norm32(v, sd, p + ".video_in_layers.0", 2)), sd, p + ".video_in_layers.2")
@@ -240,9 +241,15 @@ def res_block(v, a, emb, sd, s: ResSpec, heads: int):
     e = F.linear(F.silu(emb), sd[p + ".emb_layers.1.weight"], sd[p + ".emb_layers.1.bias"])
     scale, shift = e.chunk(2, dim=1)
     vh = group_norm32(vh, sd, p + ".video_out_layers.0", 2) * (1 + scale[:, None, :, None, None]) + shift[:, None, :, None, None]
-    vh = video_conv_3d(F.silu(vh), sd, p + ".video_out_layers.3")
+    vh = F.silu(vh)
+    if drop is not None:
+        vh = vh * drop[0].to(vh.dtype) * drop[2]
+    vh = video_conv_3d(vh, sd, p + ".video_out_layers.3")
     ah = group_norm32(ah, sd, p + ".audio_out_layers.0") * (1 + scale[:, :, None]) + shift[:, :, None]
-    ah = audio_conv(F.silu(ah), sd, p + ".audio_out_layers.3")
+    ah = F.silu(ah)
+    if drop is not None:
+        ah = ah * drop[1].to(ah.dtype) * drop[2]
+    ah = audio_conv(ah, sd, p + ".audio_out_layers.3")
     if s.cin != s.cout:
         v = video_conv_3d(v, sd, p + ".video_skip_connection")
         a = audio_conv(a, sd, p + ".audio_skip_connection")
@@ -295,12 +302,15 @@ def cross_attention(v, a, sd, s: CrossSpec, shift: int):
     return v + vh, a + ah
 
 
-def unet_forward(sd: Dict[str, torch.Tensor], cfg: UNetConfig, video, audio, t, shifts: Sequence[int]):
+def unet_forward(sd: Dict[str, torch.Tensor], cfg: UNetConfig, video, audio, t, shifts: Sequence[int], dropout=None):
     """MultimodalUNet.forward (multimodal_unet.py:1058-1101).  `shifts`: one window shift per
     CrossAttentionBlock in execution order (0 where the block does not shift), i.e. the values
-    random.randint(0, F - window) returns inside attention_index (:619-622)."""
+    random.randint(0, F - window) returns inside attention_index (:619-622).
+    dropout (training mode): {"scale": 1 / (1 - p), "masks": [(video keep mask, audio keep mask), ...]} with one pair
+    per ResBlock in execution order."""
     topo = build_topology(cfg)
     shifts = list(shifts)
+    masks = list(dropout["masks"]) if dropout else None
     emb = timestep_embedding(t, cfg.model_channels)
     emb = F.linear(F.silu(F.linear(emb, sd["time_embed.0.weight"], sd["time_embed.0.bias"])),
                    sd["time_embed.2.weight"], sd["time_embed.2.bias"])
@@ -313,7 +323,11 @@ def unet_forward(sd: Dict[str, torch.Tensor], cfg: UNetConfig, video, audio, t, 
                 v = video_conv_2d1d(v, sd, "input_blocks.0.0.video_conv")
                 a = audio_conv(a, sd, "input_blocks.0.0.audio_conv")
             elif isinstance(s, ResSpec):
-                v, a = res_block(v, a, emb, sd, s, cfg.num_heads)
+                drop = None
+                if masks is not None:
+                    mv, ma = masks.pop(0)
+                    drop = (mv, ma, float(dropout["scale"]))
+                v, a = res_block(v, a, emb, sd, s, cfg.num_heads, drop)
             else:
                 v, a = cross_attention(v, a, sd, s, shifts.pop(0))
         return v, a
@@ -329,7 +343,7 @@ def unet_forward(sd: Dict[str, torch.Tensor], cfg: UNetConfig, video, audio, t, 
         v, a = run(blk, v, a)
     v = video_conv_3d(F.silu(group_norm32(v, sd, "video_out.0", 2)), sd, "video_out.2")
     a = audio_conv(F.silu(group_norm32(a, sd, "audio_out.0")), sd, "audio_out.2")
-    assert not shifts
+    assert not shifts and not masks
     return v, a
 
 
@@ -405,11 +419,11 @@ class DiffusionOracle:
         return {"sample": {"video": sv, "audio": sa}, "pred_start": {"video": x0v, "audio": x0a},
                 "pred_noise": {"video": ev, "audio": ea}}
 
-    def training_losses(self, sd, cfg, x_start, t, noise, shifts):
+    def training_losses(self, sd, cfg, x_start, t, noise, shifts, dropout=None):
         """multimodal_training_losses (:1114-1203), EPSILON target, MSE: per-sample losses."""
         vt = self.q_sample(x_start["video"], t, noise["video"])
         at = self.q_sample(x_start["audio"], t, noise["audio"])
-        ev, ea = unet_forward(sd, cfg, vt, at, t, shifts)
+        ev, ea = unet_forward(sd, cfg, vt, at, t, shifts, dropout)
         mv = ((noise["video"] - ev) ** 2).flatten(1).mean(1)
         ma = ((noise["audio"] - ea) ** 2).flatten(1).mean(1)
         return {"loss": mv + ma, "mse_video": mv, "mse_audio": ma}

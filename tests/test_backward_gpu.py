@@ -224,3 +224,81 @@ def test_parameter_update_reaches_every_packed_layout(setup):
     finally:
         model.eval()
         model.load_state_dict(sd, strict=True)   # the module-scoped fixture is shared
+
+
+def test_training_with_dropout_matches_oracle_with_exported_masks(setup):
+    """nn.Dropout(p=0.1) of the ResBlock out_layers (multimodal_unet.py:370-386; the shipped training flags,
+    ssh_scripts/multimodal_train.sh:4): the keep-mask statistic is p +- 1 %, masks differ between sites and forwards,
+    and with the masks of the forward exported to the oracle the loss and every parameter gradient agree with
+    torch.autograd (same tolerances as the dropout-free test)."""
+    fx, cfg, sd, model, diffusion = setup
+    B = 2
+    x0, noise = _data(cfg, B, 555)
+    t = torch.tensor([600, 120])
+    shifts = draw_shifts(cfg, random.Random(11))
+    model.train()
+    model.dropout = 0.1
+    try:
+        model.zero_grad(set_to_none=True)
+        random.seed(11)
+        torch.manual_seed(2024)
+        terms = diffusion.multimodal_training_losses(model, {k: v.cuda() for k, v in x0.items()}, t.cuda(),
+                                                     noise={k: v.cuda() for k, v in noise.items()})
+        loss = terms["loss"].mean()
+        masks = [(mv.cpu(), ma.cpu()) for mv, ma in model.dropout_masks(B)]
+        loss.backward()
+        torch.cuda.synchronize()
+        grads = {n: p.grad.detach().float().cpu() for n, p in model.named_parameters()}
+        # a second forward draws different masks
+        random.seed(11)
+        with torch.enable_grad():
+            diffusion.multimodal_training_losses(model, {k: v.cuda() for k, v in x0.items()}, t.cuda(),
+                                                 noise={k: v.cuda() for k, v in noise.items()})
+        masks2 = [(mv.cpu(), ma.cpu()) for mv, ma in model.dropout_masks(B)]
+    finally:
+        model.dropout = 0
+        model.eval()
+    kept = sum(int(mv.sum()) + int(ma.sum()) for mv, ma in masks)
+    total = sum(mv.numel() + ma.numel() for mv, ma in masks)
+    drop_rate = 1.0 - kept / total
+    per_site = [1.0 - float(mv.float().mean()) for mv, _ in masks] + [1.0 - float(ma.float().mean()) for _, ma in masks]
+    print(f"[dropout] {len(masks)} ResBlocks, {total} elements, drop rate {drop_rate:.5f}, per-site range "
+          f"{min(per_site):.4f}..{max(per_site):.4f}")
+    assert abs(drop_rate - 0.1) < 0.001                     # p +- 1 %
+    assert all(abs(r - 0.1) < 0.02 for r in per_site)       # every site, small ones included
+    assert any((a[0] != b[0]).any() for a, b in zip(masks, masks2)), "masks did not change between forwards"
+    same_shape = [(i, j) for i in range(len(masks)) for j in range(i + 1, len(masks)) if masks[i][0].shape == masks[j][0].shape]
+    assert same_shape and all((masks[i][0] != masks[j][0]).any() for i, j in same_shape), "two sites share a mask"
+
+    thresh = int(0.1 * 65536.0 + 0.5)
+    drop = {"scale": 1.0 / (1.0 - thresh / 65536.0), "masks": masks}
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ref_terms = DiffusionOracle(1000).training_losses(sdg, cfg, x0, t, noise, shifts, dropout=drop)
+    ref_terms["loss"].mean().backward()
+    lerr = abs(loss.item() - ref_terms["loss"].mean().item()) / abs(ref_terms["loss"].mean().item())
+    num = sum((grads[n] - sdg[n].grad).double().pow(2).sum().item() for n in grads)
+    den = sum(sdg[n].grad.double().pow(2).sum().item() for n in grads)
+    glob = (num / den) ** 0.5
+    print(f"[dropout] loss rel-err {lerr:.2e}; global gradient rel-L2 vs oracle autograd with the same masks {glob:.3e}")
+    assert lerr < 1e-2
+    assert glob < 3e-2, glob
+
+
+def test_stale_forward_is_rejected(setup):
+    """One tape per batch size: a backward whose forward was overwritten by a later differentiable forward must fail
+    loudly instead of differentiating the wrong activations."""
+    from mm_diffusion_b200._lib import MmdError
+    fx, cfg, sd, model, diffusion = setup
+    B = 2
+    x0, noise = _data(cfg, B, 99)
+    t = torch.tensor([10, 900]).cuda()
+    model.train()
+    try:
+        a = diffusion.multimodal_training_losses(model, {k: v.cuda() for k, v in x0.items()}, t)["loss"].mean()
+        b = diffusion.multimodal_training_losses(model, {k: v.cuda() for k, v in x0.items()}, t)["loss"].mean()
+        with pytest.raises((MmdError, RuntimeError), match="stale forward"):
+            a.backward()
+        b.backward()   # the latest forward is still differentiable
+    finally:
+        model.zero_grad(set_to_none=True)
+        model.eval()

@@ -42,6 +42,62 @@ def test_conv_pointwise(ops, m, cins, cout):
     assert rel_l2(y, ref) < 2e-3
 
 
+def _ref_gn(x, gamma, beta, ns, film=None, ns_per_batch=1, silu=False):
+    """GroupNorm32 (+FiLM, +SiLU) of nn.py:16-33 / multimodal_unet.py:459-470 on [ns * rows, C] fp32."""
+    c = x.shape[-1]
+    xd = x.float().reshape(ns, -1, c).permute(0, 2, 1)
+    y = F.group_norm(xd, 32, gamma, beta, eps=1e-5)
+    if film is not None:
+        fb = film.float().repeat_interleave(ns_per_batch, dim=0)
+        y = y * (1 + fb[:, :c, None]) + fb[:, c:2 * c, None]
+    if silu:
+        y = F.silu(y)
+    return y.permute(0, 2, 1).reshape(x.shape)
+
+
+@pytest.mark.parametrize("m,c,cskip,cout,ns,film,silu", [
+    (4096, 128, 0, 128, 4, True, True),        # out_layers, one domain per tile, BN=128
+    (2048, 64, 64, 64, 2, True, True),         # small-config widths (BN=64), skip segment untouched
+    (65536, 256, 256, 256, 4, True, True),     # BN=256, residual / skip K-segment after the normalised one
+    (16384, 384, 0, 1152, 64, False, False),   # attention norm -> qkv, per-frame domains of 256 rows, 9 N tiles
+    (4096, 512, 0, 1536, 64, False, False),    # 64-row domains: two domains per tile
+    (40960, 128, 128, 128, 5, True, True),     # many tiles per CTA (table rebuilt when the domain changes)
+    (32768, 512, 1024, 512, 2, True, True),    # widest source, long skip segment
+])
+def test_conv_pointwise_fused_gn_apply(ops, m, c, cskip, cout, ns, film, silu):
+    """GroupNorm apply (+FiLM, +SiLU) folded into the GEMM's A path == norm then conv in fp32."""
+    x = (_rand(m, c, seed=31) * 1.5 + 0.3).half()
+    srcs = [x]
+    if cskip:
+        srcs.append(_rand(m, cskip, seed=32).half())
+    gamma = 1 + 0.2 * _rand(c, seed=33)
+    beta = 0.2 * _rand(c, seed=34)
+    fb = 0.3 * _rand(ns, 2 * c + 6, seed=35) if film else None   # film_ld > 2C like the stacked emb table
+    w = _rand(cout, c + cskip, scale=0.05, seed=36)
+    b = _rand(cout, seed=37)
+    y = ops.conv_pointwise_gn(srcs, w, b, gamma, beta, ns, film=fb, silu=silu)
+    h = _ref_gn(x, gamma, beta, ns, film=fb, silu=silu)
+    ref = torch.cat([h] + [s_.float() for s_ in srcs[1:]], dim=1) @ w.t() + b
+    assert rel_l2(y, ref) < 2e-3
+
+
+@pytest.mark.parametrize("b,l,c,cout,silu", [(2, 1600, 128, 128, True), (3, 400, 512, 1536, False), (4, 400, 256, 256, True)])
+def test_conv_audio_pointwise_fused_gn_apply(ops, b, l, c, cout, silu):
+    """audio geometry (L,B): one domain per sample, ragged last tile (L % 128 != 0), fused output statistics on top"""
+    x = (_rand(b, l, c, seed=41) + 0.5).half()
+    gamma = 1 + 0.2 * _rand(c, seed=42)
+    beta = 0.2 * _rand(c, seed=43)
+    fb = 0.3 * _rand(b, 2 * c, seed=44) if silu else None
+    w = _rand(cout, c, scale=0.05, seed=45)
+    bias = _rand(cout, seed=46)
+    sums = torch.zeros(b, 32, 2, dtype=torch.float64, device="cuda")
+    y = ops.conv_pointwise_gn([x], w, bias, gamma, beta, b, film=fb, silu=silu, gn_sums=sums, gn_rows=l)
+    h = _ref_gn(x.reshape(b * l, c), gamma, beta, b, film=fb, silu=silu)
+    ref = (h @ w.t() + bias).reshape(b, l, cout)
+    assert rel_l2(y, ref) < 2e-3
+    _check_sums(sums, y, b)
+
+
 def _ref_gn_sums(y, domains):
     """(sum, sum of squares) per (domain, group of C/32 channels) of the fp16 result the kernel stored."""
     c = y.shape[-1]

@@ -60,16 +60,18 @@ def test_shard_bounds_partition_the_batch():
 
 
 class _FlatGradModel(torch.nn.Module):
-    """Stand-in with the gradient layout the sm_100a backward produces: .grad tensors are views of one flat buffer."""
+    """Stand-in with the two gradient layouts of the sm_100a backward: flat-gradient mode (.grad are views of the
+    persistent model.flat_grad) and autograd mode (.grad are separate tensors; flat_grad is a per-backward scratch)."""
 
-    def __init__(self, rank, alias=True):
+    def __init__(self, rank, alias=True, accumulated=0.0):
         super().__init__()
         self.a = torch.nn.Parameter(torch.zeros(3, 4))
         self.b = torch.nn.Parameter(torch.zeros(5))
         self.flat_grad = torch.arange(20, dtype=torch.float32) * (rank + 1)   # 12 + pad to 15 + 5
         self.flat_grad_views = [self.flat_grad[0:12].view(3, 4), self.flat_grad[15:20]]
-        self.a.grad = self.flat_grad_views[0] if alias else self.flat_grad_views[0].clone()
-        self.b.grad = self.flat_grad_views[1] if alias else self.flat_grad_views[1].clone()
+        # `accumulated`: what earlier micro-batches already left in .grad (autograd mode only)
+        self.a.grad = self.flat_grad_views[0] if alias else self.flat_grad_views[0].clone() + accumulated
+        self.b.grad = self.flat_grad_views[1] if alias else self.flat_grad_views[1].clone() + accumulated
 
 
 def _grad_worker(rank, world, port, ret):
@@ -78,22 +80,33 @@ def _grad_worker(rank, world, port, ret):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         ok = True
-        for alias in (True, False):
-            m = _FlatGradModel(rank, alias)
+        mean = torch.arange(20, dtype=torch.float32) * (sum(range(1, world + 1)) / world)
+        for alias, acc in ((True, 0.0), (False, 0.0), (False, 10.0)):
+            m = _FlatGradModel(rank, alias, acc)
             aliased = allreduce_flat_gradients(m)
-            mean = torch.arange(20, dtype=torch.float32) * (sum(range(1, world + 1)) / world)
-            ok = ok and aliased == alias and torch.allclose(m.a.grad, mean[0:12].view(3, 4)) and torch.allclose(m.b.grad, mean[15:20])
+            # an accumulated .grad (two micro-batches) must be averaged as it is, never overwritten by the last step's buffer
+            ok = ok and aliased == alias and torch.allclose(m.a.grad, mean[0:12].view(3, 4) + acc) and \
+                torch.allclose(m.b.grad, mean[15:20] + acc)
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()
 
 
 def test_flat_gradient_allreduce_world2_gloo():
-    """The training step's only collective: one all-reduce over the flat gradient buffer averages every parameter
-    gradient on every rank (views alias the buffer; non-aliased .grad tensors are refreshed by copy)."""
+    """The training step's only collective: one all-reduce averages every parameter gradient on every rank — over the
+    persistent flat buffer when the .grad tensors alias it, over the flattened .grad tensors (accumulation included)
+    otherwise."""
     world = 2
     port = _free_port()
     with mp.Manager() as mgr:
         ret = mgr.dict()
         mp.spawn(_grad_worker, args=(world, port, ret), nprocs=world, join=True)
         assert dict(ret) == {0: True, 1: True}
+
+
+def test_flat_gradient_allreduce_single_process():
+    m = _FlatGradModel(0, alias=True)
+    assert allreduce_flat_gradients(m) is True
+    m2 = _FlatGradModel(0, alias=False, accumulated=3.0)
+    before = m2.a.grad.clone()
+    assert allreduce_flat_gradients(m2) is False and torch.equal(m2.a.grad, before)
