@@ -427,9 +427,10 @@ MMD_DEVINL float attn64_rowmax(uint32_t s_addr, int kvalid) {
     tmem_ld32(s_addr, va);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
+        if (!FULL && c * 32 >= kvalid) break;   // ragged tile: 32-column chunks past the last valid key are never touched
         uint32_t* cur = (c & 1) ? vb : va;
         tmem_ld_wait();
-        if (c < 3) tmem_ld32(s_addr + (c + 1) * 32, (c & 1) ? va : vb);
+        if (c < 3 && (FULL || (c + 1) * 32 < kvalid)) tmem_ld32(s_addr + (c + 1) * 32, (c & 1) ? va : vb);
 #pragma unroll
         for (int i = 0; i < 32; ++i)
             if (FULL || c * 32 + i < kvalid) mx = fmaxf(mx, __uint_as_float(cur[i]));
@@ -444,9 +445,11 @@ MMD_DEVINL void attn64_write_p(uint32_t s_addr, int kvalid, float scale_log2, fl
     tmem_ld32(s_addr, va);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
+        // ragged tile: the P.V / P.1 MMAs read ceil(kvalid / 16) 16-key steps only, all inside the chunks written here
+        if (!FULL && c * 32 >= kvalid) break;
         uint32_t* cur = (c & 1) ? vb : va;
         tmem_ld_wait();
-        if (c < 3) tmem_ld32(s_addr + (c + 1) * 32, (c & 1) ? va : vb);
+        if (c < 3 && (FULL || (c + 1) * 32 < kvalid)) tmem_ld32(s_addr + (c + 1) * 32, (c & 1) ? va : vb);
         uint8_t* chunk = p_smem + (c >> 1) * (ATT_BQ * 128);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -638,11 +641,24 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention64_kernel(const __gri
             const AttnWork w = attn_decode(p, item);
             const int T = w.n_tiles;
             float m_used = 0.f;
+            // ragged query blocks (400 / 100 / 25 audio tokens per segment): a warp whose 32 rows all lie past the block
+            // skips the whole softmax (the exp unit is the limiter) and only keeps the barrier protocol going; its
+            // P / O rows are garbage that is never stored
+            const bool warp_active = warp * 32 < w.q_valid;
             for (int t = 0; t < T; ++t, ++g) {
                 int krow, kvalid;
                 attn_tile(w, t, krow, kvalid);
                 mbar_wait(s_full, g & 1);
                 tc_fence_after();
+                if (!warp_active) {
+                    if (t > 0) {
+                        mbar_wait(o_full, (g - 1) & 1);
+                        tc_fence_after();
+                    }
+                    tc_fence_before();
+                    mbar_arrive(p_ready);
+                    continue;
+                }
                 const bool full_tile = (kvalid == ATT_BKV);
                 // ---- pass 1: row maximum
                 const float mx = full_tile ? attn64_rowmax<true>(s_addr, kvalid) : attn64_rowmax<false>(s_addr, kvalid);

@@ -42,8 +42,10 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(GnSrc s, int R, int rows_
     const int rows_per_pass = blockDim.x / vpr;
     const int vec = threadIdx.x % vpr;
     const int rsub = threadIdx.x / vpr;
-    __shared__ float sh[64];
-    if (threadIdx.x < 64) sh[threadIdx.x] = 0.f;
+    // double accumulators in shared memory too: the order of the atomic additions then only moves the sums at the 1e-16
+    // level, far below the fp32 mean / rstd they turn into, so the forward is bit-reproducible in practice
+    __shared__ double sh[64];
+    if (threadIdx.x < 64) sh[threadIdx.x] = 0.0;
     __syncthreads();
     if (rsub < rows_per_pass) {
         float sm[8], sq[8];
@@ -79,17 +81,17 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(GnSrc s, int R, int rows_
         for (int i = 0; i < 8; ++i) {
             const int gi = (c0 + i) / cpg;
             if (gi != g) {
-                atomicAdd(&sh[2 * g], as);
-                atomicAdd(&sh[2 * g + 1], aq);
+                atomicAdd(&sh[2 * g], static_cast<double>(as));
+                atomicAdd(&sh[2 * g + 1], static_cast<double>(aq));
                 g = gi; as = 0.f; aq = 0.f;
             }
             as += sm[i]; aq += sq[i];
         }
-        atomicAdd(&sh[2 * g], as);
-        atomicAdd(&sh[2 * g + 1], aq);
+        atomicAdd(&sh[2 * g], static_cast<double>(as));
+        atomicAdd(&sh[2 * g + 1], static_cast<double>(aq));
     }
     __syncthreads();
-    if (threadIdx.x < 64) atomicAdd(&sums[static_cast<size_t>(ns) * 64 + threadIdx.x], static_cast<double>(sh[threadIdx.x]));
+    if (threadIdx.x < 64) atomicAdd(&sums[static_cast<size_t>(ns) * 64 + threadIdx.x], sh[threadIdx.x]);
 }
 
 // ---------------------------------------------------------------------------

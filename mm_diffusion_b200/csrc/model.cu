@@ -14,9 +14,19 @@
 #include <memory>
 #include <unordered_map>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "host.cuh"
 
 namespace mmd {
+
+// NVTX range per plan step (named by kernel family) on the eager paths (MMD_NO_GRAPH=1 / profiling hooks): nsys and ncu
+// --nvtx captures can filter by family.  Graph replays carry no ranges (the graph is one node to the tools).
+struct NvtxStep {
+    static bool on() { static const bool v = [] { const char* e = getenv("MMD_NVTX"); return !(e && e[0] == '0'); }(); return v; }
+    explicit NvtxStep(const char* name) { if (on()) nvtxRangePushA(name); }
+    ~NvtxStep() { if (on()) nvtxRangePop(); }
+};
 
 struct ShiftArgs { int n; int v[64]; };
 __global__ void set_shifts_kernel(ShiftArgs a, int* dst) {
@@ -1515,6 +1525,21 @@ static int validate_cfg(const MmdConfig& c) {
     for (int i = 1; i < c.n_levels; ++i) adown *= 4;
     if (c.audio_l % adown) return fail(MMD_EINVAL, "audio length not divisible by %lld", adown);
     if ((c.video_w & (c.video_w - 1)) || (c.video_h & (c.video_h - 1))) return fail(MMD_EINVAL, "video H/W must be powers of two");
+    // QKVAttention lets the last audio segment absorb the remainder when the audio length at a cross-attention level is
+    // not a multiple of the frame count (multimodal_unet.py:547-548, 644-645).  The window kernels here take equal
+    // segments (every shipped configuration: 25600 / 4^l is a multiple of 16), so such a configuration is rejected when
+    // the model is created instead of at the first forward.
+    {
+        long long L = c.audio_l;
+        for (int level = 0, ds = 1; level < c.n_levels; ++level, ds *= 2) {
+            bool cross = false;
+            for (int i = 0; i < c.n_cross; ++i) cross = cross || c.cross_attention_resolutions[i] == ds;
+            if (cross && L % c.video_f != 0)
+                return fail(MMD_EINVAL, "audio length %lld at cross-attention resolution %d is not a multiple of the %d frames: "
+                            "the reference's remainder segment (multimodal_unet.py:547-548) is not supported", L, ds, c.video_f);
+            L /= 4;
+        }
+    }
     return MMD_OK;
 }
 
@@ -1880,7 +1905,10 @@ int mmd_model_profile(MmdModel* m, int batch, int reps, float* ms, int cap, void
     for (int rep = 0; rep < reps && r == MMD_OK; ++rep) {
         MMD_CUDA_OK(cudaEventRecord(ev[0], st));
         for (int i = 0; i < n; ++i) {
-            r = plan->steps[i](st);
+            {
+                NvtxStep range(plan->info[i].kind.c_str());
+                r = plan->steps[i](st);
+            }
             if (r != MMD_OK) break;
             MMD_CUDA_OK(cudaEventRecord(ev[i + 1], st));
         }
@@ -1950,7 +1978,10 @@ int mmd_model_forward(MmdModel* m, int batch, const float* video_in, const float
         MMD_CUDA_OK(cudaGraphLaunch(plan->graph, st));
     } else {
         PdlScope pdl(st, nullptr);
-        for (auto& step : plan->steps) MMD_TRY(step(st));
+        for (size_t i = 0; i < plan->steps.size(); ++i) {
+            NvtxStep range(plan->info[i].kind.c_str());
+            MMD_TRY(plan->steps[i](st));
+        }
     }
     MMD_CUDA_OK(cudaMemcpyAsync(video_out, plan->out_video, vout, cudaMemcpyDeviceToDevice, st));
     MMD_CUDA_OK(cudaMemcpyAsync(audio_out, plan->out_audio, aout, cudaMemcpyDeviceToDevice, st));
@@ -1975,7 +2006,10 @@ int mmd_model_forward_train(MmdModel* m, int batch, const float* video_in, const
         MMD_CUDA_OK(cudaGraphLaunch(plan->graph, st));
     } else {
         PdlScope pdl(st, nullptr);
-        for (auto& step : plan->steps) MMD_TRY(step(st));
+        for (size_t i = 0; i < plan->steps.size(); ++i) {
+            NvtxStep range(plan->info[i].kind.c_str());
+            MMD_TRY(plan->steps[i](st));
+        }
     }
     const MmdConfig& c = m->cfg;
     const size_t vout = sizeof(float) * batch * c.video_f * c.video_out_channels * c.video_h * c.video_w;
@@ -2062,7 +2096,10 @@ int mmd_model_backward(MmdModel* m, int batch, const float* d_video_out, const f
         if (!plan->bwd_graph) MMD_TRY(capture_backward_graph(m, plan, st));
         MMD_CUDA_OK(cudaGraphLaunch(plan->bwd_graph, st));
     } else {
-        for (auto& step : plan->bwd_steps) MMD_TRY(step(st));
+        for (size_t i = 0; i < plan->bwd_steps.size(); ++i) {
+            NvtxStep range(plan->bwd_kind[i].c_str());
+            MMD_TRY(plan->bwd_steps[i](st));
+        }
     }
     if (param_grads)
         MMD_CUDA_OK(cudaMemcpyAsync(param_grads, plan->g32, sizeof(float) * m->w32_floats, cudaMemcpyDeviceToDevice, st));

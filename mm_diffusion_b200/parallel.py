@@ -37,6 +37,13 @@ def gather_samples(sample: Dict[str, torch.Tensor], group=None) -> Dict[str, tor
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return {"video": video, "audio": audio}
     world = dist.get_world_size(group)
+    if dist.get_backend(group) != "nccl" and video.is_cuda:
+        # gloo (CPU rendezvous, e.g. several ranks sharing one GPU in the tests): stage through the host
+        lv = [torch.empty_like(video, device="cpu") for _ in range(world)]
+        la = [torch.empty_like(audio, device="cpu") for _ in range(world)]
+        dist.all_gather(lv, video.cpu(), group=group)
+        dist.all_gather(la, audio.cpu(), group=group)
+        return {"video": torch.cat(lv).to(video.device), "audio": torch.cat(la).to(audio.device)}
     gv = torch.empty((world * video.shape[0],) + tuple(video.shape[1:]), dtype=video.dtype, device=video.device)
     ga = torch.empty((world * audio.shape[0],) + tuple(audio.shape[1:]), dtype=audio.dtype, device=audio.device)
     dist.all_gather_into_tensor(gv, video, group=group)

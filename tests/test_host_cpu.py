@@ -82,6 +82,11 @@ def test_unsupported_configs_are_rejected():
     with pytest.raises(NotImplementedError):
         MultimodalUNet([8, 3, 16, 16], [1, 2048], 64, 3, 1, 1, [1], [1], True, [1], [-1], channel_mult=(1,),
                        num_heads=1, num_head_channels=64, use_scale_shift_norm=False)
+    # audio length not a multiple of the frame count at a cross-attention level: the reference's remainder segment
+    # (multimodal_unet.py:547-548) is rejected at construction, not at the first forward
+    with pytest.raises(MmdError, match="remainder segment"):
+        MultimodalUNet([8, 3, 16, 16], [1, 2052], 64, 3, 1, 1, [1], [1], True, [1], [-1], channel_mult=(1,),
+                       num_heads=1, num_head_channels=64, use_scale_shift_norm=True)
 
 
 def test_factories_and_schedule_tables_match_oracle():

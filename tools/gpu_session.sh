@@ -16,7 +16,7 @@ if [ -n "$SMOKE" ]; then
 fi
 for v in $VARIANTS; do
   tag=${v%%:*}; envs=$(echo "${v#*:}" | tr ',' ' ')
-  env $envs timeout 600 python bench.py --steps ${STEPS:-20} --warmup 3 --batch ${BATCH:-4} --no-cpu-baseline --profile-reps 2 \
+  env $envs timeout 600 python bench.py --steps ${STEPS:-20} --warmup 3 --batch ${BATCH:-4} --no-cpu-baseline --no-gpu-baseline --no-extras --profile-reps 2 \
       > $O/bench_$tag.json 2> $O/bench_$tag.err || tail -3 $O/bench_$tag.err
   python tools/bench_summary.py $O/bench_$tag.json $tag
 done
