@@ -66,6 +66,11 @@ int mmd_model_param_info(const MmdModel* m, int index, const char** name, int* n
 /* Upload one parameter (fp32, contiguous, device pointer, reference layout [Cout,Cin,k...]).
  * The library repacks into its own fp16 K-major layout; the caller keeps ownership of `data`. */
 int mmd_model_set_param(MmdModel* m, const char* name, const float* data, int64_t numel, void* stream);
+/* All parameters in one call: `flat` (device, fp32) holds every tensor at the float offset mmd_model_param_offset()
+ * reports for it (the layout of the flat gradient buffer of mmd_model_backward); n_floats == mmd_model_param_floats().
+ * The Python shim keeps its nn.Parameters as views of such a buffer, so an optimizer step (fp16_util.py:64-74 copies
+ * the masters back per tensor in the reference) reaches the library as ONE device copy + one repack graph launch. */
+int mmd_model_set_params_flat(MmdModel* m, const float* flat, int64_t n_floats, void* stream);
 /* Number of cross-attention blocks that draw a random window shift per forward
  * (CrossAttentionBlock.attention_index, multimodal_unet.py:619-622), in execution order,
  * and the inclusive upper bound F - window of each draw. */

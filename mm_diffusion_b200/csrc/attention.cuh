@@ -418,6 +418,20 @@ MMD_DEVINL uint32_t ex2_h2(float lo, float hi) {
     return r;
 }
 
+// exp2 on the FMA / ALU pipes (no MUFU): Cody-Waite split x = r + f, r = round(x), f in [-0.5, 0.5]; cubic minimax of 2^f
+// (max relative error 7.5e-5, an order below the fp16 rounding of the probability it becomes) scaled by 2^r through the
+// exponent field.  The exp unit (16 ex2/clk/SM) is the limiter of the d = 64 softmax; a fraction of the elements takes
+// this path so both pipes work (the split is a template parameter of the kernels).
+MMD_DEVINL float ex2_poly(float x) {
+    x = fmaxf(x, -126.0f);
+    const float xi = x + 12582912.0f;            // 1.5 * 2^23: the integer part lands in the low mantissa bits
+    const float f = x - (xi - 12582912.0f);
+    float pl = fmaf(0.05517165f, f, 0.24261112f);
+    pl = fmaf(pl, f, 0.69326099f);
+    pl = fmaf(pl, f, 0.99992807f);
+    return __int_as_float(__float_as_int(pl) + (__float_as_int(xi) << 23));
+}
+
 // Row maximum of a 128-column logit tile in TMEM (thread = row); the next 32-column load is in flight while
 // the current one is reduced.  FULL tiles carry no masking code at all.
 template <bool FULL>
@@ -439,7 +453,8 @@ MMD_DEVINL float attn64_rowmax(uint32_t s_addr, int kvalid) {
 }
 
 // p = exp2(s * scale - m) as fp16 into the swizzled P tile (two 64-key chunks).
-template <bool FULL>
+// PQ of every 4 consecutive elements take ex2_poly instead of the MUFU op (0, 1 or 2).
+template <bool FULL, int PQ>
 MMD_DEVINL void attn64_write_p(uint32_t s_addr, int kvalid, float scale_log2, float nm, uint8_t* p_smem, int row) {
     uint32_t va[32], vb[32];
     tmem_ld32(s_addr, va);
@@ -458,8 +473,10 @@ MMD_DEVINL void attn64_write_p(uint32_t s_addr, int kvalid, float scale_log2, fl
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int col = c * 32 + j * 8 + 2 * k;
-                float e0 = ex2_fast(fmaf(__uint_as_float(cur[j * 8 + 2 * k]), scale_log2, nm));
-                float e1 = ex2_fast(fmaf(__uint_as_float(cur[j * 8 + 2 * k + 1]), scale_log2, nm));
+                const float a0 = fmaf(__uint_as_float(cur[j * 8 + 2 * k]), scale_log2, nm);
+                const float a1 = fmaf(__uint_as_float(cur[j * 8 + 2 * k + 1]), scale_log2, nm);
+                float e0 = ex2_fast(a0);
+                float e1 = (PQ == 2 || (PQ == 1 && (k & 1))) ? ex2_poly(a1) : ex2_fast(a1);
                 if (!FULL) {
                     if (col >= kvalid) e0 = 0.f;
                     if (col + 1 >= kvalid) e1 = 0.f;
@@ -472,6 +489,7 @@ MMD_DEVINL void attn64_write_p(uint32_t s_addr, int kvalid, float scale_log2, fl
     }
 }
 
+template <int PQ>
 __global__ void __launch_bounds__(ATT_THREADS, 2) attention64_kernel(const __grid_constant__ AttnParams p, int n_items) {
     // Persistent: a CTA walks work items blockIdx.x, +gridDim.x, ... ; the TMA warp runs ahead into the next item
     // (Q as soon as the last Q·K^T of the current item has been issued, K/V as stages free up), so the per-item
@@ -690,8 +708,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention64_kernel(const __gri
                     }
                 }
                 // ---- pass 2: probabilities (fp16) -> shared memory
-                if (full_tile) attn64_write_p<true>(s_addr, kvalid, p.scale_log2, -m_used, p_smem, row);
-                else attn64_write_p<false>(s_addr, kvalid, p.scale_log2, -m_used, p_smem, row);
+                if (full_tile) attn64_write_p<true, PQ>(s_addr, kvalid, p.scale_log2, -m_used, p_smem, row);
+                else attn64_write_p<false, PQ>(s_addr, kvalid, p.scale_log2, -m_used, p_smem, row);
                 fence_proxy_async_smem();
                 tc_fence_before();
                 mbar_arrive(p_ready);
@@ -730,6 +748,340 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention64_kernel(const __gri
     tc_fence_before();
     __syncthreads();
     if (warp == 5) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, S::TMEM_COLS);
+    }
+}
+
+
+// ===========================================================================
+// attention64x2_kernel — head_dim 64 with TWO 128-row query tiles per CTA sharing every K/V tile.
+// One CTA per SM (512 TMEM columns, ~165 KB shared memory): two softmax groups of four warps each own one query tile
+// (S, P, O, l of its own), one TMA warp, one MMA thread.  While group 0 is in its softmax the tensor core runs group 1's
+// Q·K^T / P·V and vice versa, so the exp unit — the limiter at d = 64 — sees eight softmax warps with independent
+// dependencies instead of two CTAs that each stall on their own MMA round trip, and every K/V tile is fetched once for
+// 256 query rows.  Items whose query block has no second tile (<= 128 rows) run with group 1 idle.
+// Same arithmetic as attention64_kernel (shared row-max / probability helpers): results are bit-identical.
+// ===========================================================================
+struct Attn64x2Smem {
+    static constexpr int Q_OFF = 0;                       // two query tiles
+    static constexpr int K_OFF = 2 * 16384;               // 2 stages
+    static constexpr int V_OFF = K_OFF + 2 * 16384;       // 2 stages
+    static constexpr int P_OFF = V_OFF + 2 * 16384;       // 2 x (128 x 128 fp16)
+    static constexpr int ONES_OFF = P_OFF + 2 * 32768;
+    static constexpr int BAR_OFF = ONES_OFF + 4096;
+    static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+    static constexpr int TMEM_COLS = 512;                 // S0 0 | S1 128 | O0 256 | O1 320 | l0 384 | l1 400
+};
+constexpr int ATT2_THREADS = 320;   // warps 0-3: softmax of tile 0, 4-7: softmax of tile 1, 8: TMA, 9: MMA
+
+struct AttnWork2 {
+    AttnWork w;      // tile 0 of the pair (q_row0, key segments, head)
+    int qv[2];       // valid rows of the two tiles (qv[1] == 0: single-tile item)
+};
+MMD_DEVINL AttnWork2 attn_decode2(const AttnParams& p, int q_pairs, int idx) {
+    const int qp = idx % q_pairs;
+    const int rest = idx / q_pairs;
+    AttnWork2 r;
+    r.w = attn_decode(p, rest * p.q_tiles + 2 * qp);
+    r.qv[0] = r.w.q_valid;
+    r.qv[1] = max(0, min(ATT_BQ, p.q_blk - (2 * qp + 1) * ATT_BQ));
+    return r;
+}
+
+// P·V and P·1 of one 128-key tile into the O / l accumulators of one query tile (single issuing thread).
+MMD_DEVINL void attn64_issue_pv(uint32_t tmem_O, uint32_t tmem_L, uint64_t pd0, uint64_t vd0, uint64_t od0, int kvalid, int t) {
+    constexpr int D = 64;
+    constexpr uint32_t idesc_pv = umma_idesc_f16(ATT_BQ, D, 0, 1);   // V is MN-major
+    constexpr uint32_t idesc_l = umma_idesc_f16(ATT_BQ, 16, 0, 0);   // P x ones^T
+    const int nks = (kvalid + 15) >> 4;
+    if (nks == ATT_BKV / 16) {
+#pragma unroll
+        for (int ks = 0; ks < ATT_BKV / 16; ++ks)
+            umma_f16_ss(tmem_O, pd0 + ((ks >> 2) * (ATT_BQ * 128 >> 4) + (ks & 3) * 2), vd0 + ks * (2048 >> 4), idesc_pv,
+                        (t | ks) != 0 ? 1u : 0u);
+#pragma unroll
+        for (int ks = 0; ks < ATT_BKV / 16; ++ks)
+            umma_f16_ss(tmem_L, pd0 + ((ks >> 2) * (ATT_BQ * 128 >> 4) + (ks & 3) * 2),
+                        od0 + ((ks >> 2) * (2048 >> 4) + (ks & 3) * 2), idesc_l, (t | ks) != 0 ? 1u : 0u);
+    } else {
+        uint64_t pd = pd0, vd = vd0;
+        for (int ks = 0; ks < nks; ++ks) {
+            umma_f16_ss(tmem_O, pd, vd, idesc_pv, (t | ks) != 0 ? 1u : 0u);
+            vd += 2048 >> 4;
+            pd += (ks == 3) ? (ATT_BQ * 128 >> 4) - 6 : 2;
+        }
+        uint64_t od = od0;
+        pd = pd0;
+        for (int ks = 0; ks < nks; ++ks) {
+            umma_f16_ss(tmem_L, pd, od, idesc_l, (t | ks) != 0 ? 1u : 0u);
+            pd += (ks == 3) ? (ATT_BQ * 128 >> 4) - 6 : 2;
+            od += (ks == 3) ? (2048 >> 4) - 6 : 2;
+        }
+    }
+}
+
+template <int PQ>
+__global__ void __launch_bounds__(ATT2_THREADS, 1) attention64x2_kernel(const __grid_constant__ AttnParams p, int n_items, int q_pairs) {
+    using S = Attn64x2Smem;
+    constexpr int D = 64;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
+    uint64_t* q_full = bars;         // 1
+    uint64_t* q_empty = bars + 1;    // 1
+    uint64_t* k_full = bars + 2;     // 2
+    uint64_t* k_empty = bars + 4;    // 2
+    uint64_t* v_full = bars + 6;     // 2
+    uint64_t* v_empty = bars + 8;    // 2 (two arrivals: one per query tile's P·V)
+    uint64_t* s_full = bars + 10;    // 2 (per group)
+    uint64_t* p_ready = bars + 12;   // 2 (128 arrivals each)
+    uint64_t* o_full = bars + 14;    // 2
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    pdl_trigger();
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&p.q_map);
+        tma_prefetch_desc(&p.k_map);
+        tma_prefetch_desc(&p.v_map);
+        mbar_init(q_full, 1);
+        mbar_init(q_empty, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&k_full[i], 1);
+            mbar_init(&k_empty[i], 1);
+            mbar_init(&v_full[i], 1);
+            mbar_init(&v_empty[i], 2);
+            mbar_init(&s_full[i], 1);
+            mbar_init(&p_ready[i], 128);
+            mbar_init(&o_full[i], 1);
+        }
+        fence_mbar_init();
+    }
+    for (int i = threadIdx.x; i < 4096 / 16; i += ATT2_THREADS)
+        reinterpret_cast<uint4*>(smem + S::ONES_OFF)[i] = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
+    fence_proxy_async_smem();
+    if (warp == 9) tmem_alloc(tmem_slot, S::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();   // q/k/v come from the previous kernel
+
+    if (warp == 8) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int n = 0;    // K/V tiles issued so far (all items)
+            int it = 0;   // items started
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                const AttnWork2 w2 = attn_decode2(p, q_pairs, item);
+                const AttnWork& w = w2.w;
+                const bool two = w2.qv[1] > 0;
+                mbar_wait(q_empty, (it & 1) ^ 1);   // the last Q·K^T of the previous item has retired
+                mbar_expect_tx(q_full, two ? 32768 : 16384);
+                tma_load_2d(smem + S::Q_OFF, &p.q_map, q_full, p.q_col0 + w.head * D, w.q_row0);
+                if (two) tma_load_2d(smem + S::Q_OFF + 16384, &p.q_map, q_full, p.q_col0 + w.head * D, w.q_row0 + ATT_BQ);
+                for (int t = 0; t < w.n_tiles; ++t, ++n) {
+                    const int st = n & 1;
+                    const uint32_t ph = (n >> 1) & 1;
+                    int krow, kvalid;
+                    attn_tile(w, t, krow, kvalid);
+                    mbar_wait(&k_empty[st], ph ^ 1);
+                    mbar_expect_tx(&k_full[st], 16384);
+                    tma_load_2d(smem + S::K_OFF + st * 16384, &p.k_map, &k_full[st], p.k_col0 + w.head * D, krow);
+                    mbar_wait(&v_empty[st], ph ^ 1);
+                    mbar_expect_tx(&v_full[st], 16384);
+                    tma_load_2d(smem + S::V_OFF + st * 16384, &p.v_map, &v_full[st], p.v_col0 + w.head * D, krow);
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc_qk = umma_idesc_f16(ATT_BQ, ATT_BKV, 0, 0);
+            const uint64_t qd0 = umma_desc_sw128(smem_u32(smem + S::Q_OFF), 16, 1024);
+            const uint64_t kd0 = umma_desc_sw128(smem_u32(smem + S::K_OFF), 16, 1024);
+            const uint64_t pd0 = umma_desc_sw128(smem_u32(smem + S::P_OFF), 16, 1024);
+            const uint64_t vd0 = umma_desc_sw128(smem_u32(smem + S::V_OFF), ATT_BKV * 128, 1024);   // MN-major V
+            const uint64_t od0 = umma_desc_sw128(smem_u32(smem + S::ONES_OFF), 16, 1024);
+            int itq = 0;            // items whose Q has been waited for
+            int gs[2] = {0, 0};     // tiles processed per group (phases of p_ready / o_full; s_full runs one ahead)
+            // Q·K^T of K tile `kidx` (global tile counter) of an item for group grp; `last_of_tile`: no further Q·K^T
+            // reads this K stage; `last_of_item`: nor this item's Q
+            auto issue_qk = [&](int grp, int kidx, bool first_of_item, bool last_of_tile, bool last_of_item) {
+                if (first_of_item) {
+                    mbar_wait(q_full, itq & 1);
+                    ++itq;
+                }
+                const int st = kidx & 1;
+                mbar_wait(&k_full[st], (kidx >> 1) & 1);
+                tc_fence_after();
+                const uint64_t qd = qd0 + static_cast<uint64_t>(grp) * (16384 >> 4);
+                const uint64_t kd = kd0 + static_cast<uint64_t>(st) * (16384 >> 4);
+                const uint32_t tS = tmem_base + grp * 128;
+#pragma unroll
+                for (int ks = 0; ks < D / 16; ++ks) umma_f16_ss(tS, qd + 2 * ks, kd + 2 * ks, idesc_qk, ks != 0 ? 1u : 0u);
+                if (last_of_tile) umma_commit(&k_empty[st]);
+                if (last_of_tile && last_of_item) umma_commit(q_empty);
+                umma_commit(&s_full[grp]);
+            };
+            int n = 0;   // global index of the current K/V tile
+            bool have = static_cast<int>(blockIdx.x) < n_items;
+            AttnWork2 cur{};
+            if (have) {
+                cur = attn_decode2(p, q_pairs, blockIdx.x);
+                const bool two = cur.qv[1] > 0;
+                issue_qk(0, 0, true, !two, cur.w.n_tiles == 1);
+                if (two) issue_qk(1, 0, false, true, cur.w.n_tiles == 1);
+            }
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const bool two = cur.qv[1] > 0;
+                const int T = cur.w.n_tiles;
+                const bool has_next = item + static_cast<int>(gridDim.x) < n_items;
+                AttnWork2 nxt{};
+                if (has_next) nxt = attn_decode2(p, q_pairs, item + gridDim.x);
+                const bool next_two = has_next && nxt.qv[1] > 0;
+                for (int t = 0; t < T; ++t, ++n) {
+                    int krow, kvalid;
+                    attn_tile(cur.w, t, krow, kvalid);
+                    const int vst = n & 1;
+                    const uint32_t vph = (n >> 1) & 1;
+                    const uint64_t vd = vd0 + static_cast<uint64_t>(vst) * (16384 >> 4);
+                    for (int grp = 0; grp < (two ? 2 : 1); ++grp) {
+                        mbar_wait(&p_ready[grp], gs[grp] & 1);
+                        mbar_wait(&v_full[vst], vph);
+                        tc_fence_after();
+                        attn64_issue_pv(tmem_base + 256 + grp * 64, tmem_base + 384 + grp * 16,
+                                        pd0 + static_cast<uint64_t>(grp) * (32768 >> 4), vd, od0, kvalid, t);
+                        umma_commit(&v_empty[vst]);
+                        umma_commit(&o_full[grp]);
+                        ++gs[grp];
+                        // next logits of this group: same item, or the first tile of the next item
+                        if (t + 1 < T) {
+                            issue_qk(grp, n + 1, false, grp == (two ? 1 : 0), t + 2 == T);
+                        } else if (has_next && (grp == 0 || next_two)) {
+                            issue_qk(grp, n + 1, grp == 0, grp == (next_two ? 1 : 0), nxt.w.n_tiles == 1);
+                        }
+                    }
+                    if (!two) {
+                        umma_commit(&v_empty[vst]);   // the idle group's arrival
+                        if (t + 1 == T && next_two) issue_qk(1, n + 1, false, true, nxt.w.n_tiles == 1);
+                    }
+                }
+                cur = nxt;
+            }
+        }
+    } else {
+        // ===================== softmax groups (thread = query row of the group's tile) =====================
+        const int grp = warp >> 2;
+        const int wg = warp & 3;
+        const int row = wg * 32 + lane;
+        const uint32_t lane_base = static_cast<uint32_t>(wg * 32) << 16;
+        const uint32_t tmem_S = tmem_base + grp * 128;
+        const uint32_t tmem_O = tmem_base + 256 + grp * 64;
+        const uint32_t tmem_L = tmem_base + 384 + grp * 16;
+        const uint32_t s_addr = tmem_S + lane_base;
+        uint8_t* p_smem = smem + S::P_OFF + grp * 32768;
+        uint64_t* sf = &s_full[grp];
+        uint64_t* pr = &p_ready[grp];
+        uint64_t* of = &o_full[grp];
+        int g = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const AttnWork2 w2 = attn_decode2(p, q_pairs, item);
+            const AttnWork& w = w2.w;
+            const int q_valid = w2.qv[grp];
+            if (q_valid <= 0) continue;   // single-tile item: group 1 sits it out (the MMA thread skips it too)
+            const int q_row0 = w.q_row0 + grp * ATT_BQ;
+            const int T = w.n_tiles;
+            float m_used = 0.f;
+            const bool warp_active = wg * 32 < q_valid;
+            for (int t = 0; t < T; ++t, ++g) {
+                int krow, kvalid;
+                attn_tile(w, t, krow, kvalid);
+                mbar_wait(sf, g & 1);
+                tc_fence_after();
+                if (!warp_active) {
+                    if (t > 0) {
+                        mbar_wait(of, (g - 1) & 1);
+                        tc_fence_after();
+                    }
+                    tc_fence_before();
+                    mbar_arrive(pr);
+                    continue;
+                }
+                const bool full_tile = (kvalid == ATT_BKV);
+                const float mx = full_tile ? attn64_rowmax<true>(s_addr, kvalid) : attn64_rowmax<false>(s_addr, kvalid);
+                const float mxs = mx * p.scale_log2;
+                if (t == 0) {
+                    m_used = mxs;
+                } else {
+                    mbar_wait(of, (g - 1) & 1);   // P·V of the previous tile is done: P and O may be touched
+                    tc_fence_after();
+                    if (__any_sync(0xffffffffu, mxs > m_used + 8.0f)) {
+                        const float m_new = fmaxf(m_used, mxs);
+                        const float alpha = ex2_fast(m_used - m_new);
+                        m_used = m_new;
+                        uint32_t o[32];
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            tmem_ld32(tmem_O + lane_base + c * 32, o);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                            tmem_st32(tmem_O + lane_base + c * 32, o);
+                        }
+                        tmem_ld16(tmem_L + lane_base, o);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        tmem_st16(tmem_L + lane_base, o);
+                        tmem_st_wait();
+                    }
+                }
+                if (full_tile) attn64_write_p<true, PQ>(s_addr, kvalid, p.scale_log2, -m_used, p_smem, row);
+                else attn64_write_p<false, PQ>(s_addr, kvalid, p.scale_log2, -m_used, p_smem, row);
+                fence_proxy_async_smem();
+                tc_fence_before();
+                mbar_arrive(pr);
+            }
+            // ---- item epilogue: O / l -> global
+            mbar_wait(of, (g - 1) & 1);
+            tc_fence_after();
+            if (warp_active) {
+                uint32_t lv[16];
+                tmem_ld16(tmem_L + lane_base, lv);
+                tmem_ld_wait();
+                const float inv_l = 1.f / __uint_as_float(lv[0]);
+                if (p.lse != nullptr && row < q_valid)
+                    p.lse[static_cast<size_t>(w.head) * p.lse_ld + q_row0 + row] = m_used + log2f(__uint_as_float(lv[0]));
+                act_t* orow = p.out + static_cast<size_t>(q_row0 + row) * p.out_ld + w.head * D;
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_O + lane_base + c * 32, v);
+                    tmem_ld_wait();
+                    if (row < q_valid) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            uint4 pk;
+                            __half2* ph2 = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                ph2[k] = __floats2half2_rn(__uint_as_float(v[j * 8 + 2 * k]) * inv_l, __uint_as_float(v[j * 8 + 2 * k + 1]) * inv_l);
+                            *reinterpret_cast<uint4*>(orow + c * 32 + j * 8) = pk;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();   // O / l reads are complete before this thread's next p_ready arrival
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
         __syncwarp();
         tmem_dealloc(tmem_base, S::TMEM_COLS);
     }

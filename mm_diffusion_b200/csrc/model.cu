@@ -92,6 +92,7 @@ struct Plan {
     std::vector<std::string> bwd_kind;   // kernel family tag per backward step (profiling)
     std::vector<LaunchFn> tpack_ops;   // transposed weight packs for the data gradients (re-run when weights change)
     bool tpack_dirty = true;
+    cudaGraphExec_t tpack_graph = nullptr;   // the same ops as one multi-branch graph (one launch per parameter update)
     float *d_out_video = nullptr, *d_out_audio = nullptr;   // staged output gradients (fp32, API layout)
     float *d_in_video = nullptr, *d_in_audio = nullptr;     // input gradients (fp32, API layout)
     float* gscale = nullptr;            // {s, 1/s}
@@ -110,6 +111,7 @@ struct Plan {
     ~Plan() {
         if (graph) cudaGraphExecDestroy(graph);
         if (bwd_graph) cudaGraphExecDestroy(bwd_graph);
+        if (tpack_graph) cudaGraphExecDestroy(tpack_graph);
         for (auto e : events) cudaEventDestroy(e);
         if (ws) cudaFree(ws);
         if (wpk_t) cudaFree(wpk_t);
@@ -157,6 +159,7 @@ struct MmdModel {
     size_t w32_floats = 0;
     std::map<std::string, PackedConv> packs;
     std::vector<LaunchFn> pack_ops;
+    cudaGraphExec_t pack_graph = nullptr;   // pack_ops as one multi-branch graph: a parameter update costs one launch
     act_t* wpk = nullptr;      // packed fp16 weights
     size_t wpk_halves = 0;
     float* bpk = nullptr;      // packed fp32 biases + stacked emb weights
@@ -175,6 +178,7 @@ struct MmdModel {
     ~MmdModel() {
         plans.clear();
         train_plans.clear();
+        if (pack_graph) cudaGraphExecDestroy(pack_graph);
         if (w32) cudaFree(w32);
         if (wpk) cudaFree(wpk);
         if (bpk) cudaFree(bpk);
@@ -1777,11 +1781,61 @@ static int capture_backward_graph(MmdModel* m, Plan* plan, cudaStream_t st) {
     return MMD_OK;
 }
 
+// A list of small independent device operations (weight repacks: distinct destinations, fixed pointers) as ONE graph
+// with `branches` parallel chains: a parameter update then costs one graph launch instead of thousands of stream
+// launches (~2 600 per update for the production network), and the chains overlap on the device.
+static int capture_parallel_ops(MmdModel* m, const std::vector<LaunchFn>& ops, cudaStream_t st, cudaGraphExec_t* out,
+                                int branches = 8) {
+    MMD_CUDA_OK(cudaStreamSynchronize(st));
+    std::vector<cudaStream_t> side(branches - 1, nullptr);
+    std::vector<cudaEvent_t> evs;
+    auto new_event = [&]() { cudaEvent_t e = nullptr; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); evs.push_back(e); return e; };
+    for (auto& s : side) MMD_CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    cudaGraph_t g = nullptr;
+    int r = MMD_OK;
+    cudaError_t ce = cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal);
+    if (ce == cudaSuccess) {
+        cudaEvent_t fork = new_event();
+        ce = cudaEventRecord(fork, m->cap_stream);
+        for (auto& s : side) if (ce == cudaSuccess) ce = cudaStreamWaitEvent(s, fork, 0);
+        for (size_t i = 0; i < ops.size() && r == MMD_OK && ce == cudaSuccess; ++i) {
+            const size_t b = i % branches;
+            r = ops[i](b == 0 ? m->cap_stream : side[b - 1]);
+        }
+        for (auto& s : side) {
+            if (ce != cudaSuccess) break;
+            cudaEvent_t j = new_event();
+            ce = cudaEventRecord(j, s);
+            if (ce == cudaSuccess) ce = cudaStreamWaitEvent(m->cap_stream, j, 0);
+        }
+        const cudaError_t e = cudaStreamEndCapture(m->cap_stream, &g);
+        if (ce == cudaSuccess) ce = e;
+    }
+    for (auto& s : side) if (s) cudaStreamDestroy(s);
+    for (auto& e : evs) cudaEventDestroy(e);
+    if (r != MMD_OK) { if (g) cudaGraphDestroy(g); return r; }
+    if (ce != cudaSuccess) { if (g) cudaGraphDestroy(g); cudaGetLastError(); return fail(MMD_ECUDA, "repack graph capture: %s", cudaGetErrorString(ce)); }
+    ce = cudaGraphInstantiate(out, g, 0);
+    cudaGraphDestroy(g);
+    if (ce != cudaSuccess) return fail(MMD_ECUDA, "repack graph instantiate: %s", cudaGetErrorString(ce));
+    return MMD_OK;
+}
+
+static bool repack_graphs_enabled() {
+    static const bool on = [] { const char* e = getenv("MMD_REPACK_GRAPH"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 // Re-derive every packed weight layout after a parameter update: the forward's K-major fp16 packs now, the transposed
 // packs of the training plans lazily at their next backward (whichever entry point notices the update first).
 static int repack_if_dirty(MmdModel* m, cudaStream_t st) {
     if (!m->dirty) return MMD_OK;
-    for (auto& op : m->pack_ops) MMD_TRY(op(st));
+    if (m->use_graph && repack_graphs_enabled()) {
+        if (!m->pack_graph) MMD_TRY(capture_parallel_ops(m, m->pack_ops, st, &m->pack_graph));
+        MMD_CUDA_OK(cudaGraphLaunch(m->pack_graph, st));
+    } else {
+        for (auto& op : m->pack_ops) MMD_TRY(op(st));
+    }
     m->dirty = false;
     for (auto& tp : m->train_plans) tp.second->tpack_dirty = true;
     return MMD_OK;
@@ -1849,6 +1903,19 @@ int mmd_model_set_param(MmdModel* m, const char* name, const float* data, int64_
     MMD_CUDA_OK(cudaMemcpyAsync(m->w32 + p.offset, data, sizeof(float) * numel, cudaMemcpyDeviceToDevice,
                                 static_cast<cudaStream_t>(stream)));
     p.set = true;
+    m->dirty = true;
+    return MMD_OK;
+}
+
+/* Every parameter at once: `flat` holds the parameters at the float offsets of mmd_model_param_offset (the layout of
+ * the flat gradient buffer), `n_floats` == mmd_model_param_floats.  One device copy instead of one call per tensor. */
+int mmd_model_set_params_flat(MmdModel* m, const float* flat, int64_t n_floats, void* stream) {
+    if (!m || !flat) return fail(MMD_EINVAL, "null argument");
+    if (n_floats != static_cast<int64_t>(m->w32_floats))
+        return fail(MMD_EINVAL, "flat parameter buffer has %lld floats, %lld expected", (long long)n_floats, (long long)m->w32_floats);
+    MMD_TRY(ensure_device(m));
+    MMD_CUDA_OK(cudaMemcpyAsync(m->w32, flat, sizeof(float) * m->w32_floats, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+    for (auto& p : m->params) p.set = true;
     m->dirty = true;
     return MMD_OK;
 }
@@ -2089,7 +2156,12 @@ int mmd_model_backward(MmdModel* m, int batch, const float* d_video_out, const f
     make_gscale_kernel<<<1, 1, 0, st>>>(plan->amax_bits, plan->gscale);
     MMD_CUDA_OK(cudaGetLastError());
     if (plan->tpack_dirty) {
-        for (auto& op : plan->tpack_ops) MMD_TRY(op(st));
+        if (m->use_graph && repack_graphs_enabled()) {
+            if (!plan->tpack_graph) MMD_TRY(capture_parallel_ops(m, plan->tpack_ops, st, &plan->tpack_graph));
+            MMD_CUDA_OK(cudaGraphLaunch(plan->tpack_graph, st));
+        } else {
+            for (auto& op : plan->tpack_ops) MMD_TRY(op(st));
+        }
         plan->tpack_dirty = false;
     }
     if (m->use_graph && train_graphs_enabled()) {

@@ -313,15 +313,35 @@ int launch_attn(const AttnParams& p, int d, cudaStream_t st) {
     static bool done = false;
     if (!done) {
         MMD_CUDA_OK(cudaFuncSetAttribute(attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes<64>()));
-        MMD_CUDA_OK(cudaFuncSetAttribute(attention64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64Smem::TOTAL));
+        MMD_CUDA_OK(cudaFuncSetAttribute(attention64_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64Smem::TOTAL));
+        MMD_CUDA_OK(cudaFuncSetAttribute(attention64_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64Smem::TOTAL));
+        MMD_CUDA_OK(cudaFuncSetAttribute(attention64_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64Smem::TOTAL));
+        MMD_CUDA_OK(cudaFuncSetAttribute(attention64x2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64x2Smem::TOTAL));
+        MMD_CUDA_OK(cudaFuncSetAttribute(attention64x2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64x2Smem::TOTAL));
+        MMD_CUDA_OK(cudaFuncSetAttribute(attention64x2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64x2Smem::TOTAL));
         MMD_CUDA_OK(cudaFuncSetAttribute(attention_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes<96>()));
         MMD_CUDA_OK(cudaFuncSetAttribute(attention_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes<128>()));
         done = true;
     }
     const int grid = p.B * p.n_blocks * p.heads * p.q_tiles;
     static const bool generic64 = [] { const char* e = getenv("MMD_ATTN_GENERIC"); return e && e[0] == '1'; }();
-    if (d == 64 && !generic64)
-        MMD_CUDA_OK(launch_kernel(attention64_kernel, std::min(grid, 2 * num_sms()), ATT_THREADS, Attn64Smem::TOTAL, st, p, grid));
+    // two query tiles per CTA (shared K/V, ping-pong softmax groups) once a query block has at least two tiles
+    static const bool pair64 = [] { const char* e = getenv("MMD_ATTN_PAIR"); return e ? e[0] == '1' : false; }();
+    // MMD_ATTN_POLY = 0 / 1 / 2 of every 4 exponentials on the FMA pipe (cubic Cody-Waite) instead of the MUFU unit
+    static const int poly = [] { const char* e = getenv("MMD_ATTN_POLY"); const int v = e ? atoi(e) : 0; return v < 0 ? 0 : (v > 2 ? 2 : v); }();
+    if (d == 64 && !generic64 && pair64 && p.q_tiles >= 2) {
+        const int q_pairs = (p.q_tiles + 1) / 2;
+        const int items = p.B * p.n_blocks * p.heads * q_pairs;
+        const int g2 = std::min(items, num_sms());
+        if (poly == 0) MMD_CUDA_OK(launch_kernel(attention64x2_kernel<0>, g2, ATT2_THREADS, Attn64x2Smem::TOTAL, st, p, items, q_pairs));
+        else if (poly == 1) MMD_CUDA_OK(launch_kernel(attention64x2_kernel<1>, g2, ATT2_THREADS, Attn64x2Smem::TOTAL, st, p, items, q_pairs));
+        else MMD_CUDA_OK(launch_kernel(attention64x2_kernel<2>, g2, ATT2_THREADS, Attn64x2Smem::TOTAL, st, p, items, q_pairs));
+    } else if (d == 64 && !generic64) {
+        const int g1 = std::min(grid, 2 * num_sms());
+        if (poly == 0) MMD_CUDA_OK(launch_kernel(attention64_kernel<0>, g1, ATT_THREADS, Attn64Smem::TOTAL, st, p, grid));
+        else if (poly == 1) MMD_CUDA_OK(launch_kernel(attention64_kernel<1>, g1, ATT_THREADS, Attn64Smem::TOTAL, st, p, grid));
+        else MMD_CUDA_OK(launch_kernel(attention64_kernel<2>, g1, ATT_THREADS, Attn64Smem::TOTAL, st, p, grid));
+    }
     else if (d == 64) MMD_CUDA_OK(launch_kernel(attention_kernel<64>, grid, ATT_THREADS, attn_smem_bytes<64>(), st, p));
     else if (d == 96) MMD_CUDA_OK(launch_kernel(attention_kernel<96>, grid, ATT_THREADS, attn_smem_bytes<96>(), st, p));
     else MMD_CUDA_OK(launch_kernel(attention_kernel<128>, grid, ATT_THREADS, attn_smem_bytes<128>(), st, p));

@@ -193,6 +193,8 @@ class MultimodalUNet(nn.Module):
         self._drop_calls = 0
         self._flat_mode = False
         self._flat_views_ok = False
+        self.flat_parameters = True    # keep the parameters as views of one flat fp32 buffer (see _flatten_parameters)
+        self._flat_params = None
         self.flat_grad = None          # fp32 buffer holding every parameter gradient (see use_flat_gradients)
         self.flat_grad_views: List = []
         self._param_names: List[str] = []
@@ -301,11 +303,50 @@ class MultimodalUNet(nn.Module):
             check(lib.mmd_model_create(C.byref(self._cfg), C.byref(h)))
         self._handle, self._handle_device = h, device
         self._synced = {}
+        self._offsets = None
         self._needs_sync = True
+
+    def _flat_params_ok(self) -> bool:
+        """Every parameter is an fp32 view of self._flat_params at the library's offset (the layout of the flat gradient
+        buffer)."""
+        flat = self._flat_params
+        if flat is None or self._plist is None:
+            return False
+        base = flat.data_ptr()
+        for p, off in zip(self._plist, self._param_offsets()):
+            if p.dtype != torch.float32 or p.data_ptr() != base + 4 * off:
+                return False
+        return True
+
+    @torch.no_grad()
+    def _flatten_parameters(self, device) -> bool:
+        """Re-home the nn.Parameters (same objects, same names) as views of ONE flat fp32 device buffer laid out like the
+        library's parameter arena.  An optimizer step then reaches the library as one device copy
+        (mmd_model_set_params_flat) instead of one call per tensor, and the flat gradient buffer lines up element for
+        element with it (fused multi-tensor updates are plain vector operations on the two buffers)."""
+        if self._plist is None:
+            self._plist = list(self.parameters())
+        if any(p.dtype != torch.float32 or p.device != device for p in self._plist):
+            return False   # e.g. module.half(): keep the per-tensor path
+        n = int(_lib.load().mmd_model_param_floats(self._handle))
+        flat = torch.zeros(n, dtype=torch.float32, device=device)
+        for p, off in zip(self._plist, self._param_offsets()):
+            view = flat[off:off + p.numel()].view(p.shape)
+            view.copy_(p.detach())
+            p.data = view
+        self._flat_params = flat
+        return True
 
     def _sync_parameters(self):
         lib = _lib.load()
         stream = _lib.current_stream_ptr()
+        if self._plist is None:
+            self._plist = list(self.parameters())
+        if self.flat_parameters and (self._flat_params_ok() or self._flatten_parameters(self._handle_device)):
+            check(lib.mmd_model_set_params_flat(self._handle, self._flat_params.data_ptr(), self._flat_params.numel(), stream))
+            self._synced = {}
+            self._needs_sync = False
+            return
         for name, p in zip(self._param_names, self.parameters()):
             key = (p.data_ptr(), p._version, p.dtype)
             if self._synced.get(name) == key:
@@ -316,6 +357,17 @@ class MultimodalUNet(nn.Module):
             check(lib.mmd_model_set_param(self._handle, name.encode(), src.data_ptr(), src.numel(), stream))
             self._synced[name] = key
         self._needs_sync = False
+
+    def __getstate__(self):
+        """copy.deepcopy / pickle: the library handle and everything derived from it stay behind; the copy creates its
+        own on its first forward (EMA copies of a model, checkpoints of whole modules)."""
+        state = dict(self.__dict__)
+        state.update(_handle=None, _handle_device=None, _synced={}, _synced_vsum=-1, _needs_sync=True, _plist=None,
+                     _offsets=None, _flat_params=None, flat_grad=None, flat_grad_views=[], _flat_views_ok=False)
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
 
     def __del__(self):
         try:

@@ -172,3 +172,49 @@ def test_training_plan_dry_run_is_consistent():
             assert offs == sorted(offs) and offs[0] == 0
         finally:
             lib.mmd_model_destroy(h)
+
+
+def test_flat_parameter_storage_keeps_the_module_surface():
+    """The shim re-homes its nn.Parameters as views of one flat fp32 buffer laid out like the library's arena (one device
+    copy per optimizer step instead of one call per tensor): names / shapes / values, state_dict round trips, optimizer
+    updates and deepcopy must behave like ordinary parameters (host-only: the handle is created without a device)."""
+    import copy
+    import ctypes as C
+    from mm_diffusion_b200 import _lib
+    cfg = cfg_of(load_golden("small"))
+    model = build_b200_model(cfg, device="cpu")
+    lib = _lib.load()
+    h = C.c_void_p()
+    _lib.check(lib.mmd_model_create(C.byref(model._cfg), C.byref(h)))
+    model._handle, model._handle_device = h, torch.device("cpu")
+    before = {k: v.clone() for k, v in model.state_dict().items()}
+    params_before = list(model.parameters())
+    assert model._flatten_parameters(torch.device("cpu")) and model._flat_params_ok()
+    assert all(a is b for a, b in zip(params_before, model.parameters()))           # same Parameter objects
+    after = model.state_dict()
+    assert list(after) == list(before) and all(torch.equal(after[k], before[k]) for k in before)
+    # the flat buffer has the library's layout: parameter i lives at mmd_model_param_offset(i)
+    offs = model._param_offsets()
+    flat = model._flat_params
+    assert flat.numel() == lib.mmd_model_param_floats(h)
+    for p, off in list(zip(model.parameters(), offs))[::37]:
+        assert torch.equal(flat[off:off + p.numel()].view(p.shape), p.detach())
+    # an optimizer step updates the buffer in place and bumps the version sum the forward checks
+    v0 = sum(p._version for p in model.parameters())
+    opt = torch.optim.SGD(model.parameters(), lr=0.5)
+    for p in model.parameters():
+        p.grad = torch.ones_like(p)
+    snap = flat.clone()
+    opt.step()
+    assert sum(p._version for p in model.parameters()) > v0
+    p0, off0 = next(iter(model.parameters())), offs[0]
+    assert torch.allclose(flat[off0:off0 + p0.numel()], snap[off0:off0 + p0.numel()] - 0.5)
+    # load_state_dict copies in place (aliasing kept); deepcopy yields independent tensors and is detected
+    model.load_state_dict(before)
+    model._plist = list(model.parameters())   # (the forward rebuilds this cache lazily)
+    assert model._flat_params_ok() and torch.equal(next(iter(model.parameters())).detach(), before[next(iter(before))])
+    clone = copy.deepcopy(model)   # the library handle stays behind; the copy's parameters are independent tensors
+    assert clone._handle is None and clone._flat_params is None
+    assert all(torch.equal(a, b) and a.data_ptr() != b.data_ptr() for a, b in zip(clone.parameters(), model.parameters()))
+    model._handle = None
+    lib.mmd_model_destroy(h)
