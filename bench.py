@@ -317,7 +317,8 @@ def run_b200(ctx, args, model, diffusion):
 
     def sample_epilogue(x):
         """End-of-loop work of the sample scripts: uint8 video, and (N>1) the one NCCL gather of finished samples."""
-        v8 = ((x["video"] + 1) * 127.5).clamp(0, 255).to(torch.uint8)
+        from mm_diffusion_b200.parallel import sample_epilogue as fused_epilogue
+        v8 = fused_epilogue(x["video"])   # uint8 + channels-last permute of the script (:159-163) in one kernel
         a = x["audio"]
         if world > 1:
             gv = torch.empty((world,) + tuple(v8.shape), dtype=torch.uint8, device=device)

@@ -140,6 +140,11 @@ int mmd_p_sample_tail(const float* x, const float* eps, const float* noise, cons
 int mmd_q_sample(const float* x_start, const float* noise, const float* coef, int batch, int64_t per_sample, float* out,
                  void* stream);
 
+/* ---- sample epilogue of the sampling scripts (py_scripts/multimodal_sample_sr.py:159-163):
+ *      video fp32 [n_images][channels][hw] in [-1, 1] -> uint8 [n_images][hw][channels] =
+ *      ((x + 1) * 127.5).clamp(0, 255).to(uint8) with the permute(0, 1, 3, 4, 2) folded in (n_images = batch x frames). ---- */
+int mmd_sample_epilogue(const float* video, unsigned char* out, int64_t n_images, int channels, int64_t hw, void* stream);
+
 /* ---- DPM-Solver state arithmetic (DPM_Solver, multimodal_dpm_solver_plus.py:373-1298) ----
  * Every solver update and the eps -> x0 conversion is a linear combination of at most four fp32 tensors with
  * step-wide scalar coefficients (:532-1036, :419-430): out = sum_i coef[i] * src[i].  src: host array of device

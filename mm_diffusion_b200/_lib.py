@@ -110,6 +110,7 @@ _PROTOS = [
      [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
       C.c_void_p]),
     ("mmd_q_sample", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
+    ("mmd_sample_epilogue", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_void_p]),
     ("mmd_lincomb", C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_float), C.c_int64, C.c_void_p, C.c_void_p]),
     ("mmd_dpm_threshold", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_void_p]),
     ("mmd_dpm_error_sq", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_float, C.c_void_p,

@@ -629,6 +629,25 @@ __global__ void q_sample_kernel(const float* __restrict__ x0, const float* __res
     }
 }
 
+// Sample epilogue of the sampling scripts (py_scripts/multimodal_sample_sr.py:159-163): video [N, C, H, W] fp32 in
+// [-1, 1] (N = batch x frames) -> uint8 [N, H, W, C] = ((x + 1) * 127.5).clamp(0, 255).to(uint8) with the permute to
+// channels-last folded in.  Thread = one output pixel (C bytes); reads are coalesced per channel plane.
+__global__ void sample_epilogue_kernel(const float* __restrict__ x, unsigned char* __restrict__ out, long long n_img, int C,
+                                       int HW) {
+    const long long total = n_img * HW;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long img = i / HW;
+        const int px = static_cast<int>(i - img * HW);
+        const float* src = x + (img * C) * HW + px;
+        unsigned char* dst = out + i * C;
+        for (int c = 0; c < C; ++c) {
+            const float v = fminf(fmaxf((src[static_cast<long long>(c) * HW] + 1.0f) * 127.5f, 0.0f), 255.0f);
+            dst[c] = static_cast<unsigned char>(v);   // truncation, like torch's float -> uint8 cast
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------
 // DPM-Solver state updates (multimodal_dpm_solver_plus.py:532-1036): every first/second/third-order update, and the
 // x0 conversion of data_prediction_fn (:419-440), is x_t = sum_i c_i * tensor_i with step-wide scalars c_i.

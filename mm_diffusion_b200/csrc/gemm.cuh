@@ -91,9 +91,12 @@ struct GemmSmem {
     // barriers (256 B) | GroupNorm partials [BN/64 units][4 bands][16 quads][2] floats
     static constexpr int GN_BYTES = (BN >= 64) ? (BN / 64) * 4 * 16 * 2 * 4 : 0;
     // XF: per-channel affine table [2 domains][a|b][GEMM_XF_MAXC] floats + group mean / rstd [2][32][2]
-    static constexpr int XF_OFF = 256 + GN_BYTES;
+    // this tile's bias [BN] floats (epilogue reads it from shared memory: the global loads sat on its critical path)
+    static constexpr int BIAS_OFF = 256 + GN_BYTES;
+    static constexpr int BIAS_BYTES = (BN >= 64) ? BN * 4 : 0;
+    static constexpr int XF_OFF = BIAS_OFF + BIAS_BYTES;
     static constexpr int XF_BYTES = XF ? (2 * 2 * GEMM_XF_MAXC * 4 + 512) : 0;
-    static constexpr int BAR_BYTES = 256 + GN_BYTES + XF_BYTES;
+    static constexpr int BAR_BYTES = 256 + GN_BYTES + BIAS_BYTES + XF_BYTES;
     static constexpr int LIMIT = 232448;   // 227 KB
     static constexpr int FIT = (LIMIT - OUT_BYTES - BAR_BYTES) / STAGE_BYTES;
     static constexpr int STAGES = FIT > 8 ? 8 : FIT;
@@ -129,6 +132,7 @@ __global__ void __launch_bounds__(XF ? GEMM_THREADS_XF : GEMM_THREADS, 1) conv_g
     uint64_t* xf_bar = bars + 2 * S::STAGES + 4;   // [STAGES] (XF only): A tile transformed, the MMA may read it
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S::STAGES + 4);
     float* gn_part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
+    float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + S::BIAS_OFF);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -400,6 +404,10 @@ __global__ void __launch_bounds__(XF ? GEMM_THREADS_XF : GEMM_THREADS, 1) conv_g
                     uint8_t* obuf = out_stage + (obuf_sel & 1) * S::OUT_BUF;
                     ++obuf_sel;
                     if (leader) tma_store_wait_read1();  // the store issued two chunks ago has drained this buffer
+                    if (cc == 0) {   // (readers of the previous tile's bias are past that tile's last barrier)
+#pragma unroll
+                        for (int i = et; i < BN; i += 128) bias_s[i] = __ldg(bias + i);
+                    }
                     named_bar_sync(1, 128);
                     // accumulator -> fp16 staging, 32 columns at a time with the next TMEM load already in flight
                     uint32_t va[32], vb[32];
@@ -410,11 +418,11 @@ __global__ void __launch_bounds__(XF ? GEMM_THREADS_XF : GEMM_THREADS, 1) conv_g
                         tmem_ld_wait();
                         if (l + 1 < OC / 32) tmem_ld32(t_addr + cc * OC + (l + 1) * 32, (l & 1) ? va : vb);
                         uint8_t* unit_base = obuf + (l >> 1) * (GEMM_BM * 128);
-                        const float* bcol = bias + cc * OC + l * 32;
+                        const float* bcol = bias_s + cc * OC + l * 32;
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bcol + q * 8));
-                            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bcol + q * 8 + 4));
+                            const float4 b0 = *reinterpret_cast<const float4*>(bcol + q * 8);
+                            const float4 b1 = *reinterpret_cast<const float4*>(bcol + q * 8 + 4);
                             __half2 h0 = __floats2half2_rn(__uint_as_float(v[q * 8 + 0]) + b0.x, __uint_as_float(v[q * 8 + 1]) + b0.y);
                             __half2 h1 = __floats2half2_rn(__uint_as_float(v[q * 8 + 2]) + b0.z, __uint_as_float(v[q * 8 + 3]) + b0.w);
                             __half2 h2 = __floats2half2_rn(__uint_as_float(v[q * 8 + 4]) + b1.x, __uint_as_float(v[q * 8 + 5]) + b1.y);

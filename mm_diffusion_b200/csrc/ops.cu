@@ -669,6 +669,16 @@ int mmd_q_sample(const float* x_start, const float* noise, const float* coef, in
     return MMD_OK;
 }
 
+int mmd_sample_epilogue(const float* video, unsigned char* out, int64_t n_images, int channels, int64_t hw, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!video || !out || n_images <= 0 || channels <= 0 || hw <= 0) return fail(MMD_EINVAL, "sample_epilogue: bad arguments");
+    const long long total = n_images * hw;
+    const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>((total + 255) / 256, 8LL * num_sms())));
+    sample_epilogue_kernel<<<grid, 256, 0, st>>>(video, out, n_images, channels, static_cast<int>(hw));
+    MMD_CUDA_OK(cudaGetLastError());
+    return MMD_OK;
+}
+
 int mmd_lincomb(int n_terms, const float* const* src, const float* coef, int64_t numel, float* out, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (n_terms < 1 || n_terms > 4 || !src || !coef || !out) return fail(MMD_EINVAL, "lincomb: 1..4 terms, non-null arguments");

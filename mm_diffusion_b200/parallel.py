@@ -29,6 +29,20 @@ def to_uint8_video(video: torch.Tensor) -> torch.Tensor:
     return ((video + 1) * 127.5).clamp(0, 255).to(torch.uint8)
 
 
+def sample_epilogue(video: torch.Tensor) -> torch.Tensor:
+    """The whole video epilogue of the sampling scripts (multimodal_sample_sr.py:159-163) in one kernel: [B,F,C,H,W] float
+    in [-1,1] -> uint8 [B,F,H,W,C] (`((v + 1) * 127.5).clamp(0, 255).to(uint8).permute(0, 1, 3, 4, 2).contiguous()`)."""
+    if not video.is_cuda:
+        return to_uint8_video(video).permute(0, 1, 3, 4, 2).contiguous()
+    from . import _lib
+    B, F, C, H, W = video.shape
+    v = video.detach().to(torch.float32).contiguous()
+    out = torch.empty((B, F, H, W, C), dtype=torch.uint8, device=video.device)
+    with torch.cuda.device(video.device):
+        _lib.check(_lib.load().mmd_sample_epilogue(v.data_ptr(), out.data_ptr(), B * F, C, H * W, _lib.current_stream_ptr()))
+    return out
+
+
 def gather_samples(sample: Dict[str, torch.Tensor], group=None) -> Dict[str, torch.Tensor]:
     """All ranks receive every rank's finished samples concatenated in rank order: uint8 video + fp32 audio
     (≈0.3 MB per sample).  Equal per-rank batch sizes are required (weak scaling: fixed batch per GPU)."""

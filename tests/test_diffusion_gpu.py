@@ -125,3 +125,14 @@ def test_p_sample_loop_api_and_replacement_conditioning(setup):
     out = diff.conditional_p_sample_loop(model, shape, use_fp16=False, model_kwargs={"audio": cond.cuda()},
                                          device=torch.device("cuda"), progress=False, class_scale=3.0)
     assert out["video"].shape == shape["video"] and torch.isfinite(out["video"]).all() and torch.isfinite(out["audio"]).all()
+
+
+def test_sample_epilogue_matches_the_script_conversion():
+    """uint8 + channels-last epilogue of multimodal_sample_sr.py:159-163 in one kernel, byte for byte."""
+    from mm_diffusion_b200.parallel import sample_epilogue
+    g = torch.Generator().manual_seed(5)
+    v = (torch.randn(3, 16, 3, 64, 64, generator=g) * 0.8).cuda()
+    v[0, 0, 0, 0, :4] = torch.tensor([-1.0, 1.0, -3.0, 3.0]).cuda()
+    ref = ((v + 1) * 127.5).clamp(0, 255).to(torch.uint8).permute(0, 1, 3, 4, 2).contiguous()
+    got = sample_epilogue(v)
+    assert got.dtype == torch.uint8 and got.shape == ref.shape and torch.equal(got, ref)
