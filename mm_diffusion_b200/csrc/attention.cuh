@@ -763,6 +763,49 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention64_kernel(const __gri
 // 256 query rows.  Items whose query block has no second tile (<= 128 rows) run with group 1 idle.
 // Same arithmetic as attention64_kernel (shared row-max / probability helpers): results are bit-identical.
 // ===========================================================================
+// Register-resident logit row (128 fp32) of the two-tile kernel: the four TMEM loads are in flight together and the
+// row is read from TMEM once — the separate max / exp passes of attention64_kernel wait for TMEM four times each.
+template <bool FULL>
+MMD_DEVINL float attn64_row_load_max(uint32_t s_addr, int kvalid, uint32_t (&sv)[128]) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        if (FULL || c * 32 < kvalid) tmem_ld32(s_addr + c * 32, &sv[c * 32]);
+    tmem_ld_wait();
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 128; ++i)
+        if (FULL || i < kvalid) mx = fmaxf(mx, __uint_as_float(sv[i]));
+    return mx;
+}
+template <bool FULL, int PQ>
+MMD_DEVINL void attn64_row_write_p(const uint32_t (&sv)[128], int kvalid, float scale_log2, float nm, uint8_t* p_smem, int row) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        if (!FULL && c * 32 >= kvalid) break;
+        uint8_t* chunk = p_smem + (c >> 1) * (ATT_BQ * 128);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint4 pk;
+            uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int col = c * 32 + j * 8 + 2 * k;
+                const float a0 = fmaf(__uint_as_float(sv[col]), scale_log2, nm);
+                const float a1 = fmaf(__uint_as_float(sv[col + 1]), scale_log2, nm);
+                float e0 = ex2_fast(a0);
+                float e1 = (PQ == 2 || (PQ == 1 && (k & 1))) ? ex2_poly(a1) : ex2_fast(a1);
+                if (!FULL) {
+                    if (col >= kvalid) e0 = 0.f;
+                    if (col + 1 >= kvalid) e1 = 0.f;
+                }
+                const __half2 h = __floats2half2_rn(e0, e1);
+                pw[k] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(chunk + sw128_off(row, (c & 1) * 4 + j)) = pk;
+        }
+    }
+}
+
 struct Attn64x2Smem {
     static constexpr int Q_OFF = 0;                       // two query tiles
     static constexpr int K_OFF = 2 * 16384;               // 2 stages
@@ -773,7 +816,11 @@ struct Attn64x2Smem {
     static constexpr int TOTAL = BAR_OFF + 256 + 1024;
     static constexpr int TMEM_COLS = 512;                 // S0 0 | S1 128 | O0 256 | O1 320 | l0 384 | l1 400
 };
-constexpr int ATT2_THREADS = 320;   // warps 0-3: softmax of tile 0, 4-7: softmax of tile 1, 8: TMA, 9: MMA
+constexpr int ATT2_THREADS = 384;   // warps 0-3: softmax of tile 0, 4-7: softmax of tile 1, 8: TMA, 9: MMA, 10-11: idle
+// Three warpgroups so the register file can be re-split (setmaxnreg): the softmax threads hold a whole 128-column logit
+// row in registers, the producer warpgroup needs next to nothing.
+constexpr int ATT2_REGS_SOFTMAX = 208;
+constexpr int ATT2_REGS_PRODUCER = 88;
 
 struct AttnWork2 {
     AttnWork w;      // tile 0 of the pair (q_row0, key segments, head)
@@ -872,6 +919,7 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention64x2_kernel(const __
 
     if (warp == 8) {
         // ===================== TMA producer =====================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ATT2_REGS_PRODUCER));
         if (lane == 0) {
             int n = 0;    // K/V tiles issued so far (all items)
             int it = 0;   // items started
@@ -899,6 +947,7 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention64x2_kernel(const __
         }
     } else if (warp == 9) {
         // ===================== MMA issuer =====================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ATT2_REGS_PRODUCER));
         if (lane == 0) {
             constexpr uint32_t idesc_qk = umma_idesc_f16(ATT_BQ, ATT_BKV, 0, 0);
             const uint64_t qd0 = umma_desc_sw128(smem_u32(smem + S::Q_OFF), 16, 1024);
@@ -973,8 +1022,11 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention64x2_kernel(const __
                 cur = nxt;
             }
         }
+    } else if (warp >= 10) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ATT2_REGS_PRODUCER));   // idle half of the producer warpgroup
     } else {
         // ===================== softmax groups (thread = query row of the group's tile) =====================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(ATT2_REGS_SOFTMAX));
         const int grp = warp >> 2;
         const int wg = warp & 3;
         const int row = wg * 32 + lane;
@@ -1012,7 +1064,8 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention64x2_kernel(const __
                     continue;
                 }
                 const bool full_tile = (kvalid == ATT_BKV);
-                const float mx = full_tile ? attn64_rowmax<true>(s_addr, kvalid) : attn64_rowmax<false>(s_addr, kvalid);
+                uint32_t sv[128];
+                const float mx = full_tile ? attn64_row_load_max<true>(s_addr, kvalid, sv) : attn64_row_load_max<false>(s_addr, kvalid, sv);
                 const float mxs = mx * p.scale_log2;
                 if (t == 0) {
                     m_used = mxs;
@@ -1040,8 +1093,8 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention64x2_kernel(const __
                         tmem_st_wait();
                     }
                 }
-                if (full_tile) attn64_write_p<true, PQ>(s_addr, kvalid, p.scale_log2, -m_used, p_smem, row);
-                else attn64_write_p<false, PQ>(s_addr, kvalid, p.scale_log2, -m_used, p_smem, row);
+                if (full_tile) attn64_row_write_p<true, PQ>(sv, kvalid, p.scale_log2, -m_used, p_smem, row);
+                else attn64_row_write_p<false, PQ>(sv, kvalid, p.scale_log2, -m_used, p_smem, row);
                 fence_proxy_async_smem();
                 tc_fence_before();
                 mbar_arrive(pr);
