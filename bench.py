@@ -219,16 +219,21 @@ KERNEL_OF = {"conv3x3_spatial": "conv_gemm_kernel", "conv1x1_qkv": "conv_gemm_ke
 def ncu_traffic(kernel, batch):
     """Measured DRAM bytes per launch of `kernel` (ncu dram__bytes_read.sum + dram__bytes_write.sum averaged over the
     launches of one forward at this batch), from the committed summary of the capture; None if not captured."""
-    path = os.path.join(ROOT, "profiles", "r01_dram_traffic.json")
-    try:
-        with open(path) as f:
-            t = json.load(f)
-        if t.get("batch") != batch:
-            return None
-        ks = t["kernels"]
-        return (ks.get(kernel) or ks["mmd::" + kernel])["dram_bytes_per_launch"]
-    except Exception:
-        return None
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_dram_traffic.json")), reverse=True):   # latest round first
+        try:
+            with open(path) as f:
+                t = json.load(f)
+            if t.get("batch") != batch:
+                continue
+            ks = t["kernels"]
+            hit = [v for k, v in ks.items() if kernel in k]
+            if hit:
+                n = sum(v.get("launches", 1) for v in hit)
+                return sum(v["dram_bytes_per_launch"] * v.get("launches", 1) for v in hit) / max(n, 1), os.path.basename(path)
+        except Exception:
+            continue
+    return None
 
 
 def family_summary(steps):
@@ -399,7 +404,8 @@ def run_b200(ctx, args, model, diffusion):
         else:
             roof = {"bound": "hbm", "achieved": round(gbs, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": round(gbs / peaks["hbm_gbs"], 4)}
-        traffic = ncu_traffic(dname, B)
+        traffic_src = ncu_traffic(dname, B)
+        traffic, traffic_file = traffic_src if traffic_src else (None, None)
         roof.update({"kernel": dname, "launches_per_step": d["launches"], "share_of_step": round(d["ms"] / fwd_ms, 4),
                      "algorithmic_gflop_per_launch": round(d["flops"] / d["launches"] / 1e9, 3),
                      "algorithmic_mb_per_launch": round(d["bytes"] / d["launches"] / 1e6, 3),
@@ -410,7 +416,7 @@ def run_b200(ctx, args, model, diffusion):
                                                        if tensor_bound else " (copy)"),
                      "traffic": traffic,
                      "traffic_note": "mean dram__bytes_read+write per launch of this kernel over one forward, ncu capture "
-                                     "summarised in profiles/r01_dram_traffic.json" if traffic is not None else None,
+                                     f"summarised in profiles/{traffic_file}" if traffic is not None else None,
                      "how": "sum of the algorithmic FLOPs/bytes of this kernel's launches in one forward / sum of their "
                             f"CUDA-event durations on the launch stream, mean of {args.profile_reps} un-graphed passes "
                             "after the timed region"})

@@ -31,6 +31,7 @@ def sass_by_function():
     ("conv_gemm_kernel", ("UTCHMMA", "UTMALDG", "LDTM", "UTMASTG")),   # implicit-GEMM conv: tcgen05.mma, TMA load / store, TMEM epilogue
     ("conv_wgrad_kernel", ("UTCHMMA", "UTMALDG", "LDTM")),             # weight gradient
     ("attention64_kernel", ("UTCHMMA", "UTMALDG", "LDTM", "STTM")),    # flash attention d = 64 (O rescale in TMEM)
+    ("attention64x2_kernel", ("UTCHMMA", "UTMALDG", "LDTM", "STTM", "USETMAXREG")),   # two query tiles per CTA, register re-split
     ("attention_kernel", ("UTCHMMA", "UTMALDG", "LDTM")),
     ("attn_bwd_kernel", ("UTCHMMA", "UTMALDG", "LDTM")),               # flash attention backward
 ])
@@ -46,3 +47,14 @@ def test_tensor_core_kernels_use_tcgen05_and_tma(sass_by_function, kernel, needs
         missing = [m for m in req if m not in body]
         assert not missing, f"{name}: SASS lacks {missing}"
         assert "HMMA.16816" not in body, f"{name} contains legacy mma.sync"
+
+
+def test_fused_groupnorm_gemm_variant_exists(sass_by_function):
+    """The XF instantiations (GroupNorm apply on the A operand in shared memory) are in the library next to the plain ones,
+    and carry the tanh (SiLU) of the fused out_layers path."""
+    xf = {n: b for n, b in sass_by_function.items() if "conv_gemm_kernel" in n and "ELb1E" in n}
+    plain = {n: b for n, b in sass_by_function.items() if "conv_gemm_kernel" in n and "ELb0E" in n}
+    assert len(xf) >= 5 and len(plain) >= 6, (list(xf), list(plain))
+    for name, body in xf.items():
+        assert "MUFU.TANH" in body and "UTCHMMA" in body, name
+    assert all("MUFU.TANH" not in b for b in plain.values())
