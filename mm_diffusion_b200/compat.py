@@ -22,10 +22,18 @@ _MAP = {
 }
 
 
-def install(force: bool = True):
-    """Alias the hot-path modules under the reference's names; returns the list of names installed."""
+_TAIL = {"mm_diffusion.fp16_util": "mm_diffusion_b200.fp16_util"}
+
+
+def install(force: bool = True, optimizer_tail: bool = False):
+    """Alias the hot-path modules under the reference's names; returns the list of names installed.
+    optimizer_tail=True also aliases `mm_diffusion.fp16_util`: TrainLoop then builds the flat-buffer
+    MixedPrecisionTrainer (one master parameter = the model's flat parameter buffer, one host sync per step)."""
     done = []
-    for ref_name, ours in _MAP.items():
+    mapping = dict(_MAP)
+    if optimizer_tail:
+        mapping.update(_TAIL)
+    for ref_name, ours in mapping.items():
         if ref_name in sys.modules and not force:
             continue
         sys.modules[ref_name] = importlib.import_module(ours)

@@ -298,9 +298,10 @@ class MultimodalUNet(nn.Module):
         if self._handle is not None:
             lib.mmd_model_destroy(self._handle)
             self._handle = None
-        with torch.cuda.device(device):
+        import contextlib
+        with (torch.cuda.device(device) if device.type == "cuda" else contextlib.nullcontext()):
             h = C.c_void_p()
-            check(lib.mmd_model_create(C.byref(self._cfg), C.byref(h)))
+            check(lib.mmd_model_create(C.byref(self._cfg), C.byref(h)))   # host-only until the first forward
         self._handle, self._handle_device = h, device
         self._synced = {}
         self._offsets = None
@@ -336,6 +337,22 @@ class MultimodalUNet(nn.Module):
             p.data = view
         self._flat_params = flat
         return True
+
+    def flatten_for_training(self):
+        """(flat fp32 parameter buffer, names, float offsets, shapes): the parameters re-homed as views of one buffer
+        (see _flatten_parameters).  Used by fp16_util.MixedPrecisionTrainer, whose single master parameter IS this
+        buffer, so the optimizer updates the model in place."""
+        device = next(self.parameters()).device
+        self._ensure_handle(device)
+        self._plist = list(self.parameters())
+        if not self._flat_params_ok() and not self._flatten_parameters(device):
+            raise MmdError("flatten_for_training needs fp32 parameters on one device")
+        return self._flat_params, list(self._param_names), list(self._param_offsets()), [tuple(p.shape) for p in self._plist]
+
+    def mark_parameters_updated(self):
+        """The flat parameter buffer was written directly (optimizer step on the master view): re-send and re-pack at the
+        next forward."""
+        self._needs_sync = True
 
     def _sync_parameters(self):
         lib = _lib.load()
