@@ -370,6 +370,11 @@ __global__ void __launch_bounds__(XF ? GEMM_THREADS_XF : GEMM_THREADS, 1) conv_g
                         fence_proxy_async_smem();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&xf_bar[stage]);
+                    } else {
+                        // untransformed block (skip / residual segment): still observe its phase.  Parity waits are only
+                        // meaningful for a waiter that follows every phase of a stage in order — a warp that skipped ahead
+                        // could see "complete" for a fill that has not even started (TMA loads land out of order).
+                        mbar_wait(&full_bar[stage], phase);
                     }
                     if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
                 }
