@@ -454,8 +454,11 @@ MMD_DEVINL float attn64_rowmax(uint32_t s_addr, int kvalid) {
 
 // p = exp2(s * scale - m) as fp16 into the swizzled P tile (two 64-key chunks).
 // PQ of every 4 consecutive elements take ex2_poly instead of the MUFU op (0, 1 or 2).
+// Returns the largest exponent argument s * scale - m of the valid columns: the streaming path of the kernels uses the
+// running maximum of EARLIER tiles as m and only checks afterwards that nothing came near the fp16 range of P.
 template <bool FULL, int PQ>
-MMD_DEVINL void attn64_write_p(uint32_t s_addr, int kvalid, float scale_log2, float nm, uint8_t* p_smem, int row) {
+MMD_DEVINL float attn64_write_p(uint32_t s_addr, int kvalid, float scale_log2, float nm, uint8_t* p_smem, int row) {
+    float amax = -INFINITY;
     uint32_t va[32], vb[32];
     tmem_ld32(s_addr, va);
 #pragma unroll
@@ -478,8 +481,10 @@ MMD_DEVINL void attn64_write_p(uint32_t s_addr, int kvalid, float scale_log2, fl
                 float e0 = ex2_fast(a0);
                 float e1 = (PQ == 2 || (PQ == 1 && (k & 1))) ? ex2_poly(a1) : ex2_fast(a1);
                 if (!FULL) {
-                    if (col >= kvalid) e0 = 0.f;
-                    if (col + 1 >= kvalid) e1 = 0.f;
+                    if (col >= kvalid) e0 = 0.f; else amax = fmaxf(amax, a0);
+                    if (col + 1 >= kvalid) e1 = 0.f; else amax = fmaxf(amax, a1);
+                } else {
+                    amax = fmaxf(amax, fmaxf(a0, a1));
                 }
                 const __half2 h = __floats2half2_rn(e0, e1);
                 pw[k] = *reinterpret_cast<const uint32_t*>(&h);
@@ -487,7 +492,30 @@ MMD_DEVINL void attn64_write_p(uint32_t s_addr, int kvalid, float scale_log2, fl
             *reinterpret_cast<uint4*>(chunk + sw128_off(row, (c & 1) * 4 + j)) = pk;
         }
     }
+    return amax;
 }
+
+// Rescale the O / l accumulators of this thread's row in TMEM by alpha (the running maximum moved).
+MMD_DEVINL void attn64_rescale(uint32_t tmem_O, uint32_t tmem_L, uint32_t lane_base, float alpha) {
+    uint32_t o[32];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        tmem_ld32(tmem_O + lane_base + c * 32, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+        tmem_st32(tmem_O + lane_base + c * 32, o);
+    }
+    tmem_ld16(tmem_L + lane_base, o);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+    tmem_st16(tmem_L + lane_base, o);
+    tmem_st_wait();
+}
+
+// Largest exponent the streaming pass may produce: P is fp16 (max 65504 = 2^15.999), sums and O are fp32.
+constexpr float ATT_STREAM_LIMIT = 14.0f;
 
 template <int PQ>
 __global__ void __launch_bounds__(ATT_THREADS, 2) attention64_kernel(const __grid_constant__ AttnParams p, int n_items) {
@@ -678,38 +706,27 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention64_kernel(const __gri
                     continue;
                 }
                 const bool full_tile = (kvalid == ATT_BKV);
-                // ---- pass 1: row maximum
-                const float mx = full_tile ? attn64_rowmax<true>(s_addr, kvalid) : attn64_rowmax<false>(s_addr, kvalid);
-                const float mxs = mx * p.scale_log2;
+                // First tile of an item: the true row maximum has to be known before any exponential (a max pass, then the
+                // probability pass).  Later tiles: ONE streaming pass over the logits (TMEM reads, 64 B/clk/SM, cost as much
+                // as the exponentials) — the probabilities are taken against the running maximum of the EARLIER tiles (P is
+                // fp16 and O / l are fp32, so exponents up to 2^14 are harmless), and only if a row overshoots that range
+                // (rare after the first tile) the accumulators are rescaled and the pass is repeated.
                 if (t == 0) {
-                    m_used = mxs;
+                    const float mx = full_tile ? attn64_rowmax<true>(s_addr, kvalid) : attn64_rowmax<false>(s_addr, kvalid);
+                    m_used = mx * p.scale_log2;
                 } else {
                     mbar_wait(o_full, (g - 1) & 1);   // P·V of the previous tile is done: P and O may be touched
                     tc_fence_after();
-                    if (__any_sync(0xffffffffu, mxs > m_used + 8.0f)) {
-                        const float m_new = fmaxf(m_used, mxs);
-                        const float alpha = ex2_fast(m_used - m_new);
-                        m_used = m_new;
-                        uint32_t o[32];
-#pragma unroll
-                        for (int c = 0; c < 2; ++c) {
-                            tmem_ld32(tmem_O + lane_base + c * 32, o);
-                            tmem_ld_wait();
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                            tmem_st32(tmem_O + lane_base + c * 32, o);
-                        }
-                        tmem_ld16(tmem_L + lane_base, o);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                        tmem_st16(tmem_L + lane_base, o);
-                        tmem_st_wait();
-                    }
                 }
-                // ---- pass 2: probabilities (fp16) -> shared memory
-                if (full_tile) attn64_write_p<true, PQ>(s_addr, kvalid, p.scale_log2, -m_used, p_smem, row);
-                else attn64_write_p<false, PQ>(s_addr, kvalid, p.scale_log2, -m_used, p_smem, row);
+#pragma unroll 1
+                for (int attempt = 0; attempt < 2; ++attempt) {
+                    const float amax = full_tile ? attn64_write_p<true, PQ>(s_addr, kvalid, p.scale_log2, -m_used, p_smem, row)
+                                                 : attn64_write_p<false, PQ>(s_addr, kvalid, p.scale_log2, -m_used, p_smem, row);
+                    if (t == 0 || attempt == 1 || !__any_sync(0xffffffffu, amax > ATT_STREAM_LIMIT)) break;
+                    const float m_new = m_used + fmaxf(amax, 0.f);
+                    attn64_rescale(tmem_O, tmem_L, lane_base, ex2_fast(m_used - m_new));
+                    m_used = m_new;
+                }
                 fence_proxy_async_smem();
                 tc_fence_before();
                 mbar_arrive(p_ready);
@@ -1064,37 +1081,24 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention64x2_kernel(const __
                     continue;
                 }
                 const bool full_tile = (kvalid == ATT_BKV);
-                uint32_t sv[128];
-                const float mx = full_tile ? attn64_row_load_max<true>(s_addr, kvalid, sv) : attn64_row_load_max<false>(s_addr, kvalid, sv);
-                const float mxs = mx * p.scale_log2;
+                // first tile: max pass + probability pass; later tiles: one streaming pass against the running maximum of the
+                // earlier tiles, repeated after a rescale in the rare case a row overshoots (see attention64_kernel)
                 if (t == 0) {
-                    m_used = mxs;
+                    const float mx = full_tile ? attn64_rowmax<true>(s_addr, kvalid) : attn64_rowmax<false>(s_addr, kvalid);
+                    m_used = mx * p.scale_log2;
                 } else {
                     mbar_wait(of, (g - 1) & 1);   // P·V of the previous tile is done: P and O may be touched
                     tc_fence_after();
-                    if (__any_sync(0xffffffffu, mxs > m_used + 8.0f)) {
-                        const float m_new = fmaxf(m_used, mxs);
-                        const float alpha = ex2_fast(m_used - m_new);
-                        m_used = m_new;
-                        uint32_t o[32];
-#pragma unroll
-                        for (int c = 0; c < 2; ++c) {
-                            tmem_ld32(tmem_O + lane_base + c * 32, o);
-                            tmem_ld_wait();
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                            tmem_st32(tmem_O + lane_base + c * 32, o);
-                        }
-                        tmem_ld16(tmem_L + lane_base, o);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                        tmem_st16(tmem_L + lane_base, o);
-                        tmem_st_wait();
-                    }
                 }
-                if (full_tile) attn64_row_write_p<true, PQ>(sv, kvalid, p.scale_log2, -m_used, p_smem, row);
-                else attn64_row_write_p<false, PQ>(sv, kvalid, p.scale_log2, -m_used, p_smem, row);
+#pragma unroll 1
+                for (int attempt = 0; attempt < 2; ++attempt) {
+                    const float amax = full_tile ? attn64_write_p<true, PQ>(s_addr, kvalid, p.scale_log2, -m_used, p_smem, row)
+                                                 : attn64_write_p<false, PQ>(s_addr, kvalid, p.scale_log2, -m_used, p_smem, row);
+                    if (t == 0 || attempt == 1 || !__any_sync(0xffffffffu, amax > ATT_STREAM_LIMIT)) break;
+                    const float m_new = m_used + fmaxf(amax, 0.f);
+                    attn64_rescale(tmem_O, tmem_L, lane_base, ex2_fast(m_used - m_new));
+                    m_used = m_new;
+                }
                 fence_proxy_async_smem();
                 tc_fence_before();
                 mbar_arrive(pr);

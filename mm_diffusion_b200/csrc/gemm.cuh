@@ -137,6 +137,12 @@ __global__ void __launch_bounds__(XF ? GEMM_THREADS_XF : GEMM_THREADS, 1) conv_g
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int total_tiles = p.m_tiles * p.n_tiles;
+    // Tile schedule of this CTA.  Plain kernels: strided (tile = blockIdx.x + i * gridDim.x): the N tiles of one row block
+    // run at the same time on neighbouring CTAs and share the A tile through L2.  XF kernels: a contiguous range, so a CTA
+    // stays inside one GroupNorm domain for many tiles and rebuilds its affine table once or twice instead of per tile.
+    const int tile_begin = XF ? static_cast<int>(static_cast<long long>(blockIdx.x) * total_tiles / gridDim.x) : static_cast<int>(blockIdx.x);
+    const int tile_end = XF ? static_cast<int>(static_cast<long long>(blockIdx.x + 1) * total_tiles / gridDim.x) : total_tiles;
+    const int tile_step = XF ? 1 : static_cast<int>(gridDim.x);
     int total_chunks = 0;
     for (int s = 0; s < p.n_src; ++s) total_chunks += p.src_chunks[s];
     const int num_kb = p.n_taps * total_chunks;
@@ -174,8 +180,8 @@ __global__ void __launch_bounds__(XF ? GEMM_THREADS_XF : GEMM_THREADS, 1) conv_g
             // Weights are constants of the plan, activations come from the previous kernel: the B halves of the first
             // pipeline stages are requested before the grid dependency resolves, the A halves after it.
             int pre = 0;
-            if (static_cast<int>(blockIdx.x) < total_tiles) {
-                const int n_idx0 = blockIdx.x % p.n_tiles;
+            if (tile_begin < tile_end) {
+                const int n_idx0 = tile_begin % p.n_tiles;
                 pre = min(S::STAGES, num_kb);
                 for (int kb = 0; kb < pre; ++kb) {
                     mbar_expect_tx(&full_bar[kb], S::STAGE_BYTES);
@@ -187,8 +193,8 @@ __global__ void __launch_bounds__(XF ? GEMM_THREADS_XF : GEMM_THREADS, 1) conv_g
             // is paired with the prefetch of the same k-block pf_tiles tiles ahead
             const int pf = p.pf_tiles;
             for (int d = 1; d < pf; ++d) {
-                const int tile = blockIdx.x + d * gridDim.x;
-                if (tile >= total_tiles) break;
+                const int tile = tile_begin + d * tile_step;
+                if (tile >= tile_end) break;
                 int org[5];
                 gemm_tile_origin(p, tile / p.n_tiles, org);
                 for (int t = 0; t < p.n_taps; ++t) {
@@ -203,13 +209,13 @@ __global__ void __launch_bounds__(XF ? GEMM_THREADS_XF : GEMM_THREADS, 1) conv_g
             int stage = 0;
             uint32_t phase = 0;
             int gk = 0;   // k-blocks issued by this CTA (the first `pre` already have their B half in flight)
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
                 const int m_idx = tile / p.n_tiles;
                 const int n_idx = tile - m_idx * p.n_tiles;
                 int org[5];
                 gemm_tile_origin(p, m_idx, org);
-                const int pf_tile = tile + pf * static_cast<int>(gridDim.x);
-                const bool pf_on = pf > 0 && pf_tile < total_tiles;
+                const int pf_tile = tile + pf * tile_step;
+                const bool pf_on = pf > 0 && pf_tile < tile_end;
                 int porg[5] = {0, 0, 0, 0, 0};
                 if (pf_on) gemm_tile_origin(p, pf_tile / p.n_tiles, porg);
                 int kb = 0;
@@ -244,22 +250,17 @@ __global__ void __launch_bounds__(XF ? GEMM_THREADS_XF : GEMM_THREADS, 1) conv_g
             constexpr uint32_t idesc = umma_idesc_f16(GEMM_BM, BN, 0, 0);
             int stage = 0;
             uint32_t phase = 0;
-            uint32_t xf_bits = 0;   // per-stage phase parity of xf_bar (a stage's xf barrier only cycles when it held a transformed block)
-            const int xf_chunks = (XF && p.xf_sums != nullptr) ? p.src_chunks[0] : 0;   // pointwise: the first k-blocks of a tile
             int it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++it) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    if (XF && kb < xf_chunks) {
-                        mbar_wait(&xf_bar[stage], (xf_bits >> stage) & 1u);
-                        xf_bits ^= 1u << stage;
-                    } else {
-                        mbar_wait(&full_bar[stage], phase);
-                    }
+                    // XF kernels: every k-block is handed over by the transform warps (they wait for the TMA, transform the
+                    // blocks of source 0 and pass the others through), so all roles follow the ring in lock-step
+                    mbar_wait(XF ? &xf_bar[stage] : &full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(stage_base + stage * S::STAGE_BYTES);
                     // one descriptor per operand and k-iteration; the 16-element k-steps only bump the 16-byte-unit
@@ -296,7 +297,7 @@ __global__ void __launch_bounds__(XF ? GEMM_THREADS_XF : GEMM_THREADS, 1) conv_g
             int stage = 0;
             uint32_t phase = 0;
             int cached_dom = -1;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
                 const int m_idx = tile / p.n_tiles;
                 int org[5];
                 gemm_tile_origin(p, m_idx, org);
@@ -368,14 +369,15 @@ __global__ void __launch_bounds__(XF ? GEMM_THREADS_XF : GEMM_THREADS, 1) conv_g
                             *ptr = raw;
                         }
                         fence_proxy_async_smem();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&xf_bar[stage]);
                     } else {
-                        // untransformed block (skip / residual segment): still observe its phase.  Parity waits are only
-                        // meaningful for a waiter that follows every phase of a stage in order — a warp that skipped ahead
-                        // could see "complete" for a fill that has not even started (TMA loads land out of order).
+                        // untransformed block (skip / residual segment): passed through.  A parity wait is only meaningful
+                        // for a waiter that follows every phase of a stage — skipping blocks here either lets the warp run
+                        // ahead of a fill that has not started or fall two phases behind one that has — so every block is
+                        // waited for and handed on.
                         mbar_wait(&full_bar[stage], phase);
                     }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&xf_bar[stage]);
                     if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -388,7 +390,7 @@ __global__ void __launch_bounds__(XF ? GEMM_THREADS_XF : GEMM_THREADS, 1) conv_g
         const bool leader = (et == 0);
         int it = 0;
         uint32_t obuf_sel = 0;   // staging buffer rotation (leader's bulk-group order matches it)
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             const int m_idx = tile / p.n_tiles;
