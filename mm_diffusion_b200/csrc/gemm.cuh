@@ -32,6 +32,7 @@ constexpr int GEMM_XF_MAXC = 512;  // widest source the fused GroupNorm apply su
 struct alignas(64) GemmParams {
     CUtensorMap a_map[GEMM_MAX_SRC];  // activation sources, rank `rank`, box (64, box[0..3])
     CUtensorMap b_map;                // packed weights [N, K_total] (K-major), box (64, BN)
+    CUtensorMap b2_map;               // same tensor, box (64, BN / 2): one CTA's half of the tile in the pair kernel (gemm2.cuh)
     CUtensorMap o_map;                // output, same geometry as A (out_mode 0)
     int n_src;
     int src_chunks[GEMM_MAX_SRC];     // 64-channel chunks per source

@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
+#include "gemm2.cuh"
 #include "wgrad.cuh"
 
 namespace mmd {

@@ -133,6 +133,10 @@ int build_gemm(const GemmProblem& pr, GemmParams* out) {
     str[0] = kt * sizeof(act_t);
     box[0] = GEMM_BK; box[1] = bn;
     MMD_TRY(encode_tmap(&p.b_map, pr.w, 2, dims, str, box));
+    if (bn >= 128) {   // half-tile boxes for the CTA-pair kernel
+        box[1] = bn / 2;
+        MMD_TRY(encode_tmap(&p.b2_map, pr.w, 2, dims, str, box));
+    }
     p.m_tiles = static_cast<int>(m_tiles);
     p.n_tiles = pr.n_pad() / bn;
     p.bias = pr.bias;
@@ -217,6 +221,10 @@ int gemm_init_attrs() {
     MMD_TRY((gemm_attr<128, 64, true>()));
     MMD_TRY((gemm_attr<128, 128, true>()));
     MMD_TRY((gemm_attr<64, 64, true>()));
+    MMD_CUDA_OK(cudaFuncSetAttribute(conv_gemm2_kernel<256, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Smem<256, 64>::TOTAL));
+    MMD_CUDA_OK(cudaFuncSetAttribute(conv_gemm2_kernel<256, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Smem<256, 128>::TOTAL));
+    MMD_CUDA_OK(cudaFuncSetAttribute(conv_gemm2_kernel<128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Smem<128, 64>::TOTAL));
+    MMD_CUDA_OK(cudaFuncSetAttribute(conv_gemm2_kernel<128, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Smem<128, 128>::TOTAL));
     done = true;
     return MMD_OK;
 }
@@ -267,6 +275,21 @@ int launch_gemm(const GemmParams& p, int bn, cudaStream_t st) {
         else if (bn == 128) MMD_GEMM_CASE(128, 128, true);
         else if (bn == 64) MMD_GEMM_CASE(64, 64, true);
         else return fail(MMD_EINVAL, "fused GroupNorm apply: unsupported BN %d", bn);
+        return MMD_OK;
+    }
+    // CTA-pair kernel (tcgen05.mma.cta_group::2): 256-token x BN tiles, the weight tile split across the two CTAs.
+    // MMD_GEMM2 bitmask: 1 = BN 256, 2 = BN 128.
+    static const int pair_mask = [] { const char* e = getenv("MMD_GEMM2"); return e ? atoi(e) : 0; }();
+    if (p.out_mode == 0 && ((bn == 256 && (pair_mask & 1)) || (bn == 128 && (pair_mask & 2))) && p.m_tiles >= 2) {
+        const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
+        const int g2 = 2 * std::min(pairs, num_sms() / 2);
+#define MMD_GEMM2_CASE(BN_, OC_) \
+    MMD_CUDA_OK(launch_kernel(conv_gemm2_kernel<BN_, OC_>, g2, GEMM_THREADS, Gemm2Smem<BN_, OC_>::TOTAL, st, p))
+        if (bn == 256 && oc == 64) MMD_GEMM2_CASE(256, 64);
+        else if (bn == 256) MMD_GEMM2_CASE(256, 128);
+        else if (oc == 64) MMD_GEMM2_CASE(128, 64);
+        else MMD_GEMM2_CASE(128, 128);
+#undef MMD_GEMM2_CASE
         return MMD_OK;
     }
     if (bn == 256 && oc == 64) MMD_GEMM_CASE(256, 64, false);

@@ -29,6 +29,7 @@ def sass_by_function():
 
 @pytest.mark.parametrize("kernel,needs", [
     ("conv_gemm_kernel", ("UTCHMMA", "UTMALDG", "LDTM", "UTMASTG")),   # implicit-GEMM conv: tcgen05.mma, TMA load / store, TMEM epilogue
+    ("conv_gemm2_kernel", ("UTCHMMA.2CTA", "UTMALDG", "2CTA", "LDTM", "UTMASTG", "UTCBAR.2CTA.MULTICAST")),   # CTA-pair variant (cta_group::2)
     ("conv_wgrad_kernel", ("UTCHMMA", "UTMALDG", "LDTM")),             # weight gradient
     ("attention64_kernel", ("UTCHMMA", "UTMALDG", "LDTM", "STTM")),    # flash attention d = 64 (O rescale in TMEM)
     ("attention64x2_kernel", ("UTCHMMA", "UTMALDG", "LDTM", "STTM", "USETMAXREG")),   # two query tiles per CTA, register re-split
