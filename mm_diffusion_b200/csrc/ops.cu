@@ -341,6 +341,7 @@ int launch_attn(const AttnParams& p, int d, cudaStream_t st) {
         MMD_CUDA_OK(cudaFuncSetAttribute(attention64_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64Smem::TOTAL));
         MMD_CUDA_OK(cudaFuncSetAttribute(attention64_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64Smem::TOTAL));
         MMD_CUDA_OK(cudaFuncSetAttribute(attention64_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64Smem::TOTAL));
+        MMD_CUDA_OK(cudaFuncSetAttribute(attention64p_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64pSmem::TOTAL));
         MMD_CUDA_OK(cudaFuncSetAttribute(attention64x2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64x2Smem::TOTAL));
         MMD_CUDA_OK(cudaFuncSetAttribute(attention64x2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64x2Smem::TOTAL));
         MMD_CUDA_OK(cudaFuncSetAttribute(attention64x2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64x2Smem::TOTAL));
@@ -354,7 +355,11 @@ int launch_attn(const AttnParams& p, int d, cudaStream_t st) {
     static const bool pair64 = [] { const char* e = getenv("MMD_ATTN_PAIR"); return e ? e[0] == '1' : false; }();
     // MMD_ATTN_POLY = 0 / 1 / 2 of every 4 exponentials on the FMA pipe (cubic Cody-Waite) instead of the MUFU unit
     static const int poly = [] { const char* e = getenv("MMD_ATTN_POLY"); const int v = e ? atoi(e) : 0; return v < 0 ? 0 : (v > 2 ? 2 : v); }();
-    if (d == 64 && !generic64 && pair64 && p.q_tiles >= 2) {
+    // software-pipelined variant: one CTA per SM, S / P / K / V / Q double buffered, Q·K^T issued two tiles ahead
+    static const bool pipe64 = [] { const char* e = getenv("MMD_ATTN_PIPE"); return e ? e[0] == '1' : false; }();
+    if (d == 64 && !generic64 && pipe64) {
+        MMD_CUDA_OK(launch_kernel(attention64p_kernel<0>, std::min(grid, num_sms()), ATT_THREADS, Attn64pSmem::TOTAL, st, p, grid));
+    } else if (d == 64 && !generic64 && pair64 && p.q_tiles >= 2) {
         const int q_pairs = (p.q_tiles + 1) / 2;
         const int items = p.B * p.n_blocks * p.heads * q_pairs;
         const int g2 = std::min(items, num_sms());

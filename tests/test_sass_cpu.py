@@ -33,6 +33,7 @@ def sass_by_function():
     ("conv_wgrad_kernel", ("UTCHMMA", "UTMALDG", "LDTM")),             # weight gradient
     ("attention64_kernel", ("UTCHMMA", "UTMALDG", "LDTM", "STTM")),    # flash attention d = 64 (O rescale in TMEM)
     ("attention64x2_kernel", ("UTCHMMA", "UTMALDG", "LDTM", "STTM", "USETMAXREG")),   # two query tiles per CTA, register re-split
+    ("attention64p_kernel", ("UTCHMMA", "UTMALDG", "LDTM", "STTM")),   # software-pipelined: S / P double buffered
     ("attention_kernel", ("UTCHMMA", "UTMALDG", "LDTM")),
     ("attn_bwd_kernel", ("UTCHMMA", "UTMALDG", "LDTM")),               # flash attention backward
 ])
