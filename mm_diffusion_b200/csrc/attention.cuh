@@ -866,8 +866,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention64p_kernel(const __gr
     uint64_t* v_empty = bars + 10;   // 2
     uint64_t* s_full = bars + 12;    // 2 (one per S buffer)
     uint64_t* o_full = bars + 14;    // 2 (one per P buffer: P·V of the tile that used it has retired)
-    uint64_t* p_ready = bars + 16;   // 1 (128 arrivals)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+    uint64_t* p_ready = bars + 16;   // 2 (128 arrivals each; by tile parity: a fast warp may be one tile ahead of a slow one,
+                                     //    its arrival must not count towards the previous tile's phase)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -887,7 +888,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention64p_kernel(const __gr
             mbar_init(&s_full[i], 1);
             mbar_init(&o_full[i], 1);
         }
-        mbar_init(p_ready, 128);
+        mbar_init(&p_ready[0], 128);
+        mbar_init(&p_ready[1], 128);
         fence_mbar_init();
     }
     for (int i = threadIdx.x; i < 4096 / 16; i += ATT_THREADS)
@@ -966,7 +968,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention64p_kernel(const __gr
                 int krow, kvalid;
                 attn_tile(cp.w, cp.t, krow, kvalid);
                 const int st = np & 1;
-                mbar_wait(p_ready, np & 1);
+                mbar_wait(&p_ready[st], (np >> 1) & 1);
                 mbar_wait(&v_full[st], (np >> 1) & 1);
                 tc_fence_after();
                 attn64_issue_pv(tmem_O, tmem_L, pd0 + static_cast<uint64_t>(st) * (32768 >> 4),
@@ -1022,7 +1024,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention64p_kernel(const __gr
                     fence_proxy_async_smem();
                 }
                 tc_fence_before();
-                mbar_arrive(p_ready);
+                mbar_arrive(&p_ready[sb]);
             }
             // ---- item epilogue: O / l -> global (the next item's first P·V waits for our next p_ready arrival)
             mbar_wait(&o_full[(n - 1) & 1], ((n - 1) >> 1) & 1);

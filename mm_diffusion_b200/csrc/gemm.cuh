@@ -76,6 +76,9 @@ struct alignas(64) GemmParams {
     // the bytes in flight against DRAM latency, not by the tensor pipe; prefetching the tiles this CTA will load a
     // few iterations from now turns the pipeline's TMA loads into L2 hits.
     int pf_tiles;
+    // measurement only (MMD_GEMM_DBG, results are wrong when set): ablation switches that locate the bound of a shape —
+    // 1: no global store of the output, 2: no TMEM -> shared conversion, 4: no MMA issue, 8: no A loads, 16: no B loads
+    int dbg;
 };
 
 template <int BN, int OC, bool XF = false>
@@ -183,7 +186,7 @@ __global__ void __launch_bounds__(XF ? GEMM_THREADS_XF : GEMM_THREADS, 1) conv_g
             int pre = 0;
             if (tile_begin < tile_end) {
                 const int n_idx0 = tile_begin % p.n_tiles;
-                pre = min(S::STAGES, num_kb);
+                pre = (p.dbg & 24) ? 0 : min(S::STAGES, num_kb);
                 for (int kb = 0; kb < pre; ++kb) {
                     mbar_expect_tx(&full_bar[kb], S::STAGE_BYTES);
                     tma_load_2d(stage_base + kb * S::STAGE_BYTES + S::A_BYTES, &p.b_map, &full_bar[kb], kb * GEMM_BK, n_idx0 * BN);
@@ -235,6 +238,18 @@ __global__ void __launch_bounds__(XF ? GEMM_THREADS_XF : GEMM_THREADS, 1) conv_g
                             }
                             mbar_wait(&empty_bar[stage], phase ^ 1);
                             uint8_t* a_dst = stage_base + stage * S::STAGE_BYTES;
+                            if (p.dbg & 24) {   // ablation: drop the A and / or B loads
+                                const uint32_t bytes = ((p.dbg & 8) ? 0 : S::A_BYTES) + ((p.dbg & 16) ? 0 : S::B_BYTES);
+                                if (bytes == 0) { mbar_arrive(&full_bar[stage]); }
+                                else {
+                                    mbar_expect_tx(&full_bar[stage], bytes);
+                                    c[0] = ch * GEMM_BK;
+                                    if (!(p.dbg & 8)) tma_load_nd(p.rank, a_dst, &p.a_map[s], &full_bar[stage], c);
+                                    if (!(p.dbg & 16)) tma_load_2d(a_dst + S::A_BYTES, &p.b_map, &full_bar[stage], kb * GEMM_BK, n_idx * BN);
+                                }
+                                if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
+                                continue;
+                            }
                             if (gk >= pre) mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
                             c[0] = ch * GEMM_BK;
                             tma_load_nd(p.rank, a_dst, &p.a_map[s], &full_bar[stage], c);
@@ -268,9 +283,11 @@ __global__ void __launch_bounds__(XF ? GEMM_THREADS_XF : GEMM_THREADS, 1) conv_g
                     // start-address field (+32 bytes = +2), keeping the single issuing thread off the critical path
                     const uint64_t ad0 = umma_desc_sw128(a_addr, 16, 1024);
                     const uint64_t bd0 = umma_desc_sw128(a_addr + S::A_BYTES, 16, 1024);
+                    if (!(p.dbg & 4)) {
 #pragma unroll
-                    for (int k = 0; k < GEMM_BK / 16; ++k)
-                        umma_f16_ss(d_tmem, ad0 + 2 * k, bd0 + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < GEMM_BK / 16; ++k)
+                            umma_f16_ss(d_tmem, ad0 + 2 * k, bd0 + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
                     umma_commit(&empty_bar[stage]);
                     if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -419,9 +436,10 @@ __global__ void __launch_bounds__(XF ? GEMM_THREADS_XF : GEMM_THREADS, 1) conv_g
                     named_bar_sync(1, 128);
                     // accumulator -> fp16 staging, 32 columns at a time with the next TMEM load already in flight
                     uint32_t va[32], vb[32];
-                    tmem_ld32(t_addr + cc * OC, va);
+                    if (!(p.dbg & 2)) tmem_ld32(t_addr + cc * OC, va);
 #pragma unroll
                     for (int l = 0; l < OC / 32; ++l) {
+                        if (p.dbg & 2) break;
                         uint32_t* v = (l & 1) ? vb : va;
                         tmem_ld_wait();
                         if (l + 1 < OC / 32) tmem_ld32(t_addr + cc * OC + (l + 1) * 32, (l & 1) ? va : vb);
@@ -450,7 +468,7 @@ __global__ void __launch_bounds__(XF ? GEMM_THREADS_XF : GEMM_THREADS, 1) conv_g
                     }
                     fence_proxy_async_smem();
                     named_bar_sync(1, 128);
-                    if (leader) {
+                    if (leader && !(p.dbg & 1)) {
                         int c[5] = {0, org[1], org[2], org[3], org[4]};
 #pragma unroll
                         for (int u = 0; u < S::UNITS; ++u) {

@@ -191,6 +191,10 @@ int build_gemm(const GemmProblem& pr, GemmParams* out) {
         for (int i = 0; i < 4; ++i) p.xf_mul[i] = pr.xf_mul[i];
         p.xf_div = pr.xf_div;
     }
+    {
+        static const int dbg = [] { const char* e = getenv("MMD_GEMM_DBG"); return e ? atoi(e) : 0; }();
+        p.dbg = dbg;
+    }
     {   // L2 prefetch distance: short-K GEMMs only (K-heavy ones re-read their taps from L2 anyway)
         // measured on B200 (round 2): prefetching 16 k-blocks ahead makes the step 3 % SLOWER (12.64 -> 13.01 ms) — the
         // short-K GEMMs are not bound by DRAM latency x bytes in flight after all — so it is off unless MMD_PF_KB is set
