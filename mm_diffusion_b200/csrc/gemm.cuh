@@ -25,8 +25,11 @@ constexpr int GEMM_BM = 128;       // tokens per tile (UMMA M)
 constexpr int GEMM_BK = 64;        // channels per k-iteration (one 128-byte swizzle atom)
 constexpr int GEMM_MAX_SRC = 4;
 constexpr int GEMM_MAX_TAPS = 27;
-constexpr int GEMM_THREADS = 192;  // warp0 TMA, warp1 MMA, warps2-5 epilogue
-constexpr int GEMM_THREADS_XF = 320;  // + warps6-9: A-operand transform (fused GroupNorm apply)
+// warp0 TMA, warp1 MMA, then EG epilogue warpgroups of four warps (EG = 2: the two groups take alternate tiles of the
+// CTA, one per TMEM accumulator stage, so two tiles drain at the same time — the short-K GEMMs are bound by the
+// epilogue, not by the tensor pipe or the loads), then (XF) four warps that transform the A operand (fused GroupNorm apply)
+constexpr int gemm_threads(int eg, bool xf) { return 64 + 128 * eg + (xf ? 128 : 0); }
+constexpr int GEMM_THREADS = gemm_threads(1, false);   // the pair kernel (gemm2.cuh) keeps one epilogue warpgroup
 constexpr int GEMM_XF_MAXC = 512;  // widest source the fused GroupNorm apply supports
 
 struct alignas(64) GemmParams {
@@ -81,7 +84,7 @@ struct alignas(64) GemmParams {
     int dbg;
 };
 
-template <int BN, int OC, bool XF = false>
+template <int BN, int OC, bool XF = false, int EG = 1>
 struct GemmSmem {
     static constexpr int A_BYTES = GEMM_BM * 128;
     static constexpr int B_BYTES = BN * 128;
@@ -91,13 +94,14 @@ struct GemmSmem {
     static constexpr int NCHUNK = (BN >= 64) ? BN / OC : 0;
     static constexpr int UNITS = OC / 64;
     static constexpr int OUT_BUF = UNITS * GEMM_BM * 128;
-    static constexpr int OUT_BYTES = (BN >= 64) ? 2 * OUT_BUF : 0;
+    static constexpr int OUT_BYTES = (BN >= 64) ? EG * 2 * OUT_BUF : 0;   // per epilogue warpgroup
     // barriers (256 B) | GroupNorm partials [BN/64 units][4 bands][16 quads][2] floats
-    static constexpr int GN_BYTES = (BN >= 64) ? (BN / 64) * 4 * 16 * 2 * 4 : 0;
+    static constexpr int GN_ONE = (BN >= 64) ? (BN / 64) * 4 * 16 * 2 * 4 : 0;
+    static constexpr int GN_BYTES = EG * GN_ONE;
     // XF: per-channel affine table [2 domains][a|b][GEMM_XF_MAXC] floats + group mean / rstd [2][32][2]
     // this tile's bias [BN] floats (epilogue reads it from shared memory: the global loads sat on its critical path)
     static constexpr int BIAS_OFF = 256 + GN_BYTES;
-    static constexpr int BIAS_BYTES = (BN >= 64) ? BN * 4 : 0;
+    static constexpr int BIAS_BYTES = (BN >= 64) ? EG * BN * 4 : 0;
     static constexpr int XF_OFF = BIAS_OFF + BIAS_BYTES;
     static constexpr int XF_BYTES = XF ? (2 * 2 * GEMM_XF_MAXC * 4 + 512) : 0;
     static constexpr int BAR_BYTES = 256 + GN_BYTES + BIAS_BYTES + XF_BYTES;
@@ -122,9 +126,10 @@ MMD_DEVINL void gemm_tile_origin(const GemmParams& p, int m_idx, int* c /*[5]*/)
     c[0] = 0;
 }
 
-template <int BN, int OC, bool XF>
-__global__ void __launch_bounds__(XF ? GEMM_THREADS_XF : GEMM_THREADS, 1) conv_gemm_kernel(const __grid_constant__ GemmParams p) {
-    using S = GemmSmem<BN, OC, XF>;
+template <int BN, int OC, bool XF, int EG>
+__global__ void __launch_bounds__(gemm_threads(EG, XF), 1) conv_gemm_kernel(const __grid_constant__ GemmParams p) {
+    using S = GemmSmem<BN, OC, XF, EG>;
+    static_assert(EG == 1 || EG == 2, "one or two epilogue warpgroups");
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* stage_base = smem;
     uint8_t* out_stage = smem + S::STAGES * S::STAGE_BYTES;
@@ -294,7 +299,7 @@ __global__ void __launch_bounds__(XF ? GEMM_THREADS_XF : GEMM_THREADS, 1) conv_g
                 umma_commit(&tfull_bar[acc]);
             }
         }
-    } else if (XF && warp >= 6) {
+    } else if (XF && warp >= 2 + 4 * EG) {
         // ================= A-operand transform (4 warps): fused GroupNorm apply (+FiLM, +SiLU) on source 0 =================
         // thread = (16-byte column unit `oct` of the 128-byte row, group of 8 rows `rg`): a warp touches four complete
         // rows per access (conflict-free in the 128-byte swizzle), and every thread needs just 8 channels of the affine
@@ -303,7 +308,7 @@ __global__ void __launch_bounds__(XF ? GEMM_THREADS_XF : GEMM_THREADS, 1) conv_g
         if (p.xf_sums != nullptr) {
             float* xf_coef = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + S::XF_OFF);   // [dl][a|b][c]
             float* xf_gstat = xf_coef + 2 * 2 * GEMM_XF_MAXC;                                          // [dl][32][mean|rstd]
-            const int tt = threadIdx.x - 192;           // 0..127
+            const int tt = threadIdx.x - (64 + 128 * EG);   // 0..127
             const int oct = tt & 7, rg = tt >> 3;
             const int C = p.xf_c;
             const int cpg = C / 32;
@@ -404,21 +409,33 @@ __global__ void __launch_bounds__(XF ? GEMM_THREADS_XF : GEMM_THREADS, 1) conv_g
         // ================= epilogue (4 warps, thread = accumulator row) =================
         const int quad = warp & 3;
         const int row = quad * 32 + lane;
-        const int et = threadIdx.x - 64;   // 0..127
+        const int eg = (warp - 2) >> 2;            // epilogue warpgroup: with EG = 2 group g drains accumulator stage g
+        const int et = (threadIdx.x - 64) & 127;   // 0..127 inside the group
         const bool leader = (et == 0);
+        const int ebar = 1 + 2 * eg;               // named barrier of this group (2 belongs to the transform warps)
+        uint8_t* const out_stage_g = out_stage + eg * 2 * S::OUT_BUF;
+        float* const gn_part_g = gn_part + eg * (S::GN_ONE / 4);
+        float* const bias_g = bias_s + eg * BN;
         int it = 0;
         uint32_t obuf_sel = 0;   // staging buffer rotation (leader's bulk-group order matches it)
         for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++it) {
+            if (EG == 2 && (it & 1) != eg) continue;
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             const int m_idx = tile / p.n_tiles;
             const int n_idx = tile - m_idx * p.n_tiles;
             int org[5];
             gemm_tile_origin(p, m_idx, org);
+            const float* bias = p.bias + n_idx * BN;
+            // this tile's bias: requested before the wait for the accumulator so its latency hides behind the mainloop
+            float bias_pre[(BN + 127) / 128];
+            if constexpr (BN >= 64) {
+#pragma unroll
+                for (int i = 0; i < (BN + 127) / 128; ++i) bias_pre[i] = (et + i * 128 < BN) ? __ldg(bias + et + i * 128) : 0.f;
+            }
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
-            const float* bias = p.bias + n_idx * BN;
 
             if constexpr (BN >= 64) {
                 int valid_rows = GEMM_BM;
@@ -426,14 +443,15 @@ __global__ void __launch_bounds__(XF ? GEMM_THREADS_XF : GEMM_THREADS, 1) conv_g
                     valid_rows = min(GEMM_BM, p.dims[p.stats_valid_coord] - org[p.stats_valid_coord + 1]);
 #pragma unroll 1
                 for (int cc = 0; cc < S::NCHUNK; ++cc) {
-                    uint8_t* obuf = out_stage + (obuf_sel & 1) * S::OUT_BUF;
+                    uint8_t* obuf = out_stage_g + (obuf_sel & 1) * S::OUT_BUF;
                     ++obuf_sel;
                     if (leader) tma_store_wait_read1();  // the store issued two chunks ago has drained this buffer
                     if (cc == 0) {   // (readers of the previous tile's bias are past that tile's last barrier)
 #pragma unroll
-                        for (int i = et; i < BN; i += 128) bias_s[i] = __ldg(bias + i);
+                        for (int i = 0; i < (BN + 127) / 128; ++i)
+                            if (et + i * 128 < BN) bias_g[et + i * 128] = bias_pre[i];
                     }
-                    named_bar_sync(1, 128);
+                    named_bar_sync(ebar, 128);
                     // accumulator -> fp16 staging, 32 columns at a time with the next TMEM load already in flight
                     uint32_t va[32], vb[32];
                     if (!(p.dbg & 2)) tmem_ld32(t_addr + cc * OC, va);
@@ -444,7 +462,7 @@ __global__ void __launch_bounds__(XF ? GEMM_THREADS_XF : GEMM_THREADS, 1) conv_g
                         tmem_ld_wait();
                         if (l + 1 < OC / 32) tmem_ld32(t_addr + cc * OC + (l + 1) * 32, (l & 1) ? va : vb);
                         uint8_t* unit_base = obuf + (l >> 1) * (GEMM_BM * 128);
-                        const float* bcol = bias_s + cc * OC + l * 32;
+                        const float* bcol = bias_g + cc * OC + l * 32;
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             const float4 b0 = *reinterpret_cast<const float4*>(bcol + q * 8);
@@ -467,7 +485,7 @@ __global__ void __launch_bounds__(XF ? GEMM_THREADS_XF : GEMM_THREADS, 1) conv_g
                         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
                     }
                     fence_proxy_async_smem();
-                    named_bar_sync(1, 128);
+                    named_bar_sync(ebar, 128);
                     if (leader && !(p.dbg & 1)) {
                         int c[5] = {0, org[1], org[2], org[3], org[4]};
 #pragma unroll
@@ -504,7 +522,7 @@ __global__ void __launch_bounds__(XF ? GEMM_THREADS_XF : GEMM_THREADS, 1) conv_g
                             su += __shfl_xor_sync(0xffffffffu, su, 16);
                             sq += __shfl_xor_sync(0xffffffffu, sq, 16);
                             if (half == 0) {   // gn_part[64-column unit of the tile][band][quad][2]
-                                float* part = gn_part + (((cc * S::UNITS + u) * 4 + band) * 16 + quad4) * 2;
+                                float* part = gn_part_g + (((cc * S::UNITS + u) * 4 + band) * 16 + quad4) * 2;
                                 part[0] = su;
                                 part[1] = sq;
                             }
@@ -512,7 +530,7 @@ __global__ void __launch_bounds__(XF ? GEMM_THREADS_XF : GEMM_THREADS, 1) conv_g
                     }
                 }
                 if (p.stats != nullptr) {
-                    named_bar_sync(1, 128);
+                    named_bar_sync(ebar, 128);
                     // thread = (domain-in-tile, local group, statistic): fold bands x quads of that group
                     const int cpg = p.stats_cpg;                 // multiple of 4
                     const int qpg = cpg >> 2;                    // quads per group
@@ -536,7 +554,7 @@ __global__ void __launch_bounds__(XF ? GEMM_THREADS_XF : GEMM_THREADS, 1) conv_g
                             const int ql = q - (col_base >> 2);           // 0 .. BN/4-1
                             const int uq = ql >> 4, qq = ql & 15;
                             for (int b = 0; b < bands_per_dom; ++b)
-                                a += gn_part[((uq * 4 + dl * bands_per_dom + b) * 16 + qq) * 2 + st];
+                                a += gn_part_g[((uq * 4 + dl * bands_per_dom + b) * 16 + qq) * 2 + st];
                         }
                         if (q_hi > q_lo)
                             atomicAdd(&p.stats[(static_cast<size_t>(dom_base + dl) * 32 + g) * 2 + st], static_cast<double>(a));

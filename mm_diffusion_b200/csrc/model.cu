@@ -237,8 +237,11 @@ struct Walker {
     int emb_row_top = 0;
     bool wide_n = true;         // MMD_NO_BN256=1 keeps 128-wide GEMM tiles
     bool fuse_stats = true;     // MMD_NO_FUSED_STATS=1 keeps every GroupNorm on the standalone statistics kernel
-    int xf_mask = 7;            // MMD_XF bitmask: GroupNorm apply folded into the consumer GEMM's A path for
-                                // 1 = ResBlock out_layers, 2 = self-attention norms, 4 = cross-attention norms
+    int xf_mask = 0;            // MMD_XF bitmask: GroupNorm apply folded into the consumer GEMM's A path for
+                                // 1 = ResBlock out_layers, 2 = self-attention norms, 4 = cross-attention norms.
+                                // Off by default: measured on B200 the standalone apply pass it removes (3.2 -> 1.7 ms of
+                                // ungraphed kernel time) is more than paid back by the slower consumer GEMMs inside the
+                                // two-branch step graph (12.52 ms -> 13.02 ms per step with every family on); DESIGN.md §6.
     float* emb_all = nullptr;   // [B][emb_rows]
     float* silu_emb = nullptr;  // [B][E]
 

@@ -205,9 +205,10 @@ int build_gemm(const GemmProblem& pr, GemmParams* out) {
     return MMD_OK;
 }
 
-template <int BN, int OC, bool XF = false>
+template <int BN, int OC, bool XF = false, int EG = 1>
 static int gemm_attr() {
-    MMD_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<BN, OC, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN, OC, XF>::TOTAL));
+    MMD_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<BN, OC, XF, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     GemmSmem<BN, OC, XF, EG>::TOTAL));
     return MMD_OK;
 }
 
@@ -220,6 +221,9 @@ int gemm_init_attrs() {
     MMD_TRY((gemm_attr<128, 128>()));
     MMD_TRY((gemm_attr<64, 64>()));
     MMD_TRY((gemm_attr<16, 64>()));
+    MMD_TRY((gemm_attr<256, 64, false, 2>()));
+    MMD_TRY((gemm_attr<128, 64, false, 2>()));
+    MMD_TRY((gemm_attr<64, 64, false, 2>()));
     MMD_TRY((gemm_attr<256, 64, true>()));
     MMD_TRY((gemm_attr<256, 128, true>()));
     MMD_TRY((gemm_attr<128, 64, true>()));
@@ -235,10 +239,13 @@ int gemm_init_attrs() {
 
 // Staged output columns per epilogue chunk: K-heavy GEMMs hide the epilogue under the mainloop and want every spare
 // kilobyte as pipeline stages (64); short-K GEMMs are epilogue / store bound and want fewer barrier rounds (128).
-int pick_oc(int bn, long long num_kb) {
+static int pick_oc_min_kb() {
     static const int min_kb = [] { const char* e = getenv("MMD_OC64_MIN_KB"); return e ? atoi(e) : 16; }();
+    return min_kb;
+}
+int pick_oc(int bn, long long num_kb) {
     if (bn < 128) return 64;
-    return num_kb >= min_kb ? 64 : 128;
+    return num_kb >= pick_oc_min_kb() ? 64 : 128;
 }
 
 PdlState& pdl_state() {
@@ -269,9 +276,10 @@ int launch_gemm(const GemmParams& p, int bn, cudaStream_t st) {
     for (int s = 0; s < p.n_src; ++s) num_kb += p.src_chunks[s];
     num_kb *= p.n_taps;
     const int oc = pick_oc(bn, num_kb);
-#define MMD_GEMM_CASE(BN_, OC_, XF_)                                                                                         \
-    MMD_CUDA_OK(launch_kernel(conv_gemm_kernel<BN_, OC_, XF_>, grid, (XF_) ? GEMM_THREADS_XF : GEMM_THREADS,                  \
-                              GemmSmem<BN_, OC_, XF_>::TOTAL, st, p))
+#define MMD_GEMM_CASE_EG(BN_, OC_, XF_, EG_)                                                                                 \
+    MMD_CUDA_OK(launch_kernel(conv_gemm_kernel<BN_, OC_, XF_, EG_>, grid, gemm_threads(EG_, XF_),                            \
+                              GemmSmem<BN_, OC_, XF_, EG_>::TOTAL, st, p))
+#define MMD_GEMM_CASE(BN_, OC_, XF_) MMD_GEMM_CASE_EG(BN_, OC_, XF_, 1)
     if (p.xf_sums != nullptr) {   // fused GroupNorm apply on the A operand: the variant with the four transform warps
         if (bn == 256 && oc == 64) MMD_GEMM_CASE(256, 64, true);
         else if (bn == 256) MMD_GEMM_CASE(256, 128, true);
@@ -296,6 +304,16 @@ int launch_gemm(const GemmParams& p, int bn, cudaStream_t st) {
 #undef MMD_GEMM2_CASE
         return MMD_OK;
     }
+    // Two epilogue warpgroups (alternate tiles, one TMEM accumulator stage each) where the epilogue is the long pole:
+    // short-K GEMMs with more than one tile per CTA.  MMD_EG: 0 = never, 1 = short-K only (default), 2 = every GEMM.
+    static const int eg_mode = [] { const char* e = getenv("MMD_EG"); return e ? atoi(e) : 1; }();
+    const bool short_k = num_kb < pick_oc_min_kb();
+    if (bn >= 64 && tiles > grid && (eg_mode == 2 || (eg_mode == 1 && short_k))) {
+        if (bn == 256) MMD_GEMM_CASE_EG(256, 64, false, 2);
+        else if (bn == 128) MMD_GEMM_CASE_EG(128, 64, false, 2);
+        else MMD_GEMM_CASE_EG(64, 64, false, 2);
+        return MMD_OK;
+    }
     if (bn == 256 && oc == 64) MMD_GEMM_CASE(256, 64, false);
     else if (bn == 256) MMD_GEMM_CASE(256, 128, false);
     else if (bn == 128 && oc == 64) MMD_GEMM_CASE(128, 64, false);
@@ -304,6 +322,7 @@ int launch_gemm(const GemmParams& p, int bn, cudaStream_t st) {
     else if (bn == 16) MMD_GEMM_CASE(16, 64, false);
     else return fail(MMD_EINVAL, "unsupported BN %d", bn);
 #undef MMD_GEMM_CASE
+#undef MMD_GEMM_CASE_EG
     return MMD_OK;
 }
 
