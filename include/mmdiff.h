@@ -197,6 +197,11 @@ typedef struct MmdConvDesc {
     int64_t gn_rows;
 } MmdConvDesc;
 int mmd_op_conv(const MmdConvDesc* d, void* stream);
+
+/* Measurement entry (tools/gpu_gemm_micro.py): mmd_op_conv, then the same packed problem launched `reps` more times back to
+   back on `stream` between two CUDA events; *us_per_launch = average device time per launch in microseconds (weight
+   packing excluded).  Blocks until the launches are done.  No reference counterpart. */
+int mmd_op_conv_timed(const MmdConvDesc* d, int reps, float* us_per_launch, void* stream);
 /* Pointwise convolution (n_taps == 1) whose source 0 is first normalised: conv(act(GroupNorm32(src0) * (1 + scale) +
  * shift) ++ src1..) — the ResBlock out_layers (multimodal_unet.py:459-470) and the attention norms (:284, :664) with
  * the GroupNorm apply done on the GEMM's A operand in shared memory (no normalised tensor in HBM).  ns domains:

@@ -122,6 +122,7 @@ _PROTOS = [
      [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     ("mmd_op_resample", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     ("mmd_op_conv", C.c_int, [C.POINTER(MmdConvDesc), C.c_void_p]),
+    ("mmd_op_conv_timed", C.c_int, [C.POINTER(MmdConvDesc), C.c_int, C.POINTER(C.c_float), C.c_void_p]),
     ("mmd_model_set_params_flat", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     ("mmd_model_set_dropout", C.c_int, [C.c_void_p, C.c_float, C.c_uint64]),
     ("mmd_model_train_generation", C.c_int64, [C.c_void_p, C.c_int]),

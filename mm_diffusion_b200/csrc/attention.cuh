@@ -160,34 +160,43 @@ __global__ void __launch_bounds__(ATT_THREADS, (D == 64) ? 2 : 1) attention_kern
     const uint32_t tmem_O = tmem_base + Cfg::O_COL;   // D columns
 
     if (warp == 4) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            mbar_expect_tx(q_full, S::TILE);
-            for (int ch = 0; ch < S::NCH; ++ch)
-                tma_load_2d(smem + S::Q_OFF + ch * (ATT_BQ * 128), &p.q_map, q_full, p.q_col0 + w.head * D + ch * 64,
-                            w.q_row0);
+        // ===================== TMA producer (uniform warp, elected lane issues; see gemm.cuh) =====================
+        {
+            if (elect_one()) {
+                mbar_expect_tx(q_full, S::TILE);
+                for (int ch = 0; ch < S::NCH; ++ch)
+                    tma_load_2d(smem + S::Q_OFF + ch * (ATT_BQ * 128), &p.q_map, q_full, p.q_col0 + w.head * D + ch * 64,
+                                w.q_row0);
+            }
+            __syncwarp();
             for (int t = 0; t < T; ++t) {
                 const int st = t & 1;
                 const uint32_t ph = (t >> 1) & 1;
                 int krow, kvalid;
                 attn_tile(w, t, krow, kvalid);
                 mbar_wait(&k_empty[st], ph ^ 1);
-                mbar_expect_tx(&k_full[st], S::TILE);
-                for (int ch = 0; ch < S::NCH; ++ch)
-                    tma_load_2d(smem + S::K_OFF + st * S::TILE + ch * (ATT_BKV * 128), &p.k_map, &k_full[st],
-                                p.k_col0 + w.head * D + ch * 64, krow);
+                if (elect_one()) {
+                    mbar_expect_tx(&k_full[st], S::TILE);
+                    for (int ch = 0; ch < S::NCH; ++ch)
+                        tma_load_2d(smem + S::K_OFF + st * S::TILE + ch * (ATT_BKV * 128), &p.k_map, &k_full[st],
+                                    p.k_col0 + w.head * D + ch * 64, krow);
+                }
+                __syncwarp();
                 const int vs = (VST == 2) ? st : 0;
                 const uint32_t vph = (VST == 2) ? ph : static_cast<uint32_t>(t & 1);
                 mbar_wait(&v_empty[vs], vph ^ 1);
-                mbar_expect_tx(&v_full[vs], S::TILE);
-                for (int ch = 0; ch < S::NCH; ++ch)
-                    tma_load_2d(smem + S::V_OFF + vs * S::TILE + ch * (ATT_BKV * 128), &p.v_map, &v_full[vs],
-                                p.v_col0 + w.head * D + ch * 64, krow);
+                if (elect_one()) {
+                    mbar_expect_tx(&v_full[vs], S::TILE);
+                    for (int ch = 0; ch < S::NCH; ++ch)
+                        tma_load_2d(smem + S::V_OFF + vs * S::TILE + ch * (ATT_BKV * 128), &p.v_map, &v_full[vs],
+                                    p.v_col0 + w.head * D + ch * 64, krow);
+                }
+                __syncwarp();
             }
         }
     } else if (warp == 5) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (uniform warp, elected lane issues) =====================
+        {
             constexpr uint32_t idesc_qk = umma_idesc_f16(ATT_BQ, ATT_BKV, 0, 0);
             constexpr uint32_t idesc_pv = umma_idesc_f16(ATT_BQ, D, 0, 1);  // B (=V) is MN-major
             const uint32_t q_addr = smem_u32(smem + S::Q_OFF);
@@ -198,15 +207,18 @@ __global__ void __launch_bounds__(ATT_THREADS, (D == 64) ? 2 : 1) attention_kern
                 mbar_wait(&k_full[st], ph);
                 tc_fence_after();
                 const uint32_t k_addr = smem_u32(smem + S::K_OFF + st * S::TILE);
-#pragma unroll
                 const int sb = (SBUF == 2) ? st : 0;
-                for (int ks = 0; ks < D / 16; ++ks) {
-                    const uint32_t off = (ks >> 2) * (ATT_BQ * 128) + (ks & 3) * 32;
-                    umma_f16_ss(tmem_S + sb * 128, umma_desc_sw128(q_addr + off, 16, 1024),
-                                umma_desc_sw128(k_addr + off, 16, 1024), idesc_qk, ks != 0 ? 1u : 0u);
+                if (elect_one()) {
+#pragma unroll
+                    for (int ks = 0; ks < D / 16; ++ks) {
+                        const uint32_t off = (ks >> 2) * (ATT_BQ * 128) + (ks & 3) * 32;
+                        umma_f16_ss(tmem_S + sb * 128, umma_desc_sw128(q_addr + off, 16, 1024),
+                                    umma_desc_sw128(k_addr + off, 16, 1024), idesc_qk, ks != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&k_empty[st]);
+                    umma_commit(&s_full[sb]);
                 }
-                umma_commit(&k_empty[st]);
-                umma_commit(&s_full[sb]);
+                __syncwarp();
             };
             mbar_wait(q_full, 0);
             tc_fence_after();
@@ -224,13 +236,16 @@ __global__ void __launch_bounds__(ATT_THREADS, (D == 64) ? 2 : 1) attention_kern
                 tc_fence_after();
                 const uint32_t v_addr = smem_u32(smem + S::V_OFF + vs * S::TILE);
                 const int nks = (kvalid + 15) >> 4;
-                for (int ks = 0; ks < nks; ++ks) {
-                    const uint32_t poff = (ks >> 2) * (ATT_BQ * 128) + (ks & 3) * 32;
-                    umma_f16_ss(tmem_O, umma_desc_sw128(p_addr + poff, 16, 1024),
-                                umma_desc_sw128(v_addr + ks * 2048, ATT_BKV * 128, 1024), idesc_pv, ks != 0 ? 1u : 0u);
+                if (elect_one()) {
+                    for (int ks = 0; ks < nks; ++ks) {
+                        const uint32_t poff = (ks >> 2) * (ATT_BQ * 128) + (ks & 3) * 32;
+                        umma_f16_ss(tmem_O, umma_desc_sw128(p_addr + poff, 16, 1024),
+                                    umma_desc_sw128(v_addr + ks * 2048, ATT_BKV * 128, 1024), idesc_pv, ks != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&v_empty[vs]);
+                    umma_commit(o_full);
                 }
-                umma_commit(&v_empty[vs]);
-                umma_commit(o_full);
+                __syncwarp();
                 if (SBUF == 1 && t + 1 < T) issue_qk(t + 1);   // single S buffer: next logits after this tile's PV
             }
         }
@@ -572,30 +587,41 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention64_kernel(const __gri
 
     if (warp == 4) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        // whole warp in uniform control flow (all lanes wait), one elected lane issues: a lane-guarded branch makes
+        // ptxas wrap every TMA / tcgen05 instruction in an ELECT + BRA.U.ANY loop over the active lanes (gemm.cuh)
+        {
             int g = 0;   // KV tiles issued so far (all items)
             int it = 0;  // items started
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
                 const AttnWork w = attn_decode(p, item);
                 mbar_wait(q_empty, (it & 1) ^ 1);   // last Q·K^T of the previous item has been issued and retired
-                mbar_expect_tx(q_full, 16384);
-                tma_load_2d(smem + S::Q_OFF, &p.q_map, q_full, p.q_col0 + w.head * D, w.q_row0);
+                if (elect_one()) {
+                    mbar_expect_tx(q_full, 16384);
+                    tma_load_2d(smem + S::Q_OFF, &p.q_map, q_full, p.q_col0 + w.head * D, w.q_row0);
+                }
+                __syncwarp();
                 for (int t = 0; t < w.n_tiles; ++t, ++g) {
                     const int st = g & 1;
                     int krow, kvalid;
                     attn_tile(w, t, krow, kvalid);
                     mbar_wait(&k_empty[st], ((g >> 1) & 1) ^ 1);
-                    mbar_expect_tx(&k_full[st], 16384);
-                    tma_load_2d(smem + S::K_OFF + st * 16384, &p.k_map, &k_full[st], p.k_col0 + w.head * D, krow);
+                    if (elect_one()) {
+                        mbar_expect_tx(&k_full[st], 16384);
+                        tma_load_2d(smem + S::K_OFF + st * 16384, &p.k_map, &k_full[st], p.k_col0 + w.head * D, krow);
+                    }
+                    __syncwarp();
                     mbar_wait(v_empty, (g & 1) ^ 1);
-                    mbar_expect_tx(v_full, 16384);
-                    tma_load_2d(smem + S::V_OFF, &p.v_map, v_full, p.v_col0 + w.head * D, krow);
+                    if (elect_one()) {
+                        mbar_expect_tx(v_full, 16384);
+                        tma_load_2d(smem + S::V_OFF, &p.v_map, v_full, p.v_col0 + w.head * D, krow);
+                    }
+                    __syncwarp();
                 }
             }
         }
     } else if (warp == 5) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (uniform warp, elected lane) =====================
+        {
             constexpr uint32_t idesc_qk = umma_idesc_f16(ATT_BQ, ATT_BKV, 0, 0);
             constexpr uint32_t idesc_pv = umma_idesc_f16(ATT_BQ, D, 0, 1);   // V is MN-major
             constexpr uint32_t idesc_l = umma_idesc_f16(ATT_BQ, 16, 0, 0);   // P x ones^T
@@ -616,12 +642,15 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention64_kernel(const __gri
                 mbar_wait(&k_full[st], (gq >> 1) & 1);
                 tc_fence_after();
                 const uint64_t kd = kd0 + static_cast<uint64_t>(st) * (16384 >> 4);
+                if (elect_one()) {
 #pragma unroll
-                for (int ks = 0; ks < D / 16; ++ks)
-                    umma_f16_ss(tmem_S, qd0 + 2 * ks, kd + 2 * ks, idesc_qk, ks != 0 ? 1u : 0u);
-                umma_commit(&k_empty[st]);
-                if (t == w.n_tiles - 1) umma_commit(q_empty);
-                umma_commit(s_full);
+                    for (int ks = 0; ks < D / 16; ++ks)
+                        umma_f16_ss(tmem_S, qd0 + 2 * ks, kd + 2 * ks, idesc_qk, ks != 0 ? 1u : 0u);
+                    umma_commit(&k_empty[st]);
+                    if (t == w.n_tiles - 1) umma_commit(q_empty);
+                    umma_commit(s_full);
+                }
+                __syncwarp();
                 ++gq;
             };
             int g = 0;
@@ -636,36 +665,38 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention64_kernel(const __gri
                     mbar_wait(v_full, g & 1);
                     tc_fence_after();
                     const int nks = (kvalid + 15) >> 4;
-                    // descriptors are base + compile-time increments (16-byte units), so the single issuing thread
-                    // spends its time on tcgen05.mma issue, not on address arithmetic
-                    if (nks == ATT_BKV / 16) {
-                        // full tile: straight-line issue with compile-time descriptor increments
+                    if (elect_one()) {
+                        // descriptors are base + compile-time increments (16-byte units)
+                        if (nks == ATT_BKV / 16) {
+                            // full tile: straight-line issue with compile-time descriptor increments
 #pragma unroll
-                        for (int ks = 0; ks < ATT_BKV / 16; ++ks)
-                            umma_f16_ss(tmem_O, pd0 + ((ks >> 2) * (ATT_BQ * 128 >> 4) + (ks & 3) * 2), vd0 + ks * (2048 >> 4),
-                                        idesc_pv, (t | ks) != 0 ? 1u : 0u);
+                            for (int ks = 0; ks < ATT_BKV / 16; ++ks)
+                                umma_f16_ss(tmem_O, pd0 + ((ks >> 2) * (ATT_BQ * 128 >> 4) + (ks & 3) * 2), vd0 + ks * (2048 >> 4),
+                                            idesc_pv, (t | ks) != 0 ? 1u : 0u);
 #pragma unroll
-                        for (int ks = 0; ks < ATT_BKV / 16; ++ks)
-                            umma_f16_ss(tmem_L, pd0 + ((ks >> 2) * (ATT_BQ * 128 >> 4) + (ks & 3) * 2),
-                                        od0 + ((ks >> 2) * (2048 >> 4) + (ks & 3) * 2), idesc_l, (t | ks) != 0 ? 1u : 0u);
-                    } else {
-                        // ragged tile: running descriptors (a 64-column chunk boundary after ks = 3)
-                        uint64_t pd = pd0, vd = vd0;
-                        for (int ks = 0; ks < nks; ++ks) {
-                            umma_f16_ss(tmem_O, pd, vd, idesc_pv, (t | ks) != 0 ? 1u : 0u);
-                            vd += 2048 >> 4;
-                            pd += (ks == 3) ? (ATT_BQ * 128 >> 4) - 6 : 2;
+                            for (int ks = 0; ks < ATT_BKV / 16; ++ks)
+                                umma_f16_ss(tmem_L, pd0 + ((ks >> 2) * (ATT_BQ * 128 >> 4) + (ks & 3) * 2),
+                                            od0 + ((ks >> 2) * (2048 >> 4) + (ks & 3) * 2), idesc_l, (t | ks) != 0 ? 1u : 0u);
+                        } else {
+                            // ragged tile: running descriptors (a 64-column chunk boundary after ks = 3)
+                            uint64_t pd = pd0, vd = vd0;
+                            for (int ks = 0; ks < nks; ++ks) {
+                                umma_f16_ss(tmem_O, pd, vd, idesc_pv, (t | ks) != 0 ? 1u : 0u);
+                                vd += 2048 >> 4;
+                                pd += (ks == 3) ? (ATT_BQ * 128 >> 4) - 6 : 2;
+                            }
+                            uint64_t od = od0;
+                            pd = pd0;
+                            for (int ks = 0; ks < nks; ++ks) {
+                                umma_f16_ss(tmem_L, pd, od, idesc_l, (t | ks) != 0 ? 1u : 0u);
+                                pd += (ks == 3) ? (ATT_BQ * 128 >> 4) - 6 : 2;
+                                od += (ks == 3) ? (2048 >> 4) - 6 : 2;
+                            }
                         }
-                        uint64_t od = od0;
-                        pd = pd0;
-                        for (int ks = 0; ks < nks; ++ks) {
-                            umma_f16_ss(tmem_L, pd, od, idesc_l, (t | ks) != 0 ? 1u : 0u);
-                            pd += (ks == 3) ? (ATT_BQ * 128 >> 4) - 6 : 2;
-                            od += (ks == 3) ? (2048 >> 4) - 6 : 2;
-                        }
+                        umma_commit(v_empty);
+                        umma_commit(o_full);
                     }
-                    umma_commit(v_empty);
-                    umma_commit(o_full);
+                    __syncwarp();
                     // next logits: same item, or the first tile of the next item (S is free: softmax of this tile is done)
                     if (t + 1 < w.n_tiles) {
                         issue_qk(w, t + 1);

@@ -123,30 +123,36 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_kernel(const __grid_co
     const uint32_t tmem_A2 = tmem_base + 384;     // D columns (KV)
 
     if (warp == 8) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            mbar_expect_tx(x_full, 2 * S::TILE);
-            for (int ch = 0; ch < S::NCH; ++ch) {
-                tma_load_2d(smem + S::X1_OFF + ch * 16384, &p.x1_map, x_full, p.x1_col0 + head * D + ch * 64, x_row0);
-                tma_load_2d(smem + S::X2_OFF + ch * 16384, &p.x2_map, x_full, p.x2_col0 + head * D + ch * 64, x_row0);
+        // ===================== TMA producer (uniform warp, elected lane issues; see gemm.cuh) =====================
+        {
+            if (elect_one()) {
+                mbar_expect_tx(x_full, 2 * S::TILE);
+                for (int ch = 0; ch < S::NCH; ++ch) {
+                    tma_load_2d(smem + S::X1_OFF + ch * 16384, &p.x1_map, x_full, p.x1_col0 + head * D + ch * 64, x_row0);
+                    tma_load_2d(smem + S::X2_OFF + ch * 16384, &p.x2_map, x_full, p.x2_col0 + head * D + ch * 64, x_row0);
+                }
             }
+            __syncwarp();
             for (int t = 0; t < T; ++t) {
                 const int st = t % YST;
                 const uint32_t use = static_cast<uint32_t>(t / YST);
                 int yrow, yvalid;
                 y_tile(t, yrow, yvalid);
                 mbar_wait(&y_empty[st], (use & 1) ^ 1);
-                mbar_expect_tx(&y_full[st], 2 * S::TILE);
                 uint8_t* y1 = smem + S::Y_OFF + st * 2 * S::TILE;
-                for (int ch = 0; ch < S::NCH; ++ch) {
-                    tma_load_2d(y1 + ch * 16384, &p.y1_map, &y_full[st], p.y1_col0 + head * D + ch * 64, yrow);
-                    tma_load_2d(y1 + S::TILE + ch * 16384, &p.y2_map, &y_full[st], p.y2_col0 + head * D + ch * 64, yrow);
+                if (elect_one()) {
+                    mbar_expect_tx(&y_full[st], 2 * S::TILE);
+                    for (int ch = 0; ch < S::NCH; ++ch) {
+                        tma_load_2d(y1 + ch * 16384, &p.y1_map, &y_full[st], p.y1_col0 + head * D + ch * 64, yrow);
+                        tma_load_2d(y1 + S::TILE + ch * 16384, &p.y2_map, &y_full[st], p.y2_col0 + head * D + ch * 64, yrow);
+                    }
                 }
+                __syncwarp();
             }
         }
     } else if (warp == 9) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (uniform warp, elected lane issues) =====================
+        {
             constexpr uint32_t idesc_s = umma_idesc_f16(128, 128, 0, 0);
             constexpr uint32_t idesc_acc = umma_idesc_f16(128, D, 0, 1);   // B (Y tile) is MN-major
             const uint32_t x1 = smem_u32(smem + S::X1_OFF), x2 = smem_u32(smem + S::X2_OFF);
@@ -157,19 +163,22 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_kernel(const __grid_co
                 mbar_wait(&y_full[st], (t / YST) & 1);
                 tc_fence_after();
                 const uint32_t y1 = smem_u32(smem + S::Y_OFF + st * 2 * S::TILE), y2 = y1 + S::TILE;
+                if (elect_one()) {
 #pragma unroll
-                for (int ks = 0; ks < D / 16; ++ks) {
-                    const uint32_t off = (ks >> 2) * 16384 + (ks & 3) * 32;
-                    umma_f16_ss(tmem_S, umma_desc_sw128(x1 + off, 16, 1024), umma_desc_sw128(y1 + off, 16, 1024), idesc_s,
-                                ks != 0 ? 1u : 0u);
-                }
+                    for (int ks = 0; ks < D / 16; ++ks) {
+                        const uint32_t off = (ks >> 2) * 16384 + (ks & 3) * 32;
+                        umma_f16_ss(tmem_S, umma_desc_sw128(x1 + off, 16, 1024), umma_desc_sw128(y1 + off, 16, 1024), idesc_s,
+                                    ks != 0 ? 1u : 0u);
+                    }
 #pragma unroll
-                for (int ks = 0; ks < D / 16; ++ks) {
-                    const uint32_t off = (ks >> 2) * 16384 + (ks & 3) * 32;
-                    umma_f16_ss(tmem_DP, umma_desc_sw128(x2 + off, 16, 1024), umma_desc_sw128(y2 + off, 16, 1024), idesc_s,
-                                ks != 0 ? 1u : 0u);
+                    for (int ks = 0; ks < D / 16; ++ks) {
+                        const uint32_t off = (ks >> 2) * 16384 + (ks & 3) * 32;
+                        umma_f16_ss(tmem_DP, umma_desc_sw128(x2 + off, 16, 1024), umma_desc_sw128(y2 + off, 16, 1024), idesc_s,
+                                    ks != 0 ? 1u : 0u);
+                    }
+                    umma_commit(s_full);
                 }
-                umma_commit(s_full);
+                __syncwarp();
             };
             mbar_wait(x_full, 0);
             issue_s(0);
@@ -183,15 +192,18 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attn_bwd_kernel(const __grid_co
                 const uint64_t y1m = umma_desc_sw128(y1, 128 * 128, 1024);   // MN-major views of the Y tiles
                 const uint64_t y2m = umma_desc_sw128(y1 + S::TILE, 128 * 128, 1024);
                 const int nks = (yvalid + 15) >> 4;
-                for (int ks = 0; ks < nks; ++ks) {
-                    const uint64_t aoff = static_cast<uint64_t>((ks >> 2) * (16384 >> 4) + (ks & 3) * 2);
-                    umma_f16_ss(tmem_A1, dsd0 + aoff, y1m + static_cast<uint64_t>(ks) * (2048 >> 4), idesc_acc, (t | ks) != 0 ? 1u : 0u);
-                    if (KV)
-                        umma_f16_ss(tmem_A2, pd0 + aoff, y2m + static_cast<uint64_t>(ks) * (2048 >> 4), idesc_acc, (t | ks) != 0 ? 1u : 0u);
+                if (elect_one()) {
+                    for (int ks = 0; ks < nks; ++ks) {
+                        const uint64_t aoff = static_cast<uint64_t>((ks >> 2) * (16384 >> 4) + (ks & 3) * 2);
+                        umma_f16_ss(tmem_A1, dsd0 + aoff, y1m + static_cast<uint64_t>(ks) * (2048 >> 4), idesc_acc, (t | ks) != 0 ? 1u : 0u);
+                        if (KV)
+                            umma_f16_ss(tmem_A2, pd0 + aoff, y2m + static_cast<uint64_t>(ks) * (2048 >> 4), idesc_acc, (t | ks) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&y_empty[st]);
+                    if (t == T - 1) umma_commit(acc_full);
                 }
-                umma_commit(&y_empty[st]);
-                if (t == T - 1) umma_commit(acc_full);
-                else issue_s(t + 1);   // S / dP are free (p_ready(t)); queued right behind the accumulate MMAs
+                __syncwarp();
+                if (t != T - 1) issue_s(t + 1);   // S / dP are free (p_ready(t)); queued right behind the accumulate MMAs
             }
         }
     } else {

@@ -84,10 +84,25 @@ MMD_DEVINL bool mbar_try_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t hin
         : "memory");
     return ok != 0;
 }
+// MMD_WAIT_MODE (compile time): 0 = one plain try_wait, then try_wait with a 20 us suspend-time hint (ptxas lowers the
+// hint to NANOSLEEP.SYNCS + PHASECHK); 1 = plain try_wait in a loop (the hardware-blocking form with its own short time
+// limit, as CUTLASS waits); 2 = plain try_wait loop with a 32 ns nanosleep back-off between attempts.
+#ifndef MMD_WAIT_MODE
+#define MMD_WAIT_MODE 0
+#endif
 MMD_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
+#if MMD_WAIT_MODE == 0
     while (!mbar_try_wait_sleep(bar, parity, 20000u)) {
+#else
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+#if MMD_WAIT_MODE == 2
+        __nanosleep(32);
+#endif
+        if ((++spins & 1023u) != 0) continue;
+#endif
         if (clock64() - t0 > MMD_WAIT_CYCLES) {
             printf("mmd: mbarrier timeout block %d thread %d bar@%u parity %u\n", blockIdx.x, threadIdx.x, smem_u32(bar), parity);
             __trap();

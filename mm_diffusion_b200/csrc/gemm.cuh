@@ -181,40 +181,48 @@ __global__ void __launch_bounds__(gemm_threads(EG, XF), 1) conv_gemm_kernel(cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    if (warp != 0) pdl_wait();   // the producer thread waits after it has requested the first weight tiles
+    if (warp != 0) pdl_wait();   // the producer warp waits after it has requested the first weight tiles
 
     if (warp == 0) {
-        // ================= TMA producer (one thread) =================
-        if (lane == 0) {
+        // ================= TMA producer =================
+        // Same shape as the MMA issuer below: the whole warp walks the loops in uniform control flow, one elected lane
+        // issues the expect_tx + TMA instructions (no per-instruction ELECT / BRA.U.ANY loops in the SASS).
+        {
             // Weights are constants of the plan, activations come from the previous kernel: the B halves of the first
             // pipeline stages are requested before the grid dependency resolves, the A halves after it.
             int pre = 0;
             if (tile_begin < tile_end) {
                 const int n_idx0 = tile_begin % p.n_tiles;
                 pre = (p.dbg & 24) ? 0 : min(S::STAGES, num_kb);
-                for (int kb = 0; kb < pre; ++kb) {
-                    mbar_expect_tx(&full_bar[kb], S::STAGE_BYTES);
-                    tma_load_2d(stage_base + kb * S::STAGE_BYTES + S::A_BYTES, &p.b_map, &full_bar[kb], kb * GEMM_BK, n_idx0 * BN);
+                if (elect_one()) {
+                    for (int kb = 0; kb < pre; ++kb) {
+                        mbar_expect_tx(&full_bar[kb], S::STAGE_BYTES);
+                        tma_load_2d(stage_base + kb * S::STAGE_BYTES + S::A_BYTES, &p.b_map, &full_bar[kb], kb * GEMM_BK, n_idx0 * BN);
+                    }
                 }
+                __syncwarp();
             }
             pdl_wait();
             // A tiles of the next pf_tiles-1 tiles of this CTA go to L2 right away; inside the loop every k-block load
             // is paired with the prefetch of the same k-block pf_tiles tiles ahead
             const int pf = p.pf_tiles;
-            for (int d = 1; d < pf; ++d) {
-                const int tile = tile_begin + d * tile_step;
-                if (tile >= tile_end) break;
-                int org[5];
-                gemm_tile_origin(p, tile / p.n_tiles, org);
-                for (int t = 0; t < p.n_taps; ++t) {
-                    int c[5] = {0, org[1] + p.tap[t][0], org[2] + p.tap[t][1], org[3] + p.tap[t][2], org[4]};
-                    for (int s = 0; s < p.n_src; ++s)
-                        for (int ch = 0; ch < p.src_chunks[s]; ++ch) {
-                            c[0] = ch * GEMM_BK;
-                            tma_prefetch_nd(p.rank, &p.a_map[s], c);
-                        }
+            if (pf > 1 && lane == 0) {
+                for (int d = 1; d < pf; ++d) {
+                    const int tile = tile_begin + d * tile_step;
+                    if (tile >= tile_end) break;
+                    int org[5];
+                    gemm_tile_origin(p, tile / p.n_tiles, org);
+                    for (int t = 0; t < p.n_taps; ++t) {
+                        int c[5] = {0, org[1] + p.tap[t][0], org[2] + p.tap[t][1], org[3] + p.tap[t][2], org[4]};
+                        for (int s = 0; s < p.n_src; ++s)
+                            for (int ch = 0; ch < p.src_chunks[s]; ++ch) {
+                                c[0] = ch * GEMM_BK;
+                                tma_prefetch_nd(p.rank, &p.a_map[s], c);
+                            }
+                    }
                 }
             }
+            __syncwarp();
             int stage = 0;
             uint32_t phase = 0;
             int gk = 0;   // k-blocks issued by this CTA (the first `pre` already have their B half in flight)
@@ -237,28 +245,29 @@ __global__ void __launch_bounds__(gemm_threads(EG, XF), 1) conv_gemm_kernel(cons
                     int pc[5] = {0, porg[1] + p.tap[t][0], porg[2] + p.tap[t][1], porg[3] + p.tap[t][2], porg[4]};
                     for (int s = 0; s < p.n_src; ++s) {
                         for (int ch = 0; ch < p.src_chunks[s]; ++ch, ++kb, ++gk) {
-                            if (pf_on) {
-                                pc[0] = ch * GEMM_BK;
-                                tma_prefetch_nd(p.rank, &p.a_map[s], pc);
-                            }
                             mbar_wait(&empty_bar[stage], phase ^ 1);
                             uint8_t* a_dst = stage_base + stage * S::STAGE_BYTES;
-                            if (p.dbg & 24) {   // ablation: drop the A and / or B loads
-                                const uint32_t bytes = ((p.dbg & 8) ? 0 : S::A_BYTES) + ((p.dbg & 16) ? 0 : S::B_BYTES);
-                                if (bytes == 0) { mbar_arrive(&full_bar[stage]); }
-                                else {
-                                    mbar_expect_tx(&full_bar[stage], bytes);
-                                    c[0] = ch * GEMM_BK;
-                                    if (!(p.dbg & 8)) tma_load_nd(p.rank, a_dst, &p.a_map[s], &full_bar[stage], c);
-                                    if (!(p.dbg & 16)) tma_load_2d(a_dst + S::A_BYTES, &p.b_map, &full_bar[stage], kb * GEMM_BK, n_idx * BN);
-                                }
-                                if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
-                                continue;
-                            }
-                            if (gk >= pre) mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
                             c[0] = ch * GEMM_BK;
-                            tma_load_nd(p.rank, a_dst, &p.a_map[s], &full_bar[stage], c);
-                            if (gk >= pre) tma_load_2d(a_dst + S::A_BYTES, &p.b_map, &full_bar[stage], kb * GEMM_BK, n_idx * BN);
+                            if (elect_one()) {
+                                if (pf_on) {
+                                    pc[0] = ch * GEMM_BK;
+                                    tma_prefetch_nd(p.rank, &p.a_map[s], pc);
+                                }
+                                if (p.dbg & 24) {   // ablation: drop the A and / or B loads
+                                    const uint32_t bytes = ((p.dbg & 8) ? 0 : S::A_BYTES) + ((p.dbg & 16) ? 0 : S::B_BYTES);
+                                    if (bytes == 0) { mbar_arrive(&full_bar[stage]); }
+                                    else {
+                                        mbar_expect_tx(&full_bar[stage], bytes);
+                                        if (!(p.dbg & 8)) tma_load_nd(p.rank, a_dst, &p.a_map[s], &full_bar[stage], c);
+                                        if (!(p.dbg & 16)) tma_load_2d(a_dst + S::A_BYTES, &p.b_map, &full_bar[stage], kb * GEMM_BK, n_idx * BN);
+                                    }
+                                } else {
+                                    if (gk >= pre) mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+                                    tma_load_nd(p.rank, a_dst, &p.a_map[s], &full_bar[stage], c);
+                                    if (gk >= pre) tma_load_2d(a_dst + S::A_BYTES, &p.b_map, &full_bar[stage], kb * GEMM_BK, n_idx * BN);
+                                }
+                            }
+                            __syncwarp();
                             if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
                         }
                     }
@@ -266,8 +275,13 @@ __global__ void __launch_bounds__(gemm_threads(EG, XF), 1) conv_gemm_kernel(cons
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer (one thread) =================
-        if (lane == 0) {
+        // ================= MMA issuer =================
+        // The whole warp walks the tile / k-block loops in uniform control flow (all lanes wait on the barriers); one
+        // elected lane issues the tcgen05 instructions.  Issuing from a lane-guarded branch (`if (lane == 0)`) makes
+        // ptxas wrap every UTCHMMA / UTCBAR in an ELECT + BRA.U.ANY loop over the active lanes with R2UR moves of each
+        // operand: ~75 dependent instructions per k-block on one warp, longer than the 256 cycles the tensor pipe needs
+        // for a 128 x 128 x 64 block (measured: the k-block loop alone, no loads / MMAs / epilogue, cost ~500 cycles).
+        {
             constexpr uint32_t idesc = umma_idesc_f16(GEMM_BM, BN, 0, 0);
             int stage = 0;
             uint32_t phase = 0;
@@ -285,18 +299,21 @@ __global__ void __launch_bounds__(gemm_threads(EG, XF), 1) conv_gemm_kernel(cons
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(stage_base + stage * S::STAGE_BYTES);
                     // one descriptor per operand and k-iteration; the 16-element k-steps only bump the 16-byte-unit
-                    // start-address field (+32 bytes = +2), keeping the single issuing thread off the critical path
+                    // start-address field (+32 bytes = +2)
                     const uint64_t ad0 = umma_desc_sw128(a_addr, 16, 1024);
                     const uint64_t bd0 = umma_desc_sw128(a_addr + S::A_BYTES, 16, 1024);
-                    if (!(p.dbg & 4)) {
+                    if (elect_one()) {
+                        if (!(p.dbg & 4)) {
 #pragma unroll
-                        for (int k = 0; k < GEMM_BK / 16; ++k)
-                            umma_f16_ss(d_tmem, ad0 + 2 * k, bd0 + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                            for (int k = 0; k < GEMM_BK / 16; ++k)
+                                umma_f16_ss(d_tmem, ad0 + 2 * k, bd0 + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
+                        umma_commit(&empty_bar[stage]);
+                        if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
                     }
-                    umma_commit(&empty_bar[stage]);
+                    __syncwarp();
                     if (++stage == S::STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tfull_bar[acc]);
             }
         }
     } else if (XF && warp >= 2 + 4 * EG) {
@@ -411,7 +428,7 @@ __global__ void __launch_bounds__(gemm_threads(EG, XF), 1) conv_gemm_kernel(cons
         const int row = quad * 32 + lane;
         const int eg = (warp - 2) >> 2;            // epilogue warpgroup: with EG = 2 group g drains accumulator stage g
         const int et = (threadIdx.x - 64) & 127;   // 0..127 inside the group
-        const bool leader = (et == 0);
+        const bool lead_warp = (et >> 5) == 0;     // its elected lane issues the TMA stores of the group
         const int ebar = 1 + 2 * eg;               // named barrier of this group (2 belongs to the transform warps)
         uint8_t* const out_stage_g = out_stage + eg * 2 * S::OUT_BUF;
         float* const gn_part_g = gn_part + eg * (S::GN_ONE / 4);
@@ -445,7 +462,10 @@ __global__ void __launch_bounds__(gemm_threads(EG, XF), 1) conv_gemm_kernel(cons
                 for (int cc = 0; cc < S::NCHUNK; ++cc) {
                     uint8_t* obuf = out_stage_g + (obuf_sel & 1) * S::OUT_BUF;
                     ++obuf_sel;
-                    if (leader) tma_store_wait_read1();  // the store issued two chunks ago has drained this buffer
+                    if (lead_warp) {
+                        if (elect_one()) tma_store_wait_read1();  // the store issued two chunks ago has drained this buffer
+                        __syncwarp();
+                    }
                     if (cc == 0) {   // (readers of the previous tile's bias are past that tile's last barrier)
 #pragma unroll
                         for (int i = 0; i < (BN + 127) / 128; ++i)
@@ -486,14 +506,17 @@ __global__ void __launch_bounds__(gemm_threads(EG, XF), 1) conv_gemm_kernel(cons
                     }
                     fence_proxy_async_smem();
                     named_bar_sync(ebar, 128);
-                    if (leader && !(p.dbg & 1)) {
-                        int c[5] = {0, org[1], org[2], org[3], org[4]};
+                    if (lead_warp && !(p.dbg & 1)) {
+                        if (elect_one()) {
+                            int c[5] = {0, org[1], org[2], org[3], org[4]};
 #pragma unroll
-                        for (int u = 0; u < S::UNITS; ++u) {
-                            c[0] = n_idx * BN + cc * OC + u * 64;
-                            tma_store_nd(p.rank, &p.o_map, obuf + u * (GEMM_BM * 128), c);
+                            for (int u = 0; u < S::UNITS; ++u) {
+                                c[0] = n_idx * BN + cc * OC + u * 64;
+                                tma_store_nd(p.rank, &p.o_map, obuf + u * (GEMM_BM * 128), c);
+                            }
+                            tma_store_commit();
                         }
-                        tma_store_commit();
+                        __syncwarp();
                     }
                     if (p.stats != nullptr) {
                         // Column sums of the staged fp16 chunk without atomics, one 64-column unit at a time: lane & 15 =
@@ -587,7 +610,10 @@ __global__ void __launch_bounds__(gemm_threads(EG, XF), 1) conv_gemm_kernel(cons
             }
         }
         if constexpr (BN >= 64) {
-            if (leader) tma_store_wait_all0();
+            if (lead_warp) {
+                if (elect_one()) tma_store_wait_all0();
+                __syncwarp();
+            }
         }
     }
 

@@ -577,7 +577,7 @@ struct OpConvGn {
     const float* gamma; const float* beta; const float* film; int film_ld; int ns; int ns_per_batch; int silu;
 };
 
-static int op_conv_impl(const MmdConvDesc* d, const OpConvGn* gn, void* stream) {
+static int op_conv_impl(const MmdConvDesc* d, const OpConvGn* gn, void* stream, int reps = 1, float* us_per_launch = nullptr) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (!d) return fail(MMD_EINVAL, "null conv desc");
     GemmProblem pr;
@@ -664,6 +664,21 @@ static int op_conv_impl(const MmdConvDesc* d, const OpConvGn* gn, void* stream) 
     GemmParams gp;
     if (r == MMD_OK) r = build_gemm(pr, &gp);
     if (r == MMD_OK) r = launch_gemm(gp, pr.bn, st);
+    if (r == MMD_OK && us_per_launch) {
+        // measurement entry: the packed problem launched `reps` more times back to back between two events on `st`
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        MMD_CUDA_OK(cudaEventCreate(&e0));
+        MMD_CUDA_OK(cudaEventCreate(&e1));
+        MMD_CUDA_OK(cudaEventRecord(e0, st));
+        for (int i = 0; i < reps && r == MMD_OK; ++i) r = launch_gemm(gp, pr.bn, st);
+        MMD_CUDA_OK(cudaEventRecord(e1, st));
+        MMD_CUDA_OK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        MMD_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+        *us_per_launch = reps > 0 ? ms * 1000.f / reps : 0.f;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    }
     cudaFreeAsync(wp, st);
     cudaFreeAsync(bp, st);
     if (xsums) cudaFreeAsync(xsums, st);
@@ -671,6 +686,11 @@ static int op_conv_impl(const MmdConvDesc* d, const OpConvGn* gn, void* stream) 
 }
 
 int mmd_op_conv(const MmdConvDesc* d, void* stream) { return op_conv_impl(d, nullptr, stream); }
+
+int mmd_op_conv_timed(const MmdConvDesc* d, int reps, float* us_per_launch, void* stream) {
+    if (reps <= 0 || !us_per_launch) return fail(MMD_EINVAL, "conv_timed: reps > 0 and a result pointer required");
+    return op_conv_impl(d, nullptr, stream, reps, us_per_launch);
+}
 
 int mmd_op_conv_gn(const MmdConvDesc* d, const float* gamma, const float* beta, const float* film, int film_ld, int ns,
                    int ns_per_batch, int silu, void* stream) {

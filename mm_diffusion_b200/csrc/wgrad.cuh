@@ -134,8 +134,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_kernel(const __grid_
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ================= TMA producer =================
-        if (lane == 0) {
+        // ================= TMA producer (uniform warp, elected lane issues; see gemm.cuh) =================
+        {
             int stage = 0;
             uint32_t phase = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -146,26 +146,29 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_kernel(const __grid_
                     wgrad_tile_origin(p, m, org);
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* dst = smem + stage * WG_STAGE_BYTES;
-                    mbar_expect_tx(&full_bar[stage], bytes);
-                    c[1] = org[1]; c[2] = org[2]; c[3] = org[3]; c[4] = org[4];
-                    for (int h = 0; h < 2; ++h) {
-                        c[0] = w.n_tile * 128 + h * 64;
-                        tma_load_nd(p.rank, dst + h * (GEMM_BM * 128), &p.dy_map, &full_bar[stage], c);
+                    if (elect_one()) {
+                        mbar_expect_tx(&full_bar[stage], bytes);
+                        c[1] = org[1]; c[2] = org[2]; c[3] = org[3]; c[4] = org[4];
+                        for (int h = 0; h < 2; ++h) {
+                            c[0] = w.n_tile * 128 + h * 64;
+                            tma_load_nd(p.rank, dst + h * (GEMM_BM * 128), &p.dy_map, &full_bar[stage], c);
+                        }
+                        c[1] = org[1] + p.tap[w.tap][0];
+                        c[2] = org[2] + p.tap[w.tap][1];
+                        c[3] = org[3] + p.tap[w.tap][2];
+                        for (int h = 0; h < w.ncols / 64; ++h) {
+                            c[0] = (w.chunk0 + h) * GEMM_BK;
+                            tma_load_nd(p.rank, dst + WG_DY_BYTES + h * (GEMM_BM * 128), &p.a_map[w.src], &full_bar[stage], c);
+                        }
                     }
-                    c[1] = org[1] + p.tap[w.tap][0];
-                    c[2] = org[2] + p.tap[w.tap][1];
-                    c[3] = org[3] + p.tap[w.tap][2];
-                    for (int h = 0; h < w.ncols / 64; ++h) {
-                        c[0] = (w.chunk0 + h) * GEMM_BK;
-                        tma_load_nd(p.rank, dst + WG_DY_BYTES + h * (GEMM_BM * 128), &p.a_map[w.src], &full_bar[stage], c);
-                    }
+                    __syncwarp();
                     if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
+        // ================= MMA issuer (uniform warp, elected lane issues) =================
+        {
             constexpr uint32_t idesc128 = umma_idesc_f16(128, 128, 1, 1);
             constexpr uint32_t idesc64 = umma_idesc_f16(128, 64, 1, 1);
             constexpr uint32_t idesc16 = umma_idesc_f16(128, 16, 1, 1);
@@ -190,16 +193,20 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_kernel(const __grid_
                     // chunk of the M / N extent sits one [128 x 128 B] unit further (LBO)
                     const uint64_t ad0 = umma_desc_sw128(base, GEMM_BM * 128, 1024);
                     const uint64_t bd0 = umma_desc_sw128(base + WG_DY_BYTES, GEMM_BM * 128, 1024);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int ks = 0; ks < GEMM_BM / 16; ++ks) {
-                        umma_f16_ss(d_tmem, ad0 + ks * (2048 >> 4), bd0 + ks * (2048 >> 4), idesc, first ? 0u : 1u);
-                        if (w.bias) umma_f16_ss(tmem_base + 256 + acc * 16, ad0 + ks * (2048 >> 4), ones_d, idesc16, first ? 0u : 1u);
-                        first = false;
+                        for (int ks = 0; ks < GEMM_BM / 16; ++ks) {
+                            const uint32_t accum = (first && ks == 0) ? 0u : 1u;
+                            umma_f16_ss(d_tmem, ad0 + ks * (2048 >> 4), bd0 + ks * (2048 >> 4), idesc, accum);
+                            if (w.bias) umma_f16_ss(tmem_base + 256 + acc * 16, ad0 + ks * (2048 >> 4), ones_d, idesc16, accum);
+                        }
+                        umma_commit(&empty_bar[stage]);
+                        if (m == w.m_end - 1) umma_commit(&tfull_bar[acc]);
                     }
-                    umma_commit(&empty_bar[stage]);
+                    __syncwarp();
+                    first = false;
                     if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tfull_bar[acc]);
             }
         }
     } else {

@@ -18,7 +18,7 @@ from ._lib import MmdAttnDesc, MmdConvDesc, check, current_stream_ptr, ptr
 
 
 def _conv(srcs, weight, bias, n, rank, dims, taps, out=None, out_f32=None, ostride=None, ostride_c=0, gn_sums=None,
-          gn_rows=0, gn_in=None):
+          gn_rows=0, gn_in=None, timed_reps=0):
     lib = _lib.load()
     d = MmdConvDesc()
     d.rank = rank
@@ -58,6 +58,10 @@ def _conv(srcs, weight, bias, n, rank, dims, taps, out=None, out_f32=None, ostri
         check(lib.mmd_op_conv_gn(C.byref(d), g.data_ptr(), b2.data_ptr(), ptr(f), 0 if f is None else f.shape[-1],
                                  int(gn_in["ns"]), int(gn_in.get("ns_per_batch", 1)), int(bool(gn_in.get("silu", False))),
                                  current_stream_ptr()))
+    elif timed_reps > 0:   # measurement: average device microseconds per launch over timed_reps back-to-back launches
+        us = C.c_float(0.0)
+        check(lib.mmd_op_conv_timed(C.byref(d), int(timed_reps), C.byref(us), current_stream_ptr()))
+        return us.value
     else:
         check(lib.mmd_op_conv(C.byref(d), current_stream_ptr()))
     return out if out is not None else out_f32
