@@ -1223,7 +1223,7 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention64x2_kernel(const __
     if (warp == 8) {
         // ===================== TMA producer =====================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ATT2_REGS_PRODUCER));
-        if (lane == 0) {
+        {   // uniform warp, elected lane issues (see gemm.cuh)
             int n = 0;    // K/V tiles issued so far (all items)
             int it = 0;   // items started
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
@@ -1231,27 +1231,36 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention64x2_kernel(const __
                 const AttnWork& w = w2.w;
                 const bool two = w2.qv[1] > 0;
                 mbar_wait(q_empty, (it & 1) ^ 1);   // the last Q·K^T of the previous item has retired
-                mbar_expect_tx(q_full, two ? 32768 : 16384);
-                tma_load_2d(smem + S::Q_OFF, &p.q_map, q_full, p.q_col0 + w.head * D, w.q_row0);
-                if (two) tma_load_2d(smem + S::Q_OFF + 16384, &p.q_map, q_full, p.q_col0 + w.head * D, w.q_row0 + ATT_BQ);
+                if (elect_one()) {
+                    mbar_expect_tx(q_full, two ? 32768 : 16384);
+                    tma_load_2d(smem + S::Q_OFF, &p.q_map, q_full, p.q_col0 + w.head * D, w.q_row0);
+                    if (two) tma_load_2d(smem + S::Q_OFF + 16384, &p.q_map, q_full, p.q_col0 + w.head * D, w.q_row0 + ATT_BQ);
+                }
+                __syncwarp();
                 for (int t = 0; t < w.n_tiles; ++t, ++n) {
                     const int st = n & 1;
                     const uint32_t ph = (n >> 1) & 1;
                     int krow, kvalid;
                     attn_tile(w, t, krow, kvalid);
                     mbar_wait(&k_empty[st], ph ^ 1);
-                    mbar_expect_tx(&k_full[st], 16384);
-                    tma_load_2d(smem + S::K_OFF + st * 16384, &p.k_map, &k_full[st], p.k_col0 + w.head * D, krow);
+                    if (elect_one()) {
+                        mbar_expect_tx(&k_full[st], 16384);
+                        tma_load_2d(smem + S::K_OFF + st * 16384, &p.k_map, &k_full[st], p.k_col0 + w.head * D, krow);
+                    }
+                    __syncwarp();
                     mbar_wait(&v_empty[st], ph ^ 1);
-                    mbar_expect_tx(&v_full[st], 16384);
-                    tma_load_2d(smem + S::V_OFF + st * 16384, &p.v_map, &v_full[st], p.v_col0 + w.head * D, krow);
+                    if (elect_one()) {
+                        mbar_expect_tx(&v_full[st], 16384);
+                        tma_load_2d(smem + S::V_OFF + st * 16384, &p.v_map, &v_full[st], p.v_col0 + w.head * D, krow);
+                    }
+                    __syncwarp();
                 }
             }
         }
     } else if (warp == 9) {
         // ===================== MMA issuer =====================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ATT2_REGS_PRODUCER));
-        if (lane == 0) {
+        {   // uniform warp, elected lane issues
             constexpr uint32_t idesc_qk = umma_idesc_f16(ATT_BQ, ATT_BKV, 0, 0);
             const uint64_t qd0 = umma_desc_sw128(smem_u32(smem + S::Q_OFF), 16, 1024);
             const uint64_t kd0 = umma_desc_sw128(smem_u32(smem + S::K_OFF), 16, 1024);
@@ -1273,11 +1282,14 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention64x2_kernel(const __
                 const uint64_t qd = qd0 + static_cast<uint64_t>(grp) * (16384 >> 4);
                 const uint64_t kd = kd0 + static_cast<uint64_t>(st) * (16384 >> 4);
                 const uint32_t tS = tmem_base + grp * 128;
+                if (elect_one()) {
 #pragma unroll
-                for (int ks = 0; ks < D / 16; ++ks) umma_f16_ss(tS, qd + 2 * ks, kd + 2 * ks, idesc_qk, ks != 0 ? 1u : 0u);
-                if (last_of_tile) umma_commit(&k_empty[st]);
-                if (last_of_tile && last_of_item) umma_commit(q_empty);
-                umma_commit(&s_full[grp]);
+                    for (int ks = 0; ks < D / 16; ++ks) umma_f16_ss(tS, qd + 2 * ks, kd + 2 * ks, idesc_qk, ks != 0 ? 1u : 0u);
+                    if (last_of_tile) umma_commit(&k_empty[st]);
+                    if (last_of_tile && last_of_item) umma_commit(q_empty);
+                    umma_commit(&s_full[grp]);
+                }
+                __syncwarp();
             };
             int n = 0;   // global index of the current K/V tile
             bool have = static_cast<int>(blockIdx.x) < n_items;
@@ -1305,10 +1317,13 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention64x2_kernel(const __
                         mbar_wait(&p_ready[grp], gs[grp] & 1);
                         mbar_wait(&v_full[vst], vph);
                         tc_fence_after();
-                        attn64_issue_pv(tmem_base + 256 + grp * 64, tmem_base + 384 + grp * 16,
-                                        pd0 + static_cast<uint64_t>(grp) * (32768 >> 4), vd, od0, kvalid, t);
-                        umma_commit(&v_empty[vst]);
-                        umma_commit(&o_full[grp]);
+                        if (elect_one()) {
+                            attn64_issue_pv(tmem_base + 256 + grp * 64, tmem_base + 384 + grp * 16,
+                                            pd0 + static_cast<uint64_t>(grp) * (32768 >> 4), vd, od0, kvalid, t);
+                            umma_commit(&v_empty[vst]);
+                            umma_commit(&o_full[grp]);
+                        }
+                        __syncwarp();
                         ++gs[grp];
                         // next logits of this group: same item, or the first tile of the next item
                         if (t + 1 < T) {
@@ -1318,7 +1333,8 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention64x2_kernel(const __
                         }
                     }
                     if (!two) {
-                        umma_commit(&v_empty[vst]);   // the idle group's arrival
+                        if (elect_one()) umma_commit(&v_empty[vst]);   // the idle group's arrival
+                        __syncwarp();
                         if (t + 1 == T && next_two) issue_qk(1, n + 1, false, true, nxt.w.n_tiles == 1);
                     }
                 }

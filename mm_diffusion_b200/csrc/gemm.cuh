@@ -84,9 +84,13 @@ struct alignas(64) GemmParams {
     int dbg;
 };
 
-template <int BN, int OC, bool XF = false, int EG = 1>
+// MT = 128-token row blocks per CTA tile.  MT = 2: one weight tile feeds two accumulators (256 tokens x BN per k-block),
+// which cuts the L2 -> shared-memory bytes per flop by 25 % (BN 128) / 33 % (BN 256): at 128 x BN tiles the K loop of
+// every conv family sits on the L2 delivery rate (~43 B/clk/SM with all SMs loading), not on the tensor pipe.
+template <int BN, int OC, bool XF = false, int EG = 1, int MT = 1>
 struct GemmSmem {
-    static constexpr int A_BYTES = GEMM_BM * 128;
+    static constexpr int A_ONE = GEMM_BM * 128;
+    static constexpr int A_BYTES = MT * A_ONE;
     static constexpr int B_BYTES = BN * 128;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     // epilogue staging: two buffers of OC columns (OC/64 swizzled 16 KB units each), rotated per chunk, so the TMA
@@ -110,9 +114,13 @@ struct GemmSmem {
     static constexpr int STAGES = FIT > 8 ? 8 : FIT;
     static constexpr int TOTAL = STAGES * STAGE_BYTES + OUT_BYTES + BAR_BYTES;   // base is 1024-aligned (checked)
     static_assert(BN < 64 || (OC % 64 == 0 && BN % OC == 0), "staging chunk");
-    static_assert(STAGES >= 3 && TOTAL <= LIMIT, "shared memory budget");
+    static_assert(STAGES >= (MT == 2 ? 2 : 3) && TOTAL <= LIMIT, "shared memory budget");
     static_assert(3 * STAGES + 4 <= 30, "barrier block");
-    static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : ((2 * BN <= 64) ? 64 : ((2 * BN <= 128) ? 128 : ((2 * BN <= 256) ? 256 : 512)));
+    static_assert(MT == 1 || (MT == 2 && EG == 2 && !XF && BN >= 128), "256-token tiles: one epilogue warpgroup per row block");
+    // accumulator stages: double buffered unless two 256-column accumulators already fill the 512 TMEM columns
+    static constexpr int NACC = (2 * MT * BN <= 512) ? 2 : 1;
+    static constexpr int ACC_COLS = NACC * MT * BN;
+    static constexpr int TMEM_COLS = (ACC_COLS <= 32) ? 32 : ((ACC_COLS <= 64) ? 64 : ((ACC_COLS <= 128) ? 128 : ((ACC_COLS <= 256) ? 256 : 512)));
 };
 
 MMD_DEVINL void gemm_tile_origin(const GemmParams& p, int m_idx, int* c /*[5]*/) {
@@ -126,9 +134,9 @@ MMD_DEVINL void gemm_tile_origin(const GemmParams& p, int m_idx, int* c /*[5]*/)
     c[0] = 0;
 }
 
-template <int BN, int OC, bool XF, int EG>
+template <int BN, int OC, bool XF, int EG, int MT>
 __global__ void __launch_bounds__(gemm_threads(EG, XF), 1) conv_gemm_kernel(const __grid_constant__ GemmParams p) {
-    using S = GemmSmem<BN, OC, XF, EG>;
+    using S = GemmSmem<BN, OC, XF, EG, MT>;
     static_assert(EG == 1 || EG == 2, "one or two epilogue warpgroups");
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* stage_base = smem;
@@ -145,7 +153,7 @@ __global__ void __launch_bounds__(gemm_threads(EG, XF), 1) conv_gemm_kernel(cons
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int total_tiles = p.m_tiles * p.n_tiles;
+    const int total_tiles = ((p.m_tiles + MT - 1) / MT) * p.n_tiles;   // CTA tiles: MT row blocks x one column block
     // Tile schedule of this CTA.  Plain kernels: strided (tile = blockIdx.x + i * gridDim.x): the N tiles of one row block
     // run at the same time on neighbouring CTAs and share the A tile through L2.  XF kernels: a contiguous range, so a CTA
     // stays inside one GroupNorm domain for many tiles and rebuilds its affine table once or twice instead of per tile.
@@ -172,7 +180,7 @@ __global__ void __launch_bounds__(gemm_threads(EG, XF), 1) conv_gemm_kernel(cons
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], 4);
+            mbar_init(&tempty_bar[i], 4 * MT);   // MT = 2: both epilogue warpgroups read every accumulator stage
         }
         fence_mbar_init();
     }
@@ -194,9 +202,11 @@ __global__ void __launch_bounds__(gemm_threads(EG, XF), 1) conv_gemm_kernel(cons
             if (tile_begin < tile_end) {
                 const int n_idx0 = tile_begin % p.n_tiles;
                 pre = (p.dbg & 24) ? 0 : min(S::STAGES, num_kb);
+                // (an incomplete last row-block pair loads one A block only)
+                const int nv0 = min(MT, p.m_tiles - (tile_begin / p.n_tiles) * MT);
                 if (elect_one()) {
                     for (int kb = 0; kb < pre; ++kb) {
-                        mbar_expect_tx(&full_bar[kb], S::STAGE_BYTES);
+                        mbar_expect_tx(&full_bar[kb], S::B_BYTES + nv0 * S::A_ONE);
                         tma_load_2d(stage_base + kb * S::STAGE_BYTES + S::A_BYTES, &p.b_map, &full_bar[kb], kb * GEMM_BK, n_idx0 * BN);
                     }
                 }
@@ -206,7 +216,7 @@ __global__ void __launch_bounds__(gemm_threads(EG, XF), 1) conv_gemm_kernel(cons
             // A tiles of the next pf_tiles-1 tiles of this CTA go to L2 right away; inside the loop every k-block load
             // is paired with the prefetch of the same k-block pf_tiles tiles ahead
             const int pf = p.pf_tiles;
-            if (pf > 1 && lane == 0) {
+            if (MT == 1 && pf > 1 && lane == 0) {
                 for (int d = 1; d < pf; ++d) {
                     const int tile = tile_begin + d * tile_step;
                     if (tile >= tile_end) break;
@@ -227,12 +237,16 @@ __global__ void __launch_bounds__(gemm_threads(EG, XF), 1) conv_gemm_kernel(cons
             uint32_t phase = 0;
             int gk = 0;   // k-blocks issued by this CTA (the first `pre` already have their B half in flight)
             for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
-                const int m_idx = tile / p.n_tiles;
-                const int n_idx = tile - m_idx * p.n_tiles;
+                const int mp = tile / p.n_tiles;
+                const int n_idx = tile - mp * p.n_tiles;
+                const int m_idx = mp * MT;
+                const int nv = min(MT, p.m_tiles - m_idx);   // row blocks of this tile that exist
                 int org[5];
                 gemm_tile_origin(p, m_idx, org);
+                int org1[5] = {0, 0, 0, 0, 0};
+                if (MT == 2 && nv == 2) gemm_tile_origin(p, m_idx + 1, org1);
                 const int pf_tile = tile + pf * tile_step;
-                const bool pf_on = pf > 0 && pf_tile < tile_end;
+                const bool pf_on = MT == 1 && pf > 0 && pf_tile < tile_end;
                 int porg[5] = {0, 0, 0, 0, 0};
                 if (pf_on) gemm_tile_origin(p, pf_tile / p.n_tiles, porg);
                 int kb = 0;
@@ -254,16 +268,26 @@ __global__ void __launch_bounds__(gemm_threads(EG, XF), 1) conv_gemm_kernel(cons
                                     tma_prefetch_nd(p.rank, &p.a_map[s], pc);
                                 }
                                 if (p.dbg & 24) {   // ablation: drop the A and / or B loads
-                                    const uint32_t bytes = ((p.dbg & 8) ? 0 : S::A_BYTES) + ((p.dbg & 16) ? 0 : S::B_BYTES);
+                                    const uint32_t bytes = ((p.dbg & 8) ? 0 : nv * S::A_ONE) + ((p.dbg & 16) ? 0 : S::B_BYTES);
                                     if (bytes == 0) { mbar_arrive(&full_bar[stage]); }
                                     else {
                                         mbar_expect_tx(&full_bar[stage], bytes);
-                                        if (!(p.dbg & 8)) tma_load_nd(p.rank, a_dst, &p.a_map[s], &full_bar[stage], c);
+                                        if (!(p.dbg & 8)) {
+                                            tma_load_nd(p.rank, a_dst, &p.a_map[s], &full_bar[stage], c);
+                                            if (MT == 2 && nv == 2) {
+                                                const int c1[5] = {c[0], org1[1] + p.tap[t][0], org1[2] + p.tap[t][1], org1[3] + p.tap[t][2], org1[4]};
+                                                tma_load_nd(p.rank, a_dst + S::A_ONE, &p.a_map[s], &full_bar[stage], c1);
+                                            }
+                                        }
                                         if (!(p.dbg & 16)) tma_load_2d(a_dst + S::A_BYTES, &p.b_map, &full_bar[stage], kb * GEMM_BK, n_idx * BN);
                                     }
                                 } else {
-                                    if (gk >= pre) mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+                                    if (gk >= pre) mbar_expect_tx(&full_bar[stage], S::B_BYTES + nv * S::A_ONE);
                                     tma_load_nd(p.rank, a_dst, &p.a_map[s], &full_bar[stage], c);
+                                    if (MT == 2 && nv == 2) {
+                                        const int c1[5] = {c[0], org1[1] + p.tap[t][0], org1[2] + p.tap[t][1], org1[3] + p.tap[t][2], org1[4]};
+                                        tma_load_nd(p.rank, a_dst + S::A_ONE, &p.a_map[s], &full_bar[stage], c1);
+                                    }
                                     if (gk >= pre) tma_load_2d(a_dst + S::A_BYTES, &p.b_map, &full_bar[stage], kb * GEMM_BK, n_idx * BN);
                                 }
                             }
@@ -287,11 +311,12 @@ __global__ void __launch_bounds__(gemm_threads(EG, XF), 1) conv_gemm_kernel(cons
             uint32_t phase = 0;
             int it = 0;
             for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++it) {
-                const int acc = it & 1;
-                const uint32_t acc_phase = (it >> 1) & 1;
+                const int acc = (S::NACC == 2) ? (it & 1) : 0;
+                const uint32_t acc_phase = (S::NACC == 2) ? ((it >> 1) & 1) : (it & 1);
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
+                const uint32_t d_tmem = tmem_base + acc * (MT * BN);
+                const bool two = MT == 2 && (tile / p.n_tiles) * MT + 1 < p.m_tiles;   // second row block exists
                 for (int kb = 0; kb < num_kb; ++kb) {
                     // XF kernels: every k-block is handed over by the transform warps (they wait for the TMA, transform the
                     // blocks of source 0 and pass the others through), so all roles follow the ring in lock-step
@@ -307,6 +332,12 @@ __global__ void __launch_bounds__(gemm_threads(EG, XF), 1) conv_gemm_kernel(cons
 #pragma unroll
                             for (int k = 0; k < GEMM_BK / 16; ++k)
                                 umma_f16_ss(d_tmem, ad0 + 2 * k, bd0 + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                            if (two) {   // second row block of the tile: same weight tile, its own accumulator columns
+                                constexpr uint64_t a1 = S::A_ONE >> 4;
+#pragma unroll
+                                for (int k = 0; k < GEMM_BK / 16; ++k)
+                                    umma_f16_ss(d_tmem + BN, ad0 + a1 + 2 * k, bd0 + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                            }
                         }
                         umma_commit(&empty_bar[stage]);
                         if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
@@ -436,11 +467,20 @@ __global__ void __launch_bounds__(gemm_threads(EG, XF), 1) conv_gemm_kernel(cons
         int it = 0;
         uint32_t obuf_sel = 0;   // staging buffer rotation (leader's bulk-group order matches it)
         for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++it) {
-            if (EG == 2 && (it & 1) != eg) continue;
-            const int acc = it & 1;
-            const uint32_t acc_phase = (it >> 1) & 1;
-            const int m_idx = tile / p.n_tiles;
-            const int n_idx = tile - m_idx * p.n_tiles;
+            // EG = 2, MT = 1: the groups take alternate tiles; MT = 2: group g drains row block g of every tile
+            if (MT == 1 && EG == 2 && (it & 1) != eg) continue;
+            const int acc = (S::NACC == 2) ? (it & 1) : 0;
+            const uint32_t acc_phase = (S::NACC == 2) ? ((it >> 1) & 1) : (it & 1);
+            const int mp = tile / p.n_tiles;
+            const int n_idx = tile - mp * p.n_tiles;
+            const int m_idx = mp * MT + (MT == 2 ? eg : 0);
+            if (MT == 2 && m_idx >= p.m_tiles) {   // missing second row block of the last pair: keep the barrier protocol going
+                mbar_wait(&tfull_bar[acc], acc_phase);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                continue;
+            }
             int org[5];
             gemm_tile_origin(p, m_idx, org);
             const float* bias = p.bias + n_idx * BN;
@@ -452,7 +492,7 @@ __global__ void __launch_bounds__(gemm_threads(EG, XF), 1) conv_gemm_kernel(cons
             }
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-            const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN;
+            const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * (MT * BN) + (MT == 2 ? eg * BN : 0);
 
             if constexpr (BN >= 64) {
                 int valid_rows = GEMM_BM;

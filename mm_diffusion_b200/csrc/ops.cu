@@ -205,10 +205,10 @@ int build_gemm(const GemmProblem& pr, GemmParams* out) {
     return MMD_OK;
 }
 
-template <int BN, int OC, bool XF = false, int EG = 1>
+template <int BN, int OC, bool XF = false, int EG = 1, int MT = 1>
 static int gemm_attr() {
-    MMD_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<BN, OC, XF, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     GemmSmem<BN, OC, XF, EG>::TOTAL));
+    MMD_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<BN, OC, XF, EG, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     GemmSmem<BN, OC, XF, EG, MT>::TOTAL));
     return MMD_OK;
 }
 
@@ -224,6 +224,7 @@ int gemm_init_attrs() {
     MMD_TRY((gemm_attr<256, 64, false, 2>()));
     MMD_TRY((gemm_attr<128, 64, false, 2>()));
     MMD_TRY((gemm_attr<64, 64, false, 2>()));
+    MMD_TRY((gemm_attr<128, 64, false, 2, 2>()));
     MMD_TRY((gemm_attr<256, 64, true>()));
     MMD_TRY((gemm_attr<256, 128, true>()));
     MMD_TRY((gemm_attr<128, 64, true>()));
@@ -277,8 +278,8 @@ int launch_gemm(const GemmParams& p, int bn, cudaStream_t st) {
     num_kb *= p.n_taps;
     const int oc = pick_oc(bn, num_kb);
 #define MMD_GEMM_CASE_EG(BN_, OC_, XF_, EG_)                                                                                 \
-    MMD_CUDA_OK(launch_kernel(conv_gemm_kernel<BN_, OC_, XF_, EG_>, grid, gemm_threads(EG_, XF_),                            \
-                              GemmSmem<BN_, OC_, XF_, EG_>::TOTAL, st, p))
+    MMD_CUDA_OK(launch_kernel(conv_gemm_kernel<BN_, OC_, XF_, EG_, 1>, grid, gemm_threads(EG_, XF_),                         \
+                              GemmSmem<BN_, OC_, XF_, EG_, 1>::TOTAL, st, p))
 #define MMD_GEMM_CASE(BN_, OC_, XF_) MMD_GEMM_CASE_EG(BN_, OC_, XF_, 1)
     if (p.xf_sums != nullptr) {   // fused GroupNorm apply on the A operand: the variant with the four transform warps
         if (bn == 256 && oc == 64) MMD_GEMM_CASE(256, 64, true);
@@ -303,6 +304,20 @@ int launch_gemm(const GemmParams& p, int bn, cudaStream_t st) {
         else MMD_GEMM2_CASE(128, 128);
 #undef MMD_GEMM2_CASE
         return MMD_OK;
+    }
+    // 256-token CTA tiles for the 128-column shapes (two row blocks share every weight tile: 25 % fewer L2 -> shared-memory
+    // bytes per flop) once the row-block pairs still give every SM a tile.  Measured (B200, production shapes): 3x3 at 64
+    // px 94 -> 78 us, temporal k3 43 -> 37 us, audio k3 22.5 -> 18.4 us, qkv at 16 px 26.8 -> 21.8 us.  The 256-column
+    // variant (two stages, single-buffered accumulators: 2 x 256 columns fill the TMEM) measured slower and is not built.
+    // MMD_MT: 0 = never, 1 = auto (default).
+    static const int mt_mode = [] { const char* e = getenv("MMD_MT"); return e ? atoi(e) : 1; }();
+    if (mt_mode == 1 && p.out_mode == 0 && bn == 128) {
+        const int pair_tiles = ((p.m_tiles + 1) / 2) * p.n_tiles;
+        if (pair_tiles >= num_sms()) {
+            MMD_CUDA_OK(launch_kernel(conv_gemm_kernel<128, 64, false, 2, 2>, std::min(pair_tiles, num_sms()), gemm_threads(2, false),
+                                      GemmSmem<128, 64, false, 2, 2>::TOTAL, st, p));
+            return MMD_OK;
+        }
     }
     // Two epilogue warpgroups (alternate tiles, one TMEM accumulator stage each) where the epilogue is the long pole:
     // short-K GEMMs with more than one tile per CTA.  MMD_EG: 0 = never, 1 = short-K only (default), 2 = every GEMM.
