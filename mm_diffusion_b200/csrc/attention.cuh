@@ -843,260 +843,6 @@ MMD_DEVINL void attn64_issue_pv(uint32_t tmem_O, uint32_t tmem_L, uint64_t pd0, 
     }
 }
 
-// ===========================================================================
-// attention64p_kernel — head_dim 64, software-pipelined: the logits of the NEXT key tile are computed while the softmax
-// of the current one runs.  The ncu profile of attention64_kernel shows its softmax warps waiting for Q·K^T a quarter of
-// the time (S is single buffered there, so Q·K^T(t+1) can only be issued after P·V(t)); here one CTA per SM owns all 512
-// TMEM columns — S0 | S1 | O | l — and double-buffers S, P, K, V and Q, so the MMA thread runs two tiles ahead:
-//     issue order  QK(0) QK(1) | PV(0) QK(2) | PV(1) QK(3) | ...      (QK(n+2) needs S[n&1], free once p_ready(n) fired)
-// and the softmax warps go from tile to tile without waiting for the tensor core.  Same arithmetic as attention64_kernel.
-// ===========================================================================
-struct Attn64pSmem {
-    static constexpr int Q_OFF = 0;                       // 2 buffers (consecutive items)
-    static constexpr int K_OFF = 2 * 16384;               // 2 stages
-    static constexpr int V_OFF = K_OFF + 2 * 16384;       // 2 stages
-    static constexpr int P_OFF = V_OFF + 2 * 16384;       // 2 buffers of 128 x 128 fp16
-    static constexpr int ONES_OFF = P_OFF + 2 * 32768;
-    static constexpr int BAR_OFF = ONES_OFF + 4096;
-    static constexpr int TOTAL = BAR_OFF + 256 + 1024;
-    static constexpr int TMEM_COLS = 512;                 // S0 0 | S1 128 | O 256 | l 320
-};
-
-// position in a CTA's sequence of (work item, key tile) pairs
-struct AttnCursor {
-    int item, t, ord;   // work item, tile inside it, ordinal of the item inside this CTA
-    AttnWork w;
-    bool valid;
-};
-MMD_DEVINL void attn_cursor_init(AttnCursor& c, const AttnParams& p, int n_items) {
-    c.item = blockIdx.x; c.t = 0; c.ord = 0;
-    c.valid = c.item < n_items;
-    if (c.valid) c.w = attn_decode(p, c.item);
-}
-MMD_DEVINL void attn_cursor_next(AttnCursor& c, const AttnParams& p, int n_items) {
-    if (++c.t < c.w.n_tiles) return;
-    c.t = 0;
-    c.item += gridDim.x;
-    ++c.ord;
-    c.valid = c.item < n_items;
-    if (c.valid) c.w = attn_decode(p, c.item);
-}
-
-template <int PQ>
-__global__ void __launch_bounds__(ATT_THREADS, 1) attention64p_kernel(const __grid_constant__ AttnParams p, int n_items) {
-    using S = Attn64pSmem;
-    constexpr int D = 64;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
-    uint64_t* q_full = bars;         // 2
-    uint64_t* q_empty = bars + 2;    // 2
-    uint64_t* k_full = bars + 4;     // 2
-    uint64_t* k_empty = bars + 6;    // 2
-    uint64_t* v_full = bars + 8;     // 2
-    uint64_t* v_empty = bars + 10;   // 2
-    uint64_t* s_full = bars + 12;    // 2 (one per S buffer)
-    uint64_t* o_full = bars + 14;    // 2 (one per P buffer: P·V of the tile that used it has retired)
-    uint64_t* p_ready = bars + 16;   // 2 (128 arrivals each; by tile parity: a fast warp may be one tile ahead of a slow one,
-                                     //    its arrival must not count towards the previous tile's phase)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-
-    pdl_trigger();
-    if (threadIdx.x == 0) {
-        tma_prefetch_desc(&p.q_map);
-        tma_prefetch_desc(&p.k_map);
-        tma_prefetch_desc(&p.v_map);
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&q_full[i], 1);
-            mbar_init(&q_empty[i], 1);
-            mbar_init(&k_full[i], 1);
-            mbar_init(&k_empty[i], 1);
-            mbar_init(&v_full[i], 1);
-            mbar_init(&v_empty[i], 1);
-            mbar_init(&s_full[i], 1);
-            mbar_init(&o_full[i], 1);
-        }
-        mbar_init(&p_ready[0], 128);
-        mbar_init(&p_ready[1], 128);
-        fence_mbar_init();
-    }
-    for (int i = threadIdx.x; i < 4096 / 16; i += ATT_THREADS)
-        reinterpret_cast<uint4*>(smem + S::ONES_OFF)[i] = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
-    fence_proxy_async_smem();
-    if (warp == 5) tmem_alloc(tmem_slot, S::TMEM_COLS);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    pdl_wait();   // q/k/v come from the previous kernel
-    const uint32_t tmem_O = tmem_base + 256;
-    const uint32_t tmem_L = tmem_base + 320;
-
-    if (warp == 4) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            int n = 0;   // key tiles issued so far (all items)
-            AttnCursor c;
-            attn_cursor_init(c, p, n_items);
-            while (c.valid) {
-                const int qb = c.ord & 1;
-                mbar_wait(&q_empty[qb], ((c.ord >> 1) & 1) ^ 1);
-                mbar_expect_tx(&q_full[qb], 16384);
-                tma_load_2d(smem + S::Q_OFF + qb * 16384, &p.q_map, &q_full[qb], p.q_col0 + c.w.head * D, c.w.q_row0);
-                const int item = c.item;
-                while (c.valid && c.item == item) {
-                    const int st = n & 1;
-                    const uint32_t ph = (n >> 1) & 1;
-                    int krow, kvalid;
-                    attn_tile(c.w, c.t, krow, kvalid);
-                    mbar_wait(&k_empty[st], ph ^ 1);
-                    mbar_expect_tx(&k_full[st], 16384);
-                    tma_load_2d(smem + S::K_OFF + st * 16384, &p.k_map, &k_full[st], p.k_col0 + c.w.head * D, krow);
-                    mbar_wait(&v_empty[st], ph ^ 1);
-                    mbar_expect_tx(&v_full[st], 16384);
-                    tma_load_2d(smem + S::V_OFF + st * 16384, &p.v_map, &v_full[st], p.v_col0 + c.w.head * D, krow);
-                    ++n;
-                    attn_cursor_next(c, p, n_items);
-                }
-            }
-        }
-    } else if (warp == 5) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc_qk = umma_idesc_f16(ATT_BQ, ATT_BKV, 0, 0);
-            const uint64_t qd0 = umma_desc_sw128(smem_u32(smem + S::Q_OFF), 16, 1024);
-            const uint64_t kd0 = umma_desc_sw128(smem_u32(smem + S::K_OFF), 16, 1024);
-            const uint64_t pd0 = umma_desc_sw128(smem_u32(smem + S::P_OFF), 16, 1024);
-            const uint64_t vd0 = umma_desc_sw128(smem_u32(smem + S::V_OFF), ATT_BKV * 128, 1024);   // MN-major V
-            const uint64_t od0 = umma_desc_sw128(smem_u32(smem + S::ONES_OFF), 16, 1024);
-            AttnCursor cq, cp;    // cq: next Q·K^T to issue (runs two tiles ahead), cp: next P·V
-            attn_cursor_init(cq, p, n_items);
-            attn_cursor_init(cp, p, n_items);
-            int nq = 0, np = 0;   // global tile indices of the two cursors
-            auto issue_qk = [&]() {
-                const int qb = cq.ord & 1;
-                if (cq.t == 0) mbar_wait(&q_full[qb], (cq.ord >> 1) & 1);
-                const int st = nq & 1;
-                mbar_wait(&k_full[st], (nq >> 1) & 1);
-                tc_fence_after();
-                const uint64_t qd = qd0 + static_cast<uint64_t>(qb) * (16384 >> 4);
-                const uint64_t kd = kd0 + static_cast<uint64_t>(st) * (16384 >> 4);
-                const uint32_t tS = tmem_base + st * 128;
-#pragma unroll
-                for (int ks = 0; ks < D / 16; ++ks) umma_f16_ss(tS, qd + 2 * ks, kd + 2 * ks, idesc_qk, ks != 0 ? 1u : 0u);
-                umma_commit(&k_empty[st]);
-                if (cq.t == cq.w.n_tiles - 1) umma_commit(&q_empty[qb]);
-                umma_commit(&s_full[st]);
-                ++nq;
-                attn_cursor_next(cq, p, n_items);
-            };
-            if (cq.valid) issue_qk();
-            if (cq.valid) issue_qk();
-            while (cp.valid) {
-                int krow, kvalid;
-                attn_tile(cp.w, cp.t, krow, kvalid);
-                const int st = np & 1;
-                mbar_wait(&p_ready[st], (np >> 1) & 1);
-                mbar_wait(&v_full[st], (np >> 1) & 1);
-                tc_fence_after();
-                attn64_issue_pv(tmem_O, tmem_L, pd0 + static_cast<uint64_t>(st) * (32768 >> 4),
-                                vd0 + static_cast<uint64_t>(st) * (16384 >> 4), od0, kvalid, cp.t);
-                umma_commit(&v_empty[st]);
-                umma_commit(&o_full[st]);
-                ++np;
-                attn_cursor_next(cp, p, n_items);
-                if (cq.valid) issue_qk();   // its S buffer (= the one the softmax just finished reading) is free
-            }
-        }
-    } else {
-        // ===================== softmax warps (thread = query row) =====================
-        const int row = warp * 32 + lane;
-        const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-        int n = 0;   // global tile index
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const AttnWork w = attn_decode(p, item);
-            const int T = w.n_tiles;
-            float m_used = 0.f;
-            const bool warp_active = warp * 32 < w.q_valid;
-            for (int t = 0; t < T; ++t, ++n) {
-                int krow, kvalid;
-                attn_tile(w, t, krow, kvalid);
-                const int sb = n & 1;
-                const uint32_t s_addr = tmem_base + sb * 128 + lane_base;
-                uint8_t* p_smem = smem + S::P_OFF + sb * 32768;
-                mbar_wait(&s_full[sb], (n >> 1) & 1);
-                tc_fence_after();
-                const bool full_tile = (kvalid == ATT_BKV);
-                if (warp_active && t == 0) {   // first tile of the item: the row maximum has to be known first (max pass)
-                    const float mx = full_tile ? attn64_rowmax<true>(s_addr, kvalid) : attn64_rowmax<false>(s_addr, kvalid);
-                    m_used = mx * p.scale_log2;
-                }
-                if (n >= 2) {   // this P buffer was read by P·V of tile n - 2
-                    mbar_wait(&o_full[sb], ((n - 2) >> 1) & 1);
-                    tc_fence_after();
-                }
-                if (warp_active) {
-#pragma unroll 1
-                    for (int attempt = 0; attempt < 2; ++attempt) {
-                        const float amax = full_tile ? attn64_write_p<true, PQ>(s_addr, kvalid, p.scale_log2, -m_used, p_smem, row)
-                                                     : attn64_write_p<false, PQ>(s_addr, kvalid, p.scale_log2, -m_used, p_smem, row);
-                        if (t == 0 || attempt == 1 || !__any_sync(0xffffffffu, amax > ATT_STREAM_LIMIT)) break;
-                        // rare: a row overshot the fp16 range of P against the running maximum — move the maximum, rescale
-                        // O / l (P·V of the previous tile must have retired) and redo the pass
-                        mbar_wait(&o_full[sb ^ 1], ((n - 1) >> 1) & 1);
-                        tc_fence_after();
-                        const float m_new = m_used + fmaxf(amax, 0.f);
-                        attn64_rescale(tmem_O, tmem_L, lane_base, ex2_fast(m_used - m_new));
-                        m_used = m_new;
-                    }
-                    fence_proxy_async_smem();
-                }
-                tc_fence_before();
-                mbar_arrive(&p_ready[sb]);
-            }
-            // ---- item epilogue: O / l -> global (the next item's first P·V waits for our next p_ready arrival)
-            mbar_wait(&o_full[(n - 1) & 1], ((n - 1) >> 1) & 1);
-            tc_fence_after();
-            if (warp_active) {
-                uint32_t lv[16];
-                tmem_ld16(tmem_L + lane_base, lv);
-                tmem_ld_wait();
-                const float inv_l = 1.f / __uint_as_float(lv[0]);
-                if (p.lse != nullptr && row < w.q_valid)
-                    p.lse[static_cast<size_t>(w.head) * p.lse_ld + w.q_row0 + row] = m_used + log2f(__uint_as_float(lv[0]));
-                act_t* orow = p.out + static_cast<size_t>(w.q_row0 + row) * p.out_ld + w.head * D;
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem_O + lane_base + c * 32, v);
-                    tmem_ld_wait();
-                    if (row < w.q_valid) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            uint4 pk;
-                            __half2* ph2 = reinterpret_cast<__half2*>(&pk);
-#pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                ph2[k] = __floats2half2_rn(__uint_as_float(v[j * 8 + 2 * k]) * inv_l, __uint_as_float(v[j * 8 + 2 * k + 1]) * inv_l);
-                            *reinterpret_cast<uint4*>(orow + c * 32 + j * 8) = pk;
-                        }
-                    }
-                }
-            }
-            tc_fence_before();   // O / l reads are complete before this thread's next p_ready arrival
-        }
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 5) {
-        __syncwarp();
-        tmem_dealloc(tmem_base, S::TMEM_COLS);
-    }
-}
 
 // Register-resident logit row (128 fp32) of the two-tile kernel: the four TMEM loads are in flight together and the
 // row is read from TMEM once — the separate max / exp passes of attention64_kernel wait for TMEM four times each.

@@ -29,13 +29,11 @@ constexpr int GEMM_MAX_TAPS = 27;
 // CTA, one per TMEM accumulator stage, so two tiles drain at the same time — the short-K GEMMs are bound by the
 // epilogue, not by the tensor pipe or the loads), then (XF) four warps that transform the A operand (fused GroupNorm apply)
 constexpr int gemm_threads(int eg, bool xf) { return 64 + 128 * eg + (xf ? 128 : 0); }
-constexpr int GEMM_THREADS = gemm_threads(1, false);   // the pair kernel (gemm2.cuh) keeps one epilogue warpgroup
 constexpr int GEMM_XF_MAXC = 512;  // widest source the fused GroupNorm apply supports
 
 struct alignas(64) GemmParams {
-    CUtensorMap a_map[GEMM_MAX_SRC];  // activation sources, rank `rank`, box (64, box[0..3])
+    CUtensorMap a_map[GEMM_MAX_SRC];  // activation sources, always rank 5 (unit extents past `rank`), box (64, box[0..3])
     CUtensorMap b_map;                // packed weights [N, K_total] (K-major), box (64, BN)
-    CUtensorMap b2_map;               // same tensor, box (64, BN / 2): one CTA's half of the tile in the pair kernel (gemm2.cuh)
     CUtensorMap o_map;                // output, same geometry as A (out_mode 0)
     int n_src;
     int src_chunks[GEMM_MAX_SRC];     // 64-channel chunks per source
@@ -134,6 +132,15 @@ MMD_DEVINL void gemm_tile_origin(const GemmParams& p, int m_idx, int* c /*[5]*/)
     c[0] = 0;
 }
 
+// Ablation switches (GemmParams::dbg, MMD_GEMM_DBG) exist only in builds with -DMMD_GEMM_ABLATION
+// (MMD_NVCC_EXTRA=-DMMD_GEMM_ABLATION MMD_LIB_OUT=... python -m mm_diffusion_b200.build; load with MMD_LIB=...): the
+// production library does not carry their loads and branches in the role loops.
+#ifdef MMD_GEMM_ABLATION
+#define GEMM_DBG(p) ((p).dbg)
+#else
+#define GEMM_DBG(p) 0
+#endif
+
 template <int BN, int OC, bool XF, int EG, int MT>
 __global__ void __launch_bounds__(gemm_threads(EG, XF), 1) conv_gemm_kernel(const __grid_constant__ GemmParams p) {
     using S = GemmSmem<BN, OC, XF, EG, MT>;
@@ -201,7 +208,7 @@ __global__ void __launch_bounds__(gemm_threads(EG, XF), 1) conv_gemm_kernel(cons
             int pre = 0;
             if (tile_begin < tile_end) {
                 const int n_idx0 = tile_begin % p.n_tiles;
-                pre = (p.dbg & 24) ? 0 : min(S::STAGES, num_kb);
+                pre = (GEMM_DBG(p) & 24) ? 0 : min(S::STAGES, num_kb);
                 // (an incomplete last row-block pair loads one A block only)
                 const int nv0 = min(MT, p.m_tiles - (tile_begin / p.n_tiles) * MT);
                 if (elect_one()) {
@@ -227,7 +234,7 @@ __global__ void __launch_bounds__(gemm_threads(EG, XF), 1) conv_gemm_kernel(cons
                         for (int s = 0; s < p.n_src; ++s)
                             for (int ch = 0; ch < p.src_chunks[s]; ++ch) {
                                 c[0] = ch * GEMM_BK;
-                                tma_prefetch_nd(p.rank, &p.a_map[s], c);
+                                tma_prefetch_nd(5, &p.a_map[s], c);
                             }
                     }
                 }
@@ -265,28 +272,28 @@ __global__ void __launch_bounds__(gemm_threads(EG, XF), 1) conv_gemm_kernel(cons
                             if (elect_one()) {
                                 if (pf_on) {
                                     pc[0] = ch * GEMM_BK;
-                                    tma_prefetch_nd(p.rank, &p.a_map[s], pc);
+                                    tma_prefetch_nd(5, &p.a_map[s], pc);
                                 }
-                                if (p.dbg & 24) {   // ablation: drop the A and / or B loads
-                                    const uint32_t bytes = ((p.dbg & 8) ? 0 : nv * S::A_ONE) + ((p.dbg & 16) ? 0 : S::B_BYTES);
+                                if (GEMM_DBG(p) & 24) {   // ablation: drop the A and / or B loads
+                                    const uint32_t bytes = ((GEMM_DBG(p) & 8) ? 0 : nv * S::A_ONE) + ((GEMM_DBG(p) & 16) ? 0 : S::B_BYTES);
                                     if (bytes == 0) { mbar_arrive(&full_bar[stage]); }
                                     else {
                                         mbar_expect_tx(&full_bar[stage], bytes);
-                                        if (!(p.dbg & 8)) {
-                                            tma_load_nd(p.rank, a_dst, &p.a_map[s], &full_bar[stage], c);
+                                        if (!(GEMM_DBG(p) & 8)) {
+                                            tma_load_5d(a_dst, &p.a_map[s], &full_bar[stage], c[0], c[1], c[2], c[3], c[4]);
                                             if (MT == 2 && nv == 2) {
                                                 const int c1[5] = {c[0], org1[1] + p.tap[t][0], org1[2] + p.tap[t][1], org1[3] + p.tap[t][2], org1[4]};
-                                                tma_load_nd(p.rank, a_dst + S::A_ONE, &p.a_map[s], &full_bar[stage], c1);
+                                                tma_load_5d(a_dst + S::A_ONE, &p.a_map[s], &full_bar[stage], c1[0], c1[1], c1[2], c1[3], c1[4]);
                                             }
                                         }
-                                        if (!(p.dbg & 16)) tma_load_2d(a_dst + S::A_BYTES, &p.b_map, &full_bar[stage], kb * GEMM_BK, n_idx * BN);
+                                        if (!(GEMM_DBG(p) & 16)) tma_load_2d(a_dst + S::A_BYTES, &p.b_map, &full_bar[stage], kb * GEMM_BK, n_idx * BN);
                                     }
                                 } else {
                                     if (gk >= pre) mbar_expect_tx(&full_bar[stage], S::B_BYTES + nv * S::A_ONE);
-                                    tma_load_nd(p.rank, a_dst, &p.a_map[s], &full_bar[stage], c);
+                                    tma_load_5d(a_dst, &p.a_map[s], &full_bar[stage], c[0], c[1], c[2], c[3], c[4]);
                                     if (MT == 2 && nv == 2) {
                                         const int c1[5] = {c[0], org1[1] + p.tap[t][0], org1[2] + p.tap[t][1], org1[3] + p.tap[t][2], org1[4]};
-                                        tma_load_nd(p.rank, a_dst + S::A_ONE, &p.a_map[s], &full_bar[stage], c1);
+                                        tma_load_5d(a_dst + S::A_ONE, &p.a_map[s], &full_bar[stage], c1[0], c1[1], c1[2], c1[3], c1[4]);
                                     }
                                     if (gk >= pre) tma_load_2d(a_dst + S::A_BYTES, &p.b_map, &full_bar[stage], kb * GEMM_BK, n_idx * BN);
                                 }
@@ -307,6 +314,7 @@ __global__ void __launch_bounds__(gemm_threads(EG, XF), 1) conv_gemm_kernel(cons
         // for a 128 x 128 x 64 block (measured: the k-block loop alone, no loads / MMAs / epilogue, cost ~500 cycles).
         {
             constexpr uint32_t idesc = umma_idesc_f16(GEMM_BM, BN, 0, 0);
+            const uint64_t a_desc0 = umma_desc_sw128(smem_u32(stage_base), 16, 1024);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -322,13 +330,12 @@ __global__ void __launch_bounds__(gemm_threads(EG, XF), 1) conv_gemm_kernel(cons
                     // blocks of source 0 and pass the others through), so all roles follow the ring in lock-step
                     mbar_wait(XF ? &xf_bar[stage] : &full_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(stage_base + stage * S::STAGE_BYTES);
-                    // one descriptor per operand and k-iteration; the 16-element k-steps only bump the 16-byte-unit
-                    // start-address field (+32 bytes = +2)
-                    const uint64_t ad0 = umma_desc_sw128(a_addr, 16, 1024);
-                    const uint64_t bd0 = umma_desc_sw128(a_addr + S::A_BYTES, 16, 1024);
+                    // descriptors: stage 0's plus the stage offset in the 16-byte-unit start-address field (shared memory
+                    // is < 256 KB, so the 14-bit field cannot carry); the 16-element k-steps bump it by +32 bytes = +2
+                    const uint64_t ad0 = a_desc0 + static_cast<uint64_t>(stage * (S::STAGE_BYTES >> 4));
+                    const uint64_t bd0 = ad0 + (S::A_BYTES >> 4);
                     if (elect_one()) {
-                        if (!(p.dbg & 4)) {
+                        if (!(GEMM_DBG(p) & 4)) {
 #pragma unroll
                             for (int k = 0; k < GEMM_BK / 16; ++k)
                                 umma_f16_ss(d_tmem, ad0 + 2 * k, bd0 + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
@@ -514,10 +521,10 @@ __global__ void __launch_bounds__(gemm_threads(EG, XF), 1) conv_gemm_kernel(cons
                     named_bar_sync(ebar, 128);
                     // accumulator -> fp16 staging, 32 columns at a time with the next TMEM load already in flight
                     uint32_t va[32], vb[32];
-                    if (!(p.dbg & 2)) tmem_ld32(t_addr + cc * OC, va);
+                    if (!(GEMM_DBG(p) & 2)) tmem_ld32(t_addr + cc * OC, va);
 #pragma unroll
                     for (int l = 0; l < OC / 32; ++l) {
-                        if (p.dbg & 2) break;
+                        if (GEMM_DBG(p) & 2) break;
                         uint32_t* v = (l & 1) ? vb : va;
                         tmem_ld_wait();
                         if (l + 1 < OC / 32) tmem_ld32(t_addr + cc * OC + (l + 1) * 32, (l & 1) ? va : vb);
@@ -546,13 +553,13 @@ __global__ void __launch_bounds__(gemm_threads(EG, XF), 1) conv_gemm_kernel(cons
                     }
                     fence_proxy_async_smem();
                     named_bar_sync(ebar, 128);
-                    if (lead_warp && !(p.dbg & 1)) {
+                    if (lead_warp && !(GEMM_DBG(p) & 1)) {
                         if (elect_one()) {
                             int c[5] = {0, org[1], org[2], org[3], org[4]};
 #pragma unroll
                             for (int u = 0; u < S::UNITS; ++u) {
                                 c[0] = n_idx * BN + cc * OC + u * 64;
-                                tma_store_nd(p.rank, &p.o_map, obuf + u * (GEMM_BM * 128), c);
+                                tma_store_5d(&p.o_map, obuf + u * (GEMM_BM * 128), c[0], c[1], c[2], c[3], c[4]);
                             }
                             tma_store_commit();
                         }

@@ -19,7 +19,6 @@
 #include "common.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
-#include "gemm2.cuh"
 #include "wgrad.cuh"
 
 namespace mmd {

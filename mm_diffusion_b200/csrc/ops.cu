@@ -119,13 +119,14 @@ int build_gemm(const GemmProblem& pr, GemmParams* out) {
         dims[0] = pr.src_c[s];
         box[0] = GEMM_BK;
         uint64_t pitch = static_cast<uint64_t>(pr.src_c[s]) * sizeof(act_t);
-        for (int i = 1; i < g.rank; ++i) {
-            dims[i] = g.dims[i - 1];
-            box[i] = g.box[i - 1];
+        for (int i = 1; i < 5; ++i) {   // always rank 5 (unit extents beyond the geometry's rank): one TMA form in the kernel
+            const bool used = i < g.rank;
+            dims[i] = used ? g.dims[i - 1] : 1;
+            box[i] = used ? g.box[i - 1] : 1;
             str[i - 1] = pitch;
-            pitch *= g.dims[i - 1];
+            if (used) pitch *= g.dims[i - 1];
         }
-        MMD_TRY(encode_tmap(&p.a_map[s], pr.src[s], g.rank, dims, str, box));
+        MMD_TRY(encode_tmap(&p.a_map[s], pr.src[s], 5, dims, str, box));
     }
     const int bn = pr.bn;
     const long long kt = pr.k_total();
@@ -133,10 +134,6 @@ int build_gemm(const GemmProblem& pr, GemmParams* out) {
     str[0] = kt * sizeof(act_t);
     box[0] = GEMM_BK; box[1] = bn;
     MMD_TRY(encode_tmap(&p.b_map, pr.w, 2, dims, str, box));
-    if (bn >= 128) {   // half-tile boxes for the CTA-pair kernel
-        box[1] = bn / 2;
-        MMD_TRY(encode_tmap(&p.b2_map, pr.w, 2, dims, str, box));
-    }
     p.m_tiles = static_cast<int>(m_tiles);
     p.n_tiles = pr.n_pad() / bn;
     p.bias = pr.bias;
@@ -146,13 +143,14 @@ int build_gemm(const GemmProblem& pr, GemmParams* out) {
         dims[0] = pr.n;
         box[0] = 64;
         uint64_t pitch = static_cast<uint64_t>(pr.n) * sizeof(act_t);
-        for (int i = 1; i < g.rank; ++i) {
-            dims[i] = g.dims[i - 1];
-            box[i] = g.box[i - 1];
+        for (int i = 1; i < 5; ++i) {
+            const bool used = i < g.rank;
+            dims[i] = used ? g.dims[i - 1] : 1;
+            box[i] = used ? g.box[i - 1] : 1;
             str[i - 1] = pitch;
-            pitch *= g.dims[i - 1];
+            if (used) pitch *= g.dims[i - 1];
         }
-        MMD_TRY(encode_tmap(&p.o_map, pr.out, g.rank, dims, str, box));
+        MMD_TRY(encode_tmap(&p.o_map, pr.out, 5, dims, str, box));
     } else {
         if (!pr.out_f32 || pr.n > 16) return fail(MMD_EINVAL, "narrow conv output needs out_f32 and n <= 16");
         p.out_mode = 1;
@@ -230,10 +228,6 @@ int gemm_init_attrs() {
     MMD_TRY((gemm_attr<128, 64, true>()));
     MMD_TRY((gemm_attr<128, 128, true>()));
     MMD_TRY((gemm_attr<64, 64, true>()));
-    MMD_CUDA_OK(cudaFuncSetAttribute(conv_gemm2_kernel<256, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Smem<256, 64>::TOTAL));
-    MMD_CUDA_OK(cudaFuncSetAttribute(conv_gemm2_kernel<256, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Smem<256, 128>::TOTAL));
-    MMD_CUDA_OK(cudaFuncSetAttribute(conv_gemm2_kernel<128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Smem<128, 64>::TOTAL));
-    MMD_CUDA_OK(cudaFuncSetAttribute(conv_gemm2_kernel<128, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Smem<128, 128>::TOTAL));
     done = true;
     return MMD_OK;
 }
@@ -288,21 +282,6 @@ int launch_gemm(const GemmParams& p, int bn, cudaStream_t st) {
         else if (bn == 128) MMD_GEMM_CASE(128, 128, true);
         else if (bn == 64) MMD_GEMM_CASE(64, 64, true);
         else return fail(MMD_EINVAL, "fused GroupNorm apply: unsupported BN %d", bn);
-        return MMD_OK;
-    }
-    // CTA-pair kernel (tcgen05.mma.cta_group::2): 256-token x BN tiles, the weight tile split across the two CTAs.
-    // MMD_GEMM2 bitmask: 1 = BN 256, 2 = BN 128.
-    static const int pair_mask = [] { const char* e = getenv("MMD_GEMM2"); return e ? atoi(e) : 0; }();
-    if (p.out_mode == 0 && ((bn == 256 && (pair_mask & 1)) || (bn == 128 && (pair_mask & 2))) && p.m_tiles >= 2) {
-        const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
-        const int g2 = 2 * std::min(pairs, num_sms() / 2);
-#define MMD_GEMM2_CASE(BN_, OC_) \
-    MMD_CUDA_OK(launch_kernel(conv_gemm2_kernel<BN_, OC_>, g2, GEMM_THREADS, Gemm2Smem<BN_, OC_>::TOTAL, st, p))
-        if (bn == 256 && oc == 64) MMD_GEMM2_CASE(256, 64);
-        else if (bn == 256) MMD_GEMM2_CASE(256, 128);
-        else if (oc == 64) MMD_GEMM2_CASE(128, 64);
-        else MMD_GEMM2_CASE(128, 128);
-#undef MMD_GEMM2_CASE
         return MMD_OK;
     }
     // 256-token CTA tiles for the 128-column shapes (two row blocks share every weight tile: 25 % fewer L2 -> shared-memory
@@ -379,7 +358,6 @@ int launch_attn(const AttnParams& p, int d, cudaStream_t st) {
         MMD_CUDA_OK(cudaFuncSetAttribute(attention64_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64Smem::TOTAL));
         MMD_CUDA_OK(cudaFuncSetAttribute(attention64_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64Smem::TOTAL));
         MMD_CUDA_OK(cudaFuncSetAttribute(attention64_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64Smem::TOTAL));
-        MMD_CUDA_OK(cudaFuncSetAttribute(attention64p_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64pSmem::TOTAL));
         MMD_CUDA_OK(cudaFuncSetAttribute(attention64x2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64x2Smem::TOTAL));
         MMD_CUDA_OK(cudaFuncSetAttribute(attention64x2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64x2Smem::TOTAL));
         MMD_CUDA_OK(cudaFuncSetAttribute(attention64x2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64x2Smem::TOTAL));
@@ -393,11 +371,7 @@ int launch_attn(const AttnParams& p, int d, cudaStream_t st) {
     static const bool pair64 = [] { const char* e = getenv("MMD_ATTN_PAIR"); return e ? e[0] == '1' : false; }();
     // MMD_ATTN_POLY = 0 / 1 / 2 of every 4 exponentials on the FMA pipe (cubic Cody-Waite) instead of the MUFU unit
     static const int poly = [] { const char* e = getenv("MMD_ATTN_POLY"); const int v = e ? atoi(e) : 0; return v < 0 ? 0 : (v > 2 ? 2 : v); }();
-    // software-pipelined variant: one CTA per SM, S / P / K / V / Q double buffered, Q·K^T issued two tiles ahead
-    static const bool pipe64 = [] { const char* e = getenv("MMD_ATTN_PIPE"); return e ? e[0] == '1' : false; }();
-    if (d == 64 && !generic64 && pipe64) {
-        MMD_CUDA_OK(launch_kernel(attention64p_kernel<0>, std::min(grid, num_sms()), ATT_THREADS, Attn64pSmem::TOTAL, st, p, grid));
-    } else if (d == 64 && !generic64 && pair64 && p.q_tiles >= 2) {
+    if (d == 64 && !generic64 && pair64 && p.q_tiles >= 2) {
         const int q_pairs = (p.q_tiles + 1) / 2;
         const int items = p.B * p.n_blocks * p.heads * q_pairs;
         const int g2 = std::min(items, num_sms());

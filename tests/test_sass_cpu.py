@@ -29,11 +29,9 @@ def sass_by_function():
 
 @pytest.mark.parametrize("kernel,needs", [
     ("conv_gemm_kernel", ("UTCHMMA", "UTMALDG", "LDTM", "UTMASTG")),   # implicit-GEMM conv: tcgen05.mma, TMA load / store, TMEM epilogue
-    ("conv_gemm2_kernel", ("UTCHMMA.2CTA", "UTMALDG", "2CTA", "LDTM", "UTMASTG", "UTCBAR.2CTA.MULTICAST")),   # CTA-pair variant (cta_group::2)
     ("conv_wgrad_kernel", ("UTCHMMA", "UTMALDG", "LDTM")),             # weight gradient
     ("attention64_kernel", ("UTCHMMA", "UTMALDG", "LDTM", "STTM")),    # flash attention d = 64 (O rescale in TMEM)
     ("attention64x2_kernel", ("UTCHMMA", "UTMALDG", "LDTM", "STTM", "USETMAXREG")),   # two query tiles per CTA, register re-split
-    ("attention64p_kernel", ("UTCHMMA", "UTMALDG", "LDTM", "STTM")),   # software-pipelined: S / P double buffered
     ("attention_kernel", ("UTCHMMA", "UTMALDG", "LDTM")),
     ("attn_bwd_kernel", ("UTCHMMA", "UTMALDG", "LDTM")),               # flash attention backward
 ])
@@ -60,3 +58,17 @@ def test_fused_groupnorm_gemm_variant_exists(sass_by_function):
     for name, body in xf.items():
         assert "MUFU.TANH" in body and "UTCHMMA" in body, name
     assert all("MUFU.TANH" not in b for b in plain.values())
+
+
+@pytest.mark.parametrize("kernel", ["conv_gemm_kernel", "attention64_kernel", "attention64x2_kernel", "attention_kernel",
+                                    "conv_wgrad_kernel", "attn_bwd_kernel"])
+def test_single_lane_issue_has_no_waterfall_loops(sass_by_function, kernel):
+    """TMA / tcgen05 instructions are issued by an elect.sync lane of a warp in uniform control flow.  Issued from an
+    `if (lane == 0)` branch instead, ptxas wraps each UTCHMMA / UTCBAR / UTMALDG in an ELECT ... BRA.U.ANY loop over the
+    active lanes (measured: the MMA warp then falls behind the tensor pipe) — none may come back."""
+    bodies = {n: b for n, b in sass_by_function.items()
+              if kernel in n and "temporal" not in n and not (kernel == "attention_kernel" and "attention64" in n)}
+    assert bodies, kernel
+    for name, body in bodies.items():
+        assert "BRA.U.ANY" not in body, f"{name}: per-instruction ELECT / BRA.U.ANY loop is back"
+        assert "ELECT" in body, name
