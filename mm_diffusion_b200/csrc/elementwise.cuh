@@ -107,6 +107,16 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnSrc s, int R, int rows_
                                 act_t* __restrict__ y, int nsub, long long stat_rows,
                                 const DropState* __restrict__ drop, uint32_t drop_site) {
     pdl_trigger();
+    // gamma / beta are constants of the plan: requested before the grid dependency resolves, so their latency overlaps the
+    // previous kernel's tail (the statistics and the FiLM vector are produced inside the step and are read after the wait)
+    const int C_pre = s.c1 + s.c2;
+    float g_pre[4], b_pre[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = threadIdx.x + i * 256;
+        g_pre[i] = c < C_pre ? __ldg(gamma + c) : 0.f;
+        b_pre[i] = c < C_pre ? __ldg(beta + c) : 0.f;
+    }
     pdl_wait();
     // nn.Dropout after the SiLU of the ResBlock out_layers (multimodal_unet.py:376,384), training forwards only
     DropState ds{0u, 0u, 0u, 0u};
@@ -119,6 +129,40 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnSrc s, int R, int rows_
     const int vpr = C / 8;
     const int ns = blockIdx.y;
     float* gstat = coef + 2 * C;
+    // Everything the block needs from global memory is requested up front, so the three dependent latencies of the
+    // straightforward order (statistics -> FiLM vector -> first rows) overlap: small tensors are latency bound here.
+    const int rows_per_pass = blockDim.x / vpr;
+    const int vec = threadIdx.x % vpr;
+    const int rsub = threadIdx.x / vpr;
+    const bool streams = rsub < rows_per_pass;
+    const int r0 = blockIdx.x * rows_per_block;
+    const int r1 = min(R, r0 + rows_per_block);
+    const int c0 = vec * 8;
+    const act_t* base;
+    int ld;
+    if (c0 < s.c1) { base = s.x1 + c0; ld = s.ld1; } else { base = s.x2 + (c0 - s.c1); ld = s.ld2; }
+    base += static_cast<size_t>(ns) * R * ld;
+    int r = r0 + rsub;
+    uint4 raw[GN_UNROLL];
+    bool have = false;
+    if (streams && r < r1) {
+#pragma unroll
+        for (int u = 0; u < GN_UNROLL; ++u) {
+            const int rr = r + u * rows_per_pass;
+            if (rr < r1) raw[u] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(rr) * ld));
+        }
+        have = true;
+    }
+    float sc_pre[4], sh_pre[4];
+    if (film != nullptr) {
+        const float* fb = film + static_cast<size_t>(ns / ns_per_batch) * film_ld;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int c = threadIdx.x + i * 256;
+            sc_pre[i] = c < C ? 1.f + fb[c] : 1.f;
+            sh_pre[i] = c < C ? fb[C + c] : 0.f;
+        }
+    }
     if (threadIdx.x < 32) {  // the only double-precision arithmetic: 32 groups (x nsub partial slots)
         const double inv_n = 1.0 / (static_cast<double>(stat_rows) * cpg);
         double su = 0.0, sq = 0.0;
@@ -133,7 +177,22 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnSrc s, int R, int rows_
         gstat[2 * threadIdx.x + 1] = rsqrtf(static_cast<float>(var) + 1e-5f);
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = threadIdx.x + i * 256;
+        if (c < C) {
+            const int g = c / cpg;
+            float a = gstat[2 * g + 1] * g_pre[i];
+            float b = b_pre[i] - gstat[2 * g] * a;
+            if (film != nullptr) {
+                a *= sc_pre[i];
+                b = b * sc_pre[i] + sh_pre[i];
+            }
+            coef[c] = a;
+            coef[C + c] = b;
+        }
+    }
+    for (int c = threadIdx.x + 4 * 256; c < C; c += 256) {   // wider than 1024 channels (not in this network)
         const int g = c / cpg;
         float a = gstat[2 * g + 1] * gamma[c];
         float b = beta[c] - gstat[2 * g] * a;
@@ -147,28 +206,20 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnSrc s, int R, int rows_
         coef[C + c] = b;
     }
     __syncthreads();
-    const int rows_per_pass = blockDim.x / vpr;
-    const int vec = threadIdx.x % vpr;
-    const int rsub = threadIdx.x / vpr;
-    if (rsub >= rows_per_pass) return;
-    const int r0 = blockIdx.x * rows_per_block;
-    const int r1 = min(R, r0 + rows_per_block);
-    const int c0 = vec * 8;
-    const act_t* base;
-    int ld;
-    if (c0 < s.c1) { base = s.x1 + c0; ld = s.ld1; } else { base = s.x2 + (c0 - s.c1); ld = s.ld2; }
-    base += static_cast<size_t>(ns) * R * ld;
+    if (!streams) return;
     act_t* ybase = y + static_cast<size_t>(ns) * R * C + c0;
     float ca[8], cb[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { ca[i] = coef[c0 + i]; cb[i] = coef[C + c0 + i]; }
-    for (int r = r0 + rsub; r < r1; r += GN_UNROLL * rows_per_pass) {
-        uint4 raw[GN_UNROLL];
+    for (; r < r1; r += GN_UNROLL * rows_per_pass) {
+        if (!have) {
 #pragma unroll
-        for (int u = 0; u < GN_UNROLL; ++u) {
-            const int rr = r + u * rows_per_pass;
-            if (rr < r1) raw[u] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(rr) * ld));
+            for (int u = 0; u < GN_UNROLL; ++u) {
+                const int rr = r + u * rows_per_pass;
+                if (rr < r1) raw[u] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(rr) * ld));
+            }
         }
+        have = false;
 #pragma unroll
         for (int u = 0; u < GN_UNROLL; ++u) {
             const int rr = r + u * rows_per_pass;

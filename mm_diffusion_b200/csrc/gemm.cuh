@@ -31,6 +31,21 @@ constexpr int GEMM_MAX_TAPS = 27;
 constexpr int gemm_threads(int eg, bool xf) { return 64 + 128 * eg + (xf ? 128 : 0); }
 constexpr int GEMM_XF_MAXC = 512;  // widest source the fused GroupNorm apply supports
 
+// Division of a non-negative 31-bit index by a launch constant (tile -> (row block, column block) -> box origin runs
+// once per tile in every role; the hardware has no integer divide).  q = (n * mul) >> (31 + shift), exact for n < 2^31.
+struct FastDiv {
+    uint32_t mul, shift, d;   // d == 1: identity (mul unused)
+    __host__ void set(uint32_t div) {
+        d = div < 1 ? 1 : div;
+        shift = 0;
+        while ((1u << shift) < d) ++shift;
+        mul = d == 1 ? 0u : static_cast<uint32_t>(((1ull << (31 + shift)) + d - 1) / d);
+    }
+    __device__ __forceinline__ int div(int n) const {
+        return d == 1 ? n : static_cast<int>(__umulhi(static_cast<uint32_t>(n), mul) >> (shift - 1));
+    }
+};
+
 struct alignas(64) GemmParams {
     CUtensorMap a_map[GEMM_MAX_SRC];  // activation sources, always rank 5 (unit extents past `rank`), box (64, box[0..3])
     CUtensorMap b_map;                // packed weights [N, K_total] (K-major), box (64, BN)
@@ -43,6 +58,7 @@ struct alignas(64) GemmParams {
     int n_taps;
     int tap[GEMM_MAX_TAPS][3];        // coordinate deltas on coordinates 1..3
     int m_tiles, n_tiles;             // 128-token tiles, BN-column tiles
+    FastDiv fd_ntile[4], fd_ntiles, fd_stats;   // dividers by ntile[i], n_tiles, stats_div
     const float* bias;                // [n_tiles*BN] fp32 (padded)
     // out_mode 1: fp32 strided scatter (network heads write NCHW fp32 directly)
     int out_mode;
@@ -125,9 +141,9 @@ MMD_DEVINL void gemm_tile_origin(const GemmParams& p, int m_idx, int* c /*[5]*/)
     int r = m_idx;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        int t = r % p.ntile[i];
-        r /= p.ntile[i];
-        c[i + 1] = t * p.box[i];
+        const int q = p.fd_ntile[i].div(r);
+        c[i + 1] = (r - q * p.ntile[i]) * p.box[i];
+        r = q;
     }
     c[0] = 0;
 }
@@ -207,10 +223,10 @@ __global__ void __launch_bounds__(gemm_threads(EG, XF), 1) conv_gemm_kernel(cons
             // pipeline stages are requested before the grid dependency resolves, the A halves after it.
             int pre = 0;
             if (tile_begin < tile_end) {
-                const int n_idx0 = tile_begin % p.n_tiles;
+                const int n_idx0 = (tile_begin - p.fd_ntiles.div(tile_begin) * p.n_tiles);
                 pre = (GEMM_DBG(p) & 24) ? 0 : min(S::STAGES, num_kb);
                 // (an incomplete last row-block pair loads one A block only)
-                const int nv0 = min(MT, p.m_tiles - (tile_begin / p.n_tiles) * MT);
+                const int nv0 = min(MT, p.m_tiles - p.fd_ntiles.div(tile_begin) * MT);
                 if (elect_one()) {
                     for (int kb = 0; kb < pre; ++kb) {
                         mbar_expect_tx(&full_bar[kb], S::B_BYTES + nv0 * S::A_ONE);
@@ -228,7 +244,7 @@ __global__ void __launch_bounds__(gemm_threads(EG, XF), 1) conv_gemm_kernel(cons
                     const int tile = tile_begin + d * tile_step;
                     if (tile >= tile_end) break;
                     int org[5];
-                    gemm_tile_origin(p, tile / p.n_tiles, org);
+                    gemm_tile_origin(p, p.fd_ntiles.div(tile), org);
                     for (int t = 0; t < p.n_taps; ++t) {
                         int c[5] = {0, org[1] + p.tap[t][0], org[2] + p.tap[t][1], org[3] + p.tap[t][2], org[4]};
                         for (int s = 0; s < p.n_src; ++s)
@@ -244,7 +260,7 @@ __global__ void __launch_bounds__(gemm_threads(EG, XF), 1) conv_gemm_kernel(cons
             uint32_t phase = 0;
             int gk = 0;   // k-blocks issued by this CTA (the first `pre` already have their B half in flight)
             for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
-                const int mp = tile / p.n_tiles;
+                const int mp = p.fd_ntiles.div(tile);
                 const int n_idx = tile - mp * p.n_tiles;
                 const int m_idx = mp * MT;
                 const int nv = min(MT, p.m_tiles - m_idx);   // row blocks of this tile that exist
@@ -255,7 +271,7 @@ __global__ void __launch_bounds__(gemm_threads(EG, XF), 1) conv_gemm_kernel(cons
                 const int pf_tile = tile + pf * tile_step;
                 const bool pf_on = MT == 1 && pf > 0 && pf_tile < tile_end;
                 int porg[5] = {0, 0, 0, 0, 0};
-                if (pf_on) gemm_tile_origin(p, pf_tile / p.n_tiles, porg);
+                if (pf_on) gemm_tile_origin(p, p.fd_ntiles.div(pf_tile), porg);
                 int kb = 0;
                 for (int t = 0; t < p.n_taps; ++t) {
                     int c[5];
@@ -324,7 +340,7 @@ __global__ void __launch_bounds__(gemm_threads(EG, XF), 1) conv_gemm_kernel(cons
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * (MT * BN);
-                const bool two = MT == 2 && (tile / p.n_tiles) * MT + 1 < p.m_tiles;   // second row block exists
+                const bool two = MT == 2 && p.fd_ntiles.div(tile) * MT + 1 < p.m_tiles;   // second row block exists
                 for (int kb = 0; kb < num_kb; ++kb) {
                     // XF kernels: every k-block is handed over by the transform warps (they wait for the TMA, transform the
                     // blocks of source 0 and pass the others through), so all roles follow the ring in lock-step
@@ -376,7 +392,7 @@ __global__ void __launch_bounds__(gemm_threads(EG, XF), 1) conv_gemm_kernel(cons
             uint32_t phase = 0;
             int cached_dom = -1;
             for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
-                const int m_idx = tile / p.n_tiles;
+                const int m_idx = p.fd_ntiles.div(tile);
                 int org[5];
                 gemm_tile_origin(p, m_idx, org);
                 const int dom_base = (org[1] * p.xf_mul[0] + org[2] * p.xf_mul[1] + org[3] * p.xf_mul[2] +
@@ -478,7 +494,7 @@ __global__ void __launch_bounds__(gemm_threads(EG, XF), 1) conv_gemm_kernel(cons
             if (MT == 1 && EG == 2 && (it & 1) != eg) continue;
             const int acc = (S::NACC == 2) ? (it & 1) : 0;
             const uint32_t acc_phase = (S::NACC == 2) ? ((it >> 1) & 1) : (it & 1);
-            const int mp = tile / p.n_tiles;
+            const int mp = p.fd_ntiles.div(tile);
             const int n_idx = tile - mp * p.n_tiles;
             const int m_idx = mp * MT + (MT == 2 ? eg : 0);
             if (MT == 2 && m_idx >= p.m_tiles) {   // missing second row block of the last pair: keep the barrier protocol going
@@ -609,8 +625,8 @@ __global__ void __launch_bounds__(gemm_threads(EG, XF), 1) conv_gemm_kernel(cons
                     const int col_base = n_idx * BN;
                     const int g_first = col_base / cpg;
                     const int groups_tile = (col_base + BN - 1) / cpg - g_first + 1;   // groups intersecting this tile
-                    const int dom_base = (org[1] * p.stats_mul[0] + org[2] * p.stats_mul[1] + org[3] * p.stats_mul[2] +
-                                          org[4] * p.stats_mul[3]) / p.stats_div;
+                    const int dom_base = p.fd_stats.div(org[1] * p.stats_mul[0] + org[2] * p.stats_mul[1] + org[3] * p.stats_mul[2] +
+                                                        org[4] * p.stats_mul[3]);
                     for (int item = et; item < ndom * groups_tile * 2; item += 128) {
                         const int st = item & 1;
                         const int gl = (item >> 1) % groups_tile;

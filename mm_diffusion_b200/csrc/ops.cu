@@ -136,6 +136,9 @@ int build_gemm(const GemmProblem& pr, GemmParams* out) {
     MMD_TRY(encode_tmap(&p.b_map, pr.w, 2, dims, str, box));
     p.m_tiles = static_cast<int>(m_tiles);
     p.n_tiles = pr.n_pad() / bn;
+    for (int i = 0; i < 4; ++i) p.fd_ntile[i].set(static_cast<uint32_t>(p.ntile[i]));
+    p.fd_ntiles.set(static_cast<uint32_t>(p.n_tiles));
+    p.fd_stats.set(1);
     p.bias = pr.bias;
     if (bn >= 64) {
         if (pr.n % 64 != 0 || !pr.out) return fail(MMD_EINVAL, "fp16 conv output needs n %% 64 == 0");
@@ -166,6 +169,7 @@ int build_gemm(const GemmProblem& pr, GemmParams* out) {
         p.stats_rows = pr.stats_rows;
         for (int i = 0; i < 4; ++i) p.stats_mul[i] = pr.stats_mul[i];
         p.stats_div = pr.stats_div;
+        p.fd_stats.set(static_cast<uint32_t>(pr.stats_div));
         p.stats_valid_coord = pr.stats_valid_coord;
         if (pr.stats_rows != 128 && pr.stats_rows != 64) return fail(MMD_EINVAL, "stats_rows %d", pr.stats_rows);
     }
