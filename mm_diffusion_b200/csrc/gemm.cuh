@@ -94,7 +94,8 @@ struct alignas(64) GemmParams {
     // few iterations from now turns the pipeline's TMA loads into L2 hits.
     int pf_tiles;
     // measurement only (MMD_GEMM_DBG, results are wrong when set): ablation switches that locate the bound of a shape —
-    // 1: no global store of the output, 2: no TMEM -> shared conversion, 4: no MMA issue, 8: no A loads, 16: no B loads
+    // 1: no global store of the output, 2: no TMEM -> shared conversion, 4: no MMA issue, 8: no A loads, 16: no B loads,
+    // 32: no column-sum pass of the fused statistics, 64: no fold + atomics of the fused statistics
     int dbg;
 };
 
@@ -581,7 +582,7 @@ __global__ void __launch_bounds__(gemm_threads(EG, XF), 1) conv_gemm_kernel(cons
                         }
                         __syncwarp();
                     }
-                    if (p.stats != nullptr) {
+                    if (p.stats != nullptr && !(GEMM_DBG(p) & 32)) {
                         // Column sums of the staged fp16 chunk without atomics, one 64-column unit at a time: lane & 15 =
                         // 4-column quad (8 bytes of a 128-byte row), the two half-warps take 16 rows each of the warp's
                         // 32-row band; per (band, quad) partials are folded into groups by the write-out pass below.
@@ -615,7 +616,7 @@ __global__ void __launch_bounds__(gemm_threads(EG, XF), 1) conv_gemm_kernel(cons
                         }
                     }
                 }
-                if (p.stats != nullptr) {
+                if (p.stats != nullptr && !(GEMM_DBG(p) & 64)) {
                     named_bar_sync(ebar, 128);
                     // thread = (domain-in-tile, local group, statistic): fold bands x quads of that group
                     const int cpg = p.stats_cpg;                 // multiple of 4

@@ -302,3 +302,63 @@ def test_stale_forward_is_rejected(setup):
     finally:
         model.zero_grad(set_to_none=True)
         model.eval()
+
+
+def test_flat_buffer_trainer_step_on_device():
+    """SURVEY.md §8 row f1 on the GPU: one training step through mm_diffusion_b200.fp16_util.MixedPrecisionTrainer (fp16
+    loss-scaling protocol) — the sm_100a backward writes the flat gradient buffer the trainer's single master parameter
+    aliases, AdamW steps it, and the next forward must run on the updated weights.  Checked against (a) a per-tensor AdamW
+    step taken from the same gradients and (b) the oracle forward at the trainer's checkpoint dict."""
+    from mm_diffusion_b200 import fp16_util as ours
+    from mm_diffusion_b200.script_util import create_gaussian_diffusion
+    from oracle.mmdiff_oracle import unet_forward
+    fx = load_golden("small")
+    cfg = cfg_of(fx)
+    sd = synthetic_state_dict(cfg, seed=fx["weight_seed"])
+    model = build_b200_model(cfg, sd).train()     # its own instance: the trainer switches it to flat gradients
+    diffusion = create_gaussian_diffusion()
+    trainer = ours.MixedPrecisionTrainer(model=model, use_fp16=True, fp16_scale_growth=1e-3)
+    lr, wd, eps = 1e-3, 0.01, 1e-8
+    opt = torch.optim.AdamW(trainer.master_params, lr=lr, weight_decay=wd, eps=eps)
+    B = 2
+    x0, noise = _data(cfg, B, 91)
+    t = torch.tensor([100, 800])
+    trainer.zero_grad()
+    random.seed(12)
+    loss = diffusion.multimodal_training_losses(model, {k: v.cuda() for k, v in x0.items()}, t.cuda(),
+                                                noise={k: v.cuda() for k, v in noise.items()})["loss"].mean()
+    trainer.backward(loss)
+    torch.cuda.synchronize()
+    scale = 2.0 ** trainer.lg_loss_scale
+    before = {n: p.detach().clone() for n, p in model.named_parameters()}
+    grads = {n: (p.grad.detach().float() / scale).clone() for n, p in model.named_parameters()}
+    assert all(torch.isfinite(g).all() for g in grads.values())
+    assert model.flat_grad is not None and all(p.grad.data_ptr() >= model.flat_grad.data_ptr() for p in model.parameters())
+    assert trainer.optimize(opt) is True
+    assert abs(trainer.lg_loss_scale - (ours.INITIAL_LOG_LOSS_SCALE + 1e-3)) < 1e-9
+    # (a) first AdamW step from zero moments: p <- p (1 - lr wd) - lr g / (|g| + eps)
+    worst = 0.0
+    for n, p in model.named_parameters():
+        g = grads[n]
+        want = before[n] * (1 - lr * wd) - lr * g / (g.abs() + eps)
+        worst = max(worst, (p.detach() - want).abs().max().item())
+    assert worst < 2e-6, worst
+    # (b) the library's packed weights follow: forward at the new weights vs the oracle at the trainer's checkpoint
+    ckpt = {k: v.detach().float().cpu() for k, v in trainer.master_params_to_state_dict(trainer.master_params).items()}
+    assert list(ckpt) == list(sd)
+    moved = max((ckpt[k] - sd[k]).abs().max().item() for k in sd)
+    assert moved > 5e-4, moved
+    g2 = torch.Generator().manual_seed(17)
+    v = torch.randn(B, *cfg.video_size, generator=g2)
+    a = torch.randn(B, *cfg.audio_size, generator=g2)
+    shifts = draw_shifts(cfg, random.Random(4))
+    model.eval()
+    with torch.no_grad():
+        ov, oa = unet_forward(ckpt, cfg, v, a, t, shifts)
+        ev, ea = model(v.cuda(), a.cuda(), t.cuda(), shifts=shifts)
+        o0v, _ = unet_forward(sd, cfg, v, a, t, shifts)
+    rv, ra = rel_l2(ev, ov), rel_l2(ea, oa)
+    print(f"[flat trainer] AdamW step max |dp| err {worst:.2e}; forward at updated weights rel-L2 video {rv:.2e} audio {ra:.2e}; "
+          f"old-vs-new output {rel_l2(o0v, ov):.2e}")
+    assert rv < 3e-3 and ra < 3e-3, (rv, ra)
+    assert rel_l2(o0v, ov) > 3 * rv    # the update is visible well above the parity tolerance

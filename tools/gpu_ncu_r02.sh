@@ -17,7 +17,8 @@ for spec in "conv1x1_qkv 4 qkv" "conv1x1_out 0 out_l0" "conv1x1_proj 2 proj" "cr
   timeout 600 env $EXTRA_ENV ncu --set full --import-source on --clock-control none --nvtx --nvtx-include "$1/" -s $2 -c 1 \
       -o $O/full_$3 -f python tools/gpu_ncu_forward.py 4 > $O/ncu_full_$3.log 2>&1
   python tools/ncu_summarize.py $O/full_$3.ncu-rep $O/full_$3_summary.txt > /dev/null 2>&1
-  find $O -name "full_$3.ncu-rep" -size +12M -delete
+  ncu -i $O/full_$3.ncu-rep --page source --csv 2>/dev/null | gzip > $O/full_$3_src.csv.gz
+  rm -f $O/full_$3.ncu-rep   # the merged gpurun_out/ is capped at 64 MiB: keep the summary and the source page only
 done
 timeout 900 env $EXTRA_ENV ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \
     --log-file $O/launches_forward.csv python tools/gpu_ncu_forward.py 4 > $O/launches_forward.log 2>&1
