@@ -592,18 +592,23 @@ __global__ void __launch_bounds__(gemm_threads(EG, XF), 1) conv_gemm_kernel(cons
                         for (int u = 0; u < S::UNITS; ++u) {
                             const uint8_t* ub = obuf + u * (GEMM_BM * 128);
                             float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
-#pragma unroll 8
+                            // all 16 loads first, then the arithmetic: a per-row `if (r < valid_rows)` makes every row its own
+                            // reconvergence block with the shared-memory latency exposed (measured 13.6 us of a 39.5 us
+                            // launch); rows past a ragged edge are masked by value instead (the staging rows exist either way)
+                            uint2 raw[16];
+#pragma unroll
+                            for (int rr = 0; rr < 16; ++rr)
+                                raw[rr] = *reinterpret_cast<const uint2*>(ub + sw128_off(band * 32 + half * 16 + rr, unit) + sub);
+#pragma unroll
                             for (int rr = 0; rr < 16; ++rr) {
-                                const int r = band * 32 + half * 16 + rr;
-                                if (r < valid_rows) {
-                                    const uint2 raw = *reinterpret_cast<const uint2*>(ub + sw128_off(r, unit) + sub);
-                                    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
-                                    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
-                                    s0 += a.x; q0 = fmaf(a.x, a.x, q0);
-                                    s1 += a.y; q1 = fmaf(a.y, a.y, q1);
-                                    s2 += b.x; q2 = fmaf(b.x, b.x, q2);
-                                    s3 += b.y; q3 = fmaf(b.y, b.y, q3);
-                                }
+                                const bool ok = band * 32 + half * 16 + rr < valid_rows;
+                                const uint32_t lo = ok ? raw[rr].x : 0u, hi = ok ? raw[rr].y : 0u;
+                                const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&lo));
+                                const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+                                s0 += a.x; q0 = fmaf(a.x, a.x, q0);
+                                s1 += a.y; q1 = fmaf(a.y, a.y, q1);
+                                s2 += b.x; q2 = fmaf(b.x, b.x, q2);
+                                s3 += b.y; q3 = fmaf(b.y, b.y, q3);
                             }
                             float su = (s0 + s1) + (s2 + s3), sq = (q0 + q1) + (q2 + q3);
                             su += __shfl_xor_sync(0xffffffffu, su, 16);
