@@ -396,9 +396,10 @@ int launch_attn(const AttnParams& p, int d, cudaStream_t st) {
 
 // ------------------------------------------------------------ elementwise
 static int gn_rows_per_block(int ns, int rows, int C) {
-    // ~6 blocks per SM over all domains; every thread streams at least two unrolled batches of rows
+    // ~6 blocks per SM over all domains (MMD_GN_BPS overrides); every thread streams at least two unrolled batches of rows
     const int rows_per_pass = std::max(1, 256 / (C / 8));
-    const int target_blocks = 6 * num_sms();
+    static const int bps = [] { const char* e = getenv("MMD_GN_BPS"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 6; }();
+    const int target_blocks = bps * num_sms();
     const int per_domain = std::max(1, target_blocks / std::max(1, ns));
     int rpb = (rows + per_domain - 1) / per_domain;
     rpb = std::max(rpb, 2 * GN_UNROLL * rows_per_pass);
