@@ -802,6 +802,372 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention64_kernel(const __gri
 }
 
 
+// ---- column-half variants for attention64h_kernel (two threads per query row): chunks c0, c0 + 1 of the four 32-column
+// chunks of a logit tile; chunk pair c0 / 2 is one 64-key chunk of P.
+template <bool FULL>
+MMD_DEVINL float attn64_rowmax_part(uint32_t s_addr, int kvalid, int c0) {
+    // one 32-column chunk in registers at a time: two CTAs x 320 threads leave 102 registers per thread
+    uint32_t v[32];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+        const int c = c0 + cc;
+        if (!FULL && c * 32 >= kvalid) break;
+        tmem_ld32(s_addr + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (FULL || c * 32 + i < kvalid) mx = fmaxf(mx, __uint_as_float(v[i]));
+    }
+    return mx;
+}
+
+// p = exp2(s * scale - m) for this thread's 64 columns as fp16 into its 64-key chunk of P.  Two logits share ONE exp-unit
+// operation: the fp32 arguments are packed to half2 (the conversion the fp16 P needs anyway) and go through
+// ex2.approx.f16x2, whose result IS the packed P word.  The argument rounding costs at most 2^-11 relative in the exponent
+// (0.03 % of the probability for the dominant arguments in [-1, 0], up to 0.5 % for probabilities below 2^-8).
+// Returns the largest exponent argument (from the raw maximum: scale > 0).
+template <bool FULL>
+MMD_DEVINL float attn64_write_p_part(uint32_t s_addr, int kvalid, float scale_log2, float nm, uint8_t* p_smem, int row, int c0) {
+    float smax = -INFINITY;
+    uint32_t v[32];
+    uint8_t* chunk = p_smem + (c0 >> 1) * (ATT_BQ * 128);
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+        const int c = c0 + cc;
+        if (!FULL && c * 32 >= kvalid) break;
+        tmem_ld32(s_addr + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint4 pk;
+            uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int col = c * 32 + j * 8 + 2 * k;
+                float s0 = __uint_as_float(v[j * 8 + 2 * k]), s1 = __uint_as_float(v[j * 8 + 2 * k + 1]);
+                if (!FULL) {   // masked keys: exponent -inf -> probability 0, and out of the maximum
+                    if (col >= kvalid) s0 = -INFINITY;
+                    if (col + 1 >= kvalid) s1 = -INFINITY;
+                }
+                smax = fmaxf(smax, fmaxf(s0, s1));
+                pw[k] = ex2_h2(fmaf(s0, scale_log2, nm), fmaf(s1, scale_log2, nm));
+            }
+            *reinterpret_cast<uint4*>(chunk + sw128_off(row, cc * 4 + j)) = pk;
+        }
+    }
+    return fmaf(smax, scale_log2, nm);
+}
+
+// half 0 rescales O columns 0..31 and the row sums, half 1 O columns 32..63
+MMD_DEVINL void attn64_rescale_part(uint32_t tmem_O, uint32_t tmem_L, uint32_t lane_base, float alpha, int hf) {
+    uint32_t o[32];
+    tmem_ld32(tmem_O + lane_base + hf * 32, o);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+    tmem_st32(tmem_O + lane_base + hf * 32, o);
+    if (hf == 0) {
+        tmem_ld16(tmem_L + lane_base, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+        tmem_st16(tmem_L + lane_base, o);
+    }
+    tmem_st_wait();
+}
+
+constexpr int ATT64H_THREADS = 320;   // warps 0-7 softmax (row quarter x column half), warp 8 TMA, warp 9 MMA
+struct Attn64hSmem : Attn64Smem {
+    static constexpr int XCH_OFF = Attn64Smem::BAR_OFF + 256;   // exchange between the column halves: row maxima 2 x 2 x 128 floats, row sums 2 x 128
+    static constexpr int TOTAL = XCH_OFF + 3072 + 1024;
+};
+
+// attention64h_kernel: attention64_kernel with EIGHT softmax warps per CTA (two threads per query row, each owning 64 of
+// the 128 logit columns = one 64-key chunk of P); everything else (TMA / MMA warps, barrier protocol, TMEM layout, two
+// CTAs per SM) is the same.
+template <int PQ>
+__global__ void __launch_bounds__(ATT64H_THREADS, 2) attention64h_kernel(const __grid_constant__ AttnParams p, int n_items) {
+    // Persistent: a CTA walks work items blockIdx.x, +gridDim.x, ... ; the TMA warp runs ahead into the next item
+    // (Q as soon as the last Q·K^T of the current item has been issued, K/V as stages free up), so the per-item
+    // start-up latency (Q/K fetch, barrier set-up, TMEM allocation) is paid once per CTA instead of once per item.
+    using S = Attn64hSmem;
+    constexpr int D = 64;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
+    uint64_t* q_full = bars;        // 1
+    uint64_t* q_empty = bars + 1;   // 1
+    uint64_t* k_full = bars + 2;    // 2
+    uint64_t* k_empty = bars + 4;   // 2
+    uint64_t* v_full = bars + 6;    // 1
+    uint64_t* v_empty = bars + 7;   // 1
+    uint64_t* s_full = bars + 8;    // 1
+    uint64_t* p_ready = bars + 9;   // 1 (256 arrivals)
+    uint64_t* o_full = bars + 10;   // 1
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    pdl_trigger();
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&p.q_map);
+        tma_prefetch_desc(&p.k_map);
+        tma_prefetch_desc(&p.v_map);
+        mbar_init(q_full, 1);
+        mbar_init(q_empty, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
+        mbar_init(v_full, 1);
+        mbar_init(v_empty, 1);
+        mbar_init(s_full, 1);
+        mbar_init(p_ready, 256);
+        mbar_init(o_full, 1);
+        fence_mbar_init();
+    }
+    // constant ones tile for the row-sum MMA
+    for (int i = threadIdx.x; i < 4096 / 16; i += ATT64H_THREADS)
+        reinterpret_cast<uint4*>(smem + S::ONES_OFF)[i] = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
+    fence_proxy_async_smem();
+    if (warp == 9) tmem_alloc(tmem_slot, S::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();   // q/k/v come from the previous kernel
+    const uint32_t tmem_S = tmem_base;
+    const uint32_t tmem_O = tmem_base + 128;
+    const uint32_t tmem_L = tmem_base + 192;
+
+    if (warp == 8) {
+        // ===================== TMA producer =====================
+        // whole warp in uniform control flow (all lanes wait), one elected lane issues: a lane-guarded branch makes
+        // ptxas wrap every TMA / tcgen05 instruction in an ELECT + BRA.U.ANY loop over the active lanes (gemm.cuh)
+        {
+            int g = 0;   // KV tiles issued so far (all items)
+            int it = 0;  // items started
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                const AttnWork w = attn_decode(p, item);
+                mbar_wait(q_empty, (it & 1) ^ 1);   // last Q·K^T of the previous item has been issued and retired
+                if (elect_one()) {
+                    mbar_expect_tx(q_full, 16384);
+                    tma_load_2d(smem + S::Q_OFF, &p.q_map, q_full, p.q_col0 + w.head * D, w.q_row0);
+                }
+                __syncwarp();
+                for (int t = 0; t < w.n_tiles; ++t, ++g) {
+                    const int st = g & 1;
+                    int krow, kvalid;
+                    attn_tile(w, t, krow, kvalid);
+                    mbar_wait(&k_empty[st], ((g >> 1) & 1) ^ 1);
+                    if (elect_one()) {
+                        mbar_expect_tx(&k_full[st], 16384);
+                        tma_load_2d(smem + S::K_OFF + st * 16384, &p.k_map, &k_full[st], p.k_col0 + w.head * D, krow);
+                    }
+                    __syncwarp();
+                    mbar_wait(v_empty, (g & 1) ^ 1);
+                    if (elect_one()) {
+                        mbar_expect_tx(v_full, 16384);
+                        tma_load_2d(smem + S::V_OFF, &p.v_map, v_full, p.v_col0 + w.head * D, krow);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // ===================== MMA issuer (uniform warp, elected lane) =====================
+        {
+            constexpr uint32_t idesc_qk = umma_idesc_f16(ATT_BQ, ATT_BKV, 0, 0);
+            constexpr uint32_t idesc_pv = umma_idesc_f16(ATT_BQ, D, 0, 1);   // V is MN-major
+            constexpr uint32_t idesc_l = umma_idesc_f16(ATT_BQ, 16, 0, 0);   // P x ones^T
+            const uint64_t qd0 = umma_desc_sw128(smem_u32(smem + S::Q_OFF), 16, 1024);
+            const uint64_t kd0 = umma_desc_sw128(smem_u32(smem + S::K_OFF), 16, 1024);
+            const uint64_t pd0 = umma_desc_sw128(smem_u32(smem + S::P_OFF), 16, 1024);
+            const uint64_t vd0 = umma_desc_sw128(smem_u32(smem + S::V_OFF), ATT_BKV * 128, 1024);   // MN-major V
+            const uint64_t od0 = umma_desc_sw128(smem_u32(smem + S::ONES_OFF), 16, 1024);
+            int gq = 0;   // Q·K^T tiles issued
+            int itq = 0;  // items whose first Q·K^T has been issued
+            // issues Q·K^T of tile t of the item `w` (first tile waits for that item's Q; last tile releases Q)
+            auto issue_qk = [&](const AttnWork& w, int t) {
+                if (t == 0) {
+                    mbar_wait(q_full, itq & 1);
+                    ++itq;
+                }
+                const int st = gq & 1;
+                mbar_wait(&k_full[st], (gq >> 1) & 1);
+                tc_fence_after();
+                const uint64_t kd = kd0 + static_cast<uint64_t>(st) * (16384 >> 4);
+                if (elect_one()) {
+#pragma unroll
+                    for (int ks = 0; ks < D / 16; ++ks)
+                        umma_f16_ss(tmem_S, qd0 + 2 * ks, kd + 2 * ks, idesc_qk, ks != 0 ? 1u : 0u);
+                    umma_commit(&k_empty[st]);
+                    if (t == w.n_tiles - 1) umma_commit(q_empty);
+                    umma_commit(s_full);
+                }
+                __syncwarp();
+                ++gq;
+            };
+            int g = 0;
+            bool first = true;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const AttnWork w = attn_decode(p, item);
+                if (first) { issue_qk(w, 0); first = false; }
+                for (int t = 0; t < w.n_tiles; ++t, ++g) {
+                    int krow, kvalid;
+                    attn_tile(w, t, krow, kvalid);
+                    mbar_wait(p_ready, g & 1);
+                    mbar_wait(v_full, g & 1);
+                    tc_fence_after();
+                    const int nks = (kvalid + 15) >> 4;
+                    if (elect_one()) {
+                        // descriptors are base + compile-time increments (16-byte units)
+                        if (nks == ATT_BKV / 16) {
+                            // full tile: straight-line issue with compile-time descriptor increments
+#pragma unroll
+                            for (int ks = 0; ks < ATT_BKV / 16; ++ks)
+                                umma_f16_ss(tmem_O, pd0 + ((ks >> 2) * (ATT_BQ * 128 >> 4) + (ks & 3) * 2), vd0 + ks * (2048 >> 4),
+                                            idesc_pv, (t | ks) != 0 ? 1u : 0u);
+#pragma unroll
+                            for (int ks = 0; ks < ATT_BKV / 16; ++ks)
+                                umma_f16_ss(tmem_L, pd0 + ((ks >> 2) * (ATT_BQ * 128 >> 4) + (ks & 3) * 2),
+                                            od0 + ((ks >> 2) * (2048 >> 4) + (ks & 3) * 2), idesc_l, (t | ks) != 0 ? 1u : 0u);
+                        } else {
+                            // ragged tile: running descriptors (a 64-column chunk boundary after ks = 3)
+                            uint64_t pd = pd0, vd = vd0;
+                            for (int ks = 0; ks < nks; ++ks) {
+                                umma_f16_ss(tmem_O, pd, vd, idesc_pv, (t | ks) != 0 ? 1u : 0u);
+                                vd += 2048 >> 4;
+                                pd += (ks == 3) ? (ATT_BQ * 128 >> 4) - 6 : 2;
+                            }
+                            uint64_t od = od0;
+                            pd = pd0;
+                            for (int ks = 0; ks < nks; ++ks) {
+                                umma_f16_ss(tmem_L, pd, od, idesc_l, (t | ks) != 0 ? 1u : 0u);
+                                pd += (ks == 3) ? (ATT_BQ * 128 >> 4) - 6 : 2;
+                                od += (ks == 3) ? (2048 >> 4) - 6 : 2;
+                            }
+                        }
+                        umma_commit(v_empty);
+                        umma_commit(o_full);
+                    }
+                    __syncwarp();
+                    // next logits: same item, or the first tile of the next item (S is free: softmax of this tile is done)
+                    if (t + 1 < w.n_tiles) {
+                        issue_qk(w, t + 1);
+                    } else if (item + static_cast<int>(gridDim.x) < n_items) {
+                        const AttnWork wn = attn_decode(p, item + gridDim.x);
+                        issue_qk(wn, 0);
+                    }
+                }
+            }
+        }
+    } else {
+        // ===================== softmax warps (two threads per query row: column halves) =====================
+        // warp w: rows 32 (w & 3) .. +31 (its TMEM lane quarter), logit columns 64 (w >> 2) .. +63 = one 64-key chunk of P.
+        // The softmax of one CTA is a dependent chain per warp (TMEM load -> scale -> exp -> pack -> store) and was latency
+        // bound with four warps per CTA; eight warps double the independent chains per scheduler.
+        const int q4 = warp & 3, hf = warp >> 2;
+        const int row = q4 * 32 + lane;
+        const uint32_t lane_base = static_cast<uint32_t>(q4 * 32) << 16;
+        const uint32_t s_addr = tmem_S + lane_base;
+        uint8_t* p_smem = smem + S::P_OFF;
+        float* xch = reinterpret_cast<float*>(smem + S::XCH_OFF);   // [tile parity][half][128 rows]
+        int g = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const AttnWork w = attn_decode(p, item);
+            const int T = w.n_tiles;
+            float m_used = 0.f;
+            // ragged query blocks: a row quarter past the block skips the softmax (both of its warps) and only keeps
+            // the barrier protocol going; its P / O rows are garbage that is never stored
+            const bool warp_active = q4 * 32 < w.q_valid;
+            for (int t = 0; t < T; ++t, ++g) {
+                int krow, kvalid;
+                attn_tile(w, t, krow, kvalid);
+                mbar_wait(s_full, g & 1);
+                tc_fence_after();
+                if (!warp_active) {
+                    if (t > 0) {
+                        mbar_wait(o_full, (g - 1) & 1);
+                        tc_fence_after();
+                    }
+                    tc_fence_before();
+                    mbar_arrive(p_ready);
+                    continue;
+                }
+                const bool full_tile = (kvalid == ATT_BKV);
+                float* mine = xch + ((g & 1) * 2 + hf) * 128 + row;
+                const float* other = xch + ((g & 1) * 2 + (hf ^ 1)) * 128 + row;
+                // First tile of an item: true row maximum first (the two halves exchange theirs), then the probabilities.
+                // Later tiles: one streaming pass against the running maximum of the earlier tiles; the halves exchange the
+                // largest exponent they produced and, if a row overshot the fp16 range of P, both rescale and repeat.
+                if (t == 0) {
+                    const float mx = full_tile ? attn64_rowmax_part<true>(s_addr, kvalid, 2 * hf) : attn64_rowmax_part<false>(s_addr, kvalid, 2 * hf);
+                    *mine = mx;
+                    named_bar_sync(1 + q4, 64);
+                    m_used = fmaxf(mx, *other) * p.scale_log2;
+                } else {
+                    mbar_wait(o_full, (g - 1) & 1);   // P·V of the previous tile is done: P and O may be touched
+                    tc_fence_after();
+                }
+#pragma unroll 1
+                for (int attempt = 0; attempt < 2; ++attempt) {
+                    const float amax = full_tile ? attn64_write_p_part<true>(s_addr, kvalid, p.scale_log2, -m_used, p_smem, row, 2 * hf)
+                                                 : attn64_write_p_part<false>(s_addr, kvalid, p.scale_log2, -m_used, p_smem, row, 2 * hf);
+                    if (t == 0 || attempt == 1) break;
+                    *mine = amax;
+                    named_bar_sync(1 + q4, 64);
+                    const float arow = fmaxf(amax, *other);
+                    if (!__any_sync(0xffffffffu, arow > ATT_STREAM_LIMIT)) break;
+                    const float m_new = m_used + fmaxf(arow, 0.f);
+                    attn64_rescale_part(tmem_O, tmem_L, lane_base, ex2_fast(m_used - m_new), hf);
+                    m_used = m_new;
+                }
+                fence_proxy_async_smem();
+                tc_fence_before();
+                mbar_arrive(p_ready);
+            }
+            // ---- item epilogue: O / l -> global (the next item's first P·V waits for our next p_ready arrival)
+            mbar_wait(o_full, (g - 1) & 1);
+            tc_fence_after();
+            uint32_t lv[16];
+            tmem_ld16(tmem_L + lane_base, lv);
+            tmem_ld_wait();
+            const float inv_l = 1.f / __uint_as_float(lv[0]);
+            if (hf == 0 && p.lse != nullptr && row < w.q_valid)
+                p.lse[static_cast<size_t>(w.head) * p.lse_ld + w.q_row0 + row] = m_used + log2f(__uint_as_float(lv[0]));
+            act_t* orow = p.out + static_cast<size_t>(w.q_row0 + row) * p.out_ld + w.head * D;
+            {
+                const int c = hf;   // this half's 32 output columns
+                uint32_t v[32];
+                tmem_ld32(tmem_O + lane_base + c * 32, v);
+                tmem_ld_wait();
+                if (row < w.q_valid) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 pk;
+                        __half2* ph2 = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            ph2[k] = __floats2half2_rn(__uint_as_float(v[j * 8 + 2 * k]) * inv_l, __uint_as_float(v[j * 8 + 2 * k + 1]) * inv_l);
+                        *reinterpret_cast<uint4*>(orow + c * 32 + j * 8) = pk;
+                    }
+                }
+            }
+            tc_fence_before();   // O / l reads are complete before this thread's next p_ready arrival
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, S::TMEM_COLS);
+    }
+}
+
+
+
+
 // ===========================================================================
 // attention64x2_kernel — head_dim 64 with TWO 128-row query tiles per CTA sharing every K/V tile.
 // One CTA per SM (512 TMEM columns, ~165 KB shared memory): two softmax groups of four warps each own one query tile

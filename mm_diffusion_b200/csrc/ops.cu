@@ -362,6 +362,9 @@ int launch_attn(const AttnParams& p, int d, cudaStream_t st) {
         MMD_CUDA_OK(cudaFuncSetAttribute(attention64_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64Smem::TOTAL));
         MMD_CUDA_OK(cudaFuncSetAttribute(attention64_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64Smem::TOTAL));
         MMD_CUDA_OK(cudaFuncSetAttribute(attention64_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64Smem::TOTAL));
+        MMD_CUDA_OK(cudaFuncSetAttribute(attention64h_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64hSmem::TOTAL));
+        MMD_CUDA_OK(cudaFuncSetAttribute(attention64h_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64hSmem::TOTAL));
+        MMD_CUDA_OK(cudaFuncSetAttribute(attention64h_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64hSmem::TOTAL));
         MMD_CUDA_OK(cudaFuncSetAttribute(attention64x2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64x2Smem::TOTAL));
         MMD_CUDA_OK(cudaFuncSetAttribute(attention64x2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64x2Smem::TOTAL));
         MMD_CUDA_OK(cudaFuncSetAttribute(attention64x2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64x2Smem::TOTAL));
@@ -384,6 +387,15 @@ int launch_attn(const AttnParams& p, int d, cudaStream_t st) {
         else MMD_CUDA_OK(launch_kernel(attention64x2_kernel<2>, g2, ATT2_THREADS, Attn64x2Smem::TOTAL, st, p, items, q_pairs));
     } else if (d == 64 && !generic64) {
         const int g1 = std::min(grid, 2 * num_sms());
+        // MMD_ATTN_SPLIT=1: eight softmax warps per CTA (two threads per query row, f16x2 exponentials).  Measured equal to the
+        // four-warp kernel (cross 1.60 vs 1.60-1.65 ms, self 1.12-1.15 vs 1.08-1.10 ms per step), so it is not the default.
+        static const bool split = [] { const char* e = getenv("MMD_ATTN_SPLIT"); return e && e[0] == '1'; }();
+        if (split) {
+            if (poly == 0) MMD_CUDA_OK(launch_kernel(attention64h_kernel<0>, g1, ATT64H_THREADS, Attn64hSmem::TOTAL, st, p, grid));
+            else if (poly == 1) MMD_CUDA_OK(launch_kernel(attention64h_kernel<1>, g1, ATT64H_THREADS, Attn64hSmem::TOTAL, st, p, grid));
+            else MMD_CUDA_OK(launch_kernel(attention64h_kernel<2>, g1, ATT64H_THREADS, Attn64hSmem::TOTAL, st, p, grid));
+            return MMD_OK;
+        }
         if (poly == 0) MMD_CUDA_OK(launch_kernel(attention64_kernel<0>, g1, ATT_THREADS, Attn64Smem::TOTAL, st, p, grid));
         else if (poly == 1) MMD_CUDA_OK(launch_kernel(attention64_kernel<1>, g1, ATT_THREADS, Attn64Smem::TOTAL, st, p, grid));
         else MMD_CUDA_OK(launch_kernel(attention64_kernel<2>, g1, ATT_THREADS, Attn64Smem::TOTAL, st, p, grid));
