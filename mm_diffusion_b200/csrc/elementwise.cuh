@@ -332,41 +332,47 @@ __global__ void resample_kernel(const act_t* __restrict__ x, act_t* __restrict__
                                 int C) {
     pdl_trigger();
     pdl_wait();
-    // video: x [N][H][W][C]; audio: x [N][H(=L)][C] with W unused
-    const int vpr = C / 8;
-    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    long long total;
-    if (mode == 0) total = static_cast<long long>(N) * (H / 2) * (W / 2) * vpr;
-    else if (mode == 1) total = static_cast<long long>(N) * (H / 4) * vpr;
-    else if (mode == 2) total = static_cast<long long>(N) * (H * 2) * (W * 2) * vpr;
-    else total = static_cast<long long>(N) * (H * 4) * vpr;
+    // video: x [N][H][W][C]; audio: x [N][H(=L)][C] with W unused.  One 16-byte vector of the output per thread; the index
+    // math is 32-bit unsigned (the launcher rejects tensors of 2^31 vectors or more): 64-bit divisions by run-time values
+    // cost more instructions than the data movement itself.
+    const uint32_t vpr = static_cast<uint32_t>(C) / 8;
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t total;
+    if (mode == 0) total = static_cast<uint32_t>(N) * (H / 2) * (W / 2) * vpr;
+    else if (mode == 1) total = static_cast<uint32_t>(N) * (H / 4) * vpr;
+    else if (mode == 2) total = static_cast<uint32_t>(N) * (H * 2) * (W * 2) * vpr;
+    else total = static_cast<uint32_t>(N) * (H * 4) * vpr;
     if (idx >= total) return;
-    const int v = static_cast<int>(idx % vpr);
-    long long t = idx / vpr;
+    const uint32_t v = idx % vpr;
+    uint32_t t = idx / vpr;
     if (mode == 0 || mode == 1) {
         const uint4* src[4];
         if (mode == 0) {
-            const int ow = static_cast<int>(t % (W / 2)); t /= (W / 2);
-            const int oh = static_cast<int>(t % (H / 2));
-            const long long n = t / (H / 2);
-            const act_t* b0 = x + ((n * H + 2 * oh) * W + 2 * ow) * static_cast<long long>(C) + v * 8;
+            const uint32_t w2 = W / 2, h2 = H / 2;
+            const uint32_t ow = t % w2; t /= w2;
+            const uint32_t oh = t % h2;
+            const uint32_t n = t / h2;
+            const act_t* b0 = x + ((static_cast<size_t>(n) * H + 2 * oh) * W + 2 * ow) * C + v * 8;
             src[0] = reinterpret_cast<const uint4*>(b0);
             src[1] = reinterpret_cast<const uint4*>(b0 + C);
-            src[2] = reinterpret_cast<const uint4*>(b0 + static_cast<long long>(W) * C);
-            src[3] = reinterpret_cast<const uint4*>(b0 + static_cast<long long>(W) * C + C);
+            src[2] = reinterpret_cast<const uint4*>(b0 + static_cast<size_t>(W) * C);
+            src[3] = reinterpret_cast<const uint4*>(b0 + static_cast<size_t>(W) * C + C);
         } else {
-            const int ol = static_cast<int>(t % (H / 4));
-            const long long n = t / (H / 4);
-            const act_t* b0 = x + (n * H + 4 * ol) * static_cast<long long>(C) + v * 8;
-            for (int k = 0; k < 4; ++k) src[k] = reinterpret_cast<const uint4*>(b0 + static_cast<long long>(k) * C);
+            const uint32_t l4 = H / 4;
+            const uint32_t ol = t % l4;
+            const uint32_t n = t / l4;
+            const act_t* b0 = x + (static_cast<size_t>(n) * H + 4 * ol) * C + v * 8;
+            for (int k = 0; k < 4; ++k) src[k] = reinterpret_cast<const uint4*>(b0 + static_cast<size_t>(k) * C);
         }
+        uint4 raw[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) raw[k] = __ldg(src[k]);
         float acc[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = 0.f;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const uint4 raw = __ldg(src[k]);
-            const __half2* h = reinterpret_cast<const __half2*>(&raw);
+            const __half2* h = reinterpret_cast<const __half2*>(&raw[k]);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const float2 f = __half22float2(h[i]);
@@ -382,17 +388,75 @@ __global__ void resample_kernel(const act_t* __restrict__ x, act_t* __restrict__
     } else {
         const act_t* b0;
         if (mode == 2) {
-            const int ow = static_cast<int>(t % (W * 2)); t /= (W * 2);
-            const int oh = static_cast<int>(t % (H * 2));
-            const long long n = t / (H * 2);
-            b0 = x + ((n * H + oh / 2) * W + ow / 2) * static_cast<long long>(C) + v * 8;
+            const uint32_t w2 = W * 2, h2 = H * 2;
+            const uint32_t ow = t % w2; t /= w2;
+            const uint32_t oh = t % h2;
+            const uint32_t n = t / h2;
+            b0 = x + ((static_cast<size_t>(n) * H + oh / 2) * W + ow / 2) * C + v * 8;
         } else {
-            const int ol = static_cast<int>(t % (H * 4));
-            const long long n = t / (H * 4);
-            b0 = x + (n * H + ol / 4) * static_cast<long long>(C) + v * 8;
+            const uint32_t l4 = H * 4;
+            const uint32_t ol = t % l4;
+            const uint32_t n = t / l4;
+            b0 = x + (static_cast<size_t>(n) * H + ol / 4) * C + v * 8;
         }
         reinterpret_cast<uint4*>(y)[idx] = __ldg(reinterpret_cast<const uint4*>(b0));
     }
+}
+
+// ---------------------------------------------------------------------------
+// Narrow 3x3x3 video head as "pointwise GEMM + gather" (inference plans).  The implicit-GEMM form re-reads every
+// activation row for 27 taps (1.8 GB through L2 for 3 output channels: 206 us per step at B = 4); instead ONE pointwise GEMM
+// computes the 27 x Co per-tap partial products of every token, Y[tok][tap * 4 + c] = sum_k W[c][k][tap] * A[tok][k]
+// (27 * 4 = 108 -> 128 columns), and this kernel sums the 27 neighbours: out[pos][c] = b[c] + sum_tap Y[pos + d(tap)][tap][c]
+// with "same" zero padding.  Reference: multimodal_unet.py:1003-1007 (video_out), :68-106 (VideoConv, conv_type '3d').
+// ---------------------------------------------------------------------------
+__global__ void pack_head_taps_kernel(const float* __restrict__ w, act_t* __restrict__ dst, int Co, int Ci, int T) {
+    // w [Co][Ci][T] fp32 -> dst [128][Ci] fp16, row = tap * 4 + c (rows past T * 4 and c >= Co are zero)
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 128 * Ci) return;
+    const int row = idx / Ci, k = idx - row * Ci;
+    const int tap = row >> 2, c = row & 3;
+    const float v = (tap < T && c < Co) ? w[(static_cast<size_t>(c) * Ci + k) * T + tap] : 0.f;
+    dst[idx] = __float2half(v);
+}
+
+__global__ void __launch_bounds__(256) head_gather3d_kernel(const act_t* __restrict__ y, const float* __restrict__ bias,
+                                                            float* __restrict__ out, int B, int F, int H, int W, int Co) {
+    pdl_trigger();
+    pdl_wait();
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t total = static_cast<uint32_t>(B) * F * H * W;
+    if (idx >= total) return;
+    const int w0 = idx % W;
+    uint32_t t = idx / W;
+    const int h0 = t % H; t /= H;
+    const int f0 = t % F;
+    const int b0 = t / F;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int kt = 0; kt < 3; ++kt) {
+        const int ff = f0 + kt - 1;
+        if (ff < 0 || ff >= F) continue;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int hh = h0 + ky - 1;
+            if (hh < 0 || hh >= H) continue;
+            const act_t* rowp = y + ((static_cast<size_t>(b0) * F + ff) * H + hh) * static_cast<size_t>(W) * 128;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int ww = w0 + kx - 1;
+                if (ww < 0 || ww >= W) continue;
+                const int tap = (kt * 3 + ky) * 3 + kx;
+                const uint2 raw = __ldg(reinterpret_cast<const uint2*>(rowp + static_cast<size_t>(ww) * 128 + tap * 4));
+                const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+                const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+                acc[0] += a.x; acc[1] += a.y; acc[2] += c.x; acc[3] += c.y;
+            }
+        }
+    }
+    const size_t hw = static_cast<size_t>(H) * W;
+    float* o = out + (static_cast<size_t>(b0) * F + f0) * Co * hw + static_cast<size_t>(h0) * W + w0;
+    for (int c = 0; c < Co; ++c) o[c * hw] = acc[c] + __ldg(bias + c);
 }
 
 // ---------------------------------------------------------------------------

@@ -354,6 +354,41 @@ struct Walker {
         return &m.packs[key];
     }
 
+    // tap-major pack of a narrow conv head: [128 = T x 4 rows][ci] fp16 (pack_head_taps_kernel), no bias (the gather adds it)
+    const PackedConv* pack_head_taps(const std::string& key, int w_param, int co, int ci, int T) {
+        if (!create) {
+            auto it = m.packs.find(key);
+            if (it == m.packs.end()) { set_err(fail(MMD_ENOTFOUND, "internal: pack %s", key.c_str())); return nullptr; }
+            return &it->second;
+        }
+        if (T * 4 > 128) { set_err(fail(MMD_EINVAL, "head taps %d", T)); return nullptr; }
+        PackedConv pc;
+        pc.segs = {};
+        pc.biases = {};
+        pc.n = 128;
+        pc.bn = 128;
+        pc.n_pad = 128;
+        pc.k_total = ci;
+        pc.identity_c = 0;
+        pc.w_off = wpk_top;
+        wpk_top += (static_cast<size_t>(128) * ci + 63) & ~size_t(63);
+        pc.b_off = bpk_top;
+        bpk_top += 128;
+        MmdModel* mp = &m;
+        m.pack_ops.push_back([mp, pc, w_param, co, ci, T](cudaStream_t st) -> int {
+            pack_head_taps_kernel<<<(128 * ci + 255) / 256, 256, 0, st>>>(mp->w32 + mp->params[w_param].offset, mp->wpk + pc.w_off, co, ci, T);
+            MMD_CUDA_OK(cudaGetLastError());
+            MMD_CUDA_OK(cudaMemsetAsync(mp->bpk + pc.b_off, 0, sizeof(float) * 128, st));
+            return MMD_OK;
+        });
+        m.packs[key] = pc;
+        return &m.packs[key];
+    }
+    static bool head_taps_on() {
+        static const bool on = [] { const char* e = getenv("MMD_HEAD_TAPS"); return !(e && e[0] == '0'); }();
+        return on;
+    }
+
     // ---------------- activations
     act_t* alloc_p(size_t elems) { return static_cast<act_t*>(persist.take(elems * sizeof(act_t))); }
     act_t* alloc_s(size_t elems) { return static_cast<act_t*>(S().take(elems * sizeof(act_t))); }
@@ -1079,6 +1114,10 @@ struct Walker {
             set_err(fail(MMD_EINVAL, "head configuration unsupported (ch %d vs %d)", ch, ch0));
         const PackedConv* p_ah = pack("audio_out.head", c.audio_out_channels, {{ahead.w, ch0, 3}}, 0, {ahead.b}, 16);
         const PackedConv* p_vh = pack("video_out.head", c.video_out_channels, {{vhead.w, ch0, 27}}, 0, {vhead.b}, 16);
+        // inference plans run the video head as one pointwise GEMM over the 27 x 4 per-tap columns + a neighbour gather
+        // (head_gather3d_kernel); the tap-major weight pack lives next to the implicit-GEMM pack the training plans use
+        const bool head_taps_ok = c.video_out_channels <= 4 && ch0 % 64 == 0;
+        const PackedConv* p_vt = head_taps_ok ? pack_head_taps("video_out.head_taps", vhead.w, c.video_out_channels, ch0, 27) : nullptr;
         if (!create) {
             const size_t mark = scratch.top, mark_a = scratch_a.top;
             const int Fr = F();
@@ -1089,7 +1128,24 @@ struct Walker {
             for (int kt = 0; kt < 3; ++kt) for (int ky = 0; ky < 3; ++ky) for (int kx = 0; kx < 3; ++kx) taps27.push_back({kx - 1, ky - 1, kt - 1});
             const long long Co = c.video_out_channels, HW = static_cast<long long>(v.H) * v.W;
             const long long os_v[4] = {1, v.W, Co * HW, Fr * Co * HW};
-            emit_gemm("conv_head", g5, {{hv, ch}}, taps27, p_vh, nullptr, plan ? plan->out_video : nullptr, os_v, HW);
+            if (!train && p_vt && head_taps_on()) {
+                const size_t tokens = vtok(v);
+                act_t* ytap = alloc_s(tokens * 128);
+                ConvGeom g2; g2.rank = 2; g2.dims[0] = static_cast<long long>(tokens); geom_fill_box(g2);
+                emit_gemm("conv_head", g2, {{hv, ch}}, {{0, 0, 0}}, p_vt, ytap);
+                if (emitting() && !bad()) {
+                    const float* hb = pf(vhead.b);
+                    float* ov = plan->out_video;
+                    const int Bc = B, Hc = v.H, Wc = v.W, Coc = c.video_out_channels;
+                    push([=](cudaStream_t st) -> int {
+                        const unsigned blocks = static_cast<unsigned>((static_cast<size_t>(Bc) * Fr * Hc * Wc + 255) / 256);
+                        MMD_CUDA_OK(launch_kernel(head_gather3d_kernel, blocks, 256, 0, st, static_cast<const act_t*>(ytap), hb, ov, Bc, Fr, Hc, Wc, Coc));
+                        return MMD_OK;
+                    }, "conv_head", 0.0, 2.0 * tokens * 128 + 4.0 * tokens * Coc, 1);
+                }
+            } else {
+                emit_gemm("conv_head", g5, {{hv, ch}}, taps27, p_vh, nullptr, plan ? plan->out_video : nullptr, os_v, HW);
+            }
             cur = 1;
             act_t* ha = emit_gn(a.p, ch, nullptr, 0, B, a.L, agn, nullptr, 1, 1, &a.st, false);
             const long long Ca = c.audio_out_channels;

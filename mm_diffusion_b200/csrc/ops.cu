@@ -511,6 +511,7 @@ int launch_resample(const act_t* x, act_t* y, int mode, int n, int h, int w, int
     else if (mode == 2) total = static_cast<long long>(n) * (h * 2) * (w * 2) * vpr;
     else if (mode == 3) total = static_cast<long long>(n) * (h * 4) * vpr;
     else return fail(MMD_EINVAL, "resample mode %d", mode);
+    if (total >= (1LL << 31) - 256) return fail(MMD_EINVAL, "resample: tensor too large for 32-bit vector indexing");
     MMD_CUDA_OK(launch_kernel(resample_kernel, static_cast<unsigned>((total + 255) / 256), 256, 0, st, x, y, mode, n, h, w, c));
     return MMD_OK;
 }
