@@ -95,6 +95,28 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(GnSrc s, int R, int rows_
 }
 
 // ---------------------------------------------------------------------------
+// GroupNorm statistics of a channel concat [x1 (c1) | x2 (c2)] from the per-4-channel partial sums the producers of x1 and
+// x2 left behind (GemmParams::stats_q): sums[d][g][2] = sum over the nsub slots of domain d and the quads of group g.
+// Replaces a full statistics pass over both tensors (the decoder's skip-concat norms, multimodal_unet.py:1093-1094 + :338).
+// ---------------------------------------------------------------------------
+__global__ void gn_fold_quads_kernel(const double* __restrict__ q1, int c1, const double* __restrict__ q2, int c2, int nsub,
+                                     double* __restrict__ sums) {
+    pdl_trigger();
+    pdl_wait();
+    const int d = blockIdx.x;
+    const int g = threadIdx.x >> 1, st = threadIdx.x & 1;   // 64 threads
+    const int n1 = c1 / 4, n2 = c2 / 4;
+    const int qpg = (n1 + n2) / 32;
+    double acc = 0.0;
+    for (int j = g * qpg; j < (g + 1) * qpg; ++j) {
+        const double* src = j < n1 ? q1 + (static_cast<size_t>(d) * nsub * n1 + j) * 2 : q2 + (static_cast<size_t>(d) * nsub * n2 + (j - n1)) * 2;
+        const size_t stride = static_cast<size_t>(j < n1 ? n1 : n2) * 2;
+        for (int k = 0; k < nsub; ++k) acc += src[k * stride + st];
+    }
+    sums[(static_cast<size_t>(d) * 32 + g) * 2 + st] = acc;
+}
+
+// ---------------------------------------------------------------------------
 // GroupNorm apply: y = act( gn(x) * (1 + scale) + shift ), act = SiLU or identity.
 // Reference: nn.py:22-33; multimodal_unet.py:338-347 (in_layers: GN -> SiLU),
 // :459-470 (out_layers: GN * (1+scale) + shift -> SiLU), :284/:664 (attention norm, no SiLU).

@@ -75,6 +75,11 @@ struct alignas(64) GemmParams {
     int stats_mul[4];       // domain base = sum_i origin[i+1] * stats_mul[i] / stats_div
     int stats_div;
     int stats_valid_coord;  // >= 0: rows >= dims[c] - origin[c+1] of the tile are padding (ragged last tile)
+    // optional second output of the same reduction at 4-channel granularity: [domain][stats_q_n = N / 4][2] doubles, so a
+    // GroupNorm over a channel CONCAT that contains this tensor can fold its groups from the producers' partial sums
+    // instead of re-reading the tensors (groups of (c1 + c2) / 32 channels do not line up with either source's groups)
+    double* stats_q;
+    int stats_q_n;
     // fused GroupNorm apply on the A operand of source 0 (XF kernels, pointwise GEMMs):
     //   a <- act(gn(a) * (1 + scale) + shift), done in shared memory between the TMA landing and the MMA
     //   (reference: nn.py:22-33 + multimodal_unet.py:459-470 out_layers / :284,664 attention norms)
@@ -650,6 +655,21 @@ __global__ void __launch_bounds__(gemm_threads(EG, XF), 1) conv_gemm_kernel(cons
                         }
                         if (q_hi > q_lo)
                             atomicAdd(&p.stats[(static_cast<size_t>(dom_base + dl) * 32 + g) * 2 + st], static_cast<double>(a));
+                    }
+                    if (p.stats_q != nullptr) {
+                        constexpr int QT = BN / 4;   // quads of this tile (power of two)
+                        for (int item = et; item < ndom * QT * 2; item += 128) {
+                            const int st = item & 1;
+                            const int ql = (item >> 1) & (QT - 1);
+                            const int dl = (item >> 1) / QT;
+                            const int uq = ql >> 4, qq = ql & 15;
+                            float a = 0.f;
+                            for (int b = 0; b < bands_per_dom; ++b)
+                                a += gn_part_g[((uq * 4 + dl * bands_per_dom + b) * 16 + qq) * 2 + st];
+                            const int qg = (col_base >> 2) + ql;
+                            if (qg < p.stats_q_n)
+                                atomicAdd(&p.stats_q[(static_cast<size_t>(dom_base + dl) * p.stats_q_n + qg) * 2 + st], static_cast<double>(a));
+                        }
                     }
                     // (the next tile's named barriers order these reads before gn_part is rewritten)
                 }

@@ -116,6 +116,7 @@ struct GemmProblem {
     int stats_mul[4] = {0, 0, 0, 0};
     int stats_div = 1;
     int stats_valid_coord = -1;
+    double* stats_q = nullptr;   // optional per-4-channel partial sums [domain][n / 4][2]
     // fused GroupNorm apply (+FiLM, +SiLU) on source 0 (pointwise GEMMs; see GemmParams::xf_*)
     const double* xf_sums = nullptr;
     const float* xf_gamma = nullptr;

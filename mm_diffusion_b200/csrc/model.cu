@@ -195,7 +195,10 @@ namespace mmd {
 // ---------------------------------------------------------------------------
 // Fused GroupNorm statistics attached to a tensor by its producer: `slots` [B*nsub][32][2] doubles
 // (video: one slot per frame, nsub = F; audio: one per sample), `rows` = rows per sample the sums cover.
-struct Stat { double* slots = nullptr; int nsub = 1; long long rows = 0; };
+struct Stat {
+    double* slots = nullptr; int nsub = 1; long long rows = 0;
+    double* qslots = nullptr;   // per-4-channel partial sums of the same slots ([slot][C / 4][2]) for concat GroupNorms
+};
 struct VT { act_t* p; int C, H, W; Stat st; };   // video [B,F,H,W,C]
 struct AT { act_t* p; int C, L; Stat st; };      // audio [B,L,C]
 // A GroupNorm whose apply is deferred into the A path of the pointwise GEMM that consumes it (inference plans):
@@ -255,9 +258,16 @@ struct Walker {
         wide_n = !(w && w[0] == '1');
         const char* x = getenv("MMD_XF");
         if (x) xf_mask = atoi(x);
+        const char* qs = getenv("MMD_NO_QUAD_STATS");
+        quad_stats = fuse_stats && !(qs && qs[0] == '1');
     }
     double* stat_slots_video() { return static_cast<double*>(stats.take(sizeof(double) * 64 * B * F())); }
     double* stat_slots_audio() { return static_cast<double*>(stats.take(sizeof(double) * 64 * B)); }
+    // block outputs also leave per-4-channel partial sums: the decoder's skip-concat GroupNorms fold their statistics
+    // from the two producers instead of re-reading both tensors (MMD_NO_QUAD_STATS=1 keeps the standalone pass)
+    bool quad_stats = true;
+    double* quad_slots_video(int C) { return quad_stats ? static_cast<double*>(stats.take(sizeof(double) * 2 * (C / 4) * B * F())) : nullptr; }
+    double* quad_slots_audio(int C) { return quad_stats ? static_cast<double*>(stats.take(sizeof(double) * 2 * (C / 4) * B)) : nullptr; }
     // fused statistics need the 64- or 128-row domain runs the GEMM epilogue reduces over
     // (the epilogue reduction works on 128-column half tiles and 4-channel quads: C % 128 == 0)
     bool can_fuse_video(int hw, int c) const { return fuse_stats && hw >= 64 && c % 128 == 0; }
@@ -419,7 +429,7 @@ struct Walker {
     void emit_gemm(const char* tag, const ConvGeom& g, const std::vector<std::pair<const act_t*, int>>& srcs,
                    const std::vector<std::array<int, 3>>& taps, const PackedConv* pc, act_t* out, float* out_f32 = nullptr,
                    const long long* ostride = nullptr, long long ostride_c = 0, double* stat_slots = nullptr,
-                   int stat_kind = 0, int stat_hw = 0, int stem = 0, const XfSpec* xf = nullptr) {
+                   int stat_kind = 0, int stat_hw = 0, int stem = 0, const XfSpec* xf = nullptr, double* stat_q = nullptr) {
         if (train && pc) {
             TapeOp op;
             op.kind = TapeOp::GEMM;
@@ -460,6 +470,7 @@ struct Walker {
         } else if (stat_slots && stat_kind == 3) {
             pr.stats = stat_slots; pr.stats_rows = 128; pr.stats_mul[1] = 1; pr.stats_div = 1; pr.stats_valid_coord = 0;
         }
+        if (pr.stats) pr.stats_q = stat_q;
         if (xf && xf->on) {
             pr.xf_sums = xf->sums; pr.xf_gamma = pf(xf->gn_g); pr.xf_beta = pf(xf->gn_b); pr.xf_film = xf->film;
             pr.xf_film_ld = m.emb_rows; pr.xf_dom_per_batch = xf->ns_per_batch; pr.xf_nsub = xf->nsub; pr.xf_silu = xf->silu;
@@ -490,7 +501,7 @@ struct Walker {
     // raw input is returned for the GEMM to read.
     act_t* emit_gn(const act_t* x1, int c1, const act_t* x2, int c2, int ns, int rows, GnP gn, const float* film,
                    int ns_per_batch, int silu, const Stat* st = nullptr, bool per_frame = false, XfSpec* xf = nullptr,
-                   int xf_kind = 0, int drop_modality = -1) {
+                   int xf_kind = 0, int drop_modality = -1, const Stat* st2 = nullptr) {
         const int C = c1 + c2;
         // training plans: the out_layers' Dropout rides on this kernel (mask from a counter-based generator, so the
         // backward regenerates it); inference plans never drop
@@ -547,6 +558,19 @@ struct Walker {
         const float* beta = pf(gn.b);
         const int film_ld = m.emb_rows;
         const uint32_t dsite = drop_site >= 0 ? static_cast<uint32_t>(drop_site) : 0u;
+        // channel concat whose two producers left per-4-channel partial sums: the group statistics are a fold of those
+        // (a few KB) instead of a pass over both tensors
+        if (x2 && st && st2 && st->qslots && st2->qslots && st->nsub == st2->nsub && st->rows == rows && st2->rows == rows &&
+            c1 % 4 == 0 && c2 % 4 == 0 && (c1 + c2) % 128 == 0) {
+            const double* q1 = st->qslots;
+            const double* q2 = st2->qslots;
+            const int nsub = st->nsub;
+            push([=](cudaStream_t stx) -> int {
+                MMD_CUDA_OK(launch_kernel(gn_fold_quads_kernel, static_cast<unsigned>(ns), 64, 0, stx, q1, c1, q2, c2, nsub, sums));
+                return launch_gn_apply(s, ns, rows, sums, gamma, beta, film, film_ld, ns_per_batch, silu, y, stx, 1, 0, drop_dev, dsite);
+            }, "group_norm", 0.0, 2.0 * ns * static_cast<double>(rows) * C + 2.0 * ns * static_cast<double>(rows) * C, 2);
+            return y;
+        }
         push([=](cudaStream_t st) -> int {
             MMD_TRY(launch_gn_stats(s, ns, rows, sums, st, false));
             return launch_gn_apply(s, ns, rows, sums, gamma, beta, film, film_ld, ns_per_batch, silu, y, st, 1, 0, drop_dev, dsite);
@@ -647,23 +671,26 @@ struct Walker {
         // statistics of the block output for its consumer's GroupNorm (the spatial output only feeds the
         // per-pixel temporal norm, which computes its own)
         double* slots = nullptr;
+        double* qsl = nullptr;
         int skind = 0, shw = 0;
         if (out_st) *out_st = Stat{};
         if (kind == 1 && can_fuse_video(vt->H * vt->W, C)) {
             slots = stat_slots_video(); skind = 1; shw = vt->H * vt->W;
-            if (out_st) *out_st = Stat{slots, F(), static_cast<long long>(F()) * shw};
+            qsl = quad_slots_video(C);
+            if (out_st) *out_st = Stat{slots, F(), static_cast<long long>(F()) * shw, qsl};
         } else if (kind == 2 && can_fuse_audio(at->L, C)) {
             slots = stat_slots_audio(); skind = 3;
-            if (out_st) *out_st = Stat{slots, 1, at->L};
+            qsl = quad_slots_audio(C);
+            if (out_st) *out_st = Stat{slots, 1, at->L, qsl};
         }
-        emit_gemm("conv1x1_proj", gtok, {{o, C}, {x, C}}, {{0, 0, 0}}, pp, out, nullptr, nullptr, 0, slots, skind, shw);
+        emit_gemm("conv1x1_proj", gtok, {{o, C}, {x, C}}, {{0, 0, 0}}, pp, out, nullptr, nullptr, 0, slots, skind, shw, 0, nullptr, qsl);
         release(S(), mark);
         cur = 0;
         return out;
     }
 
     void res_block(const std::string& p, VT& v, const act_t* v2, int vc2, AT& a, const act_t* a2, int ac2, int cout,
-                   int dilation, bool up, bool down, bool vattn, bool aattn) {
+                   int dilation, bool up, bool down, bool vattn, bool aattn, const Stat* v2st = nullptr, const Stat* a2st = nullptr) {
         const int cin = v.C + vc2;
         const int E = cfg().model_channels;
         // registration order = module definition order in ResBlock.__init__ (multimodal_unet.py:338-419)
@@ -725,7 +752,7 @@ struct Walker {
                 cur = 0;
                 const size_t mark = S().top;
                 const int hw = v.H * v.W;
-                act_t* h0 = emit_gn(v.p, v.C, v2, vc2, B, Fr * hw, vin_gn, nullptr, 1, 1, &v.st, false);
+                act_t* h0 = emit_gn(v.p, v.C, v2, vc2, B, Fr * hw, vin_gn, nullptr, 1, 1, &v.st, false, nullptr, 0, -1, v2st);
                 act_t* u = alloc_s(vtok(v) * cout);
                 VT vin{h0, cin, v.H, v.W};
                 std::vector<std::array<int, 3>> taps9;
@@ -769,9 +796,9 @@ struct Walker {
                                     (xf_mask & 1) ? &xfv : nullptr, 1, 0);
                 std::vector<std::pair<const act_t*, int>> srcs = {{h2, cout}, {xs, v.C}};
                 if (v2) srcs.push_back({v2, vc2});
-                if (can_fuse_video(hwo, cout)) vo.st = Stat{stat_slots_video(), Fr, static_cast<long long>(Fr) * hwo};
+                if (can_fuse_video(hwo, cout)) vo.st = Stat{stat_slots_video(), Fr, static_cast<long long>(Fr) * hwo, quad_slots_video(cout)};
                 emit_gemm("conv1x1_out", geom2(static_cast<long long>(B) * Fr * hwo), srcs, {{0, 0, 0}}, p_vo, vo.p,
-                          nullptr, nullptr, 0, vo.st.slots, 1, hwo, 0, &xfv);
+                          nullptr, nullptr, 0, vo.st.slots, 1, hwo, 0, &xfv, vo.st.qslots);
                 release(S(), mark);
             }
             // ---------------- audio branch
@@ -781,7 +808,7 @@ struct Walker {
                 ao.p = alloc_p(static_cast<size_t>(B) * ao.L * cout);
                 cur = 1;
                 const size_t mark = S().top;
-                act_t* h0 = emit_gn(a.p, a.C, a2, ac2, B, a.L, ain_gn, nullptr, 1, 1, &a.st, false);
+                act_t* h0 = emit_gn(a.p, a.C, a2, ac2, B, a.L, ain_gn, nullptr, 1, 1, &a.st, false, nullptr, 0, -1, a2st);
                 act_t* h1 = alloc_s(atok(a) * cout);
                 AT ain{h0, cin, a.L};
                 Stat h1st;
@@ -819,9 +846,9 @@ struct Walker {
                                     (xf_mask & 1) ? &xfa : nullptr, 3, 1);
                 std::vector<std::pair<const act_t*, int>> srcs = {{h2, cout}, {xs, a.C}};
                 if (a2) srcs.push_back({a2, ac2});
-                if (can_fuse_audio(ao.L, cout)) ao.st = Stat{stat_slots_audio(), 1, ao.L};
+                if (can_fuse_audio(ao.L, cout)) ao.st = Stat{stat_slots_audio(), 1, ao.L, quad_slots_audio(cout)};
                 emit_gemm("conv1x1_out", geom_audio(ao), srcs, {{0, 0, 0}}, p_ao, ao.p, nullptr, nullptr, 0, ao.st.slots, 3, 0,
-                          0, &xfa);
+                          0, &xfa, ao.st.qslots);
                 release(S(), mark);
                 cur = 0;
             }
@@ -898,13 +925,13 @@ struct Walker {
         sync_branches();
         cur = 0;
         Stat vst, ast;
-        if (can_fuse_video(hw, C)) vst = Stat{stat_slots_video(), Fr, static_cast<long long>(Fr) * hw};
-        if (can_fuse_audio(a.L, C)) ast = Stat{stat_slots_audio(), 1, a.L};
+        if (can_fuse_video(hw, C)) vst = Stat{stat_slots_video(), Fr, static_cast<long long>(Fr) * hw, quad_slots_video(C)};
+        if (can_fuse_audio(a.L, C)) ast = Stat{stat_slots_audio(), 1, a.L, quad_slots_audio(C)};
         emit_gemm("conv1x1_proj", geom2(static_cast<long long>(vt)), {{ov, C}, {v.p, C}}, {{0, 0, 0}}, p_vp, vout,
-                  nullptr, nullptr, 0, vst.slots, 1, hw);
+                  nullptr, nullptr, 0, vst.slots, 1, hw, 0, nullptr, vst.qslots);
         cur = 1;
         emit_gemm("conv1x1_proj", geom_audio(a), {{oa, C}, {a.p, C}}, {{0, 0, 0}}, p_ap, aout, nullptr, nullptr, 0,
-                  ast.slots, 3, 0);
+                  ast.slots, 3, 0, 0, nullptr, ast.qslots);
         cur = 0;
         release(scratch, mark_v);
         release(scratch_a, mark_a);
@@ -998,9 +1025,9 @@ struct Walker {
                         }, "im2col", 0.0, (4.0 * Cv + 128.0) * static_cast<double>(BF) * H * W, 1);
                     }
                     emit_gemm("conv_stem", geom2(static_cast<long long>(vtok(v))), {{colv, 64}}, {{0, 0, 0}}, p_sp, u, nullptr, nullptr, 0, nullptr, 0, 0, 1);
-                    if (can_fuse_video(hw0, ch)) v.st = Stat{stat_slots_video(), F(), static_cast<long long>(F()) * hw0};
+                    if (can_fuse_video(hw0, ch)) v.st = Stat{stat_slots_video(), F(), static_cast<long long>(F()) * hw0, quad_slots_video(ch)};
                     emit_gemm("conv_temporal", geom_temporal(v), {{u, ch}}, {{0, -1, 0}, {0, 0, 0}, {0, 1, 0}}, p_tp, v.p,
-                              nullptr, nullptr, 0, v.st.slots, 2, 0);
+                              nullptr, nullptr, 0, v.st.slots, 2, 0, 0, nullptr, v.st.qslots);
                     release(S(), mark);
                 }
                 {   // audio branch
@@ -1017,8 +1044,9 @@ struct Walker {
                             return MMD_OK;
                         }, "im2col", 0.0, (4.0 * Ca + 128.0) * static_cast<double>(Bc) * L, 1);
                     }
-                    if (can_fuse_audio(a.L, ch)) a.st = Stat{stat_slots_audio(), 1, a.L};
-                    emit_gemm("conv_stem", geom_audio(a), {{cola, 64}}, {{0, 0, 0}}, p_ac, a.p, nullptr, nullptr, 0, a.st.slots, 3, 0, 2);
+                    if (can_fuse_audio(a.L, ch)) a.st = Stat{stat_slots_audio(), 1, a.L, quad_slots_audio(ch)};
+                    emit_gemm("conv_stem", geom_audio(a), {{cola, 64}}, {{0, 0, 0}}, p_ac, a.p, nullptr, nullptr, 0, a.st.slots, 3, 0, 2,
+                              nullptr, a.st.qslots);
                     release(S(), mark);
                     cur = 0;
                 }
@@ -1089,7 +1117,7 @@ struct Walker {
                 int sub = 0;
                 res_block(p + "." + std::to_string(sub++), v, vs.p, ich, a, as.p, ich, cout, 1 << (dil % 10), false, false,
                           contains(c.video_attention_resolutions, c.n_video_attn, ds),
-                          contains(c.audio_attention_resolutions, c.n_audio_attn, ds));
+                          contains(c.audio_attention_resolutions, c.n_audio_attn, ds), &vs.st, &as.st);
                 dil -= 1;
                 ch = cout;
                 if (contains(c.cross_attention_resolutions, c.n_cross, ds)) {

@@ -171,6 +171,8 @@ int build_gemm(const GemmProblem& pr, GemmParams* out) {
         p.stats_div = pr.stats_div;
         p.fd_stats.set(static_cast<uint32_t>(pr.stats_div));
         p.stats_valid_coord = pr.stats_valid_coord;
+        p.stats_q = pr.stats_q;
+        p.stats_q_n = pr.n / 4;
         if (pr.stats_rows != 128 && pr.stats_rows != 64) return fail(MMD_EINVAL, "stats_rows %d", pr.stats_rows);
     }
     if (pr.xf_sums) {
