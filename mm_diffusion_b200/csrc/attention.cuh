@@ -39,7 +39,21 @@ struct alignas(64) AttnParams {
     // kernels rebuild P = exp2(s * scale_log2 - lse) from it (null = not written)
     float* lse;
     long long lse_ld;
+    // -DMMD_ATTN_TRACE builds only: clock64 stamps of the first CTAs' roles per key tile (tools/gpu_attn_trace.py)
+    long long* trace;
 };
+
+// Timeline instrumentation of attention64_kernel (compiled out unless -DMMD_ATTN_TRACE): role 0 = softmax warp 0,
+// 1 = MMA warp, 2 = TMA warp; up to 8 events per (CTA, role, tile); CTAs 0..7, tiles 0..31.
+#ifdef MMD_ATTN_TRACE
+#define ATT_TRACE(p, role, g, ev)                                                                              \
+    do {                                                                                                       \
+        if ((p).trace != nullptr && blockIdx.x < 8 && (g) < 32 && (threadIdx.x & 31) == 0)                       \
+            (p).trace[((static_cast<int>(blockIdx.x) * 3 + (role)) * 32 + (g)) * 8 + (ev)] = clock64();          \
+    } while (0)
+#else
+#define ATT_TRACE(p, role, g, ev) do { } while (0)
+#endif
 
 struct AttnWork {
     int q_row0, q_valid;
@@ -471,8 +485,11 @@ MMD_DEVINL float attn64_rowmax(uint32_t s_addr, int kvalid) {
 // PQ of every 4 consecutive elements take ex2_poly instead of the MUFU op (0, 1 or 2).
 // Returns the largest exponent argument s * scale - m of the valid columns: the streaming path of the kernels uses the
 // running maximum of EARLIER tiles as m and only checks afterwards that nothing came near the fp16 range of P.
+// wait_bar (optional): barrier that frees the P tile (P.V of the previous key tile retired); it is waited for only right
+// before the first shared-memory store, so the TMEM load and the first 32 columns' exponentials overlap that P.V.
 template <bool FULL, int PQ>
-MMD_DEVINL float attn64_write_p(uint32_t s_addr, int kvalid, float scale_log2, float nm, uint8_t* p_smem, int row) {
+MMD_DEVINL float attn64_write_p(uint32_t s_addr, int kvalid, float scale_log2, float nm, uint8_t* p_smem, int row,
+                                uint64_t* wait_bar = nullptr, uint32_t wait_parity = 0) {
     float amax = -INFINITY;
     uint32_t va[32], vb[32];
     tmem_ld32(s_addr, va);
@@ -484,10 +501,10 @@ MMD_DEVINL float attn64_write_p(uint32_t s_addr, int kvalid, float scale_log2, f
         tmem_ld_wait();
         if (c < 3 && (FULL || (c + 1) * 32 < kvalid)) tmem_ld32(s_addr + (c + 1) * 32, (c & 1) ? va : vb);
         uint8_t* chunk = p_smem + (c >> 1) * (ATT_BQ * 128);
+        uint4 pks[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            uint4 pk;
-            uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
+            uint32_t* pw = reinterpret_cast<uint32_t*>(&pks[j]);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int col = c * 32 + j * 8 + 2 * k;
@@ -504,8 +521,13 @@ MMD_DEVINL float attn64_write_p(uint32_t s_addr, int kvalid, float scale_log2, f
                 const __half2 h = __floats2half2_rn(e0, e1);
                 pw[k] = *reinterpret_cast<const uint32_t*>(&h);
             }
-            *reinterpret_cast<uint4*>(chunk + sw128_off(row, (c & 1) * 4 + j)) = pk;
         }
+        if (c == 0 && wait_bar != nullptr) {
+            mbar_wait(wait_bar, wait_parity);
+            tc_fence_after();
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(chunk + sw128_off(row, (c & 1) * 4 + j)) = pks[j];
     }
     return amax;
 }
@@ -605,12 +627,14 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention64_kernel(const __gri
                     int krow, kvalid;
                     attn_tile(w, t, krow, kvalid);
                     mbar_wait(&k_empty[st], ((g >> 1) & 1) ^ 1);
+                    ATT_TRACE(p, 2, g, 0);   // K stage free
                     if (elect_one()) {
                         mbar_expect_tx(&k_full[st], 16384);
                         tma_load_2d(smem + S::K_OFF + st * 16384, &p.k_map, &k_full[st], p.k_col0 + w.head * D, krow);
                     }
                     __syncwarp();
                     mbar_wait(v_empty, (g & 1) ^ 1);
+                    ATT_TRACE(p, 2, g, 1);   // V stage free
                     if (elect_one()) {
                         mbar_expect_tx(v_full, 16384);
                         tma_load_2d(smem + S::V_OFF, &p.v_map, v_full, p.v_col0 + w.head * D, krow);
@@ -640,6 +664,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention64_kernel(const __gri
                 }
                 const int st = gq & 1;
                 mbar_wait(&k_full[st], (gq >> 1) & 1);
+                ATT_TRACE(p, 1, gq, 0);   // K tile landed (Q.K^T of tile gq can issue)
                 tc_fence_after();
                 const uint64_t kd = kd0 + static_cast<uint64_t>(st) * (16384 >> 4);
                 if (elect_one()) {
@@ -662,7 +687,15 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention64_kernel(const __gri
                     int krow, kvalid;
                     attn_tile(w, t, krow, kvalid);
                     mbar_wait(p_ready, g & 1);
+                    ATT_TRACE(p, 1, g, 1);   // softmax of tile g done
+                    // The logits of the NEXT tile go first: S is free as soon as the softmax of this tile has read it, and the
+                    // softmax warps can start on them while P.V / P.1 of this tile are still being issued and executed
+                    // (measured: issuing the 16 small-N MMAs of P.V / P.1 alone takes ~840 cycles)
+                    // (Within an item only: the first logits of the NEXT item wait for its Q tile, which must not hold up
+                    // the last P.V of this one — measured 7400 -> 9600 cycles per item boundary when it did.)
+                    if (t + 1 < w.n_tiles) issue_qk(w, t + 1);
                     mbar_wait(v_full, g & 1);
+                    ATT_TRACE(p, 1, g, 2);   // V tile landed
                     tc_fence_after();
                     const int nks = (kvalid + 15) >> 4;
                     if (elect_one()) {
@@ -697,10 +730,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention64_kernel(const __gri
                         umma_commit(o_full);
                     }
                     __syncwarp();
-                    // next logits: same item, or the first tile of the next item (S is free: softmax of this tile is done)
-                    if (t + 1 < w.n_tiles) {
-                        issue_qk(w, t + 1);
-                    } else if (item + static_cast<int>(gridDim.x) < n_items) {
+                    ATT_TRACE(p, 1, g, 3);   // P.V of tile g issued
+                    if (t + 1 == w.n_tiles && item + static_cast<int>(gridDim.x) < n_items) {
                         const AttnWork wn = attn_decode(p, item + gridDim.x);
                         issue_qk(wn, 0);
                     }
@@ -726,6 +757,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention64_kernel(const __gri
                 int krow, kvalid;
                 attn_tile(w, t, krow, kvalid);
                 mbar_wait(s_full, g & 1);
+                if (warp == 0) ATT_TRACE(p, 0, g, 0);   // logits of tile g ready
                 tc_fence_after();
                 if (!warp_active) {
                     if (t > 0) {
@@ -745,14 +777,16 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention64_kernel(const __gri
                 if (t == 0) {
                     const float mx = full_tile ? attn64_rowmax<true>(s_addr, kvalid) : attn64_rowmax<false>(s_addr, kvalid);
                     m_used = mx * p.scale_log2;
-                } else {
-                    mbar_wait(o_full, (g - 1) & 1);   // P·V of the previous tile is done: P and O may be touched
-                    tc_fence_after();
                 }
+                // t >= 1: P (and, for a fix-up, O) may only be touched once P·V of the previous tile has retired; the wait
+                // sits inside the first pass, right before its first store
 #pragma unroll 1
                 for (int attempt = 0; attempt < 2; ++attempt) {
-                    const float amax = full_tile ? attn64_write_p<true, PQ>(s_addr, kvalid, p.scale_log2, -m_used, p_smem, row)
-                                                 : attn64_write_p<false, PQ>(s_addr, kvalid, p.scale_log2, -m_used, p_smem, row);
+                    uint64_t* wb = (t > 0 && attempt == 0) ? o_full : nullptr;
+                    const uint32_t wp = static_cast<uint32_t>((g - 1) & 1);
+                    const float amax = full_tile ? attn64_write_p<true, PQ>(s_addr, kvalid, p.scale_log2, -m_used, p_smem, row, wb, wp)
+                                                 : attn64_write_p<false, PQ>(s_addr, kvalid, p.scale_log2, -m_used, p_smem, row, wb, wp);
+                    if (warp == 0 && attempt == 0) ATT_TRACE(p, 0, g, 1);   // first pass done (P.V of tile g - 1 retired inside it)
                     if (t == 0 || attempt == 1 || !__any_sync(0xffffffffu, amax > ATT_STREAM_LIMIT)) break;
                     const float m_new = m_used + fmaxf(amax, 0.f);
                     attn64_rescale(tmem_O, tmem_L, lane_base, ex2_fast(m_used - m_new));
@@ -760,6 +794,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention64_kernel(const __gri
                 }
                 fence_proxy_async_smem();
                 tc_fence_before();
+                if (warp == 0) ATT_TRACE(p, 0, g, 2);   // probabilities of tile g written
                 mbar_arrive(p_ready);
             }
             // ---- item epilogue: O / l -> global (the next item's first P·V waits for our next p_ready arrival)
@@ -800,6 +835,338 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention64_kernel(const __gri
         tmem_dealloc(tmem_base, S::TMEM_COLS);
     }
 }
+
+
+// ---- attention64t_kernel: P never touches shared memory.  The probabilities go back to TENSOR memory (fp16, two per
+// 32-bit column, 64 columns next to S / O) and P.V reads its A operand from there (tcgen05.mma with a TMEM A operand);
+// the row sums are fp32 registers.  Per 128-key tile this removes the 32 KB of P stores and the 64 KB the P.V / P.1 MMAs read
+// back: the two CTAs of an SM were spending ~1400 of ~2200 cycles per tile on shared-memory bandwidth.
+struct Attn64tSmem {
+    static constexpr int Q_OFF = 0;
+    static constexpr int K_OFF = 16384;                 // 2 stages
+    static constexpr int V_OFF = K_OFF + 2 * 16384;     // 2 stages (the P tile's 32 KB are free)
+    static constexpr int BAR_OFF = V_OFF + 2 * 16384;
+    static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+    static constexpr int TMEM_COLS = 256;               // S 0..127 | O 128..191 | P 192..255
+};
+
+// p = exp2(s * scale - m) for the thread's row: fp16 pairs into TMEM columns p_addr .. +63, sum of the (rounded) values
+// into psum.  wait_bar: barrier that frees P / O (P.V of the previous tile retired), waited for before the first store.
+template <bool FULL>
+MMD_DEVINL float attn64_write_p_tmem(uint32_t s_addr, uint32_t p_addr, int kvalid, float scale_log2, float nm, float& psum,
+                                     uint64_t* wait_bar, uint32_t wait_parity) {
+    float amax = -INFINITY;
+    float s0 = 0.f, s1 = 0.f;
+    uint32_t va[32], vb[32];
+    tmem_ld32(s_addr, va);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        if (!FULL && c * 32 >= kvalid) break;
+        uint32_t* cur = (c & 1) ? vb : va;
+        tmem_ld_wait();
+        if (c < 3 && (FULL || (c + 1) * 32 < kvalid)) tmem_ld32(s_addr + (c + 1) * 32, (c & 1) ? va : vb);
+        uint32_t pw[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int col = c * 32 + 2 * k;
+            const float a0 = fmaf(__uint_as_float(cur[2 * k]), scale_log2, nm);
+            const float a1 = fmaf(__uint_as_float(cur[2 * k + 1]), scale_log2, nm);
+            float e0 = ex2_fast(a0);
+            float e1 = ex2_fast(a1);
+            if (!FULL) {
+                if (col >= kvalid) e0 = 0.f; else amax = fmaxf(amax, a0);
+                if (col + 1 >= kvalid) e1 = 0.f; else amax = fmaxf(amax, a1);
+            } else {
+                amax = fmaxf(amax, fmaxf(a0, a1));
+            }
+            const __half2 h = __floats2half2_rn(e0, e1);
+            const float2 hr = __half22float2(h);
+            s0 += hr.x;
+            s1 += hr.y;
+            pw[k] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        if (c == 0 && wait_bar != nullptr) {
+            mbar_wait(wait_bar, wait_parity);
+            tc_fence_after();
+        }
+        tmem_st16(p_addr + c * 16, pw);
+    }
+    psum = s0 + s1;
+    return amax;
+}
+
+MMD_DEVINL void attn64_rescale_o(uint32_t tmem_O, uint32_t lane_base, float alpha) {
+    uint32_t o[32];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        tmem_ld32(tmem_O + lane_base + c * 32, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+        tmem_st32(tmem_O + lane_base + c * 32, o);
+    }
+    tmem_st_wait();
+}
+
+template <int PQ>
+__global__ void __launch_bounds__(ATT_THREADS, 2) attention64t_kernel(const __grid_constant__ AttnParams p, int n_items) {
+    // Persistent: a CTA walks work items blockIdx.x, +gridDim.x, ... ; the TMA warp runs ahead into the next item
+    // (Q as soon as the last Q·K^T of the current item has been issued, K/V as stages free up), so the per-item
+    // start-up latency (Q/K fetch, barrier set-up, TMEM allocation) is paid once per CTA instead of once per item.
+    using S = Attn64tSmem;
+    constexpr int D = 64;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
+    uint64_t* q_full = bars;        // 1
+    uint64_t* q_empty = bars + 1;   // 1
+    uint64_t* k_full = bars + 2;    // 2
+    uint64_t* k_empty = bars + 4;   // 2
+    uint64_t* v_full = bars + 6;    // 2
+    uint64_t* v_empty = bars + 8;   // 2
+    uint64_t* s_full = bars + 10;   // 1
+    uint64_t* p_ready = bars + 11;  // 1 (128 arrivals)
+    uint64_t* o_full = bars + 12;   // 1
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    pdl_trigger();
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&p.q_map);
+        tma_prefetch_desc(&p.k_map);
+        tma_prefetch_desc(&p.v_map);
+        mbar_init(q_full, 1);
+        mbar_init(q_empty, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
+        mbar_init(s_full, 1);
+        mbar_init(p_ready, 128);
+        mbar_init(o_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 5) tmem_alloc(tmem_slot, S::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();   // q/k/v come from the previous kernel
+    const uint32_t tmem_S = tmem_base;
+    const uint32_t tmem_O = tmem_base + 128;
+    const uint32_t tmem_P = tmem_base + 192;   // P (fp16, two per column): 64 columns
+
+    if (warp == 4) {
+        // ===================== TMA producer =====================
+        // whole warp in uniform control flow (all lanes wait), one elected lane issues: a lane-guarded branch makes
+        // ptxas wrap every TMA / tcgen05 instruction in an ELECT + BRA.U.ANY loop over the active lanes (gemm.cuh)
+        {
+            int g = 0;   // KV tiles issued so far (all items)
+            int it = 0;  // items started
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                const AttnWork w = attn_decode(p, item);
+                mbar_wait(q_empty, (it & 1) ^ 1);   // last Q·K^T of the previous item has been issued and retired
+                if (elect_one()) {
+                    mbar_expect_tx(q_full, 16384);
+                    tma_load_2d(smem + S::Q_OFF, &p.q_map, q_full, p.q_col0 + w.head * D, w.q_row0);
+                }
+                __syncwarp();
+                for (int t = 0; t < w.n_tiles; ++t, ++g) {
+                    const int st = g & 1;
+                    int krow, kvalid;
+                    attn_tile(w, t, krow, kvalid);
+                    mbar_wait(&k_empty[st], ((g >> 1) & 1) ^ 1);
+                    ATT_TRACE(p, 2, g, 0);   // K stage free
+                    if (elect_one()) {
+                        mbar_expect_tx(&k_full[st], 16384);
+                        tma_load_2d(smem + S::K_OFF + st * 16384, &p.k_map, &k_full[st], p.k_col0 + w.head * D, krow);
+                    }
+                    __syncwarp();
+                    mbar_wait(&v_empty[st], ((g >> 1) & 1) ^ 1);
+                    ATT_TRACE(p, 2, g, 1);   // V stage free
+                    if (elect_one()) {
+                        mbar_expect_tx(&v_full[st], 16384);
+                        tma_load_2d(smem + S::V_OFF + st * 16384, &p.v_map, &v_full[st], p.v_col0 + w.head * D, krow);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ===================== MMA issuer (uniform warp, elected lane) =====================
+        {
+            constexpr uint32_t idesc_qk = umma_idesc_f16(ATT_BQ, ATT_BKV, 0, 0);
+            constexpr uint32_t idesc_pv = umma_idesc_f16(ATT_BQ, D, 0, 1);   // V is MN-major
+            const uint64_t qd0 = umma_desc_sw128(smem_u32(smem + S::Q_OFF), 16, 1024);
+            const uint64_t kd0 = umma_desc_sw128(smem_u32(smem + S::K_OFF), 16, 1024);
+            const uint64_t vd0 = umma_desc_sw128(smem_u32(smem + S::V_OFF), ATT_BKV * 128, 1024);   // MN-major V
+            int gq = 0;   // Q·K^T tiles issued
+            int itq = 0;  // items whose first Q·K^T has been issued
+            // issues Q·K^T of tile t of the item `w` (first tile waits for that item's Q; last tile releases Q)
+            auto issue_qk = [&](const AttnWork& w, int t) {
+                if (t == 0) {
+                    mbar_wait(q_full, itq & 1);
+                    ++itq;
+                }
+                const int st = gq & 1;
+                mbar_wait(&k_full[st], (gq >> 1) & 1);
+                ATT_TRACE(p, 1, gq, 0);   // K tile landed (Q.K^T of tile gq can issue)
+                tc_fence_after();
+                const uint64_t kd = kd0 + static_cast<uint64_t>(st) * (16384 >> 4);
+                if (elect_one()) {
+#pragma unroll
+                    for (int ks = 0; ks < D / 16; ++ks)
+                        umma_f16_ss(tmem_S, qd0 + 2 * ks, kd + 2 * ks, idesc_qk, ks != 0 ? 1u : 0u);
+                    umma_commit(&k_empty[st]);
+                    if (t == w.n_tiles - 1) umma_commit(q_empty);
+                    umma_commit(s_full);
+                }
+                __syncwarp();
+                ++gq;
+            };
+            int g = 0;
+            bool first = true;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const AttnWork w = attn_decode(p, item);
+                if (first) { issue_qk(w, 0); first = false; }
+                for (int t = 0; t < w.n_tiles; ++t, ++g) {
+                    int krow, kvalid;
+                    attn_tile(w, t, krow, kvalid);
+                    mbar_wait(p_ready, g & 1);
+                    ATT_TRACE(p, 1, g, 1);   // softmax of tile g done
+                    // The logits of the NEXT tile go first: S is free as soon as the softmax of this tile has read it, and the
+                    // softmax warps can start on them while P.V / P.1 of this tile are still being issued and executed
+                    // (measured: issuing the 16 small-N MMAs of P.V / P.1 alone takes ~840 cycles)
+                    // (Within an item only: the first logits of the NEXT item wait for its Q tile, which must not hold up
+                    // the last P.V of this one — measured 7400 -> 9600 cycles per item boundary when it did.)
+                    if (t + 1 < w.n_tiles) issue_qk(w, t + 1);
+                    const int vst = g & 1;
+                    mbar_wait(&v_full[vst], (g >> 1) & 1);
+                    ATT_TRACE(p, 1, g, 2);   // V tile landed
+                    tc_fence_after();
+                    const int nks = (kvalid + 15) >> 4;
+                    if (elect_one()) {
+                        // P is the A operand straight from tensor memory: 8 columns (16 keys) per K step
+                        const uint64_t vd = vd0 + static_cast<uint64_t>(vst) * (16384 >> 4);
+                        if (nks == ATT_BKV / 16) {
+#pragma unroll
+                            for (int ks = 0; ks < ATT_BKV / 16; ++ks)
+                                umma_f16_ts(tmem_O, tmem_P + ks * 8, vd + ks * (2048 >> 4), idesc_pv, (t | ks) != 0 ? 1u : 0u);
+                        } else {
+                            for (int ks = 0; ks < nks; ++ks)
+                                umma_f16_ts(tmem_O, tmem_P + ks * 8, vd + ks * (2048 >> 4), idesc_pv, (t | ks) != 0 ? 1u : 0u);
+                        }
+                        umma_commit(&v_empty[vst]);
+                        umma_commit(o_full);
+                    }
+                    __syncwarp();
+                    ATT_TRACE(p, 1, g, 3);   // P.V of tile g issued
+                    if (t + 1 == w.n_tiles && item + static_cast<int>(gridDim.x) < n_items) {
+                        const AttnWork wn = attn_decode(p, item + gridDim.x);
+                        issue_qk(wn, 0);
+                    }
+                }
+            }
+        }
+    } else {
+        // ===================== softmax warps (thread = query row) =====================
+        const int row = warp * 32 + lane;
+        const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+        const uint32_t s_addr = tmem_S + lane_base;
+        int g = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const AttnWork w = attn_decode(p, item);
+            const int T = w.n_tiles;
+            float m_used = 0.f;
+            float l_run = 0.f;   // row sum of the probabilities (fp32 registers; the scale of m_used)
+            // ragged query blocks (400 / 100 / 25 audio tokens per segment): a warp whose 32 rows all lie past the block
+            // skips the whole softmax (the exp unit is the limiter) and only keeps the barrier protocol going; its
+            // P / O rows are garbage that is never stored
+            const bool warp_active = warp * 32 < w.q_valid;
+            for (int t = 0; t < T; ++t, ++g) {
+                int krow, kvalid;
+                attn_tile(w, t, krow, kvalid);
+                mbar_wait(s_full, g & 1);
+                if (warp == 0) ATT_TRACE(p, 0, g, 0);   // logits of tile g ready
+                tc_fence_after();
+                if (!warp_active) {
+                    if (t > 0) {
+                        mbar_wait(o_full, (g - 1) & 1);
+                        tc_fence_after();
+                    }
+                    tc_fence_before();
+                    mbar_arrive(p_ready);
+                    continue;
+                }
+                const bool full_tile = (kvalid == ATT_BKV);
+                // First tile of an item: the true row maximum has to be known before any exponential (a max pass, then the
+                // probability pass).  Later tiles: ONE streaming pass over the logits (TMEM reads, 64 B/clk/SM, cost as much
+                // as the exponentials) — the probabilities are taken against the running maximum of the EARLIER tiles (P is
+                // fp16 and O / l are fp32, so exponents up to 2^14 are harmless), and only if a row overshoots that range
+                // (rare after the first tile) the accumulators are rescaled and the pass is repeated.
+                if (t == 0) {
+                    const float mx = full_tile ? attn64_rowmax<true>(s_addr, kvalid) : attn64_rowmax<false>(s_addr, kvalid);
+                    m_used = mx * p.scale_log2;
+                }
+                // t >= 1: P (and, for a fix-up, O) may only be touched once P·V of the previous tile has retired; the wait
+                // sits inside the first pass, right before its first store
+                float tile_sum = 0.f;
+#pragma unroll 1
+                for (int attempt = 0; attempt < 2; ++attempt) {
+                    uint64_t* wb = (t > 0 && attempt == 0) ? o_full : nullptr;
+                    const uint32_t wp = static_cast<uint32_t>((g - 1) & 1);
+                    const float amax = full_tile ? attn64_write_p_tmem<true>(s_addr, tmem_P + lane_base, kvalid, p.scale_log2, -m_used, tile_sum, wb, wp)
+                                                 : attn64_write_p_tmem<false>(s_addr, tmem_P + lane_base, kvalid, p.scale_log2, -m_used, tile_sum, wb, wp);
+                    if (warp == 0 && attempt == 0) ATT_TRACE(p, 0, g, 1);   // first pass done (P.V of tile g - 1 retired inside it)
+                    if (t == 0 || attempt == 1 || !__any_sync(0xffffffffu, amax > ATT_STREAM_LIMIT)) break;
+                    const float m_new = m_used + fmaxf(amax, 0.f);
+                    const float alpha = ex2_fast(m_used - m_new);
+                    attn64_rescale_o(tmem_O, lane_base, alpha);
+                    l_run *= alpha;
+                    m_used = m_new;
+                }
+                l_run += tile_sum;
+                tmem_st_wait();
+                tc_fence_before();
+                if (warp == 0) ATT_TRACE(p, 0, g, 2);   // probabilities of tile g written
+                mbar_arrive(p_ready);
+            }
+            // ---- item epilogue: O / l -> global (the next item's first P·V waits for our next p_ready arrival)
+            mbar_wait(o_full, (g - 1) & 1);
+            tc_fence_after();
+            const float inv_l = 1.f / l_run;
+            if (p.lse != nullptr && row < w.q_valid)
+                p.lse[static_cast<size_t>(w.head) * p.lse_ld + w.q_row0 + row] = m_used + log2f(l_run);
+            act_t* orow = p.out + static_cast<size_t>(w.q_row0 + row) * p.out_ld + w.head * D;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t v[32];
+                tmem_ld32(tmem_O + lane_base + c * 32, v);
+                tmem_ld_wait();
+                if (row < w.q_valid) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 pk;
+                        __half2* ph2 = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            ph2[k] = __floats2half2_rn(__uint_as_float(v[j * 8 + 2 * k]) * inv_l, __uint_as_float(v[j * 8 + 2 * k + 1]) * inv_l);
+                        *reinterpret_cast<uint4*>(orow + c * 32 + j * 8) = pk;
+                    }
+                }
+            }
+            tc_fence_before();   // O / l reads are complete before this thread's next p_ready arrival
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, S::TMEM_COLS);
+    }
+}
+
 
 
 // ---- column-half variants for attention64h_kernel (two threads per query row): chunks c0, c0 + 1 of the four 32-column

@@ -357,13 +357,34 @@ int build_attn(const AttnProblem& pr, AttnParams* out) {
     return MMD_OK;
 }
 
-int launch_attn(const AttnParams& p, int d, cudaStream_t st) {
+#ifdef MMD_ATTN_TRACE
+static long long* attn_trace_buf() {
+    static long long* buf = nullptr;
+    if (!buf) { cudaMalloc(&buf, sizeof(long long) * 8 * 3 * 32 * 8); }
+    return buf;
+}
+// dump of the last traced launch: rows "cta role tile ev0..ev7" in clocks relative to the CTA's first stamp
+extern "C" int mmd_attn_trace_dump(long long* host_out) {
+    cudaDeviceSynchronize();
+    return cudaMemcpy(host_out, attn_trace_buf(), sizeof(long long) * 8 * 3 * 32 * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1;
+}
+#endif
+
+int launch_attn(const AttnParams& p_in, int d, cudaStream_t st) {
+    AttnParams p = p_in;
+#ifdef MMD_ATTN_TRACE
+    p.trace = attn_trace_buf();
+    cudaMemsetAsync(p.trace, 0, sizeof(long long) * 8 * 3 * 32 * 8, st);
+#else
+    p.trace = nullptr;
+#endif
     static bool done = false;
     if (!done) {
         MMD_CUDA_OK(cudaFuncSetAttribute(attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes<64>()));
         MMD_CUDA_OK(cudaFuncSetAttribute(attention64_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64Smem::TOTAL));
         MMD_CUDA_OK(cudaFuncSetAttribute(attention64_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64Smem::TOTAL));
         MMD_CUDA_OK(cudaFuncSetAttribute(attention64_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64Smem::TOTAL));
+        MMD_CUDA_OK(cudaFuncSetAttribute(attention64t_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64tSmem::TOTAL));
         MMD_CUDA_OK(cudaFuncSetAttribute(attention64h_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64hSmem::TOTAL));
         MMD_CUDA_OK(cudaFuncSetAttribute(attention64h_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64hSmem::TOTAL));
         MMD_CUDA_OK(cudaFuncSetAttribute(attention64h_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64hSmem::TOTAL));
@@ -391,6 +412,12 @@ int launch_attn(const AttnParams& p, int d, cudaStream_t st) {
         const int g1 = std::min(grid, 2 * num_sms());
         // MMD_ATTN_SPLIT=1: eight softmax warps per CTA (two threads per query row, f16x2 exponentials).  Measured equal to the
         // four-warp kernel (cross 1.60 vs 1.60-1.65 ms, self 1.12-1.15 vs 1.08-1.10 ms per step), so it is not the default.
+        // P in tensor memory (attention64t_kernel) unless MMD_ATTN_TMEM=0
+        static const bool ptmem = [] { const char* e = getenv("MMD_ATTN_TMEM"); return !(e && e[0] == '0'); }();
+        if (ptmem && poly == 0) {
+            MMD_CUDA_OK(launch_kernel(attention64t_kernel<0>, g1, ATT_THREADS, Attn64tSmem::TOTAL, st, p, grid));
+            return MMD_OK;
+        }
         static const bool split = [] { const char* e = getenv("MMD_ATTN_SPLIT"); return e && e[0] == '1'; }();
         if (split) {
             if (poly == 0) MMD_CUDA_OK(launch_kernel(attention64h_kernel<0>, g1, ATT64H_THREADS, Attn64hSmem::TOTAL, st, p, grid));
