@@ -1535,6 +1535,339 @@ __global__ void __launch_bounds__(ATT64H_THREADS, 2) attention64h_kernel(const _
 
 
 
+// ---- attention64th_kernel: attention64t_kernel (P in tensor memory) with EIGHT softmax warps, two threads per query
+// row (column halves, as attention64h_kernel): the softmax phase is the long part of a CTA's per-tile cycle.
+struct Attn64thSmem : Attn64tSmem {
+    static constexpr int XCH_OFF = Attn64tSmem::BAR_OFF + 256;   // exchange between the column halves (3 KB)
+    static constexpr int TOTAL = XCH_OFF + 3072 + 1024;
+};
+
+// this thread's 64 logit columns (chunks c0, c0 + 1) -> P columns 16 c0 .. +31 in tensor memory; psum = sum of the rounded values
+template <bool FULL>
+MMD_DEVINL float attn64_write_p_tmem_part(uint32_t s_addr, uint32_t p_addr, int kvalid, float scale_log2, float nm, int c0,
+                                          float& psum, uint64_t* wait_bar, uint32_t wait_parity) {
+    float amax = -INFINITY;
+    float s0 = 0.f, s1 = 0.f;
+    uint32_t v[32];
+    bool waited = (wait_bar == nullptr);
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+        const int c = c0 + cc;
+        if (!FULL && c * 32 >= kvalid) break;
+        tmem_ld32(s_addr + c * 32, v);
+        tmem_ld_wait();
+        uint32_t pw[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int col = c * 32 + 2 * k;
+            const float a0 = fmaf(__uint_as_float(v[2 * k]), scale_log2, nm);
+            const float a1 = fmaf(__uint_as_float(v[2 * k + 1]), scale_log2, nm);
+            float e0 = ex2_fast(a0);
+            float e1 = ex2_fast(a1);
+            if (!FULL) {
+                if (col >= kvalid) e0 = 0.f; else amax = fmaxf(amax, a0);
+                if (col + 1 >= kvalid) e1 = 0.f; else amax = fmaxf(amax, a1);
+            } else {
+                amax = fmaxf(amax, fmaxf(a0, a1));
+            }
+            const __half2 h = __floats2half2_rn(e0, e1);
+            const float2 hr = __half22float2(h);
+            s0 += hr.x;
+            s1 += hr.y;
+            pw[k] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        if (!waited) {
+            mbar_wait(wait_bar, wait_parity);
+            tc_fence_after();
+            waited = true;
+        }
+        tmem_st16(p_addr + c * 16, pw);
+    }
+    if (!waited) {   // (a half without valid columns still has to observe the barrier before the caller touches O)
+        mbar_wait(wait_bar, wait_parity);
+        tc_fence_after();
+    }
+    psum = s0 + s1;
+    return amax;
+}
+
+MMD_DEVINL void attn64_rescale_o_part(uint32_t tmem_O, uint32_t lane_base, float alpha, int hf) {
+    uint32_t o[32];
+    tmem_ld32(tmem_O + lane_base + hf * 32, o);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+    tmem_st32(tmem_O + lane_base + hf * 32, o);
+    tmem_st_wait();
+}
+
+template <int PQ>
+__global__ void __launch_bounds__(ATT64H_THREADS, 2) attention64th_kernel(const __grid_constant__ AttnParams p, int n_items) {
+    // Persistent: a CTA walks work items blockIdx.x, +gridDim.x, ... ; the TMA warp runs ahead into the next item
+    // (Q as soon as the last Q·K^T of the current item has been issued, K/V as stages free up), so the per-item
+    // start-up latency (Q/K fetch, barrier set-up, TMEM allocation) is paid once per CTA instead of once per item.
+    using S = Attn64thSmem;
+    constexpr int D = 64;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
+    uint64_t* q_full = bars;        // 1
+    uint64_t* q_empty = bars + 1;   // 1
+    uint64_t* k_full = bars + 2;    // 2
+    uint64_t* k_empty = bars + 4;   // 2
+    uint64_t* v_full = bars + 6;    // 2
+    uint64_t* v_empty = bars + 8;   // 2
+    uint64_t* s_full = bars + 10;   // 1
+    uint64_t* p_ready = bars + 11;  // 1 (256 arrivals)
+    uint64_t* o_full = bars + 12;   // 1
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    pdl_trigger();
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&p.q_map);
+        tma_prefetch_desc(&p.k_map);
+        tma_prefetch_desc(&p.v_map);
+        mbar_init(q_full, 1);
+        mbar_init(q_empty, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
+        mbar_init(s_full, 1);
+        mbar_init(p_ready, 256);
+        mbar_init(o_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 9) tmem_alloc(tmem_slot, S::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();   // q/k/v come from the previous kernel
+    const uint32_t tmem_S = tmem_base;
+    const uint32_t tmem_O = tmem_base + 128;
+    const uint32_t tmem_P = tmem_base + 192;   // P (fp16, two per column): 64 columns
+
+    if (warp == 8) {
+        // ===================== TMA producer =====================
+        // whole warp in uniform control flow (all lanes wait), one elected lane issues: a lane-guarded branch makes
+        // ptxas wrap every TMA / tcgen05 instruction in an ELECT + BRA.U.ANY loop over the active lanes (gemm.cuh)
+        {
+            int g = 0;   // KV tiles issued so far (all items)
+            int it = 0;  // items started
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                const AttnWork w = attn_decode(p, item);
+                mbar_wait(q_empty, (it & 1) ^ 1);   // last Q·K^T of the previous item has been issued and retired
+                if (elect_one()) {
+                    mbar_expect_tx(q_full, 16384);
+                    tma_load_2d(smem + S::Q_OFF, &p.q_map, q_full, p.q_col0 + w.head * D, w.q_row0);
+                }
+                __syncwarp();
+                for (int t = 0; t < w.n_tiles; ++t, ++g) {
+                    const int st = g & 1;
+                    int krow, kvalid;
+                    attn_tile(w, t, krow, kvalid);
+                    mbar_wait(&k_empty[st], ((g >> 1) & 1) ^ 1);
+                    ATT_TRACE(p, 2, g, 0);   // K stage free
+                    if (elect_one()) {
+                        mbar_expect_tx(&k_full[st], 16384);
+                        tma_load_2d(smem + S::K_OFF + st * 16384, &p.k_map, &k_full[st], p.k_col0 + w.head * D, krow);
+                    }
+                    __syncwarp();
+                    mbar_wait(&v_empty[st], ((g >> 1) & 1) ^ 1);
+                    ATT_TRACE(p, 2, g, 1);   // V stage free
+                    if (elect_one()) {
+                        mbar_expect_tx(&v_full[st], 16384);
+                        tma_load_2d(smem + S::V_OFF + st * 16384, &p.v_map, &v_full[st], p.v_col0 + w.head * D, krow);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // ===================== MMA issuer (uniform warp, elected lane) =====================
+        {
+            constexpr uint32_t idesc_qk = umma_idesc_f16(ATT_BQ, ATT_BKV, 0, 0);
+            constexpr uint32_t idesc_pv = umma_idesc_f16(ATT_BQ, D, 0, 1);   // V is MN-major
+            const uint64_t qd0 = umma_desc_sw128(smem_u32(smem + S::Q_OFF), 16, 1024);
+            const uint64_t kd0 = umma_desc_sw128(smem_u32(smem + S::K_OFF), 16, 1024);
+            const uint64_t vd0 = umma_desc_sw128(smem_u32(smem + S::V_OFF), ATT_BKV * 128, 1024);   // MN-major V
+            int gq = 0;   // Q·K^T tiles issued
+            int itq = 0;  // items whose first Q·K^T has been issued
+            // issues Q·K^T of tile t of the item `w` (first tile waits for that item's Q; last tile releases Q)
+            auto issue_qk = [&](const AttnWork& w, int t) {
+                if (t == 0) {
+                    mbar_wait(q_full, itq & 1);
+                    ++itq;
+                }
+                const int st = gq & 1;
+                mbar_wait(&k_full[st], (gq >> 1) & 1);
+                ATT_TRACE(p, 1, gq, 0);   // K tile landed (Q.K^T of tile gq can issue)
+                tc_fence_after();
+                const uint64_t kd = kd0 + static_cast<uint64_t>(st) * (16384 >> 4);
+                if (elect_one()) {
+#pragma unroll
+                    for (int ks = 0; ks < D / 16; ++ks)
+                        umma_f16_ss(tmem_S, qd0 + 2 * ks, kd + 2 * ks, idesc_qk, ks != 0 ? 1u : 0u);
+                    umma_commit(&k_empty[st]);
+                    if (t == w.n_tiles - 1) umma_commit(q_empty);
+                    umma_commit(s_full);
+                }
+                __syncwarp();
+                ++gq;
+            };
+            int g = 0;
+            bool first = true;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const AttnWork w = attn_decode(p, item);
+                if (first) { issue_qk(w, 0); first = false; }
+                for (int t = 0; t < w.n_tiles; ++t, ++g) {
+                    int krow, kvalid;
+                    attn_tile(w, t, krow, kvalid);
+                    mbar_wait(p_ready, g & 1);
+                    ATT_TRACE(p, 1, g, 1);   // softmax of tile g done
+                    // The logits of the NEXT tile go first: S is free as soon as the softmax of this tile has read it, and the
+                    // softmax warps can start on them while P.V / P.1 of this tile are still being issued and executed
+                    // (measured: issuing the 16 small-N MMAs of P.V / P.1 alone takes ~840 cycles)
+                    // (Within an item only: the first logits of the NEXT item wait for its Q tile, which must not hold up
+                    // the last P.V of this one — measured 7400 -> 9600 cycles per item boundary when it did.)
+                    if (t + 1 < w.n_tiles) issue_qk(w, t + 1);
+                    const int vst = g & 1;
+                    mbar_wait(&v_full[vst], (g >> 1) & 1);
+                    ATT_TRACE(p, 1, g, 2);   // V tile landed
+                    tc_fence_after();
+                    const int nks = (kvalid + 15) >> 4;
+                    if (elect_one()) {
+                        // P is the A operand straight from tensor memory: 8 columns (16 keys) per K step
+                        const uint64_t vd = vd0 + static_cast<uint64_t>(vst) * (16384 >> 4);
+                        if (nks == ATT_BKV / 16) {
+#pragma unroll
+                            for (int ks = 0; ks < ATT_BKV / 16; ++ks)
+                                umma_f16_ts(tmem_O, tmem_P + ks * 8, vd + ks * (2048 >> 4), idesc_pv, (t | ks) != 0 ? 1u : 0u);
+                        } else {
+                            for (int ks = 0; ks < nks; ++ks)
+                                umma_f16_ts(tmem_O, tmem_P + ks * 8, vd + ks * (2048 >> 4), idesc_pv, (t | ks) != 0 ? 1u : 0u);
+                        }
+                        umma_commit(&v_empty[vst]);
+                        umma_commit(o_full);
+                    }
+                    __syncwarp();
+                    ATT_TRACE(p, 1, g, 3);   // P.V of tile g issued
+                    if (t + 1 == w.n_tiles && item + static_cast<int>(gridDim.x) < n_items) {
+                        const AttnWork wn = attn_decode(p, item + gridDim.x);
+                        issue_qk(wn, 0);
+                    }
+                }
+            }
+        }
+    } else {
+        // ===================== softmax warps (two threads per query row: column halves) =====================
+        // warp w: rows 32 (w & 3) .. +31 (its TMEM lane quarter), logit columns 64 (w >> 2) .. +63 -> P columns 32 (w >> 2) .. +31
+        const int q4 = warp & 3, hf = warp >> 2;
+        const int row = q4 * 32 + lane;
+        const uint32_t lane_base = static_cast<uint32_t>(q4 * 32) << 16;
+        const uint32_t s_addr = tmem_S + lane_base;
+        float* xch = reinterpret_cast<float*>(smem + S::XCH_OFF);   // [tile parity][half][128 rows] + row sums [half][128]
+        int g = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const AttnWork w = attn_decode(p, item);
+            const int T = w.n_tiles;
+            float m_used = 0.f;
+            float l_run = 0.f;   // this thread's share of the row sum (its 64 columns of every tile)
+            const bool warp_active = q4 * 32 < w.q_valid;
+            for (int t = 0; t < T; ++t, ++g) {
+                int krow, kvalid;
+                attn_tile(w, t, krow, kvalid);
+                mbar_wait(s_full, g & 1);
+                if (warp == 0) ATT_TRACE(p, 0, g, 0);   // logits of tile g ready
+                tc_fence_after();
+                if (!warp_active) {
+                    if (t > 0) {
+                        mbar_wait(o_full, (g - 1) & 1);
+                        tc_fence_after();
+                    }
+                    tc_fence_before();
+                    mbar_arrive(p_ready);
+                    continue;
+                }
+                const bool full_tile = (kvalid == ATT_BKV);
+                float* mine = xch + ((g & 1) * 2 + hf) * 128 + row;
+                const float* other = xch + ((g & 1) * 2 + (hf ^ 1)) * 128 + row;
+                if (t == 0) {
+                    const float mx = full_tile ? attn64_rowmax_part<true>(s_addr, kvalid, 2 * hf) : attn64_rowmax_part<false>(s_addr, kvalid, 2 * hf);
+                    *mine = mx;
+                    named_bar_sync(1 + q4, 64);
+                    m_used = fmaxf(mx, *other) * p.scale_log2;
+                }
+                float tile_sum = 0.f;
+#pragma unroll 1
+                for (int attempt = 0; attempt < 2; ++attempt) {
+                    uint64_t* wb = (t > 0 && attempt == 0) ? o_full : nullptr;
+                    const uint32_t wp = static_cast<uint32_t>((g - 1) & 1);
+                    const float amax = full_tile ? attn64_write_p_tmem_part<true>(s_addr, tmem_P + lane_base, kvalid, p.scale_log2, -m_used, 2 * hf, tile_sum, wb, wp)
+                                                 : attn64_write_p_tmem_part<false>(s_addr, tmem_P + lane_base, kvalid, p.scale_log2, -m_used, 2 * hf, tile_sum, wb, wp);
+                    if (warp == 0 && attempt == 0) ATT_TRACE(p, 0, g, 1);
+                    if (t == 0 || attempt == 1) break;
+                    *mine = amax;
+                    named_bar_sync(1 + q4, 64);
+                    const float arow = fmaxf(amax, *other);
+                    if (!__any_sync(0xffffffffu, arow > ATT_STREAM_LIMIT)) break;
+                    const float m_new = m_used + fmaxf(arow, 0.f);
+                    const float alpha = ex2_fast(m_used - m_new);
+                    attn64_rescale_o_part(tmem_O, lane_base, alpha, hf);
+                    l_run *= alpha;
+                    m_used = m_new;
+                }
+                l_run += tile_sum;
+                tmem_st_wait();
+                tc_fence_before();
+                if (warp == 0) ATT_TRACE(p, 0, g, 2);   // probabilities of tile g written
+                mbar_arrive(p_ready);
+            }
+            // ---- item epilogue: O / l -> global
+            mbar_wait(o_full, (g - 1) & 1);
+            tc_fence_after();
+            xch[512 + hf * 128 + row] = l_run;
+            named_bar_sync(1 + q4, 64);
+            const float l_tot = l_run + xch[512 + (hf ^ 1) * 128 + row];
+            const float inv_l = 1.f / l_tot;
+            if (hf == 0 && p.lse != nullptr && row < w.q_valid)
+                p.lse[static_cast<size_t>(w.head) * p.lse_ld + w.q_row0 + row] = m_used + log2f(l_tot);
+            act_t* orow = p.out + static_cast<size_t>(w.q_row0 + row) * p.out_ld + w.head * D;
+            {
+                const int c = hf;   // this half's 32 output columns
+                uint32_t v[32];
+                tmem_ld32(tmem_O + lane_base + c * 32, v);
+                tmem_ld_wait();
+                if (row < w.q_valid) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 pk;
+                        __half2* ph2 = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            ph2[k] = __floats2half2_rn(__uint_as_float(v[j * 8 + 2 * k]) * inv_l, __uint_as_float(v[j * 8 + 2 * k + 1]) * inv_l);
+                        *reinterpret_cast<uint4*>(orow + c * 32 + j * 8) = pk;
+                    }
+                }
+            }
+            tc_fence_before();   // O reads are complete before this thread's next p_ready arrival
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, S::TMEM_COLS);
+    }
+}
+
+
+
+
+
 // ===========================================================================
 // attention64x2_kernel — head_dim 64 with TWO 128-row query tiles per CTA sharing every K/V tile.
 // One CTA per SM (512 TMEM columns, ~165 KB shared memory): two softmax groups of four warps each own one query tile

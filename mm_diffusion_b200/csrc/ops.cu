@@ -385,6 +385,7 @@ int launch_attn(const AttnParams& p_in, int d, cudaStream_t st) {
         MMD_CUDA_OK(cudaFuncSetAttribute(attention64_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64Smem::TOTAL));
         MMD_CUDA_OK(cudaFuncSetAttribute(attention64_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64Smem::TOTAL));
         MMD_CUDA_OK(cudaFuncSetAttribute(attention64t_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64tSmem::TOTAL));
+        MMD_CUDA_OK(cudaFuncSetAttribute(attention64th_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64thSmem::TOTAL));
         MMD_CUDA_OK(cudaFuncSetAttribute(attention64h_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64hSmem::TOTAL));
         MMD_CUDA_OK(cudaFuncSetAttribute(attention64h_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64hSmem::TOTAL));
         MMD_CUDA_OK(cudaFuncSetAttribute(attention64h_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64hSmem::TOTAL));
@@ -412,10 +413,14 @@ int launch_attn(const AttnParams& p_in, int d, cudaStream_t st) {
         const int g1 = std::min(grid, 2 * num_sms());
         // MMD_ATTN_SPLIT=1: eight softmax warps per CTA (two threads per query row, f16x2 exponentials).  Measured equal to the
         // four-warp kernel (cross 1.60 vs 1.60-1.65 ms, self 1.12-1.15 vs 1.08-1.10 ms per step), so it is not the default.
-        // P in tensor memory (attention64t_kernel) unless MMD_ATTN_TMEM=0
+        // P in tensor memory unless MMD_ATTN_TMEM=0: attention64th_kernel (eight softmax warps, two threads per query row;
+        // default) or attention64t_kernel (MMD_ATTN_TMEM=1, four softmax warps: 1.48 / 1.07 ms vs 1.38-1.41 / 1.01-1.04 ms
+        // per step for the cross / self attention launches)
         static const bool ptmem = [] { const char* e = getenv("MMD_ATTN_TMEM"); return !(e && e[0] == '0'); }();
         if (ptmem && poly == 0) {
-            MMD_CUDA_OK(launch_kernel(attention64t_kernel<0>, g1, ATT_THREADS, Attn64tSmem::TOTAL, st, p, grid));
+            static const bool ptmem8 = [] { const char* e = getenv("MMD_ATTN_TMEM"); return !(e && e[0] == '1'); }();
+            if (ptmem8) MMD_CUDA_OK(launch_kernel(attention64th_kernel<0>, g1, ATT64H_THREADS, Attn64thSmem::TOTAL, st, p, grid));
+            else MMD_CUDA_OK(launch_kernel(attention64t_kernel<0>, g1, ATT_THREADS, Attn64tSmem::TOTAL, st, p, grid));
             return MMD_OK;
         }
         static const bool split = [] { const char* e = getenv("MMD_ATTN_SPLIT"); return e && e[0] == '1'; }();

@@ -34,6 +34,7 @@ def sass_by_function():
     ("attention64x2_kernel", ("UTCHMMA", "UTMALDG", "LDTM", "STTM", "USETMAXREG")),   # two query tiles per CTA, register re-split
     ("attention64h_kernel", ("UTCHMMA", "UTMALDG", "LDTM", "STTM", "MUFU.EX2.F16")),   # eight softmax warps, f16x2 exponentials
     ("attention64t_kernel", ("UTCHMMA tmem", "UTMALDG", "LDTM", "STTM")),   # P.V with the A operand (P) in tensor memory
+    ("attention64th_kernel", ("UTCHMMA tmem", "UTMALDG", "LDTM", "STTM")),  # the same with eight softmax warps (production)
     ("attention_kernel", ("UTCHMMA", "UTMALDG", "LDTM")),
     ("attn_bwd_kernel", ("UTCHMMA", "UTMALDG", "LDTM")),               # flash attention backward
 ])
@@ -62,7 +63,7 @@ def test_fused_groupnorm_gemm_variant_exists(sass_by_function):
     assert all("MUFU.TANH" not in b for b in plain.values())
 
 
-@pytest.mark.parametrize("kernel", ["conv_gemm_kernel", "attention64_kernel", "attention64t_kernel", "attention64h_kernel", "attention64x2_kernel", "attention_kernel",
+@pytest.mark.parametrize("kernel", ["conv_gemm_kernel", "attention64_kernel", "attention64t_kernel", "attention64th_kernel", "attention64h_kernel", "attention64x2_kernel", "attention_kernel",
                                     "conv_wgrad_kernel", "attn_bwd_kernel"])
 def test_single_lane_issue_has_no_waterfall_loops(sass_by_function, kernel):
     """TMA / tcgen05 instructions are issued by an elect.sync lane of a warp in uniform control flow.  Issued from an

@@ -11,6 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.parametrize("env,select", [
+    ({"MMD_ATTN_TMEM": "1"}, "attention or forward_small"),             # P in tensor memory, four softmax warps (attention64t_kernel)
     ({"MMD_ATTN_TMEM": "0"}, "attention or forward_small"),             # probabilities through shared memory (attention64_kernel)
     ({"MMD_ATTN_TMEM": "0", "MMD_ATTN_SPLIT": "1"}, "attention or forward_small"),   # eight softmax warps, f16x2 exponentials
     ({"MMD_ATTN_TMEM": "0", "MMD_ATTN_PAIR": "1"}, "attention or forward_small"),    # two query tiles per CTA
