@@ -489,26 +489,41 @@ __global__ void __launch_bounds__(256) head_gather3d_kernel(const act_t* __restr
 __global__ void im2col_video_kernel(const float* __restrict__ x, act_t* __restrict__ a, int BF, int Cin, int H, int W) {
     pdl_trigger();
     pdl_wait();
-    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const long long total = static_cast<long long>(BF) * H * W * 8;  // 8 vectors of 8 per token
+    // k -> (dy, dx, c) table once per block (the per-element divisions by run-time values cost more than the loads);
+    // 32-bit indices (the launcher's tensors are far below 2^31 elements)
+    __shared__ int tab[64];   // (dy + 1) | (dx + 1) << 2 | c << 4, or -1 past the 9 * Cin real columns
+    if (threadIdx.x < 64) {
+        const int k = threadIdx.x;
+        int e = -1;
+        if (k < 9 * Cin) {
+            const int tap = k / Cin, c = k - tap * Cin;
+            e = (tap / 3) | ((tap % 3) << 2) | (c << 4);
+        }
+        tab[k] = e;
+    }
+    __syncthreads();
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t total = static_cast<uint32_t>(BF) * H * W * 8;  // 8 vectors of 8 per token
     if (idx >= total) return;
     const int v = static_cast<int>(idx & 7);
-    long long t = idx >> 3;
+    uint32_t t = idx >> 3;
     const int w = static_cast<int>(t % W); t /= W;
     const int h = static_cast<int>(t % H);
-    const long long n = t / H;
-    uint4 o;
-    __half* oh = reinterpret_cast<__half*>(&o);
+    const uint32_t n = t / H;
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (v * 8 < 9 * Cin) {   // vectors past the real columns are all padding
+        __half* oh = reinterpret_cast<__half*>(&o);
+        const float* xn = x + static_cast<size_t>(n) * Cin * H * W;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int k = v * 8 + i;
-        float val = 0.f;
-        if (k < 9 * Cin) {
-            const int tap = k / Cin, c = k % Cin;
-            const int yy = h + tap / 3 - 1, xx = w + tap % 3 - 1;
-            if (yy >= 0 && yy < H && xx >= 0 && xx < W) val = x[((n * Cin + c) * H + yy) * W + xx];
+        for (int i = 0; i < 8; ++i) {
+            const int e = tab[v * 8 + i];
+            float val = 0.f;
+            if (e >= 0) {
+                const int yy = h + (e & 3) - 1, xx = w + ((e >> 2) & 3) - 1, c = e >> 4;
+                if (yy >= 0 && yy < H && xx >= 0 && xx < W) val = __ldg(xn + (static_cast<size_t>(c) * H + yy) * W + xx);
+            }
+            oh[i] = __float2half_rn(val);
         }
-        oh[i] = __float2half_rn(val);
     }
     reinterpret_cast<uint4*>(a)[idx] = o;
 }
