@@ -1957,11 +1957,9 @@ struct Attn64x2Smem {
     static constexpr int Q_OFF = 0;                       // two query tiles
     static constexpr int K_OFF = 2 * 16384;               // 2 stages
     static constexpr int V_OFF = K_OFF + 2 * 16384;       // 2 stages
-    static constexpr int P_OFF = V_OFF + 2 * 16384;       // 2 x (128 x 128 fp16)
-    static constexpr int ONES_OFF = P_OFF + 2 * 32768;
-    static constexpr int BAR_OFF = ONES_OFF + 4096;
+    static constexpr int BAR_OFF = V_OFF + 2 * 16384;     // (P lives in tensor memory, the row sums in registers)
     static constexpr int TOTAL = BAR_OFF + 256 + 1024;
-    static constexpr int TMEM_COLS = 512;                 // S0 0 | S1 128 | O0 256 | O1 320 | l0 384 | l1 400
+    static constexpr int TMEM_COLS = 512;                 // S0 0 | S1 128 | O0 256 | O1 320 | P0 384 | P1 448
 };
 constexpr int ATT2_THREADS = 384;   // warps 0-3: softmax of tile 0, 4-7: softmax of tile 1, 8: TMA, 9: MMA, 10-11: idle
 // Three warpgroups so the register file can be re-split (setmaxnreg): the softmax threads hold a whole 128-column logit
@@ -2022,9 +2020,6 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention64x2_kernel(const __
         }
         fence_mbar_init();
     }
-    for (int i = threadIdx.x; i < 4096 / 16; i += ATT2_THREADS)
-        reinterpret_cast<uint4*>(smem + S::ONES_OFF)[i] = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
-    fence_proxy_async_smem();
     if (warp == 9) tmem_alloc(tmem_slot, S::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
@@ -2076,9 +2071,8 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention64x2_kernel(const __
             constexpr uint32_t idesc_qk = umma_idesc_f16(ATT_BQ, ATT_BKV, 0, 0);
             const uint64_t qd0 = umma_desc_sw128(smem_u32(smem + S::Q_OFF), 16, 1024);
             const uint64_t kd0 = umma_desc_sw128(smem_u32(smem + S::K_OFF), 16, 1024);
-            const uint64_t pd0 = umma_desc_sw128(smem_u32(smem + S::P_OFF), 16, 1024);
             const uint64_t vd0 = umma_desc_sw128(smem_u32(smem + S::V_OFF), ATT_BKV * 128, 1024);   // MN-major V
-            const uint64_t od0 = umma_desc_sw128(smem_u32(smem + S::ONES_OFF), 16, 1024);
+            constexpr uint32_t idesc_pv = umma_idesc_f16(ATT_BQ, D, 0, 1);   // V is MN-major
             int itq = 0;            // items whose Q has been waited for
             int gs[2] = {0, 0};     // tiles processed per group (phases of p_ready / o_full; s_full runs one ahead)
             // Q·K^T of K tile `kidx` (global tile counter) of an item for group grp; `last_of_tile`: no further Q·K^T
@@ -2127,22 +2121,23 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention64x2_kernel(const __
                     const uint64_t vd = vd0 + static_cast<uint64_t>(vst) * (16384 >> 4);
                     for (int grp = 0; grp < (two ? 2 : 1); ++grp) {
                         mbar_wait(&p_ready[grp], gs[grp] & 1);
+                        // next logits of this group first (S is free once its softmax has read it), then P.V — inside an
+                        // item only: the next item's first logits wait for its Q tiles and go after the last P.V
+                        if (t + 1 < T) issue_qk(grp, n + 1, false, grp == (two ? 1 : 0), t + 2 == T);
                         mbar_wait(&v_full[vst], vph);
                         tc_fence_after();
                         if (elect_one()) {
-                            attn64_issue_pv(tmem_base + 256 + grp * 64, tmem_base + 384 + grp * 16,
-                                            pd0 + static_cast<uint64_t>(grp) * (32768 >> 4), vd, od0, kvalid, t);
+                            const uint32_t tO = tmem_base + 256 + grp * 64, tP = tmem_base + 384 + grp * 64;
+                            const int nks = (kvalid + 15) >> 4;
+                            for (int ks = 0; ks < nks; ++ks)
+                                umma_f16_ts(tO, tP + ks * 8, vd + static_cast<uint64_t>(ks) * (2048 >> 4), idesc_pv, (t | ks) != 0 ? 1u : 0u);
                             umma_commit(&v_empty[vst]);
                             umma_commit(&o_full[grp]);
                         }
                         __syncwarp();
                         ++gs[grp];
-                        // next logits of this group: same item, or the first tile of the next item
-                        if (t + 1 < T) {
-                            issue_qk(grp, n + 1, false, grp == (two ? 1 : 0), t + 2 == T);
-                        } else if (has_next && (grp == 0 || next_two)) {
+                        if (t + 1 == T && has_next && (grp == 0 || next_two))
                             issue_qk(grp, n + 1, grp == 0, grp == (next_two ? 1 : 0), nxt.w.n_tiles == 1);
-                        }
                     }
                     if (!two) {
                         if (elect_one()) umma_commit(&v_empty[vst]);   // the idle group's arrival
@@ -2164,9 +2159,8 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention64x2_kernel(const __
         const uint32_t lane_base = static_cast<uint32_t>(wg * 32) << 16;
         const uint32_t tmem_S = tmem_base + grp * 128;
         const uint32_t tmem_O = tmem_base + 256 + grp * 64;
-        const uint32_t tmem_L = tmem_base + 384 + grp * 16;
+        const uint32_t tmem_P = tmem_base + 384 + grp * 64;
         const uint32_t s_addr = tmem_S + lane_base;
-        uint8_t* p_smem = smem + S::P_OFF + grp * 32768;
         uint64_t* sf = &s_full[grp];
         uint64_t* pr = &p_ready[grp];
         uint64_t* of = &o_full[grp];
@@ -2179,6 +2173,7 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention64x2_kernel(const __
             const int q_row0 = w.q_row0 + grp * ATT_BQ;
             const int T = w.n_tiles;
             float m_used = 0.f;
+            float l_run = 0.f;   // row sum of the probabilities (registers)
             const bool warp_active = wg * 32 < q_valid;
             for (int t = 0; t < T; ++t, ++g) {
                 int krow, kvalid;
@@ -2200,20 +2195,25 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention64x2_kernel(const __
                 if (t == 0) {
                     const float mx = full_tile ? attn64_rowmax<true>(s_addr, kvalid) : attn64_rowmax<false>(s_addr, kvalid);
                     m_used = mx * p.scale_log2;
-                } else {
-                    mbar_wait(of, (g - 1) & 1);   // P·V of the previous tile is done: P and O may be touched
-                    tc_fence_after();
                 }
+                // (t >= 1: P·V of the previous tile must have retired before P / O are touched; waited for inside the first
+                // pass, right before its first tensor-memory store)
+                float tile_sum = 0.f;
 #pragma unroll 1
                 for (int attempt = 0; attempt < 2; ++attempt) {
-                    const float amax = full_tile ? attn64_write_p<true, PQ>(s_addr, kvalid, p.scale_log2, -m_used, p_smem, row)
-                                                 : attn64_write_p<false, PQ>(s_addr, kvalid, p.scale_log2, -m_used, p_smem, row);
+                    uint64_t* wb = (t > 0 && attempt == 0) ? of : nullptr;
+                    const uint32_t wp = static_cast<uint32_t>((g - 1) & 1);
+                    const float amax = full_tile ? attn64_write_p_tmem<true>(s_addr, tmem_P + lane_base, kvalid, p.scale_log2, -m_used, tile_sum, wb, wp)
+                                                 : attn64_write_p_tmem<false>(s_addr, tmem_P + lane_base, kvalid, p.scale_log2, -m_used, tile_sum, wb, wp);
                     if (t == 0 || attempt == 1 || !__any_sync(0xffffffffu, amax > ATT_STREAM_LIMIT)) break;
                     const float m_new = m_used + fmaxf(amax, 0.f);
-                    attn64_rescale(tmem_O, tmem_L, lane_base, ex2_fast(m_used - m_new));
+                    const float alpha = ex2_fast(m_used - m_new);
+                    attn64_rescale_o(tmem_O, lane_base, alpha);
+                    l_run *= alpha;
                     m_used = m_new;
                 }
-                fence_proxy_async_smem();
+                l_run += tile_sum;
+                tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(pr);
             }
@@ -2221,12 +2221,9 @@ __global__ void __launch_bounds__(ATT2_THREADS, 1) attention64x2_kernel(const __
             mbar_wait(of, (g - 1) & 1);
             tc_fence_after();
             if (warp_active) {
-                uint32_t lv[16];
-                tmem_ld16(tmem_L + lane_base, lv);
-                tmem_ld_wait();
-                const float inv_l = 1.f / __uint_as_float(lv[0]);
+                const float inv_l = 1.f / l_run;
                 if (p.lse != nullptr && row < q_valid)
-                    p.lse[static_cast<size_t>(w.head) * p.lse_ld + q_row0 + row] = m_used + log2f(__uint_as_float(lv[0]));
+                    p.lse[static_cast<size_t>(w.head) * p.lse_ld + q_row0 + row] = m_used + log2f(l_run);
                 act_t* orow = p.out + static_cast<size_t>(q_row0 + row) * p.out_ld + w.head * D;
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
