@@ -399,7 +399,10 @@ int launch_attn(const AttnParams& p_in, int d, cudaStream_t st) {
     const int grid = p.B * p.n_blocks * p.heads * p.q_tiles;
     static const bool generic64 = [] { const char* e = getenv("MMD_ATTN_GENERIC"); return e && e[0] == '1'; }();
     // two query tiles per CTA (shared K/V, ping-pong softmax groups) once a query block has at least two tiles
-    static const bool pair64 = [] { const char* e = getenv("MMD_ATTN_PAIR"); return e ? e[0] == '1' : false; }();
+    // two query tiles per CTA (attention64x2_kernel, P in tensor memory): MMD_ATTN_PAIR=1 everywhere, 0 never; default: the
+    // long self-attention launches only (measured 1.06 -> 1.01 ms per step there, equal on the cross-modal sites)
+    static const int pair_mode = [] { const char* e = getenv("MMD_ATTN_PAIR"); return e ? atoi(e) : -1; }();
+    const bool pair64 = pair_mode == 1 || (pair_mode < 0 && p.q_blk == p.k_blk && p.win == 1 && p.q_tiles >= 4);
     // MMD_ATTN_POLY = 0 / 1 / 2 of every 4 exponentials on the FMA pipe (cubic Cody-Waite) instead of the MUFU unit
     static const int poly = [] { const char* e = getenv("MMD_ATTN_POLY"); const int v = e ? atoi(e) : 0; return v < 0 ? 0 : (v > 2 ? 2 : v); }();
     if (d == 64 && !generic64 && pair64 && p.q_tiles >= 2) {

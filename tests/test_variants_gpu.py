@@ -14,7 +14,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     ({"MMD_ATTN_TMEM": "1"}, "attention or forward_small"),             # P in tensor memory, four softmax warps (attention64t_kernel)
     ({"MMD_ATTN_TMEM": "0"}, "attention or forward_small"),             # probabilities through shared memory (attention64_kernel)
     ({"MMD_ATTN_TMEM": "0", "MMD_ATTN_SPLIT": "1"}, "attention or forward_small"),   # eight softmax warps, f16x2 exponentials
-    ({"MMD_ATTN_TMEM": "0", "MMD_ATTN_PAIR": "1"}, "attention or forward_small"),    # two query tiles per CTA
+    ({"MMD_ATTN_PAIR": "1"}, "attention or forward_small"),             # two query tiles per CTA at every d = 64 site
+    ({"MMD_ATTN_PAIR": "0"}, "attention or forward_small or production"),  # ... at none
     ({"MMD_XF": "7"}, "forward_small or forward_production"),           # GroupNorm apply on the GEMM A operand
     ({"MMD_EG": "0", "MMD_MT": "0"}, "conv or forward_small"),          # one epilogue warpgroup, 128-token tiles only
     ({"MMD_NO_GRAPH": "1", "MMD_NO_PDL": "1"}, "forward_small"),        # eager launches without programmatic dependent launch
