@@ -61,6 +61,7 @@ class ClockSampler:
         self.gpu = gpu_index
         self.proc = None
         self.lines = []
+        self.begin = 0
 
     def start(self):
         try:
@@ -76,9 +77,18 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark(self):
+        """Start of the timed region: nvidia-smi is started earlier (its first sample takes a few hundred ms, longer than a
+        short timed region), only the samples from here on count."""
+        self.begin = len(self.lines)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        if len(self.lines) <= self.begin:   # nothing inside the region yet: take the next sample (flagged below)
+            t_end = time.time() + 1.0
+            while not self.lines and time.time() < t_end:
+                time.sleep(0.02)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -86,7 +96,11 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, power, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        window = self.lines[self.begin:]
+        outside = False
+        if not window and self.lines:   # region shorter than one sampling period: the sample taken right before it
+            window, outside = self.lines[-1:], True
+        for ln in window:
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 9:
                 continue
@@ -99,8 +113,11 @@ class ClockSampler:
                     reasons.add(name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "power_w_max": max(power),
-                "samples": len(sm), "reasons": sorted(reasons)}
+        out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "power_w_max": max(power),
+               "samples": len(sm), "reasons": sorted(reasons)}
+        if outside:
+            out["note"] = "no nvidia-smi sample fell inside the timed region (100 ms period): nearest sample outside it"
+        return out
 
 
 def production_flags():
@@ -287,11 +304,13 @@ def timed(ctx, step, warm, k, clock_sampler=None):
     """`warm` untimed + EXACTLY `k` timed calls of step(i), bracketed by barrier + synchronize, CUDA events on the
     current stream; returns the device milliseconds of the timed region (this rank)."""
     import torch
+    if clock_sampler is not None:
+        clock_sampler.start()
     for i in range(warm):
         step(i)
     ctx.barrier()
     if clock_sampler is not None:
-        clock_sampler.start()
+        clock_sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(k):
@@ -336,13 +355,14 @@ def run_b200(ctx, args, model, diffusion):
     # ---------------- device-resident loop (the headline `value`)
     x = {"video": xv_h.to(device), "audio": xa_h.to(device)}
     with torch.no_grad():
+        clocks = ClockSampler(local_rank)
+        if rank == 0:
+            clocks.start()   # nvidia-smi needs a few hundred ms to its first sample: started before the warm-up
         for i in range(W):
             x = diffusion.p_sample(model, x, ts[i])["sample"]
         sample_epilogue(x)   # warm the end-of-loop path too (first NCCL call builds the communicator)
         barrier()
-        clocks = ClockSampler(local_rank)
-        if rank == 0:
-            clocks.start()
+        clocks.mark()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(K):
@@ -811,7 +831,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=None, help="samples per GPU (sample / cond: 4, dpm: 16, train: 8)")
