@@ -1543,7 +1543,9 @@ struct Attn64thSmem : Attn64tSmem {
 };
 
 // this thread's 64 logit columns (chunks c0, c0 + 1) -> P columns 16 c0 .. +31 in tensor memory; psum = sum of the rounded values
-template <bool FULL>
+// H2: the two exponentials of a packed pair through ONE exp-unit operation (ex2.approx.f16x2 on the half2-packed arguments;
+// its result is the packed P word) instead of two fp32 ones.
+template <bool FULL, bool H2 = false>
 MMD_DEVINL float attn64_write_p_tmem_part(uint32_t s_addr, uint32_t p_addr, int kvalid, float scale_log2, float nm, int c0,
                                           float& psum, uint64_t* wait_bar, uint32_t wait_parity) {
     float amax = -INFINITY;
@@ -1560,21 +1562,33 @@ MMD_DEVINL float attn64_write_p_tmem_part(uint32_t s_addr, uint32_t p_addr, int 
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
             const int col = c * 32 + 2 * k;
-            const float a0 = fmaf(__uint_as_float(v[2 * k]), scale_log2, nm);
-            const float a1 = fmaf(__uint_as_float(v[2 * k + 1]), scale_log2, nm);
-            float e0 = ex2_fast(a0);
-            float e1 = ex2_fast(a1);
-            if (!FULL) {
-                if (col >= kvalid) e0 = 0.f; else amax = fmaxf(amax, a0);
-                if (col + 1 >= kvalid) e1 = 0.f; else amax = fmaxf(amax, a1);
-            } else {
+            float a0 = fmaf(__uint_as_float(v[2 * k]), scale_log2, nm);
+            float a1 = fmaf(__uint_as_float(v[2 * k + 1]), scale_log2, nm);
+            if (H2) {
+                if (!FULL) {   // masked keys: exponent -inf -> probability 0, kept out of the maximum
+                    if (col >= kvalid) a0 = -INFINITY;
+                    if (col + 1 >= kvalid) a1 = -INFINITY;
+                }
                 amax = fmaxf(amax, fmaxf(a0, a1));
+                pw[k] = ex2_h2(a0, a1);
+                const float2 hr = __half22float2(*reinterpret_cast<const __half2*>(&pw[k]));
+                s0 += hr.x;
+                s1 += hr.y;
+            } else {
+                float e0 = ex2_fast(a0);
+                float e1 = ex2_fast(a1);
+                if (!FULL) {
+                    if (col >= kvalid) e0 = 0.f; else amax = fmaxf(amax, a0);
+                    if (col + 1 >= kvalid) e1 = 0.f; else amax = fmaxf(amax, a1);
+                } else {
+                    amax = fmaxf(amax, fmaxf(a0, a1));
+                }
+                const __half2 h = __floats2half2_rn(e0, e1);
+                const float2 hr = __half22float2(h);
+                s0 += hr.x;
+                s1 += hr.y;
+                pw[k] = *reinterpret_cast<const uint32_t*>(&h);
             }
-            const __half2 h = __floats2half2_rn(e0, e1);
-            const float2 hr = __half22float2(h);
-            s0 += hr.x;
-            s1 += hr.y;
-            pw[k] = *reinterpret_cast<const uint32_t*>(&h);
         }
         if (!waited) {
             mbar_wait(wait_bar, wait_parity);
@@ -1805,8 +1819,8 @@ __global__ void __launch_bounds__(ATT64H_THREADS, 2) attention64th_kernel(const 
                 for (int attempt = 0; attempt < 2; ++attempt) {
                     uint64_t* wb = (t > 0 && attempt == 0) ? o_full : nullptr;
                     const uint32_t wp = static_cast<uint32_t>((g - 1) & 1);
-                    const float amax = full_tile ? attn64_write_p_tmem_part<true>(s_addr, tmem_P + lane_base, kvalid, p.scale_log2, -m_used, 2 * hf, tile_sum, wb, wp)
-                                                 : attn64_write_p_tmem_part<false>(s_addr, tmem_P + lane_base, kvalid, p.scale_log2, -m_used, 2 * hf, tile_sum, wb, wp);
+                    const float amax = full_tile ? attn64_write_p_tmem_part<true, PQ == 1>(s_addr, tmem_P + lane_base, kvalid, p.scale_log2, -m_used, 2 * hf, tile_sum, wb, wp)
+                                                 : attn64_write_p_tmem_part<false, PQ == 1>(s_addr, tmem_P + lane_base, kvalid, p.scale_log2, -m_used, 2 * hf, tile_sum, wb, wp);
                     if (warp == 0 && attempt == 0) ATT_TRACE(p, 0, g, 1);
                     if (t == 0 || attempt == 1) break;
                     *mine = amax;

@@ -386,6 +386,7 @@ int launch_attn(const AttnParams& p_in, int d, cudaStream_t st) {
         MMD_CUDA_OK(cudaFuncSetAttribute(attention64_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64Smem::TOTAL));
         MMD_CUDA_OK(cudaFuncSetAttribute(attention64t_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64tSmem::TOTAL));
         MMD_CUDA_OK(cudaFuncSetAttribute(attention64th_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64thSmem::TOTAL));
+        MMD_CUDA_OK(cudaFuncSetAttribute(attention64th_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64thSmem::TOTAL));
         MMD_CUDA_OK(cudaFuncSetAttribute(attention64h_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64hSmem::TOTAL));
         MMD_CUDA_OK(cudaFuncSetAttribute(attention64h_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64hSmem::TOTAL));
         MMD_CUDA_OK(cudaFuncSetAttribute(attention64h_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn64hSmem::TOTAL));
@@ -422,7 +423,10 @@ int launch_attn(const AttnParams& p_in, int d, cudaStream_t st) {
         static const bool ptmem = [] { const char* e = getenv("MMD_ATTN_TMEM"); return !(e && e[0] == '0'); }();
         if (ptmem && poly == 0) {
             static const bool ptmem8 = [] { const char* e = getenv("MMD_ATTN_TMEM"); return !(e && e[0] == '1'); }();
-            if (ptmem8) MMD_CUDA_OK(launch_kernel(attention64th_kernel<0>, g1, ATT64H_THREADS, Attn64thSmem::TOTAL, st, p, grid));
+            // MMD_ATTN_F16X2=1: the exponentials of a pair through one ex2.approx.f16x2
+            static const bool h2 = [] { const char* e = getenv("MMD_ATTN_F16X2"); return e && e[0] == '1'; }();
+            if (ptmem8 && h2) MMD_CUDA_OK(launch_kernel(attention64th_kernel<1>, g1, ATT64H_THREADS, Attn64thSmem::TOTAL, st, p, grid));
+            else if (ptmem8) MMD_CUDA_OK(launch_kernel(attention64th_kernel<0>, g1, ATT64H_THREADS, Attn64thSmem::TOTAL, st, p, grid));
             else MMD_CUDA_OK(launch_kernel(attention64t_kernel<0>, g1, ATT_THREADS, Attn64tSmem::TOTAL, st, p, grid));
             return MMD_OK;
         }
