@@ -148,7 +148,7 @@ MMD_DEVINL void gn_bwd_prologue(const GnBwdArgs& g, int ns, float* coef, float* 
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(GnBwdArgs g) {
+__global__ void __launch_bounds__(256, 2) gn_bwd_reduce_kernel(GnBwdArgs g) {
     extern __shared__ float gsh[];   // coef[4C] | gstat[64] | red[2C]
     const int C = g.s.c1 + g.s.c2;
     float* coef = gsh;
@@ -228,7 +228,7 @@ struct GnBwdOut {
     act_t* dx2; int ld2; int acc2;   // gradient of source 2 (nullable)
 };
 
-__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(GnBwdArgs g, GnBwdOut o) {
+__global__ void __launch_bounds__(256, 2) gn_bwd_apply_kernel(GnBwdArgs g, GnBwdOut o) {
     extern __shared__ float gsh[];   // coef[4C] | gstat[64] | p[C] | qr[64]
     const int C = g.s.c1 + g.s.c2;
     const int cpg = C / 32;
