@@ -50,6 +50,8 @@ struct alignas(64) GemmParams {
     CUtensorMap a_map[GEMM_MAX_SRC];  // activation sources, always rank 5 (unit extents past `rank`), box (64, box[0..3])
     CUtensorMap b_map;                // packed weights [N, K_total] (K-major), box (64, BN)
     CUtensorMap o_map;                // output, same geometry as A (out_mode 0)
+    CUtensorMap o32_map;              // rank-2 outputs: the same tensor with a (64 columns, 32 rows) box: one store per epilogue warp
+    int wstore;                       // 1: every epilogue warp stores its own 32-row band (no cross-warp barrier per chunk)
     int n_src;
     int src_chunks[GEMM_MAX_SRC];     // 64-channel chunks per source
     int rank;                         // tensor-map rank of A/O (2..5)
@@ -125,7 +127,7 @@ struct GemmSmem {
     // XF: per-channel affine table [2 domains][a|b][GEMM_XF_MAXC] floats + group mean / rstd [2][32][2]
     // this tile's bias [BN] floats (epilogue reads it from shared memory: the global loads sat on its critical path)
     static constexpr int BIAS_OFF = 256 + GN_BYTES;
-    static constexpr int BIAS_BYTES = (BN >= 64) ? EG * BN * 4 : 0;
+    static constexpr int BIAS_BYTES = (BN >= 64) ? EG * 2 * BN * 4 : 0;   // per group, double buffered by tile parity
     static constexpr int XF_OFF = BIAS_OFF + BIAS_BYTES;
     static constexpr int XF_BYTES = XF ? (2 * 2 * GEMM_XF_MAXC * 4 + 512) : 0;
     static constexpr int BAR_BYTES = 256 + GN_BYTES + BIAS_BYTES + XF_BYTES;
@@ -492,7 +494,8 @@ __global__ void __launch_bounds__(gemm_threads(EG, XF), 1) conv_gemm_kernel(cons
         const int ebar = 1 + 2 * eg;               // named barrier of this group (2 belongs to the transform warps)
         uint8_t* const out_stage_g = out_stage + eg * 2 * S::OUT_BUF;
         float* const gn_part_g = gn_part + eg * (S::GN_ONE / 4);
-        float* const bias_g = bias_s + eg * BN;
+        float* const bias_g0 = bias_s + eg * 2 * BN;
+        int tcount = 0;   // tiles this group has processed (bias buffer parity)
         int it = 0;
         uint32_t obuf_sel = 0;   // staging buffer rotation (leader's bulk-group order matches it)
         for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++it) {
@@ -513,6 +516,10 @@ __global__ void __launch_bounds__(gemm_threads(EG, XF), 1) conv_gemm_kernel(cons
             int org[5];
             gemm_tile_origin(p, m_idx, org);
             const float* bias = p.bias + n_idx * BN;
+            // the bias row is double buffered by tile parity: with per-warp stores a fast warp may write the next tile's row
+            // while a slow one still converts this tile (the tile's one barrier keeps them within a tile of each other)
+            float* const bias_g = bias_g0 + (tcount & 1) * BN;
+            ++tcount;
             // this tile's bias: requested before the wait for the accumulator so its latency hides behind the mainloop
             float bias_pre[(BN + 127) / 128];
             if constexpr (BN >= 64) {
@@ -531,7 +538,10 @@ __global__ void __launch_bounds__(gemm_threads(EG, XF), 1) conv_gemm_kernel(cons
                 for (int cc = 0; cc < S::NCHUNK; ++cc) {
                     uint8_t* obuf = out_stage_g + (obuf_sel & 1) * S::OUT_BUF;
                     ++obuf_sel;
-                    if (lead_warp) {
+                    // wstore (token-matrix outputs): each warp owns the 32-row band of the staging buffers it converts and stores,
+                    // so a chunk needs no cross-warp barrier at all (one per tile remains, for the shared bias row)
+                    const bool ws = p.wstore != 0;
+                    if (ws || lead_warp) {
                         if (elect_one()) tma_store_wait_read1();  // the store issued two chunks ago has drained this buffer
                         __syncwarp();
                     }
@@ -540,7 +550,7 @@ __global__ void __launch_bounds__(gemm_threads(EG, XF), 1) conv_gemm_kernel(cons
                         for (int i = 0; i < (BN + 127) / 128; ++i)
                             if (et + i * 128 < BN) bias_g[et + i * 128] = bias_pre[i];
                     }
-                    named_bar_sync(ebar, 128);
+                    if (!ws || cc == 0) named_bar_sync(ebar, 128);
                     // accumulator -> fp16 staging, 32 columns at a time with the next TMEM load already in flight
                     uint32_t va[32], vb[32];
                     if (!(GEMM_DBG(p) & 2)) tmem_ld32(t_addr + cc * OC, va);
@@ -574,6 +584,20 @@ __global__ void __launch_bounds__(gemm_threads(EG, XF), 1) conv_gemm_kernel(cons
                         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
                     }
                     fence_proxy_async_smem();
+                    if (ws) {
+                        __syncwarp();
+                        if (!(GEMM_DBG(p) & 1)) {
+                            if (elect_one()) {
+                                const int band_rows = quad * 32;   // the rows this warp converted: its TMEM lane quarter
+#pragma unroll
+                                for (int u = 0; u < S::UNITS; ++u)
+                                    tma_store_5d(&p.o32_map, obuf + u * (GEMM_BM * 128) + band_rows * 128, n_idx * BN + cc * OC + u * 64,
+                                                 org[1] + band_rows, 0, 0, 0);
+                                tma_store_commit();
+                            }
+                            __syncwarp();
+                        }
+                    } else {
                     named_bar_sync(ebar, 128);
                     if (lead_warp && !(GEMM_DBG(p) & 1)) {
                         if (elect_one()) {
@@ -587,11 +611,12 @@ __global__ void __launch_bounds__(gemm_threads(EG, XF), 1) conv_gemm_kernel(cons
                         }
                         __syncwarp();
                     }
+                    }
                     if (p.stats != nullptr && !(GEMM_DBG(p) & 32)) {
                         // Column sums of the staged fp16 chunk without atomics, one 64-column unit at a time: lane & 15 =
                         // 4-column quad (8 bytes of a 128-byte row), the two half-warps take 16 rows each of the warp's
                         // 32-row band; per (band, quad) partials are folded into groups by the write-out pass below.
-                        const int band = et >> 5, quad4 = lane & 15, half = lane >> 4;
+                        const int band = quad, quad4 = lane & 15, half = lane >> 4;   // the warp's own rows (no cross-warp read)
                         const int unit = quad4 >> 1, sub = (quad4 & 1) * 8;
 #pragma unroll 1
                         for (int u = 0; u < S::UNITS; ++u) {
@@ -699,7 +724,7 @@ __global__ void __launch_bounds__(gemm_threads(EG, XF), 1) conv_gemm_kernel(cons
             }
         }
         if constexpr (BN >= 64) {
-            if (lead_warp) {
+            if (lead_warp || p.wstore != 0) {
                 if (elect_one()) tma_store_wait_all0();
                 __syncwarp();
             }

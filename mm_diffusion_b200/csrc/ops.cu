@@ -154,6 +154,15 @@ int build_gemm(const GemmProblem& pr, GemmParams* out) {
             if (used) pitch *= g.dims[i - 1];
         }
         MMD_TRY(encode_tmap(&p.o_map, pr.out, 5, dims, str, box));
+        // token-matrix outputs (rank 2: the 128-token tile is 128 consecutive rows): a second map with 32-row boxes lets every
+        // epilogue warp store its own band without a cross-warp barrier per chunk (MMD_WSTORE=1).  Measured equal to the
+        // single store per chunk (10.73-10.86 vs 10.68-10.72 ms per step), so it is off by default.
+        static const bool wstore_on = [] { const char* e = getenv("MMD_WSTORE"); return e && e[0] == '1'; }();
+        if (g.rank == 2 && g.box[0] == GEMM_BM && wstore_on) {
+            box[1] = 32;
+            MMD_TRY(encode_tmap(&p.o32_map, pr.out, 5, dims, str, box));
+            p.wstore = 1;
+        }
     } else {
         if (!pr.out_f32 || pr.n > 16) return fail(MMD_EINVAL, "narrow conv output needs out_f32 and n <= 16");
         p.out_mode = 1;

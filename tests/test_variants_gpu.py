@@ -18,6 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     ({"MMD_ATTN_PAIR": "0"}, "attention or forward_small or production"),  # ... at none
     ({"MMD_XF": "7"}, "forward_small or forward_production"),           # GroupNorm apply on the GEMM A operand
     ({"MMD_EG": "0", "MMD_MT": "0"}, "conv or forward_small"),          # one epilogue warpgroup, 128-token tiles only
+    ({"MMD_WSTORE": "1"}, "conv or forward_small or production"),       # per-warp output stores for token-matrix GEMMs
     ({"MMD_NO_GRAPH": "1", "MMD_NO_PDL": "1"}, "forward_small"),        # eager launches without programmatic dependent launch
 ])
 def test_variant_passes_the_parity_tests(env, select):
