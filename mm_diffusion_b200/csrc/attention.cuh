@@ -1884,89 +1884,12 @@ __global__ void __launch_bounds__(ATT64H_THREADS, 2) attention64th_kernel(const 
 
 // ===========================================================================
 // attention64x2_kernel — head_dim 64 with TWO 128-row query tiles per CTA sharing every K/V tile.
-// One CTA per SM (512 TMEM columns, ~165 KB shared memory): two softmax groups of four warps each own one query tile
-// (S, P, O, l of its own), one TMA warp, one MMA thread.  While group 0 is in its softmax the tensor core runs group 1's
-// Q·K^T / P·V and vice versa, so the exp unit — the limiter at d = 64 — sees eight softmax warps with independent
-// dependencies instead of two CTAs that each stall on their own MMA round trip, and every K/V tile is fetched once for
-// 256 query rows.  Items whose query block has no second tile (<= 128 rows) run with group 1 idle.
-// Same arithmetic as attention64_kernel (shared row-max / probability helpers): results are bit-identical.
+// One CTA per SM (all 512 TMEM columns: S0 S1 O0 O1 P0 P1; ~100 KB shared memory for Q x 2, K x 2, V x 2): two softmax
+// groups of four warps each own one query tile, one TMA warp, one MMA warp.  While group 0 is in its softmax the tensor
+// core runs group 1's Q·K^T / P·V and vice versa, and every K/V tile is fetched once for 256 query rows.  P lives in tensor
+// memory and the row sums in registers as in attention64t_kernel (shared helpers); within an item the next tile's logits
+// of a group are issued before its P·V.  Items whose query block has no second tile (<= 128 rows) run with group 1 idle.
 // ===========================================================================
-// P·V and P·1 of one 128-key tile into the O / l accumulators of one query tile (single issuing thread).
-MMD_DEVINL void attn64_issue_pv(uint32_t tmem_O, uint32_t tmem_L, uint64_t pd0, uint64_t vd0, uint64_t od0, int kvalid, int t) {
-    constexpr int D = 64;
-    constexpr uint32_t idesc_pv = umma_idesc_f16(ATT_BQ, D, 0, 1);   // V is MN-major
-    constexpr uint32_t idesc_l = umma_idesc_f16(ATT_BQ, 16, 0, 0);   // P x ones^T
-    const int nks = (kvalid + 15) >> 4;
-    if (nks == ATT_BKV / 16) {
-#pragma unroll
-        for (int ks = 0; ks < ATT_BKV / 16; ++ks)
-            umma_f16_ss(tmem_O, pd0 + ((ks >> 2) * (ATT_BQ * 128 >> 4) + (ks & 3) * 2), vd0 + ks * (2048 >> 4), idesc_pv,
-                        (t | ks) != 0 ? 1u : 0u);
-#pragma unroll
-        for (int ks = 0; ks < ATT_BKV / 16; ++ks)
-            umma_f16_ss(tmem_L, pd0 + ((ks >> 2) * (ATT_BQ * 128 >> 4) + (ks & 3) * 2),
-                        od0 + ((ks >> 2) * (2048 >> 4) + (ks & 3) * 2), idesc_l, (t | ks) != 0 ? 1u : 0u);
-    } else {
-        uint64_t pd = pd0, vd = vd0;
-        for (int ks = 0; ks < nks; ++ks) {
-            umma_f16_ss(tmem_O, pd, vd, idesc_pv, (t | ks) != 0 ? 1u : 0u);
-            vd += 2048 >> 4;
-            pd += (ks == 3) ? (ATT_BQ * 128 >> 4) - 6 : 2;
-        }
-        uint64_t od = od0;
-        pd = pd0;
-        for (int ks = 0; ks < nks; ++ks) {
-            umma_f16_ss(tmem_L, pd, od, idesc_l, (t | ks) != 0 ? 1u : 0u);
-            pd += (ks == 3) ? (ATT_BQ * 128 >> 4) - 6 : 2;
-            od += (ks == 3) ? (2048 >> 4) - 6 : 2;
-        }
-    }
-}
-
-
-// Register-resident logit row (128 fp32) of the two-tile kernel: the four TMEM loads are in flight together and the
-// row is read from TMEM once — the separate max / exp passes of attention64_kernel wait for TMEM four times each.
-template <bool FULL>
-MMD_DEVINL float attn64_row_load_max(uint32_t s_addr, int kvalid, uint32_t (&sv)[128]) {
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-        if (FULL || c * 32 < kvalid) tmem_ld32(s_addr + c * 32, &sv[c * 32]);
-    tmem_ld_wait();
-    float mx = -INFINITY;
-#pragma unroll
-    for (int i = 0; i < 128; ++i)
-        if (FULL || i < kvalid) mx = fmaxf(mx, __uint_as_float(sv[i]));
-    return mx;
-}
-template <bool FULL, int PQ>
-MMD_DEVINL void attn64_row_write_p(const uint32_t (&sv)[128], int kvalid, float scale_log2, float nm, uint8_t* p_smem, int row) {
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        if (!FULL && c * 32 >= kvalid) break;
-        uint8_t* chunk = p_smem + (c >> 1) * (ATT_BQ * 128);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            uint4 pk;
-            uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int col = c * 32 + j * 8 + 2 * k;
-                const float a0 = fmaf(__uint_as_float(sv[col]), scale_log2, nm);
-                const float a1 = fmaf(__uint_as_float(sv[col + 1]), scale_log2, nm);
-                float e0 = ex2_fast(a0);
-                float e1 = (PQ == 2 || (PQ == 1 && (k & 1))) ? ex2_poly(a1) : ex2_fast(a1);
-                if (!FULL) {
-                    if (col >= kvalid) e0 = 0.f;
-                    if (col + 1 >= kvalid) e1 = 0.f;
-                }
-                const __half2 h = __floats2half2_rn(e0, e1);
-                pw[k] = *reinterpret_cast<const uint32_t*>(&h);
-            }
-            *reinterpret_cast<uint4*>(chunk + sw128_off(row, (c & 1) * 4 + j)) = pk;
-        }
-    }
-}
-
 struct Attn64x2Smem {
     static constexpr int Q_OFF = 0;                       // two query tiles
     static constexpr int K_OFF = 2 * 16384;               // 2 stages
