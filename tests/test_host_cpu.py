@@ -218,3 +218,34 @@ def test_flat_parameter_storage_keeps_the_module_surface():
     assert all(torch.equal(a, b) and a.data_ptr() != b.data_ptr() for a, b in zip(clone.parameters(), model.parameters()))
     model._handle = None
     lib.mmd_model_destroy(h)
+
+
+def test_bench_clock_sampler_windows_to_the_timed_region():
+    """bench.py starts nvidia-smi before the warm-up (its first sample takes longer than a short timed region) and counts
+    only the samples after mark(); a region without a sample falls back to the nearest one and says so."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(__file__)), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+
+    class _Proc:
+        def terminate(self): pass
+        def wait(self, timeout=None): return 0
+        def kill(self): pass
+
+    line = "0, {sm}, 1965, {pw}, 0x0000000000000004, Not Active, Not Active, Not Active, {cap}"
+    s = bench.ClockSampler(0)
+    s.proc = _Proc()
+    s.lines = [line.format(sm=1200, pw=150.0, cap="Not Active")]          # warm-up sample: must not count
+    s.mark()
+    s.lines += [line.format(sm=1900, pw=600.0, cap="Active"), line.format(sm=1920, pw=610.0, cap="Active")]
+    out = s.stop()
+    assert out["samples"] == 2 and out["sm_mhz"] == 1910.0 and out["sm_max_mhz"] == 1965.0
+    assert out["reasons"] == ["sw_power_cap"] and "note" not in out
+    s2 = bench.ClockSampler(0)
+    s2.proc = _Proc()
+    s2.lines = [line.format(sm=1800, pw=300.0, cap="Not Active")]
+    s2.mark()                                                              # nothing arrives inside the region
+    out2 = s2.stop()
+    assert out2["samples"] == 1 and out2["sm_mhz"] == 1800.0 and "note" in out2
